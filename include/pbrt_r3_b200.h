@@ -1,0 +1,301 @@
+/*
+ * pbrt_r3_b200.h — C ABI of the B200-native PathIntegrator core.
+ *
+ * Drop-in boundary for ONE hot path of ototoi/pbrt-r3: the PathIntegrator
+ * radiance bounce loop.  The reference has no FFI of its own;
+ * the path sits behind
+ *     trait Integrator { fn render(&mut self, scene: &Scene); ... }
+ *         (reference src/core/integrator/integrator.rs:6-9)
+ * selected by   create_integrator("path", ...)
+ *         (reference src/integrators/create_integrator.rs:15-36)
+ * and fed by the ParseContext callbacks of SceneContext
+ *         (reference src/core/api/parse_context.rs:5-66).
+ * A Rust `GpuPathContext: ParseContext` shim records the same
+ * callbacks into the POD arrays below and calls these entry points.
+ *
+ * Conventions: plain pointers + sizes, no C++/torch types.  All input arrays
+ * are owned by the caller and copied during pt_scene_create().  The callee
+ * owns device memory.  Return 0 = ok, non-zero = error (pt_last_error()).
+ * Float is f32 ("float-as-double" is off, reference src/core/base/types.rs:3-6).
+ */
+#ifndef PBRT_R3_B200_H
+#define PBRT_R3_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_ABI_VERSION 1
+
+/* ---- plugin names carried as enums (string names are resolved by the host) ---- */
+enum pt_material_type {       /* reference src/materials/create_material.rs:20-72 */
+  PT_MAT_NONE = -1,           /* Material "" / "none": no BSDF, ray passes through */
+  PT_MAT_MATTE = 0,           /* materials/matte.rs:26-52   */
+  PT_MAT_PLASTIC = 1,         /* materials/plastic.rs:32-70 */
+  PT_MAT_GLASS = 2,           /* materials/glass.rs:47-110  */
+  PT_MAT_METAL = 3,           /* materials/metal.rs:52-84   */
+  PT_MAT_MIRROR = 4           /* materials/mirror.rs:20-41  */
+};
+
+enum pt_light_type {          /* reference src/lights/create_light.rs:13-54 */
+  PT_LIGHT_AREA = 0,          /* lights/diffuse.rs  (one per emissive triangle) */
+  PT_LIGHT_POINT = 1,         /* lights/point.rs    */
+  PT_LIGHT_DISTANT = 2        /* lights/distant.rs  */
+};
+
+enum pt_sampler_type {        /* reference src/samplers/create_sampler.rs:12-33 */
+  PT_SAMPLER_HALTON = 0,      /* samplers/halton.rs */
+  PT_SAMPLER_SOBOL = 1,       /* samplers/sobol.rs  */
+  PT_SAMPLER_RANDOM = 2       /* samplers/random.rs */
+};
+
+enum pt_accel_type {          /* reference src/accelerators/bvh/accel/mod.rs:4-10 */
+  PT_ACCEL_QBVH = 0,          /* "bvh" on x86_64/aarch64: accel/qbvh/qbvh_x86.rs */
+  PT_ACCEL_LBVH = 1           /* "bvh" elsewhere:          accel/lbvh.rs          */
+};
+
+enum pt_split_method {        /* accelerators/bvh/create_bvh_accelerator.rs:13-20 */
+  PT_SPLIT_SAH = 0, PT_SPLIT_MIDDLE = 2, PT_SPLIT_EQUAL = 3
+};
+
+enum pt_light_strategy {      /* core/lightdistrib/create_light_sample_distribution.rs:11-45 */
+  PT_LIGHTS_SPATIAL = 0, PT_LIGHTS_UNIFORM = 1, PT_LIGHTS_POWER = 2
+};
+
+enum pt_spectrum_kind {       /* core/spectrum/mod.rs:16-20 */
+  PT_SPECTRUM_RGB = 0,        /* RGBSpectrum, 3 channels       */
+  PT_SPECTRUM_SAMPLED = 1     /* SampledSpectrum, 60 channels  */
+};
+
+/* triangle flag bits (per triangle; a mesh's flags are replicated on its triangles) */
+#define PT_TRI_REVERSE_ORIENTATION 1u  /* TriangleMesh.reverse_orientation (shapes/triangle.rs:13) */
+#define PT_TRI_SWAPS_HANDEDNESS    2u  /* TriangleMesh.swaps_handedness    (shapes/triangle.rs:14) */
+#define PT_TRI_TWO_SIDED           4u  /* TriangleMesh.two_sided, pbrt-r3 only (shapes/triangle.rs:15) */
+#define PT_TRI_HAS_N               8u  /* mesh has per-vertex normals  */
+#define PT_TRI_HAS_UV             16u  /* mesh has per-vertex uv       */
+
+/* A material after (constant) texture evaluation.  Spectra are indices into
+ * pt_scene_desc.spectra (n_channels floats each). */
+typedef struct pt_material {
+  int32_t type;               /* pt_material_type */
+  int32_t kd;                 /* matte Kd | plastic Kd                     (spectrum index) */
+  int32_t ks;                 /* plastic Ks | glass Kt | metal k           (spectrum index) */
+  int32_t kr;                 /* mirror Kr | glass Kr | metal eta          (spectrum index) */
+  float sigma;                /* matte sigma (degrees)                                      */
+  float uroughness;           /* plastic/metal roughness (also u), glass uroughness         */
+  float vroughness;           /* glass/metal vroughness                                      */
+  float eta;                  /* glass index                                                 */
+  int32_t remap_roughness;    /* bool                                                        */
+} pt_material;
+
+/* A light.  Area lights reference a top-level triangle (its index in tri_*). */
+typedef struct pt_light {
+  int32_t type;               /* pt_light_type */
+  int32_t spectrum;           /* area: Lemit = L*scale | point: I*scale | distant: L*scale (spectrum index) */
+  int32_t tri;                /* area: triangle index; else -1 */
+  int32_t two_sided;          /* area: DiffuseAreaLight.two_sided (lights/diffuse.rs:178) */
+  float v[3];                 /* point: p_light (world) | distant: w_light (world, normalised) */
+  float pad;
+} pt_light;
+
+/* An ObjectInstance: a TransformedPrimitive over object `object`
+ * (core/primitive/transformed_primitive.rs:26-46).  m = instance-to-world, row-major m[4*r+c]. */
+typedef struct pt_instance {
+  int32_t object;             /* index into objects (>= 1; object 0 is the top level) */
+  float m[16];
+  float minv[16];
+} pt_instance;
+
+typedef struct pt_camera {    /* cameras/perspective.rs, core/camera/projective.rs */
+  float raster_to_camera[16]; /* ProjectiveCamera.raster_to_camera.m   (row-major) */
+  float camera_to_world[16];  /* BaseCamera.camera_to_world (static)   (row-major) */
+  float lens_radius;
+  float focal_distance;
+  float shutter_open;
+  float shutter_close;
+} pt_camera;
+
+typedef struct pt_film {      /* core/film/film.rs:64-164 */
+  int32_t full_resolution[2];
+  int32_t cropped_pixel_bounds[4]; /* x0,y0,x1,y1 */
+  int32_t sample_bounds[4];        /* Film::get_sample_bounds (film.rs:166-179): x0,y0,x1,y1 */
+  float filter_radius[2];
+  float filter_table[256];         /* 16x16, film.rs:102-120 */
+  float scale;
+  float max_sample_luminance;
+} pt_film;
+
+typedef struct pt_sampler {
+  int32_t type;               /* pt_sampler_type */
+  int32_t samples_per_pixel;  /* as requested (sobol rounds up to a power of two itself) */
+  int32_t sample_at_pixel_center; /* halton only */
+  int32_t pad;
+} pt_sampler;
+
+typedef struct pt_integrator { /* integrators/path.rs:252-271 */
+  int32_t max_depth;
+  float rr_threshold;
+  int32_t light_strategy;     /* pt_light_strategy */
+  int32_t pad;
+} pt_integrator;
+
+typedef struct pt_accel {     /* accelerators/bvh/create_bvh_accelerator.rs:9-28 */
+  int32_t type;               /* pt_accel_type */
+  int32_t split_method;       /* pt_split_method */
+  int32_t max_prims_in_node;  /* default 4 */
+  int32_t pad;
+} pt_accel;
+
+/* Full flattened scene description (what SceneContext::make_scene/make_integrator hold). */
+typedef struct pt_scene_desc {
+  uint32_t abi_version;       /* PT_ABI_VERSION */
+  uint32_t spectrum_kind;     /* pt_spectrum_kind */
+  uint32_t n_channels;        /* 3 or 60 */
+  uint32_t n_spectra;
+  const float* spectra;       /* n_spectra * n_channels */
+  float xyz_weights[3 * 60];  /* rows X,Y,Z over channels: Spectrum::to_xyz weights (rgb.rs:58-66 / sampled.rs:53-67) */
+  float xyz_scale;            /* 1 for RGB; (700-400)/(CIE_Y_INTEGRAL*60) for sampled */
+
+  /* Triangles of ALL objects, world space for object 0, object space of the
+   * instanced object otherwise.  Degenerate triangles (area <= 1e-16) are
+   * already dropped by the host (shapes/triangle.rs:726). */
+  uint32_t n_tris;
+  const float* tri_p;         /* 9 floats per triangle: p0 p1 p2                        */
+  const float* tri_n;         /* 9 floats per triangle or NULL (PT_TRI_HAS_N)           */
+  const float* tri_uv;        /* 6 floats per triangle or NULL (PT_TRI_HAS_UV)          */
+  const uint32_t* tri_flags;  /* PT_TRI_* bits                                           */
+  const int32_t* tri_material;/* index into materials, or -1 (no material)              */
+  const int32_t* tri_light;   /* index into lights (area light of this triangle) or -1 */
+
+  /* Objects: object k owns primitives prims[obj_first[k] .. obj_first[k+1]) in
+   * definition order.  A primitive is a triangle index (>= 0) or ~instance
+   * index (< 0).  Object 0 is the top-level aggregate (RenderOptions.primitives). */
+  uint32_t n_objects;         /* >= 1 */
+  const uint32_t* obj_first;  /* n_objects + 1 entries */
+  const int32_t* prims;       /* obj_first[n_objects] entries */
+  uint32_t n_instances;
+  const pt_instance* instances;
+
+  uint32_t n_materials;
+  const pt_material* materials;
+  uint32_t n_lights;          /* sampled lights, in Scene.lights order (RenderOptions.lights push order) */
+  uint32_t n_emitters_only;   /* area lights of INSTANCED shapes: they emit when hit but are never sampled
+                                 (scene_context.rs:1296-1299); stored at lights[n_lights ..] */
+  const pt_light* lights;     /* n_lights + n_emitters_only records */
+
+  pt_camera camera;
+  pt_film film;
+  pt_sampler sampler;
+  pt_integrator integrator;
+  pt_accel accel;
+} pt_scene_desc;
+
+/* Render options that are not part of the scene (how the work is executed). */
+typedef struct pt_render_opts {
+  int32_t device;             /* CUDA device ordinal */
+  int32_t shard_index;        /* this process's shard (0 .. shard_count-1) */
+  int32_t shard_count;        /* tile-interleaved sharding over processes/GPUs (1 = whole image) */
+  int32_t tile_size;          /* sharding granule in pixels (default 16 when 0) */
+  int32_t spp_begin;          /* render samples [spp_begin, spp_end) of every pixel; 0,0 = all */
+  int32_t spp_end;
+  int32_t wave_paths;         /* path slots per wave (0 = default) */
+  int32_t collect_counters;   /* 1: count nodes/triangles visited per ray class (slower) */
+} pt_render_opts;
+
+typedef struct pt_stats {
+  uint64_t camera_rays;       /* "Integrator/Camera rays traced"                  (sampler.rs:24) */
+  uint64_t regular_rays;      /* "Intersections/Regular ray intersection tests"   (scene.rs:11)   */
+  uint64_t shadow_rays;       /* "Intersections/Shadow ray intersection tests"    (scene.rs:12)   */
+  uint64_t nodes_visited;     /* QBVH/LBVH nodes fetched (collect_counters)       */
+  uint64_t tris_tested;       /* "Intersections/Ray-triangle intersection tests"  (triangle.rs:7) */
+  uint64_t path_vertices;     /* shaded vertices */
+  uint64_t zero_radiance_samples;
+  uint64_t kernel_launches;   /* CUDA kernels launched by this call */
+  double   device_ms;         /* CUDA-event time of the whole call on the device */
+  double   extend_ms;         /* summed CUDA-event time of the closest-hit kernel (when timed) */
+  double   shadow_ms;
+  double   shade_ms;
+  uint64_t extend_launches;
+  uint64_t extend_rays;       /* rays processed by the closest-hit kernel */
+  uint64_t extend_bytes;      /* algorithmic bytes of those rays: 128*nodes + 48*tris + 48 (collect_counters) */
+} pt_stats;
+
+typedef struct pt_scene pt_scene;
+
+/* ---- life cycle ------------------------------------------------------------------ */
+/* replaces SceneContext::make_scene + make_integrator (scene_context.rs:675-731):
+ * builds the SAH BVH on the host, flattens it to the GPU node layout, uploads. */
+int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out);
+void pt_scene_destroy(pt_scene* scene);
+const char* pt_last_error(void);
+int pt_abi_version(void);
+
+/* replaces Integrator::render (core/integrator/sampler.rs:259-325 + integrators/path.rs:61-241
+ * + Film::write_image film.rs:440-484 up to the RGB float buffer).
+ * out_rgb: host buffer, 3 floats per pixel of film.cropped_pixel_bounds, row-major.
+ * With shard_count > 1 the result is this shard's PARTIAL film; use pt_render_partial +
+ * pt_film_resolve (or the NCCL path in the Python host) to combine. */
+int pt_render(pt_scene* scene, const pt_render_opts* opts, float* out_rgb, pt_stats* stats);
+
+/* Same, but leaves the partial film {X,Y,Z,sum_w} (4 floats per pixel) on the device and
+ * returns the device pointer (mirrors Film.pixels, film.rs:29-32, before write_image). */
+int pt_render_partial(pt_scene* scene, const pt_render_opts* opts, float** dev_film_xyzw, pt_stats* stats);
+/* Film::write_image's arithmetic on a device film buffer (film.rs:447-472): xyz->rgb / sum_w, clamp, scale. */
+int pt_film_resolve(pt_scene* scene, const float* dev_film_xyzw, float* out_rgb_host);
+/* zero the device film (Film::clear, film.rs:404-412) */
+int pt_film_clear(pt_scene* scene);
+
+/* ---- stage entry points (each replaces one function of the path; used by parity tests
+ *      and by the kernel-level bench) ------------------------------------------------- */
+/* Scene::intersect (core/scene/scene.rs:44-48 -> QBVHAccel::intersect qbvh_x86.rs:378-388).
+ * rays: n x {ox,oy,oz,tmax, dx,dy,dz,time} (8 floats, HOST).  Outputs (HOST, may be NULL):
+ * prim[n] = ORIGINAL top-level primitive index hit (triangle index >= 0, instances report the
+ * instanced triangle's global index) or -1; t[n]; bary[3n] = b0,b1,b2. */
+int pt_intersect(pt_scene* scene, const float* rays, uint32_t n, int32_t* prim, float* t, float* bary,
+                 uint64_t* nodes_visited, uint64_t* tris_tested);
+/* Scene::intersect_p (scene.rs:50-54 -> qbvh_x86.rs:390-399): occluded[n] = 0/1 */
+int pt_intersect_p(pt_scene* scene, const float* rays, uint32_t n, uint8_t* occluded);
+/* Device-resident variant for benchmarking the dominant kernel: rays already in HBM
+ * (two float4 arrays o_tmax[n], d_time[n]); hits written to dev_hits (float4 b0,b1,b2,prim bits). */
+int pt_intersect_device(pt_scene* scene, const void* dev_o_tmax, const void* dev_d_time, uint32_t n,
+                        void* dev_hits, int repeat, float* ms_per_launch);
+
+/* Sampler values (samplers/halton.rs:149-162, sobol.rs:168-185, random.rs): for each of n
+ * (pixel x, pixel y, sample number) triples write dims [dim0, dim0+ndims) of the stream. */
+int pt_sampler_values(pt_scene* scene, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n,
+                      uint32_t dim0, uint32_t ndims, float* out);
+/* PerspectiveCamera::generate_ray_differential (cameras/perspective.rs:121-183) on the sample
+ * stream of the scene's sampler: out rays n x 8 floats (o,tmax,d,time), out p_film n x 2. */
+int pt_camera_rays(pt_scene* scene, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n,
+                   float* rays, float* p_film);
+/* PathIntegrator::li for explicit samples (integrators/path.rs:61-241): out n x n_channels radiance. */
+int pt_li(pt_scene* scene, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, float* out_l);
+
+/* BVH export for build parity (accelerators/bvh/build/ *.rs, accel/qbvh/qbvh_x86.rs:93-176):
+ * object k's ordered primitive list and node count.  ordered may be NULL to query sizes. */
+int pt_bvh_info(pt_scene* scene, uint32_t object, uint32_t* n_nodes, uint32_t* n_prims, int32_t* ordered);
+/* copy the reference-layout view of node i of object k: boxes[2][3][4], children[4] (-1 = empty),
+ * axes[3], is_leaf */
+int pt_bvh_node(pt_scene* scene, uint32_t object, uint32_t node, float* boxes24, int64_t* children4,
+                int32_t* axes3, int32_t* is_leaf);
+
+/* SpatialLightDistribution::lookup (core/lightdistrib/spatial.rs:200-261): for n points write the
+ * voxel's cdf-ready per-light func values (n x n_lights). */
+int pt_light_distribution(pt_scene* scene, const float* points, uint32_t n, float* out_func);
+
+/* ---- host front end (the reference's own L5/L6 layers, C++ mirror because rustc is absent) ---- */
+typedef struct pt_host_scene pt_host_scene;
+/* pbrt_parse_file + SceneContext (core/parser/parser.rs:60, scene_context.rs): parse a .pbrt file
+ * (subset: see DESIGN.md) into a scene description.  Overrides < 0 / NULL mean "keep". */
+int pt_parse_file(const char* path, int pixelsamples_override, int spectrum_kind, pt_host_scene** out);
+int pt_parse_string(const char* text, int pixelsamples_override, int spectrum_kind, pt_host_scene** out);
+const pt_scene_desc* pt_host_scene_desc(const pt_host_scene* hs);
+const char* pt_host_scene_filename(const pt_host_scene* hs);   /* Film "filename" */
+void pt_host_scene_destroy(pt_host_scene* hs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBRT_R3_B200_H */

@@ -1,0 +1,365 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see o_math.h header).
+// o_sampling.h — PCG32, low-discrepancy sequences, Halton/Sobol/Random samplers, warping
+// functions, Distribution1D.
+// Follows reference src/core/rng.rs, src/core/lowdiscrepancy/{radical_inverse,primes}.rs,
+// src/core/lowdiscrepancy/sobol/sobol.rs, src/samplers/{halton,sobol,random}.rs,
+// src/core/sampler/{sampler,global_sampler}.rs, src/core/sampling/{sampling,distribution}.rs.
+#pragma once
+#include "o_math.h"
+#include <vector>
+#include <cassert>
+
+namespace orc {
+
+// ---- core/rng.rs:3-66 ------------------------------------------------------------------
+struct RNG {
+  uint64_t state, inc;
+  RNG() : state(0x853c49e6748fea9bULL), inc(0xda3e39cb94b95bdbULL) {}
+  explicit RNG(uint64_t seq) : state(0x853c49e6748fea9bULL), inc(0xda3e39cb94b95bdbULL) { set_sequence(seq); }
+  void set_sequence(uint64_t initseq) {
+    state = 0;
+    inc = (initseq << 1) | 1;
+    uniform_uint32();
+    state += 0x853c49e6748fea9bULL;
+    uniform_uint32();
+  }
+  uint32_t uniform_uint32() {
+    uint64_t oldstate = state;
+    state = oldstate * 0x5851f42d4c957f2dULL + inc;
+    uint32_t xorshifted = (uint32_t)(((oldstate >> 18) ^ oldstate) >> 27);
+    uint32_t rot = (uint32_t)(oldstate >> 59);
+    return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+  }
+  uint32_t uniform_uint32(uint32_t b) {   // uniform_uint32_threshold
+    uint32_t threshold = (~b + 1u) % b;
+    for (;;) {
+      uint32_t r = uniform_uint32();
+      if (r >= threshold) return r % b;
+    }
+  }
+  float uniform_float() {
+    float f = (float)uniform_uint32() * 2.3283064365386963e-10f;
+    return fminf(ONE_MINUS_EPSILON, f);
+  }
+};
+
+// ---- core/lowdiscrepancy/primes.rs: first 1024 primes and their prefix sums -----------------
+struct Tables {
+  std::vector<uint64_t> primes;      // PRIMES[1024]
+  std::vector<uint64_t> prime_sums;  // PRIME_SUMS (prefix sums, [0] = 0)
+  std::vector<uint16_t> perms;       // compute_radical_inverse_permutations with RNG::new()
+  const uint32_t* sobol32 = nullptr; // SOBOL_MATRICES_32 [1024*52]   (data blob)
+  const uint64_t* vdc = nullptr;     // VDC_SOBOL_MATRICES [25][52] ++ VDC_SOBOL_MATRICES_INV [26][52]
+  Tables() {
+    primes.reserve(1024);
+    for (uint64_t n = 2; primes.size() < 1024; n++) {
+      bool is = true;
+      for (uint64_t p : primes) { if (p * p > n) break; if (n % p == 0) { is = false; break; } }
+      if (is) primes.push_back(n);
+    }
+    prime_sums.resize(1024);
+    uint64_t s = 0;
+    for (int i = 0; i < 1024; i++) { prime_sums[i] = s; s += primes[i]; }
+    // radical_inverse.rs:93-109 + sampling.rs:4-15 (shuffle_array, dim = 1)
+    perms.resize(s);
+    RNG rng;
+    size_t off = 0;
+    for (int i = 0; i < 1024; i++) {
+      size_t len = primes[i];
+      for (size_t j = 0; j < len; j++) perms[off + j] = (uint16_t)j;
+      for (size_t j = 0; j < len; j++) {
+        size_t other = j + rng.uniform_uint32((uint32_t)(len - j));
+        std::swap(perms[off + j], perms[off + other]);
+      }
+      off += len;
+    }
+  }
+};
+inline Tables& tables() { static Tables t; return t; }
+
+// ---- core/lowdiscrepancy/radical_inverse.rs -----------------------------------------------------
+inline uint32_t reverse_bits32(uint32_t n) {
+  n = (n << 16) | (n >> 16);
+  n = ((n & 0x00ff00ff) << 8) | ((n & 0xff00ff00) >> 8);
+  n = ((n & 0x0f0f0f0f) << 4) | ((n & 0xf0f0f0f0) >> 4);
+  n = ((n & 0x33333333) << 2) | ((n & 0xcccccccc) >> 2);
+  n = ((n & 0x55555555) << 1) | ((n & 0xaaaaaaaa) >> 1);
+  return n;
+}
+inline uint64_t reverse_bits64(uint64_t n) {
+  uint64_t n0 = reverse_bits32((uint32_t)n);
+  uint64_t n1 = reverse_bits32((uint32_t)(n >> 32));
+  return (n0 << 32) | n1;
+}
+inline Float radical_inverse_specialized(uint64_t base, uint64_t a) {   // :38-50
+  Float inv_base = 1.0f / (Float)base;
+  uint64_t reversed_digits = 0;
+  Float inv_base_n = 1.0f;
+  while (a != 0) {
+    uint64_t next = a / base;
+    uint64_t digit = a - next * base;
+    reversed_digits = reversed_digits * base + digit;
+    inv_base_n *= inv_base;
+    a = next;
+  }
+  return rmin((Float)reversed_digits * inv_base_n, ONE_MINUS_EPSILON);
+}
+inline Float radical_inverse(uint32_t base_index, uint64_t a) {            // :52-58
+  if (base_index == 0) return (Float)reverse_bits64(a) * 5.4210108624275222e-20f;
+  return radical_inverse_specialized(tables().primes[base_index], a);
+}
+inline uint64_t inverse_radical_inverse(uint64_t base, uint64_t inverse, size_t ndigits) {  // :60-69
+  uint64_t index = 0;
+  for (size_t i = 0; i < ndigits; i++) {
+    uint64_t digit = inverse % base;
+    inverse /= base;
+    index = index * base + digit;
+  }
+  return index;
+}
+inline Float scrambled_radical_inverse(uint32_t base_index, uint64_t a, const uint16_t* perm) {  // :71-91
+  uint64_t base = tables().primes[base_index];
+  Float inv_base = 1.0f / (Float)base;
+  uint64_t reverse_digits = 0;
+  Float inv_base_n = 1.0f;
+  while (a != 0) {
+    uint64_t next = a / base;
+    uint64_t digit = a - next * base;
+    reverse_digits = reverse_digits * base + perm[digit];
+    inv_base_n *= inv_base;
+    a = next;
+  }
+  return rmin(inv_base_n * ((Float)reverse_digits + inv_base * (Float)perm[0] / (1.0f - inv_base)), ONE_MINUS_EPSILON);
+}
+
+// ---- core/lowdiscrepancy/sobol/sobol.rs -----------------------------------------------------------
+inline uint64_t sobol_interval_to_index(uint32_t m, uint64_t frame, int32_t px, int32_t py) {  // :5-34
+  if (m == 0) return 0;
+  const uint64_t* vdc = tables().vdc;
+  const uint64_t* vdc_inv = vdc + 25 * 52;
+  uint32_t m2 = m << 1;
+  uint64_t index = frame << (m2 & 63);
+  uint64_t delta = 0;
+  for (int c = 0; frame != 0; c++, frame >>= 1)
+    if (frame & 1) delta ^= vdc[(m - 1) * 52 + c];
+  uint64_t b = ((((uint64_t)(uint32_t)px) << (m & 63)) | (uint64_t)(int64_t)py) ^ delta;
+  for (int c = 0; b != 0; c++, b >>= 1)
+    if (b & 1) index ^= vdc_inv[(m - 1) * 52 + c];
+  return index;
+}
+inline float sobol_sample_float(int64_t a, uint32_t dimension, uint32_t scramble) {       // :41-56
+  const uint32_t* M = tables().sobol32;
+  const size_t LEN = 1024 * 52;
+  uint32_t v = scramble;
+  size_t i = std::min((size_t)dimension * 52, LEN - 1);
+  while (a != 0) {
+    if (a & 1) v ^= M[i];
+    a >>= 1;
+    i += 1;
+    i %= LEN;
+  }
+  float fv = (float)((double)v * 2.3283064365386963e-10);
+  return fminf(fv, ONE_MINUS_EPSILON);
+}
+
+// ---- samplers ---------------------------------------------------------------------------------
+struct SamplerConfig {
+  int type;            // pt_sampler_type
+  int spp;             // effective samples per pixel
+  int sb[4];           // sample bounds x0,y0,x1,y1
+  bool at_center;
+  // halton (samplers/halton.rs:57-101)
+  int base_scales[2], base_exponents[2], sample_stride, mult_inverse[2];
+  // sobol (samplers/sobol.rs:18-31)
+  uint32_t resolution, log2_resolution;
+};
+
+inline uint64_t math_mod(int64_t a, int64_t b) {  // halton.rs:22-29
+  int64_t result = a - (a / b) * b;
+  return result < 0 ? (uint64_t)(result + b) : (uint64_t)result;
+}
+inline void extended_gcd(uint64_t a, uint64_t b, int64_t* x, int64_t* y) {  // halton.rs:31-38
+  if (b == 0) { *x = 1; *y = 0; return; }
+  int64_t d = (int64_t)(a / b);
+  int64_t xp, yp;
+  extended_gcd(b, a % b, &xp, &yp);
+  *x = yp;
+  *y = xp - (d * yp);
+}
+inline uint64_t multiplicative_inverse(int64_t a, int64_t n) {  // halton.rs:40-43
+  int64_t x, y;
+  extended_gcd((uint64_t)a, (uint64_t)n, &x, &y);
+  return math_mod(x, n);
+}
+inline uint32_t round_up_pow2(uint32_t v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; return v + 1; }
+inline uint32_t log2int(uint32_t v) { uint32_t r = 0; while (v >>= 1) r++; return r; }
+
+inline SamplerConfig make_sampler_config(int type, int spp, const int sb[4], bool at_center) {
+  SamplerConfig c{};
+  c.type = type; c.spp = spp; c.at_center = at_center;
+  for (int i = 0; i < 4; i++) c.sb[i] = sb[i];
+  int res[2] = {sb[2] - sb[0], sb[3] - sb[1]};
+  const int BASES[2] = {2, 3};
+  for (int i = 0; i < 2; i++) {
+    int scale = 1, exp = 0;
+    while (scale < std::min(res[i], 128)) { scale *= BASES[i]; exp += 1; }
+    c.base_scales[i] = scale; c.base_exponents[i] = exp;
+  }
+  c.sample_stride = c.base_scales[0] * c.base_scales[1];
+  c.mult_inverse[0] = (int)multiplicative_inverse(c.base_scales[1], c.base_scales[0]);
+  c.mult_inverse[1] = (int)multiplicative_inverse(c.base_scales[0], c.base_scales[1]);
+  if (type == 1) {  // sobol.rs:19-30
+    c.spp = (int)round_up_pow2((uint32_t)spp);
+    c.resolution = round_up_pow2((uint32_t)std::max(res[0], res[1]));
+    c.log2_resolution = log2int(c.resolution);
+  }
+  return c;
+}
+
+// One sampler instance = the state the reference keeps per tile clone.  The Halton pixel-offset
+// cache is implemented with its INTENDED semantics (a pure function of the pixel; SURVEY §5 notes
+// the reference's shared-cache race).
+struct Sampler {
+  const SamplerConfig* cfg;
+  int px, py;           // current_pixel
+  int64_t sample_num;   // current_pixel_sample_index
+  int64_t interval_index;
+  uint32_t dimension;
+  RNG rng;              // random sampler: per-tile stream
+  int64_t halton_offset;
+
+  Sampler(const SamplerConfig* c, uint32_t tile_seed) : cfg(c), px(0), py(0), sample_num(0), interval_index(0), dimension(0), rng((uint64_t)tile_seed), halton_offset(0) {}
+
+  int64_t index_for_sample(int64_t n) const {
+    if (cfg->type == 0) return halton_offset + n * (int64_t)cfg->sample_stride;     // halton.rs:146
+    if (cfg->type == 1) return (int64_t)sobol_interval_to_index(cfg->log2_resolution, (uint64_t)n, px - cfg->sb[0], py - cfg->sb[1]);  // sobol.rs:169-172
+    return 0;
+  }
+  void start_pixel(int x, int y) {
+    px = x; py = y; sample_num = 0; dimension = 0;
+    if (cfg->type == 0) {   // halton.rs:115-147
+      halton_offset = 0;
+      int64_t stride = cfg->sample_stride;
+      if (stride > 1) {
+        uint64_t pm[2] = {math_mod(px, 128), math_mod(py, 128)};
+        const uint64_t BASES[2] = {2, 3};
+        for (int i = 0; i < 2; i++) {
+          uint64_t dim_offset = inverse_radical_inverse(BASES[i], pm[i], (size_t)cfg->base_exponents[i]);
+          int64_t addition = (int64_t)(dim_offset * (uint64_t)(int64_t)((cfg->sample_stride / cfg->base_scales[i]) * cfg->mult_inverse[i]));
+          halton_offset = halton_offset + addition;
+        }
+        halton_offset = halton_offset % stride;
+      }
+    }
+    interval_index = index_for_sample(0);
+  }
+  bool set_sample_number(int64_t n) {
+    sample_num = n; dimension = 0;
+    interval_index = index_for_sample(n);
+    return n < cfg->spp;
+  }
+  bool start_next_sample() { return set_sample_number(sample_num + 1); }
+
+  Float sample_dimension(int64_t index, uint32_t dim) const {
+    if (cfg->type == 0) {   // halton.rs:149-162
+      if (cfg->at_center && (dim == 0 || dim == 1)) return 0.5f;
+      if (dim == 0) return radical_inverse(0, (uint64_t)(index >> cfg->base_exponents[0]));
+      if (dim == 1) return radical_inverse(1, (uint64_t)(index / (int64_t)cfg->base_scales[1]));
+      assert(dim < 1024);
+      return scrambled_radical_inverse(dim, (uint64_t)index, tables().perms.data() + tables().prime_sums[dim]);
+    }
+    // sobol.rs:174-185
+    Float s = sobol_sample_float(index, dim, 0);
+    if (dim == 0 || dim == 1) {
+      int cp = dim == 0 ? px : py;
+      s = s * (Float)cfg->resolution + (Float)cfg->sb[dim];
+      s = rclamp(s - (Float)cp, 0.0f, ONE_MINUS_EPSILON);
+      s = s - truncf(s);
+    }
+    return s;
+  }
+  Float get_1d() {
+    if (cfg->type == 2) return rng.uniform_float();
+    Float x = sample_dimension(interval_index, dimension);
+    dimension += 1;
+    return x;
+  }
+  Vec2 get_2d() {
+    if (cfg->type == 2) { Float a = rng.uniform_float(); Float b = rng.uniform_float(); return Vec2(a, b); }
+    Float x = sample_dimension(interval_index, dimension);
+    Float y = sample_dimension(interval_index, dimension + 1);
+    dimension += 2;
+    return Vec2(x, y);
+  }
+};
+
+// ---- core/sampling/sampling.rs ---------------------------------------------------------------
+inline Vec2 uniform_sample_triangle(Vec2 u) { Float su0 = sqrtf(u.x); return Vec2(1.0f - su0, u.y * su0); }  // :101-104
+inline Vec2 concentric_sample_disk(Vec2 u) {                                                                    // :106-122
+  Vec2 uo = u * 2.0f - Vec2(1.0f, 1.0f);
+  if (uo.x == 0.0f && uo.y == 0.0f) return Vec2(0, 0);
+  if (fabsf(uo.x) > fabsf(uo.y)) {
+    Float r = uo.x;
+    Float theta = PI_OVER_4 * (uo.y / uo.x);
+    return Vec2(r * cosf(theta), r * sinf(theta));
+  } else {
+    Float r = uo.y;
+    Float theta = PI_OVER_2 - PI_OVER_4 * (uo.x / uo.y);
+    return Vec2(r * cosf(theta), r * sinf(theta));
+  }
+}
+inline Vec3 cosine_sample_hemisphere(Vec2 u) {                                                                  // :141-145
+  Vec2 d = concentric_sample_disk(u);
+  Float z = sqrtf(rmax(0.0f, 1.0f - d.x * d.x - d.y * d.y));
+  return Vec3(d.x, d.y, z);
+}
+inline Float power_heuristic(int nf, Float f_pdf, int ng, Float g_pdf) {                                        // :168-172
+  Float f = (Float)nf * f_pdf, g = (Float)ng * g_pdf;
+  return (f * f) / (f * f + g * g);
+}
+
+// ---- core/sampling/distribution.rs:12-106 --------------------------------------------------------
+struct Distribution1D {
+  std::vector<Float> func, cdf;
+  Float func_int, inv_count;
+  Distribution1D() : func_int(0), inv_count(0) {}
+  explicit Distribution1D(const std::vector<Float>& f) : func(f) {
+    size_t n = f.size();
+    cdf.assign(n + 1, 0.0f);
+    for (size_t i = 1; i < n + 1; i++) cdf[i] = cdf[i - 1] + func[i - 1] / (Float)n;
+    func_int = cdf[n];
+    if (func_int == 0.0f) for (size_t i = 1; i < n + 1; i++) cdf[i] = (Float)i / (Float)n;
+    else for (size_t i = 1; i < n + 1; i++) cdf[i] /= func_int;
+    inv_count = 1.0f / (Float)n;
+  }
+  size_t find_interval(Float u) const {   // :13-32
+    size_t first = 0, len = cdf.size();
+    while (len > 0) {
+      size_t half = len >> 1, middle = first + half;
+      if (cdf[middle] <= u) { first = middle + 1; len -= half + 1; }
+      else len = half;
+    }
+    size_t idx = first == 0 ? 0 : first - 1;
+    if (idx > cdf.size() - 2) return cdf.size() - 2;
+    return idx;
+  }
+  // :86-101 ; returns offset, pdf
+  size_t sample_discrete(Float u, Float* pdf) const {
+    size_t offset = find_interval(u);
+    *pdf = func_int > 0.0f ? func[offset] * inv_count / func_int : 0.0f;
+    return offset;
+  }
+  // :64-83 ; returns value, pdf, offset
+  Float sample_continuous(Float u, Float* pdf, size_t* off) const {
+    size_t offset = find_interval(u);
+    Float cdf0 = cdf[offset], cdf1 = cdf[offset + 1];
+    Float du = u - cdf0;
+    Float span = cdf1 - cdf0;
+    if (span > 0.0f) du /= span;
+    *pdf = func_int > 0.0f ? func[offset] / func_int : 0.0f;
+    *off = offset;
+    return ((Float)offset + du) * inv_count;
+  }
+};
+
+}  // namespace orc

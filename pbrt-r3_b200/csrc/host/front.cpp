@@ -1,0 +1,824 @@
+// front.cpp — .pbrt scene front end: directives -> flattened pt_scene_desc.
+//
+// C++ host mirror (rustc is not available) of the reference's L5 layer for the PathIntegrator path:
+//   pbrt_parse_file                src/core/parser/parser.rs:60-88, 137-381
+//   SceneContext (ParseContext)    src/core/api/scene_context/scene_context.rs
+//   create_triangle_mesh_shape     src/shapes/triangle.rs:696-868
+//   create_*_material              src/materials/{matte,plastic,glass,metal,mirror}.rs
+//   create_{diffuse_area,point,distant}_light   src/lights/*.rs
+//   create_film / Film::new        src/core/film/film.rs:64-179, 538-571
+//   create_perspective_camera      src/cameras/perspective.rs:345-394, core/camera/projective.rs:23-53
+//   create_{halton,sobol,random}_sampler, create_path_integrator, create_bvh_accelerator
+// The result is the POD scene description of include/pbrt_r3_b200.h; nothing here touches CUDA.
+#include "../../../include/pbrt_r3_b200.h"
+#include "params.h"
+#include "spectrum_host.h"
+#include "xform.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <memory>
+#include <sstream>
+
+using namespace pth;
+
+void pt_set_error(const std::string& s);  // api_common.cpp
+
+struct pt_host_scene {
+  std::vector<float> spectra;
+  std::vector<float> tri_p, tri_n, tri_uv;
+  std::vector<uint32_t> tri_flags;
+  std::vector<int32_t> tri_material, tri_light;
+  std::vector<std::vector<int32_t>> obj_prims;  // object 0 = top level
+  std::vector<uint32_t> obj_first;
+  std::vector<int32_t> prims;
+  std::vector<pt_instance> instances;
+  std::vector<pt_material> materials;
+  std::vector<pt_light> lights;        // sampled lights (Scene.lights order)
+  std::vector<pt_light> emitters_only; // area lights of instanced shapes (emit when hit, never sampled)
+  pt_scene_desc desc;
+  std::string filename;
+  std::vector<std::string> warnings;
+};
+
+namespace {
+
+struct MaterialInstance {
+  std::string name;  // plugin name ("" = none)
+  ParamSet params;
+};
+
+struct GraphicsState {
+  bool has_material = true;
+  MaterialInstance material{"matte", ParamSet()};  // graphics_state.rs:54-64 default matte
+  std::map<std::string, MaterialInstance> named_materials;
+  std::map<std::string, float> float_textures;            // constant float textures
+  std::map<std::string, std::vector<float>> spec_textures;  // constant spectrum textures (as rgb)
+  std::string area_light_name;
+  ParamSet area_light_params;
+  bool reverse_orientation = false;
+};
+
+struct Builder {
+  pt_host_scene* hs;
+  SpectrumFactory spec;
+  std::vector<Xf> ctm_stack;
+  Xf ctm = Xf::identity();
+  std::map<std::string, Xf> named_cs;
+  std::vector<GraphicsState> gs_stack;
+  GraphicsState gs;
+  bool in_world = false;
+  // render options (render_options.rs:61-88)
+  std::string filter_name = "box", film_name = "image", sampler_name = "halton", accel_name = "bvh",
+              integrator_name = "path", camera_name = "perspective";
+  ParamSet filter_params, film_params, sampler_params, accel_params, integrator_params, camera_params;
+  Xf camera_to_world = Xf::identity();
+  bool have_camera = false;
+  std::map<std::string, int> object_ids;
+  int current_object = 0;  // 0 = top level
+  int pixelsamples_override = -1;
+
+  Builder(pt_host_scene* h, int spectrum_kind) : hs(h), spec(spectrum_kind) { hs->obj_prims.resize(1); }
+
+  void warn(const std::string& w) { hs->warnings.push_back(w); }
+
+  // ---- parameter list --------------------------------------------------------------------
+  ParamSet parse_params(Lexer& lx) {
+    ParamSet ps;
+    while (lx.peek().kind == TK_STRING) {
+      Token decl = lx.next();
+      std::istringstream is(decl.text);
+      std::string a, b;
+      is >> a >> b;
+      std::string type, name;
+      if (b.empty()) {
+        name = a;
+        type = wellknown_type(name);
+      } else {
+        type = a;
+        name = b;
+      }
+      std::vector<Token> vals;
+      Token t = lx.next();
+      if (t.kind == TK_LBRACK) {
+        for (;;) {
+          Token v = lx.next();
+          if (v.kind == TK_RBRACK) break;
+          if (v.kind == TK_EOF) throw ParseError("unterminated parameter list for \"" + decl.text + "\"");
+          vals.push_back(v);
+        }
+      } else if (t.kind == TK_STRING || t.kind == TK_NUMBER || t.kind == TK_IDENT) {
+        vals.push_back(t);
+      } else {
+        throw ParseError("missing value for parameter \"" + decl.text + "\"");
+      }
+      Param p;
+      auto floats = [&]() { for (auto& v : vals) p.f.push_back(parse_f32(v.text)); };
+      if (type == "string") { p.cls = PC_STRING; for (auto& v : vals) p.s.push_back(v.text); }
+      else if (type == "texture") { p.cls = PC_TEXTURE; for (auto& v : vals) p.s.push_back(v.text); }
+      else if (type == "spectrum") {
+        // numeric (lambda, value) pairs are kept as floats under PC_SPECTRUM; file names as strings
+        p.cls = PC_SPECTRUM;
+        for (auto& v : vals) { if (v.kind == TK_NUMBER) p.f.push_back(parse_f32(v.text)); else p.s.push_back(v.text); }
+      }
+      else if (type == "bool") {
+        p.cls = PC_BOOL;
+        for (auto& v : vals) {
+          std::string s = v.text;
+          for (auto& c : s) c = (char)tolower(c);
+          if (s == "true") p.b.push_back(1);
+          else if (s == "false") p.b.push_back(0);
+          else throw ParseError("bad bool '" + v.text + "'");
+        }
+      }
+      else if (type == "integer") { p.cls = PC_INT; for (auto& v : vals) p.i.push_back((int32_t)strtol(v.text.c_str(), nullptr, 10)); }
+      else if (type == "color" || type == "rgb") { p.cls = PC_RGB; floats(); }
+      else if (type == "xyz") { p.cls = PC_XYZ; floats(); }
+      else if (type == "blackbody") { p.cls = PC_BLACKBODY; floats(); }
+      else if (type == "point" || type == "point2" || type == "point3" || type == "point4" || type == "vector" ||
+               type == "vector2" || type == "vector3" || type == "vector4" || type == "normal") { p.cls = PC_POINT; floats(); }
+      else { p.cls = PC_FLOAT; floats(); }
+      ps.set(p.cls, name, p);
+    }
+    return ps;
+  }
+
+  // ---- spectra -----------------------------------------------------------------------------
+  int add_spectrum(const std::vector<float>& c) {
+    size_t nc = spec.n_channels();
+    size_t n = hs->spectra.size() / nc;
+    for (size_t k = 0; k < n; k++)
+      if (memcmp(&hs->spectra[k * nc], c.data(), nc * sizeof(float)) == 0) return (int)k;
+    hs->spectra.insert(hs->spectra.end(), c.begin(), c.end());
+    return (int)n;
+  }
+  // ParamSet::find_one_spectrum / TextureParams::get_spectrum_from (param_set.rs:386-388): rgb -> Reflectance
+  bool spectrum_from(const ParamSet& ps, const std::string& key, std::vector<float>* out) {
+    if (const Param* q = ps.find(PC_RGB, key)) {
+      if (q->f.size() >= 3) { *out = spec.from_rgb(q->f.data(), /*illuminant=*/false); return true; }
+    }
+    if (const Param* q = ps.find(PC_XYZ, key)) {
+      if (q->f.size() >= 3) {
+        float rgb[3];
+        SpectrumFactory::xyz_to_rgb(q->f.data(), rgb);
+        *out = spec.from_rgb(rgb, false);
+        return true;
+      }
+    }
+    if (const Param* q = ps.find(PC_SPECTRUM, key)) {
+      if (q->f.size() >= 2 && q->f.size() % 2 == 0) {
+        std::vector<float> lam, val;
+        for (size_t i = 0; i < q->f.size(); i += 2) { lam.push_back(q->f[i]); val.push_back(q->f[i + 1]); }
+        *out = spec.from_sampled(lam, val);
+        return true;
+      }
+      if (!q->s.empty()) throw ParseError("spectrum files are not supported (\"" + key + "\")");
+    }
+    if (ps.find(PC_BLACKBODY, key)) throw ParseError("blackbody spectra are not supported (\"" + key + "\")");
+    return false;
+  }
+  std::vector<float> one_spectrum(const ParamSet& ps, const std::string& key, float dflt) {
+    std::vector<float> r;
+    if (spectrum_from(ps, key, &r)) return r;
+    return spec.constant(dflt);
+  }
+
+  // ---- TextureParams (texture_params.rs:60-190) for constant textures -------------------------
+  struct TP {
+    const ParamSet* geom;
+    const ParamSet* mat;
+  };
+  static const std::string* tex_name(const TP& tp, const std::string& key) {
+    for (const ParamSet* ps : {tp.geom, tp.mat})
+      if (const Param* q = ps->find(PC_TEXTURE, key))
+        if (!q->s.empty()) return &q->s[0];
+    return nullptr;
+  }
+  std::vector<float> tp_spectrum(const TP& tp, const std::string& key, const std::vector<float>& dflt) {
+    std::vector<float> r;
+    if (const std::string* n = tex_name(tp, key)) {
+      auto it = gs.spec_textures.find(*n);
+      if (it != gs.spec_textures.end()) return it->second;
+      if (spectrum_from(*tp.mat, *n, &r) || spectrum_from(*tp.geom, *n, &r)) return r;
+      return dflt;
+    }
+    if (spectrum_from(*tp.mat, key, &r) || spectrum_from(*tp.geom, key, &r)) return r;  // material params FIRST
+    return dflt;
+  }
+  bool tp_float_or_null(const TP& tp, const std::string& key, float* out) {
+    if (const std::string* n = tex_name(tp, key)) {
+      auto it = gs.float_textures.find(*n);
+      if (it != gs.float_textures.end()) { *out = it->second; return true; }
+      return false;
+    }
+    for (const ParamSet* ps : {tp.geom, tp.mat})
+      if (const Param* q = ps->find(PC_FLOAT, key))
+        if (q->f.size() == 1) { *out = q->f[0]; return true; }
+    return false;
+  }
+  float tp_float(const TP& tp, const std::string& key, float dflt) {
+    float v;
+    return tp_float_or_null(tp, key, &v) ? v : dflt;
+  }
+  static bool tp_bool(const TP& tp, const std::string& key, bool dflt) {
+    for (const ParamSet* ps : {tp.geom, tp.mat})
+      if (const Param* q = ps->find(PC_BOOL, key))
+        if (q->b.size() == 1) return q->b[0] != 0;
+    return dflt;
+  }
+
+  // ---- materials (materials/*.rs create_* + compute_scattering_functions inputs) ---------------
+  int make_material(const std::string& name, const ParamSet& geom, const ParamSet& mat) {
+    TP tp{&geom, &mat};
+    pt_material m;
+    memset(&m, 0, sizeof(m));
+    m.kd = m.ks = m.kr = -1;
+    m.remap_roughness = 1;
+    std::string nm = name;
+    if (nm == "" || nm == "none") return -1;
+    if (nm != "matte" && nm != "plastic" && nm != "glass" && nm != "metal" && nm != "mirror") {
+      // create_material.rs:65-70: unknown names fall back to matte with a warning
+      warn("Unable to create material \"" + nm + "\" on the GPU path; using \"matte\".");
+      nm = "matte";
+    }
+    if (nm == "matte") {
+      m.type = PT_MAT_MATTE;
+      m.kd = add_spectrum(tp_spectrum(tp, "Kd", spec.constant(0.5f)));
+      m.sigma = tp_float(tp, "sigma", 0.0f);
+    } else if (nm == "plastic") {
+      m.type = PT_MAT_PLASTIC;
+      m.kd = add_spectrum(tp_spectrum(tp, "Kd", spec.constant(0.25f)));
+      m.ks = add_spectrum(tp_spectrum(tp, "Ks", spec.constant(0.25f)));
+      m.uroughness = m.vroughness = tp_float(tp, "roughness", 0.1f);
+      m.remap_roughness = tp_bool(tp, "remaproughness", true);
+    } else if (nm == "mirror") {
+      m.type = PT_MAT_MIRROR;
+      m.kr = add_spectrum(tp_spectrum(tp, "Kr", spec.constant(0.9f)));
+    } else if (nm == "glass") {
+      m.type = PT_MAT_GLASS;
+      m.kr = add_spectrum(tp_spectrum(tp, "Kr", spec.constant(1.0f)));
+      m.ks = add_spectrum(tp_spectrum(tp, "Kt", spec.constant(1.0f)));
+      m.uroughness = tp_float(tp, "uroughness", 0.0f);
+      m.vroughness = tp_float(tp, "vroughness", 0.0f);
+      float eta;
+      if (!tp_float_or_null(tp, "eta", &eta) && !tp_float_or_null(tp, "index", &eta)) eta = 1.5f;
+      m.eta = eta;
+      m.remap_roughness = tp_bool(tp, "remaproughness", true);
+    } else {  // metal
+      m.type = PT_MAT_METAL;
+      m.kr = add_spectrum(tp_spectrum(tp, "eta", spec.copper_n()));
+      m.ks = add_spectrum(tp_spectrum(tp, "k", spec.copper_k()));
+      float rough = tp_float(tp, "roughness", 0.01f);
+      float ur, vr;
+      m.uroughness = tp_float_or_null(tp, "uroughness", &ur) ? ur : rough;
+      m.vroughness = tp_float_or_null(tp, "vroughness", &vr) ? vr : rough;
+      m.remap_roughness = tp_bool(tp, "remaproughness", true);
+    }
+    if (tex_name(tp, "bumpmap")) throw ParseError("bump maps are not supported on the GPU path");
+    for (size_t k = 0; k < hs->materials.size(); k++)
+      if (memcmp(&hs->materials[k], &m, sizeof(m)) == 0) return (int)k;
+    hs->materials.push_back(m);
+    return (int)hs->materials.size() - 1;
+  }
+
+  // scene_context.rs:224-267
+  static bool shape_may_set_material_parameters(const ParamSet& ps) {
+    for (auto& kv : ps.p) {
+      const Param& q = kv.second;
+      const std::string name = kv.first.substr(kv.first.find(':') + 1);
+      switch (q.cls) {
+        case PC_TEXTURE: if (name != "alpha" && name != "shadowalpha") return true; break;
+        case PC_FLOAT: if (q.f.size() == 1 && name != "radius") return true; break;
+        case PC_STRING: if (q.s.size() == 1 && name != "filename" && name != "type" && name != "scheme") return true; break;
+        case PC_BOOL: if (q.b.size() == 1) return true; break;
+        case PC_INT: if (q.i.size() == 1) return true; break;
+        case PC_RGB: case PC_XYZ: case PC_BLACKBODY: case PC_SPECTRUM: if (q.len() >= 1) return true; break;
+        case PC_POINT: if (q.f.size() == 3) return true; break;
+      }
+    }
+    return false;
+  }
+  int material_for_shape(const ParamSet& shape_params) {
+    if (!gs.has_material) return -1;
+    static const ParamSet empty;
+    if (shape_may_set_material_parameters(shape_params)) return make_material(gs.material.name, shape_params, gs.material.params);
+    // pbrt_material built it once with (geom = material params, mat = empty) (scene_context.rs:1116-1131)
+    return make_material(gs.material.name, gs.material.params, empty);
+  }
+
+  // ---- shapes (shapes/triangle.rs:696-868) -----------------------------------------------------
+  static bool is_fillable_uv(const std::vector<int32_t>& vi, size_t nverts) {
+    std::vector<size_t> chk(nverts, 0);
+    for (size_t i = 0; i + 2 < vi.size(); i += 3)
+      for (size_t j = 0; j < 3; j++) {
+        size_t v = (size_t)(uint32_t)vi[i + j];
+        if (v >= nverts) return false;
+        if (chk[v] == 0 || chk[v] == j) chk[v] = j;
+        else return false;
+      }
+    return true;
+  }
+
+  void shape(const std::string& name, const ParamSet& ps_in) {
+    if (name != "trianglemesh") throw ParseError("Shape \"" + name + "\" is not supported on the GPU path (triangle meshes only)");
+    ParamSet ps = ps_in;
+    bool is_area = !gs.area_light_name.empty();
+    if (is_area) {  // scene_context.rs:405-421
+      bool two_sided = gs.area_light_params.one_bool("twosided", true);
+      two_sided = ps.one_bool("twosided", two_sided);
+      Param b; b.cls = PC_BOOL; b.b.push_back(two_sided ? 1 : 0);
+      ps.set(PC_BOOL, "twosided", b);
+    }
+    if (ps.find(PC_TEXTURE, "alpha") || ps.find(PC_FLOAT, "alpha") || ps.find(PC_TEXTURE, "shadowalpha") || ps.find(PC_FLOAT, "shadowalpha"))
+      throw ParseError("alpha-masked shapes are not supported on the GPU path");
+    const Param* pi = ps.find(PC_INT, "indices");
+    const Param* pp = ps.find(PC_POINT, "P");
+    if (!pi || !pp || pi->i.empty() || pp->f.empty()) { warn("Invalid mesh"); return; }
+    const std::vector<int32_t>& vi = pi->i;
+    size_t nverts = pp->f.size() / 3;
+    for (int32_t v : vi) if (v < 0 || (size_t)v >= nverts) throw ParseError("trianglemesh index out of range");
+    const Xf& o2w = ctm;
+    std::vector<V3> P(nverts), N;
+    std::vector<float> UV;
+    for (size_t i = 0; i < nverts; i++) P[i] = m_point(o2w.m, v3(pp->f[3 * i], pp->f[3 * i + 1], pp->f[3 * i + 2]));
+    const Param* puv = ps.find(PC_FLOAT, "uv");
+    if (!puv) puv = ps.find(PC_FLOAT, "st");
+    if (puv) {
+      UV.assign(puv->f.begin(), puv->f.begin() + (puv->f.size() / 2) * 2);
+    } else if (is_fillable_uv(vi, nverts)) {
+      const float tri_uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};
+      UV.assign(nverts * 2, 0.0f);
+      for (size_t i = 0; i + 2 < vi.size(); i += 3)
+        for (int j = 0; j < 3; j++) {
+          size_t v = (size_t)vi[i + j];
+          if (UV[2 * v] == 0.0f && UV[2 * v + 1] == 0.0f) { UV[2 * v] = tri_uv[j][0]; UV[2 * v + 1] = tri_uv[j][1]; }
+        }
+    }
+    if (!UV.empty() && UV.size() / 2 < nverts) throw ParseError("trianglemesh: fewer uv values than vertices");
+    if (ps.find(PC_POINT, "S")) warn("trianglemesh \"S\" tangents are ignored on the GPU path");
+    if (const Param* pn = ps.find(PC_POINT, "N")) {
+      size_t nn = pn->f.size() / 3;
+      if (nn < nverts) throw ParseError("trianglemesh: fewer normals than vertices");
+      N.resize(nn);
+      for (size_t i = 0; i < nn; i++) N[i] = m_normal_with_inv(o2w.minv, v3(pn->f[3 * i], pn->f[3 * i + 1], pn->f[3 * i + 2]));
+    }
+    bool two_sided = ps.one_bool("twosided", true);
+    uint32_t flags = 0;
+    if (gs.reverse_orientation) flags |= PT_TRI_REVERSE_ORIENTATION;
+    if (x_swaps_handedness(o2w)) flags |= PT_TRI_SWAPS_HANDEDNESS;
+    if (two_sided) flags |= PT_TRI_TWO_SIDED;
+    if (!N.empty()) flags |= PT_TRI_HAS_N;
+    if (!UV.empty()) flags |= PT_TRI_HAS_UV;
+
+    int mat = material_for_shape(ps_in);
+    int light_spec = -1, light_two_sided = 0;
+    if (is_area) {
+      if (gs.area_light_name != "diffuse" && gs.area_light_name != "area")
+        throw ParseError("AreaLightSource \"" + gs.area_light_name + "\" unknown");
+      std::vector<float> L = one_spectrum(gs.area_light_params, "L", 1.0f);
+      std::vector<float> sc = one_spectrum(gs.area_light_params, "scale", 1.0f);
+      for (size_t k = 0; k < L.size(); k++) L[k] = L[k] * sc[k];
+      light_spec = add_spectrum(L);
+      light_two_sided = gs.area_light_params.one_bool("twosided", false) ? 1 : 0;
+    }
+    bool want_n = !N.empty(), want_uv = !UV.empty();
+    size_t ntri = vi.size() / 3;
+    for (size_t t = 0; t < ntri; t++) {
+      size_t i0 = (size_t)vi[3 * t], i1 = (size_t)vi[3 * t + 1], i2 = (size_t)vi[3 * t + 2];
+      V3 p0 = P[i0], p1 = P[i1], p2 = P[i2];
+      float area = 0.5f * vlen(vcross(p1 - p0, p2 - p0));
+      if (!(area > 1e-16f)) continue;  // triangle.rs:726
+      int32_t tri = (int32_t)hs->tri_flags.size();
+      const V3 pv[3] = {p0, p1, p2};
+      for (int k = 0; k < 3; k++) { hs->tri_p.push_back(pv[k].x); hs->tri_p.push_back(pv[k].y); hs->tri_p.push_back(pv[k].z); }
+      if (want_n || !hs->tri_n.empty()) {
+        hs->tri_n.resize((size_t)tri * 9, 0.0f);
+        const size_t ii[3] = {i0, i1, i2};
+        for (int k = 0; k < 3; k++) {
+          V3 n = want_n ? N[ii[k]] : v3(0, 0, 0);
+          hs->tri_n.push_back(n.x); hs->tri_n.push_back(n.y); hs->tri_n.push_back(n.z);
+        }
+      }
+      if (want_uv || !hs->tri_uv.empty()) {
+        hs->tri_uv.resize((size_t)tri * 6, 0.0f);
+        const size_t ii[3] = {i0, i1, i2};
+        for (int k = 0; k < 3; k++) {
+          hs->tri_uv.push_back(want_uv ? UV[2 * ii[k]] : 0.0f);
+          hs->tri_uv.push_back(want_uv ? UV[2 * ii[k] + 1] : 0.0f);
+        }
+      }
+      hs->tri_flags.push_back(flags);
+      hs->tri_material.push_back(mat);
+      int32_t li = -1;
+      if (is_area) {
+        pt_light l;
+        memset(&l, 0, sizeof(l));
+        l.type = PT_LIGHT_AREA;
+        l.spectrum = light_spec;
+        l.tri = tri;
+        l.two_sided = light_two_sided;
+        if (current_object == 0) {
+          hs->lights.push_back(l);
+          li = (int32_t)hs->lights.size() - 1;
+        } else {  // "Area lights not supported with object instancing": still emits when hit
+          hs->emitters_only.push_back(l);
+          li = -2 - ((int32_t)hs->emitters_only.size() - 1);  // fixed up in finish()
+        }
+      }
+      hs->tri_light.push_back(li);
+      hs->obj_prims[(size_t)current_object].push_back(tri);
+    }
+  }
+
+  // ---- lights (lights/{point,distant}.rs create_*) ---------------------------------------------
+  void light_source(const std::string& name, const ParamSet& ps) {
+    pt_light l;
+    memset(&l, 0, sizeof(l));
+    l.tri = -1;
+    if (name == "point") {
+      std::vector<float> I = one_spectrum(ps, "I", 1.0f), sc = one_spectrum(ps, "scale", 1.0f);
+      for (size_t k = 0; k < I.size(); k++) I[k] = I[k] * sc[k];
+      float from[3] = {0, 0, 0};
+      ps.one_point("from", from);
+      Xf l2w = x_translate(from[0], from[1], from[2]) * ctm;  // order swapped vs v3 (lights/point.rs:121)
+      V3 p = m_point(l2w.m, v3(0, 0, 0));
+      l.type = PT_LIGHT_POINT;
+      l.spectrum = add_spectrum(I);
+      l.v[0] = p.x; l.v[1] = p.y; l.v[2] = p.z;
+    } else if (name == "distant") {
+      std::vector<float> L = one_spectrum(ps, "L", 1.0f), sc = one_spectrum(ps, "scale", 1.0f);
+      for (size_t k = 0; k < L.size(); k++) L[k] = L[k] * sc[k];
+      float from[3] = {0, 0, 0}, to[3] = {0, 0, 1};
+      ps.one_point("from", from);
+      ps.one_point("to", to);
+      V3 dir = v3(from[0], from[1], from[2]) - v3(to[0], to[1], to[2]);
+      V3 w = vnorm(m_vector(ctm.m, dir));
+      l.type = PT_LIGHT_DISTANT;
+      l.spectrum = add_spectrum(L);
+      l.v[0] = w.x; l.v[1] = w.y; l.v[2] = w.z;
+    } else {
+      throw ParseError("LightSource \"" + name + "\" is not supported on the GPU path (point, distant, area lights only)");
+    }
+    hs->lights.push_back(l);
+  }
+
+  // ---- directives -----------------------------------------------------------------------------
+  static void read_floats(Lexer& lx, int n, float* out) {
+    for (int i = 0; i < n; i++) {
+      Token t = lx.next();
+      if (t.kind != TK_NUMBER) throw ParseError("expected a number, got '" + t.text + "'");
+      out[i] = parse_f32(t.text);
+    }
+  }
+  static std::vector<float> read_float_list(Lexer& lx) {
+    std::vector<float> v;
+    Token t = lx.next();
+    if (t.kind != TK_LBRACK) throw ParseError("expected '['");
+    for (;;) {
+      t = lx.next();
+      if (t.kind == TK_RBRACK) break;
+      if (t.kind != TK_NUMBER) throw ParseError("expected a number in list");
+      v.push_back(parse_f32(t.text));
+    }
+    return v;
+  }
+  static std::string read_string(Lexer& lx) {
+    Token t = lx.next();
+    if (t.kind != TK_STRING) throw ParseError("expected a string, got '" + t.text + "'");
+    return t.text;
+  }
+
+  void parse_text(const std::string& text, const std::string& dir) {
+    Lexer lx(text);
+    for (;;) {
+      Token t = lx.next();
+      if (t.kind == TK_EOF) break;
+      if (t.kind != TK_IDENT) throw ParseError("unexpected token '" + t.text + "'");
+      const std::string& d = t.text;
+      if (d == "Identity") ctm = Xf::identity();
+      else if (d == "Translate") { float v[3]; read_floats(lx, 3, v); ctm = ctm * x_translate(v[0], v[1], v[2]); }
+      else if (d == "Scale") { float v[3]; read_floats(lx, 3, v); ctm = ctm * x_scale(v[0], v[1], v[2]); }
+      else if (d == "Rotate") { float v[4]; read_floats(lx, 4, v); ctm = ctm * x_rotate(v[0], v[1], v[2], v[3]); }
+      else if (d == "LookAt") {
+        float v[9]; read_floats(lx, 9, v);
+        Xf t2;
+        if (!x_look_at(v, v + 3, v + 6, &t2)) throw ParseError("LookAt: degenerate up vector");
+        ctm = ctm * t2;
+      }
+      else if (d == "Transform" || d == "ConcatTransform") {
+        std::vector<float> v = read_float_list(lx);
+        if (v.size() != 16) throw ParseError(d + " needs 16 values");
+        M4 m;
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) m.m[4 * r + c] = v[(size_t)(4 * c + r)];  // column-major on disk
+        M4 im;
+        if (!minverse(m, &im)) { warn("Singular matrix in MatrixInvert"); continue; }
+        Xf x{m, im};
+        ctm = (d == "Transform") ? x : ctm * x;
+      }
+      else if (d == "CoordinateSystem") named_cs[read_string(lx)] = ctm;
+      else if (d == "CoordSysTransform") {
+        std::string n = read_string(lx);
+        auto it = named_cs.find(n);
+        if (it != named_cs.end()) ctm = it->second; else warn("Couldn't find named coordinate system \"" + n + "\"");
+      }
+      else if (d == "ActiveTransform") { lx.next(); }
+      else if (d == "TransformTimes") { float v[2]; read_floats(lx, 2, v); }
+      else if (d == "Camera") {
+        camera_name = read_string(lx);
+        camera_params = parse_params(lx);
+        camera_to_world = xinverse(ctm);
+        named_cs["camera"] = camera_to_world;
+        have_camera = true;
+      }
+      else if (d == "Film") { film_name = read_string(lx); film_params = parse_params(lx); }
+      else if (d == "Sampler") { sampler_name = read_string(lx); sampler_params = parse_params(lx); }
+      else if (d == "PixelFilter") { filter_name = read_string(lx); filter_params = parse_params(lx); }
+      else if (d == "Integrator" || d == "SurfaceIntegrator") { integrator_name = read_string(lx); integrator_params = parse_params(lx); }
+      else if (d == "VolumeIntegrator") { read_string(lx); parse_params(lx); }
+      else if (d == "Accelerator") { accel_name = read_string(lx); accel_params = parse_params(lx); }
+      else if (d == "WorldBegin") { in_world = true; ctm = Xf::identity(); named_cs["world"] = ctm; }
+      else if (d == "WorldEnd") { /* nothing */ }
+      else if (d == "AttributeBegin") { gs_stack.push_back(gs); ctm_stack.push_back(ctm); }
+      else if (d == "AttributeEnd") {
+        if (gs_stack.empty()) throw ParseError("Unmatched AttributeEnd");
+        gs = gs_stack.back(); gs_stack.pop_back();
+        ctm = ctm_stack.back(); ctm_stack.pop_back();
+      }
+      else if (d == "TransformBegin") ctm_stack.push_back(ctm);
+      else if (d == "TransformEnd") {
+        if (ctm_stack.empty()) throw ParseError("Unmatched TransformEnd");
+        ctm = ctm_stack.back(); ctm_stack.pop_back();
+      }
+      else if (d == "ReverseOrientation") gs.reverse_orientation = !gs.reverse_orientation;
+      else if (d == "Material") {
+        std::string n = read_string(lx);
+        ParamSet ps = parse_params(lx);
+        if (n == "") gs.has_material = false;
+        else { gs.has_material = true; gs.material = MaterialInstance{n, ps}; }
+      }
+      else if (d == "MakeNamedMaterial") {
+        std::string n = read_string(lx);
+        ParamSet ps = parse_params(lx);
+        std::string type = ps.one_string("type", "");
+        if (type.empty()) warn("No parameter string \"type\" found in MakeNamedMaterial");
+        gs.named_materials[n] = MaterialInstance{type, ps};
+      }
+      else if (d == "NamedMaterial") {
+        std::string n = read_string(lx);
+        auto it = gs.named_materials.find(n);
+        if (it == gs.named_materials.end()) warn("NamedMaterial \"" + n + "\" unknown.");
+        else { gs.has_material = true; gs.material = it->second; }
+      }
+      else if (d == "Texture") {
+        std::string n = read_string(lx), type = read_string(lx), cls = read_string(lx);
+        ParamSet ps = parse_params(lx);
+        if (cls != "constant") throw ParseError("Texture class \"" + cls + "\" is not supported on the GPU path (constant only)");
+        if (type == "float") gs.float_textures[n] = ps.one_float("value", 1.0f);
+        else if (type == "spectrum" || type == "color") gs.spec_textures[n] = one_spectrum(ps, "value", 1.0f);
+        else throw ParseError("Texture type \"" + type + "\" unknown");
+      }
+      else if (d == "LightSource") { std::string n = read_string(lx); ParamSet ps = parse_params(lx); light_source(n, ps); }
+      else if (d == "AreaLightSource") { gs.area_light_name = read_string(lx); gs.area_light_params = parse_params(lx); }
+      else if (d == "Shape") { std::string n = read_string(lx); ParamSet ps = parse_params(lx); shape(n, ps); }
+      else if (d == "ObjectBegin") {
+        std::string n = read_string(lx);
+        gs_stack.push_back(gs); ctm_stack.push_back(ctm);
+        hs->obj_prims.emplace_back();
+        object_ids[n] = (int)hs->obj_prims.size() - 1;
+        current_object = (int)hs->obj_prims.size() - 1;
+      }
+      else if (d == "ObjectEnd") {
+        current_object = 0;
+        if (gs_stack.empty()) throw ParseError("Unmatched ObjectEnd");
+        gs = gs_stack.back(); gs_stack.pop_back();
+        ctm = ctm_stack.back(); ctm_stack.pop_back();
+      }
+      else if (d == "ObjectInstance") {
+        std::string n = read_string(lx);
+        if (current_object != 0) continue;
+        auto it = object_ids.find(n);
+        if (it == object_ids.end()) { warn("ObjectInstance \"" + n + "\" unknown"); continue; }
+        if (hs->obj_prims[(size_t)it->second].empty()) continue;
+        pt_instance inst;
+        inst.object = it->second;
+        memcpy(inst.m, ctm.m.m, sizeof(inst.m));
+        memcpy(inst.minv, ctm.minv.m, sizeof(inst.minv));
+        hs->instances.push_back(inst);
+        hs->obj_prims[0].push_back(~((int32_t)hs->instances.size() - 1));
+      }
+      else if (d == "Include") {
+        std::string n = read_string(lx);
+        std::string path = (n.size() && n[0] == '/') ? n : (dir.empty() ? n : dir + "/" + n);
+        std::ifstream f(path);
+        if (!f) throw ParseError("Include: cannot open \"" + path + "\"");
+        std::stringstream ss;
+        ss << f.rdbuf();
+        size_t slash = path.find_last_of('/');
+        parse_text(ss.str(), slash == std::string::npos ? "" : path.substr(0, slash));
+      }
+      else if (d == "MakeNamedMedium") { read_string(lx); parse_params(lx); }
+      else if (d == "MediumInterface") { read_string(lx); if (lx.peek().kind == TK_STRING) read_string(lx); }
+      else throw ParseError("unknown directive '" + d + "'");
+    }
+  }
+
+  // ---- filters (filters/*.rs) ------------------------------------------------------------------
+  void make_filter(float radius[2], float table[256]) {
+    const ParamSet& ps = filter_params;
+    std::string n = filter_name;
+    float dflt = 2.0f;
+    if (n == "box") dflt = 0.5f; else if (n == "sinc") dflt = 4.0f;
+    else if (n != "gaussian" && n != "mitchell" && n != "triangle") throw ParseError("Filter \"" + n + "\" unknown.");
+    float rx = ps.one_float("xwidth", dflt), ry = ps.one_float("ywidth", dflt);
+    radius[0] = rx; radius[1] = ry;
+    float alpha = ps.one_float("alpha", 2.0f), B = ps.one_float("B", 1.0f / 3.0f), C = ps.one_float("C", 1.0f / 3.0f), tau = ps.one_float("tau", 3.0f);
+    float exp_x = expf(-alpha * rx * rx), exp_y = expf(-alpha * ry * ry);
+    float inv_rx = 1.0f / rx, inv_ry = 1.0f / ry;
+    auto mitchell = [&](float x) {
+      x = fabsf(2.0f * x);
+      if (x > 1.0f) return ((-B - 6.0f * C) * x * x * x + (6.0f * B + 30.0f * C) * x * x + (-12.0f * B - 48.0f * C) * x + (8.0f * B + 24.0f * C)) * (1.0f / 6.0f);
+      return ((12.0f - 9.0f * B - 6.0f * C) * x * x * x + (-18.0f + 12.0f * B + 6.0f * C) * x * x + (6.0f - 2.0f * B)) * (1.0f / 6.0f);
+    };
+    const float PI = 3.14159265358979323846f;
+    auto sinc = [&](float x) { x = fabsf(x); return x < 1e-5f ? 1.0f : sinf(PI * x) / (PI * x); };
+    auto wsinc = [&](float x, float r) { x = fabsf(x); return x > r ? 0.0f : sinc(x) * sinc(x / tau); };
+    for (int y = 0; y < 16; y++)
+      for (int x = 0; x < 16; x++) {  // film.rs:102-120 ("fixed" sampling x*r/15)
+        float xx = (float)x * (rx / 15.0f), yy = (float)y * (ry / 15.0f);
+        float v;
+        if (n == "box") v = 1.0f;
+        else if (n == "gaussian") v = fmaxf(0.0f, expf(-alpha * xx * xx) - exp_x) * fmaxf(0.0f, expf(-alpha * yy * yy) - exp_y);
+        else if (n == "mitchell") v = mitchell(xx * inv_rx) * mitchell(yy * inv_ry);
+        else if (n == "sinc") v = wsinc(xx, rx) * wsinc(yy, ry);
+        else v = fmaxf(0.0f, rx - fabsf(xx)) * fmaxf(0.0f, ry - fabsf(yy));
+        table[y * 16 + x] = v;
+      }
+  }
+
+  // ---- finish: film, camera, sampler, integrator, accelerator ------------------------------------
+  void finish() {
+    pt_scene_desc& D = hs->desc;
+    memset(&D, 0, sizeof(D));
+    D.abi_version = PT_ABI_VERSION;
+    D.spectrum_kind = (uint32_t)spec.kind();
+    D.n_channels = (uint32_t)spec.n_channels();
+    spec.xyz_weights(D.xyz_weights, &D.xyz_scale);
+
+    // Film (film.rs:64-179, 538-571)
+    pt_film& F = D.film;
+    int xres = film_params.one_int("xresolution", 1280), yres = film_params.one_int("yresolution", 720);
+    float crop[4] = {0, 1, 0, 1};
+    if (const Param* q = film_params.find(PC_FLOAT, "cropwindow")) {
+      if (q->f.size() != 4) throw ParseError("\"cropwindow\" expects 4 values");
+      for (int i = 0; i < 4; i++) crop[i] = q->f[(size_t)i];
+    }
+    F.full_resolution[0] = xres; F.full_resolution[1] = yres;
+    // Bounds2f::from(((c0,c2),(c1,c3))): min = (c0,c2), max = (c1,c3)
+    int x0 = std::max(0, (int)floorf((float)xres * crop[0])), y0 = std::max(0, (int)floorf((float)yres * crop[2]));
+    int x1 = std::min((int)ceilf((float)xres * crop[1]), xres), y1 = std::min((int)ceilf((float)yres * crop[3]), yres);
+    F.cropped_pixel_bounds[0] = x0; F.cropped_pixel_bounds[1] = y0; F.cropped_pixel_bounds[2] = x1; F.cropped_pixel_bounds[3] = y1;
+    make_filter(F.filter_radius, F.filter_table);
+    F.sample_bounds[0] = (int)floorf((float)x0 - F.filter_radius[0]);
+    F.sample_bounds[1] = (int)floorf((float)y0 - F.filter_radius[1]);
+    F.sample_bounds[2] = (int)ceilf((float)x1 + F.filter_radius[0]);
+    F.sample_bounds[3] = (int)ceilf((float)y1 + F.filter_radius[1]);
+    F.scale = film_params.one_float("scale", 1.0f);
+    F.max_sample_luminance = film_params.one_float("maxsampleluminance", std::numeric_limits<float>::infinity());
+    hs->filename = film_params.one_string("filename", "pbrt.exr");
+
+    // Camera (perspective.rs:345-394, projective.rs:23-53)
+    if (camera_name != "perspective") throw ParseError("Camera \"" + camera_name + "\" is not supported on the GPU path (perspective only)");
+    pt_camera& Cm = D.camera;
+    float so = camera_params.one_float("shutteropen", 0.0f), sc = camera_params.one_float("shutterclose", 1.0f);
+    if (sc < so) std::swap(so, sc);
+    float aspect = (float)xres / (float)yres;
+    Cm.lens_radius = camera_params.one_float("lensradius", 0.0f);
+    Cm.focal_distance = camera_params.one_float("focaldistance", 1e6f);
+    Cm.shutter_open = so; Cm.shutter_close = sc;
+    float frame = camera_params.one_float("frameaspectratio", aspect);
+    float sw[4];  // min.x, max.x, min.y, max.y
+    if (const Param* q = camera_params.find(PC_FLOAT, "screenwindow")) {
+      if (q->f.size() < 4) throw ParseError("\"screenwindow\" should have four values");
+      sw[0] = q->f[0]; sw[1] = q->f[1]; sw[2] = q->f[2]; sw[3] = q->f[3];
+    } else if (frame > 1.0f) { sw[0] = -frame; sw[1] = frame; sw[2] = -1.0f; sw[3] = 1.0f; }
+    else { sw[0] = -1.0f; sw[1] = 1.0f; sw[2] = -1.0f / frame; sw[3] = 1.0f / frame; }
+    float fov = camera_params.one_float("fov", 90.0f);
+    float halffov = camera_params.one_float("halffov", -1.0f);
+    if (halffov > 0.0f) fov = 2.0f * halffov;
+    Xf camera_to_screen = x_perspective(fov, 1e-2f, 1000.0f);
+    Xf screen_to_raster = x_scale((float)xres, (float)yres, 1.0f) * x_scale(1.0f / (sw[1] - sw[0]), 1.0f / (sw[2] - sw[3]), 1.0f) *
+                          x_translate(-sw[0], -sw[3], 0.0f);
+    Xf raster_to_camera = xinverse(camera_to_screen) * xinverse(screen_to_raster);
+    memcpy(Cm.raster_to_camera, raster_to_camera.m.m, sizeof(Cm.raster_to_camera));
+    memcpy(Cm.camera_to_world, camera_to_world.m.m, sizeof(Cm.camera_to_world));
+
+    // Sampler (samplers/*.rs create_*)
+    pt_sampler& S = D.sampler;
+    if (sampler_name == "halton") { S.type = PT_SAMPLER_HALTON; S.samples_per_pixel = sampler_params.one_int("pixelsamples", 16); }
+    else if (sampler_name == "sobol") { S.type = PT_SAMPLER_SOBOL; S.samples_per_pixel = sampler_params.one_int("pixelsamples", 16); }
+    else if (sampler_name == "random") { S.type = PT_SAMPLER_RANDOM; S.samples_per_pixel = sampler_params.one_int("pixelsamples", 4); }
+    else throw ParseError("Sampler \"" + sampler_name + "\" is not supported on the GPU path (halton, sobol, random)");
+    S.sample_at_pixel_center = sampler_params.one_bool("samplepixelcenter", false) ? 1 : 0;
+    if (pixelsamples_override > 0) S.samples_per_pixel = pixelsamples_override;
+
+    // Integrator (integrators/path.rs:252-271)
+    if (integrator_name != "path") throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path only)");
+    pt_integrator& I = D.integrator;
+    I.max_depth = integrator_params.one_int("maxdepth", 5);
+    I.rr_threshold = integrator_params.one_float("rrthreshold", 1.0f);
+    std::string ls = integrator_params.one_string("lightsamplestrategy", "spatial");
+    I.light_strategy = ls == "uniform" ? PT_LIGHTS_UNIFORM : (ls == "power" ? PT_LIGHTS_POWER : PT_LIGHTS_SPATIAL);
+
+    // Accelerator (create_bvh_accelerator.rs:9-28; accel/mod.rs:4-10)
+    pt_accel& A = D.accel;
+    if (accel_name != "bvh") throw ParseError("Accelerator \"" + accel_name + "\" is not supported on the GPU path (bvh only)");
+    std::string layout = accel_params.one_string("layout", "qbvh");  // GPU-path extension: "lbvh" selects accel/lbvh.rs
+    A.type = layout == "lbvh" ? PT_ACCEL_LBVH : PT_ACCEL_QBVH;
+    std::string split = accel_params.one_string("splitmethod", "sah");
+    if (split == "hlbvh") throw ParseError("splitmethod \"hlbvh\" is not supported on the GPU path");
+    A.split_method = split == "middle" ? PT_SPLIT_MIDDLE : (split == "equal" ? PT_SPLIT_EQUAL : PT_SPLIT_SAH);
+    A.max_prims_in_node = accel_params.one_int("maxnodeprims", 4);
+
+    // emitters-only fix-up: they live after the sampled lights
+    for (auto& li : hs->tri_light)
+      if (li <= -2) li = (int32_t)hs->lights.size() + (-2 - li);
+    std::vector<pt_light>& all = hs->lights;
+    size_t n_sampled = all.size();
+    all.insert(all.end(), hs->emitters_only.begin(), hs->emitters_only.end());
+
+    // objects
+    hs->obj_first.clear();
+    hs->prims.clear();
+    for (auto& v : hs->obj_prims) {
+      hs->obj_first.push_back((uint32_t)hs->prims.size());
+      hs->prims.insert(hs->prims.end(), v.begin(), v.end());
+    }
+    hs->obj_first.push_back((uint32_t)hs->prims.size());
+
+    D.n_spectra = (uint32_t)(hs->spectra.size() / spec.n_channels());
+    D.spectra = hs->spectra.data();
+    D.n_tris = (uint32_t)hs->tri_flags.size();
+    D.tri_p = hs->tri_p.data();
+    if (!hs->tri_n.empty()) { hs->tri_n.resize((size_t)D.n_tris * 9, 0.0f); D.tri_n = hs->tri_n.data(); }
+    if (!hs->tri_uv.empty()) { hs->tri_uv.resize((size_t)D.n_tris * 6, 0.0f); D.tri_uv = hs->tri_uv.data(); }
+    D.tri_flags = hs->tri_flags.data();
+    D.tri_material = hs->tri_material.data();
+    D.tri_light = hs->tri_light.data();
+    D.n_objects = (uint32_t)hs->obj_prims.size();
+    D.obj_first = hs->obj_first.data();
+    D.prims = hs->prims.data();
+    D.n_instances = (uint32_t)hs->instances.size();
+    D.instances = hs->instances.data();
+    D.n_materials = (uint32_t)hs->materials.size();
+    D.materials = hs->materials.data();
+    D.n_lights = (uint32_t)n_sampled;
+    D.n_emitters_only = (uint32_t)hs->emitters_only.size();
+    D.lights = all.data();
+  }
+};
+
+int parse_common(const std::string& text, const std::string& dir, int pixelsamples_override, int spectrum_kind, pt_host_scene** out) {
+  *out = nullptr;
+  std::unique_ptr<pt_host_scene> hs(new pt_host_scene());
+  try {
+    Builder b(hs.get(), spectrum_kind);
+    b.pixelsamples_override = pixelsamples_override;
+    b.parse_text(text, dir);
+    if (!b.have_camera) b.camera_to_world = Xf::identity();
+    b.finish();
+  } catch (const std::exception& e) {
+    pt_set_error(std::string("parse: ") + e.what());
+    return 1;
+  }
+  *out = hs.release();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pt_parse_string(const char* text, int pixelsamples_override, int spectrum_kind, pt_host_scene** out) {
+  if (!text || !out) { pt_set_error("pt_parse_string: null argument"); return 1; }
+  return parse_common(text, "", pixelsamples_override, spectrum_kind, out);
+}
+
+int pt_parse_file(const char* path, int pixelsamples_override, int spectrum_kind, pt_host_scene** out) {
+  if (!path || !out) { pt_set_error("pt_parse_file: null argument"); return 1; }
+  std::ifstream f(path);
+  if (!f) { pt_set_error(std::string("pt_parse_file: cannot open ") + path); return 1; }
+  std::stringstream ss;
+  ss << f.rdbuf();
+  std::string p(path);
+  size_t slash = p.find_last_of('/');
+  return parse_common(ss.str(), slash == std::string::npos ? "" : p.substr(0, slash), pixelsamples_override, spectrum_kind, out);
+}
+
+const pt_scene_desc* pt_host_scene_desc(const pt_host_scene* hs) { return hs ? &hs->desc : nullptr; }
+const char* pt_host_scene_filename(const pt_host_scene* hs) { return hs ? hs->filename.c_str() : ""; }
+void pt_host_scene_destroy(pt_host_scene* hs) { delete hs; }
+
+}  // extern "C"
