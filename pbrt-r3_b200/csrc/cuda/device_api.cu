@@ -1,0 +1,950 @@
+// device_api.cu — the CUDA half of the C ABI (include/pbrt_r3_b200.h): scene upload, the wavefront render loop,
+// stage entry points.  Replaces SceneContext::make_scene/make_integrator (scene_context.rs:675-731), QBVHAccel::new
+// (qbvh_x86.rs:352-371), Integrator::render (core/integrator/sampler.rs:259-325) and Film::write_image (film.rs:440-472).
+// There is no CPU fallback: every entry point fails with an error when CUDA is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../host/bvh_build.h"
+#include "../host/spectrum_host.h"
+#include "kernels.cuh"
+
+using namespace ptd;
+
+void pt_set_error(const std::string& s);
+
+#define CK(call)                                                                                             \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess) {                                                                                 \
+      pt_set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+      return 1;                                                                                              \
+    }                                                                                                        \
+  } while (0)
+
+namespace {
+
+struct DevBufs {
+  std::vector<void*> ptrs;
+  ~DevBufs() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T>
+  cudaError_t upload(const T* host, size_t n, const T** out) {
+    *out = nullptr;
+    if (n == 0) return cudaSuccess;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(d);
+    e = cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T*)d;
+    return e;
+  }
+  template <typename T>
+  cudaError_t alloc(size_t n, T** out) {
+    *out = nullptr;
+    if (n == 0) return cudaSuccess;
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(d);
+    *out = (T*)d;
+    return cudaSuccess;
+  }
+};
+
+struct ObjectHost {
+  pth::BvhResult bvh;
+  std::vector<int32_t> ordered;  // primitive ids (triangle >= 0, ~instance < 0) in leaf order
+  bool single = false;
+  pth::BBox bounds;
+};
+
+}  // namespace
+
+struct pt_scene {
+  int device = 0;
+  int n_sm = 148;
+  DScene h;            // host copy (device pointers inside)
+  DScene* d = nullptr;
+  DevBufs bufs;        // scene-lifetime buffers
+  std::vector<ObjectHost> objects;
+  uint32_t max_stack = 0;
+  cudaStream_t stream = nullptr;
+  // film + wave state
+  f4* film = nullptr;
+  float* rgb_dev = nullptr;
+  uint32_t film_pixels = 0;
+  std::unique_ptr<DevBufs> wave_bufs;
+  WaveState W;
+  Queues Q;
+  int* slot_of = nullptr;
+  unsigned long long* counters = nullptr;  // [0] nodes [1] tris [2] vertices
+  int* overflow = nullptr;
+  uint32_t wave_cap = 0;
+  // pixel list cache
+  int* pixlist = nullptr;
+  uint32_t pix_n = 0;
+  int pix_key[3] = {-1, -1, -1};
+  std::vector<int> pix_host;
+  std::unique_ptr<DevBufs> pix_bufs;
+  ~pt_scene() {
+    if (stream) cudaStreamDestroy(stream);
+    if (d) cudaFree(d);
+  }
+};
+
+namespace {
+
+inline float fmin_(float a, float b) { return fminf(a, b); }
+inline float fmax_(float a, float b) { return fmaxf(a, b); }
+
+// Triangle::world_bound (triangle.rs:214-224)
+pth::BBox tri_bbox(const float* p) {
+  pth::BBox b;
+  for (int a = 0; a < 3; a++) {
+    float mn = p[a], mx = p[a];
+    mn = fmin_(mn, p[3 + a]); mx = fmax_(mx, p[3 + a]);
+    mn = fmin_(mn, p[6 + a]); mx = fmax_(mx, p[6 + a]);
+    b.mn[a] = mn <= mx ? mn : mx;
+    b.mx[a] = mn >= mx ? mn : mx;
+  }
+  return b;
+}
+// Transform::transform_bounds (transform.rs:134-181)
+pth::BBox xform_bbox(const float* m, const pth::BBox& b) {
+  pth::BBox r;
+  bool first = true;
+  for (int ix = 0; ix < 2; ix++)
+    for (int iy = 0; iy < 2; iy++)
+      for (int iz = 0; iz < 2; iz++) {
+        f3 q = mat_point(m, mk3(ix ? b.mx[0] : b.mn[0], iy ? b.mx[1] : b.mn[1], iz ? b.mx[2] : b.mn[2]));
+        const float v[3] = {q.x, q.y, q.z};
+        for (int a = 0; a < 3; a++) {
+          if (first) { r.mn[a] = v[a]; r.mx[a] = v[a]; }
+          else { r.mn[a] = fmin_(r.mn[a], v[a]); r.mx[a] = fmax_(r.mx[a], v[a]); }
+        }
+        first = false;
+      }
+  return r;
+}
+
+// core/rng.rs PCG32 with the default state: compute_radical_inverse_permutations (radical_inverse.rs:93-109)
+struct Pcg {
+  uint64_t state = 0x853c49e6748fea9bULL, inc = 0xda3e39cb94b95bdbULL;
+  uint32_t next() {
+    uint64_t old = state;
+    state = old * 0x5851f42d4c957f2dULL + inc;
+    uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
+    uint32_t rot = (uint32_t)(old >> 59);
+    return (xs >> rot) | (xs << ((~rot + 1u) & 31));
+  }
+  uint32_t bounded(uint32_t b) {
+    uint32_t threshold = (~b + 1u) % b;
+    for (;;) {
+      uint32_t r = next();
+      if (r >= threshold) return r % b;
+    }
+  }
+};
+
+float roughness_to_alpha(float roughness) {  // trowbridge_reitz.rs:113-121 (host libm ln, like the reference)
+  roughness = fmaxf(roughness, 1e-3f);
+  float x = logf(roughness);
+  return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+uint32_t round_up_pow2(uint32_t v) { v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; return v + 1; }
+uint32_t log2int(uint32_t v) { uint32_t r = 0; while (v >>= 1) r++; return r; }
+uint64_t math_mod_h(int64_t a, int64_t b) { int64_t r = a - (a / b) * b; return r < 0 ? (uint64_t)(r + b) : (uint64_t)r; }
+void ext_gcd(uint64_t a, uint64_t b, int64_t* x, int64_t* y) {
+  if (b == 0) { *x = 1; *y = 0; return; }
+  int64_t d = (int64_t)(a / b), xp, yp;
+  ext_gcd(b, a % b, &xp, &yp);
+  *x = yp;
+  *y = xp - (d * yp);
+}
+uint64_t mult_inverse(int64_t a, int64_t n) { int64_t x, y; ext_gcd((uint64_t)a, (uint64_t)n, &x, &y); return math_mod_h(x, n); }
+
+int grid_for(const pt_scene* s, size_t n, int block, int per_sm) {
+  size_t need = (n + (size_t)block - 1) / (size_t)block;
+  size_t cap = (size_t)s->n_sm * (size_t)per_sm;
+  size_t g = std::min(need, cap);
+  return (int)std::max<size_t>(g, 1);
+}
+
+template <int NC>
+int precompute_light_distribution(pt_scene* s, uint32_t n_vox, float* func, float* cdf, float* func_int) {
+  size_t total = (size_t)n_vox * s->h.n_lights;
+  k_voxel_contrib<NC><<<grid_for(s, total, 128, 16), 128, 0, s->stream>>>(s->d, func, n_vox);
+  CK(cudaGetLastError());
+  k_voxel_cdf<<<grid_for(s, n_vox, 128, 16), 128, 0, s->stream>>>(s->h.n_lights, n_vox, func, cdf, func_int);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int build_scene(pt_scene* s, const pt_scene_desc* D) {
+  DScene& H = s->h;
+  memset(&H, 0, sizeof(H));
+  const uint32_t NC = D->n_channels;
+  H.n_channels = NC;
+  H.n_tris = D->n_tris;
+  H.n_lights = D->n_lights;
+  H.n_materials = D->n_materials;
+  H.n_objects = D->n_objects;
+  H.n_instances = D->n_instances;
+  H.has_instances = D->n_instances > 0 ? 1 : 0;
+  memcpy(H.xyz_w, D->xyz_weights, sizeof(H.xyz_w));
+  H.xyz_scale = D->xyz_scale;
+  H.camera = D->camera;
+  H.film = D->film;
+  H.integrator = D->integrator;
+
+  // ---- accelerators: instanced objects first, then the top level ------------------------------------------
+  s->objects.resize(D->n_objects);
+  for (uint32_t k = D->n_objects; k-- > 0;) {
+    ObjectHost& O = s->objects[k];
+    const int32_t* pr = D->prims + D->obj_first[k];
+    size_t n = D->obj_first[k + 1] - D->obj_first[k];
+    std::vector<pth::BBox> pb(n);
+    for (size_t i = 0; i < n; i++) {
+      if (pr[i] >= 0) pb[i] = tri_bbox(D->tri_p + (size_t)pr[i] * 9);
+      else {
+        const pt_instance& I = D->instances[~pr[i]];
+        if (I.object <= 0 || (uint32_t)I.object >= D->n_objects || (uint32_t)I.object <= k) { pt_set_error("bad instance object index"); return 1; }
+        pb[i] = xform_bbox(I.m, s->objects[(size_t)I.object].bounds);
+      }
+    }
+    if (n == 0) {
+      for (int a = 0; a < 3; a++) { O.bounds.mn[a] = FLT_MAX; O.bounds.mx[a] = -FLT_MAX; }
+    } else if (k != 0 && n == 1) {
+      O.single = true;
+      O.bounds = pb[0];
+      O.ordered.assign(pr, pr + 1);
+    } else {
+      pth::build_bvh(pb, D->accel.max_prims_in_node, D->accel.split_method, &O.bvh);
+      O.bounds = O.bvh.bounds;
+      O.ordered.resize(n);
+      for (size_t i = 0; i < n; i++) O.ordered[i] = pr[O.bvh.ordered[i]];
+      s->max_stack = std::max(s->max_stack, 3u * O.bvh.qdepth + 2u);
+    }
+  }
+  {
+    uint32_t top = 3u * s->objects[0].bvh.qdepth + 2u, nested = 0;
+    for (uint32_t k = 1; k < D->n_objects; k++) nested = std::max(nested, 3u * s->objects[k].bvh.qdepth + 3u);
+    if (top + nested > PT_MAX_STACK) {
+      pt_set_error("BVH too deep for the traversal stack (" + std::to_string(top + nested) + " > " + std::to_string(PT_MAX_STACK) + ")");
+      return 1;
+    }
+  }
+  std::vector<pth::GpuNodeH> nodes;
+  std::vector<f4> recs;
+  std::vector<ObjectRec> orecs(D->n_objects);
+  for (uint32_t k = 0; k < D->n_objects; k++) {
+    ObjectHost& O = s->objects[k];
+    ObjectRec& R = orecs[k];
+    memset(&R, 0, sizeof(R));
+    R.node_base = (uint32_t)nodes.size();
+    R.rec_base = (uint32_t)(recs.size() / 3);
+    R.n_nodes = (uint32_t)O.bvh.nodes.size();
+    R.n_prims = (uint32_t)O.ordered.size();
+    R.single = O.single ? 1 : 0;
+    for (int a = 0; a < 3; a++) { R.bmin[a] = O.bounds.mn[a]; R.bmax[a] = O.bounds.mx[a]; }
+    nodes.insert(nodes.end(), O.bvh.nodes.begin(), O.bvh.nodes.end());
+    for (int32_t p : O.ordered) {
+      if (p >= 0) {
+        const float* q = D->tri_p + (size_t)p * 9;
+        recs.push_back(mk4(q[0], q[1], q[2], bitsf((uint32_t)p)));
+        recs.push_back(mk4(q[3], q[4], q[5], bitsf(D->tri_flags[p] & 0xffu)));
+        recs.push_back(mk4(q[6], q[7], q[8], 0.0f));
+      } else {
+        recs.push_back(mk4(0, 0, 0, bitsf((uint32_t)~p)));
+        recs.push_back(mk4(0, 0, 0, bitsf(PT_REC_INSTANCE)));
+        recs.push_back(mk4(0, 0, 0, 0));
+      }
+    }
+  }
+  CK(s->bufs.upload((const QNode*)nodes.data(), nodes.size(), &H.nodes));
+  CK(s->bufs.upload(recs.data(), recs.size(), &H.recs));
+  CK(s->bufs.upload(orecs.data(), orecs.size(), &H.objects));
+  {
+    std::vector<InstanceRec> ir(D->n_instances);
+    for (uint32_t i = 0; i < D->n_instances; i++) {
+      memset(&ir[i], 0, sizeof(InstanceRec));
+      memcpy(ir[i].m, D->instances[i].m, sizeof(ir[i].m));
+      memcpy(ir[i].minv, D->instances[i].minv, sizeof(ir[i].minv));
+      ir[i].object = D->instances[i].object;
+    }
+    CK(s->bufs.upload(ir.data(), ir.size(), &H.instances));
+  }
+  {
+    std::vector<f4> tv((size_t)D->n_tris * 3);
+    for (size_t t = 0; t < D->n_tris; t++)
+      for (int v = 0; v < 3; v++) tv[t * 3 + v] = mk4(D->tri_p[t * 9 + v * 3], D->tri_p[t * 9 + v * 3 + 1], D->tri_p[t * 9 + v * 3 + 2], 0.0f);
+    CK(s->bufs.upload(tv.data(), tv.size(), &H.tri_v));
+  }
+  if (D->tri_n) CK(s->bufs.upload(D->tri_n, (size_t)D->n_tris * 9, &H.tri_n));
+  if (D->tri_uv) CK(s->bufs.upload(D->tri_uv, (size_t)D->n_tris * 6, &H.tri_uv));
+  CK(s->bufs.upload(D->tri_flags, D->n_tris, &H.tri_flags));
+  CK(s->bufs.upload(D->tri_material, D->n_tris, &H.tri_material));
+  CK(s->bufs.upload(D->tri_light, D->n_tris, &H.tri_light));
+
+  // ---- materials: clamp_zero'd spectra become extra pool entries; roughness -> alpha on the host ---------------
+  std::vector<float> spectra(D->spectra, D->spectra + (size_t)D->n_spectra * NC);
+  std::vector<pt_material> mats(D->materials, D->materials + D->n_materials);
+  std::vector<float> alpha((size_t)D->n_materials * 2, 0.0f);
+  auto clamped = [&](int idx) {
+    if (idx < 0) return idx;
+    bool neg = false;
+    for (uint32_t c = 0; c < NC; c++) if (spectra[(size_t)idx * NC + c] < 0.0f) neg = true;
+    if (!neg) return idx;
+    size_t n = spectra.size() / NC;
+    for (uint32_t c = 0; c < NC; c++) { float v = spectra[(size_t)idx * NC + c]; spectra.push_back(v < 0.0f ? 0.0f : v); }
+    return (int)n;
+  };
+  for (uint32_t m = 0; m < D->n_materials; m++) {
+    pt_material& M = mats[m];
+    if (M.type == PT_MAT_PLASTIC) { M.kd = clamped(M.kd); M.ks = clamped(M.ks); }
+    if (M.type == PT_MAT_MIRROR) M.kr = clamped(M.kr);
+    float ur = M.uroughness, vr = M.vroughness;
+    if (M.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+    alpha[2 * m] = ur;
+    alpha[2 * m + 1] = vr;
+  }
+  CK(s->bufs.upload(spectra.data(), spectra.size(), &H.spectra));
+  CK(s->bufs.upload(mats.data(), mats.size(), &H.materials));
+  CK(s->bufs.upload(alpha.data(), alpha.size(), &H.alpha));
+  CK(s->bufs.upload(D->lights, (size_t)D->n_lights + D->n_emitters_only, &H.lights));
+
+  // ---- sampler (halton.rs:57-101, sobol.rs:18-31) ---------------------------------------------------------------
+  SamplerDev& SD = H.sampler;
+  memset(&SD, 0, sizeof(SD));
+  SD.type = D->sampler.type;
+  SD.spp = D->sampler.samples_per_pixel;
+  SD.at_center = D->sampler.sample_at_pixel_center;
+  for (int i = 0; i < 4; i++) SD.sb[i] = D->film.sample_bounds[i];
+  if (SD.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\": per-tile sequential PCG32 streams are not reproduced on the GPU path yet"); return 1; }
+  if (SD.sb[2] - SD.sb[0] >= 65536 || SD.sb[3] - SD.sb[1] >= 32768) { pt_set_error("film too large for packed pixel ids"); return 1; }
+  {
+    int res[2] = {SD.sb[2] - SD.sb[0], SD.sb[3] - SD.sb[1]};
+    const int BASES[2] = {2, 3};
+    for (int i = 0; i < 2; i++) {
+      int scale = 1, e = 0;
+      while (scale < std::min(res[i], 128)) { scale *= BASES[i]; e++; }
+      SD.base_scales[i] = scale;
+      SD.base_exponents[i] = e;
+    }
+    SD.sample_stride = SD.base_scales[0] * SD.base_scales[1];
+    SD.mult_inverse[0] = (int)mult_inverse(SD.base_scales[1], SD.base_scales[0]);
+    SD.mult_inverse[1] = (int)mult_inverse(SD.base_scales[0], SD.base_scales[1]);
+    if (SD.type == PT_SAMPLER_SOBOL) {
+      SD.spp = (int)round_up_pow2((uint32_t)SD.spp);
+      SD.resolution = round_up_pow2((uint32_t)std::max(res[0], res[1]));
+      SD.log2_resolution = log2int(SD.resolution);
+    }
+  }
+  {
+    std::vector<uint32_t> primes, sums;
+    for (uint32_t n = 2; primes.size() < 1024; n++) {
+      bool is = true;
+      for (uint32_t p : primes) { if ((uint64_t)p * p > n) break; if (n % p == 0) { is = false; break; } }
+      if (is) primes.push_back(n);
+    }
+    uint32_t acc = 0;
+    for (uint32_t p : primes) { sums.push_back(acc); acc += p; }
+    std::vector<uint16_t> perms(acc);
+    Pcg rng;
+    size_t off = 0;
+    for (uint32_t p : primes) {
+      for (uint32_t j = 0; j < p; j++) perms[off + j] = (uint16_t)j;
+      for (uint32_t j = 0; j < p; j++) {  // shuffle_array (sampling.rs:4-15)
+        uint32_t other = j + rng.bounded(p - j);
+        std::swap(perms[off + j], perms[off + other]);
+      }
+      off += p;
+    }
+    CK(s->bufs.upload(primes.data(), primes.size(), &H.primes));
+    CK(s->bufs.upload(sums.data(), sums.size(), &H.prime_sums));
+    CK(s->bufs.upload(perms.data(), perms.size(), &H.perms));
+  }
+  if (SD.type == PT_SAMPLER_SOBOL) {
+    try {
+      std::string dir = pth::data_dir();
+      std::vector<uint32_t> m32(1024 * 52);
+      std::vector<uint64_t> vdc((25 + 26) * 52);
+      FILE* f = fopen((dir + "/sobol32.bin").c_str(), "rb");
+      if (!f || fread(m32.data(), 4, m32.size(), f) != m32.size()) throw std::runtime_error("cannot read " + dir + "/sobol32.bin");
+      fclose(f);
+      f = fopen((dir + "/vdc.bin").c_str(), "rb");
+      if (!f || fread(vdc.data(), 8, vdc.size(), f) != vdc.size()) throw std::runtime_error("cannot read " + dir + "/vdc.bin");
+      fclose(f);
+      CK(s->bufs.upload(m32.data(), m32.size(), &H.sobol32));
+      CK(s->bufs.upload(vdc.data(), vdc.size(), &H.vdc));
+    } catch (const std::exception& e) { pt_set_error(e.what()); return 1; }
+  }
+
+  // ---- world bound, light distribution -------------------------------------------------------------------------------
+  const pth::BBox& wb = s->objects[0].bounds;
+  {
+    float dx = wb.mx[0] - wb.mn[0], dy = wb.mx[1] - wb.mn[1], dz = wb.mx[2] - wb.mn[2];
+    H.world_radius = sqrtf(dx * dx + dy * dy + dz * dz) * 0.5f;  // Bounds3f::bounding_sphere (bounds3.rs:184-188)
+  }
+  LightDistDev& LD = H.ld;
+  memset(&LD, 0, sizeof(LD));
+  int strat = D->integrator.light_strategy;
+  if (strat == PT_LIGHTS_UNIFORM && D->n_lights != 1) strat = PT_LIGHTS_SPATIAL;
+  LD.strategy = strat;
+  for (int a = 0; a < 3; a++) { LD.wb_min[a] = wb.mn[a]; LD.wb_max[a] = wb.mx[a]; LD.voxels[a] = 1; }
+  uint32_t n_vox = 1;
+  if (strat == PT_LIGHTS_SPATIAL && D->n_lights > 0) {
+    float diag[3] = {wb.mx[0] - wb.mn[0], wb.mx[1] - wb.mn[1], wb.mx[2] - wb.mn[2]};
+    int me = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);
+    for (int a = 0; a < 3; a++) {
+      float v = ceilf(diag[a] / diag[me] * 64.0f);
+      uint32_t u = (v != v || v <= 0.0f) ? 0u : (v >= 4294967296.0f ? 0xffffffffu : (uint32_t)v);
+      LD.voxels[a] = std::min(std::max(u, 1u), 64u);
+    }
+    n_vox = LD.voxels[0] * LD.voxels[1] * LD.voxels[2];
+  }
+  float *func = nullptr, *cdf = nullptr, *fint = nullptr;
+  if (D->n_lights > 0) {
+    size_t tot = (size_t)n_vox * D->n_lights;
+    if (tot > (size_t)3 << 30) { pt_set_error("light distribution table too large"); return 1; }
+    CK(s->bufs.alloc(tot, &func));
+    CK(s->bufs.alloc((size_t)n_vox * (D->n_lights + 1), &cdf));
+    CK(s->bufs.alloc(n_vox, &fint));
+    LD.func = func; LD.cdf = cdf; LD.func_int = fint;
+  }
+  CK(cudaMalloc(&s->d, sizeof(DScene)));
+  CK(cudaMemcpy(s->d, &H, sizeof(DScene), cudaMemcpyHostToDevice));
+  if (D->n_lights > 0) {
+    if (strat == PT_LIGHTS_SPATIAL) {
+      int rc = NC == 3 ? precompute_light_distribution<3>(s, n_vox, func, cdf, fint) : precompute_light_distribution<60>(s, n_vox, func, cdf, fint);
+      if (rc) return rc;
+    } else {
+      // uniform / power (lightdistrib/{uniform,power}.rs): one distribution, built on the host
+      std::vector<float> f(D->n_lights, 1.0f);
+      if (strat == PT_LIGHTS_POWER) {
+        for (uint32_t i = 0; i < D->n_lights; i++) {
+          const pt_light& L = D->lights[i];
+          const float* sp = D->spectra + (size_t)L.spectrum * NC;
+          float k;
+          if (L.type == PT_LIGHT_AREA) {
+            const float* p = D->tri_p + (size_t)L.tri * 9;
+            f3 a = mk3(p[3] - p[0], p[4] - p[1], p[5] - p[2]), b = mk3(p[6] - p[0], p[7] - p[1], p[8] - p[2]);
+            float area = 0.5f * len3(cross3(a, b));
+            k = (L.two_sided ? 2.0f : 1.0f) * area * PT_PI;
+          } else if (L.type == PT_LIGHT_POINT) k = 4.0f * PT_PI;
+          else k = PT_PI * H.world_radius * H.world_radius;
+          const float* w = D->xyz_weights + 60;
+          float acc = w[0] * (sp[0] * k);
+          for (uint32_t c = 1; c < NC; c++) acc += w[c] * (sp[c] * k);
+          f[i] = acc * D->xyz_scale;
+        }
+      }
+      uint32_t nl = D->n_lights;
+      std::vector<float> c(nl + 1, 0.0f);
+      for (uint32_t j = 1; j < nl + 1; j++) c[j] = c[j - 1] + f[j - 1] / (float)nl;
+      float fi = c[nl];
+      if (fi == 0.0f) for (uint32_t j = 1; j < nl + 1; j++) c[j] = (float)j / (float)nl;
+      else for (uint32_t j = 1; j < nl + 1; j++) c[j] /= fi;
+      CK(cudaMemcpy(func, f.data(), nl * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(cdf, c.data(), (nl + 1) * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(fint, &fi, 4, cudaMemcpyHostToDevice));
+    }
+  }
+  // film
+  const int* cb = D->film.cropped_pixel_bounds;
+  s->film_pixels = (uint32_t)(std::max(cb[2] - cb[0], 0) * std::max(cb[3] - cb[1], 0));
+  CK(s->bufs.alloc(std::max(s->film_pixels, 1u), &s->film));
+  CK(s->bufs.alloc((size_t)std::max(s->film_pixels, 1u) * 3, &s->rgb_dev));
+  CK(cudaMemset(s->film, 0, (size_t)std::max(s->film_pixels, 1u) * sizeof(f4)));
+  const int* sb = D->film.sample_bounds;
+  size_t sbn = (size_t)std::max(sb[2] - sb[0], 1) * std::max(sb[3] - sb[1], 1);
+  CK(s->bufs.alloc(sbn, &s->slot_of));
+  CK(cudaMemset(s->slot_of, 0xff, sbn * sizeof(int)));
+  CK(s->bufs.alloc(4, &s->counters));
+  CK(s->bufs.alloc(1, &s->overflow));
+  CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(s->overflow, 0, sizeof(int)));
+  return 0;
+}
+
+int ensure_wave(pt_scene* s, uint32_t cap) {
+  if (s->wave_bufs && s->wave_cap >= cap) return 0;
+  s->wave_bufs.reset(new DevBufs());
+  DevBufs& B = *s->wave_bufs;
+  WaveState& W = s->W;
+  const uint32_t NC = s->h.n_channels;
+  W.cap = cap;
+  CK(B.alloc(cap, &W.ray_o)); CK(B.alloc(cap, &W.ray_d)); CK(B.alloc(cap, &W.hit));
+  W.hit_inst = nullptr;
+  if (s->h.has_instances) CK(B.alloc(cap, &W.hit_inst));
+  CK(B.alloc((size_t)cap * NC, &W.beta)); CK(B.alloc((size_t)cap * NC, &W.L));
+  CK(B.alloc(cap, &W.eta_scale)); CK(B.alloc(cap, &W.flags)); CK(B.alloc(cap, &W.dim)); CK(B.alloc(cap, &W.sindex));
+  CK(B.alloc(cap, &W.pix)); CK(B.alloc(cap, &W.p_film));
+  CK(B.alloc(cap, &W.sh_o)); CK(B.alloc(cap, &W.sh_d)); CK(B.alloc((size_t)cap * NC, &W.pendA));
+  CK(B.alloc(cap, &W.mis_o)); CK(B.alloc(cap, &W.mis_d)); CK(B.alloc((size_t)cap * NC, &W.pendB)); CK(B.alloc(cap, &W.mis_light));
+  Queues& Q = s->Q;
+  CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(4, &Q.counts));
+  s->wave_cap = cap;
+  return 0;
+}
+
+struct WaveTotals {
+  uint64_t regular = 0, shadow = 0, launches = 0, trace_launches = 0, trace_rays = 0;
+  double trace_ms = 0, shade_ms = 0;
+};
+
+// runs the bounce loop for n paths whose camera rays are in the state and whose ids are in Q.ext[0..n)
+template <int NC>
+int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) {
+  Queues Q = s->Q;
+  WaveState& W = s->W;
+  uint32_t counts[4] = {n, 0, 0, 0};
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
+  const bool inst = s->h.has_instances != 0;
+  int guard = 0;
+  while (counts[0] + counts[2] + counts[3] > 0) {
+    if (++guard > 100000) { pt_set_error("bounce loop did not terminate"); return 1; }
+    uint32_t total = counts[0] + counts[3] + counts[2];
+    int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
+    if (timed) cudaEventRecord(e0, s->stream);
+#define LAUNCH_TRACE(I, C) k_trace<NC, I, C><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
+    if (inst) { if (count) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
+    else { if (count) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
+#undef LAUNCH_TRACE
+    CK(cudaGetLastError());
+    if (timed) cudaEventRecord(e1, s->stream);
+    T->regular += counts[0] + counts[3];
+    T->shadow += counts[2];
+    T->launches++;
+    T->trace_launches++;
+    T->trace_rays += total;
+    uint32_t n_ext = counts[0];
+    CK(cudaMemsetAsync(Q.counts, 0, 4 * sizeof(uint32_t), s->stream));
+    if (n_ext > 0) {
+      k_shade<NC><<<grid_for(s, n_ext, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, 0, s->stream>>>(s->d, W, Q, n_ext, count ? s->counters + 2 : nullptr);
+      CK(cudaGetLastError());
+      T->launches++;
+    }
+    if (timed) cudaEventRecord(e2, s->stream);
+    CK(cudaMemcpyAsync(counts, Q.counts, sizeof(counts), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (timed) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, e0, e1);
+      cudaEventElapsedTime(&b, e1, e2);
+      T->trace_ms += a;
+      T->shade_ms += b;
+    }
+    counts[0] = counts[1];
+    counts[1] = 0;
+    std::swap(Q.ext, Q.ext_next);
+  }
+  if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
+  return 0;
+}
+
+int build_pixlist(pt_scene* s, int shard_index, int shard_count, int tile) {
+  if (s->pix_key[0] == shard_index && s->pix_key[1] == shard_count && s->pix_key[2] == tile && s->pix_bufs) return 0;
+  const int* sb = s->h.film.sample_bounds;
+  int w = sb[2] - sb[0], h = sb[3] - sb[1];
+  std::vector<int>& px = s->pix_host;
+  px.clear();
+  int ntx = (w + tile - 1) / tile, nty = (h + tile - 1) / tile;
+  for (int ty = 0; ty < nty; ty++)
+    for (int tx = 0; tx < ntx; tx++) {
+      int ti = ty * ntx + tx;
+      if (shard_count > 1 && (ti % shard_count) != shard_index) continue;
+      for (int y = ty * tile; y < std::min((ty + 1) * tile, h); y++)
+        for (int x = tx * tile; x < std::min((tx + 1) * tile, w); x++) px.push_back((y << 16) | x);
+    }
+  s->pix_bufs.reset(new DevBufs());
+  const int* dp = nullptr;
+  CK(s->pix_bufs->upload(px.data(), px.size(), &dp));
+  s->pixlist = (int*)dp;
+  s->pix_n = (uint32_t)px.size();
+  s->pix_key[0] = shard_index; s->pix_key[1] = shard_count; s->pix_key[2] = tile;
+  return 0;
+}
+
+template <int NC>
+int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
+  const int spp = s->h.sampler.spp;
+  int s_begin = 0, s_end = spp;
+  if (o && !(o->spp_begin == 0 && o->spp_end == 0)) { s_begin = std::max(o->spp_begin, 0); s_end = std::min(o->spp_end, spp); }
+  int shard_i = o ? o->shard_index : 0, shard_n = (o && o->shard_count > 0) ? o->shard_count : 1;
+  int tile = (o && o->tile_size > 0) ? o->tile_size : 16;
+  bool count = o && o->collect_counters;
+  if (build_pixlist(s, shard_i, shard_n, tile)) return 1;
+  uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? (4u << 20) : (1u << 19));
+  uint32_t npix_total = s->pix_n;
+  int ns_total = std::max(s_end - s_begin, 0);
+  if (npix_total == 0 || ns_total == 0 || s->h.n_lights == 0) return 0;  // no lights: li() returns zero (path.rs:71-75) and no sample is added... see below
+  uint32_t pix_chunk, ns_wave;
+  if ((uint64_t)npix_total * (uint64_t)ns_total <= cap) { pix_chunk = npix_total; ns_wave = (uint32_t)ns_total; }
+  else if (npix_total <= cap) { pix_chunk = npix_total; ns_wave = std::max(1u, cap / npix_total); }
+  else { pix_chunk = cap; ns_wave = 1; }
+  if (ensure_wave(s, (uint32_t)std::min<uint64_t>((uint64_t)pix_chunk * ns_wave, cap))) return 1;
+  const int* sb = s->h.film.sample_bounds;
+  const int* cb = s->h.film.cropped_pixel_bounds;
+  const int sbw = sb[2] - sb[0];
+  const float rx = s->h.film.filter_radius[0], ry = s->h.film.filter_radius[1];
+  WaveTotals T;
+  for (uint32_t c0 = 0; c0 < npix_total; c0 += pix_chunk) {
+    uint32_t npix = std::min(pix_chunk, npix_total - c0);
+    k_set_slots<<<grid_for(s, npix, 256, 8), 256, 0, s->stream>>>(s->pixlist, c0, npix, sbw, s->slot_of, 0);
+    CK(cudaGetLastError());
+    T.launches++;
+    // film footprint of this pixel chunk
+    int minx = 1 << 30, miny = 1 << 30, maxx = -(1 << 30), maxy = -(1 << 30);
+    for (uint32_t i = c0; i < c0 + npix; i++) {
+      int pk = s->pix_host[i], x = (pk & 0xffff) + sb[0], y = (pk >> 16) + sb[1];
+      minx = std::min(minx, x); maxx = std::max(maxx, x); miny = std::min(miny, y); maxy = std::max(maxy, y);
+    }
+    int fx0 = std::max((int)floorf((float)minx - rx), cb[0]), fy0 = std::max((int)floorf((float)miny - ry), cb[1]);
+    int fx1 = std::min((int)ceilf((float)(maxx + 1) + rx), cb[2]), fy1 = std::min((int)ceilf((float)(maxy + 1) + ry), cb[3]);
+    for (int s0 = s_begin; s0 < s_end; s0 += (int)ns_wave) {
+      uint32_t ns = (uint32_t)std::min<int>((int)ns_wave, s_end - s0);
+      uint32_t n = npix * ns;
+      k_raygen<NC><<<grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, 0, s->stream>>>(s->d, s->W, s->Q, s->pixlist, c0, npix, s0, ns);
+      CK(cudaGetLastError());
+      T.launches++;
+      if (st) st->camera_rays += n;
+      if (run_bounces<NC>(s, n, count, st != nullptr, &T)) return 1;
+      k_finish<NC><<<grid_for(s, n, 256, 8), 256, 0, s->stream>>>(s->d, s->W, n);
+      CK(cudaGetLastError());
+      T.launches++;
+      if (fx1 > fx0 && fy1 > fy0) {
+        k_film<NC><<<grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, 0, s->stream>>>(s->d, s->W, s->slot_of, npix, ns, fx0, fy0, fx1, fy1, s->film);
+        CK(cudaGetLastError());
+        T.launches++;
+      }
+    }
+    k_set_slots<<<grid_for(s, npix, 256, 8), 256, 0, s->stream>>>(s->pixlist, c0, npix, sbw, s->slot_of, 1);
+    CK(cudaGetLastError());
+    T.launches++;
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  int ovf = 0;
+  CK(cudaMemcpy(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ovf) { pt_set_error("traversal stack overflow"); return 1; }
+  if (st) {
+    st->regular_rays += T.regular;
+    st->shadow_rays += T.shadow;
+    st->kernel_launches += T.launches;
+    st->extend_ms += T.trace_ms;
+    st->shade_ms += T.shade_ms;
+    st->extend_launches += T.trace_launches;
+    st->extend_rays += T.trace_rays;
+    if (count) {
+      unsigned long long c[4];
+      CK(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
+      st->nodes_visited += c[0];
+      st->tris_tested += c[1];
+      st->path_vertices += c[2];
+      st->extend_bytes += 128ull * c[0] + 48ull * c[1] + 48ull * T.trace_rays;
+      CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
+    }
+  }
+  return 0;
+}
+
+int upload_rays(pt_scene* s, const float* rays, uint32_t n, DevBufs& B, f4** ro, f4** rd) {
+  std::vector<f4> o(n), d(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const float* q = rays + (size_t)i * 8;
+    o[i] = mk4(q[0], q[1], q[2], q[3]);
+    d[i] = mk4(q[4], q[5], q[6], q[7]);
+  }
+  const f4 *po = nullptr, *pd = nullptr;
+  CK(B.upload(o.data(), n, &po));
+  CK(B.upload(d.data(), n, &pd));
+  *ro = (f4*)po; *rd = (f4*)pd;
+  (void)s;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out) {
+  if (!desc || !out) { pt_set_error("pt_scene_create: null argument"); return 1; }
+  *out = nullptr;
+  if (desc->abi_version != PT_ABI_VERSION) { pt_set_error("pt_scene_create: ABI version mismatch"); return 1; }
+  if (desc->n_channels != 3 && desc->n_channels != 60) { pt_set_error("pt_scene_create: n_channels must be 3 or 60"); return 1; }
+  if (desc->n_objects < 1) { pt_set_error("pt_scene_create: need at least the top-level object"); return 1; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { pt_set_error(std::string("pt_scene_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback"); return 1; }
+  CK(cudaSetDevice(device));
+  std::unique_ptr<pt_scene> s(new pt_scene());
+  s->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  s->n_sm = prop.multiProcessorCount;
+  CK(cudaStreamCreate(&s->stream));
+  if (build_scene(s.get(), desc)) return 1;
+  *out = s.release();
+  return 0;
+}
+
+void pt_scene_destroy(pt_scene* scene) {
+  if (!scene) return;
+  cudaSetDevice(scene->device);
+  delete scene;
+}
+
+int pt_film_clear(pt_scene* s) {
+  if (!s) { pt_set_error("null scene"); return 1; }
+  CK(cudaSetDevice(s->device));
+  CK(cudaMemsetAsync(s->film, 0, (size_t)std::max(s->film_pixels, 1u) * sizeof(f4), s->stream));
+  return 0;
+}
+
+int pt_render_partial(pt_scene* s, const pt_render_opts* opts, float** dev_film_xyzw, pt_stats* stats) {
+  if (!s) { pt_set_error("null scene"); return 1; }
+  CK(cudaSetDevice(s->device));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (pt_film_clear(s)) return 1;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, s->stream));
+  int rc = s->h.n_channels == 3 ? render_waves<3>(s, opts, stats) : render_waves<60>(s, opts, stats);
+  if (rc) return rc;
+  CK(cudaEventRecord(e1, s->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (stats) stats->device_ms = ms;
+  if (dev_film_xyzw) *dev_film_xyzw = (float*)s->film;
+  return 0;
+}
+
+int pt_film_resolve(pt_scene* s, const float* dev_film_xyzw, float* out_rgb_host) {
+  if (!s || !out_rgb_host) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  const f4* film = dev_film_xyzw ? (const f4*)dev_film_xyzw : s->film;
+  if (s->film_pixels == 0) return 0;
+  k_film_resolve<<<grid_for(s, s->film_pixels, 256, 8), 256, 0, s->stream>>>(s->d, film, s->rgb_dev, s->film_pixels);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_rgb_host, s->rgb_dev, (size_t)s->film_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int pt_render(pt_scene* s, const pt_render_opts* opts, float* out_rgb, pt_stats* stats) {
+  float* film = nullptr;
+  if (pt_render_partial(s, opts, &film, stats)) return 1;
+  if (stats) stats->kernel_launches += 1;
+  return pt_film_resolve(s, film, out_rgb);
+}
+
+int pt_intersect(pt_scene* s, const float* rays, uint32_t n, int32_t* prim, float* t, float* bary, uint64_t* nodes_visited, uint64_t* tris_tested) {
+  if (!s || !rays) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  if (n == 0) return 0;
+  DevBufs B;
+  f4 *ro, *rd, *hits;
+  float* tt;
+  if (upload_rays(s, rays, n, B, &ro, &rd)) return 1;
+  CK(B.alloc(n, &hits));
+  CK(B.alloc(n, &tt));
+  bool count = nodes_visited || tris_tested;
+  CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
+  int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
+  if (s->h.has_instances) { if (count) k_intersect<true, true><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else k_intersect<true, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
+  else { if (count) k_intersect<false, true><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else k_intersect<false, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
+  CK(cudaGetLastError());
+  std::vector<f4> hh(n);
+  std::vector<float> th(n);
+  CK(cudaMemcpyAsync(hh.data(), hits, n * sizeof(f4), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(th.data(), tt, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  unsigned long long c[4] = {0, 0, 0, 0};
+  int ovf = 0;
+  CK(cudaMemcpyAsync(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaMemcpyAsync(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (ovf) { pt_set_error("traversal stack overflow"); return 1; }
+  for (uint32_t i = 0; i < n; i++) {
+    int tri = (int)fbits(hh[i].w);
+    if (prim) prim[i] = tri;
+    if (t) t[i] = th[i];
+    if (bary) { bary[3 * i] = tri >= 0 ? hh[i].x : 0.0f; bary[3 * i + 1] = tri >= 0 ? hh[i].y : 0.0f; bary[3 * i + 2] = tri >= 0 ? hh[i].z : 0.0f; }
+  }
+  if (nodes_visited) *nodes_visited = c[0];
+  if (tris_tested) *tris_tested = c[1];
+  CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
+  return 0;
+}
+
+int pt_intersect_p(pt_scene* s, const float* rays, uint32_t n, uint8_t* occluded) {
+  if (!s || !rays || !occluded) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  if (n == 0) return 0;
+  DevBufs B;
+  f4 *ro, *rd;
+  unsigned char* occ;
+  if (upload_rays(s, rays, n, B, &ro, &rd)) return 1;
+  CK(B.alloc(n, &occ));
+  int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
+  if (s->h.has_instances) k_intersect_p<true><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, occ, s->overflow);
+  else k_intersect_p<false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, occ, s->overflow);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(occluded, occ, n, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int pt_intersect_device(pt_scene* s, const void* dev_o_tmax, const void* dev_d_time, uint32_t n, void* dev_hits, int repeat, float* ms_per_launch) {
+  if (!s || !dev_o_tmax || !dev_d_time || !dev_hits) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
+  CK(cudaEventRecord(e0, s->stream));
+  for (int r = 0; r < std::max(repeat, 1); r++) {
+    if (s->h.has_instances) k_intersect<true, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
+    else k_intersect<false, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, s->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_per_launch) *ms_per_launch = ms / (float)std::max(repeat, 1);
+  return 0;
+}
+
+int pt_sampler_values(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, uint32_t dim0, uint32_t ndims, float* out) {
+  if (!s || !pixel_xy || !sample_num || !out) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  if (n == 0 || ndims == 0) return 0;
+  DevBufs B;
+  const int *pxy, *sn;
+  float* o;
+  CK(B.upload(pixel_xy, (size_t)n * 2, &pxy));
+  CK(B.upload(sample_num, n, &sn));
+  CK(B.alloc((size_t)n * ndims, &o));
+  k_sampler_values<<<grid_for(s, (size_t)n * ndims, 128, 8), 128, 0, s->stream>>>(s->d, pxy, sn, n, dim0, ndims, o);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, o, (size_t)n * ndims * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, bool bounce) {
+  if (ensure_wave(s, std::max(n, 1u))) return 1;
+  DevBufs B;
+  const int *pxy, *sn;
+  CK(B.upload(pixel_xy, (size_t)n * 2, &pxy));
+  CK(B.upload(sample_num, n, &sn));
+  if (s->h.n_channels == 3) k_raygen_list<3><<<grid_for(s, n, 128, 8), 128, 0, s->stream>>>(s->d, s->W, s->Q, pxy, sn, n);
+  else k_raygen_list<60><<<grid_for(s, n, 128, 8), 128, 0, s->stream>>>(s->d, s->W, s->Q, pxy, sn, n);
+  CK(cudaGetLastError());
+  if (bounce && s->h.n_lights > 0) {
+    WaveTotals T;
+    int rc = s->h.n_channels == 3 ? run_bounces<3>(s, n, false, false, &T) : run_bounces<60>(s, n, false, false, &T);
+    if (rc) return rc;
+    if (s->h.n_channels == 3) k_finish<3><<<grid_for(s, n, 256, 8), 256, 0, s->stream>>>(s->d, s->W, n);
+    else k_finish<60><<<grid_for(s, n, 256, 8), 256, 0, s->stream>>>(s->d, s->W, n);
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int pt_camera_rays(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, float* rays, float* p_film) {
+  if (!s || !pixel_xy || !sample_num || !rays) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  if (n == 0) return 0;
+  if (run_list(s, pixel_xy, sample_num, n, false)) return 1;
+  std::vector<f4> o(n), d(n);
+  std::vector<f2> pf(n);
+  CK(cudaMemcpy(o.data(), s->W.ray_o, n * sizeof(f4), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(d.data(), s->W.ray_d, n * sizeof(f4), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pf.data(), s->W.p_film, n * sizeof(f2), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n; i++) {
+    float* q = rays + (size_t)i * 8;
+    q[0] = o[i].x; q[1] = o[i].y; q[2] = o[i].z; q[3] = o[i].w; q[4] = d[i].x; q[5] = d[i].y; q[6] = d[i].z; q[7] = d[i].w;
+    if (p_film) { p_film[2 * i] = pf[i].x; p_film[2 * i + 1] = pf[i].y; }
+  }
+  return 0;
+}
+
+int pt_li(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, float* out_l) {
+  if (!s || !pixel_xy || !sample_num || !out_l) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  if (n == 0) return 0;
+  if (run_list(s, pixel_xy, sample_num, n, true)) return 1;
+  const uint32_t NC = s->h.n_channels, cap = s->W.cap;
+  std::vector<float> L((size_t)cap * NC);
+  CK(cudaMemcpy(L.data(), s->W.L, L.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < n; i++)
+    for (uint32_t c = 0; c < NC; c++) out_l[(size_t)i * NC + c] = L[(size_t)c * cap + i];
+  int ovf = 0;
+  CK(cudaMemcpy(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ovf) { pt_set_error("traversal stack overflow"); return 1; }
+  return 0;
+}
+
+int pt_bvh_info(pt_scene* s, uint32_t object, uint32_t* n_nodes, uint32_t* n_prims, int32_t* ordered) {
+  if (!s || object >= s->objects.size()) { pt_set_error("bad object"); return 1; }
+  const ObjectHost& O = s->objects[object];
+  std::vector<pth::RefNodeH> ref;
+  if (n_nodes) { pth::flatten_reference(O.bvh, &ref); *n_nodes = (uint32_t)ref.size(); }
+  if (n_prims) *n_prims = (uint32_t)O.ordered.size();
+  if (ordered) for (size_t i = 0; i < O.ordered.size(); i++) ordered[i] = O.ordered[i];
+  return 0;
+}
+
+int pt_bvh_node(pt_scene* s, uint32_t object, uint32_t node, float* boxes24, int64_t* children4, int32_t* axes3, int32_t* is_leaf) {
+  if (!s || object >= s->objects.size()) { pt_set_error("bad object"); return 1; }
+  static thread_local const pt_scene* cached_scene = nullptr;
+  static thread_local uint32_t cached_obj = 0;
+  static thread_local std::vector<pth::RefNodeH> ref;
+  if (cached_scene != s || cached_obj != object || ref.empty()) {
+    pth::flatten_reference(s->objects[object].bvh, &ref);
+    cached_scene = s;
+    cached_obj = object;
+  }
+  if (node >= ref.size()) { pt_set_error("bad node"); return 1; }
+  const pth::RefNodeH& q = ref[node];
+  memcpy(boxes24, q.bboxes, sizeof(q.bboxes));
+  for (int k = 0; k < 4; k++) children4[k] = q.children[k];
+  for (int k = 0; k < 3; k++) axes3[k] = q.axes[k];
+  *is_leaf = q.is_leaf;
+  return 0;
+}
+
+int pt_light_distribution(pt_scene* s, const float* points, uint32_t n, float* out_func) {
+  if (!s || !points || !out_func) { pt_set_error("null argument"); return 1; }
+  CK(cudaSetDevice(s->device));
+  const uint32_t nl = s->h.n_lights;
+  if (nl == 0 || n == 0) return 0;
+  const LightDistDev& D = s->h.ld;
+  for (uint32_t i = 0; i < n; i++) {
+    uint32_t vox = D.strategy == PT_LIGHTS_SPATIAL ? ld_voxel(D, mk3(points[3 * i], points[3 * i + 1], points[3 * i + 2])) : 0u;
+    CK(cudaMemcpy(out_func + (size_t)i * nl, D.func + (size_t)vox * nl, nl * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// dsampler.cuh — Halton and Sobol sample streams on the device, reproducing the reference's values bit for bit.
+// Replaces reference src/samplers/halton.rs:115-162 (pixel offset, sample_dimension), src/samplers/sobol.rs:168-185,
+// src/core/lowdiscrepancy/radical_inverse.rs:38-91, src/core/lowdiscrepancy/sobol/sobol.rs:5-56,
+// src/core/sampler/sampler.rs:26-36 (camera sample = dims 0-1 film, 2-3 lens, 4 time).
+// A sample is a pure function of (pixel, sample number, dimension): the wavefront keeps only an i64 index
+// and a dimension counter per path.
+#pragma once
+#include "dscene.cuh"
+
+namespace ptd {
+
+PT_HD uint32_t rev32(uint32_t n) {
+#if defined(__CUDA_ARCH__)
+  return __brev(n);
+#else
+  n = (n << 16) | (n >> 16);
+  n = ((n & 0x00ff00ffu) << 8) | ((n & 0xff00ff00u) >> 8);
+  n = ((n & 0x0f0f0f0fu) << 4) | ((n & 0xf0f0f0f0u) >> 4);
+  n = ((n & 0x33333333u) << 2) | ((n & 0xccccccccu) >> 2);
+  n = ((n & 0x55555555u) << 1) | ((n & 0xaaaaaaaau) >> 1);
+  return n;
+#endif
+}
+PT_HD uint64_t rev64(uint64_t n) { return ((uint64_t)rev32((uint32_t)n) << 32) | (uint64_t)rev32((uint32_t)(n >> 32)); }
+
+// radical_inverse(base_index, a): base 2 by bit reversal, otherwise the digit loop (radical_inverse.rs:38-58)
+PT_HD float radical_inverse_base(uint32_t base, uint64_t a) {
+  float inv_base = 1.0f / (float)base;
+  uint64_t rev = 0;
+  float inv_base_n = 1.0f;
+  if (a < 0x100000000ull) {  // 32-bit fast path: same digits, same float sequence
+    uint32_t a32 = (uint32_t)a;
+    while (a32 != 0) {
+      uint32_t next = a32 / base;
+      uint32_t digit = a32 - next * base;
+      rev = rev * base + digit;
+      inv_base_n *= inv_base;
+      a32 = next;
+    }
+  } else {
+    while (a != 0) {
+      uint64_t next = a / base;
+      uint64_t digit = a - next * base;
+      rev = rev * base + digit;
+      inv_base_n *= inv_base;
+      a = next;
+    }
+  }
+  return fminf((float)rev * inv_base_n, PT_ONE_MINUS_EPS);
+}
+PT_HD float radical_inverse2(uint64_t a) { return (float)rev64(a) * 5.4210108624275222e-20f; }
+
+PT_HD float scrambled_radical_inverse(uint32_t base, uint64_t a, const uint16_t* perm) {  // radical_inverse.rs:71-91
+  float inv_base = 1.0f / (float)base;
+  uint64_t rev = 0;
+  float inv_base_n = 1.0f;
+  if (a < 0x100000000ull) {
+    uint32_t a32 = (uint32_t)a;
+    while (a32 != 0) {
+      uint32_t next = a32 / base;
+      uint32_t digit = a32 - next * base;
+      rev = rev * base + (uint64_t)ldg(perm + digit);
+      inv_base_n *= inv_base;
+      a32 = next;
+    }
+  } else {
+    while (a != 0) {
+      uint64_t next = a / base;
+      uint64_t digit = a - next * base;
+      rev = rev * base + (uint64_t)ldg(perm + digit);
+      inv_base_n *= inv_base;
+      a = next;
+    }
+  }
+  return fminf(inv_base_n * ((float)rev + inv_base * (float)ldg(perm) / (1.0f - inv_base)), PT_ONE_MINUS_EPS);
+}
+
+PT_HD uint64_t inverse_radical_inverse(uint64_t base, uint64_t inverse, int ndigits) {  // radical_inverse.rs:60-69
+  uint64_t index = 0;
+  for (int i = 0; i < ndigits; i++) {
+    uint64_t digit = inverse % base;
+    inverse /= base;
+    index = index * base + digit;
+  }
+  return index;
+}
+PT_HD uint64_t math_mod(int64_t a, int64_t b) {  // halton.rs:22-29
+  int64_t r = a - (a / b) * b;
+  return r < 0 ? (uint64_t)(r + b) : (uint64_t)r;
+}
+
+PT_HD uint64_t sobol_interval_to_index(const uint64_t* vdc, uint32_t m, uint64_t frame, int32_t px, int32_t py) {  // sobol.rs:5-34
+  if (m == 0) return 0;
+  const uint64_t* vdc_inv = vdc + 25 * 52;
+  uint32_t m2 = m << 1;
+  uint64_t index = frame << (m2 & 63);
+  uint64_t delta = 0;
+  for (int c = 0; frame != 0; c++, frame >>= 1)
+    if (frame & 1) delta ^= ldg(vdc + (m - 1) * 52 + c);
+  uint64_t b = ((((uint64_t)(uint32_t)px) << (m & 63)) | (uint64_t)(int64_t)py) ^ delta;
+  for (int c = 0; b != 0; c++, b >>= 1)
+    if (b & 1) index ^= ldg(vdc_inv + (m - 1) * 52 + c);
+  return index;
+}
+PT_HD float sobol_sample_float(const uint32_t* M, int64_t a, uint32_t dimension, uint32_t scramble) {  // sobol.rs:41-56
+  const uint32_t LEN = 1024u * 52u;
+  uint32_t v = scramble;
+  uint32_t i = dimension * 52u;
+  if (i > LEN - 1) i = LEN - 1;
+  while (a != 0) {
+    if (a & 1) v ^= ldg(M + i);
+    a >>= 1;
+    i += 1;
+    if (i >= LEN) i -= LEN;
+  }
+  float fv = (float)((double)v * 2.3283064365386963e-10);
+  return fminf(fv, PT_ONE_MINUS_EPS);
+}
+
+// index of sample `n` of pixel (px, py)  (halton.rs:115-147 with the INTENDED per-pixel offset; sobol.rs:168-172)
+PT_HD int64_t sampler_index(const DScene& S, int px, int py, int64_t n) {
+  const SamplerDev& c = S.sampler;
+  if (c.type == PT_SAMPLER_HALTON) {
+    int64_t offset = 0;
+    int64_t stride = c.sample_stride;
+    if (stride > 1) {
+      uint64_t pm[2] = {math_mod(px, 128), math_mod(py, 128)};
+      for (int i = 0; i < 2; i++) {
+        uint64_t dim_offset = inverse_radical_inverse(i == 0 ? 2 : 3, pm[i], c.base_exponents[i]);
+        int64_t addition = (int64_t)(dim_offset * (uint64_t)(int64_t)((c.sample_stride / c.base_scales[i]) * c.mult_inverse[i]));
+        offset = offset + addition;
+      }
+      offset = offset % stride;
+    }
+    return offset + n * stride;
+  }
+  return (int64_t)sobol_interval_to_index(S.vdc, c.log2_resolution, (uint64_t)n, px - c.sb[0], py - c.sb[1]);
+}
+
+PT_HD float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, int py) {
+  const SamplerDev& c = S.sampler;
+  if (c.type == PT_SAMPLER_HALTON) {  // halton.rs:149-162
+    if (c.at_center && dim < 2) return 0.5f;
+    if (dim == 0) return radical_inverse2((uint64_t)(index >> c.base_exponents[0]));
+    if (dim == 1) return radical_inverse_base(3u, (uint64_t)(index / (int64_t)c.base_scales[1]));
+    if (dim >= 1024u) dim = 1023u;  // the reference panics here; paths that long do not occur (maxdepth <= ~100)
+    return scrambled_radical_inverse(ldg(S.primes + dim), (uint64_t)index, S.perms + ldg(S.prime_sums + dim));
+  }
+  float s = sobol_sample_float(S.sobol32, index, dim, 0u);  // sobol.rs:174-185
+  if (dim < 2) {
+    int cp = dim == 0 ? px : py;
+    s = s * (float)c.resolution + (float)c.sb[dim];
+    s = clampf(s - (float)cp, 0.0f, PT_ONE_MINUS_EPS);
+    s = s - truncf(s);
+  }
+  return s;
+}
+
+struct SampleStream {  // the per-path sampler state
+  int64_t index;
+  uint32_t dim;
+  int px, py;
+};
+PT_HD float get1d(const DScene& S, SampleStream& st) {
+  float v = sampler_dim(S, st.index, st.dim, st.px, st.py);
+  st.dim += 1;
+  return v;
+}
+PT_HD f2 get2d(const DScene& S, SampleStream& st) {
+  float a = sampler_dim(S, st.index, st.dim, st.px, st.py);
+  float b = sampler_dim(S, st.index, st.dim + 1, st.px, st.py);
+  st.dim += 2;
+  return mk2(a, b);
+}
+
+}  // namespace ptd

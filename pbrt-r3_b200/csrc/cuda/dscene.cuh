@@ -1,0 +1,99 @@
+// dscene.cuh — HBM layout of the flattened scene (what pt_scene_create uploads) and of the wavefront state.
+//
+// QBVH node, 128 B, 16-byte aligned (reference SIMDBVHNode is 144 B: accel/qbvh/qbvh_x86.rs:15-24):
+//   f4 lo[3], hi[3]  : bboxes[0][axis][lane], bboxes[1][axis][lane]                          96 B
+//   i4 child         : lane k -> >= 0 inner/leaf NODE index | < 0 inline leaf ~((first<<3)|(count-1)) | PT_EMPTY
+//   i4 meta          : x = axis_top | axis_left<<2 | axis_right<<4 | is_leaf<<8 ; y = first ; z = count (leaf nodes)
+// Triangle record, 48 B, stored in BVH leaf order (one coalesced run per leaf):
+//   f4 v0 = p0.xyz, bits(id)   id = global triangle index, or instance index when flag PT_REC_INSTANCE
+//   f4 v1 = p1.xyz, bits(flags)
+//   f4 v2 = p2.xyz, 0
+#pragma once
+#include "../../../include/pbrt_r3_b200.h"
+#include "dmath.cuh"
+
+namespace ptd {
+
+#define PT_EMPTY ((int)0x80000000)
+#define PT_LEAF_BITS 3
+#define PT_REC_INSTANCE 0x100u
+#define PT_MAX_STACK 96
+
+struct alignas(16) QNode {
+  f4 lo[3];
+  f4 hi[3];
+  i4 child;
+  i4 meta;
+};
+static_assert(sizeof(QNode) == 128, "QNode must be 128 B");
+
+struct ObjectRec {     // one per object (0 = top level)
+  uint32_t node_base;  // into nodes
+  uint32_t rec_base;   // into tri records (in units of records)
+  uint32_t n_nodes;
+  uint32_t n_prims;
+  float bmin[3], bmax[3];  // QBVHAccel.bounds (root build-node bounds)
+  int32_t single;          // 1: object with a single primitive, no accelerator, no bounds pre-test
+  int32_t pad;
+};
+
+struct InstanceRec {
+  float m[16];
+  float minv[16];
+  int32_t object;
+  int32_t pad[3];
+};
+
+struct SamplerDev {     // samplers/{halton,sobol}.rs state that is constant over the render
+  int32_t type, spp;    // spp = effective (sobol: rounded up to a power of two)
+  int32_t sb[4];
+  int32_t at_center;
+  int32_t base_scales[2], base_exponents[2], sample_stride, mult_inverse[2];
+  uint32_t resolution, log2_resolution;
+};
+
+struct LightDistDev {   // dense restatement of SpatialLightDistribution's hash table (a pure function of the voxel)
+  int32_t strategy;     // pt_light_strategy actually used
+  uint32_t voxels[3];
+  float wb_min[3], wb_max[3];
+  const float* func;    // [n_vox][n_lights]
+  const float* cdf;     // [n_vox][n_lights + 1]
+  const float* func_int;  // [n_vox]
+};
+
+struct DScene {
+  uint32_t n_channels;
+  uint32_t n_tris, n_lights, n_materials, n_objects, n_instances;
+  const QNode* nodes;
+  const f4* recs;            // 3 per record
+  const ObjectRec* objects;
+  const InstanceRec* instances;
+  // original-order triangle attributes (indexed by global triangle id)
+  const f4* tri_v;           // 3 per triangle: p.xyz, w unused (shading / light sampling re-reads by id)
+  const float* tri_n;        // 9 per triangle or null
+  const float* tri_uv;       // 6 per triangle or null
+  const uint32_t* tri_flags;
+  const int32_t* tri_material;
+  const int32_t* tri_light;
+  const pt_material* materials;
+  const pt_light* lights;
+  const float* spectra;
+  const float* alpha;        // per material: roughness_to_alpha applied on the HOST with libm logf: [n_materials][2]
+  float xyz_w[180];
+  float xyz_scale;
+  float world_radius;
+  pt_camera camera;
+  pt_film film;
+  pt_integrator integrator;
+  SamplerDev sampler;
+  LightDistDev ld;
+  // sampler tables
+  const uint32_t* primes;      // 1024
+  const uint32_t* prime_sums;  // 1024
+  const uint16_t* perms;       // sum(primes)
+  const uint32_t* sobol32;     // 1024*52
+  const uint64_t* vdc;         // (25+26)*52
+  int has_instances;
+};
+
+}  // namespace ptd

@@ -1,0 +1,426 @@
+// dshade.cuh — wavefront stages of the PathIntegrator bounce loop: camera-ray generation, vertex shading
+// (emission, one-light NEE with MIS, BSDF continuation, Russian roulette), shadow / MIS resolution.
+// Replaces reference src/core/integrator/sampler.rs:201-257 (render_tile's per-sample body),
+// src/cameras/perspective.rs:121-183, src/integrators/path.rs:61-241, src/core/integrator/sample_lights.rs:129-176,
+// 330-453, src/lights/{diffuse,point,distant}.rs, src/shapes/triangle.rs:590-651, src/core/shape/shape.rs:40-54,
+// src/core/lightdistrib/spatial.rs:86-111,200-261 (lookup), src/core/sampling/distribution.rs:13-32,86-101.
+//
+// One path = one slot of the SoA state below.  li()'s sequential loop becomes: trace(A rays) -> shade -> trace(B shadow,
+// C MIS, A continuation rays) -> shade -> ...; the three scene queries per vertex keep their own random numbers, and
+// every sample dimension is consumed in the reference's order inside shade, so the Halton/Sobol streams are reproduced.
+#pragma once
+#include "dbsdf.cuh"
+#include "dsampler.cuh"
+#include "dtrav.cuh"
+
+namespace ptd {
+
+struct WaveState {            // all arrays have `cap` path slots; spectra are channel-major: [c * cap + i]
+  uint32_t cap;
+  f4* ray_o;                  // o.xyz, tmax   (continuation / camera ray; tmax shrinks to the hit distance)
+  f4* ray_d;                  // d.xyz, time
+  f4* hit;                    // b0, b1, b2, bits(tri) (tri = -1: miss)
+  int* hit_inst;              // instance index or -1 (only when the scene has instances)
+  float* beta;                // NC
+  float* L;                   // NC
+  float* eta_scale;
+  uint32_t* flags;            // bit0 specular_bounce, bits 8.. bounces
+  uint32_t* dim;              // next sampler dimension
+  long long* sindex;          // sampler index of this sample (halton / sobol)
+  int* pix;                   // packed pixel: (y << 16 | x) relative to sample_bounds.min
+  f2* p_film;
+  f4* sh_o; f4* sh_d;         // shadow ray (d unnormalised, tmax = 1 - eps)
+  float* pendA;               // NC: light-sample term, cleared when occluded
+  f4* mis_o; f4* mis_d;       // BSDF-sample MIS ray
+  float* pendB;               // NC: BSDF-sample term, cleared unless the ray hits the sampled light's emitting side
+  int* mis_light;
+};
+
+struct Queues {
+  uint32_t* ext;       // path ids with a continuation ray to trace, then to shade
+  uint32_t* ext_next;
+  uint32_t* shadow;
+  uint32_t* mis;
+  uint32_t* counts;    // [0] ext, [1] ext_next, [2] shadow, [3] mis
+};
+
+// PerspectiveCamera::generate_ray_differential without the differentials (constant textures: they cannot reach L)
+PT_HD DRay camera_ray(const pt_camera& C, f2 p_film, f2 p_lens, float time) {
+  f3 pc = mat_point(C.raster_to_camera, mk3(p_film.x, p_film.y, 0.0f));
+  DRay r;
+  r.o = mk3(0.0f, 0.0f, 0.0f);
+  r.d = norm3(pc);
+  r.tmax = pt_inf();
+  if (C.lens_radius > 0.0f) {
+    f2 dl = concentric_disk(p_lens);
+    f2 pl = mk2(dl.x * C.lens_radius, dl.y * C.lens_radius);
+    float ft = C.focal_distance / r.d.z;
+    f3 pf = r.o + r.d * ft;
+    r.o = mk3(pl.x, pl.y, 0.0f);
+    r.d = norm3(pf - r.o);
+  }
+  r.time = lerpf(time, C.shutter_open, C.shutter_close);
+  return xform_ray(C.camera_to_world, r);
+}
+
+// ---- lights ------------------------------------------------------------------------------------------------
+struct RefPt { f3 p, perr, n; };
+
+PT_HD f3 tri_geo_normal_for_sample(const DScene& S, int tri, f3 p0, f3 p1, f3 p2, float b0, float b1) {
+  uint32_t flags = ldg(S.tri_flags + tri);
+  f3 n = norm3(cross3(p1 - p0, p2 - p0));
+  if ((flags & PT_TRI_HAS_N) && S.tri_n) {
+    const float* q = S.tri_n + (size_t)tri * 9;
+    f3 ns = b0 * mk3(ldg(q), ldg(q + 1), ldg(q + 2)) + b1 * mk3(ldg(q + 3), ldg(q + 4), ldg(q + 5)) + (1.0f - b0 - b1) * mk3(ldg(q + 6), ldg(q + 7), ldg(q + 8));
+    n = faceforward(n, ns);
+  } else if (((flags & PT_TRI_REVERSE_ORIENTATION) != 0) != ((flags & PT_TRI_SWAPS_HANDEDNESS) != 0)) {
+    n = n * -1.0f;
+  }
+  return n;
+}
+
+template <int NC>
+struct LightSampleD {
+  Sp<NC> li;
+  f3 wi;
+  float pdf;
+  f3 sh_o, sh_d;  // VisibilityTester: p0.spawn_ray_to(p1)
+};
+
+// Light::sample_li for area (one triangle), point and distant lights
+template <int NC>
+PT_HD bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSampleD<NC>* out) {
+  const pt_light& L = S.lights[li];
+  f3 lp, lperr = mk3(0.0f, 0.0f, 0.0f), ln = mk3(0.0f, 0.0f, 0.0f);
+  if (L.type == PT_LIGHT_AREA) {
+    f3 p0, p1, p2;
+    tri_verts(S, L.tri, &p0, &p1, &p2);
+    float su0 = sqrtf(u.x);
+    float b0 = 1.0f - su0, b1 = u.y * su0;  // uniform_sample_triangle
+    f3 p = b0 * p0 + b1 * p1 + (1.0f - b0 - b1) * p2;
+    f3 n = tri_geo_normal_for_sample(S, L.tri, p0, p1, p2, b0, b1);
+    f3 pas = abs3(b0 * p0) + abs3(b1 * p1) + abs3((1.0f - b0 - b1) * p2);
+    lperr = PT_GAMMA6_REF * mk3(pas.x, pas.y, pas.z);
+    float area = 0.5f * len3(cross3(p1 - p0, p2 - p0));
+    float pdf_area = 1.0f / area;
+    f3 wi = p - it.p;
+    if (len2(wi) <= 0.0f) return false;
+    wi = norm3(wi);
+    if (!(ldg(S.tri_flags + L.tri) & PT_TRI_TWO_SIDED)) {
+      if (dot3(n, -wi) <= 0.0f) return false;
+    }
+    float pdf = pdf_area * dist2(it.p, p) / absdot3(n, -wi);
+    if (pdf <= 0.0f || isinf_(pdf)) return false;
+    if (len2(p - it.p) <= 0.0f) return false;
+    out->wi = norm3(p - it.p);
+    out->pdf = pdf;
+    if (L.two_sided || dot3(n, -out->wi) > 0.0f) out->li = sp_load<NC>(S.spectra + (size_t)L.spectrum * NC);
+    else out->li = sp_const<NC>(0.0f);
+    lp = p; ln = n;
+  } else if (L.type == PT_LIGHT_POINT) {
+    f3 v = mk3(L.v[0], L.v[1], L.v[2]);
+    out->li = sp_load<NC>(S.spectra + (size_t)L.spectrum * NC) / dist2(v, it.p);
+    out->wi = norm3(v - it.p);
+    out->pdf = 1.0f;
+    lp = v;
+  } else {
+    f3 v = mk3(L.v[0], L.v[1], L.v[2]);
+    out->li = sp_load<NC>(S.spectra + (size_t)L.spectrum * NC);
+    out->wi = v;
+    out->pdf = 1.0f;
+    lp = it.p + v * (2.0f * S.world_radius);
+  }
+  // Interaction::spawn_ray_to (interaction.rs:118-127)
+  f3 origin = offset_origin(it.p, it.perr, it.n, lp - it.p);
+  f3 target = offset_origin(lp, lperr, ln, origin - lp);
+  out->sh_o = origin;
+  out->sh_d = target - origin;
+  return true;
+}
+
+// Light::pdf_li for the area light's triangle = Shape::pdf_from (re-intersect that one triangle)
+PT_HD float light_pdf_li(const DScene& S, int li, const RefPt& it, f3 wi) {
+  const pt_light& L = S.lights[li];
+  if (L.type != PT_LIGHT_AREA) return 0.0f;
+  f3 o = offset_origin(it.p, it.perr, it.n, wi);
+  f3 p0, p1, p2;
+  tri_verts(S, L.tri, &p0, &p1, &p2);
+  TriHitD th;
+  if (!tri_test(p0, p1, p2, ldg(S.tri_flags + L.tri), o, wi, pt_inf(), &th)) return 0.0f;
+  SurfD s = tri_surface(S, L.tri, wi, th.b0, th.b1, th.b2);
+  float area = 0.5f * len3(cross3(p1 - p0, p2 - p0));
+  float pdf = dist2(it.p, s.p) / (absdot3(s.n, -wi) * area);
+  if (isinf_(pdf)) return 0.0f;
+  return pdf;
+}
+
+// SurfaceInteraction::le -> DiffuseAreaLight::l
+template <int NC>
+PT_HD Sp<NC> surface_le(const DScene& S, const SurfD& si, f3 w) {
+  int li = ldg(S.tri_light + si.tri);
+  if (li < 0) return sp_const<NC>(0.0f);
+  const pt_light& L = S.lights[li];
+  if (L.two_sided || dot3(si.n, w) > 0.0f) return sp_load<NC>(S.spectra + (size_t)L.spectrum * NC);
+  return sp_const<NC>(0.0f);
+}
+
+// LightDistribution::lookup + Distribution1D::sample_discrete on the dense voxel table
+PT_HD uint32_t ld_voxel(const LightDistDev& D, f3 p) {
+  float o[3] = {p.x - D.wb_min[0], p.y - D.wb_min[1], p.z - D.wb_min[2]};
+  uint32_t pi[3];
+  for (int i = 0; i < 3; i++) {
+    if (D.wb_max[i] > D.wb_min[i]) o[i] = o[i] / (D.wb_max[i] - D.wb_min[i]);
+    float c = clampf(o[i], 0.0f, 1.0f);
+    uint32_t v = (uint32_t)(c * (float)D.voxels[i]);  // `as u32` saturates; c >= 0
+    pi[i] = v < D.voxels[i] - 1 ? v : D.voxels[i] - 1;
+  }
+  return (pi[0] * D.voxels[1] + pi[1]) * D.voxels[2] + pi[2];
+}
+PT_HD int ld_sample(const DScene& S, f3 p, float u, float* pdf) {
+  const LightDistDev& D = S.ld;
+  uint32_t nl = S.n_lights;
+  uint32_t vox = D.strategy == PT_LIGHTS_SPATIAL ? ld_voxel(D, p) : 0u;
+  const float* cdf = D.cdf + (size_t)vox * (nl + 1);
+  // find_interval(cdf.len(), |i| cdf[i] <= u) (distribution.rs:13-32)
+  uint32_t first = 0, len = nl + 1;
+  while (len > 0) {
+    uint32_t half = len >> 1, mid = first + half;
+    if (ldg(cdf + mid) <= u) { first = mid + 1; len -= half + 1; }
+    else len = half;
+  }
+  uint32_t off = first == 0 ? 0 : first - 1;
+  if (off > nl - 1) off = nl - 1;
+  float func_int = ldg(D.func_int + vox);
+  float f = ldg(D.func + (size_t)vox * nl + off);
+  *pdf = func_int > 0.0f ? f * (1.0f / (float)nl) / func_int : 0.0f;
+  return (int)off;
+}
+
+// ---- path state helpers ------------------------------------------------------------------------------------------
+template <int NC> PT_HD Sp<NC> st_load(const float* a, uint32_t cap, uint32_t i) { Sp<NC> r;
+#pragma unroll
+  for (int c = 0; c < NC; c++) r.c[c] = a[(size_t)c * cap + i]; return r; }
+template <int NC> PT_HD void st_store(float* a, uint32_t cap, uint32_t i, const Sp<NC>& v) {
+#pragma unroll
+  for (int c = 0; c < NC; c++) a[(size_t)c * cap + i] = v.c[c]; }
+
+#if defined(__CUDA_ARCH__)
+PT_D uint32_t queue_push(uint32_t* counter) {  // warp-aggregated append (ballot / popc)
+  unsigned m = __activemask();
+  int leader = __ffs(m) - 1;
+  int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+#else
+inline uint32_t queue_push(uint32_t* counter) { return (*counter)++; }
+#endif
+
+// camera-ray generation for path slot i of the current wave: pixel (px,py) absolute, sample number n
+template <int NC>
+PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int px, int py, int n) {
+  SampleStream st;
+  st.px = px; st.py = py; st.dim = 0;
+  st.index = sampler_index(S, px, py, n);
+  f2 u = get2d(S, st);
+  f2 pf = mk2((float)px + u.x, (float)py + u.y);
+  f2 pl = get2d(S, st);
+  float tm = get1d(S, st);
+  DRay r = camera_ray(S.camera, pf, pl, tm);
+  W.ray_o[i] = mk4(r.o.x, r.o.y, r.o.z, r.tmax);
+  W.ray_d[i] = mk4(r.d.x, r.d.y, r.d.z, r.time);
+  W.p_film[i] = pf;
+  W.sindex[i] = st.index;
+  W.dim[i] = st.dim;
+  W.pix[i] = ((py - S.sampler.sb[1]) << 16) | (px - S.sampler.sb[0]);
+  W.flags[i] = 0u;
+  W.eta_scale[i] = 1.0f;
+  st_store<NC>(W.beta, W.cap, i, sp_const<NC>(1.0f));
+  st_store<NC>(W.L, W.cap, i, sp_const<NC>(0.0f));
+  st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(0.0f));
+  st_store<NC>(W.pendB, W.cap, i, sp_const<NC>(0.0f));
+  Q.ext[i] = i;
+}
+
+// One iteration of PathIntegrator::li's loop body after scene.intersect (path.rs:87-233) for path slot i.
+template <int NC>
+PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsigned long long* vertex_counter) {
+  const uint32_t cap = W.cap;
+  // contributions of the previous vertex (shadow / MIS rays were resolved by the trace stage)
+  Sp<NC> L = st_load<NC>(W.L, cap, i);
+  {
+    Sp<NC> a = st_load<NC>(W.pendA, cap, i), b = st_load<NC>(W.pendB, cap, i);
+    L = L + a;
+    L = L + b;
+    st_store<NC>(W.pendA, cap, i, sp_const<NC>(0.0f));
+    st_store<NC>(W.pendB, cap, i, sp_const<NC>(0.0f));
+  }
+  f4 ro4 = W.ray_o[i], rd4 = W.ray_d[i], h4 = W.hit[i];
+  f3 ro = xyz(ro4), rd = xyz(rd4);
+  float rtime = rd4.w;
+  int tri = (int)fbits(h4.w);
+  bool found = tri >= 0;
+  uint32_t fl = W.flags[i];
+  int bounces = (int)(fl >> 8);
+  bool specular_bounce = (fl & 1u) != 0;
+  Sp<NC> beta = st_load<NC>(W.beta, cap, i);
+  SurfD si;
+  if (found) {
+    int inst = S.has_instances ? W.hit_inst[i] : -1;
+    si = make_surface(S, tri, inst, ro, rd, rtime, h4.x, h4.y, h4.z);
+  }
+  if (bounces == 0 || specular_bounce) {
+    if (found) L = L + beta * surface_le<NC>(S, si, -rd);
+  }
+  if (!found || bounces >= S.integrator.max_depth) { st_store<NC>(W.L, cap, i, L); return; }
+  BsdfD B;
+  make_bsdf<NC>(S, si, &B);
+  RefPt ref;
+  ref.p = si.p; ref.perr = si.perr; ref.n = si.n;
+  if (B.n < 0) {  // no BSDF: continue through the surface, bounces unchanged (path.rs:108-111)
+    f3 o = offset_origin(si.p, si.perr, si.n, rd);
+    W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+    st_store<NC>(W.L, cap, i, L);
+    Q.ext_next[queue_push(&Q.counts[1])] = i;
+    return;
+  }
+  if (vertex_counter) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(vertex_counter, 1ull);
+#else
+    (*vertex_counter)++;
+#endif
+  }
+  SampleStream st;
+  st.index = W.sindex[i];
+  st.dim = W.dim[i];
+  int pk = W.pix[i];
+  st.px = (pk & 0xffff) + S.sampler.sb[0];
+  st.py = (pk >> 16) + S.sampler.sb[1];
+  const int NONSPEC = F_ALL & ~F_SPEC;
+
+  // --- uniform_sample_one_light_surface + estimate_direct_surface (sample_lights.rs:129-176, 330-453)
+  if (bsdf_count(B, NONSPEC) > 0 && S.n_lights > 0) {
+    float light_pdf;
+    int ln = ld_sample(S, si.p, get1d(S, st), &light_pdf);
+    if (light_pdf > 0.0f) {
+      f2 u_light = get2d(S, st);
+      f2 u_scat = get2d(S, st);
+      const pt_light& LT = S.lights[ln];
+      bool delta = LT.type != PT_LIGHT_AREA;
+      LightSampleD<NC> ls;
+      if (light_sample<NC>(S, ln, ref, u_light, &ls)) {
+        if (ls.pdf > 0.0f && !sp_black(ls.li)) {
+          Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
+          float spdf = bsdf_pdf(B, si.wo, ls.wi, NONSPEC);
+          if (!sp_black(f)) {
+            Sp<NC> ld;
+            if (delta) ld = f * ls.li / ls.pdf;
+            else ld = f * ls.li * (power_heuristic1(ls.pdf, spdf) / ls.pdf);
+            st_store<NC>(W.pendA, cap, i, beta * (ld / light_pdf));
+            W.sh_o[i] = mk4(ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, 0.0f);
+            W.sh_d[i] = mk4(ls.sh_d.x, ls.sh_d.y, ls.sh_d.z, 1.0f - PT_SHADOW_EPS);
+            Q.shadow[queue_push(&Q.counts[2])] = i;
+          }
+        }
+      }
+      if (!delta) {
+        Sp<NC> f2v;
+        f3 wi2;
+        float pdf2;
+        int stype;
+        if (bsdf_sample<NC>(S, B, si.wo, u_scat, NONSPEC, &f2v, &wi2, &pdf2, &stype)) {
+          Sp<NC> f = f2v * absdot3(wi2, si.sn);
+          if (!sp_black(f) && pdf2 > 0.0f) {
+            float weight = 1.0f;
+            bool go = true;
+            if (!(stype & F_SPEC)) {
+              float lp = light_pdf_li(S, ln, ref, wi2);
+              if (lp == 0.0f) go = false;
+              else weight = power_heuristic1(pdf2, lp);
+            }
+            if (go) {
+              Sp<NC> li = sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
+              Sp<NC> ld = f * li * sp_const<NC>(1.0f) * (weight / pdf2);
+              st_store<NC>(W.pendB, cap, i, beta * (ld / light_pdf));
+              f3 o = offset_origin(si.p, si.perr, si.n, wi2);
+              W.mis_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+              W.mis_d[i] = mk4(wi2.x, wi2.y, wi2.z, rtime);
+              W.mis_light[i] = ln;
+              Q.mis[queue_push(&Q.counts[3])] = i;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // --- sample the BSDF for the next direction (path.rs:139-167)
+  st_store<NC>(W.L, cap, i, L);
+  f3 wo = -rd;
+  Sp<NC> f;
+  f3 wi;
+  float pdf;
+  int sflags;
+  f2 ub = get2d(S, st);
+  if (!bsdf_sample<NC>(S, B, wo, ub, F_ALL, &f, &wi, &pdf, &sflags)) return;
+  if (sp_black(f) || pdf == 0.0f) return;
+  beta = beta * (f * (absdot3(wi, si.sn) / pdf));
+  specular_bounce = (sflags & F_SPEC) != 0;
+  float eta_scale = W.eta_scale[i];
+  if ((sflags & F_SPEC) && (sflags & F_TRANS)) {
+    float eta = B.eta;
+    eta_scale *= (dot3(wo, si.n) > 0.0f) ? (eta * eta) : 1.0f / (eta * eta);
+  }
+  f3 o = offset_origin(si.p, si.perr, si.n, wi);
+  // Russian roulette (path.rs:219-229)
+  Sp<NC> rr = beta * eta_scale;
+  float rrmax = sp_max(rr);
+  if (rrmax < S.integrator.rr_threshold && bounces > 3) {
+    float q = fmaxf(0.05f, 1.0f - rrmax);
+    if (get1d(S, st) < q) return;
+    beta = beta / (1.0f - q);
+  }
+  bounces += 1;
+  st_store<NC>(W.beta, cap, i, beta);
+  W.eta_scale[i] = eta_scale;
+  W.flags[i] = ((uint32_t)bounces << 8) | (specular_bounce ? 1u : 0u);
+  W.dim[i] = st.dim;
+  W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+  W.ray_d[i] = mk4(wi.x, wi.y, wi.z, rtime);
+  Q.ext_next[queue_push(&Q.counts[1])] = i;
+}
+
+// MIS ray resolution: the BSDF-sampled ray contributes only if it hits the sampled light (pointer equality in the
+// reference, sample_lights.rs:431-441) on its emitting side.
+template <int NC>
+PT_HD void mis_resolve(const DScene& S, WaveState& W, uint32_t i, const HitD& h, bool found, f3 rd) {
+  bool keep = false;
+  if (found && h.instance < 0) {
+    int ln = W.mis_light[i];
+    if (ldg(S.tri_light + h.tri) == ln) {
+      SurfD s = tri_surface(S, h.tri, rd, h.b0, h.b1, h.b2);
+      const pt_light& LT = S.lights[ln];
+      keep = LT.two_sided || dot3(s.n, -rd) > 0.0f;
+    }
+  }
+  if (!keep) st_store<NC>(W.pendB, W.cap, i, sp_const<NC>(0.0f));
+}
+
+// end of a wave: fold the last pending terms into L and apply validate_radiance_result (sampler.rs:151-176)
+template <int NC>
+PT_HD void finish_body(const DScene& S, WaveState& W, uint32_t i) {
+  Sp<NC> L = st_load<NC>(W.L, W.cap, i);
+  L = L + st_load<NC>(W.pendA, W.cap, i);
+  L = L + st_load<NC>(W.pendB, W.cap, i);
+  if (!sp_valid(L)) L = sp_const<NC>(0.0f);
+  else {
+    float y = sp_y(S, L);
+    if (y < -1e-5f || isinf_(y)) L = sp_const<NC>(0.0f);
+  }
+  st_store<NC>(W.L, W.cap, i, L);
+}
+
+}  // namespace ptd

@@ -1,0 +1,236 @@
+// kernels.cuh — __global__ wrappers around the PT_HD stage bodies (dshade.cuh, dtrav.cuh, dfilm.cuh).
+// Launch shape: persistent grid-stride kernels, grid = k * 148 SMs (B200), queue sizes read by the host between
+// bounces.  All kernels of a render run on one stream in program order.
+#pragma once
+#include "dfilm.cuh"
+
+namespace ptd {
+
+#define PT_TRACE_BLOCK 128
+#define PT_SHADE_BLOCK 128
+
+// Traversal stack: the first PT_SMEM_STACK entries of every thread live in shared memory, strided so that
+// consecutive lanes hit consecutive banks ([entry][thread]); deeper entries spill to a small local array.
+#define PT_SMEM_STACK 24
+struct SharedStack {
+  int* sm;           // &smem[threadIdx.x], stride PT_TRACE_BLOCK
+  int n;
+  int spill[PT_MAX_STACK - PT_SMEM_STACK];
+  __device__ __forceinline__ bool push(int x) {
+    if (n < PT_SMEM_STACK) sm[n * PT_TRACE_BLOCK] = x;
+    else if (n < PT_MAX_STACK) spill[n - PT_SMEM_STACK] = x;
+    else return false;
+    n++;
+    return true;
+  }
+  __device__ __forceinline__ bool pop(int* x) {
+    if (n == 0) return false;
+    n--;
+    *x = n < PT_SMEM_STACK ? sm[n * PT_TRACE_BLOCK] : spill[n - PT_SMEM_STACK];
+    return true;
+  }
+};
+
+// Scene::intersect for continuation (A) and MIS (C) rays, Scene::intersect_p for shadow (B) rays, in one launch.
+template <int NC, bool INST, bool COUNT>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(const DScene* __restrict__ Sp, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
+                                                          uint32_t n_sh, unsigned long long* counters, int* overflow) {
+  __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
+  const DScene& S = *Sp;
+  SharedStack st;
+  st.sm = smem + threadIdx.x;
+  TravCounters tc;
+  tc.nodes = 0; tc.tris = 0;
+  int ovf = 0;
+  const uint32_t total = n_ext + n_mis + n_sh;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    st.n = 0;
+    if (k < n_ext) {
+      uint32_t i = Q.ext[k];
+      f4 o = W.ray_o[i], d = W.ray_d[i];
+      float tmax = o.w;
+      HitD h;
+      bool found = scene_intersect<INST, COUNT>(S, xyz(o), xyz(d), d.w, tmax, &h, st, &ovf, &tc);
+      W.hit[i] = mk4(h.b0, h.b1, h.b2, bitsf((uint32_t)(found ? h.tri : -1)));
+      if (INST) W.hit_inst[i] = found ? h.instance : -1;
+      if (found) W.ray_o[i].w = tmax;
+    } else if (k < n_ext + n_mis) {
+      uint32_t i = Q.mis[k - n_ext];
+      f4 o = W.mis_o[i], d = W.mis_d[i];
+      float tmax = o.w;
+      HitD h;
+      bool found = scene_intersect<INST, COUNT>(S, xyz(o), xyz(d), d.w, tmax, &h, st, &ovf, &tc);
+      mis_resolve<NC>(S, W, i, h, found, xyz(d));
+    } else {
+      uint32_t i = Q.shadow[k - n_ext - n_mis];
+      f4 o = W.sh_o[i], d = W.sh_d[i];
+      bool occ = scene_intersect_p<INST, COUNT>(S, xyz(o), xyz(d), W.ray_d[i].w, d.w, st, &ovf, &tc);
+      if (occ) st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(0.0f));
+    }
+  }
+  if (COUNT) {
+    atomicAdd(&counters[0], tc.nodes);
+    atomicAdd(&counters[1], tc.tris);
+  }
+  if (ovf) *overflow = 1;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_raygen(const DScene* __restrict__ Sp, WaveState W, Queues Q, const int* __restrict__ pixlist,
+                                                           uint32_t c0, uint32_t npix, int s0, uint32_t ns) {
+  const DScene& S = *Sp;
+  const uint32_t total = npix * ns;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t slot = i % npix, s = i / npix;
+    int pk = pixlist[c0 + slot];
+    int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
+    raygen_body<NC>(S, W, Q, i, px, py, s0 + (int)s);
+  }
+}
+// explicit (pixel, sample number) list: pt_li / pt_camera_rays
+template <int NC>
+__global__ void k_raygen_list(const DScene* __restrict__ Sp, WaveState W, Queues Q, const int* __restrict__ pixel_xy, const int* __restrict__ sample_num,
+                              uint32_t n) {
+  const DScene& S = *Sp;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    raygen_body<NC>(S, W, Q, i, pixel_xy[2 * i], pixel_xy[2 * i + 1], sample_num[i]);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_shade(const DScene* __restrict__ Sp, WaveState W, Queues Q, uint32_t n_ext, unsigned long long* vertex_counter) {
+  const DScene& S = *Sp;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_ext; k += gridDim.x * blockDim.x) shade_body<NC>(S, W, Q, Q.ext[k], vertex_counter);
+}
+
+template <int NC>
+__global__ void k_finish(const DScene* __restrict__ Sp, WaveState W, uint32_t n) {
+  const DScene& S = *Sp;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) finish_body<NC>(S, W, i);
+}
+
+__global__ void k_set_slots(const int* __restrict__ pixlist, uint32_t c0, uint32_t npix, int sbw, int* slot_of, int clear) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+    int pk = pixlist[c0 + i];
+    slot_of[(pk >> 16) * sbw + (pk & 0xffff)] = clear ? -1 : (int)i;
+  }
+}
+
+template <int NC>
+__global__ void k_film(const DScene* __restrict__ Sp, WaveState W, const int* __restrict__ slot_of, uint32_t npix, uint32_t ns, int x0, int y0, int x1, int y1,
+                       f4* film) {
+  const DScene& S = *Sp;
+  int w = x1 - x0, h = y1 - y0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x)
+    film_gather_body<NC>(S, W, slot_of, npix, ns, x0 + i % w, y0 + i / w, film);
+}
+
+__global__ void k_film_resolve(const DScene* __restrict__ Sp, const f4* film, float* rgb, uint32_t n) {
+  const DScene& S = *Sp;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) film_resolve_body(S.film, film[i], rgb + 3 * (size_t)i);
+}
+
+// ---- stage entry points ----------------------------------------------------------------------------------------
+template <bool INST, bool COUNT>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_intersect(const DScene* __restrict__ Sp, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
+                                                              f4* hits, float* t_out, unsigned long long* counters, int* overflow) {
+  __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
+  const DScene& S = *Sp;
+  SharedStack st;
+  st.sm = smem + threadIdx.x;
+  TravCounters tc;
+  tc.nodes = 0; tc.tris = 0;
+  int ovf = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    st.n = 0;
+    f4 o = ro[i], d = rd[i];
+    float tmax = o.w;
+    HitD h;
+    bool found = scene_intersect<INST, COUNT>(S, xyz(o), xyz(d), d.w, tmax, &h, st, &ovf, &tc);
+    hits[i] = mk4(h.b0, h.b1, h.b2, bitsf((uint32_t)(found ? h.tri : -1)));
+    if (t_out) t_out[i] = found ? h.t : 0.0f;
+  }
+  if (COUNT) {
+    atomicAdd(&counters[0], tc.nodes);
+    atomicAdd(&counters[1], tc.tris);
+  }
+  if (ovf) *overflow = 1;
+}
+template <bool INST>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_intersect_p(const DScene* __restrict__ Sp, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
+                                                                unsigned char* occ, int* overflow) {
+  __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
+  const DScene& S = *Sp;
+  SharedStack st;
+  st.sm = smem + threadIdx.x;
+  TravCounters tc;
+  int ovf = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    st.n = 0;
+    f4 o = ro[i], d = rd[i];
+    occ[i] = scene_intersect_p<INST, false>(S, xyz(o), xyz(d), d.w, o.w, st, &ovf, &tc) ? 1 : 0;
+  }
+  if (ovf) *overflow = 1;
+}
+
+__global__ void k_sampler_values(const DScene* __restrict__ Sp, const int* pixel_xy, const int* sample_num, uint32_t n, uint32_t dim0, uint32_t ndims, float* out) {
+  const DScene& S = *Sp;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * ndims; i += gridDim.x * blockDim.x) {
+    uint32_t s = i / ndims, k = i % ndims;
+    int px = pixel_xy[2 * s], py = pixel_xy[2 * s + 1];
+    long long idx = sampler_index(S, px, py, sample_num[s]);
+    out[i] = sampler_dim(S, idx, dim0 + k, px, py);
+  }
+}
+
+// ---- SpatialLightDistribution::compute_distribution for every voxel (spatial.rs:113-197) ---------------------------
+template <int NC>
+__global__ void k_voxel_contrib(const DScene* __restrict__ Sp, float* func, uint32_t n_vox) {
+  const DScene& S = *Sp;
+  const uint32_t nl = S.n_lights;
+  const LightDistDev& D = S.ld;
+  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < (size_t)n_vox * nl; id += (size_t)gridDim.x * blockDim.x) {
+    uint32_t vox = (uint32_t)(id / nl), j = (uint32_t)(id % nl);
+    uint32_t pz = vox % D.voxels[2], py = (vox / D.voxels[2]) % D.voxels[1], px = vox / (D.voxels[2] * D.voxels[1]);
+    const uint32_t pi[3] = {px, py, pz};
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+      float t0 = (float)pi[a] / (float)D.voxels[a], t1 = (float)(pi[a] + 1) / (float)D.voxels[a];
+      float a0 = lerpf(t0, D.wb_min[a], D.wb_max[a]), a1 = lerpf(t1, D.wb_min[a], D.wb_max[a]);
+      lo[a] = a0 <= a1 ? a0 : a1;  // Bounds3f::new
+      hi[a] = a0 >= a1 ? a0 : a1;
+    }
+    float contrib = 0.0f;
+    for (uint32_t i = 0; i < 128; i++) {
+      float tx = radical_inverse2(i), ty = radical_inverse_base(3u, i), tz = radical_inverse_base(5u, i);
+      RefPt it;
+      it.p = mk3(lerpf(tx, lo[0], hi[0]), lerpf(ty, lo[1], hi[1]), lerpf(tz, lo[2], hi[2]));
+      it.perr = mk3(0.0f, 0.0f, 0.0f);
+      it.n = mk3(0.0f, 0.0f, 0.0f);
+      f2 u = mk2(radical_inverse_base(7u, i), radical_inverse_base(11u, i));
+      LightSampleD<NC> ls;
+      if (light_sample<NC>(S, (int)j, it, u, &ls))
+        if (ls.pdf > 0.0f) contrib += sp_y(S, ls.li) / ls.pdf;
+    }
+    func[id] = contrib;
+  }
+}
+// per voxel: floor at 0.1 % of the mean, then Distribution1D::new (distribution.rs:35-62)
+__global__ void k_voxel_cdf(uint32_t nl, uint32_t n_vox, float* func, float* cdf, float* func_int) {
+  for (uint32_t vox = blockIdx.x * blockDim.x + threadIdx.x; vox < n_vox; vox += gridDim.x * blockDim.x) {
+    float* f = func + (size_t)vox * nl;
+    float* c = cdf + (size_t)vox * (nl + 1);
+    float sum = 0.0f;
+    for (uint32_t j = 0; j < nl; j++) sum += f[j];
+    float avg = sum / (float)(128u * nl);
+    float mn = avg > 0.0f ? 0.001f * avg : 1.0f;
+    for (uint32_t j = 0; j < nl; j++) f[j] = fmaxf(mn, f[j]);
+    c[0] = 0.0f;
+    for (uint32_t j = 1; j < nl + 1; j++) c[j] = c[j - 1] + f[j - 1] / (float)nl;
+    float fi = c[nl];
+    if (fi == 0.0f) { for (uint32_t j = 1; j < nl + 1; j++) c[j] = (float)j / (float)nl; }
+    else { for (uint32_t j = 1; j < nl + 1; j++) c[j] /= fi; }
+    func_int[vox] = fi;
+  }
+}
+
+}  // namespace ptd

@@ -1,0 +1,316 @@
+// bvh_build.cpp — see bvh_build.h.  Reference: src/accelerators/bvh/build/node.rs:27-151, build/sah.rs:31-170,
+// build/equal_counts.rs:6-30, build/middle.rs:10-44, accel/qbvh/qbvh_x86.rs:93-176.
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace pth {
+namespace {
+
+struct Info {
+  uint32_t number;
+  BBox b;
+  float c[3];
+};
+
+// Bounds3f helpers with the reference's PartialOrd min_/max_ (bounds3.rs:38-44)
+inline float mn_(float a, float b) { return a <= b ? a : b; }
+inline float mx_(float a, float b) { return a >= b ? a : b; }
+inline BBox b_union(const BBox& a, const BBox& b) {
+  BBox r;
+  for (int i = 0; i < 3; i++) { r.mn[i] = mn_(a.mn[i], b.mn[i]); r.mx[i] = mx_(a.mx[i], b.mx[i]); }
+  return r;
+}
+inline BBox b_empty() {  // Bounds3f::default (bounds3.rs:224-231)
+  BBox r;
+  for (int i = 0; i < 3; i++) { r.mn[i] = FLT_MAX; r.mx[i] = -FLT_MAX; }
+  return r;
+}
+inline float b_area(const BBox& b) {
+  float dx = b.mx[0] - b.mn[0], dy = b.mx[1] - b.mn[1], dz = b.mx[2] - b.mn[2];
+  return 2.0f * (dx * dy + dx * dz + dy * dz);
+}
+inline int b_max_extent(const float mn[3], const float mx[3]) {
+  float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+  if (dx > dy && dx > dz) return 0;
+  if (dy > dz) return 1;
+  return 2;
+}
+
+struct Ctx {
+  BvhResult* out;
+  size_t max_prims;
+  int split;
+  std::vector<Info> scratch;
+
+  int32_t leaf(const Info* pi, size_t n, const BBox& b) {
+    BuildNodeH nd;
+    nd.bounds = b;
+    nd.child[0] = nd.child[1] = -1;
+    nd.axis = 0;
+    nd.first = (uint32_t)out->ordered.size();
+    nd.n = (uint32_t)n;
+    for (size_t i = 0; i < n; i++) out->ordered.push_back(pi[i].number);
+    out->tree.push_back(nd);
+    return (int32_t)out->tree.size() - 1;
+  }
+  // children must be created first-then-second (the ordered list is appended in build order);
+  // the interior node is reserved BEFORE so that the root is node 0
+  int32_t reserve() {
+    out->tree.emplace_back();
+    return (int32_t)out->tree.size() - 1;
+  }
+  void set_interior(int32_t id, int axis, int32_t c0, int32_t c1) {
+    BuildNodeH& nd = out->tree[(size_t)id];
+    nd.bounds = b_union(out->tree[(size_t)c0].bounds, out->tree[(size_t)c1].bounds);
+    nd.child[0] = c0;
+    nd.child[1] = c1;
+    nd.axis = axis;
+    nd.first = 0;
+    nd.n = 0;
+  }
+  static void sort_dim(Info* pi, size_t n, int dim) {
+    std::stable_sort(pi, pi + n, [dim](const Info& a, const Info& b) { return a.c[dim] < b.c[dim]; });
+  }
+  int32_t equal_counts(int dim, Info* pi, size_t n, int32_t self) {
+    sort_dim(pi, n, dim);
+    size_t mid = n / 2;
+    int32_t c0 = build(pi, mid, -1);
+    int32_t c1 = build(pi + mid, n - mid, -1);
+    set_interior(self, dim, c0, c1);
+    return self;
+  }
+  int32_t build(Info* pi, size_t n, int32_t self) {  // recursive_build (node.rs:27-105)
+    BBox bounds = pi[0].b;
+    for (size_t i = 1; i < n; i++) bounds = b_union(bounds, pi[i].b);
+    if (n <= max_prims) return leaf_at(self, pi, n, bounds);
+    float cmn[3] = {pi[0].c[0], pi[0].c[1], pi[0].c[2]}, cmx[3] = {pi[0].c[0], pi[0].c[1], pi[0].c[2]};
+    for (size_t i = 1; i < n; i++)
+      for (int a = 0; a < 3; a++) { cmn[a] = mn_(cmn[a], pi[i].c[a]); cmx[a] = mx_(cmx[a], pi[i].c[a]); }
+    int dim = b_max_extent(cmn, cmx);
+    if (cmn[dim] == cmx[dim]) return leaf_at(self, pi, n, bounds);
+    if (self < 0) self = reserve();
+    if (split == 2) {  // middle.rs
+      float p_mid = (cmn[dim] + cmx[dim]) / 2.0f;
+      sort_dim(pi, n, dim);
+      size_t mid = 0;
+      while (mid < n && !(p_mid <= pi[mid].c[dim])) mid++;
+      if (mid == 0 || mid == n) return equal_counts(dim, pi, n, self);
+      int32_t c0 = build(pi, mid, -1);
+      int32_t c1 = build(pi + mid, n - mid, -1);
+      set_interior(self, dim, c0, c1);
+      return self;
+    }
+    if (split == 3) return equal_counts(dim, pi, n, self);
+    // split_sah (sah.rs:31-170); n >= 3 here unless maxnodeprims < 2
+    if (n == 2) {
+      sort_dim(pi, n, dim);
+      int32_t c0 = build(pi, 1, -1);
+      int32_t c1 = build(pi + 1, 1, -1);
+      set_interior(self, dim, c0, c1);
+      return self;
+    }
+    const int NB = 12;
+    int count[NB];
+    BBox bb[NB];
+    for (int i = 0; i < NB; i++) { count[i] = 0; bb[i] = b_empty(); }
+    const float ext = cmx[dim] - cmn[dim];
+    auto bucket_of = [&](const Info& p) {
+      float o = p.c[dim] - cmn[dim];
+      if (cmx[dim] > cmn[dim]) o = o / ext;
+      float f = floorf((float)NB * o);
+      int b = (f != f) ? 0 : (f >= 2147483648.0f ? INT32_MAX : (f <= -2147483648.0f ? INT32_MIN : (int)f));
+      if (b > NB - 1) b = NB - 1;
+      if (b < 0) b = 0;
+      return b;
+    };
+    for (size_t i = 0; i < n; i++) {
+      int b = bucket_of(pi[i]);
+      count[b]++;
+      bb[b] = b_union(bb[b], pi[i].b);
+    }
+    float cost[NB - 1];
+    const float inv_parent = b_area(bounds);
+    for (int i = 0; i < NB - 1; i++) {
+      int c0 = 0, c1 = 0;
+      BBox b0 = bb[i], b1 = bb[i + 1];
+      for (int j = 0; j <= i; j++) { b0 = b_union(b0, bb[j]); c0 += count[j]; }
+      for (int j = i + 1; j < NB; j++) { b1 = b_union(b1, bb[j]); c1 += count[j]; }
+      cost[i] = 1.0f + ((float)c0 * b_area(b0) + (float)c1 * b_area(b1)) / inv_parent;
+    }
+    float min_cost = cost[0];
+    int min_b = 0;
+    for (int i = 1; i < NB - 1; i++)
+      if (cost[i] < min_cost) { min_cost = cost[i]; min_b = i; }
+    float leaf_cost = (float)n;
+    if (n > max_prims || min_cost < leaf_cost) {
+      // order-preserving partition (Iterator::partition), in place via a scratch copy of the right side
+      size_t nl = 0;
+      scratch.clear();
+      for (size_t i = 0; i < n; i++) {
+        if (bucket_of(pi[i]) <= min_b) pi[nl++] = pi[i];
+        else scratch.push_back(pi[i]);
+      }
+      if (nl == 0 || nl == n) {
+        // nothing moved (one side empty): the slice is still in its original order
+        if (nl == 0) std::copy(scratch.begin(), scratch.end(), pi);
+        return equal_counts(dim, pi, n, self);
+      }
+      std::copy(scratch.begin(), scratch.end(), pi + nl);
+      int32_t c0 = build(pi, nl, -1);
+      int32_t c1 = build(pi + nl, n - nl, -1);
+      set_interior(self, dim, c0, c1);
+      return self;
+    }
+    // leaf at a reserved slot
+    BuildNodeH& nd = out->tree[(size_t)self];
+    nd.bounds = bounds;
+    nd.child[0] = nd.child[1] = -1;
+    nd.axis = 0;
+    nd.first = (uint32_t)out->ordered.size();
+    nd.n = (uint32_t)n;
+    for (size_t i = 0; i < n; i++) out->ordered.push_back(pi[i].number);
+    return self;
+  }
+  int32_t leaf_at(int32_t self, const Info* pi, size_t n, const BBox& b) {
+    if (self < 0) return leaf(pi, n, b);
+    BuildNodeH& nd = out->tree[(size_t)self];
+    nd.bounds = b;
+    nd.child[0] = nd.child[1] = -1;
+    nd.axis = 0;
+    nd.first = (uint32_t)out->ordered.size();
+    nd.n = (uint32_t)n;
+    for (size_t i = 0; i < n; i++) out->ordered.push_back(pi[i].number);
+    return self;
+  }
+};
+
+const int32_t kEmpty = (int32_t)0x80000000;
+const uint32_t kLeafBits = 3;
+
+struct Flat {
+  const BvhResult* r;
+  std::vector<GpuNodeH>* nodes;
+  uint32_t depth = 0;
+
+  // reference to a build node from its parent: inline leaf when it fits, otherwise a node index
+  int32_t ref(int32_t b, uint32_t d) {
+    const BuildNodeH& n = r->tree[(size_t)b];
+    if (n.n > 0 && n.n <= (1u << kLeafBits) && n.first < (1u << (31 - kLeafBits - 1))) {
+      if (d + 1 > depth) depth = d + 1;
+      return ~(int32_t)((n.first << kLeafBits) | (n.n - 1));
+    }
+    return emit(b, d + 1);
+  }
+  int32_t emit(int32_t b, uint32_t d) {
+    if (d > depth) depth = d;
+    size_t off = nodes->size();
+    nodes->emplace_back();
+    memset(&(*nodes)[off], 0, sizeof(GpuNodeH));
+    const BuildNodeH& n = r->tree[(size_t)b];
+    if (n.n > 0) {  // leaf node kept in the reference's form (root leaf, or more than 8 primitives)
+      GpuNodeH& g = (*nodes)[off];
+      g.meta[0] = 0x100;
+      g.meta[1] = (int32_t)n.first;
+      g.meta[2] = (int32_t)n.n;
+      for (int k = 0; k < 4; k++) g.child[k] = kEmpty;
+      return (int32_t)off;
+    }
+    int32_t idx[4] = {kEmpty, kEmpty, kEmpty, kEmpty};
+    BBox box[4];
+    memset(box, 0, sizeof(box));  // empty lanes keep a zero box (qbvh_x86.rs:69-74,101)
+    const BuildNodeH& c0 = r->tree[(size_t)n.child[0]];
+    const BuildNodeH& c1 = r->tree[(size_t)n.child[1]];
+    int32_t kids[4] = {-1, -1, -1, -1};
+    if (c0.n > 0) kids[0] = n.child[0]; else { kids[0] = c0.child[0]; kids[1] = c0.child[1]; }
+    if (c1.n > 0) kids[2] = n.child[1]; else { kids[2] = c1.child[0]; kids[3] = c1.child[1]; }
+    for (int k = 0; k < 4; k++)
+      if (kids[k] >= 0) {
+        box[k] = r->tree[(size_t)kids[k]].bounds;
+        idx[k] = ref(kids[k], d);
+      }
+    GpuNodeH& g = (*nodes)[off];
+    for (int a = 0; a < 3; a++)
+      for (int k = 0; k < 4; k++) { g.lo[a][k] = box[k].mn[a]; g.hi[a][k] = box[k].mx[a]; }
+    for (int k = 0; k < 4; k++) g.child[k] = idx[k];
+    g.meta[0] = (n.axis & 3) | ((c0.axis & 3) << 2) | ((c1.axis & 3) << 4);
+    return (int32_t)off;
+  }
+};
+
+size_t ref_flatten(const BvhResult& r, int32_t b, std::vector<RefNodeH>* out) {
+  size_t off = out->size();
+  out->emplace_back();
+  memset(&(*out)[off], 0, sizeof(RefNodeH));
+  const BuildNodeH& n = r.tree[(size_t)b];
+  if (n.n > 0) {
+    (*out)[off].is_leaf = 1;
+    (*out)[off].children[0] = n.first;
+    (*out)[off].children[1] = n.n;
+    return off;
+  }
+  const BuildNodeH& c0 = r.tree[(size_t)n.child[0]];
+  const BuildNodeH& c1 = r.tree[(size_t)n.child[1]];
+  int32_t kids[4] = {-1, -1, -1, -1};
+  if (c0.n > 0) kids[0] = n.child[0]; else { kids[0] = c0.child[0]; kids[1] = c0.child[1]; }
+  if (c1.n > 0) kids[2] = n.child[1]; else { kids[2] = c1.child[0]; kids[3] = c1.child[1]; }
+  int64_t idx[4];
+  for (int k = 0; k < 4; k++) idx[k] = kids[k] >= 0 ? (int64_t)ref_flatten(r, kids[k], out) : -1;
+  RefNodeH& q = (*out)[off];
+  for (int k = 0; k < 4; k++) {
+    q.children[k] = idx[k];
+    if (kids[k] >= 0) {
+      const BBox& bx = r.tree[(size_t)kids[k]].bounds;
+      for (int a = 0; a < 3; a++) { q.bboxes[0][a][k] = bx.mn[a]; q.bboxes[1][a][k] = bx.mx[a]; }
+    }
+  }
+  q.axes[0] = n.axis; q.axes[1] = c0.axis; q.axes[2] = c1.axis;
+  return off;
+}
+
+}  // namespace
+
+void build_bvh(const std::vector<BBox>& prim_bounds, int max_prims_in_node, int split_method, BvhResult* out) {
+  out->tree.clear();
+  out->ordered.clear();
+  out->nodes.clear();
+  size_t n = prim_bounds.size();
+  if (n == 0) { out->bounds = b_empty(); return; }
+  const float BOUND_EPS = FLT_EPSILON * 2.0f;  // node.rs:13
+  std::vector<Info> info(n);
+  for (size_t i = 0; i < n; i++) {
+    Info& f = info[i];
+    f.number = (uint32_t)i;
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; a++) { mn[a] = prim_bounds[i].mn[a] - BOUND_EPS; mx[a] = prim_bounds[i].mx[a] + BOUND_EPS; }
+    for (int a = 0; a < 3; a++) { f.b.mn[a] = mn_(mn[a], mx[a]); f.b.mx[a] = mx_(mn[a], mx[a]); }
+    for (int a = 0; a < 3; a++) f.c[a] = (f.b.mn[a] + f.b.mx[a]) * 0.5f;
+  }
+  Ctx c;
+  c.out = out;
+  c.max_prims = (size_t)std::min(std::max(max_prims_in_node, 0), 255);
+  c.split = split_method;
+  out->tree.reserve(n);
+  out->ordered.reserve(n);
+  int32_t root = c.build(info.data(), n, c.reserve());
+  (void)root;
+  out->bounds = out->tree[0].bounds;
+  Flat f;
+  f.r = out;
+  f.nodes = &out->nodes;
+  f.emit(0, 1);
+  out->qdepth = f.depth;
+  // node count of the reference's flattening = one per reachable build node after the 2-level collapse
+  std::vector<RefNodeH> tmp;
+  out->n_ref_nodes = 0;
+}
+
+void flatten_reference(const BvhResult& r, std::vector<RefNodeH>* out) {
+  out->clear();
+  if (!r.tree.empty()) ref_flatten(r, 0, out);
+}
+
+}  // namespace pth
