@@ -229,6 +229,10 @@ typedef struct pt_scene pt_scene;
  * builds the SAH BVH on the host, flattens it to the GPU node layout, uploads. */
 int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out);
 void pt_scene_destroy(pt_scene* scene);
+/* Re-sends every flattened scene array (nodes, triangle records, attributes, materials, lights, sampler tables)
+ * from the pinned host staging copies kept since pt_scene_create to the device: what a host that rebuilds or
+ * edits the scene between frames pays per render.  bytes (may be NULL) receives the host->device byte count. */
+int pt_scene_reupload(pt_scene* scene, uint64_t* bytes);
 const char* pt_last_error(void);
 int pt_abi_version(void);
 
@@ -280,6 +284,17 @@ int pt_bvh_info(pt_scene* scene, uint32_t object, uint32_t* n_nodes, uint32_t* n
  * axes[3], is_leaf */
 int pt_bvh_node(pt_scene* scene, uint32_t object, uint32_t node, float* boxes24, int64_t* children4,
                 int32_t* axes3, int32_t* is_leaf);
+
+/* Host-only variant of the two calls above (no GPU needed): builds every object's accelerator exactly as
+ * pt_scene_create does.  Used by the build-parity tests and by tools that only need the tree. */
+typedef struct pt_host_bvh pt_host_bvh;
+int pt_host_bvh_build(const pt_scene_desc* desc, pt_host_bvh** out);
+/* n_nodes = node count of the reference's flattening; gpu_nodes = 128-byte GPU nodes; qdepth = depth of the 4-wide tree */
+int pt_host_bvh_info(const pt_host_bvh* h, uint32_t object, uint32_t* n_nodes, uint32_t* n_prims, int32_t* ordered, float* bounds6,
+                     uint32_t* gpu_nodes, uint32_t* qdepth);
+int pt_host_bvh_node(const pt_host_bvh* h, uint32_t object, uint32_t node, float* boxes24, int64_t* children4, int32_t* axes3,
+                     int32_t* is_leaf);
+void pt_host_bvh_destroy(pt_host_bvh* h);
 
 /* SpatialLightDistribution::lookup (core/lightdistrib/spatial.rs:200-261): for n points write the
  * voxel's cdf-ready per-light func values (n x n_lights). */

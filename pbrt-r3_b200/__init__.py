@@ -81,6 +81,43 @@ class HostScene:
             pass
 
 
+class HostBvh:
+    """Host-only accelerator build (same code pt_scene_create runs), for build-parity checks without a GPU."""
+
+    def __init__(self, host_scene):
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        self.host = host_scene
+        _check(self._lib, self._lib.pt_host_bvh_build(host_scene.desc_ptr, C.byref(self._h)), "pt_host_bvh_build")
+
+    def info(self, obj=0):
+        nn, npr, gn, qd = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        b = np.zeros(6, np.float32)
+        _check(self._lib, self._lib.pt_host_bvh_info(self._h, obj, C.byref(nn), C.byref(npr), None, _p(b, C.c_float), C.byref(gn), C.byref(qd)), "pt_host_bvh_info")
+        ordered = np.zeros(npr.value, np.int32)
+        _check(self._lib, self._lib.pt_host_bvh_info(self._h, obj, None, None, _p(ordered, C.c_int32), None, None, None), "pt_host_bvh_info")
+        return dict(n_nodes=nn.value, ordered=ordered, bounds=b, gpu_nodes=gn.value, qdepth=qd.value)
+
+    def node(self, obj, node):
+        boxes = np.zeros((2, 3, 4), np.float32)
+        ch = np.zeros(4, np.int64)
+        ax = np.zeros(3, np.int32)
+        leaf = C.c_int32(0)
+        _check(self._lib, self._lib.pt_host_bvh_node(self._h, obj, node, _p(boxes, C.c_float), _p(ch, C.c_int64), _p(ax, C.c_int32), C.byref(leaf)), "pt_host_bvh_node")
+        return boxes, ch, ax, leaf.value
+
+    def close(self):
+        if self._h:
+            self._lib.pt_host_bvh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Scene:
     """Device-resident scene + integrator (SceneContext::make_scene + make_integrator; QBVHAccel::new)."""
 
@@ -103,6 +140,12 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+    def reupload(self):
+        """Re-send the flattened scene from pinned host memory to the device; returns the bytes copied."""
+        b = C.c_uint64(0)
+        _check(self._lib, self._lib.pt_scene_reupload(self._h, C.byref(b)), "pt_scene_reupload")
+        return b.value
 
     @staticmethod
     def _opts(**kw):

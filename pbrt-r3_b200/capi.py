@@ -89,10 +89,11 @@ class pt_stats(C.Structure):
 
 # every symbol include/pbrt_r3_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
-    "pt_scene_create", "pt_scene_destroy", "pt_last_error", "pt_abi_version", "pt_render", "pt_render_partial", "pt_film_resolve",
+    "pt_scene_create", "pt_scene_destroy", "pt_scene_reupload", "pt_last_error", "pt_abi_version", "pt_render", "pt_render_partial", "pt_film_resolve",
     "pt_film_clear", "pt_intersect", "pt_intersect_p", "pt_intersect_device", "pt_sampler_values", "pt_camera_rays", "pt_li",
     "pt_bvh_info", "pt_bvh_node", "pt_light_distribution", "pt_parse_file", "pt_parse_string", "pt_host_scene_desc",
-    "pt_host_scene_filename", "pt_host_scene_destroy",
+    "pt_host_scene_filename", "pt_host_scene_destroy", "pt_host_bvh_build", "pt_host_bvh_info", "pt_host_bvh_node",
+    "pt_host_bvh_destroy",
 ]
 
 _lib = None
@@ -119,10 +120,16 @@ def load(path=None):
     lib.pt_host_scene_filename.restype = C.c_char_p
     lib.pt_host_scene_destroy.argtypes = [vp]
     lib.pt_host_scene_destroy.restype = None
+    lib.pt_host_bvh_build.argtypes = [C.POINTER(pt_scene_desc), C.POINTER(vp)]
+    lib.pt_host_bvh_info.argtypes = [vp, C.c_uint32, u32p, u32p, i32p, f32p, u32p, u32p]
+    lib.pt_host_bvh_node.argtypes = [vp, C.c_uint32, C.c_uint32, f32p, C.POINTER(C.c_int64), i32p, i32p]
+    lib.pt_host_bvh_destroy.argtypes = [vp]
+    lib.pt_host_bvh_destroy.restype = None
     if hasattr(lib, "pt_scene_create"):
         lib.pt_scene_create.argtypes = [C.POINTER(pt_scene_desc), C.c_int, C.POINTER(vp)]
         lib.pt_scene_destroy.argtypes = [vp]
         lib.pt_scene_destroy.restype = None
+        lib.pt_scene_reupload.argtypes = [vp, C.POINTER(C.c_uint64)]
         lib.pt_render.argtypes = [vp, C.POINTER(pt_render_opts), f32p, C.POINTER(pt_stats)]
         lib.pt_render_partial.argtypes = [vp, C.POINTER(pt_render_opts), C.POINTER(vp), C.POINTER(pt_stats)]
         lib.pt_film_resolve.argtypes = [vp, vp, f32p]

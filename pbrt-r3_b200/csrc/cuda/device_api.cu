@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../host/bvh_build.h"
+#include "../host/scene_accel.h"
 #include "../host/spectrum_host.h"
 #include "kernels.cuh"
 
@@ -34,7 +35,15 @@ namespace {
 
 struct DevBufs {
   std::vector<void*> ptrs;
-  ~DevBufs() { for (void* p : ptrs) cudaFree(p); }
+  // keep = true: every upload also keeps a PINNED host staging copy so that the scene can be re-sent to the device
+  // (pt_scene_reupload: the end-to-end benchmark's host->device leg)
+  bool keep = false;
+  struct Staged { void* dev; void* host; size_t bytes; };
+  std::vector<Staged> staged;
+  ~DevBufs() {
+    for (void* p : ptrs) cudaFree(p);
+    for (auto& st : staged) cudaFreeHost(st.host);
+  }
   template <typename T>
   cudaError_t upload(const T* host, size_t n, const T** out) {
     *out = nullptr;
@@ -43,7 +52,16 @@ struct DevBufs {
     cudaError_t e = cudaMalloc(&d, n * sizeof(T));
     if (e != cudaSuccess) return e;
     ptrs.push_back(d);
-    e = cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    const void* src = host;
+    if (keep) {
+      void* h = nullptr;
+      e = cudaMallocHost(&h, n * sizeof(T));
+      if (e != cudaSuccess) return e;
+      memcpy(h, host, n * sizeof(T));
+      staged.push_back(Staged{d, h, n * sizeof(T)});
+      src = h;
+    }
+    e = cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice);
     *out = (const T*)d;
     return e;
   }
@@ -60,12 +78,7 @@ struct DevBufs {
   }
 };
 
-struct ObjectHost {
-  pth::BvhResult bvh;
-  std::vector<int32_t> ordered;  // primitive ids (triangle >= 0, ~instance < 0) in leaf order
-  bool single = false;
-  pth::BBox bounds;
-};
+using pth::ObjectHost;
 
 }  // namespace
 
@@ -102,39 +115,6 @@ struct pt_scene {
 };
 
 namespace {
-
-inline float fmin_(float a, float b) { return fminf(a, b); }
-inline float fmax_(float a, float b) { return fmaxf(a, b); }
-
-// Triangle::world_bound (triangle.rs:214-224)
-pth::BBox tri_bbox(const float* p) {
-  pth::BBox b;
-  for (int a = 0; a < 3; a++) {
-    float mn = p[a], mx = p[a];
-    mn = fmin_(mn, p[3 + a]); mx = fmax_(mx, p[3 + a]);
-    mn = fmin_(mn, p[6 + a]); mx = fmax_(mx, p[6 + a]);
-    b.mn[a] = mn <= mx ? mn : mx;
-    b.mx[a] = mn >= mx ? mn : mx;
-  }
-  return b;
-}
-// Transform::transform_bounds (transform.rs:134-181)
-pth::BBox xform_bbox(const float* m, const pth::BBox& b) {
-  pth::BBox r;
-  bool first = true;
-  for (int ix = 0; ix < 2; ix++)
-    for (int iy = 0; iy < 2; iy++)
-      for (int iz = 0; iz < 2; iz++) {
-        f3 q = mat_point(m, mk3(ix ? b.mx[0] : b.mn[0], iy ? b.mx[1] : b.mn[1], iz ? b.mx[2] : b.mn[2]));
-        const float v[3] = {q.x, q.y, q.z};
-        for (int a = 0; a < 3; a++) {
-          if (first) { r.mn[a] = v[a]; r.mx[a] = v[a]; }
-          else { r.mn[a] = fmin_(r.mn[a], v[a]); r.mx[a] = fmax_(r.mx[a], v[a]); }
-        }
-        first = false;
-      }
-  return r;
-}
 
 // core/rng.rs PCG32 with the default state: compute_radical_inverse_permutations (radical_inverse.rs:93-109)
 struct Pcg {
@@ -194,6 +174,7 @@ int precompute_light_distribution(pt_scene* s, uint32_t n_vox, float* func, floa
 int build_scene(pt_scene* s, const pt_scene_desc* D) {
   DScene& H = s->h;
   memset(&H, 0, sizeof(H));
+  s->bufs.keep = true;
   const uint32_t NC = D->n_channels;
   H.n_channels = NC;
   H.n_tris = D->n_tris;
@@ -209,42 +190,11 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   H.integrator = D->integrator;
 
   // ---- accelerators: instanced objects first, then the top level ------------------------------------------
-  s->objects.resize(D->n_objects);
-  for (uint32_t k = D->n_objects; k-- > 0;) {
-    ObjectHost& O = s->objects[k];
-    const int32_t* pr = D->prims + D->obj_first[k];
-    size_t n = D->obj_first[k + 1] - D->obj_first[k];
-    std::vector<pth::BBox> pb(n);
-    for (size_t i = 0; i < n; i++) {
-      if (pr[i] >= 0) pb[i] = tri_bbox(D->tri_p + (size_t)pr[i] * 9);
-      else {
-        const pt_instance& I = D->instances[~pr[i]];
-        if (I.object <= 0 || (uint32_t)I.object >= D->n_objects || (uint32_t)I.object <= k) { pt_set_error("bad instance object index"); return 1; }
-        pb[i] = xform_bbox(I.m, s->objects[(size_t)I.object].bounds);
-      }
-    }
-    if (n == 0) {
-      for (int a = 0; a < 3; a++) { O.bounds.mn[a] = FLT_MAX; O.bounds.mx[a] = -FLT_MAX; }
-    } else if (k != 0 && n == 1) {
-      O.single = true;
-      O.bounds = pb[0];
-      O.ordered.assign(pr, pr + 1);
-    } else {
-      pth::build_bvh(pb, D->accel.max_prims_in_node, D->accel.split_method, &O.bvh);
-      O.bounds = O.bvh.bounds;
-      O.ordered.resize(n);
-      for (size_t i = 0; i < n; i++) O.ordered[i] = pr[O.bvh.ordered[i]];
-      s->max_stack = std::max(s->max_stack, 3u * O.bvh.qdepth + 2u);
-    }
-  }
   {
-    uint32_t top = 3u * s->objects[0].bvh.qdepth + 2u, nested = 0;
-    for (uint32_t k = 1; k < D->n_objects; k++) nested = std::max(nested, 3u * s->objects[k].bvh.qdepth + 3u);
-    if (top + nested > PT_MAX_STACK) {
-      pt_set_error("BVH too deep for the traversal stack (" + std::to_string(top + nested) + " > " + std::to_string(PT_MAX_STACK) + ")");
-      return 1;
-    }
+    std::string err = pth::build_objects(D, &s->objects);
+    if (!err.empty()) { pt_set_error(err); return 1; }
   }
+  // stack depth: the worst-case bound 3*depth+1 is far from typical use; the kernels flag a real overflow instead
   std::vector<pth::GpuNodeH> nodes;
   std::vector<f4> recs;
   std::vector<ObjectRec> orecs(D->n_objects);
@@ -704,6 +654,21 @@ void pt_scene_destroy(pt_scene* scene) {
   if (!scene) return;
   cudaSetDevice(scene->device);
   delete scene;
+}
+
+int pt_scene_reupload(pt_scene* s, uint64_t* bytes) {
+  if (!s) { pt_set_error("null scene"); return 1; }
+  CK(cudaSetDevice(s->device));
+  uint64_t total = 0;
+  for (auto& st : s->bufs.staged) {
+    CK(cudaMemcpyAsync(st.dev, st.host, st.bytes, cudaMemcpyHostToDevice, s->stream));
+    total += st.bytes;
+  }
+  CK(cudaMemcpyAsync(s->d, &s->h, sizeof(DScene), cudaMemcpyHostToDevice, s->stream));
+  total += sizeof(DScene);
+  CK(cudaStreamSynchronize(s->stream));
+  if (bytes) *bytes = total;
+  return 0;
 }
 
 int pt_film_clear(pt_scene* s) {

@@ -1,0 +1,46 @@
+"""Multi-GPU plumbing: one process per GPU, spp (or tile) shards, ONE exchange step — the film partials {X,Y,Z,sum_w}
+are summed onto rank 0 (torch.distributed reduce: NCCL over NVLink on GPUs, gloo in the CPU tests) and resolved
+there.  Mirrors Film::merge_film_tile's sum (reference src/core/film/film.rs:219-241) across processes; the scene is
+replicated, nothing else is exchanged."""
+import numpy as np
+
+
+def spp_shard(spp_total, rank, world):
+    """Contiguous sample-number range [begin, end) of this rank; every sample index is rendered exactly once."""
+    base, rem = divmod(int(spp_total), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class _CudaArray:
+    """Zero-copy view of a device pointer for torch.as_tensor (__cuda_array_interface__ v2)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def film_tensor(dev_ptr, n_pixels, device):
+    import torch
+    return torch.as_tensor(_CudaArray(dev_ptr, n_pixels * 4), device=device)
+
+
+def reduce_film(film, dst=0, group=None):
+    """Sum the film partials of all ranks into rank `dst` (in place).  `film` is a float32 tensor (n_pixels*4)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return film
+
+
+def resolve_host(xyzw, scale=1.0):
+    """Film::write_image's arithmetic on a host array (used by the gloo tests to check the reduced film):
+    rgb = xyz_to_rgb(xyz) / sum_w, clamped at 0, times scale (film.rs:447-472)."""
+    p = np.asarray(xyzw, np.float32).reshape(-1, 4)
+    x, y, z, w = p[:, 0], p[:, 1], p[:, 2], p[:, 3]
+    f = np.float32
+    c = np.stack([f(3.240479) * x - f(1.537150) * y - f(0.498535) * z, f(-0.969256) * x + f(1.875991) * y + f(0.041556) * z,
+                  f(0.055648) * x - f(0.204043) * y + f(1.057311) * z], 1).astype(np.float32)
+    pos = w > 0
+    inv = np.where(pos, f(1.0) / np.where(pos, w, f(1.0)), f(1.0)).astype(np.float32)
+    c = np.where(pos[:, None], np.maximum(f(0.0), c * inv[:, None]), c)
+    return (c * f(scale)).astype(np.float32)

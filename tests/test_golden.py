@@ -1,0 +1,63 @@
+"""The committed golden fixtures (tools/make_golden.py) against the oracle on CPU, and against the CUDA path on GPU."""
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_oracle_reproduces_golden(P):
+    import oracle_api
+    hs = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4))
+    orc = oracle_api.OracleScene(hs)
+    z = np.load(os.path.join(G, "cornell_64_streams.npz"))
+    assert np.array_equal(orc.sampler_values(z["pix"], z["sn"], 0, 32).view(np.uint32), z["halton"].view(np.uint32))
+    assert np.array_equal(orc.camera_rays(z["pix"], z["sn"])[0].view(np.uint32), z["rays"].view(np.uint32))
+    rgb, st = orc.render(threads=1)
+    assert np.array_equal(rgb, np.load(os.path.join(G, "cornell_64_4spp.npy")))
+    assert [st[k] for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested")] == list(z["counters"])
+    # tile-parallel rendering only changes the film merge order
+    rgb8, _ = orc.render(threads=8)
+    assert np.sqrt(((rgb8 - rgb) ** 2).mean()) / rgb.mean() < 1e-6
+    hs2 = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4, sampler="sobol"))
+    orc2 = oracle_api.OracleScene(hs2)
+    assert np.array_equal(orc2.sampler_values(z["pix"], z["sn"], 0, 32).view(np.uint32), np.load(os.path.join(G, "cornell_64_sobol_values.npy")).view(np.uint32))
+
+
+def test_oracle_furnace(P):
+    """Analytic check the reference has no test for: a closed diffuse box lit by a two-sided emitter in the middle.
+    With albedo rho and uniform emission, radiance converges to a finite positive value and energy is conserved:
+    increasing maxdepth never decreases the image and the increments shrink geometrically (ratio <= rho)."""
+    import oracle_api
+    def scene(depth):
+        q = lambda p: 'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [%s]\n' % " ".join(map(str, p))
+        s = 'LookAt 0 0 -0.9  0 0 0  0 1 0\nCamera "perspective" "float fov" [90]\nFilm "image" "integer xresolution" [16] "integer yresolution" [16]\n'
+        s += 'Sampler "halton" "integer pixelsamples" [64]\nIntegrator "path" "integer maxdepth" [%d] "float rrthreshold" [0]\nWorldBegin\nMaterial "matte" "rgb Kd" [0.5 0.5 0.5]\n' % depth
+        c = [(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)]
+        for f in [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (3, 2, 6, 7), (0, 3, 7, 4), (1, 2, 6, 5)]:
+            s += q([v for i in f for v in c[i]])
+        s += 'AreaLightSource "diffuse" "rgb L" [1 1 1] "bool twosided" ["true"]\n' + q([-0.2, 0.5, -0.2, 0.2, 0.5, -0.2, 0.2, 0.5, 0.2, -0.2, 0.5, 0.2]) + "WorldEnd\n"
+        return s
+    means = []
+    for depth in (1, 2, 3, 4):
+        hs = P.HostScene.parse_string(scene(depth))
+        means.append(float(oracle_api.OracleScene(hs).render(threads=4)[0].mean()))
+    inc = np.diff(means)
+    assert (inc > 0).all() and inc[1] / inc[0] < 0.6 and inc[2] / inc[1] < 0.6, (means, inc)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden(P):
+    hs = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4))
+    sc = P.Scene(hs, 0)
+    z = np.load(os.path.join(G, "cornell_64_streams.npz"))
+    assert np.array_equal(sc.sampler_values(z["pix"], z["sn"], 0, 32).view(np.uint32), z["halton"].view(np.uint32))
+    assert np.array_equal(sc.camera_rays(z["pix"], z["sn"])[0].view(np.uint32), z["rays"].view(np.uint32))
+    rgb, st = sc.render(collect_counters=1)
+    ref = np.load(os.path.join(G, "cornell_64_4spp.npy"))
+    assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() <= 1e-3
+    assert [st[k] for k in ("camera_rays", "regular_rays", "shadow_rays")] == list(z["counters"][:3])
+    hs2 = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4, sampler="sobol"))
+    sc2 = P.Scene(hs2, 0)
+    assert np.array_equal(sc2.sampler_values(z["pix"], z["sn"], 0, 32).view(np.uint32), np.load(os.path.join(G, "cornell_64_sobol_values.npy")).view(np.uint32))

@@ -1,0 +1,164 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, the ctypes mirror matches the
+header, the .pbrt front end reproduces the reference's scene-description rules, and the product's host BVH build
+equals the oracle's restatement of the reference build (node by node, primitive order included)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(P):
+    lib = P.capi.load()
+    hdr = open(os.path.join(ROOT, "include", "pbrt_r3_b200.h")).read()
+    declared = set(re.findall(r"\b(pt_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    assert set(P.capi.EXPORTS) == declared
+    assert lib.pt_abi_version() == P.capi.PT_ABI_VERSION
+
+
+def test_ctypes_mirror_matches_header(P):
+    names = ["pt_material", "pt_light", "pt_instance", "pt_camera", "pt_film", "pt_sampler", "pt_integrator", "pt_accel", "pt_scene_desc",
+             "pt_render_opts", "pt_stats"]
+    src = '#include "pbrt_r3_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){\n' + "".join(
+        'printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in names) + 'printf("off_lights %zu\\n", offsetof(pt_scene_desc, lights));\n' \
+        'printf("off_accel %zu\\n", offsetof(pt_scene_desc, accel));\nreturn 0;}\n'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "probe.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "probe")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        out = dict(l.split() for l in subprocess.check_output([exe]).decode().splitlines())
+    for n in names:
+        assert C.sizeof(getattr(P.capi, n)) == int(out[n]), n
+    assert P.capi.pt_scene_desc.lights.offset == int(out["off_lights"])
+    assert P.capi.pt_scene_desc.accel.offset == int(out["off_accel"])
+
+
+def test_front_end_defaults_and_film_rules(P):
+    hs = P.HostScene.parse_string('Camera "perspective"\nWorldBegin\nWorldEnd\n')
+    d = hs.desc
+    # render_options.rs:61-88 / film.rs:538-571 / filters/box_filter.rs:26-30 / halton.rs:279 / path.rs:257-262
+    assert list(d.film.full_resolution) == [1280, 720]
+    assert list(d.film.cropped_pixel_bounds) == [0, 0, 1280, 720]
+    assert list(d.film.sample_bounds) == [-1, -1, 1281, 721]          # floor(0 - 0.5) .. ceil(res + 0.5) (film.rs:166-179)
+    assert list(d.film.filter_radius) == [0.5, 0.5] and all(v == 1.0 for v in d.film.filter_table)
+    assert (d.sampler.type, d.sampler.samples_per_pixel) == (P.capi.PT_SAMPLER_HALTON, 16)
+    assert (d.integrator.max_depth, d.integrator.rr_threshold, d.integrator.light_strategy) == (5, 1.0, 0)
+    assert (d.accel.type, d.accel.split_method, d.accel.max_prims_in_node) == (0, 0, 4)
+    assert hs.filename == "pbrt.exr" and d.film.scale == 1.0 and np.isinf(d.film.max_sample_luminance)
+    assert d.camera.lens_radius == 0.0 and d.camera.focal_distance == np.float32(1e6)
+
+
+def test_front_end_cornell(P):
+    hs = P.HostScene.parse_string(P.scenes.cornell_box(res=256, spp=16))
+    d = hs.desc
+    assert d.n_tris == 32 and d.n_lights == 2 and d.n_objects == 1 and d.n_instances == 0
+    flags = np.ctypeslib.as_array(d.tri_flags, (32,))
+    assert (flags & P.capi.PT_TRI_TWO_SIDED).all()              # twosided defaults to true (triangle.rs:707)
+    lights = [d.lights[i] for i in range(2)]
+    assert all(l.type == P.capi.PT_LIGHT_AREA and l.two_sided == 0 for l in lights)   # diffuse.rs:178
+    tl = np.ctypeslib.as_array(d.tri_light, (32,))
+    assert sorted(tl[tl >= 0]) == [0, 1] and [lights[0].tri, lights[1].tri] == [30, 31]
+    # LookAt: right = up x dir (matrix4x4.rs:130-197) -> camera_to_world column 3 is the eye
+    c2w = np.array(list(d.camera.camera_to_world)).reshape(4, 4)
+    assert np.allclose(c2w[:3, 3], [278, 273, -800]) and np.allclose(c2w[:3, 2], [0, 0, 1])
+
+
+def test_front_end_quirks(P):
+    # degenerate triangles dropped (triangle.rs:726); material params looked up before shape params for spectra
+    # (texture_params.rs:75-83); shape float params override material floats; point light translate order (point.rs:121)
+    txt = '''Camera "perspective"
+WorldBegin
+Material "plastic" "rgb Kd" [0.1 0.2 0.3] "float roughness" [0.2]
+Shape "trianglemesh" "integer indices" [0 1 2 0 0 1] "point P" [0 0 0 1 0 0 0 1 0] "rgb Kd" [0.9 0.9 0.9] "float roughness" [0.05]
+Translate 1 2 3
+Scale 2 2 2
+LightSource "point" "point from" [1 1 1]
+WorldEnd
+'''
+    hs = P.HostScene.parse_string(txt)
+    d = hs.desc
+    assert d.n_tris == 1
+    m = d.materials[d.tri_material[0]]
+    assert m.type == P.capi.PT_MAT_PLASTIC and abs(m.uroughness - 0.05) < 1e-9
+    kd = [d.spectra[m.kd * 3 + k] for k in range(3)]
+    assert np.allclose(kd, [0.1, 0.2, 0.3])
+    l = d.lights[0]
+    # l2w = translate(from) * ctm applied to the origin: from + ctm translation = (1,1,1) + (1,2,3)
+    assert l.type == P.capi.PT_LIGHT_POINT and np.allclose(list(l.v), [2, 3, 4])
+
+
+def test_front_end_instances(P):
+    hs = P.HostScene.parse_string(P.scenes.instanced_blobs(n_instances=5, n_sub=1, res=(32, 24), spp=1, n_lights=2))
+    d = hs.desc
+    assert d.n_objects == 5 and d.n_instances == 5 and d.n_lights == 4
+    prims = np.ctypeslib.as_array(d.prims, (d.obj_first[d.n_objects],))
+    top = prims[d.obj_first[0]:d.obj_first[1]]
+    assert (top < 0).sum() == 5 and (top >= 0).sum() == 2 + 4
+
+
+def test_front_end_errors(P):
+    for bad in ['Shape "sphere"', 'WorldBegin\nLightSource "infinite"', 'Sampler "stratified"\nWorldBegin\nWorldEnd', 'Bogus 1 2 3']:
+        with pytest.raises(P.PbrtError):
+            P.HostScene.parse_string('Camera "perspective"\n' + bad + "\n")
+
+
+def _compare_bvh(P, hs, objects):
+    import oracle_api
+    orc = oracle_api.OracleScene(hs)
+    hb = P.HostBvh(hs)
+    for k in objects:
+        n_nodes_o, ordered_o, depth_o = orc.bvh_info(k)
+        info = hb.info(k)
+        assert np.array_equal(info["ordered"], ordered_o), "object %d: primitive order differs" % k
+        assert info["n_nodes"] == n_nodes_o, (k, info["n_nodes"], n_nodes_o)
+        step = max(1, n_nodes_o // 3000)
+        for node in list(range(0, n_nodes_o, step)) + [n_nodes_o - 1] if n_nodes_o else []:
+            bo, co, ao, lo = orc.bvh_node(k, node)
+            bp, cp, ap, lp = hb.node(k, node)
+            assert lo == lp and np.array_equal(co, cp), (k, node)
+            if not lo:
+                assert np.array_equal(bo.view(np.uint32), bp.view(np.uint32)) and np.array_equal(ao, ap), (k, node)
+    wb = orc.world_bound()
+    assert np.array_equal(wb.view(np.uint32), hb.info(0)["bounds"].view(np.uint32))
+    orc.close()
+    hb.close()
+
+
+def test_host_bvh_equals_oracle_cornell(P):
+    _compare_bvh(P, P.HostScene.parse_string(P.scenes.cornell_box()), [0])
+
+
+def test_host_bvh_equals_oracle_grid(P):
+    _compare_bvh(P, P.HostScene.parse_string(P.scenes.displaced_grid(n=96, res=32, spp=1)), [0])
+
+
+@pytest.mark.parametrize("split", ["middle", "equal"])
+def test_host_bvh_equals_oracle_other_splits(P, split):
+    txt = P.scenes.displaced_grid(n=40, res=32, spp=1).replace('Accelerator "bvh"', 'Accelerator "bvh" "string splitmethod" ["%s"] "integer maxnodeprims" [3]' % split)
+    _compare_bvh(P, P.HostScene.parse_string(txt), [0])
+
+
+def test_host_bvh_equals_oracle_instances(P):
+    hs = P.HostScene.parse_string(P.scenes.instanced_blobs(n_instances=40, n_sub=2, res=(32, 24), spp=1, n_lights=4))
+    _compare_bvh(P, hs, [0, 1, 2, 3, 4])
+
+
+def test_host_bvh_coincident_centroids_make_big_leaf(P):
+    # many identical triangles: centroid bounds are degenerate -> one leaf with all primitives (node.rs:55-62)
+    tri = "0 0 0 1 0 0 0 1 0 "
+    n = 12
+    txt = 'Camera "perspective"\nWorldBegin\nShape "trianglemesh" "integer indices" [%s] "point P" [%s]\nWorldEnd\n' % (
+        " ".join(str(i) for i in range(3 * n)), tri * n)
+    hs = P.HostScene.parse_string(txt)
+    _compare_bvh(P, hs, [0])
+    hb = P.HostBvh(hs)
+    assert hb.info(0)["n_nodes"] == 1 and hb.node(0, 0)[3] == 1

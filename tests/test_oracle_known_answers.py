@@ -139,10 +139,13 @@ def test_distribution_1d_continuous(oracle):  # tests/sampling.rs:323-349
     assert sc(1.0)[0] == 1.0
 
 
-def test_triangle_badcase_misses(oracle):  # tests/shapes.rs:480-504 (the degenerate mesh is dropped at creation; if kept it must miss)
-    p = np.array([-1113.45459, -79.049614, -56.2431908, -1113.45459, -87.0922699, -56.2431908, -1113.45459, -79.2090149, -56.2431908], np.float32)
-    ray = np.array([-1081.47925, 99.9999542, 87.7701111, 0.9999, -32.1072998, -183.355865, -144.607635, 0.0], np.float32)
-    assert oracle.orc_tri_intersect_raw(p.ctypes.data, 4, ray.ctypes.data, None, None) == 0
+def test_triangle_badcase_is_dropped(P):
+    """tests/shapes.rs:480-504: the bad-case triangle is collinear; create_triangle_mesh drops it (area <= 1e-16,
+    shapes/triangle.rs:726) so the reference's assertion is vacuous.  The front end must drop it too."""
+    txt = ('Camera "perspective"\nWorldBegin\nShape "trianglemesh" "integer indices" [0 1 2] "point P" '
+           '[-1113.45459 -79.049614 -56.2431908 -1113.45459 -87.0922699 -56.2431908 -1113.45459 -79.2090149 -56.2431908]\nWorldEnd\n')
+    hs = P.HostScene.parse_string(txt)
+    assert hs.desc.n_tris == 0
 
 
 def _sphere_mesh(rng, n_theta=16, n_phi=16):

@@ -1,0 +1,26 @@
+"""Generates tests/golden/*: small fixtures produced by the CPU oracle (the Rust reference cannot be built in this
+image, so these pin the ORACLE's output, not the reference binary's; see DESIGN.md "parity unpinned").
+Run from the repo root:  python tools/make_golden.py"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as g
+g.build()
+import pbrt_r3_b200 as P
+import oracle_api
+out = os.path.join(ROOT, "tests", "golden")
+os.makedirs(out, exist_ok=True)
+hs = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4))
+orc = oracle_api.OracleScene(hs)
+rgb, st = orc.render(threads=1)
+np.save(os.path.join(out, "cornell_64_4spp.npy"), rgb)
+sb = hs.desc.film.sample_bounds
+pix = np.array([[x, y] for y in (sb[1], 0, 17, sb[3] - 1) for x in (sb[0], 0, 31, sb[2] - 1)], np.int32)
+sn = (np.arange(len(pix)) % 4).astype(np.int32)
+np.savez(os.path.join(out, "cornell_64_streams.npz"), pix=pix, sn=sn, halton=orc.sampler_values(pix, sn, 0, 32), rays=orc.camera_rays(pix, sn)[0],
+         counters=np.array([st[k] for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested")], np.int64))
+hs2 = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4, sampler="sobol"))
+orc2 = oracle_api.OracleScene(hs2)
+np.save(os.path.join(out, "cornell_64_sobol_values.npy"), orc2.sampler_values(pix, sn, 0, 32))
+print("golden written:", os.listdir(out))
