@@ -325,7 +325,7 @@ inline bool Accel::prim_intersect(const SceneGeom& g, int32_t prim, const Ray& r
     TriHit th;
     if (!tri_intersect(get_tri(g.d, prim), r, &th)) return false;
     r.t_max = th.t;
-    hit->tri = prim; hit->t = th.t; hit->b0 = th.b0; hit->b1 = th.b1; hit->b2 = th.b2;
+    hit->tri = prim; hit->instance = -1; hit->t = th.t; hit->b0 = th.b0; hit->b1 = th.b1; hit->b2 = th.b2;
     hit->local_ray = r;
     return true;
   }

@@ -7,6 +7,7 @@
 #include "o_shading.h"
 
 #include <atomic>
+#include <cstdio>
 #include <mutex>
 #include <thread>
 
@@ -89,6 +90,10 @@ inline Spec<NC> estimate_direct(Scene<NC>& sc, const SurfInt& it, const BSDF<NC>
   const pt_light& L = d->lights[light_num];
   LightSample<NC> ls;
   if (light_sample_li<NC>(d, sc.world_radius, light_num, ref, u_light, &ls)) {
+#ifdef ORC_DEBUG_PRINT
+    fprintf(stderr, "[or] p=(%g %g %g) n=(%g %g %g) perr=(%g %g %g) light %d\n", it.p.x, it.p.y, it.p.z, it.n.x, it.n.y, it.n.z, it.p_error.x, it.p_error.y, it.p_error.z, light_num);
+    fprintf(stderr, "[or] ls pdf %g li %g wi=(%g %g %g) sh_o=(%.9g %.9g %.9g) sh_d=(%.9g %.9g %.9g) occluded %d\n", ls.pdf, ls.li.c[0], ls.wi.x, ls.wi.y, ls.wi.z, ls.shadow.o.x, ls.shadow.o.y, ls.shadow.o.z, ls.shadow.d.x, ls.shadow.d.y, ls.shadow.d.z, (int)sc.intersect_p(ls.shadow, nullptr));
+#endif
     if (ls.pdf > 0.0f && !ls.li.is_black()) {
       Spec<NC> f = bsdf.f(it.wo, ls.wi, flags) * abs_dot(ls.wi, it.sn);
       Float scattering_pdf = bsdf.pdf(it.wo, ls.wi, flags);

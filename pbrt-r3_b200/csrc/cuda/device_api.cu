@@ -2,7 +2,19 @@
 // stage entry points.  Replaces SceneContext::make_scene/make_integrator (scene_context.rs:675-731), QBVHAccel::new
 // (qbvh_x86.rs:352-371), Integrator::render (core/integrator/sampler.rs:259-325) and Film::write_image (film.rs:440-472).
 // There is no CPU fallback: every entry point fails with an error when CUDA is unavailable.
+#if defined(PT_HOSTCHECK)
+// tests/hostcheck: the SAME sources compiled by g++ against a serial stand-in for the CUDA runtime, to check the
+// stage logic on a CPU-only box.  Never built into the product library (which needs a CUDA device).
+#include "cuda_shim.h"
+#define PT_LAUNCH(grid, block, stream, ...) hostcheck::begin_launch(), __VA_ARGS__
+#else
 #include <cuda_runtime.h>
+#define PT_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<(grid), (block), 0, (stream)>>>
+#endif
+// spectral channel count of the second template instantiation (tests/hostcheck may build RGB only to save compile time)
+#ifndef PT_NCS
+#define PT_NCS 60
+#endif
 
 #include <algorithm>
 #include <cfloat>
@@ -163,9 +175,9 @@ int grid_for(const pt_scene* s, size_t n, int block, int per_sm) {
 template <int NC>
 int precompute_light_distribution(pt_scene* s, uint32_t n_vox, float* func, float* cdf, float* func_int) {
   size_t total = (size_t)n_vox * s->h.n_lights;
-  k_voxel_contrib<NC><<<grid_for(s, total, 128, 16), 128, 0, s->stream>>>(s->d, func, n_vox);
+  PT_LAUNCH(grid_for(s, total, 128, 16), 128, s->stream, k_voxel_contrib<NC>)(s->d, func, n_vox);
   CK(cudaGetLastError());
-  k_voxel_cdf<<<grid_for(s, n_vox, 128, 16), 128, 0, s->stream>>>(s->h.n_lights, n_vox, func, cdf, func_int);
+  PT_LAUNCH(grid_for(s, n_vox, 128, 16), 128, s->stream, k_voxel_cdf)(s->h.n_lights, n_vox, func, cdf, func_int);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s->stream));
   return 0;
@@ -377,7 +389,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(cudaMemcpy(s->d, &H, sizeof(DScene), cudaMemcpyHostToDevice));
   if (D->n_lights > 0) {
     if (strat == PT_LIGHTS_SPATIAL) {
-      int rc = NC == 3 ? precompute_light_distribution<3>(s, n_vox, func, cdf, fint) : precompute_light_distribution<60>(s, n_vox, func, cdf, fint);
+      int rc = NC == 3 ? precompute_light_distribution<3>(s, n_vox, func, cdf, fint) : precompute_light_distribution<PT_NCS>(s, n_vox, func, cdf, fint);
       if (rc) return rc;
     } else {
       // uniform / power (lightdistrib/{uniform,power}.rs): one distribution, built on the host
@@ -469,7 +481,7 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     uint32_t total = counts[0] + counts[3] + counts[2];
     int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
     if (timed) cudaEventRecord(e0, s->stream);
-#define LAUNCH_TRACE(I, C) k_trace<NC, I, C><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
+#define LAUNCH_TRACE(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_trace<NC, I, C>)(s->d, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
     if (inst) { if (count) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
     else { if (count) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
 #undef LAUNCH_TRACE
@@ -483,7 +495,7 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     uint32_t n_ext = counts[0];
     CK(cudaMemsetAsync(Q.counts, 0, 4 * sizeof(uint32_t), s->stream));
     if (n_ext > 0) {
-      k_shade<NC><<<grid_for(s, n_ext, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, 0, s->stream>>>(s->d, W, Q, n_ext, count ? s->counters + 2 : nullptr);
+      PT_LAUNCH(grid_for(s, n_ext, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_shade<NC>)(s->d, W, Q, n_ext, count ? s->counters + 2 : nullptr);
       CK(cudaGetLastError());
       T->launches++;
     }
@@ -553,7 +565,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   WaveTotals T;
   for (uint32_t c0 = 0; c0 < npix_total; c0 += pix_chunk) {
     uint32_t npix = std::min(pix_chunk, npix_total - c0);
-    k_set_slots<<<grid_for(s, npix, 256, 8), 256, 0, s->stream>>>(s->pixlist, c0, npix, sbw, s->slot_of, 0);
+    PT_LAUNCH(grid_for(s, npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, c0, npix, sbw, s->slot_of, 0);
     CK(cudaGetLastError());
     T.launches++;
     // film footprint of this pixel chunk
@@ -567,21 +579,21 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     for (int s0 = s_begin; s0 < s_end; s0 += (int)ns_wave) {
       uint32_t ns = (uint32_t)std::min<int>((int)ns_wave, s_end - s0);
       uint32_t n = npix * ns;
-      k_raygen<NC><<<grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, 0, s->stream>>>(s->d, s->W, s->Q, s->pixlist, c0, npix, s0, ns);
+      PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->d, s->W, s->Q, s->pixlist, c0, npix, s0, ns);
       CK(cudaGetLastError());
       T.launches++;
       if (st) st->camera_rays += n;
       if (run_bounces<NC>(s, n, count, st != nullptr, &T)) return 1;
-      k_finish<NC><<<grid_for(s, n, 256, 8), 256, 0, s->stream>>>(s->d, s->W, n);
+      PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->d, s->W, n);
       CK(cudaGetLastError());
       T.launches++;
       if (fx1 > fx0 && fy1 > fy0) {
-        k_film<NC><<<grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, 0, s->stream>>>(s->d, s->W, s->slot_of, npix, ns, fx0, fy0, fx1, fy1, s->film);
+        PT_LAUNCH(grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, s->stream, k_film<NC>)(s->d, s->W, s->slot_of, npix, ns, fx0, fy0, fx1, fy1, s->film);
         CK(cudaGetLastError());
         T.launches++;
       }
     }
-    k_set_slots<<<grid_for(s, npix, 256, 8), 256, 0, s->stream>>>(s->pixlist, c0, npix, sbw, s->slot_of, 1);
+    PT_LAUNCH(grid_for(s, npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, c0, npix, sbw, s->slot_of, 1);
     CK(cudaGetLastError());
     T.launches++;
   }
@@ -633,7 +645,7 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out) {
   if (!desc || !out) { pt_set_error("pt_scene_create: null argument"); return 1; }
   *out = nullptr;
   if (desc->abi_version != PT_ABI_VERSION) { pt_set_error("pt_scene_create: ABI version mismatch"); return 1; }
-  if (desc->n_channels != 3 && desc->n_channels != 60) { pt_set_error("pt_scene_create: n_channels must be 3 or 60"); return 1; }
+  if (desc->n_channels != 3 && desc->n_channels != PT_NCS) { pt_set_error("pt_scene_create: n_channels must be 3 or 60"); return 1; }
   if (desc->n_objects < 1) { pt_set_error("pt_scene_create: need at least the top-level object"); return 1; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -687,7 +699,7 @@ int pt_render_partial(pt_scene* s, const pt_render_opts* opts, float** dev_film_
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, s->stream));
-  int rc = s->h.n_channels == 3 ? render_waves<3>(s, opts, stats) : render_waves<60>(s, opts, stats);
+  int rc = s->h.n_channels == 3 ? render_waves<3>(s, opts, stats) : render_waves<PT_NCS>(s, opts, stats);
   if (rc) return rc;
   CK(cudaEventRecord(e1, s->stream));
   CK(cudaEventSynchronize(e1));
@@ -705,7 +717,7 @@ int pt_film_resolve(pt_scene* s, const float* dev_film_xyzw, float* out_rgb_host
   CK(cudaSetDevice(s->device));
   const f4* film = dev_film_xyzw ? (const f4*)dev_film_xyzw : s->film;
   if (s->film_pixels == 0) return 0;
-  k_film_resolve<<<grid_for(s, s->film_pixels, 256, 8), 256, 0, s->stream>>>(s->d, film, s->rgb_dev, s->film_pixels);
+  PT_LAUNCH(grid_for(s, s->film_pixels, 256, 8), 256, s->stream, k_film_resolve)(s->d, film, s->rgb_dev, s->film_pixels);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_rgb_host, s->rgb_dev, (size_t)s->film_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -732,8 +744,8 @@ int pt_intersect(pt_scene* s, const float* rays, uint32_t n, int32_t* prim, floa
   bool count = nodes_visited || tris_tested;
   CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
-  if (s->h.has_instances) { if (count) k_intersect<true, true><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else k_intersect<true, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
-  else { if (count) k_intersect<false, true><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else k_intersect<false, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
+  if (s->h.has_instances) { if (count) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<true, true>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<true, false>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
+  else { if (count) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<false, true>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<false, false>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
   CK(cudaGetLastError());
   std::vector<f4> hh(n);
   std::vector<float> th(n);
@@ -767,8 +779,8 @@ int pt_intersect_p(pt_scene* s, const float* rays, uint32_t n, uint8_t* occluded
   if (upload_rays(s, rays, n, B, &ro, &rd)) return 1;
   CK(B.alloc(n, &occ));
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
-  if (s->h.has_instances) k_intersect_p<true><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, occ, s->overflow);
-  else k_intersect_p<false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, ro, rd, n, occ, s->overflow);
+  if (s->h.has_instances) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect_p<true>)(s->d, ro, rd, n, occ, s->overflow);
+  else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect_p<false>)(s->d, ro, rd, n, occ, s->overflow);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(occluded, occ, n, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -784,8 +796,8 @@ int pt_intersect_device(pt_scene* s, const void* dev_o_tmax, const void* dev_d_t
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
   CK(cudaEventRecord(e0, s->stream));
   for (int r = 0; r < std::max(repeat, 1); r++) {
-    if (s->h.has_instances) k_intersect<true, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
-    else k_intersect<false, false><<<g, PT_TRACE_BLOCK, 0, s->stream>>>(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
+    if (s->h.has_instances) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<true, false>)(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
+    else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<false, false>)(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, s->stream));
@@ -808,7 +820,7 @@ int pt_sampler_values(pt_scene* s, const int32_t* pixel_xy, const int32_t* sampl
   CK(B.upload(pixel_xy, (size_t)n * 2, &pxy));
   CK(B.upload(sample_num, n, &sn));
   CK(B.alloc((size_t)n * ndims, &o));
-  k_sampler_values<<<grid_for(s, (size_t)n * ndims, 128, 8), 128, 0, s->stream>>>(s->d, pxy, sn, n, dim0, ndims, o);
+  PT_LAUNCH(grid_for(s, (size_t)n * ndims, 128, 8), 128, s->stream, k_sampler_values)(s->d, pxy, sn, n, dim0, ndims, o);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, o, (size_t)n * ndims * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -821,15 +833,15 @@ static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_
   const int *pxy, *sn;
   CK(B.upload(pixel_xy, (size_t)n * 2, &pxy));
   CK(B.upload(sample_num, n, &sn));
-  if (s->h.n_channels == 3) k_raygen_list<3><<<grid_for(s, n, 128, 8), 128, 0, s->stream>>>(s->d, s->W, s->Q, pxy, sn, n);
-  else k_raygen_list<60><<<grid_for(s, n, 128, 8), 128, 0, s->stream>>>(s->d, s->W, s->Q, pxy, sn, n);
+  if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<3>)(s->d, s->W, s->Q, pxy, sn, n);
+  else PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<PT_NCS>)(s->d, s->W, s->Q, pxy, sn, n);
   CK(cudaGetLastError());
   if (bounce && s->h.n_lights > 0) {
     WaveTotals T;
-    int rc = s->h.n_channels == 3 ? run_bounces<3>(s, n, false, false, &T) : run_bounces<60>(s, n, false, false, &T);
+    int rc = s->h.n_channels == 3 ? run_bounces<3>(s, n, false, false, &T) : run_bounces<PT_NCS>(s, n, false, false, &T);
     if (rc) return rc;
-    if (s->h.n_channels == 3) k_finish<3><<<grid_for(s, n, 256, 8), 256, 0, s->stream>>>(s->d, s->W, n);
-    else k_finish<60><<<grid_for(s, n, 256, 8), 256, 0, s->stream>>>(s->d, s->W, n);
+    if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<3>)(s->d, s->W, n);
+    else PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<PT_NCS>)(s->d, s->W, n);
     CK(cudaGetLastError());
   }
   CK(cudaStreamSynchronize(s->stream));

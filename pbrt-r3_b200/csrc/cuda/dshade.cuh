@@ -305,6 +305,9 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   if (bsdf_count(B, NONSPEC) > 0 && S.n_lights > 0) {
     float light_pdf;
     int ln = ld_sample(S, si.p, get1d(S, st), &light_pdf);
+#ifdef PT_DEBUG_PRINT
+    fprintf(stderr, "[hc] p=(%g %g %g) n=(%g %g %g) perr=(%g %g %g) light %d pdf %g dim %u\n", si.p.x, si.p.y, si.p.z, si.n.x, si.n.y, si.n.z, si.perr.x, si.perr.y, si.perr.z, ln, light_pdf, st.dim);
+#endif
     if (light_pdf > 0.0f) {
       f2 u_light = get2d(S, st);
       f2 u_scat = get2d(S, st);
@@ -312,6 +315,9 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
       bool delta = LT.type != PT_LIGHT_AREA;
       LightSampleD<NC> ls;
       if (light_sample<NC>(S, ln, ref, u_light, &ls)) {
+#ifdef PT_DEBUG_PRINT
+        fprintf(stderr, "[hc] ls pdf %g li %g wi=(%g %g %g) sh_o=(%.9g %.9g %.9g) sh_d=(%.9g %.9g %.9g)\n", ls.pdf, ls.li.c[0], ls.wi.x, ls.wi.y, ls.wi.z, ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, ls.sh_d.x, ls.sh_d.y, ls.sh_d.z);
+#endif
         if (ls.pdf > 0.0f && !sp_black(ls.li)) {
           Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
           float spdf = bsdf_pdf(B, si.wo, ls.wi, NONSPEC);

@@ -1,0 +1,53 @@
+// cuda_shim.h — TEST INFRASTRUCTURE.  A serial, single-"thread" stand-in for the slice of the CUDA runtime that
+// pbrt-r3_b200/csrc/cuda/device_api.cu uses, so that the very same kernels (grid-stride loops) can be executed by g++
+// on a CPU-only box: device memory = malloc, a launch = one call with gridDim = blockDim = 1.
+// It exists to catch LOGIC errors before spending GPU time; it is compiled only by tests/test_hostcheck.py into
+// tests/hostcheck/_build/ and is never part of the product library.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#define __global__
+#define __device__
+#define __host__
+#define __shared__ static
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(x)
+
+struct hc_dim3 { unsigned x, y, z; };
+static const hc_dim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, gridDim = {1, 1, 1}, blockDim = {1, 1, 1};
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+struct cudaDeviceProp { int multiProcessorCount; };
+
+namespace hostcheck { inline void begin_launch() {} }
+
+inline const char* cudaGetErrorString(cudaError_t) { return "hostcheck"; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+inline cudaError_t cudaSetDevice(int) { return 0; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 1; return 0; }
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+template <typename T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
+inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return 0; }
+template <typename T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
