@@ -108,7 +108,7 @@ PT_HD f2 concentric_disk(f2 u) {
   float r, theta;
   if (fabsf(ox) > fabsf(oy)) { r = ox; theta = PT_PI_OVER_4 * (oy / ox); }
   else { r = oy; theta = PT_PI_OVER_2 - PT_PI_OVER_4 * (ox / oy); }
-  return mk2(r * cosf(theta), r * sinf(theta));
+  return mk2(r * pt_cosf(theta), r * pt_sinf(theta));
 }
 PT_HD f3 cosine_hemisphere(f2 u) {
   f2 d = concentric_disk(u);
@@ -177,8 +177,8 @@ PT_HD void tr_sample11(float ct, float u1, float u2, float* sx, float* sy) {
   if (ct > 0.9999f) {
     float r = sqrtf(u1 / (1.0f - u1));
     float phi = 2.0f * PT_PI * u2;
-    *sx = r * cosf(phi);
-    *sy = r * sinf(phi);
+    *sx = r * pt_cosf(phi);
+    *sy = r * pt_sinf(phi);
     return;
   }
   float st = sqrtf(fmaxf(0.0f, 1.0f - ct * ct));
@@ -251,7 +251,7 @@ PT_HD Sp<NC> lobe_fresnel(const DScene& S, const Lobe& L, float ci) {
 }
 
 template <int NC>
-PT_HD Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
+PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
   switch (L.kind) {
     case LB_LAMBERT: return sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * PT_INV_PI;
     case LB_OREN: {
@@ -297,7 +297,7 @@ PT_HD Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
     default: return sp_const<NC>(0.0f);
   }
 }
-PT_HD float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
+PT_HDN float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
   switch (L.kind) {
     case LB_LAMBERT: case LB_OREN: return same_hemi(wo, wi) ? acth(wi) * PT_INV_PI : 0.0f;
     case LB_MF_REFL: {
@@ -323,7 +323,7 @@ PT_HD float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
 }
 // BxDF::sample_f of one lobe; stype = 0 means "the lobe's own type"
 template <int NC>
-PT_HD bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, f3* wi_out, float* pdf, int* stype) {
+PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, f3* wi_out, float* pdf, int* stype) {
   *stype = 0;
   switch (L.kind) {
     case LB_LAMBERT: case LB_OREN: {
@@ -408,7 +408,7 @@ PT_HD void tri_verts(const DScene& S, int tri, f3* p0, f3* p1, f3* p2) {
 }
 
 // interaction part of Triangle::intersect in the triangle's own space (rd = ray direction in that space)
-PT_HD SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, float b2) {
+PT_HDN SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, float b2) {
   f3 p0, p1, p2;
   tri_verts(S, tri, &p0, &p1, &p2);
   uint32_t flags = ldg(S.tri_flags + tri);
@@ -470,7 +470,7 @@ PT_HD SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, flo
 }
 
 // Transform::transform_surface_interaction (instance -> world)
-PT_HD SurfD surf_to_world(const InstanceRec& I, const SurfD& s) {
+PT_HDN SurfD surf_to_world(const InstanceRec& I, const SurfD& s) {
   SurfD r = s;
   const float* m = I.m;
   float x = s.p.x, y = s.p.y, z = s.p.z;
@@ -531,7 +531,7 @@ PT_HD bool spectrum_black(const DScene& S, int idx, bool clamp0) {
 // Spectra that the reference clamps (clamp_zero) are clamped on the HOST at upload when a negative value is
 // present, so the device can treat every stored reflectance as already clamped except matte Kd (never clamped).
 template <int NC>
-PT_HD void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
+PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   B->n = -1;
   int mi = ldg(S.tri_material + si.tri);
   if (mi < 0) return;
@@ -622,12 +622,12 @@ PT_HD Sp<NC> bsdf_sum_f(const DScene& S, const BsdfD& B, f3 wo, f3 wi, f3 wo_w, 
   return r;
 }
 template <int NC>
-PT_HD Sp<NC> bsdf_f(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
+PT_HDN Sp<NC> bsdf_f(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return sp_const<NC>(0.0f);
   return bsdf_sum_f<NC>(S, B, wo, wi, wo_w, wi_w, flags);
 }
-PT_HD float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
+PT_HDN float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return 0.0f;
   int count = 0;
@@ -637,7 +637,7 @@ PT_HD float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
   return count > 0 ? p / (float)count : 0.0f;
 }
 template <int NC>
-PT_HD bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags, Sp<NC>* f, f3* wi_w_out, float* pdf_out, int* stype) {
+PT_HDN bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags, Sp<NC>* f, f3* wi_w_out, float* pdf_out, int* stype) {
   int matching = bsdf_count(B, flags);
   if (matching == 0) return false;
   int comp = (int)floorf(u.x * (float)matching);

@@ -333,8 +333,13 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
       }
       off += p;
     }
-    CK(s->bufs.upload(primes.data(), primes.size(), &H.primes));
-    CK(s->bufs.upload(sums.data(), sums.size(), &H.prime_sums));
+    std::vector<PrimeRec> recs1024(primes.size());
+    for (size_t i = 0; i < primes.size(); i++) {
+      recs1024[i].prime = primes[i];
+      recs1024[i].perm_offset = sums[i];
+      recs1024[i].magic = (~0ull / primes[i]) + 1ull;  // ceil(2^64 / p)
+    }
+    CK(s->bufs.upload(recs1024.data(), recs1024.size(), &H.prime_recs));
     CK(s->bufs.upload(perms.data(), perms.size(), &H.perms));
   }
   if (SD.type == PT_SAMPLER_SOBOL) {

@@ -50,14 +50,23 @@ PT_HD float radical_inverse_base(uint32_t base, uint64_t a) {
 }
 PT_HD float radical_inverse2(uint64_t a) { return (float)rev64(a) * 5.4210108624275222e-20f; }
 
-PT_HD float scrambled_radical_inverse(uint32_t base, uint64_t a, const uint16_t* perm) {  // radical_inverse.rs:71-91
+// floor(a / b) for a < 2^32 as the high half of a * ceil(2^64 / b): exact because a * b < 2^64
+PT_HD uint32_t div_magic(uint32_t a, uint64_t magic) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__umul64hi((unsigned long long)a, (unsigned long long)magic);
+#else
+  return (uint32_t)(((unsigned __int128)a * (unsigned __int128)magic) >> 64);
+#endif
+}
+
+PT_HD float scrambled_radical_inverse(uint32_t base, uint64_t magic, uint64_t a, const uint16_t* perm) {  // radical_inverse.rs:71-91
   float inv_base = 1.0f / (float)base;
   uint64_t rev = 0;
   float inv_base_n = 1.0f;
   if (a < 0x100000000ull) {
     uint32_t a32 = (uint32_t)a;
     while (a32 != 0) {
-      uint32_t next = a32 / base;
+      uint32_t next = div_magic(a32, magic);
       uint32_t digit = a32 - next * base;
       rev = rev * base + (uint64_t)ldg(perm + digit);
       inv_base_n *= inv_base;
@@ -137,14 +146,16 @@ PT_HD int64_t sampler_index(const DScene& S, int px, int py, int64_t n) {
   return (int64_t)sobol_interval_to_index(S.vdc, c.log2_resolution, (uint64_t)n, px - c.sb[0], py - c.sb[1]);
 }
 
-PT_HD float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, int py) {
+PT_HDN float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, int py) {
   const SamplerDev& c = S.sampler;
   if (c.type == PT_SAMPLER_HALTON) {  // halton.rs:149-162
     if (c.at_center && dim < 2) return 0.5f;
     if (dim == 0) return radical_inverse2((uint64_t)(index >> c.base_exponents[0]));
     if (dim == 1) return radical_inverse_base(3u, (uint64_t)(index / (int64_t)c.base_scales[1]));
     if (dim >= 1024u) dim = 1023u;  // the reference panics here; paths that long do not occur (maxdepth <= ~100)
-    return scrambled_radical_inverse(ldg(S.primes + dim), (uint64_t)index, S.perms + ldg(S.prime_sums + dim));
+    i4 pr = ldgi4(reinterpret_cast<const i4*>(S.prime_recs + dim));
+    uint64_t magic = ((uint64_t)(uint32_t)pr.w << 32) | (uint64_t)(uint32_t)pr.z;
+    return scrambled_radical_inverse((uint32_t)pr.x, magic, (uint64_t)index, S.perms + (uint32_t)pr.y);
   }
   float s = sobol_sample_float(S.sobol32, index, dim, 0u);  // sobol.rs:174-185
   if (dim < 2) {

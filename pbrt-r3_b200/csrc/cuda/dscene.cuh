@@ -44,6 +44,12 @@ struct InstanceRec {
   int32_t pad[3];
 };
 
+struct alignas(16) PrimeRec {  // PRIMES[dim], PRIME_SUMS[dim] (lowdiscrepancy/primes.rs) + ceil(2^64 / prime) for exact division by multiply-high
+  uint32_t prime;
+  uint32_t perm_offset;
+  uint64_t magic;
+};
+
 struct SamplerDev {     // samplers/{halton,sobol}.rs state that is constant over the render
   int32_t type, spp;    // spp = effective (sobol: rounded up to a power of two)
   int32_t sb[4];
@@ -88,8 +94,7 @@ struct DScene {
   SamplerDev sampler;
   LightDistDev ld;
   // sampler tables
-  const uint32_t* primes;      // 1024
-  const uint32_t* prime_sums;  // 1024
+  const PrimeRec* prime_recs;  // 1024: one 16-byte record per Halton dimension
   const uint16_t* perms;       // sum(primes)
   const uint32_t* sobol32;     // 1024*52
   const uint64_t* vdc;         // (25+26)*52

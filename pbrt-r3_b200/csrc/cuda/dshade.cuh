@@ -89,7 +89,7 @@ struct LightSampleD {
 
 // Light::sample_li for area (one triangle), point and distant lights
 template <int NC>
-PT_HD bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSampleD<NC>* out) {
+PT_HDN bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSampleD<NC>* out) {
   const pt_light& L = S.lights[li];
   f3 lp, lperr = mk3(0.0f, 0.0f, 0.0f), ln = mk3(0.0f, 0.0f, 0.0f);
   if (L.type == PT_LIGHT_AREA) {
@@ -139,7 +139,7 @@ PT_HD bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSam
 }
 
 // Light::pdf_li for the area light's triangle = Shape::pdf_from (re-intersect that one triangle)
-PT_HD float light_pdf_li(const DScene& S, int li, const RefPt& it, f3 wi) {
+PT_HDN float light_pdf_li(const DScene& S, int li, const RefPt& it, f3 wi) {
   const pt_light& L = S.lights[li];
   if (L.type != PT_LIGHT_AREA) return 0.0f;
   f3 o = offset_origin(it.p, it.perr, it.n, wi);
@@ -176,7 +176,7 @@ PT_HD uint32_t ld_voxel(const LightDistDev& D, f3 p) {
   }
   return (pi[0] * D.voxels[1] + pi[1]) * D.voxels[2] + pi[2];
 }
-PT_HD int ld_sample(const DScene& S, f3 p, float u, float* pdf) {
+PT_HDN int ld_sample(const DScene& S, f3 p, float u, float* pdf) {
   const LightDistDev& D = S.ld;
   uint32_t nl = S.n_lights;
   uint32_t vox = D.strategy == PT_LIGHTS_SPATIAL ? ld_voxel(D, p) : 0u;

@@ -45,22 +45,20 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(const DScene* __restri
   const uint32_t total = n_ext + n_mis + n_sh;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
     st.n = 0;
-    if (k < n_ext) {
-      uint32_t i = Q.ext[k];
-      f4 o = W.ray_o[i], d = W.ray_d[i];
+    if (k < n_ext + n_mis) {  // one copy of the closest-hit traversal for both ray classes
+      const bool is_ext = k < n_ext;
+      uint32_t i = is_ext ? Q.ext[k] : Q.mis[k - n_ext];
+      f4 o = is_ext ? W.ray_o[i] : W.mis_o[i], d = is_ext ? W.ray_d[i] : W.mis_d[i];
       float tmax = o.w;
       HitD h;
       bool found = scene_intersect<INST, COUNT>(S, xyz(o), xyz(d), d.w, tmax, &h, st, &ovf, &tc);
-      W.hit[i] = mk4(h.b0, h.b1, h.b2, bitsf((uint32_t)(found ? h.tri : -1)));
-      if (INST) W.hit_inst[i] = found ? h.instance : -1;
-      if (found) W.ray_o[i].w = tmax;
-    } else if (k < n_ext + n_mis) {
-      uint32_t i = Q.mis[k - n_ext];
-      f4 o = W.mis_o[i], d = W.mis_d[i];
-      float tmax = o.w;
-      HitD h;
-      bool found = scene_intersect<INST, COUNT>(S, xyz(o), xyz(d), d.w, tmax, &h, st, &ovf, &tc);
-      mis_resolve<NC>(S, W, i, h, found, xyz(d));
+      if (is_ext) {
+        W.hit[i] = mk4(h.b0, h.b1, h.b2, bitsf((uint32_t)(found ? h.tri : -1)));
+        if (INST) W.hit_inst[i] = found ? h.instance : -1;
+        if (found) W.ray_o[i].w = tmax;
+      } else {
+        mis_resolve<NC>(S, W, i, h, found, xyz(d));
+      }
     } else {
       uint32_t i = Q.shadow[k - n_ext - n_mis];
       f4 o = W.sh_o[i], d = W.sh_d[i];

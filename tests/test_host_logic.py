@@ -162,3 +162,12 @@ def test_host_bvh_coincident_centroids_make_big_leaf(P):
     _compare_bvh(P, hs, [0])
     hb = P.HostBvh(hs)
     assert hb.info(0)["n_nodes"] == 1 and hb.node(0, 0)[3] == 1
+
+
+def test_device_sincos_equals_libm(tmp_path):
+    """The device's sin/cos (dmath.cuh pt_sinf/pt_cosf, f64 polynomial) must equal the host libm bit for bit: the
+    reference's f32::sin/cos are libm calls, and ulp differences get amplified by specular chains."""
+    exe = str(tmp_path / "check_sincos")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", os.path.join(ROOT, "tools", "check_sincos.cpp"), "-o", exe])
+    out = subprocess.check_output([exe, "5000000"]).decode().split()
+    assert out[0] == "0" and out[1] == "0", out
