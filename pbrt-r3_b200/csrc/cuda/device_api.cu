@@ -113,6 +113,7 @@ struct pt_scene {
   int* slot_of = nullptr;
   unsigned long long* counters = nullptr;  // [0] nodes [1] tris [2] vertices
   int* overflow = nullptr;
+  uint32_t* fetch = nullptr;               // ray fetch counter of the stage entry points
   uint32_t wave_cap = 0;
   // pixel list cache
   int* pixlist = nullptr;
@@ -440,6 +441,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(cudaMemset(s->slot_of, 0xff, sbn * sizeof(int)));
   CK(s->bufs.alloc(4, &s->counters));
   CK(s->bufs.alloc(1, &s->overflow));
+  CK(s->bufs.alloc(1, &s->fetch));
   CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
   CK(cudaMemset(s->overflow, 0, sizeof(int)));
   return 0;
@@ -461,7 +463,8 @@ int ensure_wave(pt_scene* s, uint32_t cap) {
   CK(B.alloc(cap, &W.sh_o)); CK(B.alloc(cap, &W.sh_d)); CK(B.alloc((size_t)cap * NC, &W.pendA));
   CK(B.alloc(cap, &W.mis_o)); CK(B.alloc(cap, &W.mis_d)); CK(B.alloc((size_t)cap * NC, &W.pendB)); CK(B.alloc(cap, &W.mis_light));
   Queues& Q = s->Q;
-  CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(4, &Q.counts));
+  CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(8, &Q.counts));
+  CK(cudaMemset(Q.counts, 0, 8 * sizeof(uint32_t)));
   s->wave_cap = cap;
   return 0;
 }
@@ -498,14 +501,14 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     T->trace_launches++;
     T->trace_rays += total;
     uint32_t n_ext = counts[0];
-    CK(cudaMemsetAsync(Q.counts, 0, 4 * sizeof(uint32_t), s->stream));
+    CK(cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream));  // queue counters + the trace fetch counter
     if (n_ext > 0) {
       PT_LAUNCH(grid_for(s, n_ext, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_shade<NC>)(s->d, W, Q, n_ext, count ? s->counters + 2 : nullptr);
       CK(cudaGetLastError());
       T->launches++;
     }
     if (timed) cudaEventRecord(e2, s->stream);
-    CK(cudaMemcpyAsync(counts, Q.counts, sizeof(counts), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(counts, Q.counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     if (timed) {
       float a = 0, b = 0;
@@ -624,6 +627,17 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
       CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
     }
   }
+  return 0;
+}
+
+int launch_intersect(pt_scene* s, const f4* ro, const f4* rd, uint32_t n, f4* hits, float* tt, unsigned char* occ, bool count) {
+  CK(cudaMemsetAsync(s->fetch, 0, sizeof(uint32_t), s->stream));
+  int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
+#define LAUNCH_ISECT(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<I, C>)(s->d, ro, rd, n, hits, tt, occ, s->fetch, s->counters, s->overflow)
+  if (s->h.has_instances) { if (count) LAUNCH_ISECT(true, true); else LAUNCH_ISECT(true, false); }
+  else { if (count) LAUNCH_ISECT(false, true); else LAUNCH_ISECT(false, false); }
+#undef LAUNCH_ISECT
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -749,8 +763,7 @@ int pt_intersect(pt_scene* s, const float* rays, uint32_t n, int32_t* prim, floa
   bool count = nodes_visited || tris_tested;
   CK(cudaMemsetAsync(s->counters, 0, 4 * sizeof(unsigned long long), s->stream));
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
-  if (s->h.has_instances) { if (count) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<true, true>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<true, false>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
-  else { if (count) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<false, true>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<false, false>)(s->d, ro, rd, n, hits, tt, s->counters, s->overflow); }
+  if (launch_intersect(s, ro, rd, n, hits, tt, nullptr, count)) return 1;
   CK(cudaGetLastError());
   std::vector<f4> hh(n);
   std::vector<float> th(n);
@@ -784,9 +797,7 @@ int pt_intersect_p(pt_scene* s, const float* rays, uint32_t n, uint8_t* occluded
   if (upload_rays(s, rays, n, B, &ro, &rd)) return 1;
   CK(B.alloc(n, &occ));
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
-  if (s->h.has_instances) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect_p<true>)(s->d, ro, rd, n, occ, s->overflow);
-  else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect_p<false>)(s->d, ro, rd, n, occ, s->overflow);
-  CK(cudaGetLastError());
+  if (launch_intersect(s, ro, rd, n, nullptr, nullptr, occ, false)) return 1;
   CK(cudaMemcpyAsync(occluded, occ, n, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   return 0;
@@ -801,8 +812,7 @@ int pt_intersect_device(pt_scene* s, const void* dev_o_tmax, const void* dev_d_t
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
   CK(cudaEventRecord(e0, s->stream));
   for (int r = 0; r < std::max(repeat, 1); r++) {
-    if (s->h.has_instances) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<true, false>)(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
-    else PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<false, false>)(s->d, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, s->counters, s->overflow);
+    if (launch_intersect(s, (const f4*)dev_o_tmax, (const f4*)dev_d_time, n, (f4*)dev_hits, nullptr, nullptr, false)) return 1;
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(e1, s->stream));

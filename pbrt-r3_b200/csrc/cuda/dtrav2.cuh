@@ -1,0 +1,200 @@
+// dtrav2.cuh — resumable (flat state machine) form of the two-level 4-wide BVH traversal of dtrav.cuh, for
+// persistent warps with dynamic ray fetch: a lane that finishes its ray pulls the next one instead of idling until
+// the slowest ray of its warp is done (ncu on the nested-call version: 6-15 of 32 lanes active per instruction).
+// Same reference semantics as dtrav.cuh (qbvh_x86.rs:231-343,373-399; transformed_primitive.rs:26-46): identical
+// node visit order, leaf order, t_max shrinking and float operations, so primitive ids and the node / triangle visit
+// counters still equal the CPU path's.
+//
+// Stack entries: >= 0 node index (relative to the current object), < 0 inline leaf ~((first << 3) | (count - 1)),
+// PT_STACK_BARRIER = "the instanced object's traversal ends here, return to the top level".  When an instance is
+// met inside a top-level leaf, the leaf's remaining primitives are pushed back as inline-leaf entries below the
+// barrier, so a leaf is processed in order even though the nested traversal runs in between.
+#pragma once
+#include "dtrav.cuh"
+
+namespace ptd {
+
+struct Trav {
+  f3 o, d;              // ray in the current space (world, or the instanced object's space)
+  float idx, idy, idz;  // 1 / d
+  float tmin, tmax;     // slab range of the current level (qbvh_x86.rs:246-252, 279-283)
+  float ray_tmax;       // Ray.t_max (Cell): shrinks on every accepted hit in closest-hit mode
+  float time;
+  int cur;              // entry being processed
+  int sg;               // sign bits of d: bit0 x, bit1 y, bit2 z
+  uint32_t node_base, rec_base;
+  // level-0 state saved while inside an instance
+  f3 so, sd;
+  float stmin, stmax;
+  int inst;             // >= 0 while traversing an instanced object
+  bool leaf_hit;        // a primitive of the leaf being processed (at the current level) was accepted
+  bool outer_hit;       // ... of the top-level leaf that was interrupted by the instance
+  bool nested_hit;      // ... of some leaf of the instanced object
+  bool found;
+  bool any;             // any-hit query (intersect_p)
+  bool done;
+  HitD hit;
+};
+
+PT_HD void trav_set_ray(Trav& T, f3 o, f3 d) {
+  T.o = o; T.d = d;
+  T.idx = 1.0f / d.x; T.idy = 1.0f / d.y; T.idz = 1.0f / d.z;
+  T.sg = (signbit_(d.x) ? 1 : 0) | (signbit_(d.y) ? 2 : 0) | (signbit_(d.z) ? 4 : 0);
+}
+
+// QBVHAccel::intersect[_p] prologue on the top-level object
+PT_HD void trav_begin(const DScene& S, Trav& T, f3 o, f3 d, float tmax, float time, bool any) {
+  T.any = any; T.found = false; T.done = false; T.inst = -1; T.leaf_hit = false; T.outer_hit = false; T.nested_hit = false;
+  T.ray_tmax = tmax; T.time = time;
+  T.hit.tri = -1; T.hit.instance = -1;
+  const ObjectRec& O = S.objects[0];
+  if (O.n_prims == 0) { T.done = true; return; }
+  trav_set_ray(T, o, d);
+  if (!bounds_range(O.bmin, O.bmax, o, d, tmax, &T.tmin, &T.tmax)) { T.done = true; return; }
+  T.node_base = O.node_base; T.rec_base = O.rec_base;
+  T.cur = 0;
+}
+
+template <typename Stack>
+PT_HD void trav_pop(Trav& T, Stack& st) {
+  if (!st.pop(&T.cur)) T.done = true;
+}
+
+// one accepted-or-not triangle record in the current space; returns true when the query is finished (any-hit)
+template <bool COUNT>
+PT_HD bool trav_triangle(Trav& T, f4 v0, f4 v1, f4 v2, TravCounters* cnt) {
+  if (COUNT) cnt->tris++;
+  TriHitD th;
+  if (!tri_test(xyz(v0), xyz(v1), xyz(v2), fbits(v1.w), T.o, T.d, T.ray_tmax, &th)) return false;
+  T.found = true;
+  if (T.any) return true;
+  T.ray_tmax = th.t;
+  T.leaf_hit = true;
+  T.hit.tri = (int)fbits(v0.w);
+  T.hit.instance = T.inst;
+  T.hit.t = th.t; T.hit.b0 = th.b0; T.hit.b1 = th.b1; T.hit.b2 = th.b2;
+  return false;
+}
+
+// Processes ONE stack entry (a node, a leaf or a leaf remainder, or the barrier) and pops the next one.
+template <bool INST, bool COUNT, typename Stack>
+PT_HD void trav_step(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
+  int first = -1, count = 0;
+  if (T.cur >= 0) {
+    if (INST && T.cur == PT_STACK_BARRIER) {  // TransformedPrimitive::intersect returns: back to world space
+      trav_set_ray(T, T.so, T.sd);
+      T.tmin = T.stmin; T.tmax = T.stmax;
+      const ObjectRec& O = S.objects[0];
+      T.node_base = O.node_base; T.rec_base = O.rec_base;
+      T.inst = -1;
+      // the interrupted leaf reported a hit if any of its primitives (the instance included) did: tmax = r.t_max.
+      // Its remainder, if any, is the next entry, so no node test can observe the early update.
+      if (T.outer_hit || T.nested_hit) T.tmax = T.ray_tmax;
+      T.outer_hit = false; T.nested_hit = false; T.leaf_hit = false;
+      trav_pop(T, st);
+      return;
+    }
+    if (COUNT) cnt->nodes++;
+    const QNode* nd = S.nodes + T.node_base + T.cur;
+    i4 meta = ldgi4(&nd->meta);
+    if (meta.x & 0x100) {
+      first = meta.y;
+      count = meta.z;
+    } else {
+      const int sgx = T.sg & 1, sgy = (T.sg >> 1) & 1, sgz = (T.sg >> 2) & 1;
+      f4 nx = ldg4(sgx ? &nd->hi[0] : &nd->lo[0]), fx = ldg4(sgx ? &nd->lo[0] : &nd->hi[0]);
+      f4 ny = ldg4(sgy ? &nd->hi[1] : &nd->lo[1]), fy = ldg4(sgy ? &nd->lo[1] : &nd->hi[1]);
+      f4 nz = ldg4(sgz ? &nd->hi[2] : &nd->lo[2]), fz = ldg4(sgz ? &nd->lo[2] : &nd->hi[2]);
+      i4 ch = ldgi4(&nd->child);
+      unsigned mask = 0;
+#define PT_LANE2(L, BIT)                                                  \
+  {                                                                       \
+    float tn = T.tmin, tx = T.tmax, v;                                    \
+    v = (nx.L - T.o.x) * T.idx; tn = PT_SSE_MAX(tn, v);                   \
+    v = (fx.L - T.o.x) * T.idx; tx = PT_SSE_MIN(tx, v);                   \
+    v = (ny.L - T.o.y) * T.idy; tn = PT_SSE_MAX(tn, v);                   \
+    v = (fy.L - T.o.y) * T.idy; tx = PT_SSE_MIN(tx, v);                   \
+    v = (nz.L - T.o.z) * T.idz; tn = PT_SSE_MAX(tn, v);                   \
+    v = (fz.L - T.o.z) * T.idz; tx = PT_SSE_MIN(tx, v);                   \
+    if (tx >= tn) mask |= BIT;                                            \
+  }
+      PT_LANE2(x, 1u) PT_LANE2(y, 2u) PT_LANE2(z, 4u) PT_LANE2(w, 8u)
+#undef PT_LANE2
+      if (mask) {
+        int at = meta.x & 3, al = (meta.x >> 2) & 3, ar = (meta.x >> 4) & 3;
+        int s_t = (T.sg >> at) & 1, s_l = (T.sg >> al) & 1, s_r = (T.sg >> ar) & 1;
+        uint32_t order = kOrderTable[mask * 8 + (unsigned)((s_t << 2) | (s_l << 1) | s_r)];
+        while ((order & 0x4) == 0) {
+          int k = (int)(order & 3);
+          int c = k == 0 ? ch.x : (k == 1 ? ch.y : (k == 2 ? ch.z : ch.w));
+          if (c != PT_EMPTY) {
+            if (!st.push(c)) *overflow = 1;
+          }
+          order >>= 4;
+        }
+      }
+      trav_pop(T, st);
+      return;
+    }
+  } else {
+    if (COUNT) cnt->nodes++;
+    unsigned e = (unsigned)~T.cur;
+    first = (int)(e >> PT_LEAF_BITS);
+    count = (int)(e & ((1u << PT_LEAF_BITS) - 1u)) + 1;
+  }
+  // ---- leaf: intersect_primitives[_p] over recs[first .. first + count) in order --------------------------------
+  const f4* r = S.recs + ((size_t)T.rec_base + (size_t)first) * 3;
+  for (int i = 0; i < count; i++, r += 3) {
+    f4 v0 = ldg4(r), v1 = ldg4(r + 1), v2 = ldg4(r + 2);
+    if (INST && (fbits(v1.w) & PT_REC_INSTANCE)) {
+      // TransformedPrimitive::intersect[_p] (only top-level leaves hold instances)
+      int inst = (int)fbits(v0.w);
+      const InstanceRec& I = S.instances[inst];
+      const ObjectRec& O = S.objects[I.object];
+      DRay wr;
+      wr.o = T.o; wr.d = T.d; wr.tmax = T.ray_tmax; wr.time = T.time;
+      DRay q = xform_ray(I.minv, wr);
+      if (O.n_prims == 0) continue;
+      if (O.single) {  // one primitive, no accelerator: test it in object space right here
+        const f4* pr = S.recs + (size_t)O.rec_base * 3;
+        f3 so = T.o, sd = T.d;
+        T.o = q.o; T.d = q.d; T.inst = inst;
+        bool fin = trav_triangle<COUNT>(T, ldg4(pr), ldg4(pr + 1), ldg4(pr + 2), cnt);
+        T.o = so; T.d = sd; T.inst = -1;
+        if (fin) { T.done = true; return; }
+        continue;
+      }
+      float tn, tx;
+      if (!bounds_range(O.bmin, O.bmax, q.o, q.d, T.ray_tmax, &tn, &tx)) continue;
+      // push back the rest of this leaf (in order, chunks of <= 8), then the barrier, and descend
+      int rest = count - (i + 1), rfirst = first + i + 1;
+      while (rest > 0) {  // last chunk first so that the chunks pop in order
+        int nchunks = (rest + 7) >> 3;
+        int cfirst = rfirst + (nchunks - 1) * 8, ccount = rest - (nchunks - 1) * 8;
+        if (!st.push(~(int)(((unsigned)cfirst << PT_LEAF_BITS) | (unsigned)(ccount - 1)))) *overflow = 1;
+        if (COUNT) cnt->nodes--;  // a leaf remainder is not a node visit of the reference traversal
+        rest -= ccount;
+      }
+      if (!st.push(PT_STACK_BARRIER)) *overflow = 1;
+      T.so = T.o; T.sd = T.d; T.stmin = T.tmin; T.stmax = T.tmax;
+      trav_set_ray(T, q.o, q.d);
+      T.tmin = tn; T.tmax = tx;
+      T.node_base = O.node_base; T.rec_base = O.rec_base;
+      T.inst = inst;
+      T.outer_hit = T.leaf_hit;
+      T.leaf_hit = false;
+      T.nested_hit = false;
+      T.cur = 0;
+      return;
+    }
+    if (trav_triangle<COUNT>(T, v0, v1, v2, cnt)) { T.done = true; return; }
+  }
+  if (T.leaf_hit) {  // qbvh_x86.rs:279-283: tmax = r.t_max after a leaf that reported a hit
+    T.tmax = T.ray_tmax;
+    T.leaf_hit = false;
+    if (INST && T.inst >= 0) T.nested_hit = true;
+  }
+  trav_pop(T, st);
+}
+
+}  // namespace ptd

@@ -3,6 +3,7 @@
 // bounces.  All kernels of a render run on one stream in program order.
 #pragma once
 #include "dfilm.cuh"
+#include "dtrav2.cuh"
 
 namespace ptd {
 
@@ -31,6 +32,100 @@ struct SharedStack {
   }
 };
 
+// Persistent-warp traversal driver.  Every lane owns one ray at a time; when PT_REFILL_MIN or more lanes of a warp are
+// idle the warp claims that many new rays with ONE atomicAdd on the launch's fetch counter (ballot / popc ranks),
+// so lanes do not wait for the slowest ray of a fixed 32-ray batch.  IO supplies the rays and consumes the results:
+//   void load(uint32_t k, Trav& T)   -> trav_begin(...)        void store(uint32_t k, const Trav& T)
+#define PT_REFILL_MIN 8
+template <bool INST, bool COUNT, typename IO>
+__device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32_t total, uint32_t* fetch, SharedStack& st, int* ovf, TravCounters* tc) {
+  Trav T;
+  T.done = true;
+#if defined(__CUDA_ARCH__)
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  bool have = false, exhausted = false;
+  uint32_t myk = 0;
+  for (;;) {
+    unsigned idle = __ballot_sync(FULL, !have);
+    int nidle = __popc(idle);
+    if (!exhausted && nidle >= PT_REFILL_MIN) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(fetch, (uint32_t)nidle);
+      base = __shfl_sync(FULL, base, 0);
+      if (!have) {
+        uint32_t k = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if (k < total) {
+          myk = k;
+          st.n = 0;
+          io.load(k, T);
+          have = true;
+          if (T.done) { io.store(k, T); have = false; }
+        }
+      }
+      if (base + (uint32_t)nidle >= total) exhausted = true;
+    }
+    unsigned active = __ballot_sync(FULL, have);
+    if (active == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    for (;;) {
+      if (have) {
+        trav_step<INST, COUNT>(S, T, st, ovf, tc);
+        if (T.done) { io.store(myk, T); have = false; }
+      }
+      unsigned a = __ballot_sync(FULL, have);
+      if (a == 0) break;
+      if (!exhausted && __popc(a) <= 32 - PT_REFILL_MIN) break;
+    }
+  }
+#else
+  (void)fetch;
+  for (uint32_t k = 0; k < total; k++) {  // tests/hostcheck: serial
+    st.n = 0;
+    io.load(k, T);
+    while (!T.done) trav_step<INST, COUNT>(S, T, st, ovf, tc);
+    io.store(k, T);
+  }
+#endif
+}
+
+// rays and results of the wavefront: continuation (A) rays, then MIS (C) rays, then shadow (B) rays
+template <int NC, bool INST>
+struct WaveIO {
+  const DScene& S;
+  WaveState& W;
+  Queues& Q;
+  uint32_t n_ext, n_mis;
+  __device__ __forceinline__ void load(uint32_t k, Trav& T) {
+    if (k < n_ext + n_mis) {
+      const bool is_ext = k < n_ext;
+      uint32_t i = is_ext ? Q.ext[k] : Q.mis[k - n_ext];
+      f4 o = is_ext ? W.ray_o[i] : W.mis_o[i], d = is_ext ? W.ray_d[i] : W.mis_d[i];
+      trav_begin(S, T, xyz(o), xyz(d), o.w, d.w, false);
+    } else {
+      uint32_t i = Q.shadow[k - n_ext - n_mis];
+      f4 o = W.sh_o[i], d = W.sh_d[i];
+      trav_begin(S, T, xyz(o), xyz(d), d.w, W.ray_d[i].w, true);
+    }
+  }
+  __device__ __forceinline__ void store(uint32_t k, const Trav& T) {
+    if (k < n_ext) {
+      uint32_t i = Q.ext[k];
+      W.hit[i] = mk4(T.hit.b0, T.hit.b1, T.hit.b2, bitsf((uint32_t)(T.found ? T.hit.tri : -1)));
+      if (INST) W.hit_inst[i] = T.found ? T.hit.instance : -1;
+      if (T.found) W.ray_o[i].w = T.ray_tmax;
+    } else if (k < n_ext + n_mis) {
+      uint32_t i = Q.mis[k - n_ext];
+      mis_resolve<NC>(S, W, i, T.hit, T.found, xyz(W.mis_d[i]));
+    } else {
+      uint32_t i = Q.shadow[k - n_ext - n_mis];
+      if (T.found) st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(0.0f));
+    }
+  }
+};
+
 // Scene::intersect for continuation (A) and MIS (C) rays, Scene::intersect_p for shadow (B) rays, in one launch.
 template <int NC, bool INST, bool COUNT>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(const DScene* __restrict__ Sp, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
@@ -39,33 +134,12 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(const DScene* __restri
   const DScene& S = *Sp;
   SharedStack st;
   st.sm = smem + threadIdx.x;
+  st.n = 0;
   TravCounters tc;
   tc.nodes = 0; tc.tris = 0;
   int ovf = 0;
-  const uint32_t total = n_ext + n_mis + n_sh;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-    st.n = 0;
-    if (k < n_ext + n_mis) {  // one copy of the closest-hit traversal for both ray classes
-      const bool is_ext = k < n_ext;
-      uint32_t i = is_ext ? Q.ext[k] : Q.mis[k - n_ext];
-      f4 o = is_ext ? W.ray_o[i] : W.mis_o[i], d = is_ext ? W.ray_d[i] : W.mis_d[i];
-      float tmax = o.w;
-      HitD h;
-      bool found = scene_intersect<INST, COUNT>(S, xyz(o), xyz(d), d.w, tmax, &h, st, &ovf, &tc);
-      if (is_ext) {
-        W.hit[i] = mk4(h.b0, h.b1, h.b2, bitsf((uint32_t)(found ? h.tri : -1)));
-        if (INST) W.hit_inst[i] = found ? h.instance : -1;
-        if (found) W.ray_o[i].w = tmax;
-      } else {
-        mis_resolve<NC>(S, W, i, h, found, xyz(d));
-      }
-    } else {
-      uint32_t i = Q.shadow[k - n_ext - n_mis];
-      f4 o = W.sh_o[i], d = W.sh_d[i];
-      bool occ = scene_intersect_p<INST, COUNT>(S, xyz(o), xyz(d), W.ray_d[i].w, d.w, st, &ovf, &tc);
-      if (occ) st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(0.0f));
-    }
-  }
+  WaveIO<NC, INST> io{S, W, Q, n_ext, n_mis};
+  trace_persistent<INST, COUNT>(S, io, n_ext + n_mis + n_sh, Q.counts + 4, st, &ovf, &tc);
   if (COUNT) {
     atomicAdd(&counters[0], tc.nodes);
     atomicAdd(&counters[1], tc.tris);
@@ -128,44 +202,41 @@ __global__ void k_film_resolve(const DScene* __restrict__ Sp, const f4* film, fl
 }
 
 // ---- stage entry points ----------------------------------------------------------------------------------------
+struct ArrayIO {  // pt_intersect / pt_intersect_p / pt_intersect_device: rays and results in plain arrays
+  const DScene& S;
+  const f4* ro;
+  const f4* rd;
+  f4* hits;
+  float* t_out;
+  unsigned char* occ;
+  bool any;
+  __device__ __forceinline__ void load(uint32_t k, Trav& T) {
+    f4 o = ro[k], d = rd[k];
+    trav_begin(S, T, xyz(o), xyz(d), o.w, d.w, any);
+  }
+  __device__ __forceinline__ void store(uint32_t k, const Trav& T) {
+    if (any) { occ[k] = T.found ? 1 : 0; return; }
+    hits[k] = mk4(T.hit.b0, T.hit.b1, T.hit.b2, bitsf((uint32_t)(T.found ? T.hit.tri : -1)));
+    if (t_out) t_out[k] = T.found ? T.hit.t : 0.0f;
+  }
+};
 template <bool INST, bool COUNT>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_intersect(const DScene* __restrict__ Sp, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
-                                                              f4* hits, float* t_out, unsigned long long* counters, int* overflow) {
+                                                              f4* hits, float* t_out, unsigned char* occ, uint32_t* fetch, unsigned long long* counters,
+                                                              int* overflow) {
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
   const DScene& S = *Sp;
   SharedStack st;
   st.sm = smem + threadIdx.x;
+  st.n = 0;
   TravCounters tc;
   tc.nodes = 0; tc.tris = 0;
   int ovf = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    st.n = 0;
-    f4 o = ro[i], d = rd[i];
-    float tmax = o.w;
-    HitD h;
-    bool found = scene_intersect<INST, COUNT>(S, xyz(o), xyz(d), d.w, tmax, &h, st, &ovf, &tc);
-    hits[i] = mk4(h.b0, h.b1, h.b2, bitsf((uint32_t)(found ? h.tri : -1)));
-    if (t_out) t_out[i] = found ? h.t : 0.0f;
-  }
+  ArrayIO io{S, ro, rd, hits, t_out, occ, occ != nullptr};
+  trace_persistent<INST, COUNT>(S, io, n, fetch, st, &ovf, &tc);
   if (COUNT) {
     atomicAdd(&counters[0], tc.nodes);
     atomicAdd(&counters[1], tc.tris);
-  }
-  if (ovf) *overflow = 1;
-}
-template <bool INST>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_intersect_p(const DScene* __restrict__ Sp, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
-                                                                unsigned char* occ, int* overflow) {
-  __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
-  const DScene& S = *Sp;
-  SharedStack st;
-  st.sm = smem + threadIdx.x;
-  TravCounters tc;
-  int ovf = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    st.n = 0;
-    f4 o = ro[i], d = rd[i];
-    occ[i] = scene_intersect_p<INST, false>(S, xyz(o), xyz(d), d.w, o.w, st, &ovf, &tc) ? 1 : 0;
   }
   if (ovf) *overflow = 1;
 }
