@@ -226,6 +226,22 @@ struct Lobe {
   float a, b;     // Oren-Nayar A,B | alpha_x, alpha_y
   float ei, et;   // dielectric Fresnel eta_i, eta_t | transmission eta_a, eta_b
 };
+// Compile-time lobe sets: a shade kernel specialised for one material class only keeps the code of the lobes and
+// Fresnel terms that class can produce (bits 0-5: LB_* kinds, bits 8-10: FR_* kinds).
+#define PT_CM_ANY 0x73f
+#define PT_CM_MATTE 0x103
+#define PT_CM_PLASTIC 0x311
+#define PT_CM_MIRROR 0x104
+#define PT_CM_GLASS 0x338
+#define PT_CM_METAL 0x410
+#if defined(__CUDACC__) || defined(__GNUC__)
+#define PT_UNREACHABLE() __builtin_unreachable()
+#else
+#define PT_UNREACHABLE()
+#endif
+#define PT_KIND(K) case K: if (!((CM >> (K)) & 1)) { PT_UNREACHABLE(); }
+#define PT_HAS_FRES(F) (((CM >> (8 + (F))) & 1) != 0)
+
 PT_HD int lobe_type(int kind) {
   switch (kind) {
     case LB_LAMBERT: case LB_OREN: return F_REFL | F_DIFF;
@@ -237,10 +253,11 @@ PT_HD int lobe_type(int kind) {
 }
 PT_HD bool lobe_matches(int kind, int flags) { int t = lobe_type(kind); return (t & flags) == t; }
 
-template <int NC>
+template <int NC, int CM = PT_CM_ANY>
 PT_HD Sp<NC> lobe_fresnel(const DScene& S, const Lobe& L, float ci) {
-  if (L.fres == FR_NOOP) return sp_const<NC>(1.0f);
-  if (L.fres == FR_DIEL) return sp_const<NC>(fr_diel(ci, L.ei, L.et));
+  if (PT_HAS_FRES(FR_NOOP) && (L.fres == FR_NOOP || (!PT_HAS_FRES(FR_DIEL) && !PT_HAS_FRES(FR_COND)))) return sp_const<NC>(1.0f);
+  if (PT_HAS_FRES(FR_DIEL) && (L.fres == FR_DIEL || !PT_HAS_FRES(FR_COND))) return sp_const<NC>(fr_diel(ci, L.ei, L.et));
+  if (!PT_HAS_FRES(FR_COND)) return sp_const<NC>(1.0f);
   Sp<NC> r;
   float c = clampf(fabsf(ci), -1.0f, 1.0f);
   const float* e = S.spectra + (size_t)L.sp0 * NC;
@@ -250,11 +267,11 @@ PT_HD Sp<NC> lobe_fresnel(const DScene& S, const Lobe& L, float ci) {
   return r;
 }
 
-template <int NC>
+template <int NC, int CM = PT_CM_ANY>
 PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
   switch (L.kind) {
-    case LB_LAMBERT: return sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * PT_INV_PI;
-    case LB_OREN: {
+    PT_KIND(LB_LAMBERT) return sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * PT_INV_PI;
+    PT_KIND(LB_OREN) {
       float sti = sth(wi), sto = sth(wo);
       float max_cos = 0.0f;
       if (sti > 1e-4f && sto > 1e-4f) {
@@ -266,19 +283,19 @@ PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
       else { sin_alpha = sti; tan_beta = sto / acth(wo); }
       return sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * PT_INV_PI * (L.a + L.b * max_cos * sin_alpha * tan_beta);
     }
-    case LB_MF_REFL: {
+    PT_KIND(LB_MF_REFL) {
       float cto = acth(wo), cti = acth(wi);
       f3 wh = wi + wo;
       if (cti == 0.0f || cto == 0.0f) return sp_const<NC>(0.0f);
       if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return sp_const<NC>(0.0f);
       wh = norm3(wh);
-      Sp<NC> F = lobe_fresnel<NC>(S, L, dot3(wi, faceforward(wh, mk3(0.0f, 0.0f, 1.0f))));
+      Sp<NC> F = lobe_fresnel<NC, CM>(S, L, dot3(wi, faceforward(wh, mk3(0.0f, 0.0f, 1.0f))));
       TR D; D.ax = L.a; D.ay = L.b;
       float k = tr_d(D, wh) * tr_g(D, wo, wi) / (4.0f * cti * cto);
       Sp<NC> R = (L.fres == FR_COND) ? sp_const<NC>(1.0f) : sp_load<NC>(S.spectra + (size_t)L.sp0 * NC);
       return R * F * k;
     }
-    case LB_MF_TRANS: {
+    PT_KIND(LB_MF_TRANS) {
       if (same_hemi(wo, wi)) return sp_const<NC>(0.0f);
       float cto = cth(wo), cti = cth(wi);
       if (cti == 0.0f || cto == 0.0f) return sp_const<NC>(0.0f);
@@ -297,17 +314,18 @@ PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
     default: return sp_const<NC>(0.0f);
   }
 }
+template <int CM = PT_CM_ANY>
 PT_HDN float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
   switch (L.kind) {
-    case LB_LAMBERT: case LB_OREN: return same_hemi(wo, wi) ? acth(wi) * PT_INV_PI : 0.0f;
-    case LB_MF_REFL: {
+    case LB_LAMBERT: case LB_OREN: if (!(CM & 3)) { PT_UNREACHABLE(); } return same_hemi(wo, wi) ? acth(wi) * PT_INV_PI : 0.0f;
+    PT_KIND(LB_MF_REFL) {
       if (!same_hemi(wo, wi)) return 0.0f;
       f3 wh = norm3(wo + wi);
       if (dot3(wo, wh) < 0.0f) return 0.0f;
       TR D; D.ax = L.a; D.ay = L.b;
       return tr_pdf(D, wo, wh) / (4.0f * dot3(wo, wh));
     }
-    case LB_MF_TRANS: {
+    PT_KIND(LB_MF_TRANS) {
       if (same_hemi(wo, wi)) return 0.0f;
       float eta = cth(wo) > 0.0f ? L.et / L.ei : L.ei / L.et;
       f3 wh = norm3(wo + (wi * eta));
@@ -322,26 +340,27 @@ PT_HDN float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
   }
 }
 // BxDF::sample_f of one lobe; stype = 0 means "the lobe's own type"
-template <int NC>
+template <int NC, int CM = PT_CM_ANY>
 PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, f3* wi_out, float* pdf, int* stype) {
   *stype = 0;
   switch (L.kind) {
     case LB_LAMBERT: case LB_OREN: {
+      if (!(CM & 3)) { PT_UNREACHABLE(); }
       f3 wi = cosine_hemisphere(u);
       if (wo.z < 0.0f) wi.z *= -1.0f;
-      *pdf = lobe_pdf(L, wo, wi);
-      *f = lobe_f<NC>(S, L, wo, wi);
+      *pdf = lobe_pdf<CM>(L, wo, wi);
+      *f = lobe_f<NC, CM>(S, L, wo, wi);
       *wi_out = wi;
       return true;
     }
-    case LB_MIRROR: {
+    PT_KIND(LB_MIRROR) {
       f3 wi = mk3(-wo.x, -wo.y, wo.z);
       *pdf = 1.0f;
       *f = (sp_const<NC>(1.0f) * sp_load<NC>(S.spectra + (size_t)L.sp0 * NC)) / acth(wi);
       *wi_out = wi;
       return true;
     }
-    case LB_FRESNEL_SPEC: {
+    PT_KIND(LB_FRESNEL_SPEC) {
       float F = fr_diel(cth(wo), L.ei, L.et);
       if (u.x < F) {
         f3 wi = mk3(-wo.x, -wo.y, wo.z);
@@ -364,7 +383,7 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, 
       *wi_out = wi;
       return true;
     }
-    case LB_MF_REFL: {
+    PT_KIND(LB_MF_REFL) {
       if (wo.z == 0.0f) return false;
       TR D; D.ax = L.a; D.ay = L.b;
       f3 wh = tr_sample_wh(D, wo, u);
@@ -374,11 +393,12 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, 
       float p = tr_pdf(D, wo, wh) / (4.0f * dot3(wo, wh));
       if (p == 0.0f) return false;
       *pdf = p;
-      *f = lobe_f<NC>(S, L, wo, wi);
+      *f = lobe_f<NC, CM>(S, L, wo, wi);
       *wi_out = wi;
       return true;
     }
     default: {
+      if (!((CM >> LB_MF_TRANS) & 1)) { PT_UNREACHABLE(); }
       if (wo.z == 0.0f) return false;
       TR D; D.ax = L.a; D.ay = L.b;
       f3 wh = tr_sample_wh(D, wo, u);
@@ -386,10 +406,10 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, 
       float eta = cth(wo) > 0.0f ? L.ei / L.et : L.et / L.ei;
       f3 wi;
       if (!refract3(wo, wh, eta, &wi)) return false;
-      float p = lobe_pdf(L, wo, wi);
+      float p = lobe_pdf<CM>(L, wo, wi);
       if (!(p > 0.0f)) return false;
       *pdf = p;
-      *f = lobe_f<NC>(S, L, wo, wi);
+      *f = lobe_f<NC, CM>(S, L, wo, wi);
       *wi_out = wi;
       return true;
     }
@@ -530,7 +550,7 @@ PT_HD bool spectrum_black(const DScene& S, int idx, bool clamp0) {
 // Material::compute_scattering_functions for the five in-scope materials.
 // Spectra that the reference clamps (clamp_zero) are clamped on the HOST at upload when a negative value is
 // present, so the device can treat every stored reflectance as already clamped except matte Kd (never clamped).
-template <int NC>
+template <int NC, int MT = -1>
 PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   B->n = -1;
   int mi = ldg(S.tri_material + si.tri);
@@ -540,6 +560,7 @@ PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   int n = 0;
   switch (M.type) {
     case PT_MAT_MATTE: {
+      if (MT != -1 && MT != PT_MAT_MATTE) { PT_UNREACHABLE(); }
       if (!spectrum_black<NC>(S, M.kd, false)) {
         Lobe& L = B->lobe[n++];
         L.sp0 = M.kd; L.sp1 = -1; L.fres = FR_NOOP; L.ei = L.et = 1.0f;
@@ -556,6 +577,7 @@ PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
       break;
     }
     case PT_MAT_PLASTIC: {
+      if (MT != -1 && MT != PT_MAT_PLASTIC) { PT_UNREACHABLE(); }
       if (!spectrum_black<NC>(S, M.kd, true)) {
         Lobe& L = B->lobe[n++];
         L.kind = LB_LAMBERT; L.sp0 = M.kd; L.sp1 = -1; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = L.et = 1.0f;
@@ -569,6 +591,7 @@ PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
       break;
     }
     case PT_MAT_MIRROR: {
+      if (MT != -1 && MT != PT_MAT_MIRROR) { PT_UNREACHABLE(); }
       if (!spectrum_black<NC>(S, M.kr, true)) {
         Lobe& L = B->lobe[n++];
         L.kind = LB_MIRROR; L.sp0 = M.kr; L.sp1 = -1; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = L.et = 1.0f;
@@ -576,6 +599,7 @@ PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
       break;
     }
     case PT_MAT_GLASS: {
+      if (MT != -1 && MT != PT_MAT_GLASS) { PT_UNREACHABLE(); }
       bool rb = spectrum_black<NC>(S, M.kr, false), tb = spectrum_black<NC>(S, M.ks, false);
       if (rb && tb) return;  // no BSDF at all
       eta = M.eta;
@@ -596,6 +620,7 @@ PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
       break;
     }
     case PT_MAT_METAL: {
+      if (MT != -1 && MT != PT_MAT_METAL) { PT_UNREACHABLE(); }
       Lobe& L = B->lobe[n++];
       L.kind = LB_MF_REFL; L.sp0 = M.kr; L.sp1 = M.ks; L.fres = FR_COND; L.ei = L.et = 1.0f;
       L.a = fmaxf(0.001f, ldg(S.alpha + 2 * mi)); L.b = fmaxf(0.001f, ldg(S.alpha + 2 * mi + 1));
@@ -611,32 +636,33 @@ PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   B->ts = norm3(cross3(B->ns, B->ss));
 }
 
-template <int NC>
+template <int NC, int CM = PT_CM_ANY>
 PT_HD Sp<NC> bsdf_sum_f(const DScene& S, const BsdfD& B, f3 wo, f3 wi, f3 wo_w, f3 wi_w, int flags) {
   bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
   Sp<NC> r = sp_const<NC>(0.0f);
   for (int i = 0; i < B.n; i++) {
     int tp = lobe_type(B.lobe[i].kind);
-    if (lobe_matches(B.lobe[i].kind, flags) && ((refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS)))) r = r + lobe_f<NC>(S, B.lobe[i], wo, wi);
+    if (lobe_matches(B.lobe[i].kind, flags) && ((refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS)))) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
   }
   return r;
 }
-template <int NC>
+template <int NC, int CM = PT_CM_ANY>
 PT_HDN Sp<NC> bsdf_f(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return sp_const<NC>(0.0f);
-  return bsdf_sum_f<NC>(S, B, wo, wi, wo_w, wi_w, flags);
+  return bsdf_sum_f<NC, CM>(S, B, wo, wi, wo_w, wi_w, flags);
 }
+template <int CM = PT_CM_ANY>
 PT_HDN float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return 0.0f;
   int count = 0;
   float p = 0.0f;
   for (int i = 0; i < B.n; i++)
-    if (lobe_matches(B.lobe[i].kind, flags)) { p = p + lobe_pdf(B.lobe[i], wo, wi); count++; }
+    if (lobe_matches(B.lobe[i].kind, flags)) { p = p + lobe_pdf<CM>(B.lobe[i], wo, wi); count++; }
   return count > 0 ? p / (float)count : 0.0f;
 }
-template <int NC>
+template <int NC, int CM = PT_CM_ANY>
 PT_HDN bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags, Sp<NC>* f, f3* wi_w_out, float* pdf_out, int* stype) {
   int matching = bsdf_count(B, flags);
   if (matching == 0) return false;
@@ -653,16 +679,16 @@ PT_HDN bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flag
   f3 wi;
   float pdf;
   int t;
-  if (!lobe_sample<NC>(S, L, wo, ur, &fv, &wi, &pdf, &t)) return false;
+  if (!lobe_sample<NC, CM>(S, L, wo, ur, &fv, &wi, &pdf, &t)) return false;
   if (pdf <= 0.0f) return false;
   int ltype = lobe_type(L.kind);
   int sampled = t != 0 ? t : ltype;
   f3 wi_w = to_world(B, wi);
   if ((ltype & F_SPEC) == 0 && matching > 1)
     for (int i = 0; i < B.n; i++)
-      if (i != index && lobe_matches(B.lobe[i].kind, flags)) pdf += lobe_pdf(B.lobe[i], wo, wi);
+      if (i != index && lobe_matches(B.lobe[i].kind, flags)) pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
   if (matching > 1) pdf /= (float)matching;
-  if ((ltype & F_SPEC) == 0) fv = bsdf_sum_f<NC>(S, B, wo, wi, wo_w, wi_w, flags);
+  if ((ltype & F_SPEC) == 0) fv = bsdf_sum_f<NC, CM>(S, B, wo, wi, wo_w, wi_w, flags);
   *f = fv; *wi_w_out = wi_w; *pdf_out = pdf; *stype = sampled;
   return true;
 }

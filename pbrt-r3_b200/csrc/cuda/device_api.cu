@@ -114,6 +114,7 @@ struct pt_scene {
   unsigned long long* counters = nullptr;  // [0] nodes [1] tris [2] vertices
   int* overflow = nullptr;
   uint32_t* fetch = nullptr;               // ray fetch counter of the stage entry points
+  uint32_t class_mask = 1;                 // shading classes present in the scene (bit CL_*); CL_NONE always
   uint32_t wave_cap = 0;
   // pixel list cache
   int* pixlist = nullptr;
@@ -282,6 +283,9 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
     alpha[2 * m] = ur;
     alpha[2 * m + 1] = vr;
   }
+  s->class_mask = 1u;
+  for (uint32_t m = 0; m < D->n_materials; m++)
+    if (mats[m].type >= 0 && mats[m].type <= 4) s->class_mask |= 1u << (mats[m].type + 1);
   CK(s->bufs.upload(spectra.data(), spectra.size(), &H.spectra));
   CK(s->bufs.upload(mats.data(), mats.size(), &H.materials));
   CK(s->bufs.upload(alpha.data(), alpha.size(), &H.alpha));
@@ -463,8 +467,9 @@ int ensure_wave(pt_scene* s, uint32_t cap) {
   CK(B.alloc(cap, &W.sh_o)); CK(B.alloc(cap, &W.sh_d)); CK(B.alloc((size_t)cap * NC, &W.pendA));
   CK(B.alloc(cap, &W.mis_o)); CK(B.alloc(cap, &W.mis_d)); CK(B.alloc((size_t)cap * NC, &W.pendB)); CK(B.alloc(cap, &W.mis_light));
   Queues& Q = s->Q;
-  CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(8, &Q.counts));
-  CK(cudaMemset(Q.counts, 0, 8 * sizeof(uint32_t)));
+  CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(16, &Q.counts));
+  CK(cudaMemset(Q.counts, 0, 16 * sizeof(uint32_t)));
+  CK(B.alloc((size_t)cap * CL_COUNT, &Q.bins));
   s->wave_cap = cap;
   return 0;
 }
@@ -488,6 +493,7 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     if (++guard > 100000) { pt_set_error("bounce loop did not terminate"); return 1; }
     uint32_t total = counts[0] + counts[3] + counts[2];
     int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
+    CK(cudaMemsetAsync(Q.counts + 8, 0, 8 * sizeof(uint32_t), s->stream));  // shading-class bin sizes
     if (timed) cudaEventRecord(e0, s->stream);
 #define LAUNCH_TRACE(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_trace<NC, I, C>)(s->d, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
     if (inst) { if (count) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
@@ -503,9 +509,12 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     uint32_t n_ext = counts[0];
     CK(cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream));  // queue counters + the trace fetch counter
     if (n_ext > 0) {
-      PT_LAUNCH(grid_for(s, n_ext, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_shade<NC>)(s->d, W, Q, n_ext, count ? s->counters + 2 : nullptr);
+      int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
+      unsigned long long* vc = count ? s->counters + 2 : nullptr;
+#define LAUNCH_SHADE(C) if (s->class_mask & (1u << (C))) { PT_LAUNCH(gs, PT_SHADE_BLOCK, s->stream, k_shade<NC, C>)(s->d, W, Q, vc); T->launches++; }
+      LAUNCH_SHADE(CL_NONE) LAUNCH_SHADE(CL_MATTE) LAUNCH_SHADE(CL_PLASTIC) LAUNCH_SHADE(CL_GLASS) LAUNCH_SHADE(CL_METAL) LAUNCH_SHADE(CL_MIRROR)
+#undef LAUNCH_SHADE
       CK(cudaGetLastError());
-      T->launches++;
     }
     if (timed) cudaEventRecord(e2, s->stream);
     CK(cudaMemcpyAsync(counts, Q.counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));

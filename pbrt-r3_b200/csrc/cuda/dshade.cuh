@@ -37,12 +37,29 @@ struct WaveState {            // all arrays have `cap` path slots; spectra are c
 };
 
 struct Queues {
-  uint32_t* ext;       // path ids with a continuation ray to trace, then to shade
+  uint32_t* ext;       // path ids with a continuation ray to trace
   uint32_t* ext_next;
   uint32_t* shadow;
   uint32_t* mis;
-  uint32_t* counts;    // [0] ext, [1] ext_next, [2] shadow, [3] mis
+  uint32_t* bins;      // traced continuation rays binned by shading class: bins[cls * cap + k]
+  uint32_t* counts;    // [0] ext, [1] ext_next, [2] shadow, [3] mis, [4] trace fetch counter, [8 + cls] bin sizes
 };
+
+// Shading classes: one specialised shade kernel per material plugin ("sort by material"); class 0
+// takes the paths that need no BSDF: misses, paths at max depth, surfaces without a material.
+enum { CL_NONE = 0, CL_MATTE = 1, CL_PLASTIC = 2, CL_GLASS = 3, CL_METAL = 4, CL_MIRROR = 5, CL_COUNT = 6, CL_ANY = 7 };
+PT_HD constexpr int cls_cm(int c) {
+  return c == CL_MATTE ? PT_CM_MATTE : c == CL_PLASTIC ? PT_CM_PLASTIC : c == CL_GLASS ? PT_CM_GLASS : c == CL_METAL ? PT_CM_METAL : c == CL_MIRROR ? PT_CM_MIRROR : PT_CM_ANY;
+}
+PT_HD constexpr int cls_mt(int c) { return (c >= CL_MATTE && c <= CL_MIRROR) ? c - 1 : -1; }
+// class of a traced continuation ray (pt_material_type + 1)
+PT_HD int shade_class(const DScene& S, int tri, int bounces) {
+  if (tri < 0 || bounces >= S.integrator.max_depth) return CL_NONE;
+  int mi = ldg(S.tri_material + tri);
+  if (mi < 0) return CL_NONE;
+  int t = S.materials[mi].type;
+  return (t >= 0 && t <= 4) ? t + 1 : CL_NONE;
+}
 
 // PerspectiveCamera::generate_ray_differential without the differentials (constant textures: they cannot reach L)
 PT_HD DRay camera_ray(const pt_camera& C, f2 p_film, f2 p_lens, float time) {
@@ -245,8 +262,9 @@ PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int
 }
 
 // One iteration of PathIntegrator::li's loop body after scene.intersect (path.rs:87-233) for path slot i.
-template <int NC>
+template <int NC, int CLS>
 PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsigned long long* vertex_counter) {
+  constexpr int CM = cls_cm(CLS), MT = cls_mt(CLS);
   const uint32_t cap = W.cap;
   // contributions of the previous vertex (shadow / MIS rays were resolved by the trace stage)
   Sp<NC> L = st_load<NC>(W.L, cap, i);
@@ -276,10 +294,11 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   }
   if (!found || bounces >= S.integrator.max_depth) { st_store<NC>(W.L, cap, i, L); return; }
   BsdfD B;
-  make_bsdf<NC>(S, si, &B);
+  B.n = -1;
+  if (CLS != CL_NONE) make_bsdf<NC, MT>(S, si, &B);
   RefPt ref;
   ref.p = si.p; ref.perr = si.perr; ref.n = si.n;
-  if (B.n < 0) {  // no BSDF: continue through the surface, bounces unchanged (path.rs:108-111)
+  if (CLS == CL_NONE || B.n < 0) {  // no BSDF: continue through the surface, bounces unchanged (path.rs:108-111)
     f3 o = offset_origin(si.p, si.perr, si.n, rd);
     W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
     st_store<NC>(W.L, cap, i, L);
@@ -302,7 +321,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   const int NONSPEC = F_ALL & ~F_SPEC;
 
   // --- uniform_sample_one_light_surface + estimate_direct_surface (sample_lights.rs:129-176, 330-453)
-  if (bsdf_count(B, NONSPEC) > 0 && S.n_lights > 0) {
+  if (CLS != CL_MIRROR && bsdf_count(B, NONSPEC) > 0 && S.n_lights > 0) {
     float light_pdf;
     int ln = ld_sample(S, si.p, get1d(S, st), &light_pdf);
 #ifdef PT_DEBUG_PRINT
@@ -319,8 +338,8 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
         fprintf(stderr, "[hc] ls pdf %g li %g wi=(%g %g %g) sh_o=(%.9g %.9g %.9g) sh_d=(%.9g %.9g %.9g)\n", ls.pdf, ls.li.c[0], ls.wi.x, ls.wi.y, ls.wi.z, ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, ls.sh_d.x, ls.sh_d.y, ls.sh_d.z);
 #endif
         if (ls.pdf > 0.0f && !sp_black(ls.li)) {
-          Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
-          float spdf = bsdf_pdf(B, si.wo, ls.wi, NONSPEC);
+          Sp<NC> f = bsdf_f<NC, CM>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
+          float spdf = bsdf_pdf<CM>(B, si.wo, ls.wi, NONSPEC);
           if (!sp_black(f)) {
             Sp<NC> ld;
             if (delta) ld = f * ls.li / ls.pdf;
@@ -337,7 +356,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
         f3 wi2;
         float pdf2;
         int stype;
-        if (bsdf_sample<NC>(S, B, si.wo, u_scat, NONSPEC, &f2v, &wi2, &pdf2, &stype)) {
+        if (bsdf_sample<NC, CM>(S, B, si.wo, u_scat, NONSPEC, &f2v, &wi2, &pdf2, &stype)) {
           Sp<NC> f = f2v * absdot3(wi2, si.sn);
           if (!sp_black(f) && pdf2 > 0.0f) {
             float weight = 1.0f;
@@ -371,7 +390,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   float pdf;
   int sflags;
   f2 ub = get2d(S, st);
-  if (!bsdf_sample<NC>(S, B, wo, ub, F_ALL, &f, &wi, &pdf, &sflags)) return;
+  if (!bsdf_sample<NC, CM>(S, B, wo, ub, F_ALL, &f, &wi, &pdf, &sflags)) return;
   if (sp_black(f) || pdf == 0.0f) return;
   beta = beta * (f * (absdot3(wi, si.sn) / pdf));
   specular_bounce = (sflags & F_SPEC) != 0;

@@ -1,6 +1,8 @@
 // dtrav2.cuh — resumable (flat state machine) form of the two-level 4-wide BVH traversal of dtrav.cuh, for
 // persistent warps with dynamic ray fetch: a lane that finishes its ray pulls the next one instead of idling until
-// the slowest ray of its warp is done (ncu on the nested-call version: 6-15 of 32 lanes active per instruction).
+// the slowest ray of its warp is done, and the work is split in a NODE phase and a LEAF phase ("while-while") so that
+// the lanes of a warp run the slab tests together and the triangle tests together (ncu on the nested-call if-if
+// version: 6-15 of 32 lanes active per instruction).
 // Same reference semantics as dtrav.cuh (qbvh_x86.rs:231-343,373-399; transformed_primitive.rs:26-46): identical
 // node visit order, leaf order, t_max shrinking and float operations, so primitive ids and the node / triangle visit
 // counters still equal the CPU path's.
@@ -22,6 +24,7 @@ struct Trav {
   float time;
   int cur;              // entry being processed
   int sg;               // sign bits of d: bit0 x, bit1 y, bit2 z
+  int lf, lc;           // pending leaf: first record, count (lc = -1: the pending entry is the barrier)
   uint32_t node_base, rec_base;
   // level-0 state saved while inside an instance
   f3 so, sd;
@@ -47,6 +50,7 @@ PT_HD void trav_begin(const DScene& S, Trav& T, f3 o, f3 d, float tmax, float ti
   T.any = any; T.found = false; T.done = false; T.inst = -1; T.leaf_hit = false; T.outer_hit = false; T.nested_hit = false;
   T.ray_tmax = tmax; T.time = time;
   T.hit.tri = -1; T.hit.instance = -1;
+  T.lf = 0; T.lc = 0;
   const ObjectRec& O = S.objects[0];
   if (O.n_prims == 0) { T.done = true; return; }
   trav_set_ray(T, o, d);
@@ -76,37 +80,33 @@ PT_HD bool trav_triangle(Trav& T, f4 v0, f4 v1, f4 v2, TravCounters* cnt) {
   return false;
 }
 
-// Processes ONE stack entry (a node, a leaf or a leaf remainder, or the barrier) and pops the next one.
+// NODE phase: processes inner nodes (slab tests, ordered pushes, pop) until the current entry is a leaf, a leaf
+// remainder or the barrier (left pending in T.lf / T.lc), or the stack runs empty (T.done).
 template <bool INST, bool COUNT, typename Stack>
-PT_HD void trav_step(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
-  int first = -1, count = 0;
-  if (T.cur >= 0) {
-    if (INST && T.cur == PT_STACK_BARRIER) {  // TransformedPrimitive::intersect returns: back to world space
-      trav_set_ray(T, T.so, T.sd);
-      T.tmin = T.stmin; T.tmax = T.stmax;
-      const ObjectRec& O = S.objects[0];
-      T.node_base = O.node_base; T.rec_base = O.rec_base;
-      T.inst = -1;
-      // the interrupted leaf reported a hit if any of its primitives (the instance included) did: tmax = r.t_max.
-      // Its remainder, if any, is the next entry, so no node test can observe the early update.
-      if (T.outer_hit || T.nested_hit) T.tmax = T.ray_tmax;
-      T.outer_hit = false; T.nested_hit = false; T.leaf_hit = false;
-      trav_pop(T, st);
+PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
+  const int sgx = T.sg & 1, sgy = (T.sg >> 1) & 1, sgz = (T.sg >> 2) & 1;
+  for (;;) {
+    if (T.cur < 0) {  // inline leaf or leaf remainder
+      if (COUNT) cnt->nodes++;
+      unsigned e = (unsigned)~T.cur;
+      T.lf = (int)(e >> PT_LEAF_BITS);
+      T.lc = (int)(e & ((1u << PT_LEAF_BITS) - 1u)) + 1;
       return;
     }
+    if (INST && T.cur == PT_STACK_BARRIER) { T.lc = -1; return; }
     if (COUNT) cnt->nodes++;
     const QNode* nd = S.nodes + T.node_base + T.cur;
     i4 meta = ldgi4(&nd->meta);
-    if (meta.x & 0x100) {
-      first = meta.y;
-      count = meta.z;
-    } else {
-      const int sgx = T.sg & 1, sgy = (T.sg >> 1) & 1, sgz = (T.sg >> 2) & 1;
-      f4 nx = ldg4(sgx ? &nd->hi[0] : &nd->lo[0]), fx = ldg4(sgx ? &nd->lo[0] : &nd->hi[0]);
-      f4 ny = ldg4(sgy ? &nd->hi[1] : &nd->lo[1]), fy = ldg4(sgy ? &nd->lo[1] : &nd->hi[1]);
-      f4 nz = ldg4(sgz ? &nd->hi[2] : &nd->lo[2]), fz = ldg4(sgz ? &nd->lo[2] : &nd->hi[2]);
-      i4 ch = ldgi4(&nd->child);
-      unsigned mask = 0;
+    if (meta.x & 0x100) {  // leaf node in the reference's own form
+      T.lf = meta.y;
+      T.lc = meta.z;
+      return;
+    }
+    f4 nx = ldg4(sgx ? &nd->hi[0] : &nd->lo[0]), fx = ldg4(sgx ? &nd->lo[0] : &nd->hi[0]);
+    f4 ny = ldg4(sgy ? &nd->hi[1] : &nd->lo[1]), fy = ldg4(sgy ? &nd->lo[1] : &nd->hi[1]);
+    f4 nz = ldg4(sgz ? &nd->hi[2] : &nd->lo[2]), fz = ldg4(sgz ? &nd->lo[2] : &nd->hi[2]);
+    i4 ch = ldgi4(&nd->child);
+    unsigned mask = 0;
 #define PT_LANE2(L, BIT)                                                  \
   {                                                                       \
     float tn = T.tmin, tx = T.tmax, v;                                    \
@@ -118,31 +118,42 @@ PT_HD void trav_step(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
     v = (fz.L - T.o.z) * T.idz; tx = PT_SSE_MIN(tx, v);                   \
     if (tx >= tn) mask |= BIT;                                            \
   }
-      PT_LANE2(x, 1u) PT_LANE2(y, 2u) PT_LANE2(z, 4u) PT_LANE2(w, 8u)
+    PT_LANE2(x, 1u) PT_LANE2(y, 2u) PT_LANE2(z, 4u) PT_LANE2(w, 8u)
 #undef PT_LANE2
-      if (mask) {
-        int at = meta.x & 3, al = (meta.x >> 2) & 3, ar = (meta.x >> 4) & 3;
-        int s_t = (T.sg >> at) & 1, s_l = (T.sg >> al) & 1, s_r = (T.sg >> ar) & 1;
-        uint32_t order = kOrderTable[mask * 8 + (unsigned)((s_t << 2) | (s_l << 1) | s_r)];
-        while ((order & 0x4) == 0) {
-          int k = (int)(order & 3);
-          int c = k == 0 ? ch.x : (k == 1 ? ch.y : (k == 2 ? ch.z : ch.w));
-          if (c != PT_EMPTY) {
-            if (!st.push(c)) *overflow = 1;
-          }
-          order >>= 4;
+    if (mask) {
+      int at = meta.x & 3, al = (meta.x >> 2) & 3, ar = (meta.x >> 4) & 3;
+      int s_t = (T.sg >> at) & 1, s_l = (T.sg >> al) & 1, s_r = (T.sg >> ar) & 1;
+      uint32_t order = kOrderTable[mask * 8 + (unsigned)((s_t << 2) | (s_l << 1) | s_r)];
+      while ((order & 0x4) == 0) {
+        int k = (int)(order & 3);
+        int c = k == 0 ? ch.x : (k == 1 ? ch.y : (k == 2 ? ch.z : ch.w));
+        if (c != PT_EMPTY) {
+          if (!st.push(c)) *overflow = 1;
         }
+        order >>= 4;
       }
-      trav_pop(T, st);
-      return;
     }
-  } else {
-    if (COUNT) cnt->nodes++;
-    unsigned e = (unsigned)~T.cur;
-    first = (int)(e >> PT_LEAF_BITS);
-    count = (int)(e & ((1u << PT_LEAF_BITS) - 1u)) + 1;
+    if (!st.pop(&T.cur)) { T.done = true; return; }
   }
-  // ---- leaf: intersect_primitives[_p] over recs[first .. first + count) in order --------------------------------
+}
+
+// LEAF phase: the pending leaf (intersect_primitives[_p] over recs[lf .. lf + lc) in order) or the barrier, then pop.
+template <bool INST, bool COUNT, typename Stack>
+PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
+  if (INST && T.lc < 0) {  // TransformedPrimitive::intersect returns: back to world space
+    trav_set_ray(T, T.so, T.sd);
+    T.tmin = T.stmin; T.tmax = T.stmax;
+    const ObjectRec& O = S.objects[0];
+    T.node_base = O.node_base; T.rec_base = O.rec_base;
+    T.inst = -1;
+    // the interrupted leaf reported a hit if any of its primitives (the instance included) did: tmax = r.t_max.
+    // Its remainder, if any, is the next entry, so no node test can observe the early update.
+    if (T.outer_hit || T.nested_hit) T.tmax = T.ray_tmax;
+    T.outer_hit = false; T.nested_hit = false; T.leaf_hit = false;
+    trav_pop(T, st);
+    return;
+  }
+  const int first = T.lf, count = T.lc;
   const f4* r = S.recs + ((size_t)T.rec_base + (size_t)first) * 3;
   for (int i = 0; i < count; i++, r += 3) {
     f4 v0 = ldg4(r), v1 = ldg4(r + 1), v2 = ldg4(r + 2);

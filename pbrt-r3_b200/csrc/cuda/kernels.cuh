@@ -71,10 +71,11 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32
       continue;
     }
     for (;;) {
-      if (have) {
-        trav_step<INST, COUNT>(S, T, st, ovf, tc);
-        if (T.done) { io.store(myk, T); have = false; }
-      }
+      // while-while: all lanes run slab tests until each has a leaf (or is finished), then all run triangle tests
+      if (have) trav_nodes<INST, COUNT>(S, T, st, ovf, tc);
+      __syncwarp();
+      if (have && !T.done) trav_leaf<INST, COUNT>(S, T, st, ovf, tc);
+      if (have && T.done) { io.store(myk, T); have = false; }
       unsigned a = __ballot_sync(FULL, have);
       if (a == 0) break;
       if (!exhausted && __popc(a) <= 32 - PT_REFILL_MIN) break;
@@ -85,7 +86,10 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32
   for (uint32_t k = 0; k < total; k++) {  // tests/hostcheck: serial
     st.n = 0;
     io.load(k, T);
-    while (!T.done) trav_step<INST, COUNT>(S, T, st, ovf, tc);
+    while (!T.done) {
+      trav_nodes<INST, COUNT>(S, T, st, ovf, tc);
+      if (!T.done) trav_leaf<INST, COUNT>(S, T, st, ovf, tc);
+    }
     io.store(k, T);
   }
 #endif
@@ -113,9 +117,27 @@ struct WaveIO {
   __device__ __forceinline__ void store(uint32_t k, const Trav& T) {
     if (k < n_ext) {
       uint32_t i = Q.ext[k];
-      W.hit[i] = mk4(T.hit.b0, T.hit.b1, T.hit.b2, bitsf((uint32_t)(T.found ? T.hit.tri : -1)));
+      const int tri = T.found ? T.hit.tri : -1;
+      W.hit[i] = mk4(T.hit.b0, T.hit.b1, T.hit.b2, bitsf((uint32_t)tri));
       if (INST) W.hit_inst[i] = T.found ? T.hit.instance : -1;
       if (T.found) W.ray_o[i].w = T.ray_tmax;
+      // bin the path by shading class for the per-material shade kernels (warp-aggregated per class)
+      const int cls = shade_class(S, tri, (int)(W.flags[i] >> 8));
+      uint32_t slot;
+#if defined(__CUDA_ARCH__)
+      {
+        unsigned m = __activemask();
+        unsigned peers = __match_any_sync(m, cls);
+        int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&Q.counts[8 + cls], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+      }
+#else
+      slot = Q.counts[8 + cls]++;
+#endif
+      Q.bins[(size_t)cls * W.cap + slot] = i;
     } else if (k < n_ext + n_mis) {
       uint32_t i = Q.mis[k - n_ext];
       mis_resolve<NC>(S, W, i, T.hit, T.found, xyz(W.mis_d[i]));
@@ -168,10 +190,13 @@ __global__ void k_raygen_list(const DScene* __restrict__ Sp, WaveState W, Queues
     raygen_body<NC>(S, W, Q, i, pixel_xy[2 * i], pixel_xy[2 * i + 1], sample_num[i]);
 }
 
-template <int NC>
-__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_shade(const DScene* __restrict__ Sp, WaveState W, Queues Q, uint32_t n_ext, unsigned long long* vertex_counter) {
+// One shade kernel per shading class; the bin size is read on the device (no host round trip between trace and shade).
+template <int NC, int CLS>
+__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_shade(const DScene* __restrict__ Sp, WaveState W, Queues Q, unsigned long long* vertex_counter) {
   const DScene& S = *Sp;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_ext; k += gridDim.x * blockDim.x) shade_body<NC>(S, W, Q, Q.ext[k], vertex_counter);
+  const uint32_t n = Q.counts[8 + CLS];
+  const uint32_t* bin = Q.bins + (size_t)CLS * W.cap;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) shade_body<NC, CLS>(S, W, Q, bin[k], vertex_counter);
 }
 
 template <int NC>
