@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpbrt_r3_b200.so")
+LIB_PATH = os.environ.get("PBRT_R3_B200_LIB") or os.path.join(HERE, "libpbrt_r3_b200.so")  # env override: kernel A/B experiments
 DATA_DIR = os.path.join(HERE, "data")
 
 PT_ABI_VERSION = 1

@@ -14,6 +14,20 @@
 #pragma once
 #include "dtrav.cuh"
 
+// tuning switches (A/B measured on B200, see profiles/r1_trace_ab.md)
+#ifndef PT_OPT_TRI_PRED
+#define PT_OPT_TRI_PRED 0
+#endif
+#ifndef PT_OPT_PUSH_UNROLL
+#define PT_OPT_PUSH_UNROLL 0
+#endif
+#ifndef PT_OPT_HOIST
+#define PT_OPT_HOIST 0
+#endif
+#ifndef PT_OPT_NEXTREG
+#define PT_OPT_NEXTREG 0
+#endif
+
 namespace ptd {
 
 struct Trav {
@@ -24,6 +38,8 @@ struct Trav {
   float time;
   int cur;              // entry being processed
   int sg;               // sign bits of d: bit0 x, bit1 y, bit2 z
+  int kz;               // watertight test: dominant axis of d and the shear (pure functions of the ray, triangle.rs:258-277)
+  float shx, shy, shz;
   int lf, lc;           // pending leaf: first record, count (lc = -1: the pending entry is the barrier)
   uint32_t node_base, rec_base;
   // level-0 state saved while inside an instance
@@ -43,6 +59,83 @@ PT_HD void trav_set_ray(Trav& T, f3 o, f3 d) {
   T.o = o; T.d = d;
   T.idx = 1.0f / d.x; T.idy = 1.0f / d.y; T.idz = 1.0f / d.z;
   T.sg = (signbit_(d.x) ? 1 : 0) | (signbit_(d.y) ? 2 : 0) | (signbit_(d.z) ? 4 : 0);
+#if !PT_OPT_HOIST
+  T.kz = 0; T.shx = T.shy = T.shz = 0.0f;
+  return;
+#endif
+  // Triangle::intersect recomputes these for every triangle; they only depend on the ray
+  int kz = max_dim(abs3(d));
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  float dx = comp(d, kx), dy = comp(d, ky), dz = comp(d, kz);
+  T.kz = kz;
+  T.shx = -dx / dz; T.shy = -dy / dz; T.shz = 1.0f / dz;
+}
+
+// tri_test (dtrav.cuh) with the per-ray constants hoisted and the rejection tests folded into one predicate, so that
+// the lanes of a warp stay converged through the leaf loop.  Same operations, same order, same results.
+PT_HD bool tri_test_ray(f3 p0, f3 p1, f3 p2, uint32_t flags, const Trav& T, TriHitD* out) {
+  if (!(flags & PT_TRI_TWO_SIDED)) {
+    f3 n = cross3(p0 - p2, p1 - p2);
+    if (((flags & PT_TRI_REVERSE_ORIENTATION) != 0) != ((flags & PT_TRI_SWAPS_HANDEDNESS) != 0)) n = n * -1.0f;
+    if (dot3(n, T.d) >= 0.0f) return false;
+  }
+  f3 a = p0 - T.o, b = p1 - T.o, c = p2 - T.o;
+  const int kz = T.kz;
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  float ax = comp(a, kx), ay = comp(a, ky), az = comp(a, kz);
+  float bx = comp(b, kx), by = comp(b, ky), bz = comp(b, kz);
+  float cx = comp(c, kx), cy = comp(c, ky), cz = comp(c, kz);
+  const float sx = T.shx, sy = T.shy, sz = T.shz;
+  ax += sx * az; ay += sy * az;
+  bx += sx * bz; by += sy * bz;
+  cx += sx * cz; cy += sy * cz;
+  float e0 = bx * cy - by * cx;
+  float e1 = cx * ay - cy * ax;
+  float e2 = ax * by - ay * bx;
+  if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {  // rare: exact edge hit, f64 fallback (triangle.rs:283-293)
+    e0 = (float)((double)cy * (double)bx - (double)cx * (double)by);
+    e1 = (float)((double)ay * (double)cx - (double)ax * (double)cy);
+    e2 = (float)((double)by * (double)ax - (double)bx * (double)ay);
+  }
+#if PT_OPT_TRI_PRED
+  bool ok = !((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f));
+  float det = e0 + e1 + e2;
+  ok = ok && det != 0.0f;
+  az *= sz; bz *= sz; cz *= sz;
+  float ts = e0 * az + e1 * bz + e2 * cz;
+  const float tmax = T.ray_tmax;
+  if (det < 0.0f && (ts >= 0.0f || ts < tmax * det)) ok = false;
+  else if (det > 0.0f && (ts <= 0.0f || ts > tmax * det)) ok = false;
+  if (!ok) return false;
+#else
+  if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+  float det = e0 + e1 + e2;
+  if (det == 0.0f) return false;
+  az *= sz; bz *= sz; cz *= sz;
+  float ts = e0 * az + e1 * bz + e2 * cz;
+  const float tmax = T.ray_tmax;
+  if (det < 0.0f && (ts >= 0.0f || ts < tmax * det)) return false;
+  else if (det > 0.0f && (ts <= 0.0f || ts > tmax * det)) return false;
+#endif
+  float inv_det = 1.0f / det;
+  float t = ts * inv_det;
+  float max_zt = fmaxf(fabsf(az), fmaxf(fabsf(bz), fabsf(cz)));
+  float delta_z = PT_GAMMA(3.0f) * max_zt;
+  float max_xt = fmaxf(fabsf(ax), fmaxf(fabsf(bx), fabsf(cx)));
+  float max_yt = fmaxf(fabsf(ay), fmaxf(fabsf(by), fabsf(cy)));
+  float delta_x = PT_GAMMA(5.0f) * (max_xt + max_zt);
+  float delta_y = PT_GAMMA(5.0f) * (max_yt + max_zt);
+  float delta_e = 2.0f * (PT_GAMMA(2.0f) * max_xt * max_yt + delta_y * max_xt + delta_x * max_yt);
+  float max_e = fmaxf(fabsf(e0), fmaxf(fabsf(e1), fabsf(e2)));
+  float delta_t = 3.0f * (PT_GAMMA(3.0f) * max_e * max_zt + delta_e * max_zt + delta_z * max_e) * fabsf(inv_det);
+  if (t <= delta_t) return false;
+  out->t = t;
+  out->b0 = e0 * inv_det;
+  out->b1 = e1 * inv_det;
+  out->b2 = e2 * inv_det;
+  return true;
 }
 
 // QBVHAccel::intersect[_p] prologue on the top-level object
@@ -69,7 +162,11 @@ template <bool COUNT>
 PT_HD bool trav_triangle(Trav& T, f4 v0, f4 v1, f4 v2, TravCounters* cnt) {
   if (COUNT) cnt->tris++;
   TriHitD th;
+#if PT_OPT_HOIST
+  if (!tri_test_ray(xyz(v0), xyz(v1), xyz(v2), fbits(v1.w), T, &th)) return false;
+#else
   if (!tri_test(xyz(v0), xyz(v1), xyz(v2), fbits(v1.w), T.o, T.d, T.ray_tmax, &th)) return false;
+#endif
   T.found = true;
   if (T.any) return true;
   T.ray_tmax = th.t;
@@ -120,20 +217,43 @@ PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCo
   }
     PT_LANE2(x, 1u) PT_LANE2(y, 2u) PT_LANE2(z, 4u) PT_LANE2(w, 8u)
 #undef PT_LANE2
-    if (mask) {
+    // children in the reference's push order (ORDER_TABLE nibble list, terminated by 4); the LAST pushed child is the
+    // next one popped, so it stays in a register instead of going through the stack.  Unrolled and predicated: no
+    // data-dependent loop inside the warp.
+    int next = PT_EMPTY;
+    {
       int at = meta.x & 3, al = (meta.x >> 2) & 3, ar = (meta.x >> 4) & 3;
       int s_t = (T.sg >> at) & 1, s_l = (T.sg >> al) & 1, s_r = (T.sg >> ar) & 1;
-      uint32_t order = kOrderTable[mask * 8 + (unsigned)((s_t << 2) | (s_l << 1) | s_r)];
+      uint32_t order = kOrderTable[mask * 8 + (unsigned)((s_t << 2) | (s_l << 1) | s_r)];  // mask 0 -> empty list
+#if PT_OPT_PUSH_UNROLL
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int k = (int)((order >> (4 * j)) & 7u);
+        int c = (k & 3) == 0 ? ch.x : ((k & 3) == 1 ? ch.y : ((k & 3) == 2 ? ch.z : ch.w));
+        if (!(k & 4) && c != PT_EMPTY) {
+          if (next != PT_EMPTY) { if (!st.push(next)) *overflow = 1; }
+          next = c;
+        }
+      }
+#else
       while ((order & 0x4) == 0) {
         int k = (int)(order & 3);
         int c = k == 0 ? ch.x : (k == 1 ? ch.y : (k == 2 ? ch.z : ch.w));
         if (c != PT_EMPTY) {
-          if (!st.push(c)) *overflow = 1;
+          if (next != PT_EMPTY) { if (!st.push(next)) *overflow = 1; }
+          next = c;
         }
         order >>= 4;
       }
+#endif
     }
+#if PT_OPT_NEXTREG
+    if (next != PT_EMPTY) T.cur = next;
+    else if (!st.pop(&T.cur)) { T.done = true; return; }
+#else
+    if (next != PT_EMPTY) { if (!st.push(next)) *overflow = 1; }
     if (!st.pop(&T.cur)) { T.done = true; return; }
+#endif
   }
 }
 
@@ -169,9 +289,11 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
       if (O.single) {  // one primitive, no accelerator: test it in object space right here
         const f4* pr = S.recs + (size_t)O.rec_base * 3;
         f3 so = T.o, sd = T.d;
-        T.o = q.o; T.d = q.d; T.inst = inst;
+        trav_set_ray(T, q.o, q.d);
+        T.inst = inst;
         bool fin = trav_triangle<COUNT>(T, ldg4(pr), ldg4(pr + 1), ldg4(pr + 2), cnt);
-        T.o = so; T.d = sd; T.inst = -1;
+        trav_set_ray(T, so, sd);
+        T.inst = -1;
         if (fin) { T.done = true; return; }
         continue;
       }

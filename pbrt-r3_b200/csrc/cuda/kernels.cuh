@@ -8,6 +8,9 @@
 namespace ptd {
 
 #define PT_TRACE_BLOCK 128
+#ifndef PT_TRACE_MINBLOCKS
+#define PT_TRACE_MINBLOCKS 1
+#endif
 #define PT_SHADE_BLOCK 128
 
 // Traversal stack: the first PT_SMEM_STACK entries of every thread live in shared memory, strided so that
@@ -150,7 +153,7 @@ struct WaveIO {
 
 // Scene::intersect for continuation (A) and MIS (C) rays, Scene::intersect_p for shadow (B) rays, in one launch.
 template <int NC, bool INST, bool COUNT>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace(const DScene* __restrict__ Sp, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(const DScene* __restrict__ Sp, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
                                                           uint32_t n_sh, unsigned long long* counters, int* overflow) {
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
   const DScene& S = *Sp;
@@ -246,7 +249,7 @@ struct ArrayIO {  // pt_intersect / pt_intersect_p / pt_intersect_device: rays a
   }
 };
 template <bool INST, bool COUNT>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_intersect(const DScene* __restrict__ Sp, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_intersect(const DScene* __restrict__ Sp, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
                                                               f4* hits, float* t_out, unsigned char* occ, uint32_t* fetch, unsigned long long* counters,
                                                               int* overflow) {
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];

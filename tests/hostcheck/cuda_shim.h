@@ -14,7 +14,7 @@
 #define __shared__ static
 #define __forceinline__ inline
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 
 struct hc_dim3 { unsigned x, y, z; };
 static const hc_dim3 blockIdx = {0, 0, 0}, threadIdx = {0, 0, 0}, gridDim = {1, 1, 1}, blockDim = {1, 1, 1};
