@@ -177,7 +177,7 @@ int grid_for(const pt_scene* s, size_t n, int block, int per_sm) {
 template <int NC>
 int precompute_light_distribution(pt_scene* s, uint32_t n_vox, float* func, float* cdf, float* func_int) {
   size_t total = (size_t)n_vox * s->h.n_lights;
-  PT_LAUNCH(grid_for(s, total, 128, 16), 128, s->stream, k_voxel_contrib<NC>)(s->d, func, n_vox);
+  PT_LAUNCH(grid_for(s, total, 128, 16), 128, s->stream, k_voxel_contrib<NC>)(s->h, func, n_vox);
   CK(cudaGetLastError());
   PT_LAUNCH(grid_for(s, n_vox, 128, 16), 128, s->stream, k_voxel_cdf)(s->h.n_lights, n_vox, func, cdf, func_int);
   CK(cudaGetLastError());
@@ -495,7 +495,7 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
     CK(cudaMemsetAsync(Q.counts + 8, 0, 8 * sizeof(uint32_t), s->stream));  // shading-class bin sizes
     if (timed) cudaEventRecord(e0, s->stream);
-#define LAUNCH_TRACE(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_trace<NC, I, C>)(s->d, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
+#define LAUNCH_TRACE(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_trace<NC, I, C>)(s->h, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
     if (inst) { if (count) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
     else { if (count) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
 #undef LAUNCH_TRACE
@@ -511,7 +511,7 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
-#define LAUNCH_SHADE(C) if (s->class_mask & (1u << (C))) { PT_LAUNCH(gs, PT_SHADE_BLOCK, s->stream, k_shade<NC, C>)(s->d, W, Q, vc); T->launches++; }
+#define LAUNCH_SHADE(C) if (s->class_mask & (1u << (C))) { PT_LAUNCH(gs, PT_SHADE_BLOCK, s->stream, k_shade<NC, C>)(s->h, W, Q, vc); T->launches++; }
       LAUNCH_SHADE(CL_NONE) LAUNCH_SHADE(CL_MATTE) LAUNCH_SHADE(CL_PLASTIC) LAUNCH_SHADE(CL_GLASS) LAUNCH_SHADE(CL_METAL) LAUNCH_SHADE(CL_MIRROR)
 #undef LAUNCH_SHADE
       CK(cudaGetLastError());
@@ -596,16 +596,16 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     for (int s0 = s_begin; s0 < s_end; s0 += (int)ns_wave) {
       uint32_t ns = (uint32_t)std::min<int>((int)ns_wave, s_end - s0);
       uint32_t n = npix * ns;
-      PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->d, s->W, s->Q, s->pixlist, c0, npix, s0, ns);
+      PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->h, s->W, s->Q, s->pixlist, c0, npix, s0, ns);
       CK(cudaGetLastError());
       T.launches++;
       if (st) st->camera_rays += n;
       if (run_bounces<NC>(s, n, count, st != nullptr, &T)) return 1;
-      PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->d, s->W, n);
+      PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->h, s->W, n);
       CK(cudaGetLastError());
       T.launches++;
       if (fx1 > fx0 && fy1 > fy0) {
-        PT_LAUNCH(grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, s->stream, k_film<NC>)(s->d, s->W, s->slot_of, npix, ns, fx0, fy0, fx1, fy1, s->film);
+        PT_LAUNCH(grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, s->stream, k_film<NC>)(s->h, s->W, s->slot_of, npix, ns, fx0, fy0, fx1, fy1, s->film);
         CK(cudaGetLastError());
         T.launches++;
       }
@@ -642,7 +642,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
 int launch_intersect(pt_scene* s, const f4* ro, const f4* rd, uint32_t n, f4* hits, float* tt, unsigned char* occ, bool count) {
   CK(cudaMemsetAsync(s->fetch, 0, sizeof(uint32_t), s->stream));
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
-#define LAUNCH_ISECT(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<I, C>)(s->d, ro, rd, n, hits, tt, occ, s->fetch, s->counters, s->overflow)
+#define LAUNCH_ISECT(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<I, C>)(s->h, ro, rd, n, hits, tt, occ, s->fetch, s->counters, s->overflow)
   if (s->h.has_instances) { if (count) LAUNCH_ISECT(true, true); else LAUNCH_ISECT(true, false); }
   else { if (count) LAUNCH_ISECT(false, true); else LAUNCH_ISECT(false, false); }
 #undef LAUNCH_ISECT
@@ -745,7 +745,7 @@ int pt_film_resolve(pt_scene* s, const float* dev_film_xyzw, float* out_rgb_host
   CK(cudaSetDevice(s->device));
   const f4* film = dev_film_xyzw ? (const f4*)dev_film_xyzw : s->film;
   if (s->film_pixels == 0) return 0;
-  PT_LAUNCH(grid_for(s, s->film_pixels, 256, 8), 256, s->stream, k_film_resolve)(s->d, film, s->rgb_dev, s->film_pixels);
+  PT_LAUNCH(grid_for(s, s->film_pixels, 256, 8), 256, s->stream, k_film_resolve)(s->h, film, s->rgb_dev, s->film_pixels);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out_rgb_host, s->rgb_dev, (size_t)s->film_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -844,7 +844,7 @@ int pt_sampler_values(pt_scene* s, const int32_t* pixel_xy, const int32_t* sampl
   CK(B.upload(pixel_xy, (size_t)n * 2, &pxy));
   CK(B.upload(sample_num, n, &sn));
   CK(B.alloc((size_t)n * ndims, &o));
-  PT_LAUNCH(grid_for(s, (size_t)n * ndims, 128, 8), 128, s->stream, k_sampler_values)(s->d, pxy, sn, n, dim0, ndims, o);
+  PT_LAUNCH(grid_for(s, (size_t)n * ndims, 128, 8), 128, s->stream, k_sampler_values)(s->h, pxy, sn, n, dim0, ndims, o);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, o, (size_t)n * ndims * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
@@ -857,15 +857,15 @@ static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_
   const int *pxy, *sn;
   CK(B.upload(pixel_xy, (size_t)n * 2, &pxy));
   CK(B.upload(sample_num, n, &sn));
-  if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<3>)(s->d, s->W, s->Q, pxy, sn, n);
-  else PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<PT_NCS>)(s->d, s->W, s->Q, pxy, sn, n);
+  if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<3>)(s->h, s->W, s->Q, pxy, sn, n);
+  else PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<PT_NCS>)(s->h, s->W, s->Q, pxy, sn, n);
   CK(cudaGetLastError());
   if (bounce && s->h.n_lights > 0) {
     WaveTotals T;
     int rc = s->h.n_channels == 3 ? run_bounces<3>(s, n, false, false, &T) : run_bounces<PT_NCS>(s, n, false, false, &T);
     if (rc) return rc;
-    if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<3>)(s->d, s->W, n);
-    else PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<PT_NCS>)(s->d, s->W, n);
+    if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<3>)(s->h, s->W, n);
+    else PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<PT_NCS>)(s->h, s->W, n);
     CK(cudaGetLastError());
   }
   CK(cudaStreamSynchronize(s->stream));

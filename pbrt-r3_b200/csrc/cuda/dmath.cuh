@@ -92,6 +92,13 @@ PT_HD float bitsf(uint32_t u) {
 PT_HD bool isinf_(float v) { return (fbits(v) & 0x7fffffffu) == 0x7f800000u; }
 PT_HD bool isfinite_(float v) { return (fbits(v) & 0x7f800000u) != 0x7f800000u; }
 PT_HD bool signbit_(float v) { return (fbits(v) >> 31) != 0; }
+PT_HD int popc_(unsigned v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
 PT_HD float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }  // f32::clamp
 PT_HD float lerpf(float t, float a, float b) { return (1.0f - t) * a + t * b; }
 

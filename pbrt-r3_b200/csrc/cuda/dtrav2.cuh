@@ -22,10 +22,19 @@
 #define PT_OPT_PUSH_UNROLL 0
 #endif
 #ifndef PT_OPT_HOIST
-#define PT_OPT_HOIST 0
+#define PT_OPT_HOIST 1
 #endif
 #ifndef PT_OPT_NEXTREG
 #define PT_OPT_NEXTREG 0
+#endif
+#ifndef PT_OPT_FMNMX
+#define PT_OPT_FMNMX 1
+#endif
+#ifndef PT_OPT_POS
+#define PT_OPT_POS 1
+#endif
+#ifndef PT_OPT_POPLUT
+#define PT_OPT_POPLUT 0
 #endif
 
 namespace ptd {
@@ -38,6 +47,7 @@ struct Trav {
   float time;
   int cur;              // entry being processed
   int sg;               // sign bits of d: bit0 x, bit1 y, bit2 z
+  bool nonan;           // no slab product of this ray can be NaN: max_ps/min_ps == fmaxf/fminf (see trav_nodes)
   int kz;               // watertight test: dominant axis of d and the shear (pure functions of the ray, triangle.rs:258-277)
   float shx, shy, shz;
   int lf, lc;           // pending leaf: first record, count (lc = -1: the pending entry is the barrier)
@@ -59,6 +69,12 @@ PT_HD void trav_set_ray(Trav& T, f3 o, f3 d) {
   T.o = o; T.d = d;
   T.idx = 1.0f / d.x; T.idy = 1.0f / d.y; T.idz = 1.0f / d.z;
   T.sg = (signbit_(d.x) ? 1 : 0) | (signbit_(d.y) ? 2 : 0) | (signbit_(d.z) ? 4 : 0);
+  // (box - o) * idir is NaN only for 0 * inf or a NaN operand: excluded when every 1/d is finite and non-zero and o is finite
+  {
+    const float big = 3.0e38f;
+    T.nonan = fabsf(T.idx) < big && fabsf(T.idy) < big && fabsf(T.idz) < big && fabsf(T.idx) > 0.0f && fabsf(T.idy) > 0.0f && fabsf(T.idz) > 0.0f &&
+              fabsf(o.x) < big && fabsf(o.y) < big && fabsf(o.z) < big;
+  }
 #if !PT_OPT_HOIST
   T.kz = 0; T.shx = T.shy = T.shz = 0.0f;
   return;
@@ -177,33 +193,59 @@ PT_HD bool trav_triangle(Trav& T, f4 v0, f4 v1, f4 v2, TravCounters* cnt) {
   return false;
 }
 
-// NODE phase: processes inner nodes (slab tests, ordered pushes, pop) until the current entry is a leaf, a leaf
-// remainder or the barrier (left pending in T.lf / T.lc), or the stack runs empty (T.done).
+// NODE phase, one step: processes the current entry - an inner node (slab tests, ordered pushes, pop; returns true:
+// stay in the node phase), or a leaf, a leaf remainder or the barrier (left pending in T.lf / T.lc), or finds the
+// stack empty (T.done) (returns false).
+//
+// Child order.  The reference pushes the hit children in ORDER_TABLE order and pops the last one pushed
+// (qbvh_x86.rs:187-204,264-274).  With s = sign[axis_top] << 2 | sign[axis_left] << 1 | sign[axis_right] that order is
+//   s_t = 0: [3 ^ s_r, 2 ^ s_r, 1 ^ s_l, 0 ^ s_l]        s_t = 1: [1 ^ s_l, 0 ^ s_l, 3 ^ s_r, 2 ^ s_r]
+// restricted to the hit lanes (checked against all 128 table entries by tests/test_host_logic.py).  So the stack
+// position of child k is popc(mask & before_k), before_k = the lanes pushed before k: every hit child is stored with
+// one predicated st.shared, the one at the top goes straight to T.cur - no table lookup, no data-dependent loop.
 template <bool INST, bool COUNT, typename Stack>
-PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
-  const int sgx = T.sg & 1, sgy = (T.sg >> 1) & 1, sgz = (T.sg >> 2) & 1;
-  for (;;) {
+PT_HD bool trav_node_step(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
+  const uint32_t sx = (T.sg & 1) ? 48u : 0u, sy = (T.sg & 2) ? 48u : 0u, sz = (T.sg & 4) ? 48u : 0u;
+  const int sg3 = 3 * T.sg;
+  const char* nbase = reinterpret_cast<const char*>(S.nodes + T.node_base);
+  {
     if (T.cur < 0) {  // inline leaf or leaf remainder
       if (COUNT) cnt->nodes++;
       unsigned e = (unsigned)~T.cur;
       T.lf = (int)(e >> PT_LEAF_BITS);
       T.lc = (int)(e & ((1u << PT_LEAF_BITS) - 1u)) + 1;
-      return;
+      return false;
     }
-    if (INST && T.cur == PT_STACK_BARRIER) { T.lc = -1; return; }
+    if (INST && T.cur == PT_STACK_BARRIER) { T.lc = -1; return false; }
     if (COUNT) cnt->nodes++;
-    const QNode* nd = S.nodes + T.node_base + T.cur;
-    i4 meta = ldgi4(&nd->meta);
+    // the whole 128-byte node is requested at once (one L2 round trip); bboxes[sign][axis] / bboxes[1 - sign][axis]
+    const char* nd = nbase + (size_t)(uint32_t)T.cur * sizeof(QNode);
+    const f4 nx = ldg4(reinterpret_cast<const f4*>(nd + sx)), fx = ldg4(reinterpret_cast<const f4*>(nd + (48u - sx)));
+    const f4 ny = ldg4(reinterpret_cast<const f4*>(nd + (16u + sy))), fy = ldg4(reinterpret_cast<const f4*>(nd + (64u - sy)));
+    const f4 nz = ldg4(reinterpret_cast<const f4*>(nd + (32u + sz))), fz = ldg4(reinterpret_cast<const f4*>(nd + (80u - sz)));
+    const i4 ch = ldgi4(reinterpret_cast<const i4*>(nd + 96));
+    const i4 meta = ldgi4(reinterpret_cast<const i4*>(nd + 112));
     if (meta.x & 0x100) {  // leaf node in the reference's own form
       T.lf = meta.y;
       T.lc = meta.z;
-      return;
+      return false;
     }
-    f4 nx = ldg4(sgx ? &nd->hi[0] : &nd->lo[0]), fx = ldg4(sgx ? &nd->lo[0] : &nd->hi[0]);
-    f4 ny = ldg4(sgy ? &nd->hi[1] : &nd->lo[1]), fy = ldg4(sgy ? &nd->lo[1] : &nd->hi[1]);
-    f4 nz = ldg4(sgz ? &nd->hi[2] : &nd->lo[2]), fz = ldg4(sgz ? &nd->lo[2] : &nd->hi[2]);
-    i4 ch = ldgi4(&nd->child);
     unsigned mask = 0;
+#if PT_OPT_FMNMX
+    if (T.nonan) {
+      // without NaNs `a > b ? a : b` (max_ps) and fmaxf(a, b) differ only in the sign of a zero, which `tx >= tn` ignores:
+      // FMNMX3 instead of FSETP + FSEL per slab
+#define PT_LANE3(L, BIT)                                                                                              \
+  {                                                                                                                   \
+    float tn = fmaxf(fmaxf(T.tmin, (nx.L - T.o.x) * T.idx), fmaxf((ny.L - T.o.y) * T.idy, (nz.L - T.o.z) * T.idz));   \
+    float tx = fminf(fminf(T.tmax, (fx.L - T.o.x) * T.idx), fminf((fy.L - T.o.y) * T.idy, (fz.L - T.o.z) * T.idz));   \
+    if (tx >= tn) mask |= BIT;                                                                                        \
+  }
+      PT_LANE3(x, 1u) PT_LANE3(y, 2u) PT_LANE3(z, 4u) PT_LANE3(w, 8u)
+#undef PT_LANE3
+    } else
+#endif
+    {
 #define PT_LANE2(L, BIT)                                                  \
   {                                                                       \
     float tn = T.tmin, tx = T.tmax, v;                                    \
@@ -215,46 +257,67 @@ PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCo
     v = (fz.L - T.o.z) * T.idz; tx = PT_SSE_MIN(tx, v);                   \
     if (tx >= tn) mask |= BIT;                                            \
   }
-    PT_LANE2(x, 1u) PT_LANE2(y, 2u) PT_LANE2(z, 4u) PT_LANE2(w, 8u)
+      PT_LANE2(x, 1u) PT_LANE2(y, 2u) PT_LANE2(z, 4u) PT_LANE2(w, 8u)
 #undef PT_LANE2
-    // children in the reference's push order (ORDER_TABLE nibble list, terminated by 4); the LAST pushed child is the
-    // next one popped, so it stays in a register instead of going through the stack.  Unrolled and predicated: no
-    // data-dependent loop inside the warp.
-    int next = PT_EMPTY;
-    {
-      int at = meta.x & 3, al = (meta.x >> 2) & 3, ar = (meta.x >> 4) & 3;
-      int s_t = (T.sg >> at) & 1, s_l = (T.sg >> al) & 1, s_r = (T.sg >> ar) & 1;
-      uint32_t order = kOrderTable[mask * 8 + (unsigned)((s_t << 2) | (s_l << 1) | s_r)];  // mask 0 -> empty list
-#if PT_OPT_PUSH_UNROLL
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        int k = (int)((order >> (4 * j)) & 7u);
-        int c = (k & 3) == 0 ? ch.x : ((k & 3) == 1 ? ch.y : ((k & 3) == 2 ? ch.z : ch.w));
-        if (!(k & 4) && c != PT_EMPTY) {
-          if (next != PT_EMPTY) { if (!st.push(next)) *overflow = 1; }
-          next = c;
-        }
-      }
+    }
+#if PT_OPT_POS
+    // NOTE (measured, profiles/r1_trace_ab.md): no `continue` / early loop-back in this body.  A lane that jumps to the
+    // loop tail ahead of the others is never merged back (independent thread scheduling reconverges only at the
+    // compiler's BSSY/BSYNC pairs), and the warp then runs the loop once per lane group.
+    const unsigned s = ((unsigned)meta.w >> sg3) & 7u;
+    const unsigned bl = (s & 4u) ? 0u : 0xcu, br = (s & 4u) ? 0x3u : 0u;  // lanes of the other pair that are pushed first
+#if PT_OPT_POPLUT
+    // popc of a 4-bit value, 2 bits per entry (POPC issues at 1/4 of the ALU rate); popc(15) wraps to 0
+#define PT_POP4(v) ((int)((0x3ee9e994u >> (2u * (v))) & 3u))
+    const int p0 = PT_POP4(mask & (bl | ((s & 2u) ? 0u : 2u))), p1 = PT_POP4(mask & (bl | ((s & 2u) ? 1u : 0u)));
+    const int p2 = PT_POP4(mask & (br | ((s & 1u) ? 0u : 8u))), p3 = PT_POP4(mask & (br | ((s & 1u) ? 4u : 0u)));
+    const int last = (mask == 15u ? 4 : PT_POP4(mask)) - 1;
+#undef PT_POP4
 #else
+    const int p0 = popc_(mask & (bl | ((s & 2u) ? 0u : 2u))), p1 = popc_(mask & (bl | ((s & 2u) ? 1u : 0u)));
+    const int p2 = popc_(mask & (br | ((s & 1u) ? 0u : 8u))), p3 = popc_(mask & (br | ((s & 1u) ? 4u : 0u)));
+    const int last = popc_(mask) - 1;  // -1: no child hit
+#endif
+    const bool h0 = (mask & 1u) != 0u, h1 = (mask & 2u) != 0u, h2 = (mask & 4u) != 0u, h3 = (mask & 8u) != 0u;
+    if (st.room(last)) {
+      if (h0 && p0 < last) st.put(p0, ch.x);
+      if (h1 && p1 < last) st.put(p1, ch.y);
+      if (h2 && p2 < last) st.put(p2, ch.z);
+      if (h3 && p3 < last) st.put(p3, ch.w);
+      if (last > 0) st.advance(last);
+    } else {
+#pragma unroll 1
+      for (int pos = 0; pos < last; pos++) {
+        int c = (h0 && p0 == pos) ? ch.x : ((h1 && p1 == pos) ? ch.y : ((h2 && p2 == pos) ? ch.z : ch.w));
+        if (!st.push(c)) *overflow = 1;
+      }
+    }
+    int nxt = (h0 && p0 == last) ? ch.x : ((h1 && p1 == last) ? ch.y : ((h2 && p2 == last) ? ch.z : ch.w));
+    bool out = false;
+    if (last < 0) out = !st.pop(&nxt);
+    if (out) { T.done = true; return false; }
+    T.cur = nxt;
+#else
+    {
+      unsigned si = ((unsigned)meta.w >> sg3) & 7u;
+      uint32_t order = kOrderTable[mask * 8 + si];  // mask 0 -> empty list
       while ((order & 0x4) == 0) {
         int k = (int)(order & 3);
         int c = k == 0 ? ch.x : (k == 1 ? ch.y : (k == 2 ? ch.z : ch.w));
-        if (c != PT_EMPTY) {
-          if (next != PT_EMPTY) { if (!st.push(next)) *overflow = 1; }
-          next = c;
-        }
+        if (!st.push(c)) *overflow = 1;
         order >>= 4;
       }
-#endif
     }
-#if PT_OPT_NEXTREG
-    if (next != PT_EMPTY) T.cur = next;
-    else if (!st.pop(&T.cur)) { T.done = true; return; }
-#else
-    if (next != PT_EMPTY) { if (!st.push(next)) *overflow = 1; }
-    if (!st.pop(&T.cur)) { T.done = true; return; }
+    if (!st.pop(&T.cur)) { T.done = true; return false; }
 #endif
   }
+  return true;
+}
+
+// the node phase of one ray on its own (tests/hostcheck and the fallback driver)
+template <bool INST, bool COUNT, typename Stack>
+PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
+  while (trav_node_step<INST, COUNT>(S, T, st, overflow, cnt)) {}
 }
 
 // LEAF phase: the pending leaf (intersect_primitives[_p] over recs[lf .. lf + lc) in order) or the barrier, then pop.

@@ -9,20 +9,61 @@ namespace ptd {
 
 #define PT_TRACE_BLOCK 128
 #ifndef PT_TRACE_MINBLOCKS
-#define PT_TRACE_MINBLOCKS 1
+#define PT_TRACE_MINBLOCKS 7
 #endif
 #define PT_SHADE_BLOCK 128
 
 // Traversal stack: the first PT_SMEM_STACK entries of every thread live in shared memory, strided so that
 // consecutive lanes hit consecutive banks ([entry][thread]); deeper entries spill to a small local array.
+#ifndef PT_SMEM_STACK
 #define PT_SMEM_STACK 24
+#endif
+// On the device the column is addressed with explicit st.shared / ld.shared on a 32-bit shared-space address (the
+// generic-pointer form cost an LDL of the pointer + a 64-bit IMAD.WIDE + a generic ST per push); the spill array is a
+// separate local array so that `n` and the address stay in registers.
+#ifndef PT_OPT_STS
+#define PT_OPT_STS 1
+#endif
+#if defined(__CUDA_ARCH__) && PT_OPT_STS
+#define PT_STS_ASM 1
+#else
+#define PT_STS_ASM 0
+#endif
 struct SharedStack {
-  int* sm;           // &smem[threadIdx.x], stride PT_TRACE_BLOCK
+#if PT_STS_ASM
+  uint32_t sa;       // shared-space byte address of smem[threadIdx.x]; entry stride = PT_TRACE_BLOCK * 4 bytes
+#else
+  int* sm;           // tests/hostcheck: &smem[0]
+#endif
   int n;
-  int spill[PT_MAX_STACK - PT_SMEM_STACK];
+  int* spill;        // PT_MAX_STACK - PT_SMEM_STACK entries of local memory
+  __device__ __forceinline__ void attach(int* smem_col, int* spill_arr) {
+#if PT_STS_ASM
+    sa = (uint32_t)__cvta_generic_to_shared(smem_col);
+#else
+    sm = smem_col;
+#endif
+    spill = spill_arr;
+    n = 0;
+  }
+  // fast path of the node phase: k entries fit into the shared part -> put(pos, x) at n + pos, then advance(k)
+  __device__ __forceinline__ bool room(int k) const { return n + k <= PT_SMEM_STACK; }
+  __device__ __forceinline__ void put(int pos, int x) {
+#if PT_STS_ASM
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa + (uint32_t)(n + pos) * (PT_TRACE_BLOCK * 4u)), "r"(x) : "memory");
+#else
+    sm[(n + pos) * PT_TRACE_BLOCK] = x;
+#endif
+  }
+  __device__ __forceinline__ void advance(int k) { n += k; }
   __device__ __forceinline__ bool push(int x) {
-    if (n < PT_SMEM_STACK) sm[n * PT_TRACE_BLOCK] = x;
-    else if (n < PT_MAX_STACK) spill[n - PT_SMEM_STACK] = x;
+    if (n < PT_SMEM_STACK) {
+#if PT_STS_ASM
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(sa + (uint32_t)n * (PT_TRACE_BLOCK * 4u)), "r"(x) : "memory");
+#else
+      sm[n * PT_TRACE_BLOCK] = x;
+#endif
+    } else if (n < PT_MAX_STACK) spill[n - PT_SMEM_STACK] = x;
     else return false;
     n++;
     return true;
@@ -30,7 +71,15 @@ struct SharedStack {
   __device__ __forceinline__ bool pop(int* x) {
     if (n == 0) return false;
     n--;
-    *x = n < PT_SMEM_STACK ? sm[n * PT_TRACE_BLOCK] : spill[n - PT_SMEM_STACK];
+    if (n < PT_SMEM_STACK) {
+#if PT_STS_ASM
+      int v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sa + (uint32_t)n * (PT_TRACE_BLOCK * 4u)) : "memory");
+      *x = v;
+#else
+      *x = sm[n * PT_TRACE_BLOCK];
+#endif
+    } else *x = spill[n - PT_SMEM_STACK];
     return true;
   }
 };
@@ -39,7 +88,12 @@ struct SharedStack {
 // idle the warp claims that many new rays with ONE atomicAdd on the launch's fetch counter (ballot / popc ranks),
 // so lanes do not wait for the slowest ray of a fixed 32-ray batch.  IO supplies the rays and consumes the results:
 //   void load(uint32_t k, Trav& T)   -> trav_begin(...)        void store(uint32_t k, const Trav& T)
-#define PT_REFILL_MIN 8
+#ifndef PT_REFILL_MIN
+#define PT_REFILL_MIN 16
+#endif
+#ifndef PT_NODE_EXIT_MIN
+#define PT_NODE_EXIT_MIN 8
+#endif
 template <bool INST, bool COUNT, typename IO>
 __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32_t total, uint32_t* fetch, SharedStack& st, int* ovf, TravCounters* tc) {
   Trav T;
@@ -74,10 +128,26 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32
       continue;
     }
     for (;;) {
-      // while-while: all lanes run slab tests until each has a leaf (or is finished), then all run triangle tests
-      if (have) trav_nodes<INST, COUNT>(S, T, st, ovf, tc);
-      __syncwarp();
-      if (have && !T.done) trav_leaf<INST, COUNT>(S, T, st, ovf, tc);
+      // while-while: all lanes run slab tests until each has a leaf (or is finished), then all run triangle tests.
+      // The node loop is warp-synchronous (one vote per step): the lanes of a warp meet again after EVERY node, whatever
+      // branches the step took (left to the compiler, lanes that reach the loop latch early run ahead and are never
+      // merged back: measured 7 instead of 13 active lanes per instruction).
+      {
+        bool inn = have;
+        for (;;) {
+          unsigned m = __ballot_sync(FULL, inn);
+          if (m == 0u) break;
+#if PT_NODE_EXIT_MIN > 0
+          // few lanes still walking nodes while others wait with a leaf: let the leaf phase run first
+          if (__popc(m) < PT_NODE_EXIT_MIN && __any_sync(FULL, have && !T.done && T.lc != 0)) break;
+#endif
+          if (inn) inn = trav_node_step<INST, COUNT>(S, T, st, ovf, tc);
+        }
+      }
+      if (have && !T.done && T.lc != 0) {
+        trav_leaf<INST, COUNT>(S, T, st, ovf, tc);
+        T.lc = 0;
+      }
       if (have && T.done) { io.store(myk, T); have = false; }
       unsigned a = __ballot_sync(FULL, have);
       if (a == 0) break;
@@ -153,13 +223,12 @@ struct WaveIO {
 
 // Scene::intersect for continuation (A) and MIS (C) rays, Scene::intersect_p for shadow (B) rays, in one launch.
 template <int NC, bool INST, bool COUNT>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(const DScene* __restrict__ Sp, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(const __grid_constant__ DScene S, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
                                                           uint32_t n_sh, unsigned long long* counters, int* overflow) {
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
-  const DScene& S = *Sp;
+  int spill[PT_MAX_STACK - PT_SMEM_STACK];
   SharedStack st;
-  st.sm = smem + threadIdx.x;
-  st.n = 0;
+  st.attach(smem + threadIdx.x, spill);
   TravCounters tc;
   tc.nodes = 0; tc.tris = 0;
   int ovf = 0;
@@ -173,9 +242,8 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(co
 }
 
 template <int NC>
-__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_raygen(const DScene* __restrict__ Sp, WaveState W, Queues Q, const int* __restrict__ pixlist,
+__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_raygen(const __grid_constant__ DScene S, WaveState W, Queues Q, const int* __restrict__ pixlist,
                                                            uint32_t c0, uint32_t npix, int s0, uint32_t ns) {
-  const DScene& S = *Sp;
   const uint32_t total = npix * ns;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     uint32_t slot = i % npix, s = i / npix;
@@ -186,25 +254,22 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK) k_raygen(const DScene* __restr
 }
 // explicit (pixel, sample number) list: pt_li / pt_camera_rays
 template <int NC>
-__global__ void k_raygen_list(const DScene* __restrict__ Sp, WaveState W, Queues Q, const int* __restrict__ pixel_xy, const int* __restrict__ sample_num,
+__global__ void k_raygen_list(const __grid_constant__ DScene S, WaveState W, Queues Q, const int* __restrict__ pixel_xy, const int* __restrict__ sample_num,
                               uint32_t n) {
-  const DScene& S = *Sp;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     raygen_body<NC>(S, W, Q, i, pixel_xy[2 * i], pixel_xy[2 * i + 1], sample_num[i]);
 }
 
 // One shade kernel per shading class; the bin size is read on the device (no host round trip between trace and shade).
 template <int NC, int CLS>
-__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_shade(const DScene* __restrict__ Sp, WaveState W, Queues Q, unsigned long long* vertex_counter) {
-  const DScene& S = *Sp;
+__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WaveState W, Queues Q, unsigned long long* vertex_counter) {
   const uint32_t n = Q.counts[8 + CLS];
   const uint32_t* bin = Q.bins + (size_t)CLS * W.cap;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) shade_body<NC, CLS>(S, W, Q, bin[k], vertex_counter);
 }
 
 template <int NC>
-__global__ void k_finish(const DScene* __restrict__ Sp, WaveState W, uint32_t n) {
-  const DScene& S = *Sp;
+__global__ void k_finish(const __grid_constant__ DScene S, WaveState W, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) finish_body<NC>(S, W, i);
 }
 
@@ -216,16 +281,14 @@ __global__ void k_set_slots(const int* __restrict__ pixlist, uint32_t c0, uint32
 }
 
 template <int NC>
-__global__ void k_film(const DScene* __restrict__ Sp, WaveState W, const int* __restrict__ slot_of, uint32_t npix, uint32_t ns, int x0, int y0, int x1, int y1,
+__global__ void k_film(const __grid_constant__ DScene S, WaveState W, const int* __restrict__ slot_of, uint32_t npix, uint32_t ns, int x0, int y0, int x1, int y1,
                        f4* film) {
-  const DScene& S = *Sp;
   int w = x1 - x0, h = y1 - y0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x)
     film_gather_body<NC>(S, W, slot_of, npix, ns, x0 + i % w, y0 + i / w, film);
 }
 
-__global__ void k_film_resolve(const DScene* __restrict__ Sp, const f4* film, float* rgb, uint32_t n) {
-  const DScene& S = *Sp;
+__global__ void k_film_resolve(const __grid_constant__ DScene S, const f4* film, float* rgb, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) film_resolve_body(S.film, film[i], rgb + 3 * (size_t)i);
 }
 
@@ -249,14 +312,13 @@ struct ArrayIO {  // pt_intersect / pt_intersect_p / pt_intersect_device: rays a
   }
 };
 template <bool INST, bool COUNT>
-__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_intersect(const DScene* __restrict__ Sp, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
+__global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_intersect(const __grid_constant__ DScene S, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n,
                                                               f4* hits, float* t_out, unsigned char* occ, uint32_t* fetch, unsigned long long* counters,
                                                               int* overflow) {
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
-  const DScene& S = *Sp;
+  int spill[PT_MAX_STACK - PT_SMEM_STACK];
   SharedStack st;
-  st.sm = smem + threadIdx.x;
-  st.n = 0;
+  st.attach(smem + threadIdx.x, spill);
   TravCounters tc;
   tc.nodes = 0; tc.tris = 0;
   int ovf = 0;
@@ -269,8 +331,7 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_intersec
   if (ovf) *overflow = 1;
 }
 
-__global__ void k_sampler_values(const DScene* __restrict__ Sp, const int* pixel_xy, const int* sample_num, uint32_t n, uint32_t dim0, uint32_t ndims, float* out) {
-  const DScene& S = *Sp;
+__global__ void k_sampler_values(const __grid_constant__ DScene S, const int* pixel_xy, const int* sample_num, uint32_t n, uint32_t dim0, uint32_t ndims, float* out) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n * ndims; i += gridDim.x * blockDim.x) {
     uint32_t s = i / ndims, k = i % ndims;
     int px = pixel_xy[2 * s], py = pixel_xy[2 * s + 1];
@@ -281,8 +342,7 @@ __global__ void k_sampler_values(const DScene* __restrict__ Sp, const int* pixel
 
 // ---- SpatialLightDistribution::compute_distribution for every voxel (spatial.rs:113-197) ---------------------------
 template <int NC>
-__global__ void k_voxel_contrib(const DScene* __restrict__ Sp, float* func, uint32_t n_vox) {
-  const DScene& S = *Sp;
+__global__ void k_voxel_contrib(const __grid_constant__ DScene S, float* func, uint32_t n_vox) {
   const uint32_t nl = S.n_lights;
   const LightDistDev& D = S.ld;
   for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < (size_t)n_vox * nl; id += (size_t)gridDim.x * blockDim.x) {

@@ -233,10 +233,23 @@ struct Flat {
         idx[k] = ref(kids[k], d);
       }
     GpuNodeH& g = (*nodes)[off];
+    // The reference keeps a zero box in an empty lane and skips the lane by its child index (qbvh_x86.rs:69-74,267-274);
+    // here the lane gets the box (+inf, -inf), which no slab test can hit, so the traversal needs no index check.
     for (int a = 0; a < 3; a++)
-      for (int k = 0; k < 4; k++) { g.lo[a][k] = box[k].mn[a]; g.hi[a][k] = box[k].mx[a]; }
+      for (int k = 0; k < 4; k++) {
+        g.lo[a][k] = kids[k] >= 0 ? box[k].mn[a] : INFINITY;
+        g.hi[a][k] = kids[k] >= 0 ? box[k].mx[a] : -INFINITY;
+      }
     for (int k = 0; k < 4; k++) g.child[k] = idx[k];
     g.meta[0] = (n.axis & 3) | ((c0.axis & 3) << 2) | ((c1.axis & 3) << 4);
+    // meta.w: for each of the 8 ray sign octants sg (bit a = sign of d[a]) the ORDER_TABLE column
+    // sign[axis_top] << 2 | sign[axis_left] << 1 | sign[axis_right] (qbvh_x86.rs:264-266), 3 bits each
+    uint32_t tab = 0;
+    for (uint32_t sg = 0; sg < 8; sg++) {
+      uint32_t st = (sg >> (n.axis & 3)) & 1u, sl = (sg >> (c0.axis & 3)) & 1u, sr = (sg >> (c1.axis & 3)) & 1u;
+      tab |= ((st << 2) | (sl << 1) | sr) << (3 * sg);
+    }
+    g.meta[3] = (int32_t)tab;
     return (int32_t)off;
   }
 };

@@ -14,6 +14,7 @@
 #define __shared__ static
 #define __forceinline__ inline
 #define __restrict__
+#define __grid_constant__
 #define __launch_bounds__(...)
 
 struct hc_dim3 { unsigned x, y, z; };
