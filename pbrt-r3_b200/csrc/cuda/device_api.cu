@@ -122,6 +122,9 @@ struct pt_scene {
   int pix_key[3] = {-1, -1, -1};
   std::vector<int> pix_host;
   std::unique_ptr<DevBufs> pix_bufs;
+  // Sampler "random": per render tile {first pixel in pixlist, pixel count, tile number in the whole film}
+  std::vector<int> tiles_host;
+  int* tiles = nullptr;
   ~pt_scene() {
     if (stream) cudaStreamDestroy(stream);
     if (d) cudaFree(d);
@@ -298,7 +301,6 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   SD.spp = D->sampler.samples_per_pixel;
   SD.at_center = D->sampler.sample_at_pixel_center;
   for (int i = 0; i < 4; i++) SD.sb[i] = D->film.sample_bounds[i];
-  if (SD.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\": per-tile sequential PCG32 streams are not reproduced on the GPU path yet"); return 1; }
   if (SD.sb[2] - SD.sb[0] >= 65536 || SD.sb[3] - SD.sb[1] >= 32768) { pt_set_error("film too large for packed pixel ids"); return 1; }
   {
     int res[2] = {SD.sb[2] - SD.sb[0], SD.sb[3] - SD.sb[1]};
@@ -534,23 +536,62 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
   return 0;
 }
 
+int finish_render(pt_scene* s, pt_stats* st, const WaveTotals& T, bool count) {
+  CK(cudaStreamSynchronize(s->stream));
+  int ovf = 0;
+  CK(cudaMemcpy(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ovf) { pt_set_error("traversal stack overflow"); return 1; }
+  if (st) {
+    st->regular_rays += T.regular;
+    st->shadow_rays += T.shadow;
+    st->kernel_launches += T.launches;
+    st->extend_ms += T.trace_ms;
+    st->shade_ms += T.shade_ms;
+    st->extend_launches += T.trace_launches;
+    st->extend_rays += T.trace_rays;
+    if (count) {
+      unsigned long long c[4];
+      CK(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
+      st->nodes_visited += c[0];
+      st->tris_tested += c[1];
+      st->path_vertices += c[2];
+      st->extend_bytes += 128ull * c[0] + 48ull * c[1] + 48ull * T.trace_rays;
+      CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
+    }
+  }
+  return 0;
+}
+
 int build_pixlist(pt_scene* s, int shard_index, int shard_count, int tile) {
   if (s->pix_key[0] == shard_index && s->pix_key[1] == shard_count && s->pix_key[2] == tile && s->pix_bufs) return 0;
   const int* sb = s->h.film.sample_bounds;
   int w = sb[2] - sb[0], h = sb[3] - sb[1];
   std::vector<int>& px = s->pix_host;
   px.clear();
+  s->tiles_host.clear();
   int ntx = (w + tile - 1) / tile, nty = (h + tile - 1) / tile;
   for (int ty = 0; ty < nty; ty++)
     for (int tx = 0; tx < ntx; tx++) {
       int ti = ty * ntx + tx;
       if (shard_count > 1 && (ti % shard_count) != shard_index) continue;
+      int first = (int)px.size();
       for (int y = ty * tile; y < std::min((ty + 1) * tile, h); y++)
         for (int x = tx * tile; x < std::min((tx + 1) * tile, w); x++) px.push_back((y << 16) | x);
+      s->tiles_host.push_back(first);
+      s->tiles_host.push_back((int)px.size() - first);
+      s->tiles_host.push_back(ti);
     }
   s->pix_bufs.reset(new DevBufs());
   const int* dp = nullptr;
   CK(s->pix_bufs->upload(px.data(), px.size(), &dp));
+  s->tiles = nullptr;
+  s->h.tile_rng = nullptr;
+  if (s->h.sampler.type == PT_SAMPLER_RANDOM && !s->tiles_host.empty()) {
+    const int* dt = nullptr;
+    CK(s->pix_bufs->upload(s->tiles_host.data(), s->tiles_host.size(), &dt));
+    s->tiles = (int*)dt;
+    CK(s->pix_bufs->alloc(s->tiles_host.size() / 3, &s->h.tile_rng));
+  }
   s->pixlist = (int*)dp;
   s->pix_n = (uint32_t)px.size();
   s->pix_key[0] = shard_index; s->pix_key[1] = shard_count; s->pix_key[2] = tile;
@@ -614,29 +655,91 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     CK(cudaGetLastError());
     T.launches++;
   }
-  CK(cudaStreamSynchronize(s->stream));
-  int ovf = 0;
-  CK(cudaMemcpy(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost));
-  if (ovf) { pt_set_error("traversal stack overflow"); return 1; }
-  if (st) {
-    st->regular_rays += T.regular;
-    st->shadow_rays += T.shadow;
-    st->kernel_launches += T.launches;
-    st->extend_ms += T.trace_ms;
-    st->shade_ms += T.shade_ms;
-    st->extend_launches += T.trace_launches;
-    st->extend_rays += T.trace_rays;
-    if (count) {
-      unsigned long long c[4];
-      CK(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
-      st->nodes_visited += c[0];
-      st->tris_tested += c[1];
-      st->path_vertices += c[2];
-      st->extend_bytes += 128ull * c[0] + 48ull * c[1] + 48ull * T.trace_rays;
-      CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
-    }
+  return finish_render(s, st, T, count);
+}
+
+// Sampler "random" (samplers/random.rs): the reference gives every 16x16 render tile its own PCG32 sequence
+// (sampler.rs:285, seed = tile number) and runs the tile's pixels and samples one after the other, each path drawing a
+// data-dependent count of numbers.  Reproducing the streams therefore serialises the paths of a tile: wave (q, n) carries
+// sample n of pixel q of every tile, all tiles in parallel; the film is gathered once per tile group as usual.
+template <int NC>
+int render_waves_random(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
+  const int spp = s->h.sampler.spp;
+  if (o && !(o->spp_begin == 0 && o->spp_end == 0) && !(o->spp_begin <= 0 && o->spp_end >= spp)) {
+    pt_set_error("Sampler \"random\": a sample-number range cannot be rendered on its own (sequential per-tile streams); shard by tiles");
+    return 1;
   }
-  return 0;
+  int shard_i = o ? o->shard_index : 0, shard_n = (o && o->shard_count > 0) ? o->shard_count : 1;
+  bool count = o && o->collect_counters;
+  if (build_pixlist(s, shard_i, shard_n, 16)) return 1;  // render tiles are 16x16 (sampler.rs:267)
+  const uint32_t n_tiles = (uint32_t)(s->tiles_host.size() / 3);
+  if (n_tiles == 0 || spp <= 0 || s->h.n_lights == 0) return 0;
+  {  // RNG::new_sequence(tile number) (core/rng.rs:21-33)
+    std::vector<uint64_t> init(n_tiles);
+    for (uint32_t t = 0; t < n_tiles; t++) {
+      Pcg r;
+      r.state = 0;
+      r.inc = ((uint64_t)(uint32_t)s->tiles_host[3 * t + 2] << 1) | 1ull;
+      r.next();
+      r.state += 0x853c49e6748fea9bULL;
+      r.next();
+      init[t] = r.state;
+    }
+    CK(cudaMemcpy(s->h.tile_rng, init.data(), n_tiles * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  }
+  uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? (4u << 20) : (1u << 19));
+  cap = std::max<uint32_t>(cap, 256u * (uint32_t)spp);
+  const int* sb = s->h.film.sample_bounds;
+  const int* cb = s->h.film.cropped_pixel_bounds;
+  const int sbw = sb[2] - sb[0];
+  const float rx = s->h.film.filter_radius[0], ry = s->h.film.filter_radius[1];
+  WaveTotals T;
+  for (uint32_t t0 = 0; t0 < n_tiles;) {
+    uint32_t t1 = t0, npix = 0, maxq = 0;
+    while (t1 < n_tiles && (uint64_t)(npix + (uint32_t)s->tiles_host[3 * t1 + 1]) * (uint64_t)spp <= cap) {
+      npix += (uint32_t)s->tiles_host[3 * t1 + 1];
+      maxq = std::max(maxq, (uint32_t)s->tiles_host[3 * t1 + 1]);
+      t1++;
+    }
+    const uint32_t c0 = (uint32_t)s->tiles_host[3 * t0];
+    const uint32_t n = npix * (uint32_t)spp;
+    if (ensure_wave(s, n)) return 1;
+    PT_LAUNCH(grid_for(s, npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, c0, npix, sbw, s->slot_of, 0);
+    CK(cudaGetLastError());
+    T.launches++;
+    int minx = 1 << 30, miny = 1 << 30, maxx = -(1 << 30), maxy = -(1 << 30);
+    for (uint32_t i = c0; i < c0 + npix; i++) {
+      int pk = s->pix_host[i], x = (pk & 0xffff) + sb[0], y = (pk >> 16) + sb[1];
+      minx = std::min(minx, x); maxx = std::max(maxx, x); miny = std::min(miny, y); maxy = std::max(maxy, y);
+    }
+    int fx0 = std::max((int)floorf((float)minx - rx), cb[0]), fy0 = std::max((int)floorf((float)miny - ry), cb[1]);
+    int fx1 = std::min((int)ceilf((float)(maxx + 1) + rx), cb[2]), fy1 = std::min((int)ceilf((float)(maxy + 1) + ry), cb[3]);
+    for (uint32_t q = 0; q < maxq; q++) {
+      uint32_t active = 0;
+      for (uint32_t t = t0; t < t1; t++) active += (uint32_t)s->tiles_host[3 * t + 1] > q ? 1u : 0u;
+      for (int smp = 0; smp < spp; smp++) {
+        CK(cudaMemsetAsync(s->Q.counts + 5, 0, sizeof(uint32_t), s->stream));
+        PT_LAUNCH(grid_for(s, t1 - t0, 128, 8), 128, s->stream, k_raygen_random<NC>)(s->h, s->W, s->Q, s->pixlist, s->tiles, t0, t1 - t0, c0, npix, q, smp);
+        CK(cudaGetLastError());
+        T.launches++;
+        if (st) st->camera_rays += active;
+        if (run_bounces<NC>(s, active, count, st != nullptr, &T)) return 1;
+      }
+    }
+    PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->h, s->W, n);
+    CK(cudaGetLastError());
+    T.launches++;
+    if (fx1 > fx0 && fy1 > fy0) {
+      PT_LAUNCH(grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, s->stream, k_film<NC>)(s->h, s->W, s->slot_of, npix, (uint32_t)spp, fx0, fy0, fx1, fy1, s->film);
+      CK(cudaGetLastError());
+      T.launches++;
+    }
+    PT_LAUNCH(grid_for(s, npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, c0, npix, sbw, s->slot_of, 1);
+    CK(cudaGetLastError());
+    T.launches++;
+    t0 = t1;
+  }
+  return finish_render(s, st, T, count);
 }
 
 int launch_intersect(pt_scene* s, const f4* ro, const f4* rd, uint32_t n, f4* hits, float* tt, unsigned char* occ, bool count) {
@@ -727,7 +830,9 @@ int pt_render_partial(pt_scene* s, const pt_render_opts* opts, float** dev_film_
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, s->stream));
-  int rc = s->h.n_channels == 3 ? render_waves<3>(s, opts, stats) : render_waves<PT_NCS>(s, opts, stats);
+  int rc;
+  if (s->h.sampler.type == PT_SAMPLER_RANDOM) rc = s->h.n_channels == 3 ? render_waves_random<3>(s, opts, stats) : render_waves_random<PT_NCS>(s, opts, stats);
+  else rc = s->h.n_channels == 3 ? render_waves<3>(s, opts, stats) : render_waves<PT_NCS>(s, opts, stats);
   if (rc) return rc;
   CK(cudaEventRecord(e1, s->stream));
   CK(cudaEventSynchronize(e1));
@@ -837,6 +942,7 @@ int pt_intersect_device(pt_scene* s, const void* dev_o_tmax, const void* dev_d_t
 int pt_sampler_values(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, uint32_t dim0, uint32_t ndims, float* out) {
   if (!s || !pixel_xy || !sample_num || !out) { pt_set_error("null argument"); return 1; }
   CK(cudaSetDevice(s->device));
+  if (s->h.sampler.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\" has no index-based stream: only pt_render reproduces it (per-tile sequential PCG32)"); return 1; }
   if (n == 0 || ndims == 0) return 0;
   DevBufs B;
   const int *pxy, *sn;
@@ -875,6 +981,7 @@ static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_
 int pt_camera_rays(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, float* rays, float* p_film) {
   if (!s || !pixel_xy || !sample_num || !rays) { pt_set_error("null argument"); return 1; }
   CK(cudaSetDevice(s->device));
+  if (s->h.sampler.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\" has no index-based stream: only pt_render reproduces it (per-tile sequential PCG32)"); return 1; }
   if (n == 0) return 0;
   if (run_list(s, pixel_xy, sample_num, n, false)) return 1;
   std::vector<f4> o(n), d(n);
@@ -893,6 +1000,7 @@ int pt_camera_rays(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_n
 int pt_li(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, float* out_l) {
   if (!s || !pixel_xy || !sample_num || !out_l) { pt_set_error("null argument"); return 1; }
   CK(cudaSetDevice(s->device));
+  if (s->h.sampler.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\" has no index-based stream: only pt_render reproduces it (per-tile sequential PCG32)"); return 1; }
   if (n == 0) return 0;
   if (run_list(s, pixel_xy, sample_num, n, true)) return 1;
   const uint32_t NC = s->h.n_channels, cap = s->W.cap;

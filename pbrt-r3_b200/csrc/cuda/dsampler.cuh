@@ -169,15 +169,33 @@ PT_HDN float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, i
 
 struct SampleStream {  // the per-path sampler state
   int64_t index;
-  uint32_t dim;
+  uint32_t dim;          // next dimension; Sampler "random": the path's tile slot in DScene::tile_rng
   int px, py;
 };
+
+// Sampler "random" (samplers/random.rs:21-30, core/rng.rs:34-66): every draw advances the PCG32 stream of the path's
+// render tile.  The reference runs the pixels and samples of a tile one after the other on one stream, so a wave holds at
+// most one path per tile and the state lives in memory, not in the path.
+PT_HD float random_draw(const DScene& S, uint32_t tile_slot, uint64_t tile_seq) {
+  uint64_t old = S.tile_rng[tile_slot];
+  S.tile_rng[tile_slot] = old * 0x5851f42d4c957f2dULL + ((tile_seq << 1) | 1ull);
+  uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
+  uint32_t rot = (uint32_t)(old >> 59);
+  uint32_t r = (xs >> rot) | (xs << ((~rot + 1u) & 31u));
+  return fminf(PT_ONE_MINUS_EPS, (float)r * 2.3283064365386963e-10f);
+}
 PT_HD float get1d(const DScene& S, SampleStream& st) {
+  if (S.sampler.type == PT_SAMPLER_RANDOM) return random_draw(S, st.dim, (uint64_t)st.index);
   float v = sampler_dim(S, st.index, st.dim, st.px, st.py);
   st.dim += 1;
   return v;
 }
 PT_HD f2 get2d(const DScene& S, SampleStream& st) {
+  if (S.sampler.type == PT_SAMPLER_RANDOM) {
+    float a = random_draw(S, st.dim, (uint64_t)st.index);
+    float b = random_draw(S, st.dim, (uint64_t)st.index);
+    return mk2(a, b);
+  }
   float a = sampler_dim(S, st.index, st.dim, st.px, st.py);
   float b = sampler_dim(S, st.index, st.dim + 1, st.px, st.py);
   st.dim += 2;

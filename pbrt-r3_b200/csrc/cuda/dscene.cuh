@@ -99,6 +99,9 @@ struct DScene {
   const uint32_t* sobol32;     // 1024*52
   const uint64_t* vdc;         // (25+26)*52
   int has_instances;
+  // Sampler "random": PCG32 state of every 16x16 render tile of the current shard (samplers/random.rs; one sequential
+  // stream per tile, sampler.rs:285); rewritten by every draw
+  uint64_t* tile_rng;
 };
 
 }  // namespace ptd

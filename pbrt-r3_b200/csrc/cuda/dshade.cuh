@@ -236,11 +236,15 @@ inline uint32_t queue_push(uint32_t* counter) { return (*counter)++; }
 #endif
 
 // camera-ray generation for path slot i of the current wave: pixel (px,py) absolute, sample number n
+// Sampler "random": tile_slot / tile_seq select the PCG32 stream (st.index carries the sequence number = tile index of the
+// whole film, st.dim the slot); the path is appended to the queue at position qpos instead of i.
 template <int NC>
-PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int px, int py, int n) {
+PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int px, int py, int n, int tile_slot = -1, uint32_t tile_seq = 0u,
+                       uint32_t qpos = 0xffffffffu) {
   SampleStream st;
   st.px = px; st.py = py; st.dim = 0;
-  st.index = sampler_index(S, px, py, n);
+  if (tile_slot >= 0) { st.index = (int64_t)tile_seq; st.dim = (uint32_t)tile_slot; }
+  else st.index = sampler_index(S, px, py, n);
   f2 u = get2d(S, st);
   f2 pf = mk2((float)px + u.x, (float)py + u.y);
   f2 pl = get2d(S, st);
@@ -258,7 +262,7 @@ PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int
   st_store<NC>(W.L, W.cap, i, sp_const<NC>(0.0f));
   st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(0.0f));
   st_store<NC>(W.pendB, W.cap, i, sp_const<NC>(0.0f));
-  Q.ext[i] = i;
+  Q.ext[qpos == 0xffffffffu ? i : qpos] = i;
 }
 
 // One iteration of PathIntegrator::li's loop body after scene.intersect (path.rs:87-233) for path slot i.

@@ -252,6 +252,21 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK) k_raygen(const __grid_constant
     raygen_body<NC>(S, W, Q, i, px, py, s0 + (int)s);
   }
 }
+// Sampler "random", wave w of a tile group: one path per tile = pixel number w / spp of the tile (scan order, as
+// render_tile visits them), sample number w % spp.  tiles[t] = {first pixel in pixlist, pixel count, tile sequence number}.
+template <int NC>
+__global__ void k_raygen_random(const __grid_constant__ DScene S, WaveState W, Queues Q, const int* __restrict__ pixlist, const int* __restrict__ tiles,
+                                uint32_t tile0, uint32_t n_tiles, uint32_t c0, uint32_t npix, uint32_t q, int sample) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+    const int* tr = tiles + 3 * (size_t)(tile0 + t);
+    if (q >= (uint32_t)tr[1]) continue;
+    uint32_t slot = (uint32_t)tr[0] + q - c0;
+    int pk = pixlist[c0 + slot];
+    int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
+    uint32_t qpos = atomicAdd(&Q.counts[5], 1u);
+    raygen_body<NC>(S, W, Q, (uint32_t)sample * npix + slot, px, py, sample, (int)(tile0 + t), (uint32_t)tr[2], qpos);
+  }
+}
 // explicit (pixel, sample number) list: pt_li / pt_camera_rays
 template <int NC>
 __global__ void k_raygen_list(const __grid_constant__ DScene S, WaveState W, Queues Q, const int* __restrict__ pixel_xy, const int* __restrict__ sample_num,

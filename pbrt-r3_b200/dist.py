@@ -12,6 +12,16 @@ def spp_shard(spp_total, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def shard_opts(sampler_type, spp_total, rank, world):
+    """pt_render_partial options of this rank.  Halton / Sobol samples are pure functions of (pixel, sample number):
+    shard the sample numbers.  Sampler "random" draws from one sequential PCG32 stream per 16x16 render tile
+    (samplers/random.rs), so only whole tiles can be split: interleave the tiles across ranks."""
+    if int(sampler_type) == 2:   # PT_SAMPLER_RANDOM
+        return {"shard_index": int(rank), "shard_count": int(world)}
+    b, e = spp_shard(spp_total, rank, world)
+    return {"spp_begin": b, "spp_end": e}
+
+
 class _CudaArray:
     """Zero-copy view of a device pointer for torch.as_tensor (__cuda_array_interface__ v2)."""
 

@@ -42,6 +42,13 @@ def test_spp_shards_partition():
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
 
 
+def test_shard_opts_by_sampler():
+    from pbrt_r3_b200 import dist as D
+    assert D.shard_opts(0, 64, 1, 4) == {"spp_begin": 16, "spp_end": 32}
+    assert D.shard_opts(1, 64, 3, 4) == {"spp_begin": 48, "spp_end": 64}
+    assert D.shard_opts(2, 64, 1, 4) == {"shard_index": 1, "shard_count": 4}
+
+
 def test_two_rank_film_reduce_matches_single_process(P, tmp_path):
     import oracle_api
     out = str(tmp_path / "img.npy")

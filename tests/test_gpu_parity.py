@@ -236,5 +236,16 @@ def test_edge_cases(P):
     sc = P.Scene(hs, 0)
     assert not sc.render()[0].any()
     sc.close()
-    with pytest.raises(P.PbrtError):
-        P.Scene(P.HostScene.parse_string(P.scenes.cornell_box(res=16, spp=1, sampler="random")), 0)
+    with pytest.raises(P.PbrtError):   # the random sampler has no (pixel, sample number) -> value function
+        P.Scene(P.HostScene.parse_string(P.scenes.cornell_box(res=16, spp=1, sampler="random")), 0).li(np.zeros((1, 2), np.int32), np.zeros(1, np.int32))
+
+
+def test_image_random_sampler(P, pair):
+    """Sampler "random" (samplers/random.rs): per-tile sequential PCG32 streams reproduced; image and ray counts vs the oracle."""
+    hs, sc, orc = pair("random", P.scenes.cornell_box(res=72, spp=4, sampler="random"))
+    rgb, st = sc.render(collect_counters=1)
+    ref, so = orc.render()
+    assert rel_rmse(rgb, ref) <= RMSE_TOL, rel_rmse(rgb, ref)
+    for k in ("camera_rays", "regular_rays", "shadow_rays"):
+        assert abs(st[k] - so[k]) <= 1e-3 * so[k], (k, st[k], so[k])
+    assert np.array_equal(rgb, sc.render()[0])

@@ -171,3 +171,26 @@ def test_device_sincos_equals_libm(tmp_path):
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", os.path.join(ROOT, "tools", "check_sincos.cpp"), "-o", exe])
     out = subprocess.check_output([exe, "5000000"]).decode().split()
     assert out[0] == "0" and out[1] == "0", out
+
+
+def test_push_position_formula_matches_order_table():
+    """k_trace stores hit child k at stack position popc(mask & before_k) (dtrav2.cuh, trav_node_step) instead of walking
+    the reference's ORDER_TABLE nibble list (qbvh_x86.rs:187-204).  Check the closed form against all 128 entries."""
+    import re
+    src = open(os.path.join(ROOT, "pbrt-r3_b200", "csrc", "cuda", "dtrav.cuh")).read()
+    body = src[src.index("kOrderTable[128] = {"):]
+    body = body[:body.index("};")]
+    table = [int(x, 16) for x in re.findall(r"0x[0-9a-fA-F]+", body)]
+    assert len(table) == 128
+    for mask in range(16):
+        for s in range(8):
+            order, lst = table[mask * 8 + s], []
+            while (order & 4) == 0:
+                lst.append(order & 3)
+                order >>= 4
+            bl = 0 if (s & 4) else 0xC
+            br = 0x3 if (s & 4) else 0
+            before = [bl | (0 if (s & 2) else 2), bl | (1 if (s & 2) else 0), br | (0 if (s & 1) else 8), br | (4 if (s & 1) else 0)]
+            mine = sorted([k for k in range(4) if mask & (1 << k)], key=lambda k: bin(mask & before[k]).count("1"))
+            assert mine == lst, (mask, s, mine, lst)
+            assert sorted(bin(mask & before[k]).count("1") for k in mine) == list(range(len(lst)))

@@ -87,3 +87,30 @@ def test_hostcheck_gaussian_filter_film(HC):
     rgb, _ = P.Scene(hs).render(wave_paths=500)
     ref, _ = oracle_api.OracleScene(hs).render(threads=2)
     assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5
+
+
+def test_hostcheck_random_sampler_tile_streams(HC):
+    """Sampler "random": one PCG32 stream per 16x16 render tile, drawn from in pixel / sample / path order
+    (samplers/random.rs, sampler.rs:285).  Same image and the same ray / node / triangle counts as the oracle's
+    tile-sequential loop; tile groups (small waves) and tile shards do not change the streams."""
+    P = HC
+    import oracle_api
+    import ctypes as C
+    from pbrt_r3_b200 import dist as D
+    hs = P.HostScene.parse_string(P.scenes.cornell_box(res=33, spp=2, sampler="random"))
+    sc = P.Scene(hs)
+    rgb, st = sc.render(collect_counters=1)
+    ref, so = oracle_api.OracleScene(hs).render(threads=2)
+    assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5
+    for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+        assert st[k] == so[k], k
+    assert np.array_equal(rgb, sc.render(wave_paths=600)[0])
+    acc = np.zeros(33 * 33 * 4, np.float32)
+    for r in range(3):
+        ptr, n, _ = sc.render_partial(shard_index=r, shard_count=3)
+        acc += np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), (n * 4,))
+    assert np.sqrt(((D.resolve_host(acc).reshape(33, 33, 3) - rgb) ** 2).mean()) / rgb.mean() < 1e-6
+    with pytest.raises(P.PbrtError):
+        sc.render_partial(spp_begin=0, spp_end=1)      # a sample range alone cannot reproduce the sequential streams
+    with pytest.raises(P.PbrtError):
+        sc.li(np.zeros((1, 2), np.int32), np.zeros(1, np.int32))
