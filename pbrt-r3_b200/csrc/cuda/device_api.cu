@@ -2,19 +2,7 @@
 // stage entry points.  Replaces SceneContext::make_scene/make_integrator (scene_context.rs:675-731), QBVHAccel::new
 // (qbvh_x86.rs:352-371), Integrator::render (core/integrator/sampler.rs:259-325) and Film::write_image (film.rs:440-472).
 // There is no CPU fallback: every entry point fails with an error when CUDA is unavailable.
-#if defined(PT_HOSTCHECK)
-// tests/hostcheck: the SAME sources compiled by g++ against a serial stand-in for the CUDA runtime, to check the
-// stage logic on a CPU-only box.  Never built into the product library (which needs a CUDA device).
-#include "cuda_shim.h"
-#define PT_LAUNCH(grid, block, stream, ...) hostcheck::begin_launch(), __VA_ARGS__
-#else
-#include <cuda_runtime.h>
-#define PT_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<(grid), (block), 0, (stream)>>>
-#endif
-// spectral channel count of the second template instantiation (tests/hostcheck may build RGB only to save compile time)
-#ifndef PT_NCS
-#define PT_NCS 60
-#endif
+#include "launch.cuh"
 
 #include <algorithm>
 #include <cfloat>
@@ -33,6 +21,8 @@
 using namespace ptd;
 
 void pt_set_error(const std::string& s);
+// shade_tu.cu: k_shade<n_channels, cls> (PT_SHADE_BLOCK threads per block) on `stream`
+void launch_shade(int n_channels, int cls, int grid, cudaStream_t stream, const DScene& S, const WaveState& W, const Queues& Q, unsigned long long* vertex_counter);
 
 #define CK(call)                                                                                             \
   do {                                                                                                       \
@@ -513,9 +503,8 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
-#define LAUNCH_SHADE(C) if (s->class_mask & (1u << (C))) { PT_LAUNCH(gs, PT_SHADE_BLOCK, s->stream, k_shade<NC, C>)(s->h, W, Q, vc); T->launches++; }
-      LAUNCH_SHADE(CL_NONE) LAUNCH_SHADE(CL_MATTE) LAUNCH_SHADE(CL_PLASTIC) LAUNCH_SHADE(CL_GLASS) LAUNCH_SHADE(CL_METAL) LAUNCH_SHADE(CL_MIRROR)
-#undef LAUNCH_SHADE
+      for (int c = 0; c < CL_COUNT; c++)
+        if (s->class_mask & (1u << c)) { launch_shade(NC, c, gs, s->stream, s->h, W, Q, vc); T->launches++; }
       CK(cudaGetLastError());
     }
     if (timed) cudaEventRecord(e2, s->stream);
@@ -1057,3 +1046,7 @@ int pt_light_distribution(pt_scene* s, const float* points, uint32_t n, float* o
 }
 
 }  // extern "C"
+
+#if defined(PT_HOSTCHECK)
+#include "shade_tu.cu"  // tests/hostcheck builds one translation unit
+#endif

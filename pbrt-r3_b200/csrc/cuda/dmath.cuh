@@ -13,7 +13,7 @@
 #define PT_D __device__ __forceinline__
 /* large stage functions: ONE out-of-line copy each keeps the shade kernel inside the instruction cache (ncu: the
    fully inlined kernel was 34K instructions and stalled on no_instruction for 19-63 cycles per issue) */
-#define PT_HDN __host__ __device__ __noinline__
+#define PT_HDN inline __host__ __device__ __noinline__
 #else
 #define PT_HD inline
 #define PT_D inline
@@ -92,6 +92,15 @@ PT_HD float bitsf(uint32_t u) {
 PT_HD bool isinf_(float v) { return (fbits(v) & 0x7fffffffu) == 0x7f800000u; }
 PT_HD bool isfinite_(float v) { return (fbits(v) & 0x7f800000u) != 0x7f800000u; }
 PT_HD bool signbit_(float v) { return (fbits(v) >> 31) != 0; }
+// IEEE division whatever -prec-div says: the shade translation unit is compiled with approximate division / sqrt, but
+// sampler values and the voxel of the light distribution must stay bit-exact (SURVEY 8d parity gates)
+PT_HD float div_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
 PT_HD int popc_(unsigned v) {
 #if defined(__CUDA_ARCH__)
   return __popc(v);

@@ -25,7 +25,7 @@ PT_HD uint64_t rev64(uint64_t n) { return ((uint64_t)rev32((uint32_t)n) << 32) |
 
 // radical_inverse(base_index, a): base 2 by bit reversal, otherwise the digit loop (radical_inverse.rs:38-58)
 PT_HD float radical_inverse_base(uint32_t base, uint64_t a) {
-  float inv_base = 1.0f / (float)base;
+  float inv_base = div_rn(1.0f, (float)base);
   uint64_t rev = 0;
   float inv_base_n = 1.0f;
   if (a < 0x100000000ull) {  // 32-bit fast path: same digits, same float sequence
@@ -60,7 +60,7 @@ PT_HD uint32_t div_magic(uint32_t a, uint64_t magic) {
 }
 
 PT_HD float scrambled_radical_inverse(uint32_t base, uint64_t magic, uint64_t a, const uint16_t* perm) {  // radical_inverse.rs:71-91
-  float inv_base = 1.0f / (float)base;
+  float inv_base = div_rn(1.0f, (float)base);
   uint64_t rev = 0;
   float inv_base_n = 1.0f;
   if (a < 0x100000000ull) {
@@ -81,7 +81,7 @@ PT_HD float scrambled_radical_inverse(uint32_t base, uint64_t magic, uint64_t a,
       a = next;
     }
   }
-  return fminf(inv_base_n * ((float)rev + inv_base * (float)ldg(perm) / (1.0f - inv_base)), PT_ONE_MINUS_EPS);
+  return fminf(inv_base_n * ((float)rev + div_rn(inv_base * (float)ldg(perm), 1.0f - inv_base)), PT_ONE_MINUS_EPS);
 }
 
 PT_HD uint64_t inverse_radical_inverse(uint64_t base, uint64_t inverse, int ndigits) {  // radical_inverse.rs:60-69
@@ -146,8 +146,20 @@ PT_HD int64_t sampler_index(const DScene& S, int px, int py, int64_t n) {
   return (int64_t)sobol_interval_to_index(S.vdc, c.log2_resolution, (uint64_t)n, px - c.sb[0], py - c.sb[1]);
 }
 
+// Sampler "random" (samplers/random.rs:21-30, core/rng.rs:34-66): every draw advances the PCG32 stream of the path's
+// render tile.  The reference runs the pixels and samples of a tile one after the other on one stream, so a wave holds at
+// most one path per tile and the state lives in memory, not in the path.
+PT_HD float random_draw(const DScene& S, uint32_t tile_slot, uint64_t tile_seq) {
+  uint64_t old = S.tile_rng[tile_slot];
+  S.tile_rng[tile_slot] = old * 0x5851f42d4c957f2dULL + ((tile_seq << 1) | 1ull);
+  uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
+  uint32_t rot = (uint32_t)(old >> 59);
+  uint32_t r = (xs >> rot) | (xs << ((~rot + 1u) & 31u));
+  return fminf(PT_ONE_MINUS_EPS, (float)r * 2.3283064365386963e-10f);
+}
 PT_HDN float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, int py) {
   const SamplerDev& c = S.sampler;
+  if (c.type == PT_SAMPLER_RANDOM) return random_draw(S, (uint32_t)((uint64_t)index >> 32), (uint64_t)(uint32_t)index);
   if (c.type == PT_SAMPLER_HALTON) {  // halton.rs:149-162
     if (c.at_center && dim < 2) return 0.5f;
     if (dim == 0) return radical_inverse2((uint64_t)(index >> c.base_exponents[0]));
@@ -168,34 +180,17 @@ PT_HDN float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, i
 }
 
 struct SampleStream {  // the per-path sampler state
-  int64_t index;
-  uint32_t dim;          // next dimension; Sampler "random": the path's tile slot in DScene::tile_rng
+  int64_t index;         // Halton / Sobol sample index; Sampler "random": tile slot << 32 | tile sequence number
+  uint32_t dim;
   int px, py;
 };
 
-// Sampler "random" (samplers/random.rs:21-30, core/rng.rs:34-66): every draw advances the PCG32 stream of the path's
-// render tile.  The reference runs the pixels and samples of a tile one after the other on one stream, so a wave holds at
-// most one path per tile and the state lives in memory, not in the path.
-PT_HD float random_draw(const DScene& S, uint32_t tile_slot, uint64_t tile_seq) {
-  uint64_t old = S.tile_rng[tile_slot];
-  S.tile_rng[tile_slot] = old * 0x5851f42d4c957f2dULL + ((tile_seq << 1) | 1ull);
-  uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
-  uint32_t rot = (uint32_t)(old >> 59);
-  uint32_t r = (xs >> rot) | (xs << ((~rot + 1u) & 31u));
-  return fminf(PT_ONE_MINUS_EPS, (float)r * 2.3283064365386963e-10f);
-}
 PT_HD float get1d(const DScene& S, SampleStream& st) {
-  if (S.sampler.type == PT_SAMPLER_RANDOM) return random_draw(S, st.dim, (uint64_t)st.index);
   float v = sampler_dim(S, st.index, st.dim, st.px, st.py);
   st.dim += 1;
   return v;
 }
 PT_HD f2 get2d(const DScene& S, SampleStream& st) {
-  if (S.sampler.type == PT_SAMPLER_RANDOM) {
-    float a = random_draw(S, st.dim, (uint64_t)st.index);
-    float b = random_draw(S, st.dim, (uint64_t)st.index);
-    return mk2(a, b);
-  }
   float a = sampler_dim(S, st.index, st.dim, st.px, st.py);
   float b = sampler_dim(S, st.index, st.dim + 1, st.px, st.py);
   st.dim += 2;

@@ -186,7 +186,7 @@ PT_HD uint32_t ld_voxel(const LightDistDev& D, f3 p) {
   float o[3] = {p.x - D.wb_min[0], p.y - D.wb_min[1], p.z - D.wb_min[2]};
   uint32_t pi[3];
   for (int i = 0; i < 3; i++) {
-    if (D.wb_max[i] > D.wb_min[i]) o[i] = o[i] / (D.wb_max[i] - D.wb_min[i]);
+    if (D.wb_max[i] > D.wb_min[i]) o[i] = div_rn(o[i], D.wb_max[i] - D.wb_min[i]);
     float c = clampf(o[i], 0.0f, 1.0f);
     uint32_t v = (uint32_t)(c * (float)D.voxels[i]);  // `as u32` saturates; c >= 0
     pi[i] = v < D.voxels[i] - 1 ? v : D.voxels[i] - 1;
@@ -236,14 +236,14 @@ inline uint32_t queue_push(uint32_t* counter) { return (*counter)++; }
 #endif
 
 // camera-ray generation for path slot i of the current wave: pixel (px,py) absolute, sample number n
-// Sampler "random": tile_slot / tile_seq select the PCG32 stream (st.index carries the sequence number = tile index of the
-// whole film, st.dim the slot); the path is appended to the queue at position qpos instead of i.
+// Sampler "random": tile_slot / tile_seq select the PCG32 stream (packed into st.index: slot << 32 | sequence number = tile
+// index of the whole film); the path is appended to the queue at position qpos instead of i.
 template <int NC>
 PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int px, int py, int n, int tile_slot = -1, uint32_t tile_seq = 0u,
                        uint32_t qpos = 0xffffffffu) {
   SampleStream st;
   st.px = px; st.py = py; st.dim = 0;
-  if (tile_slot >= 0) { st.index = (int64_t)tile_seq; st.dim = (uint32_t)tile_slot; }
+  if (tile_slot >= 0) st.index = (int64_t)(((uint64_t)(uint32_t)tile_slot << 32) | (uint64_t)tile_seq);
   else st.index = sampler_index(S, px, py, n);
   f2 u = get2d(S, st);
   f2 pf = mk2((float)px + u.x, (float)py + u.y);

@@ -2,6 +2,7 @@
 // Launch shape: persistent grid-stride kernels, grid = k * 148 SMs (B200), queue sizes read by the host between
 // bounces.  All kernels of a render run on one stream in program order.
 #pragma once
+#include "launch.cuh"
 #include "dfilm.cuh"
 #include "dtrav2.cuh"
 
@@ -11,7 +12,6 @@ namespace ptd {
 #ifndef PT_TRACE_MINBLOCKS
 #define PT_TRACE_MINBLOCKS 7
 #endif
-#define PT_SHADE_BLOCK 128
 
 // Traversal stack: the first PT_SMEM_STACK entries of every thread live in shared memory, strided so that
 // consecutive lanes hit consecutive banks ([entry][thread]); deeper entries spill to a small local array.
@@ -273,14 +273,6 @@ __global__ void k_raygen_list(const __grid_constant__ DScene S, WaveState W, Que
                               uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     raygen_body<NC>(S, W, Q, i, pixel_xy[2 * i], pixel_xy[2 * i + 1], sample_num[i]);
-}
-
-// One shade kernel per shading class; the bin size is read on the device (no host round trip between trace and shade).
-template <int NC, int CLS>
-__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_shade(const __grid_constant__ DScene S, WaveState W, Queues Q, unsigned long long* vertex_counter) {
-  const uint32_t n = Q.counts[8 + CLS];
-  const uint32_t* bin = Q.bins + (size_t)CLS * W.cap;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) shade_body<NC, CLS>(S, W, Q, bin[k], vertex_counter);
 }
 
 template <int NC>

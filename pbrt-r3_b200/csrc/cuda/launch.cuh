@@ -1,0 +1,21 @@
+// launch.cuh — launch macro shared by the translation units of the library (device_api.cu: exact arithmetic;
+// shade_tu.cu: the shading stage, compiled with approximate division / square root).
+#pragma once
+#if defined(PT_HOSTCHECK)
+// tests/hostcheck: the SAME sources compiled by g++ against a serial stand-in for the CUDA runtime, to check the
+// stage logic on a CPU-only box.  Never built into the product library (which needs a CUDA device).
+#include "cuda_shim.h"
+#define PT_LAUNCH(grid, block, stream, ...) hostcheck::begin_launch(), __VA_ARGS__
+#else
+#include <cuda_runtime.h>
+#define PT_LAUNCH(grid, block, stream, ...) __VA_ARGS__<<<(grid), (block), 0, (stream)>>>
+#endif
+// spectral channel count of the second template instantiation (tests/hostcheck may build RGB only to save compile time)
+#ifndef PT_NCS
+#define PT_NCS 60
+#endif
+
+#define PT_SHADE_BLOCK 128
+#ifndef PT_SHADE_MINBLOCKS
+#define PT_SHADE_MINBLOCKS 4
+#endif
