@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--spp", type=int, default=CONFIG["spp"])
     ap.add_argument("--maxdepth", type=int, default=CONFIG["maxdepth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wave-paths", type=int, default=0, help="path slots per wave (0 = library default)")
+    ap.add_argument("--wave-segments", type=int, default=0, help="waves in flight (0 = library default)")
     args = ap.parse_args()
     cfg = {"grid_n": args.grid, "res": args.res, "spp": args.spp, "maxdepth": args.maxdepth}
     if args.impl == "reference":
@@ -165,13 +167,15 @@ def main():
     dev = "cuda:%d" % local
     H, W, _ = hs.image_shape
 
+    wopts = {"wave_paths": args.wave_paths, "wave_segments": args.wave_segments}
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(local)
 
     # untimed counting pass of one step: N_node / N_tri of the reference traversal (deterministic)
-    ptr, npx, cst = sc.render_partial(spp_begin=s0, spp_end=s1, collect_counters=1)
+    ptr, npx, cst = sc.render_partial(spp_begin=s0, spp_end=s1, collect_counters=1, **wopts)
     rays_per_step = cst["regular_rays"] + cst["shadow_rays"]
     samples_per_step = cst["camera_rays"]
     alg_bytes = cst["extend_bytes"]
@@ -179,7 +183,7 @@ def main():
     def step_device():
         """One step; returns (stats, device seconds): CUDA events on the library's launch stream bracket the render
         (pt_stats.device_ms), torch events on torch's stream bracket the NCCL reduce."""
-        ptr, npx, st = sc.render_partial(spp_begin=s0, spp_end=s1)
+        ptr, npx, st = sc.render_partial(spp_begin=s0, spp_end=s1, **wopts)
         dev_ms = st["device_ms"]
         if world > 1:
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -193,9 +197,9 @@ def main():
     def step_e2e():
         nb = sc.reupload()
         if world == 1:
-            rgb, st = sc.render(spp_begin=s0, spp_end=s1)
+            rgb, st = sc.render(spp_begin=s0, spp_end=s1, **wopts)
             return st, nb, rgb.nbytes
-        ptr, npx, st = sc.render_partial(spp_begin=s0, spp_end=s1)
+        ptr, npx, st = sc.render_partial(spp_begin=s0, spp_end=s1, **wopts)
         film = D.film_tensor(ptr, npx, dev)
         D.reduce_film(film, dst=0)
         d2h = 0
@@ -274,9 +278,10 @@ def main():
                 pass
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            mr, ms, dt, _ = oracle_rate(hs, cores, 0, 1)
+            ncpu = max(1, min(cfg["spp"], 4))     # about 20-30 s of CPU work on a 16-core host
+            mr, ms, dt, _ = oracle_rate(hs, cores, 0, ncpu)
             line["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                                    "sample": "sample number 0 of every pixel (1/%d of the step), %d threads, %.1f s; C++ restatement of pbrt-r3's CPU path" % (cfg["spp"], cores, dt),
+                                    "sample": "sample numbers 0..%d of every pixel (%d/%d of the step), %d threads, %.1f s wall; C++ restatement of pbrt-r3's CPU path" % (ncpu - 1, ncpu, cfg["spp"], cores, dt),
                                     "msamples_per_s": ms}
         print(json.dumps(line))
     if world > 1:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PT_ABI_VERSION 1
+#define PT_ABI_VERSION 2
 
 /* ---- plugin names carried as enums (string names are resolved by the host) ---- */
 enum pt_material_type {       /* reference src/materials/create_material.rs:20-72 */
@@ -202,6 +202,10 @@ typedef struct pt_render_opts {
   int32_t spp_end;
   int32_t wave_paths;         /* path slots per wave (0 = default) */
   int32_t collect_counters;   /* 1: count nodes/triangles visited per ray class (slower) */
+  int32_t wave_segments;      /* waves in flight: the bounce loop is software-pipelined over this many waves, each in its own
+                                 segment of the path state, so that the thin late bounces of one wave share their kernel
+                                 launches with the early bounces of the next (0 = default, 1 = one wave at a time, max 8).
+                                 Results do not depend on it: the film is gathered wave by wave in order. */
 } pt_render_opts;
 
 typedef struct pt_stats {

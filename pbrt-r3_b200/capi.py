@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PBRT_R3_B200_LIB") or os.path.join(HERE, "libpbrt_r3_b200.so")  # env override: kernel A/B experiments
 DATA_DIR = os.path.join(HERE, "data")
 
-PT_ABI_VERSION = 1
+PT_ABI_VERSION = 2
 PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MIRROR = -1, 0, 1, 2, 3, 4
 PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT = 0, 1, 2
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
@@ -74,7 +74,7 @@ class pt_scene_desc(C.Structure):
 
 class pt_render_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("shard_index", C.c_int32), ("shard_count", C.c_int32), ("tile_size", C.c_int32),
-                ("spp_begin", C.c_int32), ("spp_end", C.c_int32), ("wave_paths", C.c_int32), ("collect_counters", C.c_int32)]
+                ("spp_begin", C.c_int32), ("spp_end", C.c_int32), ("wave_paths", C.c_int32), ("collect_counters", C.c_int32), ("wave_segments", C.c_int32)]
 
 
 class pt_stats(C.Structure):

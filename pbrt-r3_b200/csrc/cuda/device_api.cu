@@ -100,7 +100,9 @@ struct pt_scene {
   std::unique_ptr<DevBufs> wave_bufs;
   WaveState W;
   Queues Q;
-  int* slot_of = nullptr;
+  int* slot_of = nullptr;                  // pixel -> slot maps of the waves in flight (slot_segs x sample-bounds pixels)
+  std::unique_ptr<DevBufs> slot_bufs;
+  uint32_t slot_segs = 0;
   unsigned long long* counters = nullptr;  // [0] nodes [1] tris [2] vertices
   int* overflow = nullptr;
   uint32_t* fetch = nullptr;               // ray fetch counter of the stage entry points
@@ -431,10 +433,6 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(s->bufs.alloc(std::max(s->film_pixels, 1u), &s->film));
   CK(s->bufs.alloc((size_t)std::max(s->film_pixels, 1u) * 3, &s->rgb_dev));
   CK(cudaMemset(s->film, 0, (size_t)std::max(s->film_pixels, 1u) * sizeof(f4)));
-  const int* sb = D->film.sample_bounds;
-  size_t sbn = (size_t)std::max(sb[2] - sb[0], 1) * std::max(sb[3] - sb[1], 1);
-  CK(s->bufs.alloc(sbn, &s->slot_of));
-  CK(cudaMemset(s->slot_of, 0xff, sbn * sizeof(int)));
   CK(s->bufs.alloc(4, &s->counters));
   CK(s->bufs.alloc(1, &s->overflow));
   CK(s->bufs.alloc(1, &s->fetch));
@@ -443,8 +441,24 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   return 0;
 }
 
-int ensure_wave(pt_scene* s, uint32_t cap) {
-  if (s->wave_bufs && s->wave_cap >= cap) return 0;
+// Path state for `nseg` waves in flight of up to `seg_cap` paths each (one wave: nseg = 1).  Buffers only grow.
+int ensure_wave(pt_scene* s, uint32_t seg_cap, uint32_t nseg = 1) {
+  seg_cap = std::max(seg_cap, 1u);
+  nseg = std::min(std::max(nseg, 1u), (uint32_t)PT_MAX_SEGMENTS);
+  const uint64_t need = (uint64_t)seg_cap * nseg;
+  if (need > 0x7fffffffull) { pt_set_error("wave state too large"); return 1; }
+  const int* sb = s->h.film.sample_bounds;
+  const size_t sbn = (size_t)std::max(sb[2] - sb[0], 1) * std::max(sb[3] - sb[1], 1);
+  if (!s->slot_bufs || s->slot_segs < nseg) {  // one pixel -> slot map per wave in flight
+    s->slot_bufs.reset(new DevBufs());
+    CK(s->slot_bufs->alloc(sbn * nseg, &s->slot_of));
+    CK(cudaMemset(s->slot_of, 0xff, sbn * nseg * sizeof(int)));
+    s->slot_segs = nseg;
+  }
+  s->W.seg_cap = seg_cap;
+  s->W.nseg = nseg;
+  if (s->wave_bufs && s->wave_cap >= need) return 0;
+  const uint32_t cap = (uint32_t)need;
   s->wave_bufs.reset(new DevBufs());
   DevBufs& B = *s->wave_bufs;
   WaveState& W = s->W;
@@ -459,8 +473,8 @@ int ensure_wave(pt_scene* s, uint32_t cap) {
   CK(B.alloc(cap, &W.sh_o)); CK(B.alloc(cap, &W.sh_d)); CK(B.alloc((size_t)cap * NC, &W.pendA));
   CK(B.alloc(cap, &W.mis_o)); CK(B.alloc(cap, &W.mis_d)); CK(B.alloc((size_t)cap * NC, &W.pendB)); CK(B.alloc(cap, &W.mis_light));
   Queues& Q = s->Q;
-  CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(16, &Q.counts));
-  CK(cudaMemset(Q.counts, 0, 16 * sizeof(uint32_t)));
+  CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(32, &Q.counts));
+  CK(cudaMemset(Q.counts, 0, 32 * sizeof(uint32_t)));
   CK(B.alloc((size_t)cap * CL_COUNT, &Q.bins));
   s->wave_cap = cap;
   return 0;
@@ -587,6 +601,27 @@ int build_pixlist(pt_scene* s, int shard_index, int shard_count, int tile) {
   return 0;
 }
 
+// One wave = `ns` consecutive sample numbers of a contiguous chunk of the pixel list.
+struct WaveJob {
+  uint32_t c0, npix;
+  int s0;
+  uint32_t ns;
+  int fx0, fy0, fx1, fy1;  // film footprint of the pixel chunk
+};
+struct WaveSeg {
+  enum { IDLE = 0, ACTIVE = 1, DRAINING = 2, TRACED = 3 };
+  int state = IDLE;
+  int job = -1;
+  int start_iter = 0;
+  uint32_t map_c0 = 0xffffffffu, map_npix = 0;  // pixel chunk currently in this segment's slot_of map
+};
+
+// Integrator::render for the index-based samplers (halton, sobol): the bounce loop of li(), software-pipelined over
+// `wave_segments` waves.  A wave's late bounces carry few rays (a 3 M-path wave of the 1 M-triangle scene ends with five
+// iterations of < 2 % of its rays) and such launches are bound by the latency of single rays, not by throughput; so the
+// next waves start in their own segments of the path state while the previous ones thin out, and every launch of
+// k_trace / k_shade works on the union of their queues.  Paths never interact, and the film gathers the finished waves
+// strictly in wave order, so the image does not depend on the pipelining.
 template <int NC>
 int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   const int spp = s->h.sampler.spp;
@@ -595,6 +630,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   int shard_i = o ? o->shard_index : 0, shard_n = (o && o->shard_count > 0) ? o->shard_count : 1;
   int tile = (o && o->tile_size > 0) ? o->tile_size : 16;
   bool count = o && o->collect_counters;
+  const bool timed = st != nullptr;
   if (build_pixlist(s, shard_i, shard_n, tile)) return 1;
   uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? (4u << 20) : (1u << 19));
   uint32_t npix_total = s->pix_n;
@@ -604,46 +640,170 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   if ((uint64_t)npix_total * (uint64_t)ns_total <= cap) { pix_chunk = npix_total; ns_wave = (uint32_t)ns_total; }
   else if (npix_total <= cap) { pix_chunk = npix_total; ns_wave = std::max(1u, cap / npix_total); }
   else { pix_chunk = cap; ns_wave = 1; }
-  if (ensure_wave(s, (uint32_t)std::min<uint64_t>((uint64_t)pix_chunk * ns_wave, cap))) return 1;
   const int* sb = s->h.film.sample_bounds;
   const int* cb = s->h.film.cropped_pixel_bounds;
   const int sbw = sb[2] - sb[0];
+  const size_t sbn = (size_t)std::max(sb[2] - sb[0], 1) * std::max(sb[3] - sb[1], 1);
   const float rx = s->h.film.filter_radius[0], ry = s->h.film.filter_radius[1];
-  WaveTotals T;
+  std::vector<WaveJob> jobs;
   for (uint32_t c0 = 0; c0 < npix_total; c0 += pix_chunk) {
-    uint32_t npix = std::min(pix_chunk, npix_total - c0);
-    PT_LAUNCH(grid_for(s, npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, c0, npix, sbw, s->slot_of, 0);
-    CK(cudaGetLastError());
-    T.launches++;
-    // film footprint of this pixel chunk
+    WaveJob J;
+    J.c0 = c0;
+    J.npix = std::min(pix_chunk, npix_total - c0);
     int minx = 1 << 30, miny = 1 << 30, maxx = -(1 << 30), maxy = -(1 << 30);
-    for (uint32_t i = c0; i < c0 + npix; i++) {
+    for (uint32_t i = c0; i < c0 + J.npix; i++) {
       int pk = s->pix_host[i], x = (pk & 0xffff) + sb[0], y = (pk >> 16) + sb[1];
       minx = std::min(minx, x); maxx = std::max(maxx, x); miny = std::min(miny, y); maxy = std::max(maxy, y);
     }
-    int fx0 = std::max((int)floorf((float)minx - rx), cb[0]), fy0 = std::max((int)floorf((float)miny - ry), cb[1]);
-    int fx1 = std::min((int)ceilf((float)(maxx + 1) + rx), cb[2]), fy1 = std::min((int)ceilf((float)(maxy + 1) + ry), cb[3]);
+    J.fx0 = std::max((int)floorf((float)minx - rx), cb[0]); J.fy0 = std::max((int)floorf((float)miny - ry), cb[1]);
+    J.fx1 = std::min((int)ceilf((float)(maxx + 1) + rx), cb[2]); J.fy1 = std::min((int)ceilf((float)(maxy + 1) + ry), cb[3]);
     for (int s0 = s_begin; s0 < s_end; s0 += (int)ns_wave) {
-      uint32_t ns = (uint32_t)std::min<int>((int)ns_wave, s_end - s0);
-      uint32_t n = npix * ns;
-      PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->h, s->W, s->Q, s->pixlist, c0, npix, s0, ns);
+      J.s0 = s0;
+      J.ns = (uint32_t)std::min<int>((int)ns_wave, s_end - s0);
+      jobs.push_back(J);
+    }
+  }
+  const uint32_t seg_cap = (uint32_t)std::min<uint64_t>((uint64_t)pix_chunk * ns_wave, cap);
+  uint32_t nseg = (o && o->wave_segments > 0) ? (uint32_t)o->wave_segments : 6u;  // measured: profiles/r1_wave_pipelining.md
+  nseg = (uint32_t)std::min<size_t>(std::min(nseg, (uint32_t)PT_MAX_SEGMENTS), jobs.size());
+  if (ensure_wave(s, seg_cap, nseg)) return 1;
+  Queues Q = s->Q;
+  WaveState& W = s->W;
+  const bool inst = s->h.has_instances != 0;
+  WaveTotals T;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+  if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); }
+  std::vector<WaveSeg> segs(nseg);
+  std::vector<int> seg_of_job(jobs.size(), -1);
+  size_t next_job = 0, next_film = 0;
+  uint32_t n_ext = 0, n_sh = 0, n_mis = 0;
+  int iter = 0, last_start = -(1 << 30), wave_iters = s->h.integrator.max_depth + 3;
+  uint32_t counts[32];
+  int rc = 0;
+  // k_finish + k_film for the waves whose rays are all traced, in wave order
+  auto gather_ready = [&]() -> int {
+    while (next_film < jobs.size() && seg_of_job[next_film] >= 0 && segs[seg_of_job[next_film]].state == WaveSeg::TRACED) {
+      const int k = seg_of_job[next_film];
+      const WaveJob& J = jobs[next_film];
+      const uint32_t n = J.npix * J.ns, base = (uint32_t)k * seg_cap;
+      PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->h, W, base, n);
       CK(cudaGetLastError());
       T.launches++;
-      if (st) st->camera_rays += n;
-      if (run_bounces<NC>(s, n, count, st != nullptr, &T)) return 1;
-      PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->h, s->W, n);
-      CK(cudaGetLastError());
-      T.launches++;
-      if (fx1 > fx0 && fy1 > fy0) {
-        PT_LAUNCH(grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, s->stream, k_film<NC>)(s->h, s->W, s->slot_of, npix, ns, fx0, fy0, fx1, fy1, s->film);
+      if (J.fx1 > J.fx0 && J.fy1 > J.fy0) {
+        PT_LAUNCH(grid_for(s, (size_t)(J.fx1 - J.fx0) * (J.fy1 - J.fy0), 128, 8), 128, s->stream, k_film<NC>)(s->h, W, s->slot_of + (size_t)k * sbn, base, J.npix, J.ns, J.fx0,
+                                                                                                             J.fy0, J.fx1, J.fy1, s->film);
         CK(cudaGetLastError());
         T.launches++;
       }
+      wave_iters = std::max(iter - segs[k].start_iter, 1);
+      segs[k].state = WaveSeg::IDLE;
+      segs[k].job = -1;
+      next_film++;
     }
-    PT_LAUNCH(grid_for(s, npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, c0, npix, sbw, s->slot_of, 1);
-    CK(cudaGetLastError());
+    return 0;
+  };
+  for (;;) {
+    if (++iter > 10000000) { pt_set_error("bounce loop did not terminate"); rc = 1; break; }
+    // (1) start the next wave in an idle segment; the starts are spread over a wave's life (wave_iters iterations)
+    bool any_busy = false;
+    for (auto& g : segs) any_busy = any_busy || g.state != WaveSeg::IDLE;
+    const int stagger = std::max(1, wave_iters / (int)nseg);
+    if (next_job < jobs.size() && (!any_busy || iter - last_start >= stagger)) {
+      for (uint32_t k = 0; k < nseg; k++) {
+        WaveSeg& g = segs[k];
+        if (g.state != WaveSeg::IDLE) continue;
+        const WaveJob& J = jobs[next_job];
+        const uint32_t n = J.npix * J.ns, base = k * seg_cap;
+        int* map = s->slot_of + (size_t)k * sbn;
+        if (g.map_c0 != J.c0 || g.map_npix != J.npix) {
+          if (g.map_npix > 0) {
+            PT_LAUNCH(grid_for(s, g.map_npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, g.map_c0, g.map_npix, sbw, map, 1);
+            T.launches++;
+          }
+          PT_LAUNCH(grid_for(s, J.npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, J.c0, J.npix, sbw, map, 0);
+          if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_set_slots launch failed"); break; }
+          T.launches++;
+          g.map_c0 = J.c0; g.map_npix = J.npix;
+        }
+        PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->h, W, Q, s->pixlist, J.c0, J.npix, J.s0, J.ns, base, n_ext);
+        if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_raygen launch failed"); break; }
+        T.launches++;
+        if (st) st->camera_rays += n;
+        n_ext += n;
+        g.state = WaveSeg::ACTIVE;
+        g.job = (int)next_job;
+        g.start_iter = iter;
+        seg_of_job[next_job] = (int)k;
+        next_job++;
+        last_start = iter;
+        break;
+      }
+      if (rc) break;
+    }
+    const uint32_t total = n_ext + n_mis + n_sh;
+    if (total == 0) {
+      // nothing left to trace: the draining waves are complete
+      for (auto& g : segs) if (g.state == WaveSeg::DRAINING) g.state = WaveSeg::TRACED;
+      if ((rc = gather_ready())) break;
+      bool busy = false;
+      for (auto& g : segs) busy = busy || g.state != WaveSeg::IDLE;
+      if (!busy && next_job >= jobs.size()) break;
+      continue;
+    }
+    // (2) one bounce of every wave in flight: trace the three queues, shade the continuation hits
+    int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
+    if ((rc = (cudaMemsetAsync(Q.counts + 8, 0, 8 * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }  // shading-class bin sizes
+    if (timed) cudaEventRecord(e0, s->stream);
+#define LAUNCH_TRACE(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_trace<NC, I, C>)(s->h, W, Q, n_ext, n_mis, n_sh, s->counters, s->overflow)
+    if (inst) { if (count) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
+    else { if (count) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
+#undef LAUNCH_TRACE
+    if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_trace launch failed"); break; }
+    if (timed) cudaEventRecord(e1, s->stream);
+    T.regular += n_ext + n_mis;
+    T.shadow += n_sh;
     T.launches++;
+    T.trace_launches++;
+    T.trace_rays += total;
+    // the shadow / MIS rays of the draining waves are resolved now
+    for (auto& sg : segs) if (sg.state == WaveSeg::DRAINING) sg.state = WaveSeg::TRACED;
+    if ((rc = gather_ready())) break;
+    if (timed) cudaEventRecord(e2, s->stream);
+    cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream);  // queue counters + the trace fetch counter
+    if ((rc = (cudaMemsetAsync(Q.counts + 16, 0, PT_MAX_SEGMENTS * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }
+    if (n_ext > 0) {
+      int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
+      unsigned long long* vc = count ? s->counters + 2 : nullptr;
+      for (int c = 0; c < CL_COUNT; c++)
+        if (s->class_mask & (1u << c)) { launch_shade(NC, c, gs, s->stream, s->h, W, Q, vc); T.launches++; }
+      if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_shade launch failed"); break; }
+    }
+    if (timed) cudaEventRecord(e3, s->stream);
+    if ((rc = (cudaMemcpyAsync(counts, Q.counts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess))) { pt_set_error("cudaMemcpyAsync failed"); break; }
+    if ((rc = (cudaStreamSynchronize(s->stream) != cudaSuccess))) { pt_set_error(std::string("bounce loop: ") + cudaGetErrorString(cudaGetLastError())); break; }
+    if (timed) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, e0, e1);
+      cudaEventElapsedTime(&b, e2, e3);
+      T.trace_ms += a;
+      T.shade_ms += b;
+    }
+    for (uint32_t k = 0; k < nseg; k++)
+      if (segs[k].state == WaveSeg::ACTIVE && (nseg > 1 ? counts[16 + k] : counts[1]) == 0) segs[k].state = WaveSeg::DRAINING;
+    n_ext = counts[1];
+    n_sh = counts[2];
+    n_mis = counts[3];
+    std::swap(Q.ext, Q.ext_next);
   }
+  if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); }
+  if (rc) return 1;
+  // leave the pixel -> slot maps empty for the next render
+  for (uint32_t k = 0; k < nseg; k++)
+    if (segs[k].map_npix > 0) {
+      PT_LAUNCH(grid_for(s, segs[k].map_npix, 256, 8), 256, s->stream, k_set_slots)(s->pixlist, segs[k].map_c0, segs[k].map_npix, sbw, s->slot_of + (size_t)k * sbn, 1);
+      CK(cudaGetLastError());
+      T.launches++;
+    }
   return finish_render(s, st, T, count);
 }
 
@@ -715,11 +875,11 @@ int render_waves_random(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
         if (run_bounces<NC>(s, active, count, st != nullptr, &T)) return 1;
       }
     }
-    PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->h, s->W, n);
+    PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->h, s->W, 0u, n);
     CK(cudaGetLastError());
     T.launches++;
     if (fx1 > fx0 && fy1 > fy0) {
-      PT_LAUNCH(grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, s->stream, k_film<NC>)(s->h, s->W, s->slot_of, npix, (uint32_t)spp, fx0, fy0, fx1, fy1, s->film);
+      PT_LAUNCH(grid_for(s, (size_t)(fx1 - fx0) * (fy1 - fy0), 128, 8), 128, s->stream, k_film<NC>)(s->h, s->W, s->slot_of, 0u, npix, (uint32_t)spp, fx0, fy0, fx1, fy1, s->film);
       CK(cudaGetLastError());
       T.launches++;
     }
@@ -959,8 +1119,8 @@ static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_
     WaveTotals T;
     int rc = s->h.n_channels == 3 ? run_bounces<3>(s, n, false, false, &T) : run_bounces<PT_NCS>(s, n, false, false, &T);
     if (rc) return rc;
-    if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<3>)(s->h, s->W, n);
-    else PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<PT_NCS>)(s->h, s->W, n);
+    if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<3>)(s->h, s->W, 0u, n);
+    else PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<PT_NCS>)(s->h, s->W, 0u, n);
     CK(cudaGetLastError());
   }
   CK(cudaStreamSynchronize(s->stream));

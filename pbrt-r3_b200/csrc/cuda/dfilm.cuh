@@ -15,9 +15,10 @@ PT_HD int film_fidx(float d, float radius, float l) {  // filter-table index alo
 }
 
 // One film pixel (fx, fy) of the cropped pixel bounds, for a wave holding `ns` samples of each pixel listed in `slot_of`
-// (slot_of[(y - sb.y0) * sbw + (x - sb.x0)] = slot or -1); path id = s * npix + slot.
+// (slot_of[(y - sb.y0) * sbw + (x - sb.x0)] = slot or -1); path id = base + s * npix + slot (base = first path slot of the
+// wave's segment of the state).
 template <int NC>
-PT_HD void film_gather_body(const DScene& S, const WaveState& W, const int* slot_of, uint32_t npix, uint32_t ns, int fx, int fy, f4* film) {
+PT_HD void film_gather_body(const DScene& S, const WaveState& W, const int* slot_of, uint32_t base, uint32_t npix, uint32_t ns, int fx, int fy, f4* film) {
   const pt_film& F = S.film;
   const float rx = F.filter_radius[0], ry = F.filter_radius[1];
   const float lx = (1.0f / rx) * 15.0f, ly = (1.0f / ry) * 15.0f;
@@ -39,7 +40,7 @@ PT_HD void film_gather_body(const DScene& S, const WaveState& W, const int* slot
       int slot = slot_of[(qy - sb[1]) * sbw + (qx - sb[0])];
       if (slot < 0) continue;
       for (uint32_t s = 0; s < ns; s++) {
-        uint32_t i = s * npix + (uint32_t)slot;
+        uint32_t i = base + s * npix + (uint32_t)slot;
         f2 pf = W.p_film[i];
         int ix = film_fidx(fabsf((float)fx + 0.5f - pf.x), rx, lx);
         int iy = film_fidx(fabsf((float)fy + 0.5f - pf.y), ry, ly);

@@ -17,6 +17,8 @@ namespace ptd {
 
 struct WaveState {            // all arrays have `cap` path slots; spectra are channel-major: [c * cap + i]
   uint32_t cap;
+  uint32_t seg_cap;           // waves in flight own disjoint segments of the slots: segment = path id / seg_cap (render_waves)
+  uint32_t nseg;
   f4* ray_o;                  // o.xyz, tmax   (continuation / camera ray; tmax shrinks to the hit distance)
   f4* ray_d;                  // d.xyz, time
   f4* hit;                    // b0, b1, b2, bits(tri) (tri = -1: miss)
@@ -42,8 +44,10 @@ struct Queues {
   uint32_t* shadow;
   uint32_t* mis;
   uint32_t* bins;      // traced continuation rays binned by shading class: bins[cls * cap + k]
-  uint32_t* counts;    // [0] ext, [1] ext_next, [2] shadow, [3] mis, [4] trace fetch counter, [8 + cls] bin sizes
+  uint32_t* counts;    // [0] ext, [1] ext_next, [2] shadow, [3] mis, [4] trace fetch counter, [8 + cls] bin sizes,
+                       // [16 + segment] continuation rays pushed by the last shade stage for each wave in flight
 };
+#define PT_MAX_SEGMENTS 8
 
 // Shading classes: one specialised shade kernel per material plugin ("sort by material"); class 0
 // takes the paths that need no BSDF: misses, paths at max depth, surfaces without a material.
@@ -234,6 +238,21 @@ PT_D uint32_t queue_push(uint32_t* counter) {  // warp-aggregated append (ballot
 #else
 inline uint32_t queue_push(uint32_t* counter) { return (*counter)++; }
 #endif
+// the path goes on: append it to the next extend queue and count it for its wave (the host retires a wave when the
+// shade stage pushed no continuation ray for its segment)
+PT_HD void push_next(const WaveState& W, Queues& Q, uint32_t i) {
+  Q.ext_next[queue_push(&Q.counts[1])] = i;
+  if (W.nseg > 1) {
+    const uint32_t seg = i / W.seg_cap;
+#if defined(__CUDA_ARCH__)
+    unsigned m = __activemask();
+    unsigned peers = __match_any_sync(m, seg);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&Q.counts[16 + seg], (uint32_t)__popc(peers));
+#else
+    Q.counts[16 + seg]++;
+#endif
+  }
+}
 
 // camera-ray generation for path slot i of the current wave: pixel (px,py) absolute, sample number n
 // Sampler "random": tile_slot / tile_seq select the PCG32 stream (packed into st.index: slot << 32 | sequence number = tile
@@ -306,7 +325,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
     f3 o = offset_origin(si.p, si.perr, si.n, rd);
     W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
     st_store<NC>(W.L, cap, i, L);
-    Q.ext_next[queue_push(&Q.counts[1])] = i;
+    push_next(W, Q, i);
     return;
   }
   if (vertex_counter) {
@@ -419,7 +438,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   W.dim[i] = st.dim;
   W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
   W.ray_d[i] = mk4(wi.x, wi.y, wi.z, rtime);
-  Q.ext_next[queue_push(&Q.counts[1])] = i;
+  push_next(W, Q, i);
 }
 
 // MIS ray resolution: the BSDF-sampled ray contributes only if it hits the sampled light (pointer equality in the

@@ -243,13 +243,14 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(co
 
 template <int NC>
 __global__ void __launch_bounds__(PT_SHADE_BLOCK) k_raygen(const __grid_constant__ DScene S, WaveState W, Queues Q, const int* __restrict__ pixlist,
-                                                           uint32_t c0, uint32_t npix, int s0, uint32_t ns) {
+                                                           uint32_t c0, uint32_t npix, int s0, uint32_t ns, uint32_t base, uint32_t q0) {
+  // path slots base .. base + npix * ns (the wave's segment of the state), appended to the extend queue at q0
   const uint32_t total = npix * ns;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     uint32_t slot = i % npix, s = i / npix;
     int pk = pixlist[c0 + slot];
     int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
-    raygen_body<NC>(S, W, Q, i, px, py, s0 + (int)s);
+    raygen_body<NC>(S, W, Q, base + i, px, py, s0 + (int)s, -1, 0u, q0 + i);
   }
 }
 // Sampler "random", wave w of a tile group: one path per tile = pixel number w / spp of the tile (scan order, as
@@ -276,8 +277,8 @@ __global__ void k_raygen_list(const __grid_constant__ DScene S, WaveState W, Que
 }
 
 template <int NC>
-__global__ void k_finish(const __grid_constant__ DScene S, WaveState W, uint32_t n) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) finish_body<NC>(S, W, i);
+__global__ void k_finish(const __grid_constant__ DScene S, WaveState W, uint32_t base, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) finish_body<NC>(S, W, base + i);
 }
 
 __global__ void k_set_slots(const int* __restrict__ pixlist, uint32_t c0, uint32_t npix, int sbw, int* slot_of, int clear) {
@@ -288,11 +289,11 @@ __global__ void k_set_slots(const int* __restrict__ pixlist, uint32_t c0, uint32
 }
 
 template <int NC>
-__global__ void k_film(const __grid_constant__ DScene S, WaveState W, const int* __restrict__ slot_of, uint32_t npix, uint32_t ns, int x0, int y0, int x1, int y1,
-                       f4* film) {
+__global__ void k_film(const __grid_constant__ DScene S, WaveState W, const int* __restrict__ slot_of, uint32_t base, uint32_t npix, uint32_t ns, int x0, int y0,
+                       int x1, int y1, f4* film) {
   int w = x1 - x0, h = y1 - y0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x)
-    film_gather_body<NC>(S, W, slot_of, npix, ns, x0 + i % w, y0 + i / w, film);
+    film_gather_body<NC>(S, W, slot_of, base, npix, ns, x0 + i % w, y0 + i / w, film);
 }
 
 __global__ void k_film_resolve(const __grid_constant__ DScene S, const f4* film, float* rgb, uint32_t n) {

@@ -191,6 +191,22 @@ def test_sharding_properties(P, pair):
     assert rel_rmse(rgb, full) < 1e-5
 
 
+def test_wave_pipelining_is_invisible(P, pair):
+    """render_waves runs up to 8 waves at once in segments of the path state (pt_render_opts.wave_segments): paths do not
+    interact and the film gathers the waves in order, so the image is bit-identical and the ray / node / triangle
+    counters are equal for any number of waves in flight (mixed materials: paths of very different lengths)."""
+    hs, sc, orc = pair("mixed_pipe", P.scenes.cornell_box(res=96, spp=8, materials="mixed", extra_lights=True, maxdepth=8))
+    base, st1 = sc.render(wave_paths=20000, wave_segments=1, collect_counters=1)
+    for k in (2, 4, 8):
+        rgb, st = sc.render(wave_paths=20000, wave_segments=k, collect_counters=1)
+        assert np.array_equal(rgb, base), k
+        for key in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[key] == st1[key], (k, key)
+        assert st["extend_launches"] < st1["extend_launches"]
+    ref, _ = orc.render()
+    assert rel_rmse(base, ref) <= RMSE_TOL
+
+
 def test_full_size_config2_properties(P):
     """configs[1] geometry at full size (1M triangles): BVH build on the host, primary hits vs the oracle on a sample of
     rays, closest-hit/any-hit consistency and determinism on the whole primary wave."""

@@ -58,6 +58,14 @@ def test_hostcheck_cornell_image_and_streams(HC):
     assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5
     for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
         assert st[k] == so[k], k
+    # waves in flight (software-pipelined bounce loop): same image bit for bit, same counters, fewer launches
+    one, st1 = sc.render(collect_counters=1, wave_paths=1000, wave_segments=1)
+    for k in (2, 3, 8):
+        many, stk = sc.render(collect_counters=1, wave_paths=1000, wave_segments=k)
+        assert np.array_equal(one, many), k
+        for key in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert stk[key] == st1[key], (k, key)
+        assert stk["extend_launches"] < st1["extend_launches"]
     # shards add up
     a, _ = sc.render(wave_paths=3000)
     import ctypes as C
