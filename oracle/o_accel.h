@@ -303,9 +303,49 @@ struct Hit {
   Ray local_ray;      // the ray in the triangle's space (object space for instances)
 };
 
+// LinearBVHNode (accel/lbvh.rs:14-19)
+struct LNode {
+  Bounds3 bounds;
+  size_t offset = 0;        // leaf: first primitive; interior: second child
+  size_t n_primitives = 0;  // 0 -> interior node
+  uint8_t axis = 0;
+};
+// flatten_bvh_tree (accel/lbvh.rs:55-73)
+inline size_t flatten_lbvh(std::vector<LNode>& nodes, const BuildNode* node) {
+  LNode ln;
+  ln.bounds = node->bounds;
+  ln.n_primitives = node->n;
+  ln.axis = (uint8_t)node->split_axis;
+  size_t offset = nodes.size();
+  if (node->n > 0) {
+    ln.offset = node->first;
+    nodes.push_back(ln);
+  } else {
+    ln.n_primitives = 0;
+    nodes.push_back(ln);
+    flatten_lbvh(nodes, node->c[0].get());
+    size_t second = flatten_lbvh(nodes, node->c[1].get());
+    nodes[offset].offset = second;
+  }
+  return offset;
+}
+// intersect_box_array_i (core/geometry/intersect.rs:46-65)
+inline bool box_array_i(const Bounds3& b, const Float* org, const Float* idir, const int* sign, Float* t0, Float* t1) {
+  for (int i = 0; i < 3; i++) {
+    Float lo = sign[i] ? b.mx[i] : b.mn[i], hi = sign[i] ? b.mn[i] : b.mx[i];
+    *t0 = rmax(*t0, (lo - org[i]) * idir[i]);
+    *t1 = rmin(*t1, (hi - org[i]) * idir[i]);
+  }
+  return *t0 <= *t1;
+}
+
 struct Accel {
   std::vector<int32_t> prims;  // ordered primitive list (triangle index >= 0, ~instance < 0)
   std::vector<QNode> nodes;
+  std::vector<LNode> lnodes;   // Accelerator layout "lbvh" (LBVHAccel) instead of the 4-wide nodes
+  bool lbvh = false;
+  bool intersect_lbvh(const SceneGeom& g, const Ray& r, Hit* hit, Counters* cnt) const;
+  bool intersect_p_lbvh(const SceneGeom& g, const Ray& r, Counters* cnt) const;
   Bounds3 bounds;
   bool single = false;  // object with exactly one primitive: no accelerator is built (scene_context.rs:1372-1379)
   size_t max_depth = 0;
@@ -351,8 +391,71 @@ inline bool Accel::prim_intersect_p(const SceneGeom& g, int32_t prim, const Ray&
   return g.objects[(size_t)I.object]->intersect_p(g, ray, cnt);
 }
 
+// LBVHAccel::intersect (accel/lbvh.rs:128-186)
+inline bool Accel::intersect_lbvh(const SceneGeom& g, const Ray& r, Hit* hit, Counters* cnt) const {
+  if (lnodes.empty()) return false;
+  bool found = false;
+  struct E { size_t node; Float t0, t1; };
+  std::vector<E> stack;
+  stack.reserve(64);
+  Float t_max = r.t_max;
+  Float org[3] = {r.o.x, r.o.y, r.o.z};
+  Float idir[3] = {1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
+  int neg[3] = {std::signbit(idir[0]) ? 1 : 0, std::signbit(idir[1]) ? 1 : 0, std::signbit(idir[2]) ? 1 : 0};
+  stack.push_back(E{0, 0.0f, t_max});
+  while (!stack.empty()) {
+    E e = stack.back();
+    stack.pop_back();
+    Float t0 = e.t0, t1 = rmin(t_max, e.t1);
+    if (t1 < t0) continue;
+    const LNode& node = lnodes[e.node];
+    if (cnt) cnt->nodes++;
+    if (!box_array_i(node.bounds, org, idir, neg, &t0, &t1)) continue;
+    if (node.n_primitives > 0) {
+      for (size_t i = node.offset; i < node.offset + node.n_primitives; i++)
+        if (prim_intersect(g, prims[i], r, hit, cnt)) { t_max = r.t_max; found = true; }
+    } else {
+      size_t child[2] = {e.node + 1, node.offset};
+      int idx[2] = {neg[node.axis], 1 - neg[node.axis]};
+      stack.push_back(E{child[idx[1]], t0, t1});
+      stack.push_back(E{child[idx[0]], t0, t1});
+    }
+  }
+  return found;
+}
+// LBVHAccel::intersect_p (accel/lbvh.rs:188-241): the popped range is not clipped against t_max
+inline bool Accel::intersect_p_lbvh(const SceneGeom& g, const Ray& r, Counters* cnt) const {
+  if (lnodes.empty()) return false;
+  struct E { size_t node; Float t0, t1; };
+  std::vector<E> stack;
+  stack.reserve(64);
+  Float org[3] = {r.o.x, r.o.y, r.o.z};
+  Float idir[3] = {1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
+  int neg[3] = {std::signbit(idir[0]) ? 1 : 0, std::signbit(idir[1]) ? 1 : 0, std::signbit(idir[2]) ? 1 : 0};
+  stack.push_back(E{0, 0.0f, r.t_max});
+  while (!stack.empty()) {
+    E e = stack.back();
+    stack.pop_back();
+    Float t0 = e.t0, t1 = e.t1;
+    const LNode& node = lnodes[e.node];
+    if (cnt) cnt->nodes++;
+    if (!box_array_i(node.bounds, org, idir, neg, &t0, &t1)) continue;
+    if (node.n_primitives > 0) {
+      for (size_t i = node.offset; i < node.offset + node.n_primitives; i++)
+        if (prim_intersect_p(g, prims[i], r, cnt)) return true;
+    } else {
+      size_t child[2] = {e.node + 1, node.offset};
+      int idx[2] = {neg[node.axis], 1 - neg[node.axis]};
+      stack.push_back(E{child[idx[1]], t0, t1});
+      stack.push_back(E{child[idx[0]], t0, t1});
+    }
+  }
+  return false;
+}
+
 inline bool Accel::intersect(const SceneGeom& g, const Ray& r, Hit* hit, Counters* cnt) const {
   if (single) return prim_intersect(g, prims[0], r, hit, cnt);
+  if (lbvh) return intersect_lbvh(g, r, hit, cnt);
   Float tmin, tmax;
   if (!box_range(bounds, r, &tmin, &tmax)) return false;
   bool found = false;
@@ -398,6 +501,7 @@ inline bool Accel::intersect(const SceneGeom& g, const Ray& r, Hit* hit, Counter
 }
 inline bool Accel::intersect_p(const SceneGeom& g, const Ray& r, Counters* cnt) const {
   if (single) return prim_intersect_p(g, prims[0], r, cnt);
+  if (lbvh) return intersect_p_lbvh(g, r, cnt);
   Float tmin, tmax;
   if (!box_range(bounds, r, &tmin, &tmax)) return false;
   std::vector<size_t> stack;
@@ -499,7 +603,8 @@ inline std::unique_ptr<Accel> build_accel(const SceneGeom& g, const int32_t* pri
   auto root = B.build(info.data(), n);
   A->prims.resize(n);
   for (size_t i = 0; i < n; i++) A->prims[i] = prims[B.ordered[i]];
-  flatten_qbvh(A->nodes, root.get());
+  if (cfg.type == PT_ACCEL_LBVH) { A->lbvh = true; flatten_lbvh(A->lnodes, root.get()); }
+  else flatten_qbvh(A->nodes, root.get());
   A->bounds = root->bounds;
   A->max_depth = build_depth(root.get());
   return A;

@@ -205,19 +205,28 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   }
   // stack depth: the worst-case bound 3*depth+1 is far from typical use; the kernels flag a real overflow instead
   std::vector<pth::GpuNodeH> nodes;
+  std::vector<pth::LNodeH> lnodes;
+  const bool lbvh = D->accel.type == PT_ACCEL_LBVH;
+  H.accel_type = lbvh ? PT_ACCEL_LBVH : PT_ACCEL_QBVH;
   std::vector<f4> recs;
   std::vector<ObjectRec> orecs(D->n_objects);
   for (uint32_t k = 0; k < D->n_objects; k++) {
     ObjectHost& O = s->objects[k];
     ObjectRec& R = orecs[k];
     memset(&R, 0, sizeof(R));
-    R.node_base = (uint32_t)nodes.size();
+    R.node_base = (uint32_t)(lbvh ? lnodes.size() : nodes.size());
     R.rec_base = (uint32_t)(recs.size() / 3);
+    if (lbvh) {
+      const size_t before = lnodes.size();
+      uint32_t depth = pth::flatten_lbvh(O.bvh, &lnodes);
+      if (depth + 2 > (uint32_t)PT_MAX_STACK / 2) { pt_set_error("BVH too deep for the LBVH traversal stack"); return 1; }
+      R.n_nodes = (uint32_t)(lnodes.size() - before);
+    } else
     R.n_nodes = (uint32_t)O.bvh.nodes.size();
     R.n_prims = (uint32_t)O.ordered.size();
     R.single = O.single ? 1 : 0;
     for (int a = 0; a < 3; a++) { R.bmin[a] = O.bounds.mn[a]; R.bmax[a] = O.bounds.mx[a]; }
-    nodes.insert(nodes.end(), O.bvh.nodes.begin(), O.bvh.nodes.end());
+    if (!lbvh) nodes.insert(nodes.end(), O.bvh.nodes.begin(), O.bvh.nodes.end());
     for (int32_t p : O.ordered) {
       if (p >= 0) {
         const float* q = D->tri_p + (size_t)p * 9;
@@ -232,6 +241,8 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
     }
   }
   CK(s->bufs.upload((const QNode*)nodes.data(), nodes.size(), &H.nodes));
+  static_assert(sizeof(pth::LNodeH) == 2 * sizeof(f4), "LNodeH = 2 x f4");
+  CK(s->bufs.upload((const f4*)lnodes.data(), lnodes.size() * 2, &H.lnodes));
   CK(s->bufs.upload(recs.data(), recs.size(), &H.recs));
   CK(s->bufs.upload(orecs.data(), orecs.size(), &H.objects));
   {
@@ -501,9 +512,14 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
     CK(cudaMemsetAsync(Q.counts + 8, 0, 8 * sizeof(uint32_t), s->stream));  // shading-class bin sizes
     if (timed) cudaEventRecord(e0, s->stream);
-#define LAUNCH_TRACE(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_trace<NC, I, C>)(s->h, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
-    if (inst) { if (count) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
-    else { if (count) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
+#define LAUNCH_TRACE(K, I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, K<NC, I, C>)(s->h, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
+    if (s->h.accel_type == PT_ACCEL_LBVH) {
+      if (inst) { if (count) LAUNCH_TRACE(k_trace_lbvh, true, true); else LAUNCH_TRACE(k_trace_lbvh, true, false); }
+      else { if (count) LAUNCH_TRACE(k_trace_lbvh, false, true); else LAUNCH_TRACE(k_trace_lbvh, false, false); }
+    } else {
+      if (inst) { if (count) LAUNCH_TRACE(k_trace, true, true); else LAUNCH_TRACE(k_trace, true, false); }
+      else { if (count) LAUNCH_TRACE(k_trace, false, true); else LAUNCH_TRACE(k_trace, false, false); }
+    }
 #undef LAUNCH_TRACE
     CK(cudaGetLastError());
     if (timed) cudaEventRecord(e1, s->stream);
@@ -558,7 +574,8 @@ int finish_render(pt_scene* s, pt_stats* st, const WaveTotals& T, bool count) {
       st->nodes_visited += c[0];
       st->tris_tested += c[1];
       st->path_vertices += c[2];
-      st->extend_bytes += 128ull * c[0] + 48ull * c[1] + 48ull * T.trace_rays;
+      // algorithmic bytes: one node per visit (128 B 4-wide / 32 B LinearBVHNode), 48 B per triangle test, 48 B ray + hit
+      st->extend_bytes += (s->h.accel_type == PT_ACCEL_LBVH ? 32ull : 128ull) * c[0] + 48ull * c[1] + 48ull * T.trace_rays;
       CK(cudaMemset(s->counters, 0, 4 * sizeof(unsigned long long)));
     }
   }
@@ -754,9 +771,14 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
     if ((rc = (cudaMemsetAsync(Q.counts + 8, 0, 8 * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }  // shading-class bin sizes
     if (timed) cudaEventRecord(e0, s->stream);
-#define LAUNCH_TRACE(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_trace<NC, I, C>)(s->h, W, Q, n_ext, n_mis, n_sh, s->counters, s->overflow)
-    if (inst) { if (count) LAUNCH_TRACE(true, true); else LAUNCH_TRACE(true, false); }
-    else { if (count) LAUNCH_TRACE(false, true); else LAUNCH_TRACE(false, false); }
+#define LAUNCH_TRACE(K, I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, K<NC, I, C>)(s->h, W, Q, n_ext, n_mis, n_sh, s->counters, s->overflow)
+    if (s->h.accel_type == PT_ACCEL_LBVH) {
+      if (inst) { if (count) LAUNCH_TRACE(k_trace_lbvh, true, true); else LAUNCH_TRACE(k_trace_lbvh, true, false); }
+      else { if (count) LAUNCH_TRACE(k_trace_lbvh, false, true); else LAUNCH_TRACE(k_trace_lbvh, false, false); }
+    } else {
+      if (inst) { if (count) LAUNCH_TRACE(k_trace, true, true); else LAUNCH_TRACE(k_trace, true, false); }
+      else { if (count) LAUNCH_TRACE(k_trace, false, true); else LAUNCH_TRACE(k_trace, false, false); }
+    }
 #undef LAUNCH_TRACE
     if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_trace launch failed"); break; }
     if (timed) cudaEventRecord(e1, s->stream);
@@ -894,9 +916,14 @@ int render_waves_random(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
 int launch_intersect(pt_scene* s, const f4* ro, const f4* rd, uint32_t n, f4* hits, float* tt, unsigned char* occ, bool count) {
   CK(cudaMemsetAsync(s->fetch, 0, sizeof(uint32_t), s->stream));
   int g = grid_for(s, n, PT_TRACE_BLOCK, 8);
-#define LAUNCH_ISECT(I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, k_intersect<I, C>)(s->h, ro, rd, n, hits, tt, occ, s->fetch, s->counters, s->overflow)
-  if (s->h.has_instances) { if (count) LAUNCH_ISECT(true, true); else LAUNCH_ISECT(true, false); }
-  else { if (count) LAUNCH_ISECT(false, true); else LAUNCH_ISECT(false, false); }
+#define LAUNCH_ISECT(K, I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, K<I, C>)(s->h, ro, rd, n, hits, tt, occ, s->fetch, s->counters, s->overflow)
+  if (s->h.accel_type == PT_ACCEL_LBVH) {
+    if (s->h.has_instances) { if (count) LAUNCH_ISECT(k_intersect_lbvh, true, true); else LAUNCH_ISECT(k_intersect_lbvh, true, false); }
+    else { if (count) LAUNCH_ISECT(k_intersect_lbvh, false, true); else LAUNCH_ISECT(k_intersect_lbvh, false, false); }
+  } else {
+    if (s->h.has_instances) { if (count) LAUNCH_ISECT(k_intersect, true, true); else LAUNCH_ISECT(k_intersect, true, false); }
+    else { if (count) LAUNCH_ISECT(k_intersect, false, true); else LAUNCH_ISECT(k_intersect, false, false); }
+  }
 #undef LAUNCH_ISECT
   CK(cudaGetLastError());
   return 0;

@@ -70,7 +70,9 @@ struct LightDistDev {   // dense restatement of SpatialLightDistribution's hash 
 struct DScene {
   uint32_t n_channels;
   uint32_t n_tris, n_lights, n_materials, n_objects, n_instances;
-  const QNode* nodes;
+  const QNode* nodes;        // 4-wide layout (accel_type PT_ACCEL_QBVH)
+  const f4* lnodes;          // binary LinearBVHNode layout, 2 x f4 per node (accel_type PT_ACCEL_LBVH, dlbvh.cuh)
+  int accel_type;
   const f4* recs;            // 3 per record
   const ObjectRec* objects;
   const InstanceRec* instances;

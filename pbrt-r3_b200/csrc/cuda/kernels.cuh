@@ -5,6 +5,7 @@
 #include "launch.cuh"
 #include "dfilm.cuh"
 #include "dtrav2.cuh"
+#include "dlbvh.cuh"
 
 namespace ptd {
 
@@ -175,17 +176,25 @@ struct WaveIO {
   WaveState& W;
   Queues& Q;
   uint32_t n_ext, n_mis;
-  __device__ __forceinline__ void load(uint32_t k, Trav& T) {
+  // ray k of the launch: o, d, tmax, time; returns true for an any-hit (shadow) query
+  __device__ __forceinline__ bool ray(uint32_t k, f3* o3, f3* d3, float* tmax, float* time) {
     if (k < n_ext + n_mis) {
       const bool is_ext = k < n_ext;
       uint32_t i = is_ext ? Q.ext[k] : Q.mis[k - n_ext];
       f4 o = is_ext ? W.ray_o[i] : W.mis_o[i], d = is_ext ? W.ray_d[i] : W.mis_d[i];
-      trav_begin(S, T, xyz(o), xyz(d), o.w, d.w, false);
-    } else {
-      uint32_t i = Q.shadow[k - n_ext - n_mis];
-      f4 o = W.sh_o[i], d = W.sh_d[i];
-      trav_begin(S, T, xyz(o), xyz(d), d.w, W.ray_d[i].w, true);
+      *o3 = xyz(o); *d3 = xyz(d); *tmax = o.w; *time = d.w;
+      return false;
     }
+    uint32_t i = Q.shadow[k - n_ext - n_mis];
+    f4 o = W.sh_o[i], d = W.sh_d[i];
+    *o3 = xyz(o); *d3 = xyz(d); *tmax = d.w; *time = W.ray_d[i].w;
+    return true;
+  }
+  __device__ __forceinline__ void load(uint32_t k, Trav& T) {
+    f3 o, d;
+    float tmax, time;
+    const bool any = ray(k, &o, &d, &tmax, &time);
+    trav_begin(S, T, o, d, tmax, time, any);
   }
   __device__ __forceinline__ void store(uint32_t k, const Trav& T) {
     if (k < n_ext) {
@@ -309,6 +318,11 @@ struct ArrayIO {  // pt_intersect / pt_intersect_p / pt_intersect_device: rays a
   float* t_out;
   unsigned char* occ;
   bool any;
+  __device__ __forceinline__ bool ray(uint32_t k, f3* o3, f3* d3, float* tmax, float* time) {
+    f4 o = ro[k], d = rd[k];
+    *o3 = xyz(o); *d3 = xyz(d); *tmax = o.w; *time = d.w;
+    return any;
+  }
   __device__ __forceinline__ void load(uint32_t k, Trav& T) {
     f4 o = ro[k], d = rd[k];
     trav_begin(S, T, xyz(o), xyz(d), o.w, d.w, any);
@@ -332,6 +346,66 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_intersec
   int ovf = 0;
   ArrayIO io{S, ro, rd, hits, t_out, occ, occ != nullptr};
   trace_persistent<INST, COUNT>(S, io, n, fetch, st, &ovf, &tc);
+  if (COUNT) {
+    atomicAdd(&counters[0], tc.nodes);
+    atomicAdd(&counters[1], tc.tris);
+  }
+  if (ovf) *overflow = 1;
+}
+
+// ---- LinearBVHNode layout (dlbvh.cuh): one ray per lane, 32 rays per warp fetch ------------------------------------
+template <bool INST, bool COUNT, typename IO>
+__device__ __forceinline__ void trace_lbvh(const DScene& S, IO& io, uint32_t total, uint32_t* fetch, int* ovf, TravCounters* tc) {
+  LStack st;
+  st.n = 0;
+#if defined(__CUDA_ARCH__)
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(fetch, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= total) break;
+    const uint32_t k = base + (uint32_t)lane;
+    if (k >= total) continue;
+#else
+  (void)fetch;
+  for (uint32_t k = 0; k < total; k++) {
+#endif
+    Trav T;
+    f3 o, d;
+    float tmax, time;
+    const bool any = io.ray(k, &o, &d, &tmax, &time);
+    T.hit.tri = -1; T.hit.instance = -1;
+    T.hit.t = 0.0f; T.hit.b0 = T.hit.b1 = T.hit.b2 = 0.0f;
+    T.ray_tmax = tmax;
+    st.n = 0;
+    if (any) T.found = lbvh_traverse<true, INST, COUNT, 0>(S, 0u, o, d, time, T.ray_tmax, &T.hit, st, ovf, tc);
+    else T.found = lbvh_traverse<false, INST, COUNT, 0>(S, 0u, o, d, time, T.ray_tmax, &T.hit, st, ovf, tc);
+    io.store(k, T);
+  }
+}
+template <int NC, bool INST, bool COUNT>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_lbvh(const __grid_constant__ DScene S, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis, uint32_t n_sh,
+                                                               unsigned long long* counters, int* overflow) {
+  TravCounters tc;
+  tc.nodes = 0; tc.tris = 0;
+  int ovf = 0;
+  WaveIO<NC, INST> io{S, W, Q, n_ext, n_mis};
+  trace_lbvh<INST, COUNT>(S, io, n_ext + n_mis + n_sh, Q.counts + 4, &ovf, &tc);
+  if (COUNT) {
+    atomicAdd(&counters[0], tc.nodes);
+    atomicAdd(&counters[1], tc.tris);
+  }
+  if (ovf) *overflow = 1;
+}
+template <bool INST, bool COUNT>
+__global__ void __launch_bounds__(PT_TRACE_BLOCK) k_intersect_lbvh(const __grid_constant__ DScene S, const f4* __restrict__ ro, const f4* __restrict__ rd, uint32_t n, f4* hits,
+                                                                   float* t_out, unsigned char* occ, uint32_t* fetch, unsigned long long* counters, int* overflow) {
+  TravCounters tc;
+  tc.nodes = 0; tc.tris = 0;
+  int ovf = 0;
+  ArrayIO io{S, ro, rd, hits, t_out, occ, occ != nullptr};
+  trace_lbvh<INST, COUNT>(S, io, n, fetch, &ovf, &tc);
   if (COUNT) {
     atomicAdd(&counters[0], tc.nodes);
     atomicAdd(&counters[1], tc.tris);

@@ -321,6 +321,34 @@ void build_bvh(const std::vector<BBox>& prim_bounds, int max_prims_in_node, int 
   out->n_ref_nodes = 0;
 }
 
+namespace {
+uint32_t lbvh_emit(const BvhResult& r, int32_t b, size_t base, std::vector<LNodeH>* out) {
+  const size_t off = out->size();
+  out->emplace_back();
+  const BuildNodeH& n = r.tree[(size_t)b];
+  LNodeH g;
+  for (int a = 0; a < 3; a++) { g.mn[a] = n.bounds.mn[a]; g.mx[a] = n.bounds.mx[a]; }
+  uint32_t depth = 1;
+  if (n.n > 0) {
+    g.offset = (int32_t)n.first;
+    g.meta = n.n & 0x3fffffffu;
+    (*out)[off] = g;
+    return depth;
+  }
+  g.meta = ((uint32_t)n.axis & 3u) << 30;
+  uint32_t d0 = lbvh_emit(r, n.child[0], base, out);
+  g.offset = (int32_t)(out->size() - base);  // node indices are relative to the object's first node
+  uint32_t d1 = lbvh_emit(r, n.child[1], base, out);
+  (*out)[off] = g;
+  return 1 + std::max(d0, d1);
+}
+}  // namespace
+
+uint32_t flatten_lbvh(const BvhResult& r, std::vector<LNodeH>* out) {
+  if (r.tree.empty()) return 0;
+  return lbvh_emit(r, 0, out->size(), out);
+}
+
 void flatten_reference(const BvhResult& r, std::vector<RefNodeH>* out) {
   out->clear();
   if (!r.tree.empty()) ref_flatten(r, 0, out);

@@ -29,6 +29,14 @@ struct GpuNodeH {     // 128 B, mirrors ptd::QNode
 };
 static_assert(sizeof(GpuNodeH) == 128, "GpuNodeH must be 128 bytes");
 
+struct LNodeH {       // 32 B, the LinearBVHNode layout of cuda/dlbvh.cuh (accel/lbvh.rs:14-19)
+  float mn[3];
+  int32_t offset;     // leaf: first primitive of the ordered list; interior: second child (the first one is this + 1)
+  float mx[3];
+  uint32_t meta;      // n_primitives | axis << 30
+};
+static_assert(sizeof(LNodeH) == 32, "LNodeH must be 32 bytes");
+
 struct RefNodeH {     // the reference's SIMDBVHNode view (for build-parity checks only)
   float bboxes[2][3][4];
   int64_t children[4];
@@ -47,6 +55,8 @@ struct BvhResult {
 
 // prim_bounds: world bounds of each primitive BEFORE inflation.
 void build_bvh(const std::vector<BBox>& prim_bounds, int max_prims_in_node, int split_method, BvhResult* out);
+// flatten_bvh_tree (accel/lbvh.rs:55-73): depth-first, root = 0; returns the depth of the binary tree
+uint32_t flatten_lbvh(const BvhResult& r, std::vector<LNodeH>* out);
 // the reference's flatten_qbvh_tree, for parity checks
 void flatten_reference(const BvhResult& r, std::vector<RefNodeH>* out);
 

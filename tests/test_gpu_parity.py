@@ -102,6 +102,47 @@ def test_closest_hit_bit_exact(P, pair, name):
     assert np.array_equal(sc.intersect_p(r), orc.intersect_p(r))
 
 
+LBVH = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
+
+
+@pytest.mark.parametrize("name", ["cornell", "grid", "instances"])
+def test_lbvh_layout_bit_exact(P, pair, name):
+    """the binary LinearBVHNode layout (accel/lbvh.rs) next to the 4-wide one: primitive ids, t,
+    barycentrics and the node / triangle visit counters equal the oracle's LBVHAccel restatement; the closest hits are
+    the ones the 4-wide layout finds (same t; ids may differ only on exact ties, which the visit order decides)."""
+    texts = {"cornell": lambda: P.scenes.cornell_box(res=200, spp=64),
+             "grid": lambda: P.scenes.displaced_grid(n=160, res=128, spp=4),
+             "instances": lambda: P.scenes.instanced_blobs(n_instances=60, n_sub=2, res=(96, 64), spp=4, n_lights=8)}
+    txt = texts[name]()
+    assert 'Accelerator "bvh"' in txt
+    hs, sc, orc = pair("lbvh_" + name, LBVH(txt))
+    assert hs.desc.accel.type == P.capi.PT_ACCEL_LBVH
+    pix, sn = _samples(hs, 20000, 4)
+    rays, _ = orc.camera_rays(pix, sn)
+    assert _check_intersections(sc, orc, rays) > 0.3
+    _check_intersections(sc, orc, _random_rays(orc, 20000, 7))
+    r = _random_rays(orc, 20000, 9, tmax=np.random.RandomState(3).uniform(0.01, 50.0, 20000))
+    assert np.array_equal(sc.intersect_p(r), orc.intersect_p(r))
+    # against the 4-wide layout of the same scene
+    hq, sq, oq = pair(name, txt)
+    pa, ta, _ = sc.intersect(rays)
+    pq, tq, _ = sq.intersect(rays)
+    assert np.array_equal(ta.view(np.uint32), tq.view(np.uint32))
+    assert (pa != pq).mean() < 1e-3
+    assert np.array_equal(sc.intersect_p(r), sq.intersect_p(r))
+
+
+def test_lbvh_layout_image(P, pair):
+    hs, sc, orc = pair("lbvh_mixed", LBVH(P.scenes.cornell_box(res=96, spp=16, materials="mixed", extra_lights=True, maxdepth=8)))
+    rgb, st = sc.render(collect_counters=1)
+    ref, so = orc.render()
+    assert rel_rmse(rgb, ref) <= RMSE_TOL
+    for k in ("camera_rays", "regular_rays", "shadow_rays"):
+        assert st[k] == so[k], (k, st[k], so[k])
+    assert abs(st["nodes_visited"] - so["nodes_visited"]) <= 1e-3 * so["nodes_visited"]
+    assert st["extend_bytes"] == 32 * st["nodes_visited"] + 48 * st["tris_tested"] + 48 * st["extend_rays"]
+
+
 def test_light_distribution_bit_exact(P, pair):
     for name, txt in [("cornell_halton", P.scenes.cornell_box(res=200, spp=64)), ("cornell_lights", P.scenes.cornell_box(res=64, spp=4, extra_lights=True))]:
         hs, sc, orc = pair(name, txt)

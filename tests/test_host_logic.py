@@ -164,6 +164,40 @@ def test_host_bvh_coincident_centroids_make_big_leaf(P):
     assert hb.info(0)["n_nodes"] == 1 and hb.node(0, 0)[3] == 1
 
 
+@pytest.mark.parametrize("scene", ["cornell", "grid", "instances"])
+def test_oracle_lbvh_layout_finds_the_same_hits(P, scene):
+    """Accelerator layout "lbvh" (accel/lbvh.rs) vs the 4-wide layout in the oracle: the same binary tree walked two ways.
+    Closest-hit t is identical (same triangle test, same shrinking t_max), ids differ at most on exact ties, any-hit agrees,
+    and the binary walk visits more (smaller) nodes."""
+    import oracle_api
+    txt = {"cornell": lambda: P.scenes.cornell_box(res=64, spp=4), "grid": lambda: P.scenes.displaced_grid(n=64, res=64, spp=1),
+           "instances": lambda: P.scenes.instanced_blobs(n_instances=20, n_sub=1, res=(48, 32), spp=1, n_lights=4)}[scene]()
+    hq = P.HostScene.parse_string(txt)
+    hl = P.HostScene.parse_string(txt.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"'))
+    assert (hq.desc.accel.type, hl.desc.accel.type) == (P.capi.PT_ACCEL_QBVH, P.capi.PT_ACCEL_LBVH)
+    oq, ol = oracle_api.OracleScene(hq), oracle_api.OracleScene(hl)
+    sb = hq.desc.film.sample_bounds
+    rng = np.random.RandomState(11)
+    n = 4000
+    pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+    rays, _ = oq.camera_rays(pix, np.zeros(n, np.int32))
+    wb = oq.world_bound()
+    o = rng.uniform(wb[:3], wb[3:], (n, 3))
+    d = rng.normal(size=(n, 3))
+    d[:30] = np.eye(3)[rng.randint(0, 3, 30)]                      # axis-aligned: inf / NaN slab products
+    rnd = np.concatenate([o, np.full((n, 1), np.inf), d, np.zeros((n, 1))], 1).astype(np.float32)
+    for r in (rays, rnd):
+        pq, tq, bq, nq, trq = oq.intersect(r)
+        pl, tl, bl, nl, trl = ol.intersect(r)
+        assert np.array_equal(tq.view(np.uint32), tl.view(np.uint32))
+        assert (pq != pl).mean() < 2e-3
+        assert nl > nq
+    r = rnd.copy()
+    r[:, 3] = rng.uniform(0.01, 30.0, n)
+    assert np.array_equal(oq.intersect_p(r), ol.intersect_p(r))
+    oq.close(); ol.close()
+
+
 def test_device_sincos_equals_libm(tmp_path):
     """The device's sin/cos (dmath.cuh pt_sinf/pt_cosf, f64 polynomial) must equal the host libm bit for bit: the
     reference's f32::sin/cos are libm calls, and ulp differences get amplified by specular chains."""

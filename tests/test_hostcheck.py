@@ -87,6 +87,18 @@ def test_hostcheck_li_instances(HC):
     _cmp_li(HC, HC.scenes.instanced_blobs(n_instances=30, n_sub=1, res=(48, 32), spp=4, n_lights=4), 3000, 4, 0.999)
 
 
+def test_hostcheck_lbvh_layout(HC):
+    """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
+    lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
+    hs, sc, orc = _cmp_li(HC, lb(HC.scenes.instanced_blobs(n_instances=30, n_sub=1, res=(48, 32), spp=4, n_lights=4)), 2000, 4, 0.999)
+    assert hs.desc.accel.type == HC.capi.PT_ACCEL_LBVH
+    rgb, st = sc.render(collect_counters=1)
+    ref, so = orc.render(threads=2)
+    assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5
+    for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+        assert st[k] == so[k], k
+
+
 def test_hostcheck_gaussian_filter_film(HC):
     P = HC
     import oracle_api
