@@ -75,6 +75,7 @@ enum pt_spectrum_kind {       /* core/spectrum/mod.rs:16-20 */
 #define PT_TRI_TWO_SIDED           4u  /* TriangleMesh.two_sided, pbrt-r3 only (shapes/triangle.rs:15) */
 #define PT_TRI_HAS_N               8u  /* mesh has per-vertex normals  */
 #define PT_TRI_HAS_UV             16u  /* mesh has per-vertex uv       */
+#define PT_TRI_HAS_S              32u  /* mesh has per-vertex tangents "S" (shapes/triangle.rs:18,386-391) */
 
 /* A material after (constant) texture evaluation.  Spectra are indices into
  * pt_scene_desc.spectra (n_channels floats each). */
@@ -165,6 +166,7 @@ typedef struct pt_scene_desc {
   const float* tri_p;         /* 9 floats per triangle: p0 p1 p2                        */
   const float* tri_n;         /* 9 floats per triangle or NULL (PT_TRI_HAS_N)           */
   const float* tri_uv;        /* 6 floats per triangle or NULL (PT_TRI_HAS_UV)          */
+  const float* tri_s;         /* 9 floats per triangle or NULL (PT_TRI_HAS_S): tangents, object_to_world applied */
   const uint32_t* tri_flags;  /* PT_TRI_* bits                                           */
   const int32_t* tri_material;/* index into materials, or -1 (no material)              */
   const int32_t* tri_light;   /* index into lights (area light of this triangle) or -1 */

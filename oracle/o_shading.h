@@ -459,13 +459,22 @@ inline SurfInt tri_interaction(const pt_scene_desc* d, int tri, const Ray& r, Fl
   si.sdpdu = dpdu;
   si.tri = tri;
   si.time = r.time;
-  if ((T.flags & PT_TRI_HAS_N) && d->tri_n) {
-    const float* q = d->tri_n + (size_t)tri * 9;
-    Vec3 n0(q[0], q[1], q[2]), n1(q[3], q[4], q[5]), n2(q[6], q[7], q[8]);
+  const bool has_n = (T.flags & PT_TRI_HAS_N) && d->tri_n, has_s = (T.flags & PT_TRI_HAS_S) && d->tri_s;
+  if (has_n || has_s) {  // triangle.rs:376-444
     Vec3 ns = si.n;
-    Vec3 nns = b0 * n0 + b1 * n1 + b2 * n2;
-    if (length_squared(nns) > 0.0f) ns = normalize(nns);
+    if (has_n) {
+      const float* q = d->tri_n + (size_t)tri * 9;
+      Vec3 n0(q[0], q[1], q[2]), n1(q[3], q[4], q[5]), n2(q[6], q[7], q[8]);
+      Vec3 nns = b0 * n0 + b1 * n1 + b2 * n2;
+      if (length_squared(nns) > 0.0f) ns = normalize(nns);
+    }
     Vec3 ss = normalize(si.dpdu);
+    if (has_s) {
+      const float* q = d->tri_s + (size_t)tri * 9;
+      Vec3 s0(q[0], q[1], q[2]), s1(q[3], q[4], q[5]), s2(q[6], q[7], q[8]);
+      Vec3 nss = b0 * s0 + b1 * s1 + b2 * s2;
+      if (length_squared(nss) > 0.0f) ss = normalize(nss);
+    }
     Vec3 ts = cross(ns, ss);
     if (length_squared(ts) > 0.0f) {
       ts = normalize(ts);

@@ -16,7 +16,7 @@ PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT = 0, 1, 2
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
 PT_SPECTRUM_RGB, PT_SPECTRUM_SAMPLED = 0, 1
-PT_TRI_REVERSE_ORIENTATION, PT_TRI_SWAPS_HANDEDNESS, PT_TRI_TWO_SIDED, PT_TRI_HAS_N, PT_TRI_HAS_UV = 1, 2, 4, 8, 16
+PT_TRI_REVERSE_ORIENTATION, PT_TRI_SWAPS_HANDEDNESS, PT_TRI_TWO_SIDED, PT_TRI_HAS_N, PT_TRI_HAS_UV, PT_TRI_HAS_S = 1, 2, 4, 8, 16, 32
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
@@ -63,7 +63,7 @@ class pt_accel(C.Structure):
 class pt_scene_desc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("spectrum_kind", C.c_uint32), ("n_channels", C.c_uint32), ("n_spectra", C.c_uint32),
                 ("spectra", f32p), ("xyz_weights", C.c_float * 180), ("xyz_scale", C.c_float),
-                ("n_tris", C.c_uint32), ("tri_p", f32p), ("tri_n", f32p), ("tri_uv", f32p), ("tri_flags", u32p),
+                ("n_tris", C.c_uint32), ("tri_p", f32p), ("tri_n", f32p), ("tri_uv", f32p), ("tri_s", f32p), ("tri_flags", u32p),
                 ("tri_material", i32p), ("tri_light", i32p),
                 ("n_objects", C.c_uint32), ("obj_first", u32p), ("prims", i32p), ("n_instances", C.c_uint32),
                 ("instances", C.POINTER(pt_instance)),

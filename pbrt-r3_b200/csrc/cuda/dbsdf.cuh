@@ -467,13 +467,22 @@ PT_HDN SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, fl
   si.sn = n;
   si.sdpdu = dpdu;
   si.tri = tri;
-  if ((flags & PT_TRI_HAS_N) && S.tri_n) {
-    const float* q = S.tri_n + (size_t)tri * 9;
-    f3 n0 = mk3(ldg(q), ldg(q + 1), ldg(q + 2)), n1 = mk3(ldg(q + 3), ldg(q + 4), ldg(q + 5)), n2 = mk3(ldg(q + 6), ldg(q + 7), ldg(q + 8));
+  const bool has_n = (flags & PT_TRI_HAS_N) && S.tri_n, has_s = (flags & PT_TRI_HAS_S) && S.tri_s;
+  if (has_n || has_s) {  // triangle.rs:376-444
     f3 ns = si.n;
-    f3 nns = b0 * n0 + b1 * n1 + b2 * n2;
-    if (len2(nns) > 0.0f) ns = norm3(nns);
+    if (has_n) {
+      const float* q = S.tri_n + (size_t)tri * 9;
+      f3 n0 = mk3(ldg(q), ldg(q + 1), ldg(q + 2)), n1 = mk3(ldg(q + 3), ldg(q + 4), ldg(q + 5)), n2 = mk3(ldg(q + 6), ldg(q + 7), ldg(q + 8));
+      f3 nns = b0 * n0 + b1 * n1 + b2 * n2;
+      if (len2(nns) > 0.0f) ns = norm3(nns);
+    }
     f3 ss = norm3(dpdu);
+    if (has_s) {
+      const float* q = S.tri_s + (size_t)tri * 9;
+      f3 s0 = mk3(ldg(q), ldg(q + 1), ldg(q + 2)), s1 = mk3(ldg(q + 3), ldg(q + 4), ldg(q + 5)), s2 = mk3(ldg(q + 6), ldg(q + 7), ldg(q + 8));
+      f3 nss = b0 * s0 + b1 * s1 + b2 * s2;
+      if (len2(nss) > 0.0f) ss = norm3(nss);
+    }
     f3 ts = cross3(ns, ss);
     if (len2(ts) > 0.0f) {
       ts = norm3(ts);

@@ -263,6 +263,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   }
   if (D->tri_n) CK(s->bufs.upload(D->tri_n, (size_t)D->n_tris * 9, &H.tri_n));
   if (D->tri_uv) CK(s->bufs.upload(D->tri_uv, (size_t)D->n_tris * 6, &H.tri_uv));
+  if (D->tri_s) CK(s->bufs.upload(D->tri_s, (size_t)D->n_tris * 9, &H.tri_s));
   CK(s->bufs.upload(D->tri_flags, D->n_tris, &H.tri_flags));
   CK(s->bufs.upload(D->tri_material, D->n_tris, &H.tri_material));
   CK(s->bufs.upload(D->tri_light, D->n_tris, &H.tri_light));

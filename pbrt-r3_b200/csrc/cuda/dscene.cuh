@@ -80,6 +80,7 @@ struct DScene {
   const f4* tri_v;           // 3 per triangle: p.xyz, w unused (shading / light sampling re-reads by id)
   const float* tri_n;        // 9 per triangle or null
   const float* tri_uv;       // 6 per triangle or null
+  const float* tri_s;        // 9 per triangle or null: mesh tangents "S"
   const uint32_t* tri_flags;
   const int32_t* tri_material;
   const int32_t* tri_light;

@@ -29,7 +29,7 @@ void pt_set_error(const std::string& s);  // api_common.cpp
 
 struct pt_host_scene {
   std::vector<float> spectra;
-  std::vector<float> tri_p, tri_n, tri_uv;
+  std::vector<float> tri_p, tri_n, tri_uv, tri_s;
   std::vector<uint32_t> tri_flags;
   std::vector<int32_t> tri_material, tri_light;
   std::vector<std::vector<int32_t>> obj_prims;  // object 0 = top level
@@ -341,7 +341,7 @@ struct Builder {
     size_t nverts = pp->f.size() / 3;
     for (int32_t v : vi) if (v < 0 || (size_t)v >= nverts) throw ParseError("trianglemesh index out of range");
     const Xf& o2w = ctm;
-    std::vector<V3> P(nverts), N;
+    std::vector<V3> P(nverts), N, Sv;
     std::vector<float> UV;
     for (size_t i = 0; i < nverts; i++) P[i] = m_point(o2w.m, v3(pp->f[3 * i], pp->f[3 * i + 1], pp->f[3 * i + 2]));
     const Param* puv = ps.find(PC_FLOAT, "uv");
@@ -358,7 +358,12 @@ struct Builder {
         }
     }
     if (!UV.empty() && UV.size() / 2 < nverts) throw ParseError("trianglemesh: fewer uv values than vertices");
-    if (ps.find(PC_POINT, "S")) warn("trianglemesh \"S\" tangents are ignored on the GPU path");
+    if (const Param* pst = ps.find(PC_POINT, "S")) {  // triangle.rs:823-829; TriangleMesh::new transforms them as vectors (:55-60)
+      size_t nsv = pst->f.size() / 3;
+      if (nsv < nverts) throw ParseError("trianglemesh: fewer tangents than vertices");
+      Sv.resize(nsv);
+      for (size_t i = 0; i < nsv; i++) Sv[i] = m_vector(o2w.m, v3(pst->f[3 * i], pst->f[3 * i + 1], pst->f[3 * i + 2]));
+    }
     if (const Param* pn = ps.find(PC_POINT, "N")) {
       size_t nn = pn->f.size() / 3;
       if (nn < nverts) throw ParseError("trianglemesh: fewer normals than vertices");
@@ -372,6 +377,7 @@ struct Builder {
     if (two_sided) flags |= PT_TRI_TWO_SIDED;
     if (!N.empty()) flags |= PT_TRI_HAS_N;
     if (!UV.empty()) flags |= PT_TRI_HAS_UV;
+    if (!Sv.empty()) flags |= PT_TRI_HAS_S;
 
     int mat = material_for_shape(ps_in);
     int light_spec = -1, light_two_sided = 0;
@@ -384,7 +390,7 @@ struct Builder {
       light_spec = add_spectrum(L);
       light_two_sided = gs.area_light_params.one_bool("twosided", false) ? 1 : 0;
     }
-    bool want_n = !N.empty(), want_uv = !UV.empty();
+    bool want_n = !N.empty(), want_uv = !UV.empty(), want_s = !Sv.empty();
     size_t ntri = vi.size() / 3;
     for (size_t t = 0; t < ntri; t++) {
       size_t i0 = (size_t)vi[3 * t], i1 = (size_t)vi[3 * t + 1], i2 = (size_t)vi[3 * t + 2];
@@ -400,6 +406,14 @@ struct Builder {
         for (int k = 0; k < 3; k++) {
           V3 n = want_n ? N[ii[k]] : v3(0, 0, 0);
           hs->tri_n.push_back(n.x); hs->tri_n.push_back(n.y); hs->tri_n.push_back(n.z);
+        }
+      }
+      if (want_s || !hs->tri_s.empty()) {
+        hs->tri_s.resize((size_t)tri * 9, 0.0f);
+        const size_t ii[3] = {i0, i1, i2};
+        for (int k = 0; k < 3; k++) {
+          V3 sv = want_s ? Sv[ii[k]] : v3(0, 0, 0);
+          hs->tri_s.push_back(sv.x); hs->tri_s.push_back(sv.y); hs->tri_s.push_back(sv.z);
         }
       }
       if (want_uv || !hs->tri_uv.empty()) {
@@ -764,6 +778,7 @@ struct Builder {
     D.tri_p = hs->tri_p.data();
     if (!hs->tri_n.empty()) { hs->tri_n.resize((size_t)D.n_tris * 9, 0.0f); D.tri_n = hs->tri_n.data(); }
     if (!hs->tri_uv.empty()) { hs->tri_uv.resize((size_t)D.n_tris * 6, 0.0f); D.tri_uv = hs->tri_uv.data(); }
+    if (!hs->tri_s.empty()) { hs->tri_s.resize((size_t)D.n_tris * 9, 0.0f); D.tri_s = hs->tri_s.data(); }
     D.tri_flags = hs->tri_flags.data();
     D.tri_material = hs->tri_material.data();
     D.tri_light = hs->tri_light.data();

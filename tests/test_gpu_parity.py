@@ -143,6 +143,20 @@ def test_lbvh_layout_image(P, pair):
     assert st["extend_bytes"] == 32 * st["nodes_visited"] + 48 * st["tris_tested"] + 48 * st["extend_rays"]
 
 
+def test_mesh_tangents(P, pair):
+    """Mesh "S" tangents (triangle.rs:386-391) with anisotropic metal / plastic: radiance per sample vs the oracle."""
+    from test_hostcheck import tangent_scene
+    hs, sc, orc = pair("tangents", tangent_scene(P, res=64, spp=8))
+    pix, sn = _samples(hs, 20000, 8, seed=6)
+    la = sc.li(pix, sn)
+    lb, _, _, _ = orc.li(pix, sn)
+    close = (np.abs(la - lb) <= 1e-3 * np.maximum(np.abs(lb), 1e-2)).all(1)
+    assert close.mean() > 0.999, close.mean()
+    rgb, _ = sc.render()
+    ref, _ = orc.render()
+    assert rel_rmse(rgb, ref) <= RMSE_TOL
+
+
 def test_light_distribution_bit_exact(P, pair):
     for name, txt in [("cornell_halton", P.scenes.cornell_box(res=200, spp=64)), ("cornell_lights", P.scenes.cornell_box(res=64, spp=4, extra_lights=True))]:
         hs, sc, orc = pair(name, txt)

@@ -87,6 +87,31 @@ def test_hostcheck_li_instances(HC):
     _cmp_li(HC, HC.scenes.instanced_blobs(n_instances=30, n_sub=1, res=(48, 32), spp=4, n_lights=4), 3000, 4, 0.999)
 
 
+def tangent_scene(P, res=32, spp=8):
+    """Cornell box whose floor is an anisotropic copper sheet with per-vertex tangents "S", and whose back wall has both
+    "N" and "S" (triangle.rs:376-444: the shading frame is built from S when the mesh has tangents, N or not)."""
+    txt = P.scenes.cornell_box(res=res, spp=spp, maxdepth=6)
+    shapes = [l for l in txt.split("\n") if l.startswith("Shape")]
+    floor, back = shapes[0], shapes[2]
+    txt = txt.replace('Material "matte" "rgb Kd" [0.725 0.71 0.68]\n' + floor,
+                      'Material "metal" "float uroughness" [0.05] "float vroughness" [0.4]\n' + floor + ' "point S" [1 0 1  1 0 0.5  0.2 0 1  -1 0 1]')
+    txt = txt.replace('Material "matte" "rgb Kd" [0.725 0.71 0.68]\n' + back,
+                      'Material "plastic" "rgb Kd" [0.3 0.3 0.6] "rgb Ks" [0.5 0.5 0.5] "float uroughness" [0.02] "float vroughness" [0.3]\n' + back +
+                      ' "point S" [1 1 0  0 1 0  -1 1 0  1 0.5 0] "normal N" [0 0.1 -1  0.1 0 -1  0 -0.1 -1  -0.1 0 -1]')
+    assert '"point S"' in txt and txt.count('"point S"') == 2
+    return txt
+
+
+def test_hostcheck_mesh_tangents(HC):
+    hs, sc, orc = _cmp_li(HC, tangent_scene(HC), 3000, 8, 0.999)
+    flags = np.ctypeslib.as_array(hs.desc.tri_flags, (hs.desc.n_tris,))
+    assert ((flags & HC.capi.PT_TRI_HAS_S) != 0).sum() == 4 and bool(hs.desc.tri_s)
+    # the tangents change the result: same scene without them
+    plain = HC.HostScene.parse_string(__import__("re").sub(r' "point S" \[[^\]]*\]', "", tangent_scene(HC)))
+    pix = np.array([[16, 28], [10, 30], [16, 10]], np.int32)
+    assert not np.array_equal(sc.li(pix, np.zeros(3, np.int32)), HC.Scene(plain).li(pix, np.zeros(3, np.int32)))
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')

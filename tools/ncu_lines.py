@@ -42,3 +42,14 @@ for k, a in sorted(agg.items(), key=lambda x: -x[1][1])[:top]:
 pf = collections.defaultdict(lambda: [0, 0])
 for k, a in agg.items(): pf[k[0]][0] += a[0]; pf[k[0]][1] += a[1]
 for f, a in sorted(pf.items(), key=lambda x: -x[1][1]): print("FILE %-16s inst %5.1f%%  samples %5.1f%%" % (f, 100.0 * a[0] / max(tot_i, 1), 100.0 * a[1] / max(tot_s, 1)))
+# optional: coarse groups by (file, line range) given as extra args "name=file:lo-hi"
+groups = [a for a in sys.argv[5:] if "=" in a]
+if groups:
+    print("--- groups")
+    for gspec in groups:
+        name, rest = gspec.split("=")
+        f, rng = rest.split(":")
+        lo, hi = map(int, rng.split("-"))
+        gi = sum(a[0] for k, a in agg.items() if k[0] == f and lo <= k[1] <= hi)
+        gs = sum(a[1] for k, a in agg.items() if k[0] == f and lo <= k[1] <= hi)
+        print("%-28s inst %5.1f%%  samples %5.1f%%" % (name, 100.0 * gi / max(tot_i, 1), 100.0 * gs / max(tot_s, 1)))
