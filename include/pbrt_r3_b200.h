@@ -308,6 +308,15 @@ int pt_light_distribution(pt_scene* scene, const float* points, uint32_t n, floa
 
 /* ---- host front end (the reference's own L5/L6 layers, C++ mirror because rustc is absent) ---- */
 typedef struct pt_host_scene pt_host_scene;
+/* PbrtOptions (core/options/pbrt_options.rs:6-12), the process-wide options the reference's main sets from its command
+ * line (src/bin/pbrt.rs:363-369) and its factories read: --quick renders at 1/4 resolution (film.rs:548-554) with one
+ * sample per pixel (halton.rs:288-290, sobol.rs:199-201), --quick-full-resolution keeps the resolution. */
+typedef struct pt_options {
+  int32_t quick_render;
+  int32_t quick_render_full_resolution;
+} pt_options;
+void pt_set_options(const pt_options* options);   /* PbrtOptions::set; NULL restores the defaults */
+void pt_get_options(pt_options* out);
 /* pbrt_parse_file + SceneContext (core/parser/parser.rs:60, scene_context.rs): parse a .pbrt file
  * (subset: see DESIGN.md) into a scene description.  Overrides < 0 / NULL mean "keep". */
 int pt_parse_file(const char* path, int pixelsamples_override, int spectrum_kind, pt_host_scene** out);

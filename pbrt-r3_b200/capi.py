@@ -87,13 +87,17 @@ class pt_stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class pt_options(C.Structure):
+    _fields_ = [("quick_render", C.c_int32), ("quick_render_full_resolution", C.c_int32)]
+
+
 # every symbol include/pbrt_r3_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "pt_scene_create", "pt_scene_destroy", "pt_scene_reupload", "pt_last_error", "pt_abi_version", "pt_render", "pt_render_partial", "pt_film_resolve",
     "pt_film_clear", "pt_intersect", "pt_intersect_p", "pt_intersect_device", "pt_sampler_values", "pt_camera_rays", "pt_li",
     "pt_bvh_info", "pt_bvh_node", "pt_light_distribution", "pt_parse_file", "pt_parse_string", "pt_host_scene_desc",
     "pt_host_scene_filename", "pt_host_scene_destroy", "pt_host_bvh_build", "pt_host_bvh_info", "pt_host_bvh_node",
-    "pt_host_bvh_destroy",
+    "pt_host_bvh_destroy", "pt_set_options", "pt_get_options",
 ]
 
 _lib = None
@@ -125,6 +129,10 @@ def load(path=None):
     lib.pt_host_bvh_node.argtypes = [vp, C.c_uint32, C.c_uint32, f32p, C.POINTER(C.c_int64), i32p, i32p]
     lib.pt_host_bvh_destroy.argtypes = [vp]
     lib.pt_host_bvh_destroy.restype = None
+    lib.pt_set_options.argtypes = [C.POINTER(pt_options)]
+    lib.pt_set_options.restype = None
+    lib.pt_get_options.argtypes = [C.POINTER(pt_options)]
+    lib.pt_get_options.restype = None
     if hasattr(lib, "pt_scene_create"):
         lib.pt_scene_create.argtypes = [C.POINTER(pt_scene_desc), C.c_int, C.POINTER(vp)]
         lib.pt_scene_destroy.argtypes = [vp]

@@ -479,11 +479,12 @@ int ensure_wave(pt_scene* s, uint32_t seg_cap, uint32_t nseg = 1) {
   CK(B.alloc(cap, &W.ray_o)); CK(B.alloc(cap, &W.ray_d)); CK(B.alloc(cap, &W.hit));
   W.hit_inst = nullptr;
   if (s->h.has_instances) CK(B.alloc(cap, &W.hit_inst));
-  CK(B.alloc((size_t)cap * NC, &W.beta)); CK(B.alloc((size_t)cap * NC, &W.L));
+  const uint32_t SS = st_stride(NC);  // RGB: padded to 16-byte records
+  CK(B.alloc((size_t)cap * SS, &W.beta)); CK(B.alloc((size_t)cap * SS, &W.L));
   CK(B.alloc(cap, &W.eta_scale)); CK(B.alloc(cap, &W.flags)); CK(B.alloc(cap, &W.dim)); CK(B.alloc(cap, &W.sindex));
   CK(B.alloc(cap, &W.pix)); CK(B.alloc(cap, &W.p_film));
-  CK(B.alloc(cap, &W.sh_o)); CK(B.alloc(cap, &W.sh_d)); CK(B.alloc((size_t)cap * NC, &W.pendA));
-  CK(B.alloc(cap, &W.mis_o)); CK(B.alloc(cap, &W.mis_d)); CK(B.alloc((size_t)cap * NC, &W.pendB)); CK(B.alloc(cap, &W.mis_light));
+  CK(B.alloc(cap, &W.sh_o)); CK(B.alloc(cap, &W.sh_d)); CK(B.alloc((size_t)cap * SS, &W.pendA));
+  CK(B.alloc(cap, &W.mis_o)); CK(B.alloc(cap, &W.mis_d)); CK(B.alloc((size_t)cap * SS, &W.pendB)); CK(B.alloc(cap, &W.mis_light));
   Queues& Q = s->Q;
   CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(32, &Q.counts));
   CK(cudaMemset(Q.counts, 0, 32 * sizeof(uint32_t)));
@@ -1181,10 +1182,10 @@ int pt_li(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint3
   if (n == 0) return 0;
   if (run_list(s, pixel_xy, sample_num, n, true)) return 1;
   const uint32_t NC = s->h.n_channels, cap = s->W.cap;
-  std::vector<float> L((size_t)cap * NC);
+  std::vector<float> L((size_t)cap * st_stride(NC));
   CK(cudaMemcpy(L.data(), s->W.L, L.size() * sizeof(float), cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < n; i++)
-    for (uint32_t c = 0; c < NC; c++) out_l[(size_t)i * NC + c] = L[(size_t)c * cap + i];
+    for (uint32_t c = 0; c < NC; c++) out_l[(size_t)i * NC + c] = NC == 3 ? L[(size_t)i * 4 + c] : L[(size_t)c * cap + i];
   int ovf = 0;
   CK(cudaMemcpy(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost));
   if (ovf) { pt_set_error("traversal stack overflow"); return 1; }

@@ -15,7 +15,8 @@
 
 namespace ptd {
 
-struct WaveState {            // all arrays have `cap` path slots; spectra are channel-major: [c * cap + i]
+struct WaveState {            // all arrays have `cap` path slots; spectra: RGB = one 16-byte record {r, g, b, -} per path
+                              // (one sector per access); 60 bins = channel-major [c * cap + i] (st_load / st_store)
   uint32_t cap;
   uint32_t seg_cap;           // waves in flight own disjoint segments of the slots: segment = path id / seg_cap (render_waves)
   uint32_t nseg;
@@ -218,12 +219,27 @@ PT_HDN int ld_sample(const DScene& S, f3 p, float u, float* pdf) {
 }
 
 // ---- path state helpers ------------------------------------------------------------------------------------------
-template <int NC> PT_HD Sp<NC> st_load(const float* a, uint32_t cap, uint32_t i) { Sp<NC> r;
+// floats per path of a spectral state array
+PT_HD constexpr uint32_t st_stride(uint32_t nc) { return nc == 3 ? 4u : nc; }
+template <int NC> PT_HD Sp<NC> st_load(const float* a, uint32_t cap, uint32_t i) {
+  Sp<NC> r;
+  if (NC == 3) {
+    f4 v = reinterpret_cast<const f4*>(a)[i];
+    r.c[0] = v.x; r.c[1] = v.y; r.c[NC - 1] = v.z;
+    return r;
+  }
 #pragma unroll
-  for (int c = 0; c < NC; c++) r.c[c] = a[(size_t)c * cap + i]; return r; }
+  for (int c = 0; c < NC; c++) r.c[c] = a[(size_t)c * cap + i];
+  return r;
+}
 template <int NC> PT_HD void st_store(float* a, uint32_t cap, uint32_t i, const Sp<NC>& v) {
+  if (NC == 3) {
+    reinterpret_cast<f4*>(a)[i] = mk4(v.c[0], v.c[1], v.c[NC - 1], 0.0f);
+    return;
+  }
 #pragma unroll
-  for (int c = 0; c < NC; c++) a[(size_t)c * cap + i] = v.c[c]; }
+  for (int c = 0; c < NC; c++) a[(size_t)c * cap + i] = v.c[c];
+}
 
 #if defined(__CUDA_ARCH__)
 PT_D uint32_t queue_push(uint32_t* counter) {  // warp-aggregated append (ballot / popc)

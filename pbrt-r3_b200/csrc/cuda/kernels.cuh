@@ -203,6 +203,10 @@ struct WaveIO {
       W.hit[i] = mk4(T.hit.b0, T.hit.b1, T.hit.b2, bitsf((uint32_t)tri));
       if (INST) W.hit_inst[i] = T.found ? T.hit.instance : -1;
       if (T.found) W.ray_o[i].w = T.ray_tmax;
+      // A ray that leaves the scene ends its path (no infinite lights on this path: path.rs:93-104 adds nothing), and the
+      // pending light / MIS terms of its last vertex are folded into L by k_finish in the same order (L + a) + b that
+      // the shade stage would use: nothing to shade.
+      if (tri < 0) return;
       // bin the path by shading class for the per-material shade kernels (warp-aggregated per class)
       const int cls = shade_class(S, tri, (int)(W.flags[i] >> 8));
       uint32_t slot;

@@ -26,6 +26,7 @@
 using namespace pth;
 
 void pt_set_error(const std::string& s);  // api_common.cpp
+const pt_options& pt_current_options();    // api_common.cpp: PbrtOptions singleton
 
 struct pt_host_scene {
   std::vector<float> spectra;
@@ -684,6 +685,11 @@ struct Builder {
     // Film (film.rs:64-179, 538-571)
     pt_film& F = D.film;
     int xres = film_params.one_int("xresolution", 1280), yres = film_params.one_int("yresolution", 720);
+    const pt_options& opt = pt_current_options();
+    if (opt.quick_render && !opt.quick_render_full_resolution) {  // film.rs:548-554
+      xres = std::max(1, xres / 4);
+      yres = std::max(1, yres / 4);
+    }
     float crop[4] = {0, 1, 0, 1};
     if (const Param* q = film_params.find(PC_FLOAT, "cropwindow")) {
       if (q->f.size() != 4) throw ParseError("\"cropwindow\" expects 4 values");
@@ -736,7 +742,8 @@ struct Builder {
     else if (sampler_name == "random") { S.type = PT_SAMPLER_RANDOM; S.samples_per_pixel = sampler_params.one_int("pixelsamples", 4); }
     else throw ParseError("Sampler \"" + sampler_name + "\" is not supported on the GPU path (halton, sobol, random)");
     S.sample_at_pixel_center = sampler_params.one_bool("samplepixelcenter", false) ? 1 : 0;
-    if (pixelsamples_override > 0) S.samples_per_pixel = pixelsamples_override;
+    if (pixelsamples_override > 0) S.samples_per_pixel = pixelsamples_override;  // pbrt.rs:234-238 (replace_params_int before the factory runs)
+    if (pt_current_options().quick_render && S.type != PT_SAMPLER_RANDOM) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
 
     // Integrator (integrators/path.rs:252-271)
     if (integrator_name != "path") throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path only)");

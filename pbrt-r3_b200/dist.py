@@ -54,3 +54,24 @@ def resolve_host(xyzw, scale=1.0):
     inv = np.where(pos, f(1.0) / np.where(pos, w, f(1.0)), f(1.0)).astype(np.float32)
     c = np.where(pos[:, None], np.maximum(f(0.0), c * inv[:, None]), c)
     return (c * f(scale)).astype(np.float32)
+
+
+def render_distributed(scene, host_scene, rank, world, local_device, backend="nccl"):
+    """One Integrator::render over `world` processes (one per GPU): every rank renders its shard of the samples (tiles for
+    Sampler "random") into a partial film, one reduce sums the partials onto rank 0, which resolves the image.
+    Returns (rgb or None on ranks > 0, stats of this rank)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        import os
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_device)
+        dist.init_process_group(backend, device_id=torch.device("cuda", local_device))
+    d = host_scene.desc
+    opts = shard_opts(d.sampler.type, d.sampler.samples_per_pixel, rank, world)
+    ptr, npx, st = scene.render_partial(**opts)
+    film = film_tensor(ptr, npx, "cuda:%d" % local_device)
+    reduce_film(film, dst=0)
+    rgb = scene.film_resolve(film.data_ptr()) if rank == 0 else None
+    dist.barrier()
+    return rgb, st

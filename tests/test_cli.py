@@ -1,0 +1,96 @@
+"""The reference's command line (src/bin/pbrt.rs:44-135) on the GPU path: option surface, PbrtOptions overrides in the
+front end, image writers (write_image.rs).  The render itself runs in tests/hostcheck (CPU) and under -m gpu."""
+import os
+import struct
+import subprocess
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cli_accepts_the_reference_options(P):
+    from pbrt_r3_b200 import cli
+    ap = cli.build_parser()
+    o = ap.parse_args(["scene.pbrt", "--outfile", "a.exr", "--nthreads", "8", "--quick", "--quiet", "--pixelsamples", "4", "--cropwindow", "0,1,0,1",
+                       "--logdir", "/tmp", "--logtostderr", "--minloglevel", "1", "--stats", "--profile", "--display-server", "localhost:14158"])
+    assert o.pbrtfile == ["scene.pbrt"] and o.outfile == "a.exr" and o.quick and o.quiet and o.pixelsamples == 4 and o.stats
+    o = ap.parse_args(["-i", "s.pbrt", "-o", "b.png", "-j", "2", "-s", "16", "--quick-full-resolution", "-k", "dir"])
+    assert o.infile == "s.pbrt" and o.quick_full_resolution and o.sequential_display == "dir"
+    assert cli.main([]) == -1 and cli.main(["/nonexistent.pbrt"]) == -1        # usage + exit code -1 (pbrt.rs:373-383)
+
+
+def test_pbrt_options_quick_render(P):
+    lib = P.capi.load()
+    txt = P.scenes.cornell_box(res=64, spp=16)
+    try:
+        lib.pt_set_options(P.capi.pt_options(1, 0))
+        d = P.HostScene.parse_string(txt).desc
+        assert list(d.film.full_resolution) == [16, 16] and d.sampler.samples_per_pixel == 1      # film.rs:548-554, halton.rs:288-290
+        assert P.HostScene.parse_string(txt, 8).desc.sampler.samples_per_pixel == 1              # --quick wins over --pixelsamples
+        lib.pt_set_options(P.capi.pt_options(1, 1))
+        d = P.HostScene.parse_string(txt).desc
+        assert list(d.film.full_resolution) == [64, 64] and d.sampler.samples_per_pixel == 1
+        got = P.capi.pt_options()
+        lib.pt_get_options(got)
+        assert (got.quick_render, got.quick_render_full_resolution) == (1, 1)
+    finally:
+        lib.pt_set_options(None)
+    d = P.HostScene.parse_string(txt).desc
+    assert list(d.film.full_resolution) == [64, 64] and d.sampler.samples_per_pixel == 16
+    assert P.HostScene.parse_string(txt, 8).desc.sampler.samples_per_pixel == 8                  # pbrt.rs:234-238
+
+
+def test_image_writers(P, tmp_path):
+    from pbrt_r3_b200 import imageio
+    rng = np.random.RandomState(0)
+    rgb = rng.uniform(0, 2, (5, 7, 3)).astype(np.float32)
+    rgb[0, 0] = [0.0, 0.001, np.nan]
+    exr = str(tmp_path / "a.exr")
+    imageio.write_image(exr, rgb)
+    back = imageio.read_exr(exr)
+    assert np.array_equal(back.view(np.uint32), rgb.view(np.uint32))                              # floats kept bit for bit
+    # to_byte (write_image.rs:16-18): clamp(255 * gamma_correct(v), 0, 255) as u8
+    b = imageio.to_bytes(np.array([[[0.0, 0.0031308, 0.5], [1.0, 2.0, np.nan]]], np.float32))
+    assert b.tolist() == [[[0, 10, 187], [254, 255, 0]]]      # f32: 1.055 - 0.055 = 0.99999994 -> 254, as in the reference
+    png = str(tmp_path / "a.png")
+    imageio.write_image(png, rgb)
+    raw = open(png, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h = struct.unpack(">II", raw[16:24])
+    assert (w, h) == (7, 5)
+    idat = raw[raw.index(b"IDAT") + 4: raw.index(b"IEND") - 8]
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(5, 1 + 21)
+    assert np.array_equal(rows[:, 1:].reshape(5, 7, 3), imageio.to_bytes(rgb))
+    imageio.write_image(str(tmp_path / "a.pfm"), rgb)
+    with pytest.raises(ValueError):
+        imageio.write_image(str(tmp_path / "noext"), rgb)
+
+
+@pytest.mark.gpu
+def test_cli_renders_like_the_library(P, tmp_path):
+    from pbrt_r3_b200 import imageio
+    scene = tmp_path / "cornell.pbrt"
+    scene.write_text(P.scenes.cornell_box(res=48, spp=4))
+    out = str(tmp_path / "out.exr")
+    r = subprocess.run([sys.executable, "-m", "pbrt_r3_b200", str(scene), "--outfile", out, "--pixelsamples", "2", "--stats", "--nthreads", "4"],
+                       cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Camera rays traced" in r.stdout and str(50 * 50 * 2) in r.stdout
+    hs = P.HostScene.parse_string(P.scenes.cornell_box(res=48, spp=4), 2)
+    sc = P.Scene(hs, 0)
+    rgb, _ = sc.render()
+    sc.close()
+    assert np.array_equal(imageio.read_exr(out), rgb)
+    # Film "filename" is used when --outfile is absent; --quick = 1/4 resolution, 1 spp
+    r = subprocess.run([sys.executable, "-m", "pbrt_r3_b200", "--quiet", "--quick", "-i", str(scene)], cwd=str(tmp_path), capture_output=True, text=True,
+                       env=dict(os.environ, PYTHONPATH=ROOT))
+    assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr)
+    assert imageio.read_exr(str(tmp_path / "cornell.exr")).shape == (12, 12, 3)
+    bad = tmp_path / "bad.pbrt"
+    bad.write_text('Camera "perspective"\nWorldBegin\nShape "trianglemesh" "integer indices" [0 1 5] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
+    r = subprocess.run([sys.executable, "-m", "pbrt_r3_b200", str(bad)], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 255 and "ERROR" in r.stderr                                           # exit(-1)

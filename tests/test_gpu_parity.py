@@ -291,6 +291,36 @@ def test_full_size_config2_properties(P):
     orc.close()
 
 
+def test_full_size_config3_properties(P):
+    """configs[2] geometry at full size: 1000 instances of a 20 480-triangle blob (20.5 M instanced triangles), 256 emissive
+    quads, two-level 4-wide BVH.  Primary hits vs the oracle on a sample of rays (ids, t, barycentrics, visit counters),
+    closest-hit / any-hit consistency, per-sample radiance vs the oracle, determinism."""
+    import oracle_api
+    hs = P.HostScene.parse_string(P.scenes.instanced_blobs(n_instances=1000, n_sub=5, res=(240, 135), spp=2, maxdepth=8, n_lights=256))
+    assert hs.desc.n_instances == 1000 and hs.desc.n_lights == 512
+    sc = P.Scene(hs, 0)
+    orc = oracle_api.OracleScene(hs)
+    pix, sn = _samples(hs, 30000, 2)
+    rays, _ = orc.camera_rays(pix, sn)
+    assert _check_intersections(sc, orc, rays) > 0.2
+    _check_intersections(sc, orc, _random_rays(orc, 30000, 13))
+    p, t, _ = sc.intersect(rays)
+    hit = p >= 0
+    r2 = rays[hit].copy()
+    r2[:, 3] = t[hit] * 1.001
+    assert sc.intersect_p(r2).all()
+    r2[:, 3] = t[hit] * 0.5
+    assert np.array_equal(sc.intersect_p(r2).astype(bool), sc.intersect(r2)[0] >= 0)
+    la = sc.li(pix[:8000], sn[:8000])
+    lb = orc.li(pix[:8000], sn[:8000])[0]
+    close = (np.abs(la - lb) <= 1e-3 * np.maximum(np.abs(lb), 1e-2)).all(1)
+    assert close.mean() > 0.999, close.mean()
+    a, _ = sc.render()
+    assert np.array_equal(a, sc.render(wave_segments=1)[0])
+    sc.close()
+    orc.close()
+
+
 def test_edge_cases(P):
     # empty scene (no primitives, no lights) renders black; scene without lights renders black; zero rays is fine
     hs = P.HostScene.parse_string('Camera "perspective"\nFilm "image" "integer xresolution" [8] "integer yresolution" [8]\nWorldBegin\nWorldEnd\n')
