@@ -59,29 +59,56 @@ PT_HD uint32_t div_magic(uint32_t a, uint64_t magic) {
 #endif
 }
 
+// high half of a 32 x 32 bit product
+PT_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
 PT_HD float scrambled_radical_inverse(uint32_t base, uint64_t magic, uint64_t a, const uint16_t* perm) {  // radical_inverse.rs:71-91
   float inv_base = div_rn(1.0f, (float)base);
-  uint64_t rev = 0;
   float inv_base_n = 1.0f;
-  if (a < 0x100000000ull) {
-    uint32_t a32 = (uint32_t)a;
+  float frev;
+  if (a * (uint64_t)base < 0x100000000ull) {
+    // Everything fits 32 bits (the usual case: index < 2^21 at 64 spp): the reversed number has as many digits as a, so
+    // rev < a * base < 2^32; and with m = ceil(2^32 / base) = (2^32 + e) / base, e <= base, floor(a * m / 2^32) = floor(a / base)
+    // exactly because a * e <= a * base < 2^32.  Same digits, same float sequence as the reference's u64 loop.
+    const uint32_t m32 = (uint32_t)(magic >> 32) + 1u;  // base is not a power of two (dimensions >= 2: primes >= 5)
+    uint32_t a32 = (uint32_t)a, rev = 0;
     while (a32 != 0) {
-      uint32_t next = div_magic(a32, magic);
+      uint32_t next = mulhi32(a32, m32);
       uint32_t digit = a32 - next * base;
-      rev = rev * base + (uint64_t)ldg(perm + digit);
+      rev = rev * base + (uint32_t)ldg(perm + digit);
       inv_base_n *= inv_base;
       a32 = next;
     }
+    frev = (float)rev;
   } else {
-    while (a != 0) {
-      uint64_t next = a / base;
-      uint64_t digit = a - next * base;
-      rev = rev * base + (uint64_t)ldg(perm + digit);
-      inv_base_n *= inv_base;
-      a = next;
+    uint64_t rev = 0;
+    if (a < 0x100000000ull) {
+      uint32_t a32 = (uint32_t)a;
+      while (a32 != 0) {
+        uint32_t next = div_magic(a32, magic);
+        uint32_t digit = a32 - next * base;
+        rev = rev * base + (uint64_t)ldg(perm + digit);
+        inv_base_n *= inv_base;
+        a32 = next;
+      }
+    } else {
+      while (a != 0) {
+        uint64_t next = a / base;
+        uint64_t digit = a - next * base;
+        rev = rev * base + (uint64_t)ldg(perm + digit);
+        inv_base_n *= inv_base;
+        a = next;
+      }
     }
+    frev = (float)rev;
   }
-  return fminf(inv_base_n * ((float)rev + div_rn(inv_base * (float)ldg(perm), 1.0f - inv_base)), PT_ONE_MINUS_EPS);
+  return fminf(inv_base_n * (frev + div_rn(inv_base * (float)ldg(perm), 1.0f - inv_base)), PT_ONE_MINUS_EPS);
 }
 
 PT_HD uint64_t inverse_radical_inverse(uint64_t base, uint64_t inverse, int ndigits) {  // radical_inverse.rs:60-69

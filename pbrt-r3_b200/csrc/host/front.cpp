@@ -15,6 +15,7 @@
 #include "spectrum_host.h"
 #include "xform.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -81,6 +82,7 @@ struct Builder {
   std::map<std::string, int> object_ids;
   int current_object = 0;  // 0 = top level
   int pixelsamples_override = -1;
+  std::string cur_dir;  // directory of the file being parsed: relative "filename" parameters resolve against it
 
   Builder(pt_host_scene* h, int spectrum_kind) : hs(h), spec(spectrum_kind) { hs->obj_prims.resize(1); }
 
@@ -323,8 +325,111 @@ struct Builder {
     return true;
   }
 
+  // raw mesh arrays in object space, before TriangleMesh::new transforms them
+  struct MeshData {
+    std::vector<int32_t> vi;
+    std::vector<float> P, N, S, UV;   // 3, 3, 3, 2 floats per vertex; N / S / UV may be empty
+  };
+
+  // PLY reader (shapes/plymesh.rs:253-378 on top of the ply-rs crate): ascii, binary_little_endian and binary_big_endian;
+  // element "vertex" with float properties x y z [nx ny nz] [u v | s t | texture_u texture_v | texture_s texture_t],
+  // element "face" with an integer list vertex_indices / vertex_index; triangles, and quads split as (0,1,2) (3,0,2).
+  // Other properties are skipped; vertex properties the reference panics on (non-float) are an error.
+  static std::string load_ply(const std::string& path, MeshData* M) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return "cannot open file";
+    std::string line;
+    if (!std::getline(f, line) || line.substr(0, 3) != "ply") return "not a PLY file";
+    enum { ASCII, LE, BE } fmt = ASCII;
+    struct Prop { std::string name, type, ctype; bool list; };
+    struct Elem { std::string name; size_t count; std::vector<Prop> props; };
+    std::vector<Elem> elems;
+    bool header_done = false;
+    while (std::getline(f, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      std::istringstream is(line);
+      std::string w;
+      is >> w;
+      if (w == "format") { std::string t; is >> t; fmt = t == "ascii" ? ASCII : (t == "binary_little_endian" ? LE : BE); }
+      else if (w == "element") { Elem e; is >> e.name >> e.count; elems.push_back(e); }
+      else if (w == "property") {
+        if (elems.empty()) return "property before element";
+        Prop p; std::string t; is >> t;
+        if (t == "list") { p.list = true; is >> p.ctype >> p.type >> p.name; }
+        else { p.list = false; p.type = t; is >> p.name; }
+        elems.back().props.push_back(p);
+      } else if (w == "end_header") { header_done = true; break; }
+    }
+    if (!header_done) return "missing end_header";
+    auto tsize = [](const std::string& t) -> int {
+      if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+      if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+      if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+      if (t == "double" || t == "float64") return 8;
+      return 0;
+    };
+    auto is_float = [](const std::string& t) { return t == "float" || t == "float32"; };
+    // one scalar of type t as double
+    auto read_scalar = [&](const std::string& t, double* out) -> bool {
+      if (fmt == ASCII) { return (bool)(f >> *out); }
+      int n = tsize(t);
+      unsigned char b[8];
+      if (n == 0 || !f.read((char*)b, n)) return false;
+      if (fmt == BE) std::reverse(b, b + n);
+      if (t == "char" || t == "int8") *out = (double)(int8_t)b[0];
+      else if (t == "uchar" || t == "uint8") *out = (double)b[0];
+      else if (t == "short" || t == "int16") { int16_t v; memcpy(&v, b, 2); *out = v; }
+      else if (t == "ushort" || t == "uint16") { uint16_t v; memcpy(&v, b, 2); *out = v; }
+      else if (t == "int" || t == "int32") { int32_t v; memcpy(&v, b, 4); *out = v; }
+      else if (t == "uint" || t == "uint32") { uint32_t v; memcpy(&v, b, 4); *out = v; }
+      else if (is_float(t)) { float v; memcpy(&v, b, 4); *out = v; }
+      else { double v; memcpy(&v, b, 8); *out = v; }
+      return true;
+    };
+    for (const Elem& e : elems) {
+      if (e.name == "vertex") {
+        int ix[8] = {-1, -1, -1, -1, -1, -1, -1, -1};  // x y z nx ny nz u v
+        for (size_t k = 0; k < e.props.size(); k++) {
+          const std::string& n = e.props[k].name;
+          int slot = n == "x" ? 0 : n == "y" ? 1 : n == "z" ? 2 : n == "nx" ? 3 : n == "ny" ? 4 : n == "nz" ? 5
+                     : (n == "u" || n == "s" || n == "texture_u" || n == "texture_s") ? 6 : (n == "v" || n == "t" || n == "texture_v" || n == "texture_t") ? 7 : -1;
+          if (e.props[k].list) return "list property in the vertex element";
+          if (slot >= 0 && !is_float(e.props[k].type)) return "vertex property \"" + n + "\" must be float";
+          if (slot >= 0) ix[slot] = (int)k;
+        }
+        bool has_p = ix[0] >= 0 || ix[1] >= 0 || ix[2] >= 0, has_n = ix[3] >= 0 || ix[4] >= 0 || ix[5] >= 0, has_uv = ix[6] >= 0 || ix[7] >= 0;
+        std::vector<double> row(e.props.size());
+        for (size_t i = 0; i < e.count; i++) {
+          for (size_t k = 0; k < e.props.size(); k++) if (!read_scalar(e.props[k].type, &row[k])) return "truncated vertex data";
+          auto val = [&](int s) { return ix[s] >= 0 ? (float)row[(size_t)ix[s]] : 0.0f; };
+          if (has_p) { M->P.push_back(val(0)); M->P.push_back(val(1)); M->P.push_back(val(2)); }
+          if (has_n) { M->N.push_back(val(3)); M->N.push_back(val(4)); M->N.push_back(val(5)); }
+          if (has_uv) { M->UV.push_back(val(6)); M->UV.push_back(val(7)); }
+        }
+      } else {
+        const bool face = e.name == "face";
+        for (size_t i = 0; i < e.count; i++) {
+          for (const Prop& p : e.props) {
+            if (!p.list) { double d; if (!read_scalar(p.type, &d)) return "truncated data"; continue; }
+            double cnt;
+            if (!read_scalar(p.ctype, &cnt)) return "truncated list";
+            std::vector<int32_t> idx((size_t)cnt);
+            for (auto& v : idx) { double d; if (!read_scalar(p.type, &d)) return "truncated list"; v = (int32_t)d; }
+            if (face && (p.name == "vertex_indices" || p.name == "vertex_index")) {
+              if (idx.size() == 3) M->vi.insert(M->vi.end(), idx.begin(), idx.end());
+              else if (idx.size() == 4) { const int32_t q[6] = {idx[0], idx[1], idx[2], idx[3], idx[0], idx[2]}; M->vi.insert(M->vi.end(), q, q + 6); }
+              else return "face with " + std::to_string(idx.size()) + " vertices (only triangles and quads are supported)";
+            }
+          }
+        }
+      }
+    }
+    return "";
+  }
+
   void shape(const std::string& name, const ParamSet& ps_in) {
-    if (name != "trianglemesh") throw ParseError("Shape \"" + name + "\" is not supported on the GPU path (triangle meshes only)");
+    if (name != "trianglemesh" && name != "plymesh")
+      throw ParseError("Shape \"" + name + "\" is not supported on the GPU path (triangle meshes: trianglemesh, plymesh)");
     ParamSet ps = ps_in;
     bool is_area = !gs.area_light_name.empty();
     if (is_area) {  // scene_context.rs:405-421
@@ -335,41 +440,60 @@ struct Builder {
     }
     if (ps.find(PC_TEXTURE, "alpha") || ps.find(PC_FLOAT, "alpha") || ps.find(PC_TEXTURE, "shadowalpha") || ps.find(PC_FLOAT, "shadowalpha"))
       throw ParseError("alpha-masked shapes are not supported on the GPU path");
-    const Param* pi = ps.find(PC_INT, "indices");
-    const Param* pp = ps.find(PC_POINT, "P");
-    if (!pi || !pp || pi->i.empty() || pp->f.empty()) { warn("Invalid mesh"); return; }
-    const std::vector<int32_t>& vi = pi->i;
-    size_t nverts = pp->f.size() / 3;
-    for (int32_t v : vi) if (v < 0 || (size_t)v >= nverts) throw ParseError("trianglemesh index out of range");
+    MeshData M;
+    if (name == "plymesh") {  // shapes/plymesh.rs:253-378
+      std::string fn = ps.one_string("filename", "");
+      std::string path = (fn.size() && fn[0] == '/') ? fn : (cur_dir.empty() ? fn : cur_dir + "/" + fn);
+      std::string err = load_ply(path, &M);
+      if (!err.empty()) throw ParseError("plymesh \"" + path + "\": " + err);
+      if (M.vi.empty() || M.P.empty()) { warn("Invalid mesh"); return; }
+    } else {
+      const Param* pi = ps.find(PC_INT, "indices");
+      const Param* pp = ps.find(PC_POINT, "P");
+      if (!pi || !pp || pi->i.empty() || pp->f.empty()) { warn("Invalid mesh"); return; }
+      M.vi = pi->i;
+      M.P.assign(pp->f.begin(), pp->f.begin() + (pp->f.size() / 3) * 3);
+      size_t nverts = M.P.size() / 3;
+      const Param* puv = ps.find(PC_FLOAT, "uv");
+      if (!puv) puv = ps.find(PC_FLOAT, "st");
+      if (puv) {
+        M.UV.assign(puv->f.begin(), puv->f.begin() + (puv->f.size() / 2) * 2);
+      } else if (is_fillable_uv(M.vi, nverts)) {
+        const float tri_uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};
+        M.UV.assign(nverts * 2, 0.0f);
+        for (size_t i = 0; i + 2 < M.vi.size(); i += 3)
+          for (int j = 0; j < 3; j++) {
+            size_t v = (size_t)M.vi[i + j];
+            if (v < nverts && M.UV[2 * v] == 0.0f && M.UV[2 * v + 1] == 0.0f) { M.UV[2 * v] = tri_uv[j][0]; M.UV[2 * v + 1] = tri_uv[j][1]; }
+          }
+      }
+      if (const Param* pst = ps.find(PC_POINT, "S")) M.S.assign(pst->f.begin(), pst->f.begin() + (pst->f.size() / 3) * 3);  // triangle.rs:823-829
+      if (const Param* pn = ps.find(PC_POINT, "N")) M.N.assign(pn->f.begin(), pn->f.begin() + (pn->f.size() / 3) * 3);
+    }
+    emit_mesh(ps, ps_in, is_area, M);
+  }
+
+  // TriangleMesh::new + create_triangle_mesh (triangle.rs:37-92, 696-754) for either source of the arrays
+  void emit_mesh(const ParamSet& ps, const ParamSet& ps_in, bool is_area, const MeshData& M) {
+    const std::vector<int32_t>& vi = M.vi;
+    size_t nverts = M.P.size() / 3;
+    for (int32_t v : vi) if (v < 0 || (size_t)v >= nverts) throw ParseError("triangle mesh index out of range");
     const Xf& o2w = ctm;
     std::vector<V3> P(nverts), N, Sv;
-    std::vector<float> UV;
-    for (size_t i = 0; i < nverts; i++) P[i] = m_point(o2w.m, v3(pp->f[3 * i], pp->f[3 * i + 1], pp->f[3 * i + 2]));
-    const Param* puv = ps.find(PC_FLOAT, "uv");
-    if (!puv) puv = ps.find(PC_FLOAT, "st");
-    if (puv) {
-      UV.assign(puv->f.begin(), puv->f.begin() + (puv->f.size() / 2) * 2);
-    } else if (is_fillable_uv(vi, nverts)) {
-      const float tri_uv[3][2] = {{0, 0}, {1, 0}, {1, 1}};
-      UV.assign(nverts * 2, 0.0f);
-      for (size_t i = 0; i + 2 < vi.size(); i += 3)
-        for (int j = 0; j < 3; j++) {
-          size_t v = (size_t)vi[i + j];
-          if (UV[2 * v] == 0.0f && UV[2 * v + 1] == 0.0f) { UV[2 * v] = tri_uv[j][0]; UV[2 * v + 1] = tri_uv[j][1]; }
-        }
-    }
-    if (!UV.empty() && UV.size() / 2 < nverts) throw ParseError("trianglemesh: fewer uv values than vertices");
-    if (const Param* pst = ps.find(PC_POINT, "S")) {  // triangle.rs:823-829; TriangleMesh::new transforms them as vectors (:55-60)
-      size_t nsv = pst->f.size() / 3;
-      if (nsv < nverts) throw ParseError("trianglemesh: fewer tangents than vertices");
+    const std::vector<float>& UV = M.UV;
+    for (size_t i = 0; i < nverts; i++) P[i] = m_point(o2w.m, v3(M.P[3 * i], M.P[3 * i + 1], M.P[3 * i + 2]));
+    if (!UV.empty() && UV.size() / 2 < nverts) throw ParseError("triangle mesh: fewer uv values than vertices");
+    if (!M.S.empty()) {  // TriangleMesh::new transforms the tangents as vectors (triangle.rs:55-60)
+      size_t nsv = M.S.size() / 3;
+      if (nsv < nverts) throw ParseError("triangle mesh: fewer tangents than vertices");
       Sv.resize(nsv);
-      for (size_t i = 0; i < nsv; i++) Sv[i] = m_vector(o2w.m, v3(pst->f[3 * i], pst->f[3 * i + 1], pst->f[3 * i + 2]));
+      for (size_t i = 0; i < nsv; i++) Sv[i] = m_vector(o2w.m, v3(M.S[3 * i], M.S[3 * i + 1], M.S[3 * i + 2]));
     }
-    if (const Param* pn = ps.find(PC_POINT, "N")) {
-      size_t nn = pn->f.size() / 3;
-      if (nn < nverts) throw ParseError("trianglemesh: fewer normals than vertices");
+    if (!M.N.empty()) {
+      size_t nn = M.N.size() / 3;
+      if (nn < nverts) throw ParseError("triangle mesh: fewer normals than vertices");
       N.resize(nn);
-      for (size_t i = 0; i < nn; i++) N[i] = m_normal_with_inv(o2w.minv, v3(pn->f[3 * i], pn->f[3 * i + 1], pn->f[3 * i + 2]));
+      for (size_t i = 0; i < nn; i++) N[i] = m_normal_with_inv(o2w.minv, v3(M.N[3 * i], M.N[3 * i + 1], M.N[3 * i + 2]));
     }
     bool two_sided = ps.one_bool("twosided", true);
     uint32_t flags = 0;
@@ -507,6 +631,11 @@ struct Builder {
   }
 
   void parse_text(const std::string& text, const std::string& dir) {
+    struct DirGuard {
+      std::string& ref; std::string saved;
+      DirGuard(std::string& r, const std::string& v) : ref(r), saved(r) { r = v; }
+      ~DirGuard() { ref = saved; }
+    } dir_guard(cur_dir, dir);
     Lexer lx(text);
     for (;;) {
       Token t = lx.next();

@@ -96,6 +96,59 @@ WorldEnd
     assert l.type == P.capi.PT_LIGHT_POINT and np.allclose(list(l.v), [2, 3, 4])
 
 
+def test_front_end_plymesh(P, tmp_path):
+    """Shape "plymesh" (shapes/plymesh.rs): ascii and binary PLY, normals + uv, a quad split as (0,1,2) (3,0,2), file name
+    relative to the including scene file; the flattened scene equals the same mesh given as a trianglemesh."""
+    import struct
+    verts = [(0, 0, 0, 0, 0, 1, 0, 0), (1, 0, 0, 0, 0, 1, 1, 0), (1, 1, 0.25, 0, 0.1, 1, 1, 1), (0, 1, 0, 0, 0, 1, 0, 1), (2, 0, 0, 0, 0, 1, 0.5, 0.5)]
+    faces = [(0, 1, 2, 3), (1, 4, 2)]
+    hdr = "ply\nformat %s 1.0\ncomment test\nelement vertex 5\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\n" \
+          "property float ny\nproperty float nz\nproperty float u\nproperty float v\nelement face 2\nproperty list uchar int vertex_indices\nend_header\n"
+    (tmp_path / "geo").mkdir()
+    with open(tmp_path / "geo" / "a.ply", "w") as f:
+        f.write(hdr % "ascii")
+        for v in verts:
+            f.write(" ".join(repr(float(x)) for x in v) + "\n")
+        for fc in faces:
+            f.write("%d %s\n" % (len(fc), " ".join(map(str, fc))))
+    for name, fmt, e in (("l.ply", "binary_little_endian", "<"), ("b.ply", "binary_big_endian", ">")):
+        with open(tmp_path / "geo" / name, "wb") as f:
+            f.write((hdr % fmt).encode())
+            for v in verts:
+                f.write(struct.pack(e + "8f", *v))
+            for fc in faces:
+                f.write(struct.pack(e + "B%di" % len(fc), len(fc), *fc))
+    head = 'Camera "perspective"\nWorldBegin\nMaterial "matte"\nTranslate 0 0 3\nRotate 20 0 1 0\n'
+    tm = head + 'Shape "trianglemesh" "integer indices" [0 1 2 3 0 2 1 4 2] "point P" [%s] "normal N" [%s] "float uv" [%s]\nWorldEnd\n' % (
+        " ".join(repr(float(x)) for v in verts for x in v[:3]), " ".join(repr(float(x)) for v in verts for x in v[3:6]),
+        " ".join(repr(float(x)) for v in verts for x in v[6:]))
+    ref_hs = P.HostScene.parse_string(tm)       # keep the owner alive: desc points into it
+    ref = ref_hs.desc
+    assert ref.n_tris == 3
+    (tmp_path / "inc.pbrt").write_text('Shape "plymesh" "string filename" ["geo/a.ply"]\n')
+    for name in ("a.ply", "l.ply", "b.ply"):
+        scene = tmp_path / ("s_" + name + ".pbrt")
+        scene.write_text(head + 'Shape "plymesh" "string filename" ["geo/%s"]\nWorldEnd\n' % name)
+        hs = P.HostScene.parse_file(str(scene))
+        d = hs.desc
+        assert d.n_tris == 3
+        for fld, k in (("tri_p", 9), ("tri_n", 9), ("tri_uv", 6)):
+            a, b = np.ctypeslib.as_array(getattr(d, fld), (3 * k,)), np.ctypeslib.as_array(getattr(ref, fld), (3 * k,))
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, fld)
+        assert list(np.ctypeslib.as_array(d.tri_flags, (3,))) == list(np.ctypeslib.as_array(ref.tri_flags, (3,)))
+    (tmp_path / "s_inc.pbrt").write_text(head + 'Include "inc.pbrt"\nWorldEnd\n')
+    assert P.HostScene.parse_file(str(tmp_path / "s_inc.pbrt")).desc.n_tris == 3
+    with open(tmp_path / "geo" / "bad.ply", "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n"
+                "0 0 0\n1 0 0\n0 1 0\n5 0 1 2 0 1\n")
+    (tmp_path / "s_bad.pbrt").write_text(head + 'Shape "plymesh" "string filename" ["geo/bad.ply"]\nWorldEnd\n')
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_file(str(tmp_path / "s_bad.pbrt"))
+    (tmp_path / "s_missing.pbrt").write_text(head + 'Shape "plymesh" "string filename" ["geo/none.ply"]\nWorldEnd\n')
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_file(str(tmp_path / "s_missing.pbrt"))
+
+
 def test_front_end_instances(P):
     hs = P.HostScene.parse_string(P.scenes.instanced_blobs(n_instances=5, n_sub=1, res=(32, 24), spp=1, n_lights=2))
     d = hs.desc

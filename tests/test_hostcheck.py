@@ -79,6 +79,24 @@ def test_hostcheck_cornell_image_and_streams(HC):
     assert np.sqrt(((a - b) ** 2).mean()) / a.mean() < 1e-5
 
 
+def test_hostcheck_halton_digit_paths(HC):
+    """scrambled_radical_inverse has a 32-bit path (index * base < 2^32: one mul-hi per digit), a 32-bit-index path and the
+    u64 loop; all three against the oracle's u64 restatement, bit for bit, around the switch points."""
+    import oracle_api
+    P = HC
+    hs = P.HostScene.parse_string(P.scenes.cornell_box(res=200, spp=1 << 20))
+    sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+    rng = np.random.RandomState(9)
+    n = 400
+    pix = np.stack([rng.randint(-1, 201, n), rng.randint(-1, 201, n)], 1).astype(np.int32)
+    for hi in (64, 1 << 12, 1 << 17, (1 << 20) - 1):        # index up to 2^20 * 62208 = 2^36: 64-bit indices too
+        sn = rng.randint(0, hi, n).astype(np.int32)
+        sn[:4] = [0, 1, hi - 1, hi // 2]
+        for dim0, nd in [(0, 24), (180, 12), (1000, 24)]:
+            a, b = sc.sampler_values(pix, sn, dim0, nd), orc.sampler_values(pix, sn, dim0, nd)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (hi, dim0)
+
+
 def test_hostcheck_li_mixed_materials(HC):
     _cmp_li(HC, HC.scenes.cornell_box(res=32, spp=8, materials="mixed", extra_lights=True, maxdepth=8), 3000, 8, 0.999)
 
