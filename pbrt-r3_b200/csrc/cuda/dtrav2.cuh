@@ -52,10 +52,7 @@ struct Trav {
   float shx, shy, shz;
   int lf, lc;           // pending leaf: first record, count (lc = -1: the pending entry is the barrier)
   uint32_t node_base, rec_base;
-  // level-0 state saved while inside an instance
-  f3 so, sd;
-  float stmin, stmax;
-  int inst;             // >= 0 while traversing an instanced object
+  int inst;             // >= 0 while traversing an instanced object (the world-space ray state is parked in the stack's save area)
   bool leaf_hit;        // a primitive of the leaf being processed (at the current level) was accepted
   bool outer_hit;       // ... of the top-level leaf that was interrupted by the instance
   bool nested_hit;      // ... of some leaf of the instanced object
@@ -65,9 +62,12 @@ struct Trav {
   HitD hit;
 };
 
-PT_HD void trav_set_ray(Trav& T, f3 o, f3 d) {
+// trav_set_ray with the reciprocals already known (the instance entry computes them once for the object-bounds test)
+PT_HD void trav_set_ray_idir(Trav& T, f3 o, f3 d, float idx, float idy, float idz);
+PT_HD void trav_set_ray(Trav& T, f3 o, f3 d) { trav_set_ray_idir(T, o, d, 1.0f / d.x, 1.0f / d.y, 1.0f / d.z); }
+PT_HD void trav_set_ray_idir(Trav& T, f3 o, f3 d, float idx, float idy, float idz) {
   T.o = o; T.d = d;
-  T.idx = 1.0f / d.x; T.idy = 1.0f / d.y; T.idz = 1.0f / d.z;
+  T.idx = idx; T.idy = idy; T.idz = idz;
   T.sg = (signbit_(d.x) ? 1 : 0) | (signbit_(d.y) ? 2 : 0) | (signbit_(d.z) ? 4 : 0);
   // (box - o) * idir is NaN only for 0 * inf or a NaN operand: excluded when every 1/d is finite and non-zero and o is finite
   {
@@ -86,6 +86,41 @@ PT_HD void trav_set_ray(Trav& T, f3 o, f3 d) {
   float dx = comp(d, kx), dy = comp(d, ky), dz = comp(d, kz);
   T.kz = kz;
   T.shx = -dx / dz; T.shy = -dy / dz; T.shz = 1.0f / dz;
+}
+
+// everything trav_set_ray derives from a ray <-> 15 words of the stack's save area
+template <typename Stack>
+PT_HD void trav_park_ray(const Trav& T, Stack& st) {
+  st.save(0, T.o.x); st.save(1, T.o.y); st.save(2, T.o.z);
+  st.save(3, T.d.x); st.save(4, T.d.y); st.save(5, T.d.z);
+  st.save(6, T.tmin); st.save(7, T.tmax);
+  st.save(8, T.idx); st.save(9, T.idy); st.save(10, T.idz);
+  st.save(11, bitsf((uint32_t)T.sg | ((uint32_t)T.kz << 3) | (T.nonan ? 32u : 0u)));
+  st.save(12, T.shx); st.save(13, T.shy); st.save(14, T.shz);
+}
+template <typename Stack>
+PT_HD void trav_unpark_ray(Trav& T, const Stack& st) {
+  T.o = mk3(st.saved(0), st.saved(1), st.saved(2));
+  T.d = mk3(st.saved(3), st.saved(4), st.saved(5));
+  T.tmin = st.saved(6); T.tmax = st.saved(7);
+  T.idx = st.saved(8); T.idy = st.saved(9); T.idz = st.saved(10);
+  const uint32_t pk = fbits(st.saved(11));
+  T.sg = (int)(pk & 7u); T.kz = (int)((pk >> 3) & 3u); T.nonan = (pk & 32u) != 0u;
+  T.shx = st.saved(12); T.shy = st.saved(13); T.shz = st.saved(14);
+}
+// bounds_range (dtrav.cuh) with the reciprocals given
+PT_HD bool bounds_range_idir(const float* bmin, const float* bmax, f3 o, f3 d, float idx, float idy, float idz, float tmax, float* t0o, float* t1o) {
+  float t0 = 0.0f, t1 = tmax;
+  bool nx = signbit_(d.x), ny = signbit_(d.y), nz = signbit_(d.z);
+  t0 = fmaxf(t0, ((nx ? bmax[0] : bmin[0]) - o.x) * idx);
+  t1 = fminf(t1, ((nx ? bmin[0] : bmax[0]) - o.x) * idx);
+  t0 = fmaxf(t0, ((ny ? bmax[1] : bmin[1]) - o.y) * idy);
+  t1 = fminf(t1, ((ny ? bmin[1] : bmax[1]) - o.y) * idy);
+  t0 = fmaxf(t0, ((nz ? bmax[2] : bmin[2]) - o.z) * idz);
+  t1 = fminf(t1, ((nz ? bmin[2] : bmax[2]) - o.z) * idz);
+  *t0o = t0;
+  *t1o = t1;
+  return t0 <= t1;
 }
 
 // tri_test (dtrav.cuh) with the per-ray constants hoisted and the rejection tests folded into one predicate, so that
@@ -324,8 +359,7 @@ PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCo
 template <bool INST, bool COUNT, typename Stack>
 PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
   if (INST && T.lc < 0) {  // TransformedPrimitive::intersect returns: back to world space
-    trav_set_ray(T, T.so, T.sd);
-    T.tmin = T.stmin; T.tmax = T.stmax;
+    trav_unpark_ray(T, st);
     const ObjectRec& O = S.objects[0];
     T.node_base = O.node_base; T.rec_base = O.rec_base;
     T.inst = -1;
@@ -351,17 +385,18 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
       if (O.n_prims == 0) continue;
       if (O.single) {  // one primitive, no accelerator: test it in object space right here
         const f4* pr = S.recs + (size_t)O.rec_base * 3;
-        f3 so = T.o, sd = T.d;
+        trav_park_ray(T, st);
         trav_set_ray(T, q.o, q.d);
         T.inst = inst;
         bool fin = trav_triangle<COUNT>(T, ldg4(pr), ldg4(pr + 1), ldg4(pr + 2), cnt);
-        trav_set_ray(T, so, sd);
+        trav_unpark_ray(T, st);
         T.inst = -1;
         if (fin) { T.done = true; return; }
         continue;
       }
       float tn, tx;
-      if (!bounds_range(O.bmin, O.bmax, q.o, q.d, T.ray_tmax, &tn, &tx)) continue;
+      const float qix = 1.0f / q.d.x, qiy = 1.0f / q.d.y, qiz = 1.0f / q.d.z;  // shared by the bounds test and the traversal
+      if (!bounds_range_idir(O.bmin, O.bmax, q.o, q.d, qix, qiy, qiz, T.ray_tmax, &tn, &tx)) continue;
       // push back the rest of this leaf (in order, chunks of <= 8), then the barrier, and descend
       int rest = count - (i + 1), rfirst = first + i + 1;
       while (rest > 0) {  // last chunk first so that the chunks pop in order
@@ -372,8 +407,8 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
         rest -= ccount;
       }
       if (!st.push(PT_STACK_BARRIER)) *overflow = 1;
-      T.so = T.o; T.sd = T.d; T.stmin = T.tmin; T.stmax = T.tmax;
-      trav_set_ray(T, q.o, q.d);
+      trav_park_ray(T, st);
+      trav_set_ray_idir(T, q.o, q.d, qix, qiy, qiz);
       T.tmin = tn; T.tmax = tx;
       T.node_base = O.node_base; T.rec_base = O.rec_base;
       T.inst = inst;

@@ -30,6 +30,10 @@ namespace ptd {
 #else
 #define PT_STS_ASM 0
 #endif
+// Words per thread of the instance save area: the world-space ray and everything trav_set_ray derives from it, parked
+// in shared memory while the lane walks an instanced object (instead of 8 live registers + recomputing 6 IEEE divisions
+// on the way out).
+#define PT_SAVE_WORDS 15
 struct SharedStack {
 #if PT_STS_ASM
   uint32_t sa;       // shared-space byte address of smem[threadIdx.x]; entry stride = PT_TRACE_BLOCK * 4 bytes
@@ -38,15 +42,19 @@ struct SharedStack {
 #endif
   int n;
   int* spill;        // PT_MAX_STACK - PT_SMEM_STACK entries of local memory
-  __device__ __forceinline__ void attach(int* smem_col, int* spill_arr) {
+  float* sv;         // save area column: sv[k * PT_TRACE_BLOCK], k < PT_SAVE_WORDS (null when the scene has no instances)
+  __device__ __forceinline__ void attach(int* smem_col, int* spill_arr, float* save_col = nullptr) {
 #if PT_STS_ASM
     sa = (uint32_t)__cvta_generic_to_shared(smem_col);
 #else
     sm = smem_col;
 #endif
     spill = spill_arr;
+    sv = save_col;
     n = 0;
   }
+  __device__ __forceinline__ void save(int k, float v) { sv[k * PT_TRACE_BLOCK] = v; }
+  __device__ __forceinline__ float saved(int k) const { return sv[k * PT_TRACE_BLOCK]; }
   // fast path of the node phase: k entries fit into the shared part -> put(pos, x) at n + pos, then advance(k)
   __device__ __forceinline__ bool room(int k) const { return n + k <= PT_SMEM_STACK; }
   __device__ __forceinline__ void put(int pos, int x) {
@@ -95,6 +103,13 @@ struct SharedStack {
 #ifndef PT_NODE_EXIT_MIN
 #define PT_NODE_EXIT_MIN 8
 #endif
+#ifndef PT_VOTE_AGE
+#define PT_VOTE_AGE 2
+#endif
+// majority-vote state machine for two-level scenes: measured SLOWER than while-while (profiles/r1_instanced_trace.md), off
+#ifndef PT_INST_VOTE
+#define PT_INST_VOTE 0
+#endif
 template <bool INST, bool COUNT, typename IO>
 __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32_t total, uint32_t* fetch, SharedStack& st, int* ovf, TravCounters* tc) {
   Trav T;
@@ -126,6 +141,41 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32
     unsigned active = __ballot_sync(FULL, have);
     if (active == 0) {
       if (exhausted) break;
+      continue;
+    }
+    if (INST && PT_INST_VOTE) {
+      // Two-level scenes: a lane is walking nodes (0), has a triangle leaf of an instanced object (1), a top-level leaf
+      // whose records are mostly instances to enter - ray transform, object-bounds test (2) - or the barrier that ends an
+      // instanced object (3).  Running "the leaf phase" for all of them at once serialises three different code paths at
+      // 3-5 active lanes each (ncu, instanced 20 M-triangle scene: 8.3 active lanes per instruction overall).  So every
+      // step the warp votes and runs only the state most lanes are in; the others wait for company.
+      // and a state that was passed over gains PT_VOTE_AGE votes per step, so that no lane waits for long.
+      int w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      for (;;) {
+        const int stt = (!have || T.done) ? 4 : (T.lc == 0 ? 0 : (T.lc < 0 ? 3 : (T.inst >= 0 ? 1 : 2)));
+        const unsigned m0 = __ballot_sync(FULL, stt == 0), m1 = __ballot_sync(FULL, stt == 1), m2 = __ballot_sync(FULL, stt == 2), m3 = __ballot_sync(FULL, stt == 3);
+        const int c0 = __popc(m0), c1 = __popc(m1), c2 = __popc(m2), c3 = __popc(m3);
+        if ((c0 | c1 | c2 | c3) == 0) break;
+        const int v0 = c0 ? c0 + w0 : 0, v1 = c1 ? c1 + w1 : 0, v2 = c2 ? c2 + w2 : 0, v3 = c3 ? c3 + w3 : 0;
+        int pick = 0, best = v0;
+        if (v1 > best) { pick = 1; best = v1; }
+        if (v2 > best) { pick = 2; best = v2; }
+        if (v3 > best) { pick = 3; best = v3; }
+        w0 = (pick == 0 || !c0) ? 0 : w0 + PT_VOTE_AGE;
+        w1 = (pick == 1 || !c1) ? 0 : w1 + PT_VOTE_AGE;
+        w2 = (pick == 2 || !c2) ? 0 : w2 + PT_VOTE_AGE;
+        w3 = (pick == 3 || !c3) ? 0 : w3 + PT_VOTE_AGE;
+        if (pick == 0) {
+          if (stt == 0) trav_node_step<INST, COUNT>(S, T, st, ovf, tc);
+        } else if (stt == pick) {
+          trav_leaf<INST, COUNT>(S, T, st, ovf, tc);
+          T.lc = 0;
+        }
+        if (have && T.done) { io.store(myk, T); have = false; }
+        unsigned a = __ballot_sync(FULL, have);
+        if (a == 0) break;
+        if (!exhausted && __popc(a) <= 32 - PT_REFILL_MIN) break;
+      }
       continue;
     }
     for (;;) {
@@ -239,9 +289,10 @@ template <int NC, bool INST, bool COUNT>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(const __grid_constant__ DScene S, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
                                                           uint32_t n_sh, unsigned long long* counters, int* overflow) {
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
+  __shared__ float ssave[INST ? PT_SAVE_WORDS * PT_TRACE_BLOCK : 1];
   int spill[PT_MAX_STACK - PT_SMEM_STACK];
   SharedStack st;
-  st.attach(smem + threadIdx.x, spill);
+  st.attach(smem + threadIdx.x, spill, INST ? ssave + threadIdx.x : nullptr);
   TravCounters tc;
   tc.nodes = 0; tc.tris = 0;
   int ovf = 0;
@@ -342,9 +393,10 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_intersec
                                                               f4* hits, float* t_out, unsigned char* occ, uint32_t* fetch, unsigned long long* counters,
                                                               int* overflow) {
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
+  __shared__ float ssave[INST ? PT_SAVE_WORDS * PT_TRACE_BLOCK : 1];
   int spill[PT_MAX_STACK - PT_SMEM_STACK];
   SharedStack st;
-  st.attach(smem + threadIdx.x, spill);
+  st.attach(smem + threadIdx.x, spill, INST ? ssave + threadIdx.x : nullptr);
   TravCounters tc;
   tc.nodes = 0; tc.tris = 0;
   int ovf = 0;

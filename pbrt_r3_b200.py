@@ -9,3 +9,7 @@ _spec = importlib.util.spec_from_file_location("pbrt_r3_b200", os.path.join(_d, 
 _m = importlib.util.module_from_spec(_spec)
 sys.modules["pbrt_r3_b200"] = _m
 _spec.loader.exec_module(_m)
+
+if __name__ == "__main__":   # `python -m pbrt_r3_b200 scene.pbrt ...`: the reference's command line (pbrt-r3_b200/cli.py)
+    from pbrt_r3_b200.cli import main
+    sys.exit(main())
