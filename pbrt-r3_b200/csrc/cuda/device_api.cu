@@ -1185,7 +1185,7 @@ int pt_li(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint3
   std::vector<float> L((size_t)cap * st_stride(NC));
   CK(cudaMemcpy(L.data(), s->W.L, L.size() * sizeof(float), cudaMemcpyDeviceToHost));
   for (uint32_t i = 0; i < n; i++)
-    for (uint32_t c = 0; c < NC; c++) out_l[(size_t)i * NC + c] = NC == 3 ? L[(size_t)i * 4 + c] : L[(size_t)c * cap + i];
+    for (uint32_t c = 0; c < NC; c++) out_l[(size_t)i * NC + c] = L[(size_t)i * st_stride(NC) + c];  // path-major records
   int ovf = 0;
   CK(cudaMemcpy(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost));
   if (ovf) { pt_set_error("traversal stack overflow"); return 1; }

@@ -15,8 +15,10 @@
 
 namespace ptd {
 
-struct WaveState {            // all arrays have `cap` path slots; spectra: RGB = one 16-byte record {r, g, b, -} per path
-                              // (one sector per access); 60 bins = channel-major [c * cap + i] (st_load / st_store)
+struct WaveState {            // all arrays have `cap` path slots; spectra are path-major (st_load / st_store): RGB = one
+                              // 16-byte record {r, g, b, -} per path, 60 bins = 240 contiguous bytes per path (15 x 16-byte
+                              // accesses, whole sectors: the path ids of a shading bin are scattered, so a channel-major
+                              // layout costs one 32-byte sector per FLOAT)
   uint32_t cap;
   uint32_t seg_cap;           // waves in flight own disjoint segments of the slots: segment = path id / seg_cap (render_waves)
   uint32_t nseg;
@@ -228,8 +230,14 @@ template <int NC> PT_HD Sp<NC> st_load(const float* a, uint32_t cap, uint32_t i)
     r.c[0] = v.x; r.c[1] = v.y; r.c[NC - 1] = v.z;
     return r;
   }
+  static_assert(NC == 3 || NC % 4 == 0, "spectral state records are read as 16-byte vectors");
+  const f4* p = reinterpret_cast<const f4*>(a + (size_t)i * NC);
 #pragma unroll
-  for (int c = 0; c < NC; c++) r.c[c] = a[(size_t)c * cap + i];
+  for (int k = 0; k < NC / 4; k++) {
+    f4 v = p[k];
+    r.c[4 * k] = v.x; r.c[4 * k + 1] = v.y; r.c[4 * k + 2] = v.z; r.c[4 * k + 3] = v.w;
+  }
+  (void)cap;
   return r;
 }
 template <int NC> PT_HD void st_store(float* a, uint32_t cap, uint32_t i, const Sp<NC>& v) {
@@ -237,8 +245,10 @@ template <int NC> PT_HD void st_store(float* a, uint32_t cap, uint32_t i, const 
     reinterpret_cast<f4*>(a)[i] = mk4(v.c[0], v.c[1], v.c[NC - 1], 0.0f);
     return;
   }
+  f4* p = reinterpret_cast<f4*>(a + (size_t)i * NC);
 #pragma unroll
-  for (int c = 0; c < NC; c++) a[(size_t)c * cap + i] = v.c[c];
+  for (int k = 0; k < NC / 4; k++) p[k] = mk4(v.c[4 * k], v.c[4 * k + 1], v.c[4 * k + 2], v.c[4 * k + 3]);
+  (void)cap;
 }
 
 #if defined(__CUDA_ARCH__)

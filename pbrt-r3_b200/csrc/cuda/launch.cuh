@@ -19,3 +19,8 @@
 #ifndef PT_SHADE_MINBLOCKS
 #define PT_SHADE_MINBLOCKS 4
 #endif
+// 60-bin spectra: three live spectra are 180 registers; at the RGB kernels' 128-register cap the spectral shade kernels
+// spill 2.2 KB per thread, so they trade occupancy for registers (255 registers, 2 CTAs / SM)
+#ifndef PT_SHADE_MINBLOCKS_SPECTRAL
+#define PT_SHADE_MINBLOCKS_SPECTRAL 2
+#endif

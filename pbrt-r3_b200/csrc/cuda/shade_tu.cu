@@ -12,7 +12,7 @@ namespace ptd {
 
 // One shade kernel per shading class; the bin size is read on the device (no host round trip between trace and shade).
 template <int NC, int CLS>
-__global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_SHADE_MINBLOCKS) k_shade(const __grid_constant__ DScene S, WaveState W, Queues Q, unsigned long long* vertex_counter) {
+__global__ void __launch_bounds__(PT_SHADE_BLOCK, NC == 3 ? PT_SHADE_MINBLOCKS : PT_SHADE_MINBLOCKS_SPECTRAL) k_shade(const __grid_constant__ DScene S, WaveState W, Queues Q, unsigned long long* vertex_counter) {
   const uint32_t n = Q.counts[8 + CLS];
   const uint32_t* bin = Q.bins + (size_t)CLS * W.cap;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) shade_body<NC, CLS>(S, W, Q, bin[k], vertex_counter);
