@@ -1,5 +1,5 @@
-"""Throughput of the BASELINE.json configs that are not the bench line (configs[2] instanced 10 M triangles and
-configs[3] 60-bin spectral Cornell), at reduced spp so that a run takes seconds.  Prints one JSON line per config:
+"""Throughput of the BASELINE.json configs that are not the bench line (configs[2] instanced 10 M triangles,
+configs[3] 60-bin spectral Cornell, configs[4] = the instanced scene at 3840x2160: pixel-chunked waves), at reduced spp so that a run takes seconds.  Prints one JSON line per config:
 Mrays/s, Msamples/s, k_trace algorithmic-bytes fraction of the measured HBM peak (same definitions as bench.py).
 Usage: python tools/bench_configs.py [--spp3 N] [--spp4 N] [--steps K]"""
 import argparse
@@ -13,6 +13,7 @@ import pbrt_r3_b200 as P
 ap = argparse.ArgumentParser()
 ap.add_argument("--spp3", type=int, default=8)
 ap.add_argument("--spp4", type=int, default=16)
+ap.add_argument("--spp5", type=int, default=2)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--only", default="")
 args = ap.parse_args()
@@ -49,3 +50,6 @@ if args.only in ("", "3"):
         P.scenes.instanced_blobs(n_instances=1000, n_sub=5, res=(1920, 1080), spp=args.spp3, maxdepth=8, n_lights=256), args.spp3)
 if args.only in ("", "4"):
     run("configs[3]: 60-bin SampledSpectrum Cornell box 512x512", P.scenes.cornell_box(res=512, spp=args.spp4), args.spp4, spectrum="sampled")
+if args.only in ("", "5"):
+    run("configs[4]: the instanced scene at 3840x2160 (8.3 M sample pixels: waves are pixel chunks), one GPU's share at reduced spp",
+        P.scenes.instanced_blobs(n_instances=1000, n_sub=5, res=(3840, 2160), spp=args.spp5, maxdepth=8, n_lights=256), args.spp5)
