@@ -254,14 +254,19 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes * args.steps / (trace_ms / 1e3) / 1e9 if trace_ms > 0 else 0.0
+        npix = samples_per_step / max(cfg["spp"], 1)
+        wave_m = npix * max(1, min(cfg["spp"], int((args.wave_paths or (4 << 20)) // max(npix, 1)))) / 1e6   # paths per wave, millions
+        nseg = args.wave_segments or 6
         value = rays_all * args.steps / t_steps / 1e6
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * t_steps / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "msamples_per_s": samples_all * args.steps / t_steps / 1e6,
             "config": {"workload": workload_name(cfg), "parallelism": "spp-sharded x%d, scene replicated, NCCL film reduce" % world,
-                       "spp_per_gpu": cfg["spp"], "l2_policy": "inputs larger than L2: per step %.0f MB of path state + %.0f MB of BVH/triangles are streamed"
-                       % (samples_per_step / max(cfg["spp"], 1) * 3 * 200 / 1e6, (2 * (cfg["grid_n"] - 1) ** 2) * (48 + 48 + 32) / 1e6)},
+                       "spp_per_gpu": cfg["spp"], "waves_in_flight": nseg,
+                       "l2_policy": "inputs larger than L2 (126 MB): every bounce streams the path state of the waves in flight (%.1f GB: %d waves x %.2f M paths x ~270 B) "
+                                    "and walks %.0f MB of BVH nodes + triangle records" % (
+                                        nseg * wave_m * 270 / 1e3, nseg, wave_m, (2 * (cfg["grid_n"] - 1) ** 2) * (48 + 48 + 32) / 1e6)},
             "e2e": {"value": rays_all * args.steps / t_e2e / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": clocks,
