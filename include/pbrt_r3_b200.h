@@ -42,7 +42,8 @@ enum pt_material_type {       /* reference src/materials/create_material.rs:20-7
 enum pt_light_type {          /* reference src/lights/create_light.rs:13-54 */
   PT_LIGHT_AREA = 0,          /* lights/diffuse.rs  (one per emissive triangle) */
   PT_LIGHT_POINT = 1,         /* lights/point.rs    */
-  PT_LIGHT_DISTANT = 2        /* lights/distant.rs  */
+  PT_LIGHT_DISTANT = 2,       /* lights/distant.rs  */
+  PT_LIGHT_SPOT = 3           /* lights/spot.rs     */
 };
 
 enum pt_sampler_type {        /* reference src/samplers/create_sampler.rs:12-33 */
@@ -95,11 +96,19 @@ typedef struct pt_material {
 typedef struct pt_light {
   int32_t type;               /* pt_light_type */
   int32_t spectrum;           /* area: Lemit = L*scale | point: I*scale | distant: L*scale (spectrum index) */
-  int32_t tri;                /* area: triangle index; else -1 */
+  int32_t tri;                /* area: triangle index; spot: index into pt_scene_desc.spots; else -1 */
   int32_t two_sided;          /* area: DiffuseAreaLight.two_sided (lights/diffuse.rs:178) */
-  float v[3];                 /* point: p_light (world) | distant: w_light (world, normalised) */
+  float v[3];                 /* point, spot: p_light (world) | distant: w_light (world, normalised) */
   float pad;
 } pt_light;
+
+/* SpotLight extras (lights/spot.rs:5-56): falloff(w) looks at the z component of normalize(world_to_light * w). */
+typedef struct pt_spot {
+  float w2l[9];               /* upper 3x3 of world_to_light, row-major */
+  float cos_total_width;      /* cos(radians(coneangle)), host libm like the reference */
+  float cos_falloff_start;    /* cos(radians(coneangle - conedeltaangle)) */
+  float pad;
+} pt_spot;
 
 /* An ObjectInstance: a TransformedPrimitive over object `object`
  * (core/primitive/transformed_primitive.rs:26-46).  m = instance-to-world, row-major m[4*r+c]. */
@@ -186,6 +195,8 @@ typedef struct pt_scene_desc {
   uint32_t n_emitters_only;   /* area lights of INSTANCED shapes: they emit when hit but are never sampled
                                  (scene_context.rs:1296-1299); stored at lights[n_lights ..] */
   const pt_light* lights;     /* n_lights + n_emitters_only records */
+  uint32_t n_spots;
+  const pt_spot* spots;
 
   pt_camera camera;
   pt_film film;

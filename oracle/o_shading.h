@@ -789,6 +789,23 @@ inline bool light_sample_li(const pt_scene_desc* d, Float world_radius, int li, 
     out->wi = normalize(v - it.p);
     out->pdf = 1.0f;
     pl.p = v;
+  } else if (L.type == PT_LIGHT_SPOT) {  // spot.rs:62-80, falloff :44-57
+    const pt_spot& S = d->spots[L.tri];
+    Vec3 wi = normalize(v - it.p);
+    Vec3 w = -wi;
+    Vec3 wl = normalize(Vec3(S.w2l[0] * w.x + S.w2l[1] * w.y + S.w2l[2] * w.z, S.w2l[3] * w.x + S.w2l[4] * w.y + S.w2l[5] * w.z,
+                             S.w2l[6] * w.x + S.w2l[7] * w.y + S.w2l[8] * w.z));
+    Float ct = wl.z, fall;
+    if (ct < S.cos_total_width) fall = 0.0f;
+    else if (ct >= S.cos_falloff_start) fall = 1.0f;
+    else {
+      Float delta = (ct - S.cos_total_width) / (S.cos_falloff_start - S.cos_total_width);
+      fall = (delta * delta) * (delta * delta);
+    }
+    out->li = Spec<NC>::load(d->spectra + (size_t)L.spectrum * NC) * (fall / distance_squared(v, it.p));
+    out->wi = wi;
+    out->pdf = 1.0f;
+    pl.p = v;
   } else {  // distant.rs:62-80
     out->li = Spec<NC>::load(d->spectra + (size_t)L.spectrum * NC);
     out->wi = v;
@@ -819,6 +836,10 @@ inline Spec<NC> light_power(const pt_scene_desc* d, Float world_radius, int li) 
   Spec<NC> s = Spec<NC>::load(d->spectra + (size_t)L.spectrum * NC);
   if (L.type == PT_LIGHT_AREA) return s * ((L.two_sided ? 2.0f : 1.0f) * tri_area(d, L.tri) * PI);
   if (L.type == PT_LIGHT_POINT) return s * (4.0f * PI);
+  if (L.type == PT_LIGHT_SPOT) {  // spot.rs:82-85 (minus, unlike pbrt-v3's plus)
+    const pt_spot& S = d->spots[L.tri];
+    return s * (2.0f * PI * (1.0f - 0.5f * (S.cos_falloff_start - S.cos_total_width)));
+  }
   return s * (PI * world_radius * world_radius);
 }
 

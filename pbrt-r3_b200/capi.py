@@ -12,7 +12,7 @@ DATA_DIR = os.path.join(HERE, "data")
 
 PT_ABI_VERSION = 2
 PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MIRROR = -1, 0, 1, 2, 3, 4
-PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT = 0, 1, 2
+PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT = 0, 1, 2, 3
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
 PT_SPECTRUM_RGB, PT_SPECTRUM_SAMPLED = 0, 1
@@ -31,6 +31,10 @@ class pt_material(C.Structure):
 class pt_light(C.Structure):
     _fields_ = [("type", C.c_int32), ("spectrum", C.c_int32), ("tri", C.c_int32), ("two_sided", C.c_int32),
                 ("v", C.c_float * 3), ("pad", C.c_float)]
+
+
+class pt_spot(C.Structure):
+    _fields_ = [("w2l", C.c_float * 9), ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float), ("pad", C.c_float)]
 
 
 class pt_instance(C.Structure):
@@ -68,7 +72,7 @@ class pt_scene_desc(C.Structure):
                 ("n_objects", C.c_uint32), ("obj_first", u32p), ("prims", i32p), ("n_instances", C.c_uint32),
                 ("instances", C.POINTER(pt_instance)),
                 ("n_materials", C.c_uint32), ("materials", C.POINTER(pt_material)),
-                ("n_lights", C.c_uint32), ("n_emitters_only", C.c_uint32), ("lights", C.POINTER(pt_light)),
+                ("n_lights", C.c_uint32), ("n_emitters_only", C.c_uint32), ("lights", C.POINTER(pt_light)), ("n_spots", C.c_uint32), ("spots", C.POINTER(pt_spot)),
                 ("camera", pt_camera), ("film", pt_film), ("sampler", pt_sampler), ("integrator", pt_integrator), ("accel", pt_accel)]
 
 

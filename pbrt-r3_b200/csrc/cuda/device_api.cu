@@ -297,6 +297,9 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(s->bufs.upload(mats.data(), mats.size(), &H.materials));
   CK(s->bufs.upload(alpha.data(), alpha.size(), &H.alpha));
   CK(s->bufs.upload(D->lights, (size_t)D->n_lights + D->n_emitters_only, &H.lights));
+  CK(s->bufs.upload(D->spots, D->n_spots, &H.spots));
+  for (uint32_t i = 0; i < D->n_lights; i++)
+    if (D->lights[i].type == PT_LIGHT_SPOT && (D->lights[i].tri < 0 || (uint32_t)D->lights[i].tri >= D->n_spots)) { pt_set_error("spot light index out of range"); return 1; }
 
   // ---- sampler (halton.rs:57-101, sobol.rs:18-31) ---------------------------------------------------------------
   SamplerDev& SD = H.sampler;
@@ -421,6 +424,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
             float area = 0.5f * len3(cross3(a, b));
             k = (L.two_sided ? 2.0f : 1.0f) * area * PT_PI;
           } else if (L.type == PT_LIGHT_POINT) k = 4.0f * PT_PI;
+          else if (L.type == PT_LIGHT_SPOT) k = 2.0f * PT_PI * (1.0f - 0.5f * (D->spots[L.tri].cos_falloff_start - D->spots[L.tri].cos_total_width));  // spot.rs:82-85
           else k = PT_PI * H.world_radius * H.world_radius;
           const float* w = D->xyz_weights + 60;
           float acc = w[0] * (sp[0] * k);

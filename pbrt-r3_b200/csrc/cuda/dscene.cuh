@@ -86,6 +86,7 @@ struct DScene {
   const int32_t* tri_light;
   const pt_material* materials;
   const pt_light* lights;
+  const pt_spot* spots;      // SpotLight extras, indexed by pt_light.tri
   const float* spectra;
   const float* alpha;        // per material: roughness_to_alpha applied on the HOST with libm logf: [n_materials][2]
   float xyz_w[180];

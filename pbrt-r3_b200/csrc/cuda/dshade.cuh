@@ -147,6 +147,24 @@ PT_HDN bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSa
     out->wi = norm3(v - it.p);
     out->pdf = 1.0f;
     lp = v;
+  } else if (L.type == PT_LIGHT_SPOT) {  // lights/spot.rs:44-57 (falloff), 62-80 (sample_li)
+    f3 v = mk3(L.v[0], L.v[1], L.v[2]);
+    const pt_spot& P = S.spots[L.tri];
+    f3 wi = norm3(v - it.p);
+    f3 w = -wi;
+    f3 wl = norm3(mk3(P.w2l[0] * w.x + P.w2l[1] * w.y + P.w2l[2] * w.z, P.w2l[3] * w.x + P.w2l[4] * w.y + P.w2l[5] * w.z,
+                      P.w2l[6] * w.x + P.w2l[7] * w.y + P.w2l[8] * w.z));
+    float ct = wl.z, fall;
+    if (ct < P.cos_total_width) fall = 0.0f;
+    else if (ct >= P.cos_falloff_start) fall = 1.0f;
+    else {
+      float delta = (ct - P.cos_total_width) / (P.cos_falloff_start - P.cos_total_width);
+      fall = (delta * delta) * (delta * delta);
+    }
+    out->li = sp_load<NC>(S.spectra + (size_t)L.spectrum * NC) * (fall / dist2(v, it.p));
+    out->wi = wi;
+    out->pdf = 1.0f;
+    lp = v;
   } else {
     f3 v = mk3(L.v[0], L.v[1], L.v[2]);
     out->li = sp_load<NC>(S.spectra + (size_t)L.spectrum * NC);

@@ -32,6 +32,7 @@ const pt_options& pt_current_options();    // api_common.cpp: PbrtOptions single
 struct pt_host_scene {
   std::vector<float> spectra;
   std::vector<float> tri_p, tri_n, tri_uv, tri_s;
+  std::vector<pt_spot> spots;
   std::vector<uint32_t> tri_flags;
   std::vector<int32_t> tri_material, tri_light;
   std::vector<std::vector<int32_t>> obj_prims;  // object 0 = top level
@@ -598,8 +599,39 @@ struct Builder {
       l.type = PT_LIGHT_DISTANT;
       l.spectrum = add_spectrum(L);
       l.v[0] = w.x; l.v[1] = w.y; l.v[2] = w.z;
+    } else if (name == "spot") {  // lights/spot.rs:136-166
+      std::vector<float> I = one_spectrum(ps, "I", 1.0f), sc = one_spectrum(ps, "scale", 1.0f);
+      for (size_t k = 0; k < I.size(); k++) I[k] = I[k] * sc[k];
+      float coneangle = ps.one_float("coneangle", 30.0f);
+      float conedelta = ps.one_float("conedelta", 5.0f);
+      conedelta = ps.one_float("conedeltaangle", conedelta);
+      float from[3] = {0, 0, 0}, to[3] = {0, 0, 1};
+      ps.one_point("from", from);
+      ps.one_point("to", to);
+      V3 dir = vnorm(v3(to[0], to[1], to[2]) - v3(from[0], from[1], from[2]));
+      // Vector3f::coordinate_system (vector3.rs:72-83)
+      V3 v1 = vnorm(dir), v2;
+      if (fabsf(v1.x) > fabsf(v1.y)) v2 = vnorm(v3(-v1.z, 0.0f, v1.x));
+      else v2 = vnorm(v3(0.0f, v1.z, -v1.y));
+      V3 v3_ = vnorm(vcross(v1, v2));
+      M4 dz = M4::identity();
+      dz.m[0] = v2.x; dz.m[1] = v2.y; dz.m[2] = v2.z;
+      dz.m[4] = v3_.x; dz.m[5] = v3_.y; dz.m[6] = v3_.z;
+      dz.m[8] = v1.x; dz.m[9] = v1.y; dz.m[10] = v1.z;
+      Xf l2w = ctm * x_translate(from[0], from[1], from[2]) * xinverse(x_from_matrix(dz));
+      V3 p = m_point(l2w.m, v3(0, 0, 0));
+      pt_spot sp;
+      memset(&sp, 0, sizeof(sp));
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) sp.w2l[3 * r + c] = l2w.minv.m[4 * r + c];
+      sp.cos_total_width = cosf(radians(coneangle));
+      sp.cos_falloff_start = cosf(radians(coneangle - conedelta));
+      l.type = PT_LIGHT_SPOT;
+      l.spectrum = add_spectrum(I);
+      l.tri = (int32_t)hs->spots.size();
+      l.v[0] = p.x; l.v[1] = p.y; l.v[2] = p.z;
+      hs->spots.push_back(sp);
     } else {
-      throw ParseError("LightSource \"" + name + "\" is not supported on the GPU path (point, distant, area lights only)");
+      throw ParseError("LightSource \"" + name + "\" is not supported on the GPU path (point, spot, distant, area lights only)");
     }
     hs->lights.push_back(l);
   }
@@ -927,6 +959,8 @@ struct Builder {
     D.materials = hs->materials.data();
     D.n_lights = (uint32_t)n_sampled;
     D.n_emitters_only = (uint32_t)hs->emitters_only.size();
+    D.n_spots = (uint32_t)hs->spots.size();
+    D.spots = hs->spots.data();
     D.lights = all.data();
   }
 };

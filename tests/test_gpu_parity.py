@@ -157,6 +157,23 @@ def test_mesh_tangents(P, pair):
     assert rel_rmse(rgb, ref) <= RMSE_TOL
 
 
+def test_spot_lights(P, pair):
+    """LightSource "spot" (lights/spot.rs): radiance per sample and image vs the oracle, spatial light sampling."""
+    from test_hostcheck import spot_scene
+    hs, sc, orc = pair("spots", spot_scene(P, res=64, spp=8))
+    pix, sn = _samples(hs, 20000, 8, seed=8)
+    la = sc.li(pix, sn)
+    lb, _, _, _ = orc.li(pix, sn)
+    close = (np.abs(la - lb) <= 1e-3 * np.maximum(np.abs(lb), 1e-2)).all(1)
+    assert close.mean() > 0.999, close.mean()
+    rgb, _ = sc.render()
+    ref, _ = orc.render()
+    assert rel_rmse(rgb, ref) <= RMSE_TOL
+    wb = orc.world_bound()
+    pts = np.random.RandomState(2).uniform(wb[:3], wb[3:], (100, 3)).astype(np.float32)
+    assert np.allclose(sc.light_distribution(pts), orc.light_distribution(pts), rtol=2e-6, atol=0)
+
+
 def test_light_distribution_bit_exact(P, pair):
     for name, txt in [("cornell_halton", P.scenes.cornell_box(res=200, spp=64)), ("cornell_lights", P.scenes.cornell_box(res=64, spp=4, extra_lights=True))]:
         hs, sc, orc = pair(name, txt)

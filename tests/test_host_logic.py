@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(P):
 
 
 def test_ctypes_mirror_matches_header(P):
-    names = ["pt_material", "pt_light", "pt_instance", "pt_camera", "pt_film", "pt_sampler", "pt_integrator", "pt_accel", "pt_scene_desc",
+    names = ["pt_material", "pt_light", "pt_spot", "pt_options", "pt_instance", "pt_camera", "pt_film", "pt_sampler", "pt_integrator", "pt_accel", "pt_scene_desc",
              "pt_render_opts", "pt_stats"]
     src = '#include "pbrt_r3_b200.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){\n' + "".join(
         'printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in names) + 'printf("off_lights %zu\\n", offsetof(pt_scene_desc, lights));\n' \
@@ -147,6 +147,23 @@ def test_front_end_plymesh(P, tmp_path):
     (tmp_path / "s_missing.pbrt").write_text(head + 'Shape "plymesh" "string filename" ["geo/none.ply"]\nWorldEnd\n')
     with pytest.raises(P.PbrtError):
         P.HostScene.parse_file(str(tmp_path / "s_missing.pbrt"))
+
+
+def test_front_end_spot_light(P):
+    # lights/spot.rs:136-166: light_to_world = CTM * translate(from) * inverse(dir_to_z); cosines with the host libm
+    txt = ('Camera "perspective"\nWorldBegin\nTranslate 1 2 3\nLightSource "spot" "rgb I" [10 20 30] "rgb scale" [2 2 2] "point from" [0 5 0] "point to" [0 0 0] '
+           '"float coneangle" [40] "float conedeltaangle" [10]\nWorldEnd\n')
+    hs = P.HostScene.parse_string(txt)
+    d = hs.desc
+    assert d.n_lights == 1 and d.n_spots == 1
+    l, sp = d.lights[0], d.spots[0]
+    assert l.type == P.capi.PT_LIGHT_SPOT and l.tri == 0 and np.allclose(list(l.v), [1, 7, 3])
+    assert np.allclose(np.ctypeslib.as_array(d.spectra, (d.n_spectra * 3,))[3 * l.spectrum: 3 * l.spectrum + 3], [20, 40, 60])
+    assert sp.cos_total_width == np.float32(np.cos(np.float32(40.0) * np.float32(np.pi / 180))) or abs(sp.cos_total_width - np.cos(np.radians(40.0))) < 1e-7
+    assert abs(sp.cos_falloff_start - np.cos(np.radians(30.0))) < 1e-7
+    w2l = np.array(list(sp.w2l)).reshape(3, 3)
+    assert np.allclose(w2l @ np.array([0, -1, 0.0]), [0, 0, 1], atol=1e-6)       # the axis from -> to is +z of the light
+    assert np.allclose(w2l @ w2l.T, np.eye(3), atol=1e-6)
 
 
 def test_front_end_instances(P):

@@ -130,6 +130,29 @@ def test_hostcheck_mesh_tangents(HC):
     assert not np.array_equal(sc.li(pix, np.zeros(3, np.int32)), HC.Scene(plain).li(pix, np.zeros(3, np.int32)))
 
 
+def spot_scene(P, res=32, spp=8):
+    """Cornell box lit by two spot lights (one with a wide falloff band, one narrow, aimed at a wall) next to the area light."""
+    txt = P.scenes.cornell_box(res=res, spp=spp, maxdepth=5, materials="mixed")
+    spots = ('LightSource "spot" "rgb I" [400000 380000 300000] "point from" [278 540 280] "point to" [200 0 300] "float coneangle" [35] "float conedeltaangle" [20]\n'
+             'LightSource "spot" "rgb I" [200000 100000 100000] "point from" [100 300 100] "point to" [556 200 400] "float coneangle" [15] "float conedeltaangle" [2]\n')
+    assert "WorldBegin\n" in txt
+    return txt.replace("WorldBegin\n", "WorldBegin\n" + spots, 1)
+
+
+def test_hostcheck_spot_lights(HC):
+    hs, sc, orc = _cmp_li(HC, spot_scene(HC), 3000, 8, 0.999)
+    assert hs.desc.n_spots == 2
+    rgb, st = sc.render(collect_counters=1)
+    ref, so = orc.render(threads=2)
+    assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5
+    for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+        assert st[k] == so[k], k
+    # the "power" light strategy uses SpotLight::power (spot.rs:82-85)
+    hp = HC.HostScene.parse_string(spot_scene(HC).replace('Integrator "path"', 'Integrator "path" "string lightsamplestrategy" ["power"]'))
+    a, b = HC.Scene(hp).render()[0], __import__("oracle_api").OracleScene(hp).render(threads=2)[0]
+    assert np.sqrt(((a - b) ** 2).mean()) / b.mean() < 1e-5
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
