@@ -751,10 +751,28 @@ struct Builder {
       else if (d == "Texture") {
         std::string n = read_string(lx), type = read_string(lx), cls = read_string(lx);
         ParamSet ps = parse_params(lx);
-        if (cls != "constant") throw ParseError("Texture class \"" + cls + "\" is not supported on the GPU path (constant only)");
-        if (type == "float") gs.float_textures[n] = ps.one_float("value", 1.0f);
-        else if (type == "spectrum" || type == "color") gs.spec_textures[n] = one_spectrum(ps, "value", 1.0f);
-        else throw ParseError("Texture type \"" + type + "\" unknown");
+        // Textures whose value does not depend on the surface point fold to constants on the host: "constant", and
+        // "scale" / "mix" of such textures (textures/{constant,scale,mix}.rs; same f32 arithmetic as their evaluate()).
+        if (cls != "constant" && cls != "scale" && cls != "mix")
+          throw ParseError("Texture class \"" + cls + "\" is not supported on the GPU path (constant, scale, mix of constants)");
+        if (type != "float" && type != "spectrum" && type != "color") throw ParseError("Texture type \"" + type + "\" unknown");
+        static const ParamSet empty_mat;
+        TP tp{&ps, &empty_mat};
+        const bool is_float = type == "float";
+        if (cls == "constant") {
+          if (is_float) gs.float_textures[n] = ps.one_float("value", 1.0f);
+          else gs.spec_textures[n] = one_spectrum(ps, "value", 1.0f);
+        } else if (is_float) {
+          float t1 = tp_float(tp, "tex1", 1.0f), t2 = tp_float(tp, "tex2", 1.0f);
+          if (cls == "scale") gs.float_textures[n] = t1 * t2;
+          else { float amt = tp_float(tp, "amount", 0.5f); gs.float_textures[n] = t1 * (1.0f - amt) + t2 * amt; }
+        } else {
+          std::vector<float> t1 = tp_spectrum(tp, "tex1", spec.constant(1.0f)), t2 = tp_spectrum(tp, "tex2", spec.constant(1.0f));
+          std::vector<float> r(t1.size());
+          if (cls == "scale") { for (size_t k = 0; k < r.size(); k++) r[k] = t1[k] * t2[k]; }
+          else { float amt = tp_float(tp, "amount", 0.5f); for (size_t k = 0; k < r.size(); k++) r[k] = t1[k] * (1.0f - amt) + t2[k] * amt; }
+          gs.spec_textures[n] = r;
+        }
       }
       else if (d == "LightSource") { std::string n = read_string(lx); ParamSet ps = parse_params(lx); light_source(n, ps); }
       else if (d == "AreaLightSource") { gs.area_light_name = read_string(lx); gs.area_light_params = parse_params(lx); }

@@ -149,6 +149,29 @@ def test_front_end_plymesh(P, tmp_path):
         P.HostScene.parse_file(str(tmp_path / "s_missing.pbrt"))
 
 
+def test_front_end_constant_foldable_textures(P):
+    # textures/{constant,scale,mix}.rs: value1 * value2 ; t1 * (1 - amt) + t2 * amt, folded on the host
+    txt = ('Camera "perspective"\nWorldBegin\n'
+           'Texture "a" "spectrum" "constant" "rgb value" [0.2 0.4 0.8]\nTexture "f" "float" "constant" "float value" [0.25]\n'
+           'Texture "s" "spectrum" "scale" "texture tex1" "a" "rgb tex2" [0.5 0.5 0.25]\n'
+           'Texture "m" "spectrum" "mix" "texture tex1" "a" "texture tex2" "s" "texture amount" "f"\n'
+           'Texture "r" "float" "scale" "texture tex1" "f" "float tex2" [0.4]\n'
+           'Material "plastic" "texture Kd" "m" "texture Ks" "s" "texture roughness" "r"\n'
+           'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
+    hs = P.HostScene.parse_string(txt)
+    d = hs.desc
+    m = d.materials[0]
+    sp = np.ctypeslib.as_array(d.spectra, (d.n_spectra * 3,)).reshape(-1, 3)
+    f = np.float32
+    a, t2 = np.array([0.2, 0.4, 0.8], f), np.array([0.5, 0.5, 0.25], f)
+    s_ = a * t2
+    mix = a * (f(1.0) - f(0.25)) + s_ * f(0.25)
+    assert np.array_equal(sp[m.kd], mix) and np.array_equal(sp[m.ks], s_)
+    assert m.uroughness == f(0.25) * f(0.4)
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(txt.replace('"spectrum" "scale"', '"spectrum" "imagemap"'))
+
+
 def test_front_end_spot_light(P):
     # lights/spot.rs:136-166: light_to_world = CTM * translate(from) * inverse(dir_to_z); cosines with the host libm
     txt = ('Camera "perspective"\nWorldBegin\nTranslate 1 2 3\nLightSource "spot" "rgb I" [10 20 30] "rgb scale" [2 2 2] "point from" [0 5 0] "point to" [0 0 0] '
