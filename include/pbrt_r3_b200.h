@@ -144,11 +144,25 @@ typedef struct pt_sampler {
   int32_t pad;
 } pt_sampler;
 
-typedef struct pt_integrator { /* integrators/path.rs:252-271 */
+enum pt_integrator_type {
+  PT_INTEGRATOR_PATH = 0,     /* integrators/path.rs */
+  PT_INTEGRATOR_AOV = 1       /* integrators/aov.rs: one closest-hit query per camera sample, a geometric quantity as colour */
+};
+enum pt_aov_target {          /* integrators/aov.rs:10-58; the targets that need ray differentials are not supported */
+  PT_AOV_DISTANCE = 0,        /* "distance": t_max / |d|                       */
+  PT_AOV_DEPTH = 1,           /* "depth":    |p - o|                           */
+  PT_AOV_N = 2,               /* "n", "ng":  0.5 n + 0.5                       */
+  PT_AOV_NS = 3,              /* "ns", "shading.n"                             */
+  PT_AOV_UV = 4,              /* "uv": (u, v, 0)                               */
+  PT_AOV_DPDUS = 5            /* "dpdus", "shading.dpdu"                       */
+};
+typedef struct pt_integrator { /* integrators/path.rs:252-271, integrators/aov.rs:192-213 */
   int32_t max_depth;
   float rr_threshold;
   int32_t light_strategy;     /* pt_light_strategy */
-  int32_t pad;
+  int32_t type;               /* pt_integrator_type */
+  int32_t aov_target;         /* pt_aov_target */
+  float aov_scale;
 } pt_integrator;
 
 typedef struct pt_accel {     /* accelerators/bvh/create_bvh_accelerator.rs:9-28 */

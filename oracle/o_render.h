@@ -166,6 +166,51 @@ struct PathTrace {  // per-sample debug record for parity tests
   int bounces = 0;
 };
 
+// AOVIntegrator::li (integrators/aov.rs:101-181) for the supported targets; RGB only
+template <int NC>
+inline Spec<NC> aov_li(Scene<NC>& sc, const Ray& r, Counters* cnt, PathTrace* trace) {
+  const pt_scene_desc* d = sc.d;
+  Spec<NC> out;
+  Ray ray = r;
+  Hit h;
+  if (!sc.intersect(ray, &h, cnt)) return out;
+  SurfInt si = make_si(d, h);
+  if (trace) { trace->first_tri = h.tri; trace->first_t = h.t; }
+  const Float scale = d->integrator.aov_scale;
+  Float rgb[3] = {0, 0, 0};
+  auto v2c = [&](Vec3 v) { Vec3 c = 0.5f * v + Vec3(0.5f, 0.5f, 0.5f); rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z; };
+  switch (d->integrator.aov_target) {
+    case PT_AOV_DISTANCE: { Float dist = ray.t_max / length(ray.d); rgb[0] = rgb[1] = rgb[2] = dist; break; }
+    case PT_AOV_DEPTH: { Float dist = length(si.p - ray.o); rgb[0] = rgb[1] = rgb[2] = dist; break; }
+    case PT_AOV_N: v2c(si.n); break;
+    case PT_AOV_NS: v2c(si.sn); break;
+    case PT_AOV_UV: {
+      Vec2 uv[3];
+      tri_uvs(d, h.tri, uv);
+      rgb[0] = h.b0 * uv[0].x + h.b1 * uv[1].x + h.b2 * uv[2].x;  // triangle.rs:353-354: b0*uv[0] + b1*uv[1] + b2*uv[2]
+      rgb[1] = h.b0 * uv[0].y + h.b1 * uv[1].y + h.b2 * uv[2].y;
+      rgb[2] = 0.0f;
+      break;
+    }
+    default: v2c(si.sdpdu); break;
+  }
+  for (int c = 0; c < 3 && c < NC; c++) {
+    Float v = rgb[c];
+    v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);  // Spectrum::clamp(0, 1)
+    out.c[c] = v * scale;
+  }
+  return out;
+}
+
+template <int NC>
+inline Spec<NC> path_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace);
+// SamplerIntegrator::li of the scene's integrator
+template <int NC>
+inline Spec<NC> integrator_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace) {
+  if (sc.d->integrator.type == PT_INTEGRATOR_AOV) return aov_li(sc, r, cnt, trace);
+  return path_li(sc, r, sampler, cnt, trace);
+}
+
 // PathIntegrator::li (path.rs:61-241)
 template <int NC>
 inline Spec<NC> path_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace) {
@@ -377,7 +422,7 @@ inline void render(Scene<NC>& sc, int n_threads, int s0, int s1, float* out_rgb,
             cs.time = sampler.get_1d();
             Ray ray = camera_ray(d->camera, cs);
             cnt.camera_rays++;
-            Spec<NC> l = path_li(sc, ray, sampler, &cnt, nullptr);
+            Spec<NC> l = integrator_li(sc, ray, sampler, &cnt, nullptr);
             l = validate_radiance(d, l);
             if (s >= s0 && s < s1) ft.add_sample(cs.p_film, l, 1.0f);
           }

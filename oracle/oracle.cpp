@@ -51,7 +51,7 @@ static void do_li(Scene<NC>& S, const int32_t* pixel_xy, const int32_t* sample_n
     cs.time = sampler.get_1d();
     Ray ray = camera_ray(S.d->camera, cs);
     PathTrace tr;
-    Spec<NC> l = path_li(S, ray, sampler, &cnt, &tr);
+    Spec<NC> l = integrator_li(S, ray, sampler, &cnt, &tr);
     for (int k = 0; k < NC; k++) out_l[(size_t)i * NC + k] = l.c[k];
     if (first_tri) first_tri[i] = tr.first_tri;
     if (first_t) first_t[i] = tr.first_t;

@@ -536,7 +536,11 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     T->trace_rays += total;
     uint32_t n_ext = counts[0];
     CK(cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream));  // queue counters + the trace fetch counter
-    if (n_ext > 0) {
+    if (n_ext > 0 && s->h.integrator.type == PT_INTEGRATOR_AOV) {  // aov.rs: no bounces, nothing is pushed
+      PT_LAUNCH(grid_for(s, n_ext, 128, 8), 128, s->stream, k_aov<NC>)(s->h, W, Q.ext, n_ext);
+      CK(cudaGetLastError());
+      T->launches++;
+    } else if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
       for (int c = 0; c < CL_COUNT; c++)
@@ -658,7 +662,8 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? (4u << 20) : (1u << 19));
   uint32_t npix_total = s->pix_n;
   int ns_total = std::max(s_end - s_begin, 0);
-  if (npix_total == 0 || ns_total == 0 || s->h.n_lights == 0) return 0;  // no lights: li() returns zero (path.rs:71-75) and no sample is added... see below
+  const bool is_path = s->h.integrator.type == PT_INTEGRATOR_PATH;
+  if (npix_total == 0 || ns_total == 0 || (is_path && s->h.n_lights == 0)) return 0;  // no lights: PathIntegrator::li returns zero (path.rs:71-75)
   uint32_t pix_chunk, ns_wave;
   if ((uint64_t)npix_total * (uint64_t)ns_total <= cap) { pix_chunk = npix_total; ns_wave = (uint32_t)ns_total; }
   else if (npix_total <= cap) { pix_chunk = npix_total; ns_wave = std::max(1u, cap / npix_total); }
@@ -799,7 +804,11 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     if (timed) cudaEventRecord(e2, s->stream);
     cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream);  // queue counters + the trace fetch counter
     if ((rc = (cudaMemsetAsync(Q.counts + 16, 0, PT_MAX_SEGMENTS * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }
-    if (n_ext > 0) {
+    if (n_ext > 0 && s->h.integrator.type == PT_INTEGRATOR_AOV) {  // aov.rs: no bounces, nothing is pushed
+      PT_LAUNCH(grid_for(s, n_ext, 128, 8), 128, s->stream, k_aov<NC>)(s->h, W, Q.ext, n_ext);
+      if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_aov launch failed"); break; }
+      T.launches++;
+    } else if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
       for (int c = 0; c < CL_COUNT; c++)
@@ -850,7 +859,7 @@ int render_waves_random(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   bool count = o && o->collect_counters;
   if (build_pixlist(s, shard_i, shard_n, 16)) return 1;  // render tiles are 16x16 (sampler.rs:267)
   const uint32_t n_tiles = (uint32_t)(s->tiles_host.size() / 3);
-  if (n_tiles == 0 || spp <= 0 || s->h.n_lights == 0) return 0;
+  if (n_tiles == 0 || spp <= 0 || (s->h.integrator.type == PT_INTEGRATOR_PATH && s->h.n_lights == 0)) return 0;
   {  // RNG::new_sequence(tile number) (core/rng.rs:21-33)
     std::vector<uint64_t> init(n_tiles);
     for (uint32_t t = 0; t < n_tiles; t++) {
@@ -1148,7 +1157,7 @@ static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_
   if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<3>)(s->h, s->W, s->Q, pxy, sn, n);
   else PT_LAUNCH(grid_for(s, n, 128, 8), 128, s->stream, k_raygen_list<PT_NCS>)(s->h, s->W, s->Q, pxy, sn, n);
   CK(cudaGetLastError());
-  if (bounce && s->h.n_lights > 0) {
+  if (bounce && (s->h.n_lights > 0 || s->h.integrator.type != PT_INTEGRATOR_PATH)) {
     WaveTotals T;
     int rc = s->h.n_channels == 3 ? run_bounces<3>(s, n, false, false, &T) : run_bounces<PT_NCS>(s, n, false, false, &T);
     if (rc) return rc;

@@ -485,6 +485,44 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   push_next(W, Q, i);
 }
 
+// AOVIntegrator::li (integrators/aov.rs:101-181) for path slot i after its camera ray was traced: a geometric quantity
+// of the first hit as colour, clamped to [0, 1] and scaled; black on a miss.  RGB only.
+template <int NC>
+PT_HD void aov_body(const DScene& S, WaveState& W, uint32_t i) {
+  f4 ro4 = W.ray_o[i], rd4 = W.ray_d[i], h4 = W.hit[i];
+  const int tri = (int)fbits(h4.w);
+  Sp<NC> out = sp_const<NC>(0.0f);
+  if (tri >= 0) {
+    f3 ro = xyz(ro4), rd = xyz(rd4);
+    const int inst = S.has_instances ? W.hit_inst[i] : -1;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    const int target = S.integrator.aov_target;
+    if (target == PT_AOV_DISTANCE) { r = g = b = ro4.w / len3(rd); }
+    else if (target == PT_AOV_UV) {
+      f2 uv0 = mk2(0.0f, 0.0f), uv1 = mk2(1.0f, 0.0f), uv2 = mk2(1.0f, 1.0f);
+      if ((ldg(S.tri_flags + tri) & PT_TRI_HAS_UV) && S.tri_uv) {
+        const float* q = S.tri_uv + (size_t)tri * 6;
+        uv0 = mk2(ldg(q), ldg(q + 1)); uv1 = mk2(ldg(q + 2), ldg(q + 3)); uv2 = mk2(ldg(q + 4), ldg(q + 5));
+      }
+      r = h4.x * uv0.x + h4.y * uv1.x + h4.z * uv2.x;
+      g = h4.x * uv0.y + h4.y * uv1.y + h4.z * uv2.y;
+    } else {
+      SurfD si = make_surface(S, tri, inst, ro, rd, rd4.w, h4.x, h4.y, h4.z);
+      if (target == PT_AOV_DEPTH) { r = g = b = len3(si.p - ro); }
+      else {
+        f3 v = target == PT_AOV_N ? si.n : (target == PT_AOV_NS ? si.sn : si.sdpdu);
+        f3 c = 0.5f * v + mk3(0.5f, 0.5f, 0.5f);
+        r = c.x; g = c.y; b = c.z;
+      }
+    }
+    const float sc = S.integrator.aov_scale;
+    out.c[0] = clampf(r, 0.0f, 1.0f) * sc;
+    out.c[1] = clampf(g, 0.0f, 1.0f) * sc;
+    out.c[NC > 2 ? 2 : 0] = clampf(b, 0.0f, 1.0f) * sc;
+  }
+  st_store<NC>(W.L, W.cap, i, out);
+}
+
 // MIS ray resolution: the BSDF-sampled ray contributes only if it hits the sampled light (pointer equality in the
 // reference, sample_lights.rs:431-441) on its emitting side.
 template <int NC>

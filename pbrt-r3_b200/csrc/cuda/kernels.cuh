@@ -340,6 +340,12 @@ __global__ void k_raygen_list(const __grid_constant__ DScene S, WaveState W, Que
     raygen_body<NC>(S, W, Q, i, pixel_xy[2 * i], pixel_xy[2 * i + 1], sample_num[i]);
 }
 
+// Integrator "aov": the whole li() after the camera ray's closest-hit query
+template <int NC>
+__global__ void k_aov(const __grid_constant__ DScene S, WaveState W, const uint32_t* __restrict__ ids, uint32_t n) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) aov_body<NC>(S, W, ids[k]);
+}
+
 template <int NC>
 __global__ void k_finish(const __grid_constant__ DScene S, WaveState W, uint32_t base, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) finish_body<NC>(S, W, base + i);

@@ -925,8 +925,26 @@ struct Builder {
     if (pt_current_options().quick_render && S.type != PT_SAMPLER_RANDOM) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
 
     // Integrator (integrators/path.rs:252-271)
-    if (integrator_name != "path") throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path only)");
+    if (integrator_name != "path" && integrator_name != "aov")
+      throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path, aov)");
     pt_integrator& I = D.integrator;
+    I.type = PT_INTEGRATOR_PATH;
+    if (integrator_name == "aov") {  // integrators/aov.rs:192-213, targets :36-58
+      I.type = PT_INTEGRATOR_AOV;
+      std::string t = integrator_params.one_string("target", "uv");
+      I.aov_scale = integrator_params.one_float("scale", 1.0f);
+      if (t == "distance") I.aov_target = PT_AOV_DISTANCE;
+      else if (t == "depth") I.aov_target = PT_AOV_DEPTH;
+      else if (t == "n" || t == "ng") I.aov_target = PT_AOV_N;
+      else if (t == "ns" || t == "shading.n") I.aov_target = PT_AOV_NS;
+      else if (t == "uv") I.aov_target = PT_AOV_UV;
+      else if (t == "dpdus" || t == "shading.dpdu") I.aov_target = PT_AOV_DPDUS;
+      else if (t == "rdxc" || t == "rdyc" || t == "drodx" || t == "drddx" || t == "dpdx" || t == "dpdy" || t == "dpdu" || t == "dpdv" || t == "dstdx" ||
+               t == "dstdy" || t == "duvdx" || t == "dpdvs" || t == "shading.dpdv")
+        throw ParseError("AOV target \"" + t + "\" is not supported on the GPU path (distance, depth, n, ns, uv, dpdus)");
+      else throw ParseError("AOV target \"" + t + "\" unknown.");
+      if (spec.n_channels() != 3) throw ParseError("Integrator \"aov\" is only supported with RGB spectra");
+    }
     I.max_depth = integrator_params.one_int("maxdepth", 5);
     I.rr_threshold = integrator_params.one_float("rrthreshold", 1.0f);
     std::string ls = integrator_params.one_string("lightsamplestrategy", "spatial");

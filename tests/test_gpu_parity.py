@@ -174,6 +174,23 @@ def test_spot_lights(P, pair):
     assert np.allclose(sc.light_distribution(pts), orc.light_distribution(pts), rtol=2e-6, atol=0)
 
 
+@pytest.mark.parametrize("target", ["distance", "depth", "n", "ns", "uv", "dpdus"])
+def test_aov_integrator(P, pair, target):
+    """Integrator "aov" (integrators/aov.rs): per-sample values bit-exact vs the oracle (no transcendental functions on
+    this path), image RMSE, on a scene with normals / tangents and on an instanced one."""
+    from test_hostcheck import aov_scene
+    for instanced in (False, True):
+        hs, sc, orc = pair("aov_%s_%d" % (target, instanced), aov_scene(P, target, 0.002 if target in ("distance", "depth") else 0.75, res=72, spp=4, instanced=instanced))
+        pix, sn = _samples(hs, 20000, 4, seed=12)
+        la = sc.li(pix, sn)
+        lb = orc.li(pix, sn)[0]
+        assert np.array_equal(la.view(np.uint32), lb.view(np.uint32)), np.abs(la - lb).max()
+        rgb, st = sc.render()
+        ref, _ = orc.render()
+        assert rel_rmse(rgb, ref) <= 1e-5
+        assert st["shadow_rays"] == 0 and st["regular_rays"] == st["camera_rays"]
+
+
 def test_light_distribution_bit_exact(P, pair):
     for name, txt in [("cornell_halton", P.scenes.cornell_box(res=200, spp=64)), ("cornell_lights", P.scenes.cornell_box(res=64, spp=4, extra_lights=True))]:
         hs, sc, orc = pair(name, txt)

@@ -172,6 +172,18 @@ def test_front_end_constant_foldable_textures(P):
         P.HostScene.parse_string(txt.replace('"spectrum" "scale"', '"spectrum" "imagemap"'))
 
 
+def test_front_end_aov_integrator(P):
+    base = 'Camera "perspective"\nIntegrator "aov" %s\nWorldBegin\nWorldEnd\n'
+    d = P.HostScene.parse_string(base % "").desc.integrator
+    assert (d.type, d.aov_target, d.aov_scale) == (P.capi.PT_INTEGRATOR_AOV, P.capi.PT_AOV_UV, 1.0)       # aov.rs:197-198 defaults
+    d = P.HostScene.parse_string(base % '"string target" ["shading.n"] "float scale" [0.5]').desc.integrator
+    assert (d.aov_target, d.aov_scale) == (P.capi.PT_AOV_NS, 0.5)
+    for bad in ("dpdx", "nonsense"):
+        with pytest.raises(P.PbrtError):
+            P.HostScene.parse_string(base % ('"string target" ["%s"]' % bad))
+    assert P.HostScene.parse_string('Camera "perspective"\nWorldBegin\nWorldEnd\n').desc.integrator.type == P.capi.PT_INTEGRATOR_PATH
+
+
 def test_front_end_spot_light(P):
     # lights/spot.rs:136-166: light_to_world = CTM * translate(from) * inverse(dir_to_z); cosines with the host libm
     txt = ('Camera "perspective"\nWorldBegin\nTranslate 1 2 3\nLightSource "spot" "rgb I" [10 20 30] "rgb scale" [2 2 2] "point from" [0 5 0] "point to" [0 0 0] '

@@ -153,6 +153,42 @@ def test_hostcheck_spot_lights(HC):
     assert np.sqrt(((a - b) ** 2).mean()) / b.mean() < 1e-5
 
 
+AOV_TARGETS = ["distance", "depth", "n", "ns", "uv", "dpdus"]
+
+
+def aov_scene(P, target, scale=1.0, res=24, spp=2, instanced=False):
+    txt = P.scenes.instanced_blobs(n_instances=20, n_sub=1, res=(res, res * 2 // 3), spp=spp, n_lights=2) if instanced else tangent_scene(P, res=res, spp=spp)
+    assert 'Integrator "path"' in txt
+    head, rest = txt.split('Integrator "path"', 1)
+    return head + 'Integrator "aov" "string target" ["%s"] "float scale" [%g]' % (target, scale) + rest[rest.index("\n"):]
+
+
+@pytest.mark.parametrize("target", AOV_TARGETS)
+def test_hostcheck_aov_integrator(HC, target):
+    """Integrator "aov" (integrators/aov.rs): first-hit quantities as colour, same sampler / camera / film as the path
+    integrator; per-sample values bit-exact vs the oracle, images equal, one closest-hit query per camera sample."""
+    import oracle_api
+    P = HC
+    for instanced in (False, True):
+        hs = P.HostScene.parse_string(aov_scene(P, target, 0.002 if target in ("distance", "depth") else 0.75, instanced=instanced))
+        assert hs.desc.integrator.type == P.capi.PT_INTEGRATOR_AOV
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        sb = hs.desc.film.sample_bounds
+        rng = np.random.RandomState(5)
+        n = 1500
+        pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+        sn = rng.randint(0, 2, n).astype(np.int32)
+        la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+        assert np.array_equal(la.view(np.uint32), lb.view(np.uint32)), (target, instanced, np.abs(la - lb).max())
+        assert la.max() > 0
+        rgb, st = sc.render(collect_counters=1, wave_paths=300)
+        ref, so = orc.render(threads=2)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / max(ref.mean(), 1e-9) < 1e-5
+        assert st["regular_rays"] == st["camera_rays"] == so["camera_rays"] and st["shadow_rays"] == 0
+        for k in ("regular_rays", "nodes_visited", "tris_tested"):
+            assert st[k] == so[k], k
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
