@@ -100,6 +100,10 @@ struct SharedStack {
 #ifndef PT_REFILL_MIN
 #define PT_REFILL_MIN 16
 #endif
+// two-level scenes: rays take longer and differ more in length, refilling earlier pays (profiles/r1_instanced_trace.md)
+#ifndef PT_REFILL_MIN_INST
+#define PT_REFILL_MIN_INST 8
+#endif
 #ifndef PT_NODE_EXIT_MIN
 #define PT_NODE_EXIT_MIN 8
 #endif
@@ -117,12 +121,13 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32
 #if defined(__CUDA_ARCH__)
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  constexpr int REFILL = INST ? PT_REFILL_MIN_INST : PT_REFILL_MIN;
   bool have = false, exhausted = false;
   uint32_t myk = 0;
   for (;;) {
     unsigned idle = __ballot_sync(FULL, !have);
     int nidle = __popc(idle);
-    if (!exhausted && nidle >= PT_REFILL_MIN) {
+    if (!exhausted && nidle >= REFILL) {
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(fetch, (uint32_t)nidle);
       base = __shfl_sync(FULL, base, 0);
@@ -174,7 +179,7 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32
         if (have && T.done) { io.store(myk, T); have = false; }
         unsigned a = __ballot_sync(FULL, have);
         if (a == 0) break;
-        if (!exhausted && __popc(a) <= 32 - PT_REFILL_MIN) break;
+        if (!exhausted && __popc(a) <= 32 - REFILL) break;
       }
       continue;
     }
@@ -202,7 +207,7 @@ __device__ __forceinline__ void trace_persistent(const DScene& S, IO& io, uint32
       if (have && T.done) { io.store(myk, T); have = false; }
       unsigned a = __ballot_sync(FULL, have);
       if (a == 0) break;
-      if (!exhausted && __popc(a) <= 32 - PT_REFILL_MIN) break;
+      if (!exhausted && __popc(a) <= 32 - REFILL) break;
     }
   }
 #else
