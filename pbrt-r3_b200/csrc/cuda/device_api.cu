@@ -541,7 +541,7 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
       CK(cudaGetLastError());
       T->launches++;
     } else if (n_ext > 0) {
-      int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
+      int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
       for (int c = 0; c < CL_COUNT; c++)
         if (s->class_mask & (1u << c)) { launch_shade(NC, c, gs, s->stream, s->h, W, Q, vc); T->launches++; }
@@ -714,11 +714,11 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
       const int k = seg_of_job[next_film];
       const WaveJob& J = jobs[next_film];
       const uint32_t n = J.npix * J.ns, base = (uint32_t)k * seg_cap;
-      PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<NC>)(s->h, W, base, n);
+      PT_LAUNCH(grid_for(s, n, 256, PT_STREAM_GRID_PER_SM), 256, s->stream, k_finish<NC>)(s->h, W, base, n);
       CK(cudaGetLastError());
       T.launches++;
       if (J.fx1 > J.fx0 && J.fy1 > J.fy0) {
-        PT_LAUNCH(grid_for(s, (size_t)(J.fx1 - J.fx0) * (J.fy1 - J.fy0), 128, 8), 128, s->stream, k_film<NC>)(s->h, W, s->slot_of + (size_t)k * sbn, base, J.npix, J.ns, J.fx0,
+        PT_LAUNCH(grid_for(s, (size_t)(J.fx1 - J.fx0) * (J.fy1 - J.fy0), 128, PT_STREAM_GRID_PER_SM), 128, s->stream, k_film<NC>)(s->h, W, s->slot_of + (size_t)k * sbn, base, J.npix, J.ns, J.fx0,
                                                                                                              J.fy0, J.fx1, J.fy1, s->film);
         CK(cudaGetLastError());
         T.launches++;
@@ -753,7 +753,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
           T.launches++;
           g.map_c0 = J.c0; g.map_npix = J.npix;
         }
-        PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, 8), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->h, W, Q, s->pixlist, J.c0, J.npix, J.s0, J.ns, base, n_ext);
+        PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, PT_STREAM_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->h, W, Q, s->pixlist, J.c0, J.npix, J.s0, J.ns, base, n_ext);
         if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_raygen launch failed"); break; }
         T.launches++;
         if (st) st->camera_rays += n;
@@ -809,7 +809,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
       if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_aov launch failed"); break; }
       T.launches++;
     } else if (n_ext > 0) {
-      int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, 8);
+      int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
       for (int c = 0; c < CL_COUNT; c++)
         if (s->class_mask & (1u << c)) { launch_shade(NC, c, gs, s->stream, s->h, W, Q, vc); T.launches++; }

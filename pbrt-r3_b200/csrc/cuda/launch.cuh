@@ -19,6 +19,17 @@
 #ifndef PT_SHADE_MINBLOCKS
 #define PT_SHADE_MINBLOCKS 4
 #endif
+// CTAs per SM of the shade kernels' launch.  A persistent grid (8 per SM) with a grid-stride loop balances badly here:
+// vertices differ a lot in cost (lobe sampled, light type, MIS branch, termination) and every CTA is resident for the
+// whole kernel; with about one vertex per thread the block scheduler does the balancing: k_shade 96.4 -> 80.5 ms per
+// step on config 2 (profiles/r1_shade_fastmath.md)
+#ifndef PT_SHADE_GRID_PER_SM
+#define PT_SHADE_GRID_PER_SM 128
+#endif
+// CTAs per SM of the streaming kernels (raygen, finish, film gather)
+#ifndef PT_STREAM_GRID_PER_SM
+#define PT_STREAM_GRID_PER_SM 128
+#endif
 // 60-bin spectra: three live spectra are 180 registers; at the RGB kernels' 128-register cap the spectral shade kernels
 // spill 2.2 KB per thread, so they trade occupancy for registers (255 registers, 2 CTAs / SM)
 #ifndef PT_SHADE_MINBLOCKS_SPECTRAL
