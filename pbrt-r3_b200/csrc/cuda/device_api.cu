@@ -33,6 +33,12 @@ void launch_shade(int n_channels, int cls, int grid, cudaStream_t stream, const 
     }                                                                                                        \
   } while (0)
 
+// default path slots per wave (RGB): 6 waves of 6.4 M paths in flight = 10 GB of path state on a 180 GB part; measured
+// optimum of the wave-size / waves-in-flight sweep (profiles/r1_wave_pipelining.md)
+#ifndef PT_WAVE_PATHS_RGB
+#define PT_WAVE_PATHS_RGB 6400000u
+#endif
+
 namespace {
 
 struct DevBufs {
@@ -659,7 +665,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   bool count = o && o->collect_counters;
   const bool timed = st != nullptr;
   if (build_pixlist(s, shard_i, shard_n, tile)) return 1;
-  uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? (4u << 20) : (1u << 19));
+  uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? PT_WAVE_PATHS_RGB : (1u << 19));
   uint32_t npix_total = s->pix_n;
   int ns_total = std::max(s_end - s_begin, 0);
   const bool is_path = s->h.integrator.type == PT_INTEGRATOR_PATH;
@@ -873,7 +879,7 @@ int render_waves_random(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     }
     CK(cudaMemcpy(s->h.tile_rng, init.data(), n_tiles * sizeof(uint64_t), cudaMemcpyHostToDevice));
   }
-  uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? (4u << 20) : (1u << 19));
+  uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? PT_WAVE_PATHS_RGB : (1u << 19));
   cap = std::max<uint32_t>(cap, 256u * (uint32_t)spp);
   const int* sb = s->h.film.sample_bounds;
   const int* cb = s->h.film.cropped_pixel_bounds;

@@ -15,7 +15,9 @@
 #define PT_NCS 60
 #endif
 
+#ifndef PT_SHADE_BLOCK
 #define PT_SHADE_BLOCK 128
+#endif
 #ifndef PT_SHADE_MINBLOCKS
 #define PT_SHADE_MINBLOCKS 4
 #endif
