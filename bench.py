@@ -255,7 +255,7 @@ def main():
         peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes * args.steps / (trace_ms / 1e3) / 1e9 if trace_ms > 0 else 0.0
         npix = samples_per_step / max(cfg["spp"], 1)
-        wave_m = npix * max(1, min(cfg["spp"], int((args.wave_paths or (4 << 20)) // max(npix, 1)))) / 1e6   # paths per wave, millions
+        wave_m = npix * max(1, min(cfg["spp"], int((args.wave_paths or 6400000) // max(npix, 1)))) / 1e6   # paths per wave, millions
         nseg = args.wave_segments or 6
         value = rays_all * args.steps / t_steps / 1e6
         line = {
