@@ -25,6 +25,24 @@ def test_oracle_reproduces_golden(P):
     assert np.array_equal(orc2.sampler_values(z["pix"], z["sn"], 0, 32).view(np.uint32), np.load(os.path.join(G, "cornell_64_sobol_values.npy")).view(np.uint32))
 
 
+def _widening_scenes(P):
+    from test_hostcheck import aov_scene, spot_scene
+    return {"spot": spot_scene(P, res=32, spp=4), "aov_ns": aov_scene(P, "ns", 0.75, res=32, spp=2),
+            "lbvh": P.scenes.cornell_box(res=32, spp=2).replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')}
+
+
+def test_oracle_reproduces_golden_widening(P):
+    """Spot lights + mixed materials, the aov integrator on a mesh with normals / tangents, the LBVH layout."""
+    import oracle_api
+    z = np.load(os.path.join(G, "widening_32.npz"))
+    K = ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested")
+    for name, txt in _widening_scenes(P).items():
+        rgb, st = oracle_api.OracleScene(P.HostScene.parse_string(txt)).render(threads=1)
+        assert np.array_equal(rgb, z[name]), name
+        if name + "_counters" in z.files:
+            assert [st[k] for k in K] == list(z[name + "_counters"]), name
+
+
 def test_oracle_furnace(P):
     """Analytic check the reference has no test for: a closed diffuse box lit by a two-sided emitter in the middle.
     With albedo rho and uniform emission, radiance converges to a finite positive value and energy is conserved:
@@ -61,3 +79,19 @@ def test_gpu_reproduces_golden(P):
     hs2 = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4, sampler="sobol"))
     sc2 = P.Scene(hs2, 0)
     assert np.array_equal(sc2.sampler_values(z["pix"], z["sn"], 0, 32).view(np.uint32), np.load(os.path.join(G, "cornell_64_sobol_values.npy")).view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_widening(P):
+    z = np.load(os.path.join(G, "widening_32.npz"))
+    K = ("camera_rays", "regular_rays", "shadow_rays")
+    for name, txt in _widening_scenes(P).items():
+        sc = P.Scene(P.HostScene.parse_string(txt), 0)
+        rgb, st = sc.render(collect_counters=1)
+        ref = z[name]
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() <= 1e-3, name
+        if name + "_counters" in z.files:
+            assert [st[k] for k in K] == list(z[name + "_counters"][:3]), name
+            if name == "lbvh":
+                assert [st[k] for k in ("nodes_visited", "tris_tested")] == list(z[name + "_counters"][3:]), name
+        sc.close()

@@ -23,4 +23,15 @@ np.savez(os.path.join(out, "cornell_64_streams.npz"), pix=pix, sn=sn, halton=orc
 hs2 = P.HostScene.parse_string(P.scenes.cornell_box(res=64, spp=4, sampler="sobol"))
 orc2 = oracle_api.OracleScene(hs2)
 np.save(os.path.join(out, "cornell_64_sobol_values.npy"), orc2.sampler_values(pix, sn, 0, 32))
+# round-1 widening: spot lights + mixed materials (path), mesh tangents / normals (aov "ns"), the LBVH layout's visit counters
+from test_hostcheck import aov_scene, spot_scene
+hs3 = P.HostScene.parse_string(spot_scene(P, res=32, spp=4))
+rgb3, st3 = oracle_api.OracleScene(hs3).render(threads=1)
+hs4 = P.HostScene.parse_string(aov_scene(P, "ns", 0.75, res=32, spp=2))
+rgb4, _ = oracle_api.OracleScene(hs4).render(threads=1)
+hs5 = P.HostScene.parse_string(P.scenes.cornell_box(res=32, spp=2).replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"'))
+rgb5, st5 = oracle_api.OracleScene(hs5).render(threads=1)
+np.savez(os.path.join(out, "widening_32.npz"), spot=rgb3, aov_ns=rgb4, lbvh=rgb5,
+         spot_counters=np.array([st3[k] for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested")], np.int64),
+         lbvh_counters=np.array([st5[k] for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested")], np.int64))
 print("golden written:", os.listdir(out))
