@@ -73,6 +73,21 @@ struct DevBufs {
     *out = (const T*)d;
     return e;
   }
+  // copy into an existing device range (staged like upload() when keep is set)
+  template <typename T>
+  cudaError_t upload_into(T* dev, const T* host, size_t n) {
+    if (n == 0) return cudaSuccess;
+    const void* src = host;
+    if (keep) {
+      void* h = nullptr;
+      cudaError_t e = cudaMallocHost(&h, n * sizeof(T));
+      if (e != cudaSuccess) return e;
+      memcpy(h, host, n * sizeof(T));
+      staged.push_back(Staged{dev, h, n * sizeof(T)});
+      src = h;
+    }
+    return cudaMemcpy(dev, src, n * sizeof(T), cudaMemcpyHostToDevice);
+  }
   template <typename T>
   cudaError_t alloc(size_t n, T** out) {
     *out = nullptr;
@@ -186,6 +201,19 @@ int precompute_light_distribution(pt_scene* s, uint32_t n_vox, float* func, floa
   return 0;
 }
 
+// copies 0 and 1 of the triangle records from the identity copy (dscene.cuh: recs_perm)
+int permute_recs(pt_scene* s) {
+#if PT_TRI_PERM
+  const uint32_t n = s->h.rec_stride;
+  if (n == 0) return 0;
+  PT_LAUNCH(grid_for(s, n, 256, 64), 256, s->stream, k_permute_recs)(const_cast<f4*>(s->h.recs_perm), n);
+  CK(cudaGetLastError());
+#else
+  (void)s;
+#endif
+  return 0;
+}
+
 int build_scene(pt_scene* s, const pt_scene_desc* D) {
   DScene& H = s->h;
   memset(&H, 0, sizeof(H));
@@ -249,7 +277,23 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(s->bufs.upload((const QNode*)nodes.data(), nodes.size(), &H.nodes));
   static_assert(sizeof(pth::LNodeH) == 2 * sizeof(f4), "LNodeH = 2 x f4");
   CK(s->bufs.upload((const f4*)lnodes.data(), lnodes.size() * 2, &H.lnodes));
+#if PT_TRI_PERM
+  {  // three copies on the device, one on the wire: the identity copy is uploaded, k_permute_recs derives the other two
+    const size_t n = recs.size();
+    if (n > 0xffffffffull / 3) { pt_set_error("too many triangle records"); return 1; }
+    f4* all = nullptr;
+    CK(s->bufs.alloc(3 * n, &all));
+    if (n > 0) CK(s->bufs.upload_into(all + 2 * n, recs.data(), n));
+    H.recs_perm = all;
+    H.recs = all ? all + 2 * n : nullptr;
+    H.rec_stride = (uint32_t)n;
+    if (permute_recs(s)) return 1;
+  }
+#else
   CK(s->bufs.upload(recs.data(), recs.size(), &H.recs));
+  H.recs_perm = nullptr;
+  H.rec_stride = 0;
+#endif
   CK(s->bufs.upload(orecs.data(), orecs.size(), &H.objects));
   {
     std::vector<InstanceRec> ir(D->n_instances);
@@ -1006,6 +1050,7 @@ int pt_scene_reupload(pt_scene* s, uint64_t* bytes) {
   }
   CK(cudaMemcpyAsync(s->d, &s->h, sizeof(DScene), cudaMemcpyHostToDevice, s->stream));
   total += sizeof(DScene);
+  if (permute_recs(s)) return 1;
   CK(cudaStreamSynchronize(s->stream));
   if (bytes) *bytes = total;
   return 0;

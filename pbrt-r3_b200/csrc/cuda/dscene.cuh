@@ -74,6 +74,11 @@ struct DScene {
   const f4* lnodes;          // binary LinearBVHNode layout, 2 x f4 per node (accel_type PT_ACCEL_LBVH, dlbvh.cuh)
   int accel_type;
   const f4* recs;            // 3 per record
+  // PT_TRI_PERM: the records once more with p.xyz stored as (y,z,x) [copy 0] and (z,x,y) [copy 1]: copy kz holds the components
+  // in the order (kx, ky, kz) the watertight test permutes them to for a ray whose dominant axis is kz (triangle.rs:258-268);
+  // copy 2 is `recs` itself.  recs_perm + kz * rec_stride = copy kz (rec_stride in f4 units); null when the switch is off.
+  const f4* recs_perm;
+  uint32_t rec_stride;
   const ObjectRec* objects;
   const InstanceRec* instances;
   // original-order triangle attributes (indexed by global triangle id)

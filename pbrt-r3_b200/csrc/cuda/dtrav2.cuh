@@ -36,6 +36,10 @@
 #ifndef PT_OPT_POPLUT
 #define PT_OPT_POPLUT 0
 #endif
+// triangle records in the three axis orders of the watertight test (dscene.cuh): no per-triangle component selects
+#ifndef PT_TRI_PERM
+#define PT_TRI_PERM 1
+#endif
 
 namespace ptd {
 
@@ -122,6 +126,69 @@ PT_HD bool bounds_range_idir(const float* bmin, const float* bmax, f3 o, f3 d, f
   *t1o = t1;
   return t0 <= t1;
 }
+
+#if PT_TRI_PERM
+// tri_test_ray on a record of copy kz: q0, q1, q2 hold (p[kx], p[ky], p[kz]) and op the ray origin in the same order, so the
+// permutation of triangle.rs:258-268 is already done.  A cyclic axis rotation keeps every operand pair of the cross product,
+// and the culling dot product is summed in the original x, y, z order: same operations, same results.
+PT_HD bool tri_test_perm(f3 q0, f3 q1, f3 q2, uint32_t flags, const Trav& T, f3 op, TriHitD* out) {
+  if (!(flags & PT_TRI_TWO_SIDED)) {
+    f3 n = cross3(q0 - q2, q1 - q2);  // = (n[kx], n[ky], n[kz])
+    if (((flags & PT_TRI_REVERSE_ORIENTATION) != 0) != ((flags & PT_TRI_SWAPS_HANDEDNESS) != 0)) n = n * -1.0f;
+    const int kz = T.kz;
+    const int px = kz == 2 ? 0 : (kz == 0 ? 2 : 1), py = kz == 2 ? 1 : (kz == 0 ? 0 : 2), pz = kz == 2 ? 2 : (kz == 0 ? 1 : 0);  // where x, y, z are stored
+    if (comp(n, px) * T.d.x + comp(n, py) * T.d.y + comp(n, pz) * T.d.z >= 0.0f) return false;
+  }
+  f3 a = q0 - op, b = q1 - op, c = q2 - op;
+  float ax = a.x, ay = a.y, az = a.z;
+  float bx = b.x, by = b.y, bz = b.z;
+  float cx = c.x, cy = c.y, cz = c.z;
+  const float sx = T.shx, sy = T.shy, sz = T.shz;
+  ax += sx * az; ay += sy * az;
+  bx += sx * bz; by += sy * bz;
+  cx += sx * cz; cy += sy * cz;
+  float e0 = bx * cy - by * cx;
+  float e1 = cx * ay - cy * ax;
+  float e2 = ax * by - ay * bx;
+  if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {  // rare: exact edge hit, f64 fallback (triangle.rs:283-293)
+    e0 = (float)((double)cy * (double)bx - (double)cx * (double)by);
+    e1 = (float)((double)ay * (double)cx - (double)ax * (double)cy);
+    e2 = (float)((double)by * (double)ax - (double)bx * (double)ay);
+  }
+  if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+  float det = e0 + e1 + e2;
+  if (det == 0.0f) return false;
+  az *= sz; bz *= sz; cz *= sz;
+  float ts = e0 * az + e1 * bz + e2 * cz;
+  const float tmax = T.ray_tmax;
+  if (det < 0.0f && (ts >= 0.0f || ts < tmax * det)) return false;
+  else if (det > 0.0f && (ts <= 0.0f || ts > tmax * det)) return false;
+  float inv_det = 1.0f / det;
+  float t = ts * inv_det;
+  float max_zt = fmaxf(fabsf(az), fmaxf(fabsf(bz), fabsf(cz)));
+  float delta_z = PT_GAMMA(3.0f) * max_zt;
+  float max_xt = fmaxf(fabsf(ax), fmaxf(fabsf(bx), fabsf(cx)));
+  float max_yt = fmaxf(fabsf(ay), fmaxf(fabsf(by), fabsf(cy)));
+  float delta_x = PT_GAMMA(5.0f) * (max_xt + max_zt);
+  float delta_y = PT_GAMMA(5.0f) * (max_yt + max_zt);
+  float delta_e = 2.0f * (PT_GAMMA(2.0f) * max_xt * max_yt + delta_y * max_xt + delta_x * max_yt);
+  float max_e = fmaxf(fabsf(e0), fmaxf(fabsf(e1), fabsf(e2)));
+  float delta_t = 3.0f * (PT_GAMMA(3.0f) * max_e * max_zt + delta_e * max_zt + delta_z * max_e) * fabsf(inv_det);
+  if (t <= delta_t) return false;
+  out->t = t;
+  out->b0 = e0 * inv_det;
+  out->b1 = e1 * inv_det;
+  out->b2 = e2 * inv_det;
+  return true;
+}
+// the ray origin in the component order of copy T.kz
+PT_HD f3 trav_origin_perm(const Trav& T) {
+  const int kz = T.kz;
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  return mk3(comp(T.o, kx), comp(T.o, ky), comp(T.o, kz));
+}
+#endif
 
 // tri_test (dtrav.cuh) with the per-ray constants hoisted and the rejection tests folded into one predicate, so that
 // the lanes of a warp stay converged through the leaf loop.  Same operations, same order, same results.
@@ -210,10 +277,16 @@ PT_HD void trav_pop(Trav& T, Stack& st) {
 
 // one accepted-or-not triangle record in the current space; returns true when the query is finished (any-hit)
 template <bool COUNT>
-PT_HD bool trav_triangle(Trav& T, f4 v0, f4 v1, f4 v2, TravCounters* cnt) {
+PT_HD bool trav_triangle(Trav& T, f4 v0, f4 v1, f4 v2, TravCounters* cnt
+#if PT_TRI_PERM
+                         , f3 op
+#endif
+) {
   if (COUNT) cnt->tris++;
   TriHitD th;
-#if PT_OPT_HOIST
+#if PT_TRI_PERM
+  if (!tri_test_perm(xyz(v0), xyz(v1), xyz(v2), fbits(v1.w), T, op, &th)) return false;
+#elif PT_OPT_HOIST
   if (!tri_test_ray(xyz(v0), xyz(v1), xyz(v2), fbits(v1.w), T, &th)) return false;
 #else
   if (!tri_test(xyz(v0), xyz(v1), xyz(v2), fbits(v1.w), T.o, T.d, T.ray_tmax, &th)) return false;
@@ -371,7 +444,12 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
     return;
   }
   const int first = T.lf, count = T.lc;
+#if PT_TRI_PERM
+  const f4* r = S.recs_perm + (size_t)T.kz * S.rec_stride + ((size_t)T.rec_base + (size_t)first) * 3;
+  f3 op = trav_origin_perm(T);
+#else
   const f4* r = S.recs + ((size_t)T.rec_base + (size_t)first) * 3;
+#endif
   for (int i = 0; i < count; i++, r += 3) {
     f4 v0 = ldg4(r), v1 = ldg4(r + 1), v2 = ldg4(r + 2);
     if (INST && (fbits(v1.w) & PT_REC_INSTANCE)) {
@@ -384,11 +462,16 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
       DRay q = xform_ray(I.minv, wr);
       if (O.n_prims == 0) continue;
       if (O.single) {  // one primitive, no accelerator: test it in object space right here
-        const f4* pr = S.recs + (size_t)O.rec_base * 3;
         trav_park_ray(T, st);
         trav_set_ray(T, q.o, q.d);
         T.inst = inst;
+#if PT_TRI_PERM
+        const f4* pr = S.recs_perm + (size_t)T.kz * S.rec_stride + (size_t)O.rec_base * 3;
+        bool fin = trav_triangle<COUNT>(T, ldg4(pr), ldg4(pr + 1), ldg4(pr + 2), cnt, trav_origin_perm(T));
+#else
+        const f4* pr = S.recs + (size_t)O.rec_base * 3;
         bool fin = trav_triangle<COUNT>(T, ldg4(pr), ldg4(pr + 1), ldg4(pr + 2), cnt);
+#endif
         trav_unpark_ray(T, st);
         T.inst = -1;
         if (fin) { T.done = true; return; }
@@ -418,7 +501,11 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
       T.cur = 0;
       return;
     }
+#if PT_TRI_PERM
+    if (trav_triangle<COUNT>(T, v0, v1, v2, cnt, op)) { T.done = true; return; }
+#else
     if (trav_triangle<COUNT>(T, v0, v1, v2, cnt)) { T.done = true; return; }
+#endif
   }
   if (T.leaf_hit) {  // qbvh_x86.rs:279-283: tmax = r.t_max after a leaf that reported a hit
     T.tmax = T.ray_tmax;

@@ -356,6 +356,15 @@ __global__ void k_finish(const __grid_constant__ DScene S, WaveState W, uint32_t
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) finish_body<NC>(S, W, base + i);
 }
 
+// all[0..n) = (y,z,x,w) and all[n..2n) = (z,x,y,w) of the uploaded records all[2n..3n) (dscene.cuh: recs_perm)
+__global__ void k_permute_recs(f4* all, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const f4 v = all[2 * (size_t)n + i];
+    all[i] = mk4(v.y, v.z, v.x, v.w);
+    all[(size_t)n + i] = mk4(v.z, v.x, v.y, v.w);
+  }
+}
+
 __global__ void k_set_slots(const int* __restrict__ pixlist, uint32_t c0, uint32_t npix, int sbw, int* slot_of, int clear) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
     int pk = pixlist[c0 + i];

@@ -191,6 +191,19 @@ def test_aov_integrator(P, pair, target):
         assert st["shadow_rays"] == 0 and st["regular_rays"] == st["camera_rays"]
 
 
+def test_one_sided_triangles_bit_exact(P, pair):
+    """Back-face culling of one-sided meshes (triangle.rs:236-246), with and without ReverseOrientation."""
+    from test_hostcheck import one_sided_scene
+    hs, sc, orc = pair("one_sided", one_sided_scene(P, res=64, spp=4))
+    rays = _random_rays(orc, 30000, 21)
+    _check_intersections(sc, orc, rays)
+    r = _random_rays(orc, 30000, 22, tmax=np.random.RandomState(5).uniform(1.0, 600.0, 30000))
+    assert np.array_equal(sc.intersect_p(r), orc.intersect_p(r))
+    rgb, _ = sc.render()
+    ref, _ = orc.render()
+    assert rel_rmse(rgb, ref) <= RMSE_TOL
+
+
 def test_light_distribution_bit_exact(P, pair):
     for name, txt in [("cornell_halton", P.scenes.cornell_box(res=200, spp=64)), ("cornell_lights", P.scenes.cornell_box(res=64, spp=4, extra_lights=True))]:
         hs, sc, orc = pair(name, txt)

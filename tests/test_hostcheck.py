@@ -97,6 +97,43 @@ def test_hostcheck_halton_digit_paths(HC):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (hi, dim0)
 
 
+def one_sided_scene(P, res=32, spp=2):
+    """Cornell box with one-sided meshes (pbrt-r3's "twosided" false: back faces are culled, triangle.rs:236-246), every
+    other one with ReverseOrientation."""
+    lines, k = [], 0
+    for l in P.scenes.cornell_box(res=res, spp=spp, materials="mixed").split("\n"):
+        if l.startswith("Shape"):
+            k += 1
+            l = l + ' "bool twosided" ["false"]'
+            if k % 2 == 0:
+                l = "AttributeBegin\nReverseOrientation\n" + l + "\nAttributeEnd"
+        lines.append(l)
+    return "\n".join(lines)
+
+
+def test_hostcheck_one_sided_triangles(HC):
+    import oracle_api
+    P = HC
+    hs = P.HostScene.parse_string(one_sided_scene(P))
+    flags = np.ctypeslib.as_array(hs.desc.tri_flags, (hs.desc.n_tris,))
+    assert not (flags & P.capi.PT_TRI_TWO_SIDED).any() and (flags & P.capi.PT_TRI_REVERSE_ORIENTATION).any()
+    sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+    wb = orc.world_bound()
+    rng = np.random.RandomState(3)
+    n = 6000
+    o = rng.uniform(wb[:3], wb[3:], (n, 3))
+    d = rng.normal(size=(n, 3))
+    d[:60] = np.eye(3)[rng.randint(0, 3, 60)] * rng.choice([-1.0, 1.0], (60, 1))     # each dominant axis, exactly
+    rays = np.concatenate([o, np.full((n, 1), np.inf), d, np.zeros((n, 1))], 1).astype(np.float32)
+    pa, ta, ba, na, tra = sc.intersect(rays, counters=True)
+    pb, tb, bb, nb, trb = orc.intersect(rays)
+    assert np.array_equal(pa, pb) and np.array_equal(ta.view(np.uint32), tb.view(np.uint32)) and np.array_equal(ba.view(np.uint32), bb.view(np.uint32))
+    assert (na, tra) == (nb, trb) and 0.2 < (pa >= 0).mean() < 0.99
+    r2 = rays.copy()
+    r2[:, 3] = rng.uniform(1.0, 600.0, n)
+    assert np.array_equal(sc.intersect_p(r2), orc.intersect_p(r2))
+
+
 def test_hostcheck_li_mixed_materials(HC):
     _cmp_li(HC, HC.scenes.cornell_box(res=32, spp=8, materials="mixed", extra_lights=True, maxdepth=8), 3000, 8, 0.999)
 
