@@ -339,7 +339,40 @@ PT_HDN float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
     default: return 0.0f;
   }
 }
-// BxDF::sample_f of one lobe; stype = 0 means "the lobe's own type"
+// lobe_f and lobe_pdf of one lobe for the same pair (wo, wi), sharing what both compute (half vector, D(wh), Lambda(wo)).
+// Every shared value is produced by the same operations on the same operands as in the two separate functions
+// (wi + wo and wo + wi are the same float sums), so f and pdf are bit-identical to lobe_f / lobe_pdf.
+template <int NC, int CM = PT_CM_ANY>
+PT_HDN void lobe_f_pdf(const DScene& S, const Lobe& L, f3 wo, f3 wi, bool want_f, Sp<NC>* f, float* pdf) {
+  if (((CM >> LB_MF_REFL) & 1) && L.kind == LB_MF_REFL) {
+    *f = sp_const<NC>(0.0f);
+    *pdf = 0.0f;
+    const float cto = acth(wo), cti = acth(wi);
+    f3 wh = wi + wo;
+    const bool f_ok = want_f && !(cti == 0.0f || cto == 0.0f) && !(wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f);
+    const bool hemi = same_hemi(wo, wi);
+    if (!f_ok && !hemi) return;
+    wh = norm3(wh);
+    const bool pdf_ok = hemi && !(dot3(wo, wh) < 0.0f);
+    if (!f_ok && !pdf_ok) return;
+    TR D; D.ax = L.a; D.ay = L.b;
+    const float d = tr_d(D, wh), lo = tr_lambda(D, wo);
+    if (f_ok) {
+      Sp<NC> F = lobe_fresnel<NC, CM>(S, L, dot3(wi, faceforward(wh, mk3(0.0f, 0.0f, 1.0f))));
+      float k = d * (1.0f / (1.0f + lo + tr_lambda(D, wi))) / (4.0f * cti * cto);
+      Sp<NC> R = (L.fres == FR_COND) ? sp_const<NC>(1.0f) : sp_load<NC>(S.spectra + (size_t)L.sp0 * NC);
+      *f = R * F * k;
+    }
+    if (pdf_ok) *pdf = (d * (1.0f / (1.0f + lo)) * absdot3(wo, wh) / acth(wo)) / (4.0f * dot3(wo, wh));
+    return;
+  }
+  *f = want_f ? lobe_f<NC, CM>(S, L, wo, wi) : sp_const<NC>(0.0f);
+  *pdf = lobe_pdf<CM>(L, wo, wi);
+}
+
+// BxDF::sample_f of one lobe; stype = 0 means "the lobe's own type".
+// For the non-specular lobes *f is NOT evaluated: BSDF::sample_f recomputes f over all matching lobes right after
+// (bsdf.rs:178-196; bsdf_sample below), so the reference's own value is always discarded, and no decision depends on it.
 template <int NC, int CM = PT_CM_ANY>
 PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, f3* wi_out, float* pdf, int* stype) {
   *stype = 0;
@@ -349,8 +382,7 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, 
       f3 wi = cosine_hemisphere(u);
       if (wo.z < 0.0f) wi.z *= -1.0f;
       *pdf = lobe_pdf<CM>(L, wo, wi);
-      *f = lobe_f<NC, CM>(S, L, wo, wi);
-      *wi_out = wi;
+      *wi_out = wi;   // f: see the note above lobe_sample
       return true;
     }
     PT_KIND(LB_MIRROR) {
@@ -393,7 +425,6 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, 
       float p = tr_pdf(D, wo, wh) / (4.0f * dot3(wo, wh));
       if (p == 0.0f) return false;
       *pdf = p;
-      *f = lobe_f<NC, CM>(S, L, wo, wi);
       *wi_out = wi;
       return true;
     }
@@ -409,7 +440,6 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, 
       float p = lobe_pdf<CM>(L, wo, wi);
       if (!(p > 0.0f)) return false;
       *pdf = p;
-      *f = lobe_f<NC, CM>(S, L, wo, wi);
       *wi_out = wi;
       return true;
     }
@@ -671,6 +701,33 @@ PT_HDN float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
     if (lobe_matches(B.lobe[i].kind, flags)) { p = p + lobe_pdf<CM>(B.lobe[i], wo, wi); count++; }
   return count > 0 ? p / (float)count : 0.0f;
 }
+// BSDF::f and BSDF::pdf for the same pair of directions (estimate_direct's light sample needs both, sample_lights.rs:
+// 366-380): one pass over the lobes with lobe_f_pdf.  Same sums in the same lobe order as bsdf_f / bsdf_pdf.
+template <int NC, int CM = PT_CM_ANY>
+PT_HDN void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags, Sp<NC>* f_out, float* pdf_out) {
+  *f_out = sp_const<NC>(0.0f);
+  *pdf_out = 0.0f;
+  f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
+  if (wo.z == 0.0f || !fin3(wo)) return;
+  const bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
+  Sp<NC> r = sp_const<NC>(0.0f);
+  int count = 0;
+  float p = 0.0f;
+  for (int i = 0; i < B.n; i++) {
+    if (!lobe_matches(B.lobe[i].kind, flags)) continue;
+    const int tp = lobe_type(B.lobe[i].kind);
+    const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
+    Sp<NC> fl;
+    float pl;
+    lobe_f_pdf<NC, CM>(S, B.lobe[i], wo, wi, want_f, &fl, &pl);
+    if (want_f) r = r + fl;
+    p = p + pl;
+    count++;
+  }
+  *f_out = r;
+  *pdf_out = count > 0 ? p / (float)count : 0.0f;
+}
+
 template <int NC, int CM = PT_CM_ANY>
 PT_HDN bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags, Sp<NC>* f, f3* wi_w_out, float* pdf_out, int* stype) {
   int matching = bsdf_count(B, flags);
@@ -693,11 +750,28 @@ PT_HDN bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flag
   int ltype = lobe_type(L.kind);
   int sampled = t != 0 ? t : ltype;
   f3 wi_w = to_world(B, wi);
-  if ((ltype & F_SPEC) == 0 && matching > 1)
-    for (int i = 0; i < B.n; i++)
-      if (i != index && lobe_matches(B.lobe[i].kind, flags)) pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
+  if ((ltype & F_SPEC) == 0) {
+    // pdf += the other matching lobes' pdfs (bsdf.rs:167-176); f = sum over the matching lobes on the right side of the
+    // geometric normal (bsdf.rs:178-196), the sampled lobe included: one fused evaluation per other lobe, both in lobe order
+    const bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
+    Sp<NC> r = sp_const<NC>(0.0f);
+    for (int i = 0; i < B.n; i++) {
+      if (!lobe_matches(B.lobe[i].kind, flags)) continue;
+      const int tp = lobe_type(B.lobe[i].kind);
+      const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
+      if (i == index) {
+        if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+      } else {
+        Sp<NC> fl;
+        float pl;
+        lobe_f_pdf<NC, CM>(S, B.lobe[i], wo, wi, want_f, &fl, &pl);
+        if (want_f) r = r + fl;
+        pdf += pl;
+      }
+    }
+    fv = r;
+  }
   if (matching > 1) pdf /= (float)matching;
-  if ((ltype & F_SPEC) == 0) fv = bsdf_sum_f<NC, CM>(S, B, wo, wi, wo_w, wi_w, flags);
   *f = fv; *wi_w_out = wi_w; *pdf_out = pdf; *stype = sampled;
   return true;
 }

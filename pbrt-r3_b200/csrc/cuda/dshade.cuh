@@ -405,8 +405,10 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
         fprintf(stderr, "[hc] ls pdf %g li %g wi=(%g %g %g) sh_o=(%.9g %.9g %.9g) sh_d=(%.9g %.9g %.9g)\n", ls.pdf, ls.li.c[0], ls.wi.x, ls.wi.y, ls.wi.z, ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, ls.sh_d.x, ls.sh_d.y, ls.sh_d.z);
 #endif
         if (ls.pdf > 0.0f && !sp_black(ls.li)) {
-          Sp<NC> f = bsdf_f<NC, CM>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
-          float spdf = bsdf_pdf<CM>(B, si.wo, ls.wi, NONSPEC);
+          Sp<NC> f;
+          float spdf;
+          bsdf_f_pdf<NC, CM>(S, B, si.wo, ls.wi, NONSPEC, &f, &spdf);
+          f = f * absdot3(ls.wi, si.sn);
           if (!sp_black(f)) {
             Sp<NC> ld;
             if (delta) ld = f * ls.li / ls.pdf;
