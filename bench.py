@@ -89,7 +89,7 @@ def oracle_rate(hs, threads, s0, s1):
     return rays / dt / 1e6, st["camera_rays"] / dt / 1e6, dt, st
 
 
-def run_reference(args, cfg):
+def run_reference(args, cfg, out=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -120,11 +120,29 @@ def run_reference(args, cfg):
             "config": {"workload": workload_name(cfg), "impl": "C++ restatement of pbrt-r3's CPU path (oracle/; the Rust reference cannot be built: no rustc)"},
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     return 0
 
 
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner on the first collective,
+    make / nvcc notes from build()): route fd 1 to stderr for the whole run and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = _quiet_stdout()
+    try:
+        return _main(out)
+    finally:
+        out.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -140,7 +158,7 @@ def main():
     args = ap.parse_args()
     cfg = {"grid_n": args.grid, "res": args.res, "spp": args.spp, "maxdepth": args.maxdepth}
     if args.impl == "reference":
-        return run_reference(args, cfg)
+        return run_reference(args, cfg, out)
 
     import numpy as np
     import torch
@@ -288,7 +306,8 @@ def main():
             line["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": "port",
                                     "sample": "sample numbers 0..%d of every pixel (%d/%d of the step), %d threads, %.1f s wall; C++ restatement of pbrt-r3's CPU path" % (ncpu - 1, ncpu, cfg["spp"], cores, dt),
                                     "msamples_per_s": ms}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
