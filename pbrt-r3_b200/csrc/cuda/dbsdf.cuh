@@ -528,6 +528,25 @@ PT_HDN SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, fl
   return si;
 }
 
+// Only the point and the geometric normal of tri_surface (what Shape::pdf_from and the area-light side test read), by the
+// same operations; meshes with per-vertex normals or tangents, whose normal is flipped towards the shading normal, take
+// the full path.
+PT_HD void tri_point_normal(const DScene& S, int tri, f3 rd, float b0, float b1, float b2, f3* p_out, f3* n_out) {
+  uint32_t flags = ldg(S.tri_flags + tri);
+  if (((flags & PT_TRI_HAS_N) && S.tri_n) || ((flags & PT_TRI_HAS_S) && S.tri_s)) {
+    SurfD s = tri_surface(S, tri, rd, b0, b1, b2);
+    *p_out = s.p; *n_out = s.n;
+    return;
+  }
+  f3 p0, p1, p2;
+  tri_verts(S, tri, &p0, &p1, &p2);
+  bool rev = (flags & PT_TRI_REVERSE_ORIENTATION) != 0, swp = (flags & PT_TRI_SWAPS_HANDEDNESS) != 0;
+  f3 n = cross3(p0 - p2, p1 - p2);
+  if (rev != swp) n = n * -1.0f;
+  *n_out = norm3(n);
+  *p_out = b0 * p0 + b1 * p1 + b2 * p2;
+}
+
 // Transform::transform_surface_interaction (instance -> world)
 PT_HDN SurfD surf_to_world(const InstanceRec& I, const SurfD& s) {
   SurfD r = s;

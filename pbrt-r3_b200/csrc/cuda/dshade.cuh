@@ -189,9 +189,10 @@ PT_HDN float light_pdf_li(const DScene& S, int li, const RefPt& it, f3 wi) {
   tri_verts(S, L.tri, &p0, &p1, &p2);
   TriHitD th;
   if (!tri_test(p0, p1, p2, ldg(S.tri_flags + L.tri), o, wi, pt_inf(), &th)) return 0.0f;
-  SurfD s = tri_surface(S, L.tri, wi, th.b0, th.b1, th.b2);
+  f3 sp, sn;
+  tri_point_normal(S, L.tri, wi, th.b0, th.b1, th.b2, &sp, &sn);
   float area = 0.5f * len3(cross3(p1 - p0, p2 - p0));
-  float pdf = dist2(it.p, s.p) / (absdot3(s.n, -wi) * area);
+  float pdf = dist2(it.p, sp) / (absdot3(sn, -wi) * area);
   if (isinf_(pdf)) return 0.0f;
   return pdf;
 }
@@ -533,9 +534,13 @@ PT_HD void mis_resolve(const DScene& S, WaveState& W, uint32_t i, const HitD& h,
   if (found && h.instance < 0) {
     int ln = W.mis_light[i];
     if (ldg(S.tri_light + h.tri) == ln) {
-      SurfD s = tri_surface(S, h.tri, rd, h.b0, h.b1, h.b2);
       const pt_light& LT = S.lights[ln];
-      keep = LT.two_sided || dot3(s.n, -rd) > 0.0f;
+      keep = LT.two_sided != 0;
+      if (!keep) {
+        f3 sp, sn;
+        tri_point_normal(S, h.tri, rd, h.b0, h.b1, h.b2, &sp, &sn);
+        keep = dot3(sn, -rd) > 0.0f;
+      }
     }
   }
   if (!keep) st_store<NC>(W.pendB, W.cap, i, sp_const<NC>(0.0f));
