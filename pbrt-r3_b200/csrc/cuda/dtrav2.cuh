@@ -18,14 +18,8 @@
 #ifndef PT_OPT_TRI_PRED
 #define PT_OPT_TRI_PRED 0
 #endif
-#ifndef PT_OPT_PUSH_UNROLL
-#define PT_OPT_PUSH_UNROLL 0
-#endif
 #ifndef PT_OPT_HOIST
 #define PT_OPT_HOIST 1
-#endif
-#ifndef PT_OPT_NEXTREG
-#define PT_OPT_NEXTREG 0
 #endif
 #ifndef PT_OPT_FMNMX
 #define PT_OPT_FMNMX 1
