@@ -6,7 +6,8 @@ image is written by the film's file name extension like Film::write_image.
     python -m pbrt_r3_b200 scene.pbrt [-o out.exr] [-s 64] [--quick] [--quiet] [--stats] [--gpus N]
 
 Options of the reference that only make sense for its CPU renderer or its other subsystems are accepted and ignored
-(--nthreads, --logdir, --logtostderr, --minloglevel, --profile, --display-server, --sequential-display); --cat / --toply
+(--nthreads, --logdir, --logtostderr, --minloglevel, --profile, --display-server, --sequential-display, and --cropwindow,
+which the reference parses but never applies: PbrtOptions.crop_window is commented out, pbrt_options.rs:9); --cat / --toply
 (scene reformatting) are not part of the render path and exit with an error.  --gpus N (extension) renders with N
 processes, one per GPU, sample-sharded, with the film partials summed by NCCL (pbrt_r3_b200.dist)."""
 import argparse
