@@ -736,11 +736,16 @@ PT_HDN void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int fl
     if (!lobe_matches(B.lobe[i].kind, flags)) continue;
     const int tp = lobe_type(B.lobe[i].kind);
     const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
-    Sp<NC> fl;
-    float pl;
-    lobe_f_pdf<NC, CM>(S, B.lobe[i], wo, wi, want_f, &fl, &pl);
-    if (want_f) r = r + fl;
-    p = p + pl;
+    if (((CM >> LB_MF_REFL) & 1) && B.lobe[i].kind == LB_MF_REFL) {
+      Sp<NC> fl;
+      float pl;
+      lobe_f_pdf<NC, CM>(S, B.lobe[i], wo, wi, want_f, &fl, &pl);
+      if (want_f) r = r + fl;
+      p = p + pl;
+    } else {  // nothing to share: no spectrum-sized temporary (matters for 60 bins)
+      if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+      p = p + lobe_pdf<CM>(B.lobe[i], wo, wi);
+    }
     count++;
   }
   *f_out = r;
@@ -780,12 +785,15 @@ PT_HDN bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flag
       const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
       if (i == index) {
         if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
-      } else {
+      } else if (((CM >> LB_MF_REFL) & 1) && B.lobe[i].kind == LB_MF_REFL) {
         Sp<NC> fl;
         float pl;
         lobe_f_pdf<NC, CM>(S, B.lobe[i], wo, wi, want_f, &fl, &pl);
         if (want_f) r = r + fl;
         pdf += pl;
+      } else {
+        if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+        pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
       }
     }
     fv = r;
