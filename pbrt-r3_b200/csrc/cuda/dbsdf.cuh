@@ -774,7 +774,12 @@ PT_HDN bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flag
   int ltype = lobe_type(L.kind);
   int sampled = t != 0 ? t : ltype;
   f3 wi_w = to_world(B, wi);
-  if ((ltype & F_SPEC) == 0) {
+  if (NC != 3 && (ltype & F_SPEC) == 0) {  // 60 bins: the plain form (no spectrum-sized temporaries)
+    if (matching > 1)
+      for (int i = 0; i < B.n; i++)
+        if (i != index && lobe_matches(B.lobe[i].kind, flags)) pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
+    fv = bsdf_sum_f<NC, CM>(S, B, wo, wi, wo_w, wi_w, flags);
+  } else if ((ltype & F_SPEC) == 0) {
     // pdf += the other matching lobes' pdfs (bsdf.rs:167-176); f = sum over the matching lobes on the right side of the
     // geometric normal (bsdf.rs:178-196), the sampled lobe included: one fused evaluation per other lobe, both in lobe order
     const bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;

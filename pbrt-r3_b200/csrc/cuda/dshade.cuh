@@ -408,8 +408,13 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
         if (ls.pdf > 0.0f && !sp_black(ls.li)) {
           Sp<NC> f;
           float spdf;
-          bsdf_f_pdf<NC, CM>(S, B, si.wo, ls.wi, NONSPEC, &f, &spdf);
-          f = f * absdot3(ls.wi, si.sn);
+          if (NC == 3) {  // RGB: one fused pass (shares the microfacet terms); 60 bins: the separate functions move fewer spectra
+            bsdf_f_pdf<NC, CM>(S, B, si.wo, ls.wi, NONSPEC, &f, &spdf);
+            f = f * absdot3(ls.wi, si.sn);
+          } else {
+            f = bsdf_f<NC, CM>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
+            spdf = bsdf_pdf<CM>(B, si.wo, ls.wi, NONSPEC);
+          }
           if (!sp_black(f)) {
             Sp<NC> ld;
             if (delta) ld = f * ls.li / ls.pdf;
