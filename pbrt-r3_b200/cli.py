@@ -98,7 +98,12 @@ def main(argv=None):
         import subprocess
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(opts.gpus), "--master-addr", "127.0.0.1",
                "--master-port", os.environ.get("MASTER_PORT", "29533"), "-m", "pbrt_r3_b200"] + (argv if argv is not None else sys.argv[1:])
-        return subprocess.call(cmd, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        # the ranks keep the caller's working directory (relative scene / output paths mean the same thing there); the
+        # package is found through PYTHONPATH
+        env = dict(os.environ)
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env["PYTHONPATH"] = root + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
+        return subprocess.call(cmd, env=env)
     try:
         return render_scene(os.path.realpath(path), opts)
     except Exception as e:  # errors are logged and the exit code is -1 (pbrt.rs:334-338)

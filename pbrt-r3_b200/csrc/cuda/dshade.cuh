@@ -390,6 +390,10 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
 
   // --- uniform_sample_one_light_surface + estimate_direct_surface (sample_lights.rs:129-176, 330-453)
   if (CLS != CL_MIRROR && bsdf_count(B, NONSPEC) > 0 && S.n_lights > 0) {
+    // path.rs:122-129 adds beta * uniform_sample_one_light(..) even when the estimate is zero: a non-finite beta makes
+    // l invalid at this vertex whatever the light / MIS rays find (inf * 0 = NaN).  The terms parked in pendA / pendB
+    // are dropped when occluded, so the same effect is folded in here; for a finite beta this adds +0.
+    L = L + beta * 0.0f;
     float light_pdf;
     int ln = ld_sample(S, si.p, get1d(S, st), &light_pdf);
 #ifdef PT_DEBUG_PRINT

@@ -1,5 +1,5 @@
-// dtrav.cuh — watertight ray/triangle test and 4-wide BVH traversal (closest hit and any hit), two levels
-// for ObjectInstance.
+// dtrav.cuh — watertight ray/triangle test, world-bound slab test and the shared traversal definitions (the 4-wide
+// traversal itself is the resumable state machine of dtrav2.cuh).
 // Replaces reference src/shapes/triangle.rs:226-352,452-577 (Triangle::intersect / intersect_p decision part),
 // src/accelerators/bvh/accel/qbvh/qbvh_x86.rs:26-67,187-343,373-399 (test_aabb, ORDER_TABLE, intersect_simd[_p],
 // QBVHAccel::intersect[_p]), src/core/geometry/intersect.rs:46-65 (world-bound slab test),
@@ -113,160 +113,6 @@ PT_HD bool bounds_range(const float* bmin, const float* bmax, f3 o, f3 d, float 
 #define PT_SSE_MAX(a, b) ((a) > (b) ? (a) : (b))
 #define PT_SSE_MIN(a, b) ((a) < (b) ? (a) : (b))
 
-// Stack policy: `Stack` provides push(int)/pop(int&)/empty(); see kernels for the shared-memory backed one.
-struct LocalStack {
-  int v[PT_MAX_STACK];
-  int n;
-  PT_HD void reset() { n = 0; }
-  PT_HD bool push(int x) { if (n >= PT_MAX_STACK) return false; v[n++] = x; return true; }
-  PT_HD bool pop(int* x) { if (n == 0) return false; *x = v[--n]; return true; }
-};
-
-// One level of traversal.  LEVEL 0 = top-level object (may contain instances when INST), LEVEL 1 = instanced object.
-// ANY: any-hit (intersect_p) — returns at the first accepted primitive and never shrinks tmax.
-// The ray's tmax is passed by reference (Cell semantics of the reference's Ray.t_max).
-template <bool ANY, bool INST, bool COUNT, int LEVEL, typename Stack>
-PT_HD bool traverse_object(const DScene& S, uint32_t obj, f3 ro, f3 rd, float rtime, float& ray_tmax, HitD* hit, Stack& st, int* overflow,
-                           TravCounters* cnt);
-
-template <bool ANY, bool INST, bool COUNT, int LEVEL, typename Stack>
-PT_HD bool test_record(const DScene& S, const f4* rec, f3 ro, f3 rd, float rtime, float& ray_tmax, HitD* hit, Stack& st, int* overflow,
-                       TravCounters* cnt) {
-  f4 v0 = ldg4(rec), v1 = ldg4(rec + 1), v2 = ldg4(rec + 2);
-  uint32_t flags = fbits(v1.w);
-  if (INST && LEVEL == 0 && (flags & PT_REC_INSTANCE)) {
-    // TransformedPrimitive::intersect: inverse-transform the ray, traverse the object, keep its t_max
-    int inst = (int)fbits(v0.w);
-    const InstanceRec& I = S.instances[inst];
-    DRay r;
-    r.o = ro; r.d = rd; r.tmax = ray_tmax; r.time = rtime;
-    DRay q = xform_ray(I.minv, r);
-    float tm = q.tmax;
-    HitD h;
-    // the nested traversal continues on the same stack above a barrier entry
-    bool found = traverse_object<ANY, false, COUNT, 1, Stack>(S, (uint32_t)I.object, q.o, q.d, rtime, tm, &h, st, overflow, cnt);
-    if (!found) return false;
-    if (!ANY) {
-      ray_tmax = tm;
-      *hit = h;
-      hit->instance = inst;
-    }
-    return true;
-  }
-  if (COUNT) cnt->tris++;
-  TriHitD th;
-  if (!tri_test(xyz(v0), xyz(v1), xyz(v2), flags, ro, rd, ray_tmax, &th)) return false;
-  if (!ANY) {
-    ray_tmax = th.t;
-    hit->tri = (int)fbits(v0.w);
-    hit->instance = -1;
-    hit->t = th.t; hit->b0 = th.b0; hit->b1 = th.b1; hit->b2 = th.b2;
-  }
-  return true;
-}
-
 #define PT_STACK_BARRIER ((int)0x7fffffff)
-
-template <bool ANY, bool INST, bool COUNT, int LEVEL, typename Stack>
-PT_HD bool traverse_object(const DScene& S, uint32_t obj, f3 ro, f3 rd, float rtime, float& ray_tmax, HitD* hit, Stack& st, int* overflow,
-                           TravCounters* cnt) {
-  const ObjectRec& O = S.objects[obj];
-  const f4* recs = S.recs + (size_t)O.rec_base * 3;
-  if (O.n_prims == 0) return false;
-  if (O.single) return test_record<ANY, INST, COUNT, LEVEL, Stack>(S, recs, ro, rd, rtime, ray_tmax, hit, st, overflow, cnt);
-  float tmin, tmax;
-  if (!bounds_range(O.bmin, O.bmax, ro, rd, ray_tmax, &tmin, &tmax)) return false;
-  const QNode* nodes = S.nodes + O.node_base;
-  const float idx = 1.0f / rd.x, idy = 1.0f / rd.y, idz = 1.0f / rd.z;
-  const int sgx = signbit_(rd.x) ? 1 : 0, sgy = signbit_(rd.y) ? 1 : 0, sgz = signbit_(rd.z) ? 1 : 0;
-  bool found = false;
-  if (LEVEL == 1 && !st.push(PT_STACK_BARRIER)) { *overflow = 1; return false; }
-  int cur = 0;  // node 0 = root
-  bool have = true;
-  while (have) {
-    if (COUNT) cnt->nodes++;
-    int first = -1, count = 0;
-    if (cur >= 0) {
-      const QNode* nd = nodes + cur;
-      i4 meta = ldgi4(&nd->meta);
-      if (meta.x & 0x100) {  // leaf node in the reference's own form (root leaf, or > 8 primitives)
-        first = meta.y;
-        count = meta.z;
-      } else {
-        // test_aabb: lane k, per axis: tmin = max(tmin, (near - o) * idir); tmax = min(tmax, (far - o) * idir)
-        f4 nx = ldg4(sgx ? &nd->hi[0] : &nd->lo[0]), fx = ldg4(sgx ? &nd->lo[0] : &nd->hi[0]);
-        f4 ny = ldg4(sgy ? &nd->hi[1] : &nd->lo[1]), fy = ldg4(sgy ? &nd->lo[1] : &nd->hi[1]);
-        f4 nz = ldg4(sgz ? &nd->hi[2] : &nd->lo[2]), fz = ldg4(sgz ? &nd->lo[2] : &nd->hi[2]);
-        i4 ch = ldgi4(&nd->child);
-        unsigned mask = 0;
-#define PT_LANE(L, BIT)                                                   \
-  {                                                                       \
-    float tn = tmin, tx = tmax, v;                                        \
-    v = (nx.L - ro.x) * idx; tn = PT_SSE_MAX(tn, v);                      \
-    v = (fx.L - ro.x) * idx; tx = PT_SSE_MIN(tx, v);                      \
-    v = (ny.L - ro.y) * idy; tn = PT_SSE_MAX(tn, v);                      \
-    v = (fy.L - ro.y) * idy; tx = PT_SSE_MIN(tx, v);                      \
-    v = (nz.L - ro.z) * idz; tn = PT_SSE_MAX(tn, v);                      \
-    v = (fz.L - ro.z) * idz; tx = PT_SSE_MIN(tx, v);                      \
-    if (tx >= tn) mask |= BIT;                                            \
-  }
-        PT_LANE(x, 1u) PT_LANE(y, 2u) PT_LANE(z, 4u) PT_LANE(w, 8u)
-#undef PT_LANE
-        if (mask) {
-          int at = meta.x & 3, al = (meta.x >> 2) & 3, ar = (meta.x >> 4) & 3;
-          int s_t = at == 0 ? sgx : (at == 1 ? sgy : sgz);
-          int s_l = al == 0 ? sgx : (al == 1 ? sgy : sgz);
-          int s_r = ar == 0 ? sgx : (ar == 1 ? sgy : sgz);
-          uint32_t order = kOrderTable[mask * 8 + (unsigned)((s_t << 2) | (s_l << 1) | s_r)];
-          while ((order & 0x4) == 0) {
-            int k = (int)(order & 3);
-            int c = k == 0 ? ch.x : (k == 1 ? ch.y : (k == 2 ? ch.z : ch.w));
-            if (c != PT_EMPTY) {
-              if (!st.push(c)) { *overflow = 1; }
-            }
-            order >>= 4;
-          }
-        }
-      }
-    } else {  // inline leaf reference
-      unsigned e = (unsigned)~cur;
-      first = (int)(e >> PT_LEAF_BITS);
-      count = (int)(e & ((1u << PT_LEAF_BITS) - 1u)) + 1;
-    }
-    if (count > 0) {
-      bool any = false;
-      const f4* r = recs + (size_t)first * 3;
-      for (int i = 0; i < count; i++, r += 3) {
-        if (test_record<ANY, INST, COUNT, LEVEL, Stack>(S, r, ro, rd, rtime, ray_tmax, hit, st, overflow, cnt)) {
-          if (ANY) {
-            if (LEVEL == 1) {  // unwind this level's entries
-              int x;
-              while (st.pop(&x) && x != PT_STACK_BARRIER) {}
-            }
-            return true;
-          }
-          any = true;
-        }
-      }
-      if (any) { tmax = ray_tmax; found = true; }
-    }
-    have = st.pop(&cur);
-    if (LEVEL == 1 && have && cur == PT_STACK_BARRIER) have = false;
-  }
-  return found;
-}
-
-// Scene::intersect / Scene::intersect_p on the top-level object
-template <bool INST, bool COUNT, typename Stack>
-PT_HD bool scene_intersect(const DScene& S, f3 ro, f3 rd, float rtime, float& tmax, HitD* hit, Stack& st, int* overflow, TravCounters* cnt) {
-  hit->tri = -1;
-  hit->instance = -1;
-  return traverse_object<false, INST, COUNT, 0, Stack>(S, 0u, ro, rd, rtime, tmax, hit, st, overflow, cnt);
-}
-template <bool INST, bool COUNT, typename Stack>
-PT_HD bool scene_intersect_p(const DScene& S, f3 ro, f3 rd, float rtime, float tmax, Stack& st, int* overflow, TravCounters* cnt) {
-  HitD h;
-  return traverse_object<true, INST, COUNT, 0, Stack>(S, 0u, ro, rd, rtime, tmax, &h, st, overflow, cnt);
-}
 
 }  // namespace ptd

@@ -1,6 +1,6 @@
-// kernels.cuh — __global__ wrappers around the PT_HD stage bodies (dshade.cuh, dtrav.cuh, dfilm.cuh).
-// Launch shape: persistent grid-stride kernels, grid = k * 148 SMs (B200), queue sizes read by the host between
-// bounces.  All kernels of a render run on one stream in program order.
+// kernels.cuh — __global__ wrappers around the PT_HD stage bodies (dshade.cuh, dtrav2.cuh, dfilm.cuh).
+// Launch shapes: k_trace = persistent warps with dynamic ray fetch (PT_TRACE_MINBLOCKS x 148 SMs on B200); the
+// streaming kernels (raygen, shade, finish, film) get about one item per thread (launch.cuh).
 #pragma once
 #include "launch.cuh"
 #include "dfilm.cuh"

@@ -1,5 +1,6 @@
-// launch.cuh — launch macro shared by the translation units of the library (device_api.cu: exact arithmetic;
-// shade_tu.cu: the shading stage, compiled with approximate division / square root).
+// launch.cuh — launch macro and launch-shape constants shared by the translation units of the library (device_api.cu
+// and shade_tu.cu, the shading stage; both are compiled with exact IEEE division / square root and without FMA
+// contraction - `make FAST_SHADE=1` is an opt-in experiment, never used for a reported number).
 #pragma once
 #if defined(PT_HOSTCHECK)
 // tests/hostcheck: the SAME sources compiled by g++ against a serial stand-in for the CUDA runtime, to check the

@@ -12,13 +12,23 @@ def spp_shard(spp_total, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def effective_spp(sampler_type, spp):
+    """Samples per pixel the sampler really takes: SobolSampler rounds the request up to a power of two
+    (samplers/sobol.rs:24), as pt_scene_create does on the device."""
+    spp = max(int(spp), 1)
+    if int(sampler_type) == 1:   # PT_SAMPLER_SOBOL
+        return 1 << (spp - 1).bit_length()
+    return spp
+
+
 def shard_opts(sampler_type, spp_total, rank, world):
     """pt_render_partial options of this rank.  Halton / Sobol samples are pure functions of (pixel, sample number):
-    shard the sample numbers.  Sampler "random" draws from one sequential PCG32 stream per 16x16 render tile
-    (samplers/random.rs), so only whole tiles can be split: interleave the tiles across ranks."""
+    shard the sample numbers (of the EFFECTIVE count, see effective_spp).  Sampler "random" draws from one sequential
+    PCG32 stream per 16x16 render tile (samplers/random.rs), so only whole tiles can be split: interleave the tiles
+    across ranks."""
     if int(sampler_type) == 2:   # PT_SAMPLER_RANDOM
         return {"shard_index": int(rank), "shard_count": int(world)}
-    b, e = spp_shard(spp_total, rank, world)
+    b, e = spp_shard(effective_spp(sampler_type, spp_total), rank, world)
     return {"spp_begin": b, "spp_end": e}
 
 
@@ -39,6 +49,10 @@ def reduce_film(film, dst=0, group=None):
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        if film.is_cuda:
+            # NCCL is ordered on torch's current stream only; pt_film_resolve launches on the library's own stream
+            import torch
+            torch.cuda.current_stream(film.device).synchronize()
     return film
 
 

@@ -1,6 +1,8 @@
 import os
 import sys
 
+import subprocess
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,3 +32,33 @@ def oracle(built):
 def P(built):
     import pbrt_r3_b200
     return pbrt_r3_b200
+
+
+BUILD = os.path.join(ROOT, "tests", "hostcheck", "_build")
+HOSTCHECK_LIB = os.path.join(BUILD, "libpbrt_hostcheck.so")
+
+
+def build_hostcheck():
+    """tests/hostcheck: the product's CUDA sources compiled by g++ against a serial stand-in for the CUDA runtime (TEST
+    INFRASTRUCTURE; the product library never contains this build)."""
+    os.makedirs(BUILD, exist_ok=True)
+    csrc = os.path.join(ROOT, "pbrt-r3_b200", "csrc")
+    srcs = [os.path.join(csrc, "cuda", "device_api.cu")] + [os.path.join(csrc, "host", f) for f in ("front.cpp", "api_common.cpp", "bvh_build.cpp", "scene_accel.cpp")]
+    deps = srcs + [os.path.join(csrc, "cuda", f) for f in os.listdir(os.path.join(csrc, "cuda")) if f.endswith((".cuh", ".cu"))]
+    deps += [os.path.join(csrc, "host", f) for f in os.listdir(os.path.join(csrc, "host")) if f.endswith(".h")]
+    deps += [os.path.join(ROOT, "tests", "hostcheck", "cuda_shim.h"), os.path.join(ROOT, "include", "pbrt_r3_b200.h")]
+    if not os.path.exists(HOSTCHECK_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOSTCHECK_LIB) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-DPT_HOSTCHECK", "-DPT_NCS=3", "-I", os.path.join(ROOT, "tests", "hostcheck"),
+                               "-x", "c++", "-o", HOSTCHECK_LIB] + srcs + ["-ldl"])
+    return HOSTCHECK_LIB
+
+
+@pytest.fixture(scope="module")
+def HC(P):
+    lib = build_hostcheck()
+    os.environ["PBRT_R3_B200_DATA"] = os.path.join(ROOT, "pbrt-r3_b200", "data")
+    saved = P.capi._lib
+    P.capi._lib = P.capi.load(lib)
+    yield P
+    P.capi._lib = saved
+    os.environ.pop("PBRT_R3_B200_DATA", None)

@@ -9,26 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BUILD = os.path.join(ROOT, "tests", "hostcheck", "_build")
-LIB = os.path.join(BUILD, "libpbrt_hostcheck.so")
-
-
-@pytest.fixture(scope="module")
-def HC(P):
-    os.makedirs(BUILD, exist_ok=True)
-    csrc = os.path.join(ROOT, "pbrt-r3_b200", "csrc")
-    srcs = [os.path.join(csrc, "cuda", "device_api.cu")] + [os.path.join(csrc, "host", f) for f in ("front.cpp", "api_common.cpp", "bvh_build.cpp", "scene_accel.cpp")]
-    deps = srcs + [os.path.join(csrc, "cuda", f) for f in os.listdir(os.path.join(csrc, "cuda")) if f.endswith(".cuh")] + [os.path.join(ROOT, "tests", "hostcheck", "cuda_shim.h")]
-    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-DPT_HOSTCHECK", "-DPT_NCS=3", "-I", os.path.join(ROOT, "tests", "hostcheck"),
-                               "-x", "c++", "-o", LIB] + srcs + ["-ldl"])
-    os.environ["PBRT_R3_B200_DATA"] = os.path.join(ROOT, "pbrt-r3_b200", "data")
-    saved = P.capi._lib
-    P.capi._lib = P.capi.load(LIB)
-    yield P
-    P.capi._lib = saved
-    os.environ.pop("PBRT_R3_B200_DATA", None)
+# the HC fixture (the hostcheck build loaded through the same ctypes wrappers) lives in conftest.py
 
 
 def _cmp_li(P, text, n, spp, tol_frac):
