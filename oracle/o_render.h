@@ -390,7 +390,9 @@ struct Film {
 
 // SampleIntegratorCore::render / render_tile (sampler.rs:201-325). spp range [s0, s1) of every pixel; 0,0 = all.
 template <int NC>
-inline void render(Scene<NC>& sc, int n_threads, int s0, int s1, float* out_rgb, float* out_xyzw, Counters* total) {
+// shard_count > 1: only the 16x16 render tiles whose number is congruent to shard_index (the product's tile sharding,
+// used by bench.py to time a bounded sample of a large workload).
+inline void render(Scene<NC>& sc, int n_threads, int s0, int s1, float* out_rgb, float* out_xyzw, Counters* total, int shard_index = 0, int shard_count = 1) {
   const pt_scene_desc* d = sc.d;
   const int* sb = d->film.sample_bounds;
   const int TILE = 16;
@@ -405,6 +407,7 @@ inline void render(Scene<NC>& sc, int n_threads, int s0, int s1, float* out_rgb,
     for (;;) {
       int ti = next.fetch_add(1);
       if (ti >= ntx * nty) break;
+      if (shard_count > 1 && ti % shard_count != shard_index) continue;
       int tx = ti % ntx, ty = ti / ntx;
       int tile[4] = {sb[0] + tx * TILE, sb[1] + ty * TILE, std::min(sb[0] + tx * TILE + TILE, sb[2]), std::min(sb[1] + ty * TILE + TILE, sb[3])};
       Sampler sampler(&sc.scfg, (uint32_t)ti);
@@ -412,9 +415,9 @@ inline void render(Scene<NC>& sc, int n_threads, int s0, int s1, float* out_rgb,
       for (int y = tile[1]; y < tile[3]; y++)
         for (int x = tile[0]; x < tile[2]; x++) {
           sampler.start_pixel(x, y);
-          for (int s = 0; s < spp; s++) {
+          const bool indexed = d->sampler.type != PT_SAMPLER_RANDOM;  // halton / sobol: sample s is a pure function of (pixel, s)
+          for (int s = indexed ? std::max(s0, 0) : 0; s < (indexed ? std::min(s1, spp) : spp); s++) {
             if (s > 0) sampler.set_sample_number(s);
-            if (d->sampler.type != PT_SAMPLER_RANDOM && (s < s0 || s >= s1)) continue;
             CameraSample cs;
             Vec2 u = sampler.get_2d();
             cs.p_film = Vec2((Float)x, (Float)y) + u;

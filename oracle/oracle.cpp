@@ -97,6 +97,15 @@ int orc_render(orc_scene* s, int n_threads, int s0, int s1, float* out_rgb, floa
   return 0;
 }
 
+// orc_render restricted to the render tiles ti with ti % shard_count == shard_index
+int orc_render_shard(orc_scene* s, int n_threads, int s0, int s1, int shard_index, int shard_count, float* out_rgb, float* out_xyzw, uint64_t* counters) {
+  Counters c;
+  if (s->nc == 3) render(*s->s3, n_threads, s0, s1, out_rgb, out_xyzw, &c, shard_index, shard_count);
+  else render(*s->s60, n_threads, s0, s1, out_rgb, out_xyzw, &c, shard_index, shard_count);
+  if (counters) { counters[0] = c.camera_rays; counters[1] = c.regular_rays; counters[2] = c.shadow_rays; counters[3] = c.nodes; counters[4] = c.tris; counters[5] = c.vertices; }
+  return 0;
+}
+
 int orc_intersect(orc_scene* s, const float* rays, uint32_t n, int32_t* prim, float* t, float* bary, uint64_t* nodes, uint64_t* tris) {
   const SceneGeom& g = s->nc == 3 ? s->s3->geom : s->s60->geom;
   Counters c;

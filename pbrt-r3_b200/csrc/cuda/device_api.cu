@@ -35,6 +35,10 @@ void launch_shade(int n_channels, int cls, int grid, cudaStream_t stream, const 
 
 // default path slots per wave (RGB): 6 waves of 6.4 M paths in flight = 10 GB of path state on a 180 GB part; measured
 // optimum of the wave-size / waves-in-flight sweep (profiles/r1_wave_pipelining.md)
+// shade kernels of one bounce on one stream per shading class (1) or back to back on the render stream (0)
+#ifndef PT_SHADE_STREAMS
+#define PT_SHADE_STREAMS 1
+#endif
 #ifndef PT_WAVE_PATHS_RGB
 #define PT_WAVE_PATHS_RGB 6400000u
 #endif
@@ -105,7 +109,13 @@ using pth::ObjectHost;
 
 }  // namespace
 
+static uint64_t next_scene_uid() {
+  static uint64_t n = 0;
+  return ++n;  // scenes are created by a single-threaded caller (include/pbrt_r3_b200.h)
+}
+
 struct pt_scene {
+  uint64_t uid = next_scene_uid();  // never reused, unlike the address (pt_bvh_node's cache key)
   int device = 0;
   int n_sm = 148;
   DScene h;            // host copy (device pointers inside)
@@ -114,6 +124,10 @@ struct pt_scene {
   std::vector<ObjectHost> objects;
   uint32_t max_stack = 0;
   cudaStream_t stream = nullptr;
+  // The shade kernels of one bounce (one per shading class) run side by side on their own streams, forked from and
+  // joined to `stream` with events, so that the tail of one class overlaps the body of the next.
+  cudaStream_t cls_stream[CL_COUNT] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[CL_COUNT] = {};
   // film + wave state
   f4* film = nullptr;
   float* rgb_dev = nullptr;
@@ -121,6 +135,7 @@ struct pt_scene {
   std::unique_ptr<DevBufs> wave_bufs;
   WaveState W;
   Queues Q;
+  Queues Q_cur;                            // Q with the extend queues in the orientation of the bounce being launched
   int* slot_of = nullptr;                  // pixel -> slot maps of the waves in flight (slot_segs x sample-bounds pixels)
   std::unique_ptr<DevBufs> slot_bufs;
   uint32_t slot_segs = 0;
@@ -139,6 +154,11 @@ struct pt_scene {
   std::vector<int> tiles_host;
   int* tiles = nullptr;
   ~pt_scene() {
+    for (int c = 0; c < CL_COUNT; c++) {
+      if (cls_stream[c]) cudaStreamDestroy(cls_stream[c]);
+      if (ev_join[c]) cudaEventDestroy(ev_join[c]);
+    }
+    if (ev_fork) cudaEventDestroy(ev_fork);
     if (stream) cudaStreamDestroy(stream);
     if (d) cudaFree(d);
   }
@@ -268,9 +288,26 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
         recs.push_back(mk4(q[3], q[4], q[5], bitsf(D->tri_flags[p] & 0xffu)));
         recs.push_back(mk4(q[6], q[7], q[8], 0.0f));
       } else {
-        recs.push_back(mk4(0, 0, 0, bitsf((uint32_t)~p)));
+        // instance record: v0.xyz / v2.xyz = a CONSERVATIVE world-space box of the instance for the cull test of
+        // trav_leaf (dtrav2.cuh): TransformedPrimitive::world_bound grown by 1e-3 * (1 + |coordinate|), i.e. four
+        // orders of magnitude above the rounding of the ray transform it stands in for.  Objects with a single
+        // primitive have no bounds test in the reference (the triangle is always tested and counted): infinite box.
+        const pt_instance& I = D->instances[(uint32_t)~p];
+        const ObjectHost& IO = s->objects[(size_t)I.object];
+        float lo[3], hi[3];
+        if (IO.single || IO.ordered.empty()) {
+          for (int a = 0; a < 3; a++) { lo[a] = -INFINITY; hi[a] = INFINITY; }
+        } else {
+          pth::BBox wb = pth::instance_world_bounds(I.m, IO.bounds);
+          for (int a = 0; a < 3; a++) {
+            float g = 1e-3f * (1.0f + fmaxf(fabsf(wb.mn[a]), fabsf(wb.mx[a])));
+            lo[a] = wb.mn[a] - g; hi[a] = wb.mx[a] + g;
+            if (!(lo[a] <= hi[a])) { lo[a] = -INFINITY; hi[a] = INFINITY; }  // NaN / inverted bounds: never cull
+          }
+        }
+        recs.push_back(mk4(lo[0], lo[1], lo[2], bitsf((uint32_t)~p)));
         recs.push_back(mk4(0, 0, 0, bitsf(PT_REC_INSTANCE)));
-        recs.push_back(mk4(0, 0, 0, 0));
+        recs.push_back(mk4(hi[0], hi[1], hi[2], 0));
       }
     }
   }
@@ -280,7 +317,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
 #if PT_TRI_PERM
   {  // three copies on the device, one on the wire: the identity copy is uploaded, k_permute_recs derives the other two
     const size_t n = recs.size();
-    if (n > 0xffffffffull / 3) { pt_set_error("too many triangle records"); return 1; }
+    if (n > 0xffffffffull / 3 || (D->n_instances > 0 && n / 3 >= (1ull << 27))) { pt_set_error("too many triangle records"); return 1; }
     f4* all = nullptr;
     CK(s->bufs.alloc(3 * n, &all));
     if (n > 0) CK(s->bufs.upload_into(all + 2 * n, recs.data(), n));
@@ -507,6 +544,17 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   return 0;
 }
 
+// A render that failed half way leaves queue counters, bins and pixel -> slot maps dirty: drop the buffers so that the
+// next render on this scene allocates and initialises them again (ensure_wave).
+void invalidate_wave_state(pt_scene* s) {
+  cudaStreamSynchronize(s->stream);
+  cudaGetLastError();
+  s->wave_bufs.reset();
+  s->slot_bufs.reset();
+  s->wave_cap = 0;
+  s->slot_segs = 0;
+}
+
 // Path state for `nseg` waves in flight of up to `seg_cap` paths each (one wave: nseg = 1).  Buffers only grow.
 int ensure_wave(pt_scene* s, uint32_t seg_cap, uint32_t nseg = 1) {
   seg_cap = std::max(seg_cap, 1u);
@@ -545,6 +593,30 @@ int ensure_wave(pt_scene* s, uint32_t seg_cap, uint32_t nseg = 1) {
   CK(B.alloc((size_t)cap * CL_COUNT, &Q.bins));
   s->wave_cap = cap;
   return 0;
+}
+
+// k_shade for every shading class of the scene over the bins the last k_trace filled: forked onto the class streams
+// after everything queued on s->stream so far, joined back before anything queued later.  Returns the launch count.
+int shade_classes(pt_scene* s, int NC, int grid, unsigned long long* vc) {
+  int n = 0;
+#if PT_SHADE_STREAMS
+  int live = 0;
+  for (int c = 0; c < CL_COUNT; c++) live += (s->class_mask >> c) & 1;
+  const bool fork = live > 1 && s->ev_fork != nullptr;
+  if (fork) cudaEventRecord(s->ev_fork, s->stream);
+  for (int c = 0; c < CL_COUNT; c++)
+    if (s->class_mask & (1u << c)) {
+      cudaStream_t q = fork ? s->cls_stream[c] : s->stream;
+      if (fork) cudaStreamWaitEvent(q, s->ev_fork, 0);
+      launch_shade(NC, c, grid, q, s->h, s->W, s->Q_cur, vc);
+      if (fork) { cudaEventRecord(s->ev_join[c], q); cudaStreamWaitEvent(s->stream, s->ev_join[c], 0); }
+      n++;
+    }
+#else
+  for (int c = 0; c < CL_COUNT; c++)
+    if (s->class_mask & (1u << c)) { launch_shade(NC, c, grid, s->stream, s->h, s->W, s->Q_cur, vc); n++; }
+#endif
+  return n;
 }
 
 struct WaveTotals {
@@ -593,8 +665,8 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     } else if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
-      for (int c = 0; c < CL_COUNT; c++)
-        if (s->class_mask & (1u << c)) { launch_shade(NC, c, gs, s->stream, s->h, W, Q, vc); T->launches++; }
+      s->Q_cur = Q;
+      T->launches += shade_classes(s, NC, gs, vc);
       CK(cudaGetLastError());
     }
     if (timed) cudaEventRecord(e2, s->stream);
@@ -717,7 +789,11 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   uint32_t pix_chunk, ns_wave;
   if ((uint64_t)npix_total * (uint64_t)ns_total <= cap) { pix_chunk = npix_total; ns_wave = (uint32_t)ns_total; }
   else if (npix_total <= cap) { pix_chunk = npix_total; ns_wave = std::max(1u, cap / npix_total); }
-  else { pix_chunk = cap; ns_wave = 1; }
+  else {  // more sample pixels than path slots (4K films): equal pixel chunks, one sample number per wave
+    const uint32_t n_chunks = (npix_total + cap - 1) / cap;
+    pix_chunk = (npix_total + n_chunks - 1) / n_chunks;
+    ns_wave = 1;
+  }
   const int* sb = s->h.film.sample_bounds;
   const int* cb = s->h.film.cropped_pixel_bounds;
   const int sbw = sb[2] - sb[0];
@@ -861,8 +937,8 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     } else if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
-      for (int c = 0; c < CL_COUNT; c++)
-        if (s->class_mask & (1u << c)) { launch_shade(NC, c, gs, s->stream, s->h, W, Q, vc); T.launches++; }
+      s->Q_cur = Q;
+      T.launches += shade_classes(s, NC, gs, vc);
       if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_shade launch failed"); break; }
     }
     if (timed) cudaEventRecord(e3, s->stream);
@@ -883,7 +959,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     std::swap(Q.ext, Q.ext_next);
   }
   if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); }
-  if (rc) return 1;
+  if (rc) { invalidate_wave_state(s); return 1; }
   // leave the pixel -> slot maps empty for the next render
   for (uint32_t k = 0; k < nseg; k++)
     if (segs[k].map_npix > 0) {
@@ -1029,6 +1105,11 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out) {
   CK(cudaGetDeviceProperties(&prop, device));
   s->n_sm = prop.multiProcessorCount;
   CK(cudaStreamCreate(&s->stream));
+  CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  for (int c = 0; c < CL_COUNT; c++) {
+    CK(cudaStreamCreateWithFlags(&s->cls_stream[c], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->ev_join[c], cudaEventDisableTiming));
+  }
   if (build_scene(s.get(), desc)) return 1;
   *out = s.release();
   return 0;
@@ -1075,7 +1156,12 @@ int pt_render_partial(pt_scene* s, const pt_render_opts* opts, float** dev_film_
   int rc;
   if (s->h.sampler.type == PT_SAMPLER_RANDOM) rc = s->h.n_channels == 3 ? render_waves_random<3>(s, opts, stats) : render_waves_random<PT_NCS>(s, opts, stats);
   else rc = s->h.n_channels == 3 ? render_waves<3>(s, opts, stats) : render_waves<PT_NCS>(s, opts, stats);
-  if (rc) return rc;
+  if (rc) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    invalidate_wave_state(s);
+    return rc;
+  }
   CK(cudaEventRecord(e1, s->stream));
   CK(cudaEventSynchronize(e1));
   float ms = 0;
@@ -1211,7 +1297,7 @@ static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_
   if (bounce && (s->h.n_lights > 0 || s->h.integrator.type != PT_INTEGRATOR_PATH)) {
     WaveTotals T;
     int rc = s->h.n_channels == 3 ? run_bounces<3>(s, n, false, false, &T) : run_bounces<PT_NCS>(s, n, false, false, &T);
-    if (rc) return rc;
+    if (rc) { invalidate_wave_state(s); return rc; }
     if (s->h.n_channels == 3) PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<3>)(s->h, s->W, 0u, n);
     else PT_LAUNCH(grid_for(s, n, 256, 8), 256, s->stream, k_finish<PT_NCS>)(s->h, s->W, 0u, n);
     CK(cudaGetLastError());
@@ -1268,12 +1354,12 @@ int pt_bvh_info(pt_scene* s, uint32_t object, uint32_t* n_nodes, uint32_t* n_pri
 
 int pt_bvh_node(pt_scene* s, uint32_t object, uint32_t node, float* boxes24, int64_t* children4, int32_t* axes3, int32_t* is_leaf) {
   if (!s || object >= s->objects.size()) { pt_set_error("bad object"); return 1; }
-  static thread_local const pt_scene* cached_scene = nullptr;
+  static thread_local uint64_t cached_uid = 0;
   static thread_local uint32_t cached_obj = 0;
   static thread_local std::vector<pth::RefNodeH> ref;
-  if (cached_scene != s || cached_obj != object || ref.empty()) {
+  if (cached_uid != s->uid || cached_obj != object || ref.empty()) {
     pth::flatten_reference(s->objects[object].bvh, &ref);
-    cached_scene = s;
+    cached_uid = s->uid;
     cached_obj = object;
   }
   if (node >= ref.size()) { pt_set_error("bad node"); return 1; }

@@ -17,6 +17,7 @@ namespace ptd {
 #define PT_EMPTY ((int)0x80000000)
 #define PT_LEAF_BITS 3
 #define PT_REC_INSTANCE 0x100u
+#define PT_LEAF_REMAINDER 0x40000000u  /* inline-leaf stack entries of two-level scenes: first record < 2^27 */
 #define PT_MAX_STACK 96
 
 struct alignas(16) QNode {

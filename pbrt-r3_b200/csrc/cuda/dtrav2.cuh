@@ -7,7 +7,8 @@
 // node visit order, leaf order, t_max shrinking and float operations, so primitive ids and the node / triangle visit
 // counters still equal the CPU path's.
 //
-// Stack entries: >= 0 node index (relative to the current object), < 0 inline leaf ~((first << 3) | (count - 1)),
+// Stack entries: >= 0 node index (relative to the current object), < 0 inline leaf ~((first << 3) | (count - 1))
+// (bit 30 = PT_LEAF_REMAINDER marks the rest of a top-level leaf that an instance interrupted: not a node visit),
 // PT_STACK_BARRIER = "the instanced object's traversal ends here, return to the top level".  When an instance is
 // met inside a top-level leaf, the leaf's remaining primitives are pushed back as inline-leaf entries below the
 // barrier, so a leaf is processed in order even though the nested traversal runs in between.
@@ -29,6 +30,10 @@
 #endif
 #ifndef PT_OPT_POPLUT
 #define PT_OPT_POPLUT 0
+#endif
+// conservative world-space cull of instance records before the exact (transformed) object-bounds test
+#ifndef PT_INST_CULL
+#define PT_INST_CULL 1
 #endif
 // triangle records in the three axis orders of the watertight test (dscene.cuh): no per-triangle component selects
 #ifndef PT_TRI_PERM
@@ -83,7 +88,8 @@ PT_HD void trav_set_ray_idir(Trav& T, f3 o, f3 d, float idx, float idy, float id
   int ky = kx + 1; if (ky == 3) ky = 0;
   float dx = comp(d, kx), dy = comp(d, ky), dz = comp(d, kz);
   T.kz = kz;
-  T.shx = -dx / dz; T.shy = -dy / dz; T.shz = 1.0f / dz;
+  T.shx = -dx / dz; T.shy = -dy / dz;
+  T.shz = kz == 0 ? idx : (kz == 1 ? idy : idz);  // 1 / d[kz]: the same quotient as the slab reciprocal of that axis
 }
 
 // everything trav_set_ray derives from a ray <-> 15 words of the stack's save area
@@ -312,8 +318,9 @@ PT_HD bool trav_node_step(const DScene& S, Trav& T, Stack& st, int* overflow, Tr
   const char* nbase = reinterpret_cast<const char*>(S.nodes + T.node_base);
   {
     if (T.cur < 0) {  // inline leaf or leaf remainder
-      if (COUNT) cnt->nodes++;
       unsigned e = (unsigned)~T.cur;
+      if (COUNT && !(INST && (e & PT_LEAF_REMAINDER))) cnt->nodes++;  // a leaf remainder is not a node visit of the reference traversal
+      if (INST) e &= ~PT_LEAF_REMAINDER;
       T.lf = (int)(e >> PT_LEAF_BITS);
       T.lc = (int)(e & ((1u << PT_LEAF_BITS) - 1u)) + 1;
       return false;
@@ -448,6 +455,19 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
     f4 v0 = ldg4(r), v1 = ldg4(r + 1), v2 = ldg4(r + 2);
     if (INST && (fbits(v1.w) & PT_REC_INSTANCE)) {
       // TransformedPrimitive::intersect[_p] (only top-level leaves hold instances)
+#if PT_INST_CULL
+      // 5 of 6 instance records met by a ray of the 1000-instance scene fail the object-bounds test below, after the ray
+      // transform and four IEEE divisions.  The record carries a conservative world-space box of the instance (grown far
+      // beyond the rounding of the transform, device_api.cu): a world ray that misses it cannot pass the exact test, so
+      // it is skipped without touching the instance (63 % of the records).  NaN slab products are dropped by
+      // fmaxf / fminf, i.e. they loosen the test.
+      {
+        const bool nx = (T.sg & 1) != 0, ny = (T.sg & 2) != 0, nz = (T.sg & 4) != 0;
+        const float t0 = fmaxf(fmaxf(((nx ? v2.x : v0.x) - T.o.x) * T.idx, ((ny ? v2.y : v0.y) - T.o.y) * T.idy), fmaxf(((nz ? v2.z : v0.z) - T.o.z) * T.idz, 0.0f));
+        const float t1 = fminf(fminf(((nx ? v0.x : v2.x) - T.o.x) * T.idx, ((ny ? v0.y : v2.y) - T.o.y) * T.idy), fminf(((nz ? v0.z : v2.z) - T.o.z) * T.idz, T.ray_tmax));
+        if (t0 > t1) continue;
+      }
+#endif
       int inst = (int)fbits(v0.w);
       const InstanceRec& I = S.instances[inst];
       const ObjectRec& O = S.objects[I.object];
@@ -479,8 +499,7 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
       while (rest > 0) {  // last chunk first so that the chunks pop in order
         int nchunks = (rest + 7) >> 3;
         int cfirst = rfirst + (nchunks - 1) * 8, ccount = rest - (nchunks - 1) * 8;
-        if (!st.push(~(int)(((unsigned)cfirst << PT_LEAF_BITS) | (unsigned)(ccount - 1)))) *overflow = 1;
-        if (COUNT) cnt->nodes--;  // a leaf remainder is not a node visit of the reference traversal
+        if (!st.push(~(int)(PT_LEAF_REMAINDER | ((unsigned)cfirst << PT_LEAF_BITS) | (unsigned)(ccount - 1)))) *overflow = 1;
         rest -= ccount;
       }
       if (!st.push(PT_STACK_BARRIER)) *overflow = 1;

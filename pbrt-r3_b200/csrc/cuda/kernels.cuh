@@ -360,8 +360,10 @@ __global__ void k_finish(const __grid_constant__ DScene S, WaveState W, uint32_t
 __global__ void k_permute_recs(f4* all, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const f4 v = all[2 * (size_t)n + i];
-    all[i] = mk4(v.y, v.z, v.x, v.w);
-    all[(size_t)n + i] = mk4(v.z, v.x, v.y, v.w);
+    // instance records hold a world-space box, read in x, y, z order whatever the copy (trav_leaf)
+    const bool inst = (fbits(all[2 * (size_t)n + (i / 3u) * 3u + 1u].w) & PT_REC_INSTANCE) != 0u;
+    all[i] = inst ? v : mk4(v.y, v.z, v.x, v.w);
+    all[(size_t)n + i] = inst ? v : mk4(v.z, v.x, v.y, v.w);
   }
 }
 

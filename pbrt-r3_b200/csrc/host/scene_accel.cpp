@@ -45,6 +45,8 @@ BBox xform_bbox(const float* m, const BBox& b) {
 
 }  // namespace
 
+BBox instance_world_bounds(const float* instance_to_world, const BBox& b) { return xform_bbox(instance_to_world, b); }
+
 std::string build_objects(const pt_scene_desc* D, std::vector<ObjectHost>* out) {
   out->clear();
   out->resize(D->n_objects);

@@ -17,6 +17,9 @@ struct ObjectHost {
   BBox bounds;
 };
 
+// TransformedPrimitive::world_bound of an instance of an object with bounds `b` (Transform::transform_bounds)
+BBox instance_world_bounds(const float* instance_to_world, const BBox& b);
+
 // returns "" on success, otherwise an error message
 std::string build_objects(const pt_scene_desc* D, std::vector<ObjectHost>* out);
 

@@ -31,6 +31,7 @@ def load():
     lib.orc_scene_create.argtypes = [vp]
     lib.orc_scene_destroy.argtypes = [vp]
     lib.orc_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.orc_render_shard.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.orc_intersect.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
     lib.orc_intersect_p.argtypes = [vp, vp, C.c_uint32, vp]
     lib.orc_sampler_values.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
@@ -95,12 +96,12 @@ class OracleScene:
             self.lib.orc_scene_destroy(self.h)
             self.h = None
 
-    def render(self, threads=None, s0=0, s1=0, want_xyzw=False):
+    def render(self, threads=None, s0=0, s1=0, want_xyzw=False, shard_index=0, shard_count=1):
         H, W, _ = self.host.image_shape
         rgb = np.zeros((H, W, 3), np.float32)
         xyzw = np.zeros((H, W, 4), np.float32) if want_xyzw else None
         cnt = np.zeros(6, np.uint64)
-        self.lib.orc_render(self.h, threads or os.cpu_count() or 1, s0, s1, _ptr(rgb), _ptr(xyzw), _ptr(cnt))
+        self.lib.orc_render_shard(self.h, threads or os.cpu_count() or 1, s0, s1, shard_index, shard_count, _ptr(rgb), _ptr(xyzw), _ptr(cnt))
         stats = dict(zip(["camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"], [int(v) for v in cnt]))
         return (rgb, stats, xyzw) if want_xyzw else (rgb, stats)
 

@@ -210,7 +210,7 @@ def test_light_distribution_bit_exact(P, pair):
         wb = orc.world_bound()
         pts = np.random.RandomState(2).uniform(wb[:3], wb[3:], (200, 3)).astype(np.float32)
         a, b = sc.light_distribution(pts), orc.light_distribution(pts)
-        assert np.allclose(a, b, rtol=2e-6, atol=0), np.abs(a - b).max()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (np.abs(a - b) / np.abs(b)).max()
 
 
 @pytest.mark.parametrize("name", ["cornell", "mixed", "grid", "instances"])
@@ -394,6 +394,6 @@ def test_image_random_sampler(P, pair):
     rgb, st = sc.render(collect_counters=1)
     ref, so = orc.render()
     assert rel_rmse(rgb, ref) <= RMSE_TOL, rel_rmse(rgb, ref)
-    for k in ("camera_rays", "regular_rays", "shadow_rays"):
-        assert abs(st[k] - so[k]) <= 1e-3 * so[k], (k, st[k], so[k])
+    for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+        assert st[k] == so[k], (k, st[k], so[k])      # the streams are reproduced: every path draws the same numbers
     assert np.array_equal(rgb, sc.render()[0])
