@@ -4,6 +4,8 @@
 // PARITY UNPINNED at the image level (the Rust reference cannot be built here); leaf arithmetic is pinned by
 // tests/test_oracle_known_answers.py against the reference's own known-answer tests.
 #include "o_render.h"
+#include <atomic>
+#include <thread>
 
 #include <cstdio>
 #include <string>
@@ -122,6 +124,53 @@ int orc_intersect(orc_scene* s, const float* rays, uint32_t n, int32_t* prim, fl
   if (tris) *tris = c.tris;
   return 0;
 }
+// ExhaustiveAccel::intersect (accelerators/exhaustive/accel.rs): no acceleration structure at all - every primitive of
+// the scene in list order against the shrinking t_max, instances through TransformedPrimitive with an exhaustive loop
+// over the object's own primitives.  Independent of the BVH build, the 4-wide flattening and the traversal order, so it
+// catches errors that the oracle's QBVH and the device's share.  (The accelerator's world-bound pre-test is left out.)
+int orc_intersect_exhaustive(orc_scene* s, const float* rays, uint32_t n, int n_threads, int32_t* prim, float* t, int32_t* instance) {
+  const pt_scene_desc* d = s->d;
+  auto obj_prims = [&](uint32_t k, const int32_t** p, size_t* np) { *p = d->prims + d->obj_first[k]; *np = d->obj_first[k + 1] - d->obj_first[k]; };
+  auto one = [&](uint32_t i) {
+    const float* q = rays + (size_t)i * 8;
+    Ray r(Vec3(q[0], q[1], q[2]), Vec3(q[4], q[5], q[6]), q[3], q[7]);
+    int best = -1, best_inst = -1;
+    float best_t = 0.0f;
+    const int32_t* top; size_t ntop;
+    obj_prims(0, &top, &ntop);
+    for (size_t a = 0; a < ntop; a++) {
+      if (top[a] >= 0) {
+        TriHit th;
+        if (tri_intersect(get_tri(d, top[a]), r, &th)) { r.t_max = th.t; best = top[a]; best_inst = -1; best_t = th.t; }
+      } else {
+        const pt_instance& I = d->instances[~top[a]];
+        Ray ro = transform_ray(mat_of(I.minv), r);
+        const int32_t* op; size_t nop;
+        obj_prims((uint32_t)I.object, &op, &nop);
+        for (size_t b = 0; b < nop; b++) {
+          TriHit th;
+          if (op[b] >= 0 && tri_intersect(get_tri(d, op[b]), ro, &th)) { ro.t_max = th.t; r.t_max = th.t; best = op[b]; best_inst = ~top[a]; best_t = th.t; }
+        }
+      }
+    }
+    if (prim) prim[i] = best;
+    if (t) t[i] = best_t;
+    if (instance) instance[i] = best_inst;
+  };
+  std::atomic<uint32_t> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      uint32_t b = next.fetch_add(64);
+      if (b >= n) break;
+      for (uint32_t i = b; i < std::min(n, b + 64); i++) one(i);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int k = 0; k < std::max(n_threads, 1); k++) th.emplace_back(worker);
+  for (auto& x : th) x.join();
+  return 0;
+}
+
 int orc_intersect_p(orc_scene* s, const float* rays, uint32_t n, uint8_t* occluded) {
   const SceneGeom& g = s->nc == 3 ? s->s3->geom : s->s60->geom;
   for (uint32_t i = 0; i < n; i++) {

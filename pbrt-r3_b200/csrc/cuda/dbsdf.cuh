@@ -458,7 +458,7 @@ PT_HD void tri_verts(const DScene& S, int tri, f3* p0, f3* p1, f3* p2) {
 }
 
 // interaction part of Triangle::intersect in the triangle's own space (rd = ray direction in that space)
-PT_HDN SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, float b2) {
+PT_HD1 SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, float b2) {
   f3 p0, p1, p2;
   tri_verts(S, tri, &p0, &p1, &p2);
   uint32_t flags = ldg(S.tri_flags + tri);
@@ -548,7 +548,7 @@ PT_HD void tri_point_normal(const DScene& S, int tri, f3 rd, float b0, float b1,
 }
 
 // Transform::transform_surface_interaction (instance -> world)
-PT_HDN SurfD surf_to_world(const InstanceRec& I, const SurfD& s) {
+PT_HD1 SurfD surf_to_world(const InstanceRec& I, const SurfD& s) {
   SurfD r = s;
   const float* m = I.m;
   float x = s.p.x, y = s.p.y, z = s.p.z;
@@ -609,7 +609,7 @@ PT_HD bool spectrum_black(const DScene& S, int idx, bool clamp0) {
 // Spectra that the reference clamps (clamp_zero) are clamped on the HOST at upload when a negative value is
 // present, so the device can treat every stored reflectance as already clamped except matte Kd (never clamped).
 template <int NC, int MT = -1>
-PT_HDN void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
+PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   B->n = -1;
   int mi = ldg(S.tri_material + si.tri);
   if (mi < 0) return;
@@ -723,7 +723,7 @@ PT_HDN float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
 // BSDF::f and BSDF::pdf for the same pair of directions (estimate_direct's light sample needs both, sample_lights.rs:
 // 366-380): one pass over the lobes with lobe_f_pdf.  Same sums in the same lobe order as bsdf_f / bsdf_pdf.
 template <int NC, int CM = PT_CM_ANY>
-PT_HDN void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags, Sp<NC>* f_out, float* pdf_out) {
+PT_HD1 void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags, Sp<NC>* f_out, float* pdf_out) {
   *f_out = sp_const<NC>(0.0f);
   *pdf_out = 0.0f;
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);

@@ -8,16 +8,28 @@
 #include <stdint.h>
 #include <string.h>
 
+#ifndef PT_INLINE_SINGLE_SITE
+#define PT_INLINE_SINGLE_SITE 1
+#endif
 #if defined(__CUDACC__)
 #define PT_HD __host__ __device__ __forceinline__
 #define PT_D __device__ __forceinline__
 /* large stage functions: ONE out-of-line copy each keeps the shade kernel inside the instruction cache (ncu: the
    fully inlined kernel was 34K instructions and stalled on no_instruction for 19-63 cycles per issue) */
 #define PT_HDN inline __host__ __device__ __noinline__
+/* stage functions with ONE call site per shade kernel: inlining them does not grow the code, and their argument / result
+   structures (SurfD, LightSampleD, RefPt) stay in registers instead of the local-memory stack frame (ncu: 41 % of the
+   local loads of the shade kernels missed L1, the frames of 16 warps being as large as the cache) */
+#if PT_INLINE_SINGLE_SITE
+#define PT_HD1 __host__ __device__ __forceinline__
+#else
+#define PT_HD1 inline __host__ __device__ __noinline__
+#endif
 #else
 #define PT_HD inline
 #define PT_D inline
 #define PT_HDN inline
+#define PT_HD1 inline
 #endif
 
 namespace ptd {
@@ -106,6 +118,13 @@ PT_HD int popc_(unsigned v) {
   return __popc(v);
 #else
   return __builtin_popcount(v);
+#endif
+}
+PT_HD int ffs_(unsigned v) {  // 1-based index of the lowest set bit, 0 for v == 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v);
+#else
+  return __builtin_ffs((int)v);
 #endif
 }
 PT_HD float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }  // f32::clamp

@@ -429,6 +429,28 @@ PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCo
   while (trav_node_step<INST, COUNT>(S, T, st, overflow, cnt)) {}
 }
 
+// Survivor mask of the n <= 32 records at r of a top-level leaf: bit j is set for a triangle record and for an instance
+// record whose cull test passes.  5 of 6 instance records met by a ray of the 1000-instance scene fail the exact
+// object-bounds test, after the ray transform and four IEEE divisions.  The record carries a CONSERVATIVE world-space box
+// of the instance (grown far beyond the rounding of the transform, device_api.cu): a world ray that misses it cannot pass
+// the exact test, so the record is skipped without touching the instance (63 % of them).  NaN slab products are
+// dropped by fmaxf / fminf, i.e. they loosen the test.
+PT_HD unsigned leaf_survivors(const f4* r, int n, const Trav& T) {
+  const bool nx = (T.sg & 1) != 0, ny = (T.sg & 2) != 0, nz = (T.sg & 4) != 0;
+  unsigned m = 0u;
+  for (int j = 0; j < n; j++, r += 3) {
+    bool keep = true;
+    if (fbits(ldg4(r + 1).w) & PT_REC_INSTANCE) {
+      const f4 lo = ldg4(r), hi = ldg4(r + 2);
+      const float t0 = fmaxf(fmaxf(((nx ? hi.x : lo.x) - T.o.x) * T.idx, ((ny ? hi.y : lo.y) - T.o.y) * T.idy), fmaxf(((nz ? hi.z : lo.z) - T.o.z) * T.idz, 0.0f));
+      const float t1 = fminf(fminf(((nx ? lo.x : hi.x) - T.o.x) * T.idx, ((ny ? lo.y : hi.y) - T.o.y) * T.idy), fminf(((nz ? lo.z : hi.z) - T.o.z) * T.idz, T.ray_tmax));
+      keep = !(t0 > t1);
+    }
+    if (keep) m |= 1u << j;
+  }
+  return m;
+}
+
 // LEAF phase: the pending leaf (intersect_primitives[_p] over recs[lf .. lf + lc) in order) or the barrier, then pop.
 template <bool INST, bool COUNT, typename Stack>
 PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
@@ -451,23 +473,32 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
 #else
   const f4* r = S.recs + ((size_t)T.rec_base + (size_t)first) * 3;
 #endif
-  for (int i = 0; i < count; i++, r += 3) {
-    f4 v0 = ldg4(r), v1 = ldg4(r + 1), v2 = ldg4(r + 2);
+  // Top-level leaves (the only ones that hold instance records) are processed in two passes: first the cull test of
+  // every record of the leaf (a few instructions, all lanes of the warp together), then the surviving records in order.
+  // With the tests interleaved, pass i of the record loop ran the expensive exact instance test (ray transform, four IEEE
+  // divisions, object-bounds test) for the few lanes whose i-th record happened to survive: 3 active lanes per
+  // instruction (ncu, 1000-instance scene).  Now the k-th SURVIVOR of every lane is processed in pass k.  The records of
+  // a lane are still visited in increasing order, and the cull only uses an older (larger) t_max: same results.
+  const bool top = INST && PT_INST_CULL && T.inst < 0;
+  unsigned todo = 0u;
+  int blk = -32, i = -1;
+  for (;;) {
+    if (top) {
+      while (todo == 0u && blk + 32 < count) {
+        blk += 32;
+        todo = leaf_survivors(r + 3 * (size_t)blk, count - blk < 32 ? count - blk : 32, T);
+      }
+      if (todo == 0u) break;
+      i = blk + ffs_(todo) - 1;
+      todo &= todo - 1u;
+    } else {
+      i++;
+      if (i >= count) break;
+    }
+    const f4* ri = r + 3 * (size_t)i;
+    f4 v0 = ldg4(ri), v1 = ldg4(ri + 1), v2 = ldg4(ri + 2);
     if (INST && (fbits(v1.w) & PT_REC_INSTANCE)) {
       // TransformedPrimitive::intersect[_p] (only top-level leaves hold instances)
-#if PT_INST_CULL
-      // 5 of 6 instance records met by a ray of the 1000-instance scene fail the object-bounds test below, after the ray
-      // transform and four IEEE divisions.  The record carries a conservative world-space box of the instance (grown far
-      // beyond the rounding of the transform, device_api.cu): a world ray that misses it cannot pass the exact test, so
-      // it is skipped without touching the instance (63 % of the records).  NaN slab products are dropped by
-      // fmaxf / fminf, i.e. they loosen the test.
-      {
-        const bool nx = (T.sg & 1) != 0, ny = (T.sg & 2) != 0, nz = (T.sg & 4) != 0;
-        const float t0 = fmaxf(fmaxf(((nx ? v2.x : v0.x) - T.o.x) * T.idx, ((ny ? v2.y : v0.y) - T.o.y) * T.idy), fmaxf(((nz ? v2.z : v0.z) - T.o.z) * T.idz, 0.0f));
-        const float t1 = fminf(fminf(((nx ? v0.x : v2.x) - T.o.x) * T.idx, ((ny ? v0.y : v2.y) - T.o.y) * T.idy), fminf(((nz ? v0.z : v2.z) - T.o.z) * T.idz, T.ray_tmax));
-        if (t0 > t1) continue;
-      }
-#endif
       int inst = (int)fbits(v0.w);
       const InstanceRec& I = S.instances[inst];
       const ObjectRec& O = S.objects[I.object];

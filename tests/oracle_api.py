@@ -34,6 +34,7 @@ def load():
     lib.orc_render_shard.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.orc_intersect.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
     lib.orc_intersect_p.argtypes = [vp, vp, C.c_uint32, vp]
+    lib.orc_intersect_exhaustive.argtypes = [vp, vp, C.c_uint32, C.c_int, vp, vp, vp]
     lib.orc_sampler_values.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     lib.orc_camera_rays.argtypes = [vp, vp, vp, C.c_uint32, vp, vp]
     lib.orc_li.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, vp, vp]
@@ -120,6 +121,14 @@ class OracleScene:
         occ = np.zeros(rays.shape[0], np.uint8)
         self.lib.orc_intersect_p(self.h, _ptr(rays), rays.shape[0], _ptr(occ))
         return occ
+
+    def intersect_exhaustive(self, rays, threads=None):
+        """ExhaustiveAccel: every primitive in scene order, no BVH; returns (prim, t, instance)."""
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        prim, t, inst = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.orc_intersect_exhaustive(self.h, _ptr(rays), n, threads or os.cpu_count() or 1, _ptr(prim), _ptr(t), _ptr(inst))
+        return prim, t, inst
 
     def sampler_values(self, pixel_xy, sample_num, dim0, ndims):
         pixel_xy = np.ascontiguousarray(pixel_xy, np.int32).reshape(-1, 2)

@@ -1,0 +1,205 @@
+"""Pins for the boundaries no reference test covers (SURVEY.md 8c "parity unpinned"): properties
+and closed-form answers that hold for the REFERENCE's algorithm whatever restates it, checked on the oracle (CPU), on the
+product's stage code compiled for the host (tests/hostcheck, CPU) and on the CUDA library (-m gpu).
+
+  * Halton (2^i, 3^j) elementary intervals - the check the reference left as a TODO (tests/sampling.rs:183), on the pixel
+    samples of HaltonSampler (samplers/halton.rs:115-162): pins the per-pixel index (offset + n * stride), the multiplicative
+    inverses and dimensions 0 / 1.
+  * Sobol elementary intervals - the reference's own test (tests/sampling.rs:136-205: SobolSampler over a 10x10 film,
+    pixel (0,0), 2^k samples land once in every (2^i x 2^(k-i)) cell): pins sobol_interval_to_index + dimensions 0 / 1.
+  * Exhaustive closest hit (accelerators/exhaustive/accel.rs: every primitive in list order, no BVH) against the QBVH / LBVH
+    traversal: pins BVH build + flattening + traversal + instance transforms independently of the restatement's own BVH.
+  * White furnace: a closed Lambertian box (albedo rho) in which every wall emits Le on both sides has radiance
+    Le * sum_{k=0..maxdepth} rho^k in every direction - a known answer for PathIntegrator::li + estimate_direct (light
+    sampling, MIS, light distribution) + camera + film together."""
+import os
+
+import numpy as np
+import pytest
+
+
+# ---------------------------------------------------------------------------------------------------------------- samplers
+def _elementary_ok(u, nx, ny):
+    """every cell of the nx x ny grid over [0,1)^2 holds exactly one of the nx*ny points"""
+    assert (u >= 0).all() and (u < 1).all()
+    cx = np.floor(u[:, 0].astype(np.float64) * nx).astype(np.int64)
+    cy = np.floor(u[:, 1].astype(np.float64) * ny).astype(np.int64)
+    cells = cy * nx + cx
+    return len(np.unique(cells)) == nx * ny and len(cells) == nx * ny
+
+
+def _halton_check(scene):
+    # film 200x200 -> base scales 128 (2^7) and 243 (3^5): any 2^i * 3^j consecutive sample numbers of a pixel
+    pixels = [(-1, -1), (0, 0), (17, 133), (199, 0), (128, 127), (200, 200)]
+    for (px, py) in pixels:
+        for i, j in [(1, 0), (0, 1), (3, 1), (2, 2), (5, 3), (7, 2), (4, 4)]:
+            n = (2 ** i) * (3 ** j)
+            for first in (0, 5, n):                      # any block of n consecutive sample numbers
+                pix = np.tile(np.array([[px, py]], np.int32), (n, 1))
+                sn = np.arange(first, first + n, dtype=np.int32)
+                u = scene.sampler_values(pix, sn, 0, 2)
+                assert _elementary_ok(u, 2 ** i, 3 ** j), (px, py, i, j, first)
+
+
+def _sobol_check(make_scene):
+    for log_samples in range(2, 11):
+        sc = make_scene(1 << log_samples)
+        n = 1 << log_samples
+        pix = np.zeros((n, 2), np.int32)
+        u = sc.sampler_values(pix, np.arange(n, dtype=np.int32), 0, 2)
+        for i in range(log_samples + 1):
+            assert _elementary_ok(u, 1 << i, 1 << (log_samples - i)), (log_samples, i)
+
+
+def _no_voxels(txt):
+    """hostcheck legs: the serial host build of the 64^3-voxel spatial light table costs 10-20 s per scene and has nothing
+    to do with what these tests pin"""
+    return txt.replace('Integrator "path"', 'Integrator "path" "string lightsamplestrategy" ["power"]') if "lightsamplestrategy" not in txt else txt
+
+
+def _cornell(P, res, spp, sampler):
+    return P.HostScene.parse_string(_no_voxels(P.scenes.cornell_box(res=res, spp=spp, sampler=sampler)))
+
+
+def test_halton_elementary_intervals_oracle(P):
+    import oracle_api
+    _halton_check(oracle_api.OracleScene(_cornell(P, 200, 1 << 16, "halton")))
+
+
+def test_sobol_elementary_intervals_oracle(P):
+    import oracle_api
+    _sobol_check(lambda spp: oracle_api.OracleScene(_cornell(P, 10, spp, "sobol")))
+
+
+def test_elementary_intervals_hostcheck(HC):
+    _halton_check(HC.Scene(_cornell(HC, 200, 1 << 16, "halton")))
+    _sobol_check(lambda spp: HC.Scene(_cornell(HC, 10, spp, "sobol")))
+
+
+@pytest.mark.gpu
+def test_elementary_intervals_gpu(P):
+    _halton_check(P.Scene(_cornell(P, 200, 1 << 16, "halton"), 0))
+    _sobol_check(lambda spp: P.Scene(_cornell(P, 10, spp, "sobol"), 0))
+
+
+# ------------------------------------------------------------------------------------------------------- exhaustive vs BVH
+def _rays(orc, hs, n, seed):
+    """half camera rays, half random rays through the world bound"""
+    sb = hs.desc.film.sample_bounds
+    rng = np.random.RandomState(seed)
+    pix = np.stack([rng.randint(sb[0], sb[2], n // 2), rng.randint(sb[1], sb[3], n // 2)], 1).astype(np.int32)
+    cam, _ = orc.camera_rays(pix, np.zeros(n // 2, np.int32))
+    wb = orc.world_bound()
+    o = rng.uniform(wb[:3], wb[3:], (n - n // 2, 3))
+    d = rng.normal(size=(n - n // 2, 3))
+    rnd = np.concatenate([o, np.full((len(o), 1), np.inf), d, np.zeros((len(o), 1))], 1).astype(np.float32)
+    return np.concatenate([cam, rnd], 0)
+
+
+def _exhaustive_scenes(P, big):
+    lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
+    inst = P.scenes.instanced_blobs(n_instances=60 if big else 24, n_sub=2 if big else 1, res=(96, 64), spp=1, n_lights=8)
+    return {"cornell": (P.scenes.cornell_box(res=64, spp=1), 100000 if big else 20000),
+            "grid": (P.scenes.displaced_grid(n=160 if big else 48, res=64, spp=1), 20000 if big else 8000),
+            "grid_normals": (P.scenes.displaced_grid(n=64 if big else 32, res=64, spp=1, normals=True), 20000 if big else 4000),
+            "instances": (inst, 20000 if big else 8000),
+            "instances_lbvh": (lb(inst), 20000 if big else 4000)}
+
+
+def _check_exhaustive(get_scene, P, big):
+    import oracle_api
+    for name, (txt, n) in _exhaustive_scenes(P, big).items():
+        hs = P.HostScene.parse_string(txt if big else _no_voxels(txt))
+        orc = oracle_api.OracleScene(hs)
+        rays = _rays(orc, hs, n, 31)
+        pe, te, ie = orc.intersect_exhaustive(rays)
+        sc = get_scene(hs)
+        pa, ta, _ = sc.intersect(rays)
+        hit = pe >= 0
+        assert 0.2 < hit.mean() < 1.0, (name, hit.mean())
+        assert np.array_equal(pa >= 0, hit), name                                   # same set of rays hits something
+        assert np.array_equal(ta[hit].view(np.uint32), te[hit].view(np.uint32)), name   # the closest distance, bit for bit
+        # the primitive may differ only between primitives at exactly the same distance (shared edges): visit order decides
+        assert (pa[hit] != pe[hit]).mean() < 2e-3, (name, (pa[hit] != pe[hit]).mean())
+        # any-hit: a ray cut just beyond its closest hit is occluded, cut well before it is occluded iff something is closer
+        r2 = rays[hit].copy()
+        r2[:, 3] = te[hit] * 1.0001
+        assert sc.intersect_p(r2).all(), name
+        r2[:, 3] = te[hit] * 0.999
+        assert not sc.intersect_p(r2).any(), name
+        orc.close()
+        if hasattr(sc, "close"):
+            sc.close()
+
+
+def test_exhaustive_vs_bvh_oracle(P):
+    import oracle_api
+
+    class _O:                    # the oracle's own BVH traversal behind the Scene interface
+        def __init__(self, hs):
+            self.o = oracle_api.OracleScene(hs)
+
+        def intersect(self, rays):
+            p, t, b, _, _ = self.o.intersect(rays)
+            return p, t, b
+
+        def intersect_p(self, rays):
+            return self.o.intersect_p(rays)
+    _check_exhaustive(_O, P, big=False)
+
+
+def test_exhaustive_vs_bvh_hostcheck(HC):
+    _check_exhaustive(lambda hs: HC.Scene(hs), HC, big=False)
+
+
+@pytest.mark.gpu
+def test_exhaustive_vs_bvh_gpu(P):
+    _check_exhaustive(lambda hs: P.Scene(hs, 0), P, big=True)
+
+
+# ------------------------------------------------------------------------------------------------------------ white furnace
+def furnace_scene(maxdepth, rho, le, res=16, spp=64, strategy="spatial", sampler="halton"):
+    q = lambda p: 'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [%s]\n' % " ".join(map(str, p))
+    s = 'LookAt 0.1 0.05 -0.7  0 0.1 0.2  0 1 0\nCamera "perspective" "float fov" [75]\nFilm "image" "integer xresolution" [%d] "integer yresolution" [%d]\n' % (res, res)
+    s += 'Sampler "%s" "integer pixelsamples" [%d]\nIntegrator "path" "integer maxdepth" [%d] "float rrthreshold" [0] "string lightsamplestrategy" ["%s"]\nWorldBegin\n' % (
+        sampler, spp, maxdepth, strategy)
+    s += 'Material "matte" "rgb Kd" [%g %g %g]\nAreaLightSource "diffuse" "rgb L" [%g %g %g] "bool twosided" ["true"]\n' % (rho, rho, rho, le, le, le)
+    c = [(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)]
+    for f in [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (3, 2, 6, 7), (0, 3, 7, 4), (1, 2, 6, 5)]:
+        s += q([v for i in f for v in c[i]])
+    return s + "WorldEnd\n"
+
+
+def _furnace(render, tol, cases=((5, 0.5, 1.0, "spatial"), (3, 0.8, 2.0, "power"), (1, 0.25, 1.0, "spatial"))):
+    for maxdepth, rho, le, strategy in cases:
+        expect = le * sum(rho ** k for k in range(maxdepth + 1))
+        rgb = render(furnace_scene(maxdepth, rho, le, strategy=strategy))
+        assert np.isfinite(rgb).all()
+        assert abs(float(rgb.mean()) / expect - 1.0) < tol, (maxdepth, rho, float(rgb.mean()), expect)
+        assert np.abs(rgb / expect - 1.0).max() < 0.5                      # every pixel is an estimate of the same constant (64 spp of a 12-light estimator: noisy)
+
+
+def test_white_furnace_oracle(P):
+    import oracle_api
+    _furnace(lambda txt: oracle_api.OracleScene(P.HostScene.parse_string(txt)).render(threads=4)[0], 0.01)
+
+
+def test_white_furnace_hostcheck(HC):
+    _furnace(lambda txt: HC.Scene(HC.HostScene.parse_string(txt)).render()[0], 0.01, cases=((5, 0.5, 1.0, "power"), (2, 0.8, 2.0, "power")))
+
+
+@pytest.mark.gpu
+def test_white_furnace_gpu(P):
+    def render(txt):
+        sc = P.Scene(P.HostScene.parse_string(txt), 0)
+        try:
+            return sc.render()[0]
+        finally:
+            sc.close()
+    _furnace(render, 0.01)
+    # 60-bin spectral build and the Sobol sampler reach the same answer
+    for spectrum, sampler in (("sampled", "halton"), ("rgb", "sobol")):
+        sc = P.Scene(P.HostScene.parse_string(furnace_scene(4, 0.5, 1.0, sampler=sampler), spectrum=spectrum), 0)
+        rgb = sc.render()[0]
+        sc.close()
+        assert abs(float(rgb.mean()) / 1.9375 - 1.0) < 0.02, (spectrum, sampler, float(rgb.mean()))
