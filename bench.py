@@ -224,7 +224,11 @@ def _main(out):
     hs = P.HostScene.parse_string(scene_text(P, c), spectrum=c["spectrum"])
     parse_s = time.time() - t0
     t0 = time.time()
-    sc = P.Scene(hs, local)                 # host SAH build + flatten + upload: outside the timed region (the reference's make_scene)
+    torch.zeros(1, device="cuda:%d" % local)   # CUDA context creation, reported on its own
+    torch.cuda.synchronize(local)
+    cuda_init_s = time.time() - t0
+    t0 = time.time()
+    sc = P.Scene(hs, local)                 # host SAH build + flatten + upload + light table: outside the timed region (the reference's make_scene)
     scene_create_s = time.time() - t0
     s0, s1 = D.spp_shard(c["step_spp"], rank, world)      # the fixed job's sample numbers, split over the ranks
     dev = "cuda:%d" % local
@@ -355,7 +359,7 @@ def _main(out):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "rays_per_step": int(rays_all), "camera_samples_per_step": int(samples_all), "path_vertices": int(vertices_all),
-            "parse_s": parse_s, "scene_create_s": scene_create_s,
+            "parse_s": parse_s, "scene_create_s": scene_create_s, "cuda_init_s": cuda_init_s,
             "roofline": {"bound": "hbm", "achieved": tr_ach, "peak": peak, "unit": "GB/s", "frac": tr_ach / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": "k_trace", "peak_source": peak_src, "bytes_per_ray": tr_bytes / max(cst["extend_rays"], 1),
                          "nodes_per_ray": cst["nodes_visited"] / max(cst["extend_rays"], 1), "tris_per_ray": cst["tris_tested"] / max(cst["extend_rays"], 1),

@@ -207,9 +207,6 @@ PT_HD Sp<NC> surface_le(const DScene& S, const SurfD& si, f3 w) {
   return sp_const<NC>(0.0f);
 }
 
-#ifndef PT_CDF_KARY
-#define PT_CDF_KARY 1
-#endif
 // LightDistribution::lookup + Distribution1D::sample_discrete on the dense voxel table
 PT_HD uint32_t ld_voxel(const LightDistDev& D, f3 p) {
   float o[3] = {p.x - D.wb_min[0], p.y - D.wb_min[1], p.z - D.wb_min[2]};
@@ -229,44 +226,11 @@ PT_HD1 int ld_sample(const DScene& S, f3 p, float u, float* pdf) {
   const float* cdf = D.cdf + (size_t)vox * (nl + 1);
   // find_interval(cdf.len(), |i| cdf[i] <= u) (distribution.rs:13-32)
   uint32_t first = 0, len = nl + 1;
-#if PT_CDF_KARY
-  // The same binary search, three levels per round trip: the 7 elements the next three steps can probe are requested
-  // together and the steps are replayed on the values (a scene with 512 lights has 10 dependent probes into a table of
-  // voxels x lights floats that misses every cache: 4 round trips instead of 10).  Same probes, same decisions.
-  while (len > 0) {
-    uint32_t f[7], l[7];
-    float v[7];
-    f[0] = first; l[0] = len;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {  // children of state k: 2k + 1 = "cdf[mid] > u", 2k + 2 = "cdf[mid] <= u"
-      const uint32_t half = l[k] >> 1;
-      f[2 * k + 1] = f[k]; l[2 * k + 1] = half;
-      f[2 * k + 2] = f[k] + half + 1; l[2 * k + 2] = l[k] > half ? l[k] - half - 1 : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < 7; k++) v[k] = l[k] > 0 ? ldg(cdf + f[k] + (l[k] >> 1)) : 0.0f;
-    int k = 0;
-#pragma unroll
-    for (int lev = 0; lev < 3; lev++) {
-      if (l[k] == 0) break;
-      const int nk = (v[k] <= u) ? 2 * k + 2 : 2 * k + 1;
-      if (lev < 2) k = nk;
-      else {  // third step: its result state is not in the table
-        const uint32_t half = l[k] >> 1;
-        if (v[k] <= u) { first = f[k] + half + 1; len = l[k] - half - 1; }
-        else { first = f[k]; len = half; }
-        k = -1;
-      }
-    }
-    if (k >= 0) { first = f[k]; len = l[k]; }
-  }
-#else
   while (len > 0) {
     uint32_t half = len >> 1, mid = first + half;
     if (ldg(cdf + mid) <= u) { first = mid + 1; len -= half + 1; }
     else len = half;
   }
-#endif
   uint32_t off = first == 0 ? 0 : first - 1;
   if (off > nl - 1) off = nl - 1;
   float func_int = ldg(D.func_int + vox);

@@ -35,6 +35,10 @@
 #ifndef PT_INST_CULL
 #define PT_INST_CULL 1
 #endif
+// instance entry through the flat 96-byte InstTrav record instead of InstanceRec -> ObjectRec
+#ifndef PT_INST_FLAT
+#define PT_INST_FLAT 1
+#endif
 // triangle records in the three axis orders of the watertight test (dscene.cuh): no per-triangle component selects
 #ifndef PT_TRI_PERM
 #define PT_TRI_PERM 1
@@ -429,28 +433,6 @@ PT_HD void trav_nodes(const DScene& S, Trav& T, Stack& st, int* overflow, TravCo
   while (trav_node_step<INST, COUNT>(S, T, st, overflow, cnt)) {}
 }
 
-// Survivor mask of the n <= 32 records at r of a top-level leaf: bit j is set for a triangle record and for an instance
-// record whose cull test passes.  5 of 6 instance records met by a ray of the 1000-instance scene fail the exact
-// object-bounds test, after the ray transform and four IEEE divisions.  The record carries a CONSERVATIVE world-space box
-// of the instance (grown far beyond the rounding of the transform, device_api.cu): a world ray that misses it cannot pass
-// the exact test, so the record is skipped without touching the instance (63 % of them).  NaN slab products are
-// dropped by fmaxf / fminf, i.e. they loosen the test.
-PT_HD unsigned leaf_survivors(const f4* r, int n, const Trav& T) {
-  const bool nx = (T.sg & 1) != 0, ny = (T.sg & 2) != 0, nz = (T.sg & 4) != 0;
-  unsigned m = 0u;
-  for (int j = 0; j < n; j++, r += 3) {
-    bool keep = true;
-    if (fbits(ldg4(r + 1).w) & PT_REC_INSTANCE) {
-      const f4 lo = ldg4(r), hi = ldg4(r + 2);
-      const float t0 = fmaxf(fmaxf(((nx ? hi.x : lo.x) - T.o.x) * T.idx, ((ny ? hi.y : lo.y) - T.o.y) * T.idy), fmaxf(((nz ? hi.z : lo.z) - T.o.z) * T.idz, 0.0f));
-      const float t1 = fminf(fminf(((nx ? lo.x : hi.x) - T.o.x) * T.idx, ((ny ? lo.y : hi.y) - T.o.y) * T.idy), fminf(((nz ? lo.z : hi.z) - T.o.z) * T.idz, T.ray_tmax));
-      keep = !(t0 > t1);
-    }
-    if (keep) m |= 1u << j;
-  }
-  return m;
-}
-
 // LEAF phase: the pending leaf (intersect_primitives[_p] over recs[lf .. lf + lc) in order) or the barrier, then pop.
 template <bool INST, bool COUNT, typename Stack>
 PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCounters* cnt) {
@@ -473,38 +455,48 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
 #else
   const f4* r = S.recs + ((size_t)T.rec_base + (size_t)first) * 3;
 #endif
-  // Top-level leaves (the only ones that hold instance records) are processed in two passes: first the cull test of
-  // every record of the leaf (a few instructions, all lanes of the warp together), then the surviving records in order.
-  // With the tests interleaved, pass i of the record loop ran the expensive exact instance test (ray transform, four IEEE
-  // divisions, object-bounds test) for the few lanes whose i-th record happened to survive: 3 active lanes per
-  // instruction (ncu, 1000-instance scene).  Now the k-th SURVIVOR of every lane is processed in pass k.  The records of
-  // a lane are still visited in increasing order, and the cull only uses an older (larger) t_max: same results.
-  const bool top = INST && PT_INST_CULL && T.inst < 0;
-  unsigned todo = 0u;
-  int blk = -32, i = -1;
-  for (;;) {
-    if (top) {
-      while (todo == 0u && blk + 32 < count) {
-        blk += 32;
-        todo = leaf_survivors(r + 3 * (size_t)blk, count - blk < 32 ? count - blk : 32, T);
-      }
-      if (todo == 0u) break;
-      i = blk + ffs_(todo) - 1;
-      todo &= todo - 1u;
-    } else {
-      i++;
-      if (i >= count) break;
-    }
-    const f4* ri = r + 3 * (size_t)i;
-    f4 v0 = ldg4(ri), v1 = ldg4(ri + 1), v2 = ldg4(ri + 2);
+  for (int i = 0; i < count; i++, r += 3) {
+    f4 v0 = ldg4(r), v1 = ldg4(r + 1), v2 = ldg4(r + 2);
     if (INST && (fbits(v1.w) & PT_REC_INSTANCE)) {
       // TransformedPrimitive::intersect[_p] (only top-level leaves hold instances)
+#if PT_INST_CULL
+      // 5 of 6 instance records met by a ray of the 1000-instance scene fail the object-bounds test below, after the ray
+      // transform and four IEEE divisions.  The record carries a CONSERVATIVE world-space box of the instance (grown far
+      // beyond the rounding of the transform, device_api.cu): a world ray that misses it cannot pass the exact test, so
+      // it is skipped without touching the instance (63 % of the records).  NaN slab products are dropped by
+      // fmaxf / fminf, i.e. they loosen the test.  (Measured and rejected, profiles/r2b_ab_cfg3.txt: culling all records of
+      // the leaf first and then looping over the survivors - k_trace 125.6 -> 140.9 ms.)
+      {
+        const bool nx = (T.sg & 1) != 0, ny = (T.sg & 2) != 0, nz = (T.sg & 4) != 0;
+        const float t0 = fmaxf(fmaxf(((nx ? v2.x : v0.x) - T.o.x) * T.idx, ((ny ? v2.y : v0.y) - T.o.y) * T.idy), fmaxf(((nz ? v2.z : v0.z) - T.o.z) * T.idz, 0.0f));
+        const float t1 = fminf(fminf(((nx ? v0.x : v2.x) - T.o.x) * T.idx, ((ny ? v0.y : v2.y) - T.o.y) * T.idy), fminf(((nz ? v0.z : v2.z) - T.o.z) * T.idz, T.ray_tmax));
+        if (t0 > t1) continue;
+      }
+#endif
       int inst = (int)fbits(v0.w);
-      const InstanceRec& I = S.instances[inst];
-      const ObjectRec& O = S.objects[I.object];
       DRay wr;
       wr.o = T.o; wr.d = T.d; wr.tmax = T.ray_tmax; wr.time = T.time;
+#if PT_INST_FLAT
+      // one 96-byte record per instance (dscene.cuh InstTrav): six independent 16-byte loads
+      struct { float minv[12]; float bmin[3], bmax[3]; uint32_t node_base, rec_base, n_prims; bool single, projective; } O;
+      {
+        const f4* ip = reinterpret_cast<const f4*>(S.inst_trav + inst);
+        const f4 a0 = ldg4(ip), a1 = ldg4(ip + 1), a2 = ldg4(ip + 2), a3 = ldg4(ip + 3), a4 = ldg4(ip + 4), a5 = ldg4(ip + 5);
+        O.minv[0] = a0.x; O.minv[1] = a0.y; O.minv[2] = a0.z; O.minv[3] = a0.w;
+        O.minv[4] = a1.x; O.minv[5] = a1.y; O.minv[6] = a1.z; O.minv[7] = a1.w;
+        O.minv[8] = a2.x; O.minv[9] = a2.y; O.minv[10] = a2.z; O.minv[11] = a2.w;
+        O.bmin[0] = a3.x; O.bmin[1] = a3.y; O.bmin[2] = a3.z; O.bmax[0] = a3.w; O.bmax[1] = a4.x; O.bmax[2] = a4.y;
+        O.node_base = fbits(a4.z); O.rec_base = fbits(a4.w); O.n_prims = fbits(a5.x);
+        O.single = (fbits(a5.y) & 1u) != 0u;
+        O.projective = (fbits(a5.y) & 2u) != 0u;
+      }
+      // a projective instance transform (never produced by Translate / Rotate / Scale / LookAt) takes the general form
+      const DRay q = O.projective ? xform_ray(S.instances[inst].minv, wr) : xform_ray_affine(O.minv, wr);
+#else
+      const InstanceRec& I = S.instances[inst];
+      const ObjectRec& O = S.objects[I.object];
       DRay q = xform_ray(I.minv, wr);
+#endif
       if (O.n_prims == 0) continue;
       if (O.single) {  // one primitive, no accelerator: test it in object space right here
         trav_park_ray(T, st);

@@ -3,9 +3,11 @@
 #include "bvh_build.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 namespace pth {
 namespace {
@@ -40,28 +42,30 @@ inline int b_max_extent(const float mn[3], const float mx[3]) {
   return 2;
 }
 
+// The build is deterministic AND parallel: a subtree over n primitives owns the slice [ord, ord + n) of the ordered
+// primitive list (the reference appends leaves in depth-first order, so the left subtree's primitives come first) and
+// takes its nodes from a pre-sized arena through an atomic counter, so the two children of a large node can be built by
+// different threads.  Node numbers then depend on the thread schedule, but nothing reads them: the tree is only ever
+// walked through its child links (flattening, parity views), and the root is node 0.
 struct Ctx {
   BvhResult* out;
   size_t max_prims;
   int split;
-  std::vector<Info> scratch;
+  std::atomic<int32_t> next_node{0};
+  std::atomic<int> spare_threads{0};
+  static constexpr size_t kParallelMin = 1u << 14;  // primitives below which a subtree is not worth a thread
 
-  int32_t leaf(const Info* pi, size_t n, const BBox& b) {
-    BuildNodeH nd;
+  int32_t reserve() { return next_node.fetch_add(1); }
+  int32_t leaf_at(int32_t self, const Info* pi, size_t n, const BBox& b, size_t ord) {
+    if (self < 0) self = reserve();
+    BuildNodeH& nd = out->tree[(size_t)self];
     nd.bounds = b;
     nd.child[0] = nd.child[1] = -1;
     nd.axis = 0;
-    nd.first = (uint32_t)out->ordered.size();
+    nd.first = (uint32_t)ord;
     nd.n = (uint32_t)n;
-    for (size_t i = 0; i < n; i++) out->ordered.push_back(pi[i].number);
-    out->tree.push_back(nd);
-    return (int32_t)out->tree.size() - 1;
-  }
-  // children must be created first-then-second (the ordered list is appended in build order);
-  // the interior node is reserved BEFORE so that the root is node 0
-  int32_t reserve() {
-    out->tree.emplace_back();
-    return (int32_t)out->tree.size() - 1;
+    for (size_t i = 0; i < n; i++) out->ordered[ord + i] = pi[i].number;
+    return self;
   }
   void set_interior(int32_t id, int axis, int32_t c0, int32_t c1) {
     BuildNodeH& nd = out->tree[(size_t)id];
@@ -72,46 +76,57 @@ struct Ctx {
     nd.first = 0;
     nd.n = 0;
   }
-  static void sort_dim(Info* pi, size_t n, int dim) {
-    std::stable_sort(pi, pi + n, [dim](const Info& a, const Info& b) { return a.c[dim] < b.c[dim]; });
-  }
-  int32_t equal_counts(int dim, Info* pi, size_t n, int32_t self) {
-    sort_dim(pi, n, dim);
-    size_t mid = n / 2;
-    int32_t c0 = build(pi, mid, -1);
-    int32_t c1 = build(pi + mid, n - mid, -1);
+  // the two children of `self`: [pi, pi + nl) then [pi + nl, pi + n); the larger halves of big nodes on their own threads
+  int32_t children(int32_t self, int dim, Info* pi, size_t nl, size_t n, size_t ord) {
+    int32_t c0, c1;
+    bool forked = false;
+    if (nl >= kParallelMin && n - nl >= kParallelMin) {
+      int avail = spare_threads.load();
+      while (avail > 0 && !spare_threads.compare_exchange_weak(avail, avail - 1)) {}
+      forked = avail > 0;
+    }
+    if (forked) {
+      std::thread t([&]() { c0 = build(pi, nl, -1, ord); });
+      c1 = build(pi + nl, n - nl, -1, ord + nl);
+      t.join();
+      spare_threads.fetch_add(1);
+    } else {
+      c0 = build(pi, nl, -1, ord);
+      c1 = build(pi + nl, n - nl, -1, ord + nl);
+    }
     set_interior(self, dim, c0, c1);
     return self;
   }
-  int32_t build(Info* pi, size_t n, int32_t self) {  // recursive_build (node.rs:27-105)
+  static void sort_dim(Info* pi, size_t n, int dim) {
+    std::stable_sort(pi, pi + n, [dim](const Info& a, const Info& b) { return a.c[dim] < b.c[dim]; });
+  }
+  int32_t equal_counts(int dim, Info* pi, size_t n, int32_t self, size_t ord) {
+    sort_dim(pi, n, dim);
+    return children(self, dim, pi, n / 2, n, ord);
+  }
+  int32_t build(Info* pi, size_t n, int32_t self, size_t ord) {  // recursive_build (node.rs:27-105)
     BBox bounds = pi[0].b;
     for (size_t i = 1; i < n; i++) bounds = b_union(bounds, pi[i].b);
-    if (n <= max_prims) return leaf_at(self, pi, n, bounds);
+    if (n <= max_prims) return leaf_at(self, pi, n, bounds, ord);
     float cmn[3] = {pi[0].c[0], pi[0].c[1], pi[0].c[2]}, cmx[3] = {pi[0].c[0], pi[0].c[1], pi[0].c[2]};
     for (size_t i = 1; i < n; i++)
       for (int a = 0; a < 3; a++) { cmn[a] = mn_(cmn[a], pi[i].c[a]); cmx[a] = mx_(cmx[a], pi[i].c[a]); }
     int dim = b_max_extent(cmn, cmx);
-    if (cmn[dim] == cmx[dim]) return leaf_at(self, pi, n, bounds);
+    if (cmn[dim] == cmx[dim]) return leaf_at(self, pi, n, bounds, ord);
     if (self < 0) self = reserve();
     if (split == 2) {  // middle.rs
       float p_mid = (cmn[dim] + cmx[dim]) / 2.0f;
       sort_dim(pi, n, dim);
       size_t mid = 0;
       while (mid < n && !(p_mid <= pi[mid].c[dim])) mid++;
-      if (mid == 0 || mid == n) return equal_counts(dim, pi, n, self);
-      int32_t c0 = build(pi, mid, -1);
-      int32_t c1 = build(pi + mid, n - mid, -1);
-      set_interior(self, dim, c0, c1);
-      return self;
+      if (mid == 0 || mid == n) return equal_counts(dim, pi, n, self, ord);
+      return children(self, dim, pi, mid, n, ord);
     }
-    if (split == 3) return equal_counts(dim, pi, n, self);
+    if (split == 3) return equal_counts(dim, pi, n, self, ord);
     // split_sah (sah.rs:31-170); n >= 3 here unless maxnodeprims < 2
     if (n == 2) {
       sort_dim(pi, n, dim);
-      int32_t c0 = build(pi, 1, -1);
-      int32_t c1 = build(pi + 1, 1, -1);
-      set_interior(self, dim, c0, c1);
-      return self;
+      return children(self, dim, pi, 1, n, ord);
     }
     const int NB = 12;
     int count[NB];
@@ -149,6 +164,7 @@ struct Ctx {
     if (n > max_prims || min_cost < leaf_cost) {
       // order-preserving partition (Iterator::partition), in place via a scratch copy of the right side
       size_t nl = 0;
+      static thread_local std::vector<Info> scratch;  // reused: the copy is over before the children are built
       scratch.clear();
       for (size_t i = 0; i < n; i++) {
         if (bucket_of(pi[i]) <= min_b) pi[nl++] = pi[i];
@@ -157,34 +173,12 @@ struct Ctx {
       if (nl == 0 || nl == n) {
         // nothing moved (one side empty): the slice is still in its original order
         if (nl == 0) std::copy(scratch.begin(), scratch.end(), pi);
-        return equal_counts(dim, pi, n, self);
+        return equal_counts(dim, pi, n, self, ord);
       }
       std::copy(scratch.begin(), scratch.end(), pi + nl);
-      int32_t c0 = build(pi, nl, -1);
-      int32_t c1 = build(pi + nl, n - nl, -1);
-      set_interior(self, dim, c0, c1);
-      return self;
+      return children(self, dim, pi, nl, n, ord);
     }
-    // leaf at a reserved slot
-    BuildNodeH& nd = out->tree[(size_t)self];
-    nd.bounds = bounds;
-    nd.child[0] = nd.child[1] = -1;
-    nd.axis = 0;
-    nd.first = (uint32_t)out->ordered.size();
-    nd.n = (uint32_t)n;
-    for (size_t i = 0; i < n; i++) out->ordered.push_back(pi[i].number);
-    return self;
-  }
-  int32_t leaf_at(int32_t self, const Info* pi, size_t n, const BBox& b) {
-    if (self < 0) return leaf(pi, n, b);
-    BuildNodeH& nd = out->tree[(size_t)self];
-    nd.bounds = b;
-    nd.child[0] = nd.child[1] = -1;
-    nd.axis = 0;
-    nd.first = (uint32_t)out->ordered.size();
-    nd.n = (uint32_t)n;
-    for (size_t i = 0; i < n; i++) out->ordered.push_back(pi[i].number);
-    return self;
+    return leaf_at(self, pi, n, bounds, ord);
   }
 };
 
@@ -306,10 +300,15 @@ void build_bvh(const std::vector<BBox>& prim_bounds, int max_prims_in_node, int 
   c.out = out;
   c.max_prims = (size_t)std::min(std::max(max_prims_in_node, 0), 255);
   c.split = split_method;
-  out->tree.reserve(n);
-  out->ordered.reserve(n);
-  int32_t root = c.build(info.data(), n, c.reserve());
+  out->tree.assign(2 * n, BuildNodeH());   // a binary tree over n primitives has at most 2n - 1 nodes
+  out->ordered.assign(n, 0u);
+  {
+    unsigned hw = std::thread::hardware_concurrency();
+    c.spare_threads.store((int)std::min(std::max(hw, 1u), 64u) - 1);
+  }
+  int32_t root = c.build(info.data(), n, c.reserve(), 0);
   (void)root;
+  out->tree.resize((size_t)c.next_node.load());
   out->bounds = out->tree[0].bounds;
   Flat f;
   f.r = out;
