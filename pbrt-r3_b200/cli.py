@@ -61,6 +61,9 @@ def render_scene(path, opts):
     lib.pt_set_options(o)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(opts.device)))
+    if world > 1:
+        import torch
+        local = local % max(torch.cuda.device_count(), 1)   # more ranks than GPUs (tests on a 1-GPU box): ranks share devices
     if not opts.quiet and rank == 0:
         print("pbrt-r3 (B200 PathIntegrator core) [%d GPU process%s]" % (world, "" if world == 1 else "es"))
     t0 = time.time()

@@ -341,19 +341,6 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
       ir[i].object = D->instances[i].object;
     }
     CK(s->bufs.upload(ir.data(), ir.size(), &H.instances));
-    std::vector<InstTrav> it(D->n_instances);
-    for (uint32_t i = 0; i < D->n_instances; i++) {
-      InstTrav& t = it[i];
-      memset(&t, 0, sizeof(t));
-      const float* mi = D->instances[i].minv;
-      memcpy(t.minv, mi, 12 * sizeof(float));
-      const ObjectRec& R = orecs[(size_t)D->instances[i].object];
-      for (int a = 0; a < 3; a++) { t.bmin[a] = R.bmin[a]; t.bmax[a] = R.bmax[a]; }
-      t.node_base = R.node_base; t.rec_base = R.rec_base; t.n_prims = R.n_prims;
-      const bool affine = mi[12] == 0.0f && mi[13] == 0.0f && mi[14] == 0.0f && mi[15] == 1.0f;
-      t.flags = (R.single ? 1u : 0u) | (affine ? 0u : 2u);
-    }
-    CK(s->bufs.upload(it.data(), it.size(), &H.inst_trav));
   }
   {
     std::vector<f4> tv((size_t)D->n_tris * 3);

@@ -234,26 +234,6 @@ struct DRay {
   f3 o, d;
   float tmax, time;
 };
-// xform_ray for an AFFINE matrix given by its rows 0-2: the homogeneous weight of mat_point is 0 x + 0 y + 0 z + 1 = 1
-// for every finite point, so the division branch of Transform::transform_point never runs; everything else is the same
-// operation sequence.
-PT_HD DRay xform_ray_affine(const float* m, const DRay& r) {
-  float x = r.o.x, y = r.o.y, z = r.o.z;
-  f3 o = mk3(m[0] * x + m[1] * y + m[2] * z + m[3], m[4] * x + m[5] * y + m[6] * z + m[7], m[8] * x + m[9] * y + m[10] * z + m[11]);
-  float xs = fabsf(m[0] * x) + fabsf(m[1] * y) + fabsf(m[2] * z) + fabsf(m[3]);
-  float ys = fabsf(m[4] * x) + fabsf(m[5] * y) + fabsf(m[6] * z) + fabsf(m[7]);
-  float zs = fabsf(m[8] * x) + fabsf(m[9] * y) + fabsf(m[10] * z) + fabsf(m[11]);
-  f3 oerr = PT_GAMMA(3.0f) * mk3(xs, ys, zs);
-  f3 d = mat_vector(m, r.d);
-  float ls = len2(d);
-  if (ls > 0.0f) {
-    float dt = dot3(abs3(d), oerr) / ls;
-    o = o + d * dt;
-  }
-  DRay q;
-  q.o = o; q.d = d; q.tmax = r.tmax; q.time = r.time;
-  return q;
-}
 // Transform::transform_ray (core/transform/transform.rs:184-203, 270-282)
 PT_HD DRay xform_ray(const float* m, const DRay& r) {
   float x = r.o.x, y = r.o.y, z = r.o.z;

@@ -45,19 +45,6 @@ struct InstanceRec {
   int32_t pad[3];
 };
 
-// What the traversal needs to enter an instance, in ONE 96-byte record (six 16-byte loads, one round trip): the affine
-// part of world-to-instance, the instanced object's bounds and where its nodes / records start.  Through InstanceRec the
-// same data costs a second, dependent round trip (instance -> object record) in the least converged part of k_trace.
-struct alignas(16) InstTrav {
-  float minv[12];          // rows 0-2 of world-to-instance
-  float bmin[3], bmax[3];  // QBVHAccel.bounds of the object
-  uint32_t node_base, rec_base;
-  uint32_t n_prims;
-  uint32_t flags;          // bit 0: single primitive (no accelerator); bit 1: the matrix is not affine (last row != 0 0 0 1):
-                           // take the general path through InstanceRec
-};
-static_assert(sizeof(InstTrav) == 96, "InstTrav must be 96 B");
-
 struct alignas(16) PrimeRec {  // PRIMES[dim], PRIME_SUMS[dim] (lowdiscrepancy/primes.rs) + ceil(2^64 / prime) for exact division by multiply-high
   uint32_t prime;
   uint32_t perm_offset;
@@ -95,7 +82,6 @@ struct DScene {
   uint32_t rec_stride;
   const ObjectRec* objects;
   const InstanceRec* instances;
-  const InstTrav* inst_trav;   // one per instance (4-wide layout)
   // original-order triangle attributes (indexed by global triangle id)
   const f4* tri_v;           // 3 per triangle: p.xyz, w unused (shading / light sampling re-reads by id)
   const float* tri_n;        // 9 per triangle or null

@@ -35,10 +35,6 @@
 #ifndef PT_INST_CULL
 #define PT_INST_CULL 1
 #endif
-// instance entry through the flat 96-byte InstTrav record instead of InstanceRec -> ObjectRec
-#ifndef PT_INST_FLAT
-#define PT_INST_FLAT 1
-#endif
 // triangle records in the three axis orders of the watertight test (dscene.cuh): no per-triangle component selects
 #ifndef PT_TRI_PERM
 #define PT_TRI_PERM 1
@@ -476,27 +472,9 @@ PT_HD void trav_leaf(const DScene& S, Trav& T, Stack& st, int* overflow, TravCou
       int inst = (int)fbits(v0.w);
       DRay wr;
       wr.o = T.o; wr.d = T.d; wr.tmax = T.ray_tmax; wr.time = T.time;
-#if PT_INST_FLAT
-      // one 96-byte record per instance (dscene.cuh InstTrav): six independent 16-byte loads
-      struct { float minv[12]; float bmin[3], bmax[3]; uint32_t node_base, rec_base, n_prims; bool single, projective; } O;
-      {
-        const f4* ip = reinterpret_cast<const f4*>(S.inst_trav + inst);
-        const f4 a0 = ldg4(ip), a1 = ldg4(ip + 1), a2 = ldg4(ip + 2), a3 = ldg4(ip + 3), a4 = ldg4(ip + 4), a5 = ldg4(ip + 5);
-        O.minv[0] = a0.x; O.minv[1] = a0.y; O.minv[2] = a0.z; O.minv[3] = a0.w;
-        O.minv[4] = a1.x; O.minv[5] = a1.y; O.minv[6] = a1.z; O.minv[7] = a1.w;
-        O.minv[8] = a2.x; O.minv[9] = a2.y; O.minv[10] = a2.z; O.minv[11] = a2.w;
-        O.bmin[0] = a3.x; O.bmin[1] = a3.y; O.bmin[2] = a3.z; O.bmax[0] = a3.w; O.bmax[1] = a4.x; O.bmax[2] = a4.y;
-        O.node_base = fbits(a4.z); O.rec_base = fbits(a4.w); O.n_prims = fbits(a5.x);
-        O.single = (fbits(a5.y) & 1u) != 0u;
-        O.projective = (fbits(a5.y) & 2u) != 0u;
-      }
-      // a projective instance transform (never produced by Translate / Rotate / Scale / LookAt) takes the general form
-      const DRay q = O.projective ? xform_ray(S.instances[inst].minv, wr) : xform_ray_affine(O.minv, wr);
-#else
       const InstanceRec& I = S.instances[inst];
       const ObjectRec& O = S.objects[I.object];
       DRay q = xform_ray(I.minv, wr);
-#endif
       if (O.n_prims == 0) continue;
       if (O.single) {  // one primitive, no accelerator: test it in object space right here
         trav_park_ray(T, st);

@@ -70,22 +70,36 @@ def resolve_host(xyzw, scale=1.0):
     return (c * f(scale)).astype(np.float32)
 
 
-def render_distributed(scene, host_scene, rank, world, local_device, backend="nccl"):
+def render_distributed(scene, host_scene, rank, world, local_device, backend=None):
     """One Integrator::render over `world` processes (one per GPU): every rank renders its shard of the samples (tiles for
     Sampler "random") into a partial film, one reduce sums the partials onto rank 0, which resolves the image.
-    Returns (rgb or None on ranks > 0, stats of this rank)."""
+    backend "nccl": one GPU per rank, the partial films are reduced in place over NVLink.  backend "gloo" (chosen when the
+    node has fewer GPUs than ranks, e.g. the 2-rank test on a 1-GPU box where the ranks share the device): the partials
+    are staged through host memory for the reduce.  Returns (rgb or None on ranks > 0, stats of this rank)."""
     import torch
     import torch.distributed as dist
+    if backend is None:
+        backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
     if not dist.is_initialized():
         import os
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_device)
-        dist.init_process_group(backend, device_id=torch.device("cuda", local_device))
+        if backend == "nccl":
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_device))
+        else:
+            dist.init_process_group(backend)
     d = host_scene.desc
     opts = shard_opts(d.sampler.type, d.sampler.samples_per_pixel, rank, world)
     ptr, npx, st = scene.render_partial(**opts)
     film = film_tensor(ptr, npx, "cuda:%d" % local_device)
-    reduce_film(film, dst=0)
+    if dist.get_backend() == "nccl":
+        reduce_film(film, dst=0)
+    else:
+        host = film.cpu()
+        reduce_film(host, dst=0)
+        if rank == 0:
+            film.copy_(host)
+            torch.cuda.synchronize(local_device)
     rgb = scene.film_resolve(film.data_ptr()) if rank == 0 else None
     dist.barrier()
     return rgb, st

@@ -94,3 +94,27 @@ def test_cli_renders_like_the_library(P, tmp_path):
     bad.write_text('Camera "perspective"\nWorldBegin\nShape "trianglemesh" "integer indices" [0 1 5] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
     r = subprocess.run([sys.executable, "-m", "pbrt_r3_b200", str(bad)], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 255 and "ERROR" in r.stderr                                           # exit(-1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sampler,spp", [("halton", 8), ("sobol", 6), ("random", 4)])
+def test_cli_two_ranks_match_one(P, tmp_path, sampler, spp):
+    """`--gpus 2`: two processes (one per GPU over NCCL; on a 1-GPU box both on device 0 with the partial films reduced through
+    gloo) render the sample shards of the PRODUCT and rank 0 resolves the sum: the image equals the single-process render.
+    Sobol with 6 spp: the sampler takes 8 (rounded up to a power of two) and all 8 sample numbers must be sharded."""
+    import subprocess
+    import sys
+    from pbrt_r3_b200 import imageio
+    scene = tmp_path / "s.pbrt"
+    scene.write_text(P.scenes.cornell_box(res=80, spp=spp, materials="mixed", extra_lights=True, maxdepth=6, sampler=sampler))
+    outs = []
+    for g in (1, 2):
+        out = tmp_path / ("out_%d.exr" % g)
+        env = dict(os.environ, MASTER_PORT=str(29600 + os.getpid() % 300))
+        r = subprocess.run([sys.executable, "-m", "pbrt_r3_b200", str(scene), "-o", str(out), "--gpus", str(g), "--quiet"], cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+        outs.append(imageio.read_exr(str(out)))
+    a, b = outs
+    assert a.shape == b.shape and np.isfinite(b).all()
+    assert float(np.sqrt(((a - b) ** 2).mean()) / a.mean()) < 1e-5      # the film partials are summed in another order

@@ -121,11 +121,17 @@ def _check_exhaustive(get_scene, P, big):
         assert np.array_equal(ta[hit].view(np.uint32), te[hit].view(np.uint32)), name   # the closest distance, bit for bit
         # the primitive may differ only between primitives at exactly the same distance (shared edges): visit order decides
         assert (pa[hit] != pe[hit]).mean() < 2e-3, (name, (pa[hit] != pe[hit]).mean())
-        # any-hit: a ray cut just beyond its closest hit is occluded, cut well before it is occluded iff something is closer
-        r2 = rays[hit].copy()
-        r2[:, 3] = te[hit] * 1.0001
+        # any-hit: a ray cut just beyond its closest hit is occluded, cut before it is not.  (Hits much closer than the
+        # scene is large are left out: there the rounding of the scaled-distance test t_scaled vs t_max * det,
+        # triangle.rs:313-317, is larger than the 0.1 % margin - the oracle's own any-hit query disagrees with its
+        # closest hit on 2 of 86 830 such rays.)
+        wb = orc.world_bound()
+        far = hit & (te > 1e-2 * float(np.linalg.norm(wb[3:] - wb[:3])))
+        assert far.sum() > 0.5 * hit.sum()
+        r2 = rays[far].copy()
+        r2[:, 3] = te[far] * 1.001
         assert sc.intersect_p(r2).all(), name
-        r2[:, 3] = te[hit] * 0.999
+        r2[:, 3] = te[far] * 0.999
         assert not sc.intersect_p(r2).any(), name
         orc.close()
         if hasattr(sc, "close"):
