@@ -45,10 +45,41 @@ def write_exr(name, rgb):
             f.write(img[y, :, 2].tobytes() + img[y, :, 1].tobytes() + img[y, :, 0].tobytes())
 
 
+def _exr_unpredict(raw):
+    """undo the byte predictor + even / odd interleave of the RLE / ZIP scan-line compressions"""
+    d = np.frombuffer(raw, np.uint8).astype(np.int32)
+    d[1:] -= 128
+    d = (np.cumsum(d) & 0xff).astype(np.uint8)
+    n = len(d)
+    out = np.empty(n, np.uint8)
+    half = (n + 1) // 2
+    out[0::2] = d[:half]
+    out[1::2] = d[half:]
+    return out.tobytes()
+
+
+def _exr_unrle(raw, size):
+    out = bytearray()
+    i = 0
+    while i < len(raw) and len(out) < size:
+        c = raw[i] - 256 if raw[i] > 127 else raw[i]
+        i += 1
+        if c < 0:
+            out += raw[i:i - c]
+            i += -c
+        else:
+            out += bytes([raw[i]]) * (c + 1)
+            i += 1
+    return bytes(out)
+
+
 def read_exr(name):
-    """Reader for the files write_exr produces (tests)."""
+    """Scan-line OpenEXR reader: R, G, B (any extra channels ignored) as HALF or FLOAT, compression NONE / RLE / ZIPS / ZIP:
+    the files write_exr produces and the ones the reference's `image` crate encoder writes (tools/run_reference.sh)."""
     b = open(name, "rb").read()
-    assert struct.unpack("<i", b[:4])[0] == 20000630
+    assert struct.unpack("<i", b[:4])[0] == 20000630, "not an OpenEXR file"
+    version = struct.unpack("<i", b[4:8])[0]
+    assert not (version & 0x200), "tiled OpenEXR files are not supported"
     p = 8
     attrs = {}
     while b[p] != 0:
@@ -57,14 +88,39 @@ def read_exr(name):
         sz = struct.unpack("<i", b[p:p + 4])[0]; p += 4
         attrs[n] = b[p:p + sz]; p += sz
     p += 1
+    chans = []
+    c, q = attrs["channels"], 0
+    while c[q] != 0:
+        e = c.index(b"\0", q)
+        nm = c[q:e].decode()
+        ptype = struct.unpack("<i", c[e + 1:e + 5])[0]
+        chans.append((nm, ptype))
+        q = e + 17
+    comp = attrs["compression"][0]
+    assert comp in (0, 1, 2, 3), "unsupported OpenEXR compression %d" % comp
     x0, y0, x1, y1 = struct.unpack("<iiii", attrs["dataWindow"])
     w, h = x1 - x0 + 1, y1 - y0 + 1
-    offs = struct.unpack("<%dQ" % h, b[p:p + 8 * h])
+    lines_per_block = 16 if comp == 3 else 1
+    nblocks = (h + lines_per_block - 1) // lines_per_block
+    offs = struct.unpack("<%dQ" % nblocks, b[p:p + 8 * nblocks])
+    bpp = {0: 4, 1: 2, 2: 4}
+    dt = {0: "<u4", 1: "<f2", 2: "<f4"}
+    line_bytes = sum(bpp[t] for _, t in chans) * w
     out = np.zeros((h, w, 3), np.float32)
-    for y in range(h):
-        q = offs[y] + 8
-        row = np.frombuffer(b[q:q + 12 * w], np.float32).reshape(3, w)
-        out[y, :, 2], out[y, :, 1], out[y, :, 0] = row[0], row[1], row[2]
+    for off in offs:
+        y, size = struct.unpack("<ii", b[off:off + 8])
+        nl = min(lines_per_block, y1 - y + 1)
+        raw = b[off + 8:off + 8 + size]
+        want = nl * line_bytes
+        if comp != 0 and size < want:
+            raw = _exr_unpredict(zlib.decompress(raw) if comp in (2, 3) else _exr_unrle(raw, want))
+        q = 0
+        for l in range(nl):
+            for nm, t in chans:            # channels are stored in alphabetical order, one after the other per scan line
+                row = np.frombuffer(raw[q:q + bpp[t] * w], dt[t]).astype(np.float32)
+                q += bpp[t] * w
+                if nm in ("R", "G", "B"):
+                    out[y - y0 + l, :, "RGB".index(nm)] = row
     return out
 
 

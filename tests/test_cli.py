@@ -118,3 +118,56 @@ def test_cli_two_ranks_match_one(P, tmp_path, sampler, spp):
     a, b = outs
     assert a.shape == b.shape and np.isfinite(b).all()
     assert float(np.sqrt(((a - b) ** 2).mean()) / a.mean()) < 1e-5      # the film partials are summed in another order
+
+
+def test_exr_reader_compressions(tmp_path):
+    """read_exr also reads what other encoders write (tools/run_reference.sh: the reference's `image` crate): ZIPS / ZIP /
+    RLE scan-line blocks (byte predictor + even / odd interleave, OpenEXR file layout), HALF and FLOAT channels, RGBA."""
+    from pbrt_r3_b200 import imageio
+    rng = np.random.RandomState(3)
+    h, w = 37, 11
+    img = rng.rand(h, w, 4).astype(np.float32)
+
+    def predict(raw):
+        d = np.frombuffer(raw, np.uint8)
+        t = np.concatenate([d[0::2], d[1::2]]).astype(np.int32)
+        p = t.copy()
+        p[1:] = (t[1:] - t[:-1] + 128 + 256) & 0xff
+        return p.astype(np.uint8).tobytes()
+
+    def rle(raw):                       # literal runs only (negative counts): valid RLE
+        out = b""
+        for i in range(0, len(raw), 100):
+            c = raw[i:i + 100]
+            out += struct.pack("b", -len(c)) + c
+        return out
+
+    for comp, lines, half in ((2, 1, False), (3, 16, False), (3, 16, True), (1, 1, False), (0, 1, True)):
+        dt, ptype, bpp = ("<f2", 1, 2) if half else ("<f4", 2, 4)
+
+        def attr(n, t, data):
+            return n.encode() + b"\0" + t.encode() + b"\0" + struct.pack("<i", len(data)) + data
+        chans = b"".join(c + b"\0" + struct.pack("<iBBBBii", ptype, 0, 0, 0, 0, 1, 1) for c in (b"A", b"B", b"G", b"R")) + b"\0"
+        box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+        hdr = struct.pack("<ii", 20000630, 2) + attr("channels", "chlist", chans) + attr("compression", "compression", bytes([comp]))
+        hdr += attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0") + b"\0"
+        blocks = []
+        for y in range(0, h, lines):
+            raw = b""
+            for l in range(y, min(y + lines, h)):
+                for ch in (3, 2, 1, 0):     # A, B, G, R
+                    raw += img[l, :, ch].astype(dt).tobytes()
+            enc = raw if comp == 0 else (zlib.compress(predict(raw)) if comp in (2, 3) else rle(predict(raw)))
+            if comp != 0 and len(enc) >= len(raw):
+                enc = raw               # the format stores a block raw when compression does not shrink it
+            blocks.append(struct.pack("<ii", y, len(enc)) + enc)
+        table_at = len(hdr)
+        pos = table_at + 8 * len(blocks)
+        offs = []
+        for bl in blocks:
+            offs.append(pos)
+            pos += len(bl)
+        f = tmp_path / ("c%d_%d.exr" % (comp, half))
+        f.write_bytes(hdr + struct.pack("<%dQ" % len(offs), *offs) + b"".join(blocks))
+        got = imageio.read_exr(str(f))
+        assert np.array_equal(got, img[:, :, :3].astype(dt).astype(np.float32)), (comp, half)
