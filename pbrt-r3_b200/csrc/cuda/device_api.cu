@@ -139,6 +139,8 @@ struct pt_scene {
   int* slot_of = nullptr;                  // pixel -> slot maps of the waves in flight (slot_segs x sample-bounds pixels)
   std::unique_ptr<DevBufs> slot_bufs;
   uint32_t slot_segs = 0;
+  uint32_t* counts_host = nullptr;         // pinned: 2 x 32 queue counters, copied after every shade stage (render_waves)
+  cudaEvent_t ev_iter[2] = {}, ev_time[2][4] = {};
   unsigned long long* counters = nullptr;  // [0] nodes [1] tris [2] vertices
   int* overflow = nullptr;
   uint32_t* fetch = nullptr;               // ray fetch counter of the stage entry points
@@ -159,6 +161,11 @@ struct pt_scene {
       if (ev_join[c]) cudaEventDestroy(ev_join[c]);
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
+    for (int k = 0; k < 2; k++) {
+      if (ev_iter[k]) cudaEventDestroy(ev_iter[k]);
+      for (int j = 0; j < 4; j++) if (ev_time[k][j]) cudaEventDestroy(ev_time[k][j]);
+    }
+    if (counts_host) cudaFreeHost(counts_host);
     if (stream) cudaStreamDestroy(stream);
     if (d) cudaFree(d);
   }
@@ -469,6 +476,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   memset(&LD, 0, sizeof(LD));
   int strat = D->integrator.light_strategy;
   if (strat == PT_LIGHTS_UNIFORM && D->n_lights != 1) strat = PT_LIGHTS_SPATIAL;
+  if (D->integrator.type == PT_INTEGRATOR_AOV) strat = PT_LIGHTS_UNIFORM;  // AOVIntegrator never samples a light: no table to build
   LD.strategy = strat;
   for (int a = 0; a < 3; a++) { LD.wb_min[a] = wb.mn[a]; LD.wb_max[a] = wb.mx[a]; LD.voxels[a] = 1; }
   uint32_t n_vox = 1;
@@ -640,7 +648,7 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
     int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
     CK(cudaMemsetAsync(Q.counts + 8, 0, 8 * sizeof(uint32_t), s->stream));  // shading-class bin sizes
     if (timed) cudaEventRecord(e0, s->stream);
-#define LAUNCH_TRACE(K, I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, K<NC, I, C>)(s->h, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow)
+#define LAUNCH_TRACE(K, I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, K<NC, I, C>)(s->h, W, Q, counts[0], counts[3], counts[2], s->counters, s->overflow, 0)
     if (s->h.accel_type == PT_ACCEL_LBVH) {
       if (inst) { if (count) LAUNCH_TRACE(k_trace_lbvh, true, true); else LAUNCH_TRACE(k_trace_lbvh, true, false); }
       else { if (count) LAUNCH_TRACE(k_trace_lbvh, false, true); else LAUNCH_TRACE(k_trace_lbvh, false, false); }
@@ -824,16 +832,21 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   Queues Q = s->Q;
   WaveState& W = s->W;
   const bool inst = s->h.has_instances != 0;
+  const bool is_aov = s->h.integrator.type == PT_INTEGRATOR_AOV;
   WaveTotals T;
-  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
-  if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); }
   std::vector<WaveSeg> segs(nseg);
   std::vector<int> seg_of_job(jobs.size(), -1);
   size_t next_job = 0, next_film = 0;
-  uint32_t n_ext = 0, n_sh = 0, n_mis = 0;
   int iter = 0, last_start = -(1 << 30), wave_iters = s->h.integrator.max_depth + 3;
-  uint32_t counts[32];
   int rc = 0;
+  // The host never waits for the bounce it has just queued.  Queue sizes stay on the device: k_raygen appends the
+  // camera rays behind the continuation rays of the last shade stage, k_trace reads the three queue sizes, k_shade its
+  // bin sizes.  The counters of iteration t are copied to pinned memory behind shade(t) and looked at only after iteration
+  // t + 1 has been queued, so the GPU always has the next bounce waiting.  Until they arrive the host works with upper
+  // bounds (a path pushes at most one continuation, one shadow and one MIS ray per vertex) for the launch shapes, and a
+  // wave is retired one iteration later than it could be - which changes when k_finish / k_film run, not what they add.
+  struct Pending { bool any = false; int iter = 0, slot = 0; uint32_t n_new = 0; bool timed = false; } pend;
+  uint32_t e_last = 0;  // continuation + camera rays traced by the last queued iteration (exact once its predecessor is resolved)
   // k_finish + k_film for the waves whose rays are all traced, in wave order
   auto gather_ready = [&]() -> int {
     while (next_film < jobs.size() && seg_of_job[next_film] >= 0 && segs[seg_of_job[next_film]].state == WaveSeg::TRACED) {
@@ -856,12 +869,35 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     }
     return 0;
   };
+  // the counters of the pending iteration have arrived: ray totals of the iteration queued after it, wave retirement
+  auto resolve = [&](uint32_t n_new_after) -> int {
+    if (!pend.any) return 0;
+    if (cudaEventSynchronize(s->ev_iter[pend.slot]) != cudaSuccess) { pt_set_error(std::string("bounce loop: ") + cudaGetErrorString(cudaGetLastError())); return 1; }
+    const uint32_t* c = s->counts_host + 32 * pend.slot;
+    if (pend.timed) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, s->ev_time[pend.slot][0], s->ev_time[pend.slot][1]);
+      cudaEventElapsedTime(&b, s->ev_time[pend.slot][2], s->ev_time[pend.slot][3]);
+      T.trace_ms += a;
+      T.shade_ms += b;
+    }
+    // what shade(pend.iter) pushed is what the next iteration traces (it is queued already, or nothing was pushed)
+    T.regular += c[1] + c[3];
+    T.shadow += c[2];
+    T.trace_rays += c[1] + c[2] + c[3];
+    for (uint32_t k = 0; k < nseg; k++)
+      if (segs[k].state == WaveSeg::ACTIVE && segs[k].start_iter <= pend.iter && (nseg > 1 ? c[16 + k] : c[1]) == 0) segs[k].state = WaveSeg::TRACED;
+    e_last = c[1] + n_new_after;
+    pend.any = false;
+    return gather_ready();
+  };
   for (;;) {
     if (++iter > 10000000) { pt_set_error("bounce loop did not terminate"); rc = 1; break; }
     // (1) start the next wave in an idle segment; the starts are spread over a wave's life (wave_iters iterations)
     bool any_busy = false;
     for (auto& g : segs) any_busy = any_busy || g.state != WaveSeg::IDLE;
     const int stagger = std::max(1, wave_iters / (int)nseg);
+    uint32_t n_new = 0;
     if (next_job < jobs.size() && (!any_busy || iter - last_start >= stagger)) {
       for (uint32_t k = 0; k < nseg; k++) {
         WaveSeg& g = segs[k];
@@ -879,11 +915,11 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
           T.launches++;
           g.map_c0 = J.c0; g.map_npix = J.npix;
         }
-        PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, PT_STREAM_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->h, W, Q, s->pixlist, J.c0, J.npix, J.s0, J.ns, base, n_ext);
+        PT_LAUNCH(grid_for(s, n, PT_SHADE_BLOCK, PT_STREAM_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_raygen<NC>)(s->h, W, Q, s->pixlist, J.c0, J.npix, J.s0, J.ns, base, 0u, Q.counts + 1);
         if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_raygen launch failed"); break; }
         T.launches++;
         if (st) st->camera_rays += n;
-        n_ext += n;
+        n_new = n;
         g.state = WaveSeg::ACTIVE;
         g.job = (int)next_job;
         g.start_iter = iter;
@@ -894,21 +930,23 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
       }
       if (rc) break;
     }
-    const uint32_t total = n_ext + n_mis + n_sh;
-    if (total == 0) {
-      // nothing left to trace: the draining waves are complete
-      for (auto& g : segs) if (g.state == WaveSeg::DRAINING) g.state = WaveSeg::TRACED;
-      if ((rc = gather_ready())) break;
+    // upper bounds of the three queues of this iteration (e_last = the vertices the pending shade stage had at most)
+    const uint32_t ub_ext = (pend.any ? e_last : 0u) + n_new, ub_side = pend.any ? e_last : 0u;
+    if (ub_ext == 0 && ub_side == 0) {
+      // nothing can be in flight: every started wave has been retired by the last resolve
+      if ((rc = resolve(0u))) break;
       bool busy = false;
       for (auto& g : segs) busy = busy || g.state != WaveSeg::IDLE;
       if (!busy && next_job >= jobs.size()) break;
+      if (busy) { pt_set_error("bounce loop: a wave is active without rays in flight"); rc = 1; break; }
       continue;
     }
     // (2) one bounce of every wave in flight: trace the three queues, shade the continuation hits
-    int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
+    const int slot = iter & 1;
+    int g = grid_for(s, (size_t)ub_ext + 2 * (size_t)ub_side, PT_TRACE_BLOCK, 8);
     if ((rc = (cudaMemsetAsync(Q.counts + 8, 0, 8 * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }  // shading-class bin sizes
-    if (timed) cudaEventRecord(e0, s->stream);
-#define LAUNCH_TRACE(K, I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, K<NC, I, C>)(s->h, W, Q, n_ext, n_mis, n_sh, s->counters, s->overflow)
+    if (timed) cudaEventRecord(s->ev_time[slot][0], s->stream);
+#define LAUNCH_TRACE(K, I, C) PT_LAUNCH(g, PT_TRACE_BLOCK, s->stream, K<NC, I, C>)(s->h, W, Q, n_new, 0u, 0u, s->counters, s->overflow, 1)
     if (s->h.accel_type == PT_ACCEL_LBVH) {
       if (inst) { if (count) LAUNCH_TRACE(k_trace_lbvh, true, true); else LAUNCH_TRACE(k_trace_lbvh, true, false); }
       else { if (count) LAUNCH_TRACE(k_trace_lbvh, false, true); else LAUNCH_TRACE(k_trace_lbvh, false, false); }
@@ -918,47 +956,37 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     }
 #undef LAUNCH_TRACE
     if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_trace launch failed"); break; }
-    if (timed) cudaEventRecord(e1, s->stream);
-    T.regular += n_ext + n_mis;
-    T.shadow += n_sh;
+    if (timed) { cudaEventRecord(s->ev_time[slot][1], s->stream); cudaEventRecord(s->ev_time[slot][2], s->stream); }
+    T.regular += n_new;
+    T.trace_rays += n_new;
     T.launches++;
     T.trace_launches++;
-    T.trace_rays += total;
-    // the shadow / MIS rays of the draining waves are resolved now
-    for (auto& sg : segs) if (sg.state == WaveSeg::DRAINING) sg.state = WaveSeg::TRACED;
-    if ((rc = gather_ready())) break;
-    if (timed) cudaEventRecord(e2, s->stream);
     cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream);  // queue counters + the trace fetch counter
     if ((rc = (cudaMemsetAsync(Q.counts + 16, 0, PT_MAX_SEGMENTS * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }
-    if (n_ext > 0 && s->h.integrator.type == PT_INTEGRATOR_AOV) {  // aov.rs: no bounces, nothing is pushed
-      PT_LAUNCH(grid_for(s, n_ext, 128, 8), 128, s->stream, k_aov<NC>)(s->h, W, Q.ext, n_ext);
-      if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_aov launch failed"); break; }
-      T.launches++;
-    } else if (n_ext > 0) {
-      int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
+    if (is_aov) {  // aov.rs: no bounces, nothing is pushed: only the camera rays of this iteration are in the queue
+      if (n_new > 0) {
+        PT_LAUNCH(grid_for(s, n_new, 128, 8), 128, s->stream, k_aov<NC>)(s->h, W, Q.ext, n_new);
+        if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_aov launch failed"); break; }
+        T.launches++;
+      }
+    } else if (ub_ext > 0) {
+      int gs = grid_for(s, ub_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
       s->Q_cur = Q;
       T.launches += shade_classes(s, NC, gs, vc);
       if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_shade launch failed"); break; }
     }
-    if (timed) cudaEventRecord(e3, s->stream);
-    if ((rc = (cudaMemcpyAsync(counts, Q.counts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess))) { pt_set_error("cudaMemcpyAsync failed"); break; }
-    if ((rc = (cudaStreamSynchronize(s->stream) != cudaSuccess))) { pt_set_error(std::string("bounce loop: ") + cudaGetErrorString(cudaGetLastError())); break; }
-    if (timed) {
-      float a = 0, b = 0;
-      cudaEventElapsedTime(&a, e0, e1);
-      cudaEventElapsedTime(&b, e2, e3);
-      T.trace_ms += a;
-      T.shade_ms += b;
-    }
-    for (uint32_t k = 0; k < nseg; k++)
-      if (segs[k].state == WaveSeg::ACTIVE && (nseg > 1 ? counts[16 + k] : counts[1]) == 0) segs[k].state = WaveSeg::DRAINING;
-    n_ext = counts[1];
-    n_sh = counts[2];
-    n_mis = counts[3];
+    if (timed) cudaEventRecord(s->ev_time[slot][3], s->stream);
+    if ((rc = (cudaMemcpyAsync(s->counts_host + 32 * slot, Q.counts, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess))) { pt_set_error("cudaMemcpyAsync failed"); break; }
+    if ((rc = (cudaEventRecord(s->ev_iter[slot], s->stream) != cudaSuccess))) { pt_set_error("cudaEventRecord failed"); break; }
     std::swap(Q.ext, Q.ext_next);
+    // (3) the iteration queued BEFORE this one: its counters say what this one traces and which waves it completes
+    const bool had = pend.any;
+    if ((rc = resolve(n_new))) break;
+    if (!had) e_last = n_new;
+    pend.any = true; pend.iter = iter; pend.slot = slot; pend.n_new = n_new; pend.timed = timed;
   }
-  if (timed) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); }
+  if (!rc && pend.any) rc = resolve(0u);
   if (rc) { invalidate_wave_state(s); return 1; }
   // leave the pixel -> slot maps empty for the next render
   for (uint32_t k = 0; k < nseg; k++)
@@ -1109,6 +1137,11 @@ int pt_scene_create(const pt_scene_desc* desc, int device, pt_scene** out) {
   for (int c = 0; c < CL_COUNT; c++) {
     CK(cudaStreamCreateWithFlags(&s->cls_stream[c], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&s->ev_join[c], cudaEventDisableTiming));
+  }
+  CK(cudaMallocHost((void**)&s->counts_host, 2 * 32 * sizeof(uint32_t)));
+  for (int k = 0; k < 2; k++) {
+    CK(cudaEventCreateWithFlags(&s->ev_iter[k], cudaEventDisableTiming));
+    for (int j = 0; j < 4; j++) CK(cudaEventCreate(&s->ev_time[k][j]));
   }
   if (build_scene(s.get(), desc)) return 1;
   *out = s.release();

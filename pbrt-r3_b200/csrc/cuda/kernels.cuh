@@ -292,7 +292,10 @@ struct WaveIO {
 // Scene::intersect for continuation (A) and MIS (C) rays, Scene::intersect_p for shadow (B) rays, in one launch.
 template <int NC, bool INST, bool COUNT>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(const __grid_constant__ DScene S, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis,
-                                                          uint32_t n_sh, unsigned long long* counters, int* overflow) {
+                                                          uint32_t n_sh, unsigned long long* counters, int* overflow, int dev_counts) {
+  // dev_counts: the queue sizes are what the last shade stage left in Q.counts (the host does not wait for them,
+  // render_waves); n_ext then only holds the camera rays appended since
+  if (dev_counts) { n_ext += Q.counts[1]; n_mis = Q.counts[3]; n_sh = Q.counts[2]; }
   __shared__ int smem[PT_SMEM_STACK * PT_TRACE_BLOCK];
   __shared__ float ssave[INST ? PT_SAVE_WORDS * PT_TRACE_BLOCK : 1];
   int spill[PT_MAX_STACK - PT_SMEM_STACK];
@@ -312,8 +315,10 @@ __global__ void __launch_bounds__(PT_TRACE_BLOCK, PT_TRACE_MINBLOCKS) k_trace(co
 
 template <int NC>
 __global__ void __launch_bounds__(PT_SHADE_BLOCK) k_raygen(const __grid_constant__ DScene S, WaveState W, Queues Q, const int* __restrict__ pixlist,
-                                                           uint32_t c0, uint32_t npix, int s0, uint32_t ns, uint32_t base, uint32_t q0) {
-  // path slots base .. base + npix * ns (the wave's segment of the state), appended to the extend queue at q0
+                                                           uint32_t c0, uint32_t npix, int s0, uint32_t ns, uint32_t base, uint32_t q0, const uint32_t* q0_dev) {
+  // path slots base .. base + npix * ns (the wave's segment of the state), appended to the extend queue at q0 (+ the
+  // number of continuation rays the last shade stage pushed, read on the device)
+  if (q0_dev) q0 += *q0_dev;
   const uint32_t total = npix * ns;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     uint32_t slot = i % npix, s = i / npix;
@@ -464,7 +469,8 @@ __device__ __forceinline__ void trace_lbvh(const DScene& S, IO& io, uint32_t tot
 }
 template <int NC, bool INST, bool COUNT>
 __global__ void __launch_bounds__(PT_TRACE_BLOCK) k_trace_lbvh(const __grid_constant__ DScene S, WaveState W, Queues Q, uint32_t n_ext, uint32_t n_mis, uint32_t n_sh,
-                                                               unsigned long long* counters, int* overflow) {
+                                                               unsigned long long* counters, int* overflow, int dev_counts) {
+  if (dev_counts) { n_ext += Q.counts[1]; n_mis = Q.counts[3]; n_sh = Q.counts[2]; }
   TravCounters tc;
   tc.nodes = 0; tc.tris = 0;
   int ovf = 0;
