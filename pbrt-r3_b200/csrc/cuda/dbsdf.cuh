@@ -268,7 +268,7 @@ PT_HD Sp<NC> lobe_fresnel(const DScene& S, const Lobe& L, float ci) {
 }
 
 template <int NC, int CM = PT_CM_ANY>
-PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
+PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe L, f3 wo, f3 wi) {
   switch (L.kind) {
     PT_KIND(LB_LAMBERT) return sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * PT_INV_PI;
     PT_KIND(LB_OREN) {
@@ -315,7 +315,7 @@ PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe& L, f3 wo, f3 wi) {
   }
 }
 template <int CM = PT_CM_ANY>
-PT_HDN float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
+PT_HDN float lobe_pdf(const Lobe L, f3 wo, f3 wi) {
   switch (L.kind) {
     case LB_LAMBERT: case LB_OREN: if (!(CM & 3)) { PT_UNREACHABLE(); } return same_hemi(wo, wi) ? acth(wi) * PT_INV_PI : 0.0f;
     PT_KIND(LB_MF_REFL) {
@@ -343,7 +343,7 @@ PT_HDN float lobe_pdf(const Lobe& L, f3 wo, f3 wi) {
 // Every shared value is produced by the same operations on the same operands as in the two separate functions
 // (wi + wo and wo + wi are the same float sums), so f and pdf are bit-identical to lobe_f / lobe_pdf.
 template <int NC, int CM = PT_CM_ANY>
-PT_HDN void lobe_f_pdf(const DScene& S, const Lobe& L, f3 wo, f3 wi, bool want_f, Sp<NC>* f, float* pdf) {
+PT_HDN void lobe_f_pdf(const DScene& S, const Lobe L, f3 wo, f3 wi, bool want_f, Sp<NC>* f, float* pdf) {
   if (((CM >> LB_MF_REFL) & 1) && L.kind == LB_MF_REFL) {
     *f = sp_const<NC>(0.0f);
     *pdf = 0.0f;
@@ -374,7 +374,7 @@ PT_HDN void lobe_f_pdf(const DScene& S, const Lobe& L, f3 wo, f3 wi, bool want_f
 // For the non-specular lobes *f is NOT evaluated: BSDF::sample_f recomputes f over all matching lobes right after
 // (bsdf.rs:178-196; bsdf_sample below), so the reference's own value is always discarded, and no decision depends on it.
 template <int NC, int CM = PT_CM_ANY>
-PT_HDN bool lobe_sample(const DScene& S, const Lobe& L, f3 wo, f2 u, Sp<NC>* f, f3* wi_out, float* pdf, int* stype) {
+PT_HDN bool lobe_sample(const DScene& S, const Lobe L, f3 wo, f2 u, Sp<NC>* f, f3* wi_out, float* pdf, int* stype) {
   *stype = 0;
   switch (L.kind) {
     case LB_LAMBERT: case LB_OREN: {
@@ -581,11 +581,16 @@ PT_HD SurfD make_surface(const DScene& S, int tri, int instance, f3 ro, f3 rd, f
 }
 
 // ---- BSDF ---------------------------------------------------------------------------------------------------------
+// at most two lobes per BSDF (plastic: diffuse + glossy; rough glass: reflection + transmission).  Loops over the lobes have a
+// constant trip count and the lobe functions take the lobe by value, so that a BsdfD lives in registers: indexed through
+// a pointer it sat in the local-memory frame (ncu, matte kernel: 5 % of the stall samples on the first load of B.lobe[i].kind)
+#define PT_MAX_LOBES 2
+#define PT_LOBE_LOOP(i) _Pragma("unroll") for (int i = 0; i < PT_MAX_LOBES; i++) if (i < B.n)
 struct BsdfD {
   f3 ns, ng, ss, ts;
   float eta;
   int n;       // number of lobes; -1 = no BSDF (ray passes through)
-  Lobe lobe[2];
+  Lobe lobe[PT_MAX_LOBES];
 };
 PT_HD f3 to_local(const BsdfD& B, f3 v) { return mk3(dot3(v, B.ss), dot3(v, B.ts), dot3(v, B.ns)); }
 PT_HD f3 to_world(const BsdfD& B, f3 v) {
@@ -594,7 +599,7 @@ PT_HD f3 to_world(const BsdfD& B, f3 v) {
 PT_HD bool fin3(f3 v) { return isfinite_(v.x) && isfinite_(v.y) && isfinite_(v.z); }
 PT_HD int bsdf_count(const BsdfD& B, int flags) {
   int c = 0;
-  for (int i = 0; i < B.n; i++) if (lobe_matches(B.lobe[i].kind, flags)) c++;
+  PT_LOBE_LOOP(i) if (lobe_matches(B.lobe[i].kind, flags)) c++;
   return c;
 }
 
@@ -608,6 +613,12 @@ PT_HD bool spectrum_black(const DScene& S, int idx, bool clamp0) {
 // Material::compute_scattering_functions for the five in-scope materials.
 // Spectra that the reference clamps (clamp_zero) are clamped on the HOST at upload when a negative value is
 // present, so the device can treat every stored reflectance as already clamped except matte Kd (never clamped).
+// appends a lobe (the slot index is 0 or 1: two selects instead of an indexed store into the frame)
+PT_HD void bsdf_add(BsdfD* B, int& n, const Lobe& L) {
+  if (n == 0) B->lobe[0] = L;
+  else B->lobe[1] = L;
+  n++;
+}
 template <int NC, int MT = -1>
 PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   B->n = -1;
@@ -620,7 +631,7 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
     case PT_MAT_MATTE: {
       if (MT != -1 && MT != PT_MAT_MATTE) { PT_UNREACHABLE(); }
       if (!spectrum_black<NC>(S, M.kd, false)) {
-        Lobe& L = B->lobe[n++];
+        Lobe L;
         L.sp0 = M.kd; L.sp1 = -1; L.fres = FR_NOOP; L.ei = L.et = 1.0f;
         float sig = clampf(M.sigma, 0.0f, 90.0f);
         if (sig == 0.0f) { L.kind = LB_LAMBERT; L.a = L.b = 0.0f; }
@@ -631,28 +642,32 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
           L.a = 1.0f - (s2 / (2.0f * (s2 + 0.33f)));
           L.b = 0.45f * s2 / (s2 + 0.09f);
         }
+        bsdf_add(B, n, L);
       }
       break;
     }
     case PT_MAT_PLASTIC: {
       if (MT != -1 && MT != PT_MAT_PLASTIC) { PT_UNREACHABLE(); }
       if (!spectrum_black<NC>(S, M.kd, true)) {
-        Lobe& L = B->lobe[n++];
+        Lobe L;
         L.kind = LB_LAMBERT; L.sp0 = M.kd; L.sp1 = -1; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = L.et = 1.0f;
+        bsdf_add(B, n, L);
       }
       if (!spectrum_black<NC>(S, M.ks, true)) {
-        Lobe& L = B->lobe[n++];
+        Lobe L;
         float a = ldg(S.alpha + 2 * mi);
         L.kind = LB_MF_REFL; L.sp0 = M.ks; L.sp1 = -1; L.fres = FR_DIEL; L.ei = 1.5f; L.et = 1.0f;
         L.a = fmaxf(0.001f, a); L.b = fmaxf(0.001f, a);
+        bsdf_add(B, n, L);
       }
       break;
     }
     case PT_MAT_MIRROR: {
       if (MT != -1 && MT != PT_MAT_MIRROR) { PT_UNREACHABLE(); }
       if (!spectrum_black<NC>(S, M.kr, true)) {
-        Lobe& L = B->lobe[n++];
+        Lobe L;
         L.kind = LB_MIRROR; L.sp0 = M.kr; L.sp1 = -1; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = L.et = 1.0f;
+        bsdf_add(B, n, L);
       }
       break;
     }
@@ -662,26 +677,30 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
       if (rb && tb) return;  // no BSDF at all
       eta = M.eta;
       if (M.uroughness == 0.0f && M.vroughness == 0.0f) {
-        Lobe& L = B->lobe[n++];
+        Lobe L;
         L.kind = LB_FRESNEL_SPEC; L.sp0 = M.kr; L.sp1 = M.ks; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = 1.0f; L.et = eta;
+        bsdf_add(B, n, L);
       } else {
         float ax = fmaxf(0.001f, ldg(S.alpha + 2 * mi)), ay = fmaxf(0.001f, ldg(S.alpha + 2 * mi + 1));
         if (!rb) {
-          Lobe& L = B->lobe[n++];
+          Lobe L;
           L.kind = LB_MF_REFL; L.sp0 = M.kr; L.sp1 = -1; L.fres = FR_DIEL; L.ei = 1.0f; L.et = eta; L.a = ax; L.b = ay;
+          bsdf_add(B, n, L);
         }
         if (!tb) {
-          Lobe& L = B->lobe[n++];
+          Lobe L;
           L.kind = LB_MF_TRANS; L.sp0 = M.ks; L.sp1 = -1; L.fres = FR_NOOP; L.ei = 1.0f; L.et = eta; L.a = ax; L.b = ay;
+          bsdf_add(B, n, L);
         }
       }
       break;
     }
     case PT_MAT_METAL: {
       if (MT != -1 && MT != PT_MAT_METAL) { PT_UNREACHABLE(); }
-      Lobe& L = B->lobe[n++];
+      Lobe L;
       L.kind = LB_MF_REFL; L.sp0 = M.kr; L.sp1 = M.ks; L.fres = FR_COND; L.ei = L.et = 1.0f;
       L.a = fmaxf(0.001f, ldg(S.alpha + 2 * mi)); L.b = fmaxf(0.001f, ldg(S.alpha + 2 * mi + 1));
+      bsdf_add(B, n, L);
       break;
     }
     default: return;
@@ -698,7 +717,7 @@ template <int NC, int CM = PT_CM_ANY>
 PT_HD Sp<NC> bsdf_sum_f(const DScene& S, const BsdfD& B, f3 wo, f3 wi, f3 wo_w, f3 wi_w, int flags) {
   bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
   Sp<NC> r = sp_const<NC>(0.0f);
-  for (int i = 0; i < B.n; i++) {
+  PT_LOBE_LOOP(i) {
     int tp = lobe_type(B.lobe[i].kind);
     if (lobe_matches(B.lobe[i].kind, flags) && ((refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS)))) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
   }
@@ -716,7 +735,7 @@ PT_HDN float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
   if (wo.z == 0.0f || !fin3(wo)) return 0.0f;
   int count = 0;
   float p = 0.0f;
-  for (int i = 0; i < B.n; i++)
+  PT_LOBE_LOOP(i)
     if (lobe_matches(B.lobe[i].kind, flags)) { p = p + lobe_pdf<CM>(B.lobe[i], wo, wi); count++; }
   return count > 0 ? p / (float)count : 0.0f;
 }
@@ -732,7 +751,7 @@ PT_HD1 void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int fl
   Sp<NC> r = sp_const<NC>(0.0f);
   int count = 0;
   float p = 0.0f;
-  for (int i = 0; i < B.n; i++) {
+  PT_LOBE_LOOP(i) {
     if (!lobe_matches(B.lobe[i].kind, flags)) continue;
     const int tp = lobe_type(B.lobe[i].kind);
     const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
@@ -761,9 +780,9 @@ PT_HD bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags
   int comp = (int)floorf(u.x * (float)matching);
   if (comp > matching - 1) comp = matching - 1;
   int index = -1, cnt = comp;
-  for (int i = 0; i < B.n; i++)
+  PT_LOBE_LOOP(i)
     if (lobe_matches(B.lobe[i].kind, flags)) { if (cnt == 0) { index = i; break; } cnt--; }
-  const Lobe& L = B.lobe[index];
+  const Lobe L = index == 0 ? B.lobe[0] : B.lobe[1];
   f2 ur = mk2(fminf((u.x * (float)matching) - (float)comp, PT_ONE_MINUS_EPS), u.y);
   f3 wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return false;
@@ -778,7 +797,7 @@ PT_HD bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags
   f3 wi_w = to_world(B, wi);
   if (NC != 3 && (ltype & F_SPEC) == 0) {  // 60 bins: the plain form (no spectrum-sized temporaries)
     if (matching > 1)
-      for (int i = 0; i < B.n; i++)
+      PT_LOBE_LOOP(i)
         if (i != index && lobe_matches(B.lobe[i].kind, flags)) pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
     fv = bsdf_sum_f<NC, CM>(S, B, wo, wi, wo_w, wi_w, flags);
   } else if ((ltype & F_SPEC) == 0) {
@@ -786,7 +805,7 @@ PT_HD bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags
     // geometric normal (bsdf.rs:178-196), the sampled lobe included: one fused evaluation per other lobe, both in lobe order
     const bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
     Sp<NC> r = sp_const<NC>(0.0f);
-    for (int i = 0; i < B.n; i++) {
+    PT_LOBE_LOOP(i) {
       if (!lobe_matches(B.lobe[i].kind, flags)) continue;
       const int tp = lobe_type(B.lobe[i].kind);
       const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));

@@ -299,6 +299,40 @@ PT_HD void push_next(const WaveState& W, Queues& Q, uint32_t i) {
   }
 }
 
+// the appends of one shaded vertex to the shadow, MIS and next extend queues, warp-aggregated, the three atomics in flight
+// together (one round trip)
+PT_HD void push_rays(const WaveState& W, Queues& Q, uint32_t i, bool sh, bool mis, bool ext) {
+#if defined(__CUDA_ARCH__)
+  const unsigned m = __activemask();
+  const unsigned bs = __ballot_sync(m, sh), bm = __ballot_sync(m, mis), be = __ballot_sync(m, ext);
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  uint32_t b0 = 0, b1 = 0, b2 = 0;
+  if (lane == leader) {
+    if (bs) b0 = atomicAdd(&Q.counts[2], (uint32_t)__popc(bs));
+    if (bm) b1 = atomicAdd(&Q.counts[3], (uint32_t)__popc(bm));
+    if (be) b2 = atomicAdd(&Q.counts[1], (uint32_t)__popc(be));
+  }
+  b0 = __shfl_sync(m, b0, leader);
+  b1 = __shfl_sync(m, b1, leader);
+  b2 = __shfl_sync(m, b2, leader);
+  const unsigned lt = (1u << lane) - 1u;
+  if (sh) Q.shadow[b0 + (uint32_t)__popc(bs & lt)] = i;
+  if (mis) Q.mis[b1 + (uint32_t)__popc(bm & lt)] = i;
+  if (ext) {
+    Q.ext_next[b2 + (uint32_t)__popc(be & lt)] = i;
+    if (W.nseg > 1) {  // continuation rays per wave in flight (the host retires a wave that pushed none)
+      const uint32_t seg = i / W.seg_cap;
+      const unsigned peers = __match_any_sync(be, seg);
+      if (lane == __ffs(peers) - 1) atomicAdd(&Q.counts[16 + seg], (uint32_t)__popc(peers));
+    }
+  }
+#else
+  if (sh) Q.shadow[Q.counts[2]++] = i;
+  if (mis) Q.mis[Q.counts[3]++] = i;
+  if (ext) push_next(W, Q, i);
+#endif
+}
+
 // camera-ray generation for path slot i of the current wave: pixel (px,py) absolute, sample number n
 // Sampler "random": tile_slot / tile_seq select the PCG32 stream (packed into st.index: slot << 32 | sequence number = tile
 // index of the whole film); the path is appended to the queue at position qpos instead of i.
@@ -380,6 +414,10 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
     (*vertex_counter)++;
 #endif
   }
+  // The three queue appends of a vertex (shadow ray, MIS ray, continuation ray) are made together at the end: a warp-aggregated
+  // append waits for its atomic's return value, and three of them spread over the body cost three L2 round trips per warp
+  // (ncu, matte kernel of config 2: 11 % of the stall samples on the shuffles that hand the base out).
+  bool push_sh = false, push_mis = false, push_ext = false;
   SampleStream st;
   st.index = W.sindex[i];
   st.dim = W.dim[i];
@@ -426,7 +464,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
             st_store<NC>(W.pendA, cap, i, beta * (ld / light_pdf));
             W.sh_o[i] = mk4(ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, 0.0f);
             W.sh_d[i] = mk4(ls.sh_d.x, ls.sh_d.y, ls.sh_d.z, 1.0f - PT_SHADOW_EPS);
-            Q.shadow[queue_push(&Q.counts[2])] = i;
+            push_sh = true;
           }
         }
       }
@@ -453,7 +491,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
               W.mis_o[i] = mk4(o.x, o.y, o.z, pt_inf());
               W.mis_d[i] = mk4(wi2.x, wi2.y, wi2.z, rtime);
               W.mis_light[i] = ln;
-              Q.mis[queue_push(&Q.counts[3])] = i;
+              push_mis = true;
             }
           }
         }
@@ -463,38 +501,41 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
 
   // --- sample the BSDF for the next direction (path.rs:139-167)
   st_store<NC>(W.L, cap, i, L);
-  f3 wo = -rd;
-  Sp<NC> f;
-  f3 wi;
-  float pdf;
-  int sflags;
-  f2 ub = get2d(S, st);
-  if (!bsdf_sample<NC, CM>(S, B, wo, ub, F_ALL, &f, &wi, &pdf, &sflags)) return;
-  if (sp_black(f) || pdf == 0.0f) return;
-  beta = beta * (f * (absdot3(wi, si.sn) / pdf));
-  specular_bounce = (sflags & F_SPEC) != 0;
-  float eta_scale = W.eta_scale[i];
-  if ((sflags & F_SPEC) && (sflags & F_TRANS)) {
-    float eta = B.eta;
-    eta_scale *= (dot3(wo, si.n) > 0.0f) ? (eta * eta) : 1.0f / (eta * eta);
-  }
-  f3 o = offset_origin(si.p, si.perr, si.n, wi);
-  // Russian roulette (path.rs:219-229)
-  Sp<NC> rr = beta * eta_scale;
-  float rrmax = sp_max(rr);
-  if (rrmax < S.integrator.rr_threshold && bounces > 3) {
-    float q = fmaxf(0.05f, 1.0f - rrmax);
-    if (get1d(S, st) < q) return;
-    beta = beta / (1.0f - q);
-  }
-  bounces += 1;
-  st_store<NC>(W.beta, cap, i, beta);
-  W.eta_scale[i] = eta_scale;
-  W.flags[i] = ((uint32_t)bounces << 8) | (specular_bounce ? 1u : 0u);
-  W.dim[i] = st.dim;
-  W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
-  W.ray_d[i] = mk4(wi.x, wi.y, wi.z, rtime);
-  push_next(W, Q, i);
+  do {
+    f3 wo = -rd;
+    Sp<NC> f;
+    f3 wi;
+    float pdf;
+    int sflags;
+    f2 ub = get2d(S, st);
+    if (!bsdf_sample<NC, CM>(S, B, wo, ub, F_ALL, &f, &wi, &pdf, &sflags)) break;
+    if (sp_black(f) || pdf == 0.0f) break;
+    beta = beta * (f * (absdot3(wi, si.sn) / pdf));
+    specular_bounce = (sflags & F_SPEC) != 0;
+    float eta_scale = W.eta_scale[i];
+    if ((sflags & F_SPEC) && (sflags & F_TRANS)) {
+      float eta = B.eta;
+      eta_scale *= (dot3(wo, si.n) > 0.0f) ? (eta * eta) : 1.0f / (eta * eta);
+    }
+    f3 o = offset_origin(si.p, si.perr, si.n, wi);
+    // Russian roulette (path.rs:219-229)
+    Sp<NC> rr = beta * eta_scale;
+    float rrmax = sp_max(rr);
+    if (rrmax < S.integrator.rr_threshold && bounces > 3) {
+      float q = fmaxf(0.05f, 1.0f - rrmax);
+      if (get1d(S, st) < q) break;
+      beta = beta / (1.0f - q);
+    }
+    bounces += 1;
+    st_store<NC>(W.beta, cap, i, beta);
+    W.eta_scale[i] = eta_scale;
+    W.flags[i] = ((uint32_t)bounces << 8) | (specular_bounce ? 1u : 0u);
+    W.dim[i] = st.dim;
+    W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+    W.ray_d[i] = mk4(wi.x, wi.y, wi.z, rtime);
+    push_ext = true;
+  } while (0);
+  push_rays(W, Q, i, push_sh, push_mis, push_ext);
 }
 
 // AOVIntegrator::li (integrators/aov.rs:101-181) for path slot i after its camera ray was traced: a geometric quantity
