@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PT_ABI_VERSION 2
+#define PT_ABI_VERSION 3
 
 /* ---- plugin names carried as enums (string names are resolved by the host) ---- */
 enum pt_material_type {       /* reference src/materials/create_material.rs:20-72 */
@@ -146,7 +146,9 @@ typedef struct pt_sampler {
 
 enum pt_integrator_type {
   PT_INTEGRATOR_PATH = 0,     /* integrators/path.rs */
-  PT_INTEGRATOR_AOV = 1       /* integrators/aov.rs: one closest-hit query per camera sample, a geometric quantity as colour */
+  PT_INTEGRATOR_AOV = 1,      /* integrators/aov.rs: one closest-hit query per camera sample, a geometric quantity as colour */
+  PT_INTEGRATOR_AO = 2        /* integrators/ao.rs ("ambientocclusion"): nsamples any-hit queries per camera sample, directions
+                                 from the sampler's 2D sample ARRAY (request_2d_array / get_2d_array) */
 };
 enum pt_aov_target {          /* integrators/aov.rs:10-58; the targets that need ray differentials are not supported */
   PT_AOV_DISTANCE = 0,        /* "distance": t_max / |d|                       */
@@ -163,6 +165,8 @@ typedef struct pt_integrator { /* integrators/path.rs:252-271, integrators/aov.r
   int32_t type;               /* pt_integrator_type */
   int32_t aov_target;         /* pt_aov_target */
   float aov_scale;
+  int32_t ao_samples;         /* ambientocclusion "nsamples" (default 64; 1 under --quick), ao.rs:124-131 */
+  int32_t ao_cos_sample;      /* ambientocclusion "cossample" (default true) */
 } pt_integrator;
 
 typedef struct pt_accel {     /* accelerators/bvh/create_bvh_accelerator.rs:9-28 */

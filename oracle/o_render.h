@@ -57,6 +57,7 @@ struct Scene {
     world_radius = length(dg) * 0.5f;  // Bounds3f::bounding_sphere (bounds3.rs:184-188)
     if (desc->n_lights > 0) distrib.init(desc, world_bound, world_radius);
     scfg = make_sampler_config(desc->sampler.type, desc->sampler.samples_per_pixel, desc->film.sample_bounds, desc->sampler.sample_at_pixel_center != 0);
+    if (desc->integrator.type == PT_INTEGRATOR_AO) scfg.n_arrays_2d = 1;  // AOIntegrator::new: request_2d_array(n_samples) (ao.rs:29)
   }
   bool intersect(const Ray& r, Hit* h, Counters* c) const {
     if (c) c->regular_rays++;
@@ -202,12 +203,49 @@ inline Spec<NC> aov_li(Scene<NC>& sc, const Ray& r, Counters* cnt, PathTrace* tr
   return out;
 }
 
+// AOIntegrator::li (integrators/ao.rs:50-105): n_samples any-hit queries from the first surface that has a BSDF, directions
+// from the sampler's 2D sample array in the frame of the TRUE geometry
+template <int NC>
+inline Spec<NC> ao_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace) {
+  const pt_scene_desc* d = sc.d;
+  Spec<NC> l;
+  Ray ray = r;
+  const uint32_t n_samples = (uint32_t)d->integrator.ao_samples;  // round_count is the identity for halton / sobol (sampler.rs:41-43)
+  const bool cos_sample = d->integrator.ao_cos_sample != 0;
+  for (;;) {
+    Hit h;
+    if (!sc.intersect(ray, &h, cnt)) break;
+    SurfInt isect = make_si(d, h);
+    if (trace && trace->first_tri == -1) { trace->first_tri = h.tri; trace->first_t = h.t; }
+    RefPoint rp; rp.p = isect.p; rp.p_error = isect.p_error; rp.n = isect.n; rp.time = isect.time;
+    if (d->tri_material[isect.tri] < 0) {  // isect.bsdf.is_none(): continue through the surface (ao.rs:68-71)
+      ray = spawn_ray(rp, ray.d);
+      continue;
+    }
+    Vec3 n = face_forward(isect.n, ray.d * -1.0f);
+    Vec3 s = normalize(isect.dpdu);
+    Vec3 t = cross(isect.n, s);
+    for (uint32_t i = 0; i < n_samples; i++) {
+      Vec2 u = sampler.array_2d_elem(n_samples, i);
+      Vec3 wl;
+      Float pdf;
+      if (cos_sample) { wl = cosine_sample_hemisphere(u); pdf = fabsf(wl.z) * INV_PI; }
+      else { wl = uniform_sample_hemisphere(u); pdf = INV_2_PI; }
+      Vec3 wi(wl.x * s.x + wl.y * t.x + wl.z * n.x, wl.x * s.y + wl.y * t.y + wl.z * n.y, wl.x * s.z + wl.y * t.z + wl.z * n.z);
+      if (!sc.intersect_p(spawn_ray(rp, wi), cnt)) l = l + Spec<NC>(dot(wi, n) / (pdf * (Float)n_samples));
+    }
+    break;
+  }
+  return l;
+}
+
 template <int NC>
 inline Spec<NC> path_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace);
 // SamplerIntegrator::li of the scene's integrator
 template <int NC>
 inline Spec<NC> integrator_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace) {
   if (sc.d->integrator.type == PT_INTEGRATOR_AOV) return aov_li(sc, r, cnt, trace);
+  if (sc.d->integrator.type == PT_INTEGRATOR_AO) return ao_li(sc, r, sampler, cnt, trace);
   return path_li(sc, r, sampler, cnt, trace);
 }
 

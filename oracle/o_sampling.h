@@ -172,6 +172,8 @@ struct SamplerConfig {
   int base_scales[2], base_exponents[2], sample_stride, mult_inverse[2];
   // sobol (samplers/sobol.rs:18-31)
   uint32_t resolution, log2_resolution;
+  // sample arrays the integrator requested (base_sampler.rs:32-44): ambientocclusion one 2D array, directlighting two per light
+  uint32_t n_arrays_1d, n_arrays_2d;
 };
 
 inline uint64_t math_mod(int64_t a, int64_t b) {  // halton.rs:22-29
@@ -278,14 +280,27 @@ struct Sampler {
     }
     return s;
   }
+  // GlobalSampler: dimensions [array_start_dim = 5, array_end_dim) belong to the sample arrays (global_sampler.rs:22,
+  // halton.rs:176-178 / sobol.rs:43-45) and are skipped by get_1d / get_2d (halton.rs:227-231, 241-245)
+  uint32_t array_end_dim() const { return 5u + cfg->n_arrays_1d + 2u * cfg->n_arrays_2d; }
+  // element i of get_2d_array(n) for the current sample: start_pixel fills array[j] from the index of sample NUMBER j,
+  // j < n * spp, and get_2d_array hands out [n * s, n * (s + 1)) (halton.rs:193-207, base_sampler.rs:59-70).  Every 2D array
+  // reads the same two dimensions (`dim` is not advanced per array in the reference).
+  Vec2 array_2d_elem(uint32_t n, uint32_t i) const {
+    int64_t index = index_for_sample((int64_t)n * sample_num + (int64_t)i);
+    uint32_t dim = 5u + cfg->n_arrays_1d;
+    return Vec2(sample_dimension(index, dim), sample_dimension(index, dim + 1));
+  }
   Float get_1d() {
     if (cfg->type == 2) return rng.uniform_float();
+    if (dimension >= 5u && dimension < array_end_dim()) dimension = array_end_dim();
     Float x = sample_dimension(interval_index, dimension);
     dimension += 1;
     return x;
   }
   Vec2 get_2d() {
     if (cfg->type == 2) { Float a = rng.uniform_float(); Float b = rng.uniform_float(); return Vec2(a, b); }
+    if (dimension + 1u >= 5u && dimension < array_end_dim()) dimension = array_end_dim();
     Float x = sample_dimension(interval_index, dimension);
     Float y = sample_dimension(interval_index, dimension + 1);
     dimension += 2;
@@ -307,6 +322,12 @@ inline Vec2 concentric_sample_disk(Vec2 u) {                                    
     Float theta = PI_OVER_2 - PI_OVER_4 * (uo.x / uo.y);
     return Vec2(r * cosf(theta), r * sinf(theta));
   }
+}
+inline Vec3 uniform_sample_hemisphere(Vec2 u) {                                                                 // :85-90
+  Float z = u.x;
+  Float r = sqrtf(rmax(0.0f, 1.0f - z * z));
+  Float phi = 2.0f * PI * u.y;
+  return Vec3(r * cosf(phi), r * sinf(phi), z);
 }
 inline Vec3 cosine_sample_hemisphere(Vec2 u) {                                                                  // :141-145
   Vec2 d = concentric_sample_disk(u);

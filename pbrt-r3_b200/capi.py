@@ -10,12 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PBRT_R3_B200_LIB") or os.path.join(HERE, "libpbrt_r3_b200.so")  # env override: kernel A/B experiments
 DATA_DIR = os.path.join(HERE, "data")
 
-PT_ABI_VERSION = 2
+PT_ABI_VERSION = 3
 PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MIRROR = -1, 0, 1, 2, 3, 4
 PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT = 0, 1, 2, 3
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
-PT_INTEGRATOR_PATH, PT_INTEGRATOR_AOV = 0, 1
+PT_INTEGRATOR_PATH, PT_INTEGRATOR_AOV, PT_INTEGRATOR_AO = 0, 1, 2
 PT_AOV_DISTANCE, PT_AOV_DEPTH, PT_AOV_N, PT_AOV_NS, PT_AOV_UV, PT_AOV_DPDUS = 0, 1, 2, 3, 4, 5
 PT_SPECTRUM_RGB, PT_SPECTRUM_SAMPLED = 0, 1
 PT_TRI_REVERSE_ORIENTATION, PT_TRI_SWAPS_HANDEDNESS, PT_TRI_TWO_SIDED, PT_TRI_HAS_N, PT_TRI_HAS_UV, PT_TRI_HAS_S = 1, 2, 4, 8, 16, 32
@@ -60,7 +60,7 @@ class pt_sampler(C.Structure):
 
 class pt_integrator(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32), ("type", C.c_int32),
-                ("aov_target", C.c_int32), ("aov_scale", C.c_float)]
+                ("aov_target", C.c_int32), ("aov_scale", C.c_float), ("ao_samples", C.c_int32), ("ao_cos_sample", C.c_int32)]
 
 
 class pt_accel(C.Structure):

@@ -115,6 +115,12 @@ PT_HD f3 cosine_hemisphere(f2 u) {
   float z = sqrtf(fmaxf(0.0f, 1.0f - d.x * d.x - d.y * d.y));
   return mk3(d.x, d.y, z);
 }
+PT_HD f3 uniform_hemisphere(f2 u) {  // sampling.rs:85-90
+  float z = u.x;
+  float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+  float phi = 2.0f * PT_PI * u.y;
+  return mk3(r * pt_cosf(phi), r * pt_sinf(phi), z);
+}
 PT_HD float power_heuristic1(float f, float g) { return (f * f) / (f * f + g * g); }  // nf = ng = 1
 
 // ---- Fresnel (fresnel.rs:16-82) ---------------------------------------------------------------------------
@@ -449,6 +455,7 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe L, f3 wo, f2 u, Sp<NC>* f, f
 // ---- surface interaction --------------------------------------------------------------------------------------
 struct SurfD {
   f3 p, perr, n, wo, sn, sdpdu;
+  f3 dpdu;  // of the true geometry (read by the ambientocclusion integrator only)
   int tri;
 };
 
@@ -496,6 +503,7 @@ PT_HD1 SurfD tri_surface(const DScene& S, int tri, f3 rd, float b0, float b1, fl
   si.n = n;
   si.sn = n;
   si.sdpdu = dpdu;
+  si.dpdu = dpdu;
   si.tri = tri;
   const bool has_n = (flags & PT_TRI_HAS_N) && S.tri_n, has_s = (flags & PT_TRI_HAS_S) && S.tri_s;
   if (has_n || has_s) {  // triangle.rs:376-444
@@ -565,6 +573,7 @@ PT_HD1 SurfD surf_to_world(const InstanceRec& I, const SurfD& s) {
   r.wo = norm3(mat_vector(m, s.wo));
   r.sn = norm3(mat_normal_inv(I.minv, s.sn));
   r.sdpdu = mat_vector(m, s.sdpdu);
+  r.dpdu = mat_vector(m, s.dpdu);
   r.sn = faceforward(r.sn, r.n);
   return r;
 }

@@ -476,7 +476,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   memset(&LD, 0, sizeof(LD));
   int strat = D->integrator.light_strategy;
   if (strat == PT_LIGHTS_UNIFORM && D->n_lights != 1) strat = PT_LIGHTS_SPATIAL;
-  if (D->integrator.type == PT_INTEGRATOR_AOV) strat = PT_LIGHTS_UNIFORM;  // AOVIntegrator never samples a light: no table to build
+  if (D->integrator.type == PT_INTEGRATOR_AOV || D->integrator.type == PT_INTEGRATOR_AO) strat = PT_LIGHTS_UNIFORM;  // these integrators never sample a light: no table to build
   LD.strategy = strat;
   for (int a = 0; a < 3; a++) { LD.wb_min[a] = wb.mn[a]; LD.wb_max[a] = wb.mx[a]; LD.voxels[a] = 1; }
   uint32_t n_vox = 1;
@@ -670,6 +670,15 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
       PT_LAUNCH(grid_for(s, n_ext, 128, 8), 128, s->stream, k_aov<NC>)(s->h, W, Q.ext, n_ext);
       CK(cudaGetLastError());
       T->launches++;
+    } else if (s->h.integrator.type == PT_INTEGRATOR_AO) {  // ao.rs: every path in flight makes its next occlusion ray
+      if constexpr (NC == 3) {
+        Queues Qo = Q;
+        Qo.shadow = Q.mis;  // the queue this round fills; the one just traced is its input list
+        PT_LAUNCH(grid_for(s, (size_t)counts[0] + counts[2], PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_ao<NC>)(s->h, W, Qo, Q.shadow, counts[0], counts[2], nullptr);
+        CK(cudaGetLastError());
+        std::swap(Q.shadow, Q.mis);
+        T->launches++;
+      }
     } else if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
@@ -833,11 +842,12 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   WaveState& W = s->W;
   const bool inst = s->h.has_instances != 0;
   const bool is_aov = s->h.integrator.type == PT_INTEGRATOR_AOV;
+  const bool is_ao = s->h.integrator.type == PT_INTEGRATOR_AO;  // paths live on as occlusion rays: the shadow queue counts as in flight
   WaveTotals T;
   std::vector<WaveSeg> segs(nseg);
   std::vector<int> seg_of_job(jobs.size(), -1);
   size_t next_job = 0, next_film = 0;
-  int iter = 0, last_start = -(1 << 30), wave_iters = s->h.integrator.max_depth + 3;
+  int iter = 0, last_start = -(1 << 30), wave_iters = is_ao ? s->h.integrator.ao_samples + 2 : s->h.integrator.max_depth + 3;
   int rc = 0;
   // The host never waits for the bounce it has just queued.  Queue sizes stay on the device: k_raygen appends the
   // camera rays behind the continuation rays of the last shade stage, k_trace reads the three queue sizes, k_shade its
@@ -886,8 +896,8 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     T.shadow += c[2];
     T.trace_rays += c[1] + c[2] + c[3];
     for (uint32_t k = 0; k < nseg; k++)
-      if (segs[k].state == WaveSeg::ACTIVE && segs[k].start_iter <= pend.iter && (nseg > 1 ? c[16 + k] : c[1]) == 0) segs[k].state = WaveSeg::TRACED;
-    e_last = c[1] + n_new_after;
+      if (segs[k].state == WaveSeg::ACTIVE && segs[k].start_iter <= pend.iter && (nseg > 1 ? c[16 + k] : c[1] + (is_ao ? c[2] : 0u)) == 0) segs[k].state = WaveSeg::TRACED;
+    e_last = c[1] + (is_ao ? c[2] : 0u) + n_new_after;
     pend.any = false;
     return gather_ready();
   };
@@ -961,12 +971,22 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     T.trace_rays += n_new;
     T.launches++;
     T.trace_launches++;
+    if (is_ao) cudaMemcpyAsync(Q.counts + 24, Q.counts + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->stream);  // k_ao's input list sizes
     cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream);  // queue counters + the trace fetch counter
     if ((rc = (cudaMemsetAsync(Q.counts + 16, 0, PT_MAX_SEGMENTS * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }
     if (is_aov) {  // aov.rs: no bounces, nothing is pushed: only the camera rays of this iteration are in the queue
       if (n_new > 0) {
         PT_LAUNCH(grid_for(s, n_new, 128, 8), 128, s->stream, k_aov<NC>)(s->h, W, Q.ext, n_new);
         if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_aov launch failed"); break; }
+        T.launches++;
+      }
+    } else if (is_ao) {  // ao.rs: every path in flight makes its next occlusion ray
+      if constexpr (NC == 3) {
+        Queues Qo = Q;
+        Qo.shadow = Q.mis;  // the queue this round fills; the one just traced is its input list
+        PT_LAUNCH(grid_for(s, (size_t)ub_ext + ub_side, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_ao<NC>)(s->h, W, Qo, Q.shadow, n_new, 0u, Q.counts + 24);
+        if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_ao launch failed"); break; }
+        std::swap(Q.shadow, Q.mis);
         T.launches++;
       }
     } else if (ub_ext > 0) {

@@ -301,7 +301,8 @@ PT_HD void push_next(const WaveState& W, Queues& Q, uint32_t i) {
 
 // the appends of one shaded vertex to the shadow, MIS and next extend queues, warp-aggregated, the three atomics in flight
 // together (one round trip)
-PT_HD void push_rays(const WaveState& W, Queues& Q, uint32_t i, bool sh, bool mis, bool ext) {
+// count_sh: shadow rays keep a wave alive as well (ambientocclusion: a path is nothing but its current occlusion ray)
+PT_HD void push_rays(const WaveState& W, Queues& Q, uint32_t i, bool sh, bool mis, bool ext, bool count_sh = false) {
 #if defined(__CUDA_ARCH__)
   const unsigned m = __activemask();
   const unsigned bs = __ballot_sync(m, sh), bm = __ballot_sync(m, mis), be = __ballot_sync(m, ext);
@@ -318,18 +319,18 @@ PT_HD void push_rays(const WaveState& W, Queues& Q, uint32_t i, bool sh, bool mi
   const unsigned lt = (1u << lane) - 1u;
   if (sh) Q.shadow[b0 + (uint32_t)__popc(bs & lt)] = i;
   if (mis) Q.mis[b1 + (uint32_t)__popc(bm & lt)] = i;
-  if (ext) {
-    Q.ext_next[b2 + (uint32_t)__popc(be & lt)] = i;
-    if (W.nseg > 1) {  // continuation rays per wave in flight (the host retires a wave that pushed none)
-      const uint32_t seg = i / W.seg_cap;
-      const unsigned peers = __match_any_sync(be, seg);
-      if (lane == __ffs(peers) - 1) atomicAdd(&Q.counts[16 + seg], (uint32_t)__popc(peers));
-    }
+  if (ext) Q.ext_next[b2 + (uint32_t)__popc(be & lt)] = i;
+  const bool alive = ext || (count_sh && sh);
+  if (alive && W.nseg > 1) {  // rays per wave in flight that keep it alive (the host retires a wave that pushed none)
+    const uint32_t seg = i / W.seg_cap;
+    const unsigned peers = __match_any_sync(count_sh ? (be | bs) : be, seg);
+    if (lane == __ffs(peers) - 1) atomicAdd(&Q.counts[16 + seg], (uint32_t)__popc(peers));
   }
 #else
   if (sh) Q.shadow[Q.counts[2]++] = i;
   if (mis) Q.mis[Q.counts[3]++] = i;
   if (ext) push_next(W, Q, i);
+  else if (count_sh && sh && W.nseg > 1) Q.counts[16 + i / W.seg_cap]++;
 #endif
 }
 
@@ -360,6 +361,7 @@ PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int
   st_store<NC>(W.L, W.cap, i, sp_const<NC>(0.0f));
   st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(0.0f));
   st_store<NC>(W.pendB, W.cap, i, sp_const<NC>(0.0f));
+  if (S.integrator.type == PT_INTEGRATOR_AO) W.mis_light[i] = n;  // the sample number selects the slice of the sample array (ao_body)
   Q.ext[qpos == 0xffffffffu ? i : qpos] = i;
 }
 
@@ -574,6 +576,57 @@ PT_HD void aov_body(const DScene& S, WaveState& W, uint32_t i) {
     out.c[NC > 2 ? 2 : 0] = clampf(b, 0.0f, 1.0f) * sc;
   }
   st_store<NC>(W.L, W.cap, i, out);
+}
+
+// AOIntegrator::li (integrators/ao.rs:50-105) as a per-path state machine: flags >> 8 = number of occlusion rays made so
+// far.  Round 0 (after the camera ray's closest-hit query): a miss ends the path, a surface without a material lets the
+// ray through (ao.rs:68-71), anything else makes occlusion ray 0.  Round r > 0 (after occlusion ray r - 1 was traced: the
+// trace stage has cleared pendA if it was occluded): l += pendA, then occlusion ray r; the last ray's term is folded in by
+// k_finish, in the same order.  Element r of get_2d_array(n) for sample number s of the pixel is dimensions (5, 6) of the
+// index of sample NUMBER n * s + r (GlobalSampler::start_pixel, halton.rs:193-207, base_sampler.rs:59-70).
+// `Q.shadow` is the queue being filled (the one the last trace stage read is the caller's input list).  RGB only.
+template <int NC>
+PT_HD void ao_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i) {
+  const int ns = S.integrator.ao_samples;
+  const int round = (int)(W.flags[i] >> 8);
+  f4 ro4 = W.ray_o[i], rd4 = W.ray_d[i], h4 = W.hit[i];
+  const int tri = (int)fbits(h4.w);
+  bool push_sh = false, push_ext = false;
+  if (tri >= 0 && round < ns) {
+    f3 ro = xyz(ro4), rd = xyz(rd4);
+    const int inst = S.has_instances ? W.hit_inst[i] : -1;
+    SurfD si = make_surface(S, tri, inst, ro, rd, rd4.w, h4.x, h4.y, h4.z);
+    if (round == 0 && ldg(S.tri_material + tri) < 0) {
+      f3 o = offset_origin(si.p, si.perr, si.n, rd);
+      W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+      push_ext = true;
+    } else {
+      if (round > 0) {
+        Sp<NC> L = st_load<NC>(W.L, W.cap, i);
+        L = L + st_load<NC>(W.pendA, W.cap, i);
+        st_store<NC>(W.L, W.cap, i, L);
+      }
+      f3 n = faceforward(si.n, -rd);
+      f3 s = norm3(si.dpdu);
+      f3 t = cross3(si.n, s);
+      const int pk = W.pix[i];
+      const int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
+      const int64_t idx = sampler_index(S, px, py, (int64_t)ns * (int64_t)W.mis_light[i] + (int64_t)round);
+      f2 u = mk2(sampler_dim(S, idx, 5u, px, py), sampler_dim(S, idx, 6u, px, py));
+      f3 wl;
+      float pdf;
+      if (S.integrator.ao_cos_sample) { wl = cosine_hemisphere(u); pdf = fabsf(wl.z) * PT_INV_PI; }
+      else { wl = uniform_hemisphere(u); pdf = PT_INV_PI * 0.5f; }
+      f3 wi = mk3(wl.x * s.x + wl.y * t.x + wl.z * n.x, wl.x * s.y + wl.y * t.y + wl.z * n.y, wl.x * s.z + wl.y * t.z + wl.z * n.z);
+      st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(dot3(wi, n) / (pdf * (float)ns)));
+      f3 o = offset_origin(si.p, si.perr, si.n, wi);
+      W.sh_o[i] = mk4(o.x, o.y, o.z, 0.0f);
+      W.sh_d[i] = mk4(wi.x, wi.y, wi.z, pt_inf());
+      W.flags[i] = (uint32_t)(round + 1) << 8;
+      push_sh = true;
+    }
+  }
+  push_rays(W, Q, i, push_sh, false, push_ext, true);
 }
 
 // MIS ray resolution: the BSDF-sampled ray contributes only if it hits the sampled light (pointer equality in the

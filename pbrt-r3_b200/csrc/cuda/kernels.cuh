@@ -356,6 +356,19 @@ __global__ void k_aov(const __grid_constant__ DScene S, WaveState W, const uint3
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) aov_body<NC>(S, W, ids[k]);
 }
 
+// Integrator "ambientocclusion": one round of every path in flight (ao_body).  The paths are those whose camera /
+// pass-through ray the last k_trace answered (Q.ext[0..n_ext)) and those whose occlusion ray it answered (sh_in[0..n_sh));
+// Q.shadow is the queue this round fills.  prev = {n_ext, n_sh} as the last shade stage left them on the device (the host
+// does not wait for them, render_waves), n_ext then only holds the camera rays appended since.
+template <int NC>
+__global__ void __launch_bounds__(PT_SHADE_BLOCK) k_ao(const __grid_constant__ DScene S, WaveState W, Queues Q, const uint32_t* __restrict__ sh_in, uint32_t n_ext, uint32_t n_sh,
+                                                       const uint32_t* prev) {
+  if (prev) { n_ext += prev[0]; n_sh = prev[1]; }
+  const uint32_t total = n_ext + n_sh;
+  // whole warps run the loop body: the queue appends are warp-aggregated over the active mask
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) ao_body<NC>(S, W, Q, k < n_ext ? Q.ext[k] : sh_in[k - n_ext]);
+}
+
 template <int NC>
 __global__ void k_finish(const __grid_constant__ DScene S, WaveState W, uint32_t base, uint32_t n) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) finish_body<NC>(S, W, base + i);

@@ -925,10 +925,19 @@ struct Builder {
     if (pt_current_options().quick_render && S.type != PT_SAMPLER_RANDOM) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
 
     // Integrator (integrators/path.rs:252-271)
-    if (integrator_name != "path" && integrator_name != "aov")
-      throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path, aov)");
+    if (integrator_name != "path" && integrator_name != "aov" && integrator_name != "ambientocclusion")
+      throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path, aov, ambientocclusion)");
     pt_integrator& I = D.integrator;
     I.type = PT_INTEGRATOR_PATH;
+    if (integrator_name == "ambientocclusion") {  // integrators/ao.rs:119-138
+      I.type = PT_INTEGRATOR_AO;
+      I.ao_cos_sample = integrator_params.one_bool("cossample", true) ? 1 : 0;
+      I.ao_samples = integrator_params.one_int("nsamples", 64);
+      if (pt_current_options().quick_render) I.ao_samples = 1;
+      if (I.ao_samples < 1) throw ParseError("Integrator \"ambientocclusion\": nsamples must be positive");
+      if (S.type == PT_SAMPLER_RANDOM) throw ParseError("Integrator \"ambientocclusion\" with Sampler \"random\" is not supported on the GPU path (halton, sobol)");
+      if (spec.n_channels() != 3) throw ParseError("Integrator \"ambientocclusion\" is only supported with RGB spectra");
+    }
     if (integrator_name == "aov") {  // integrators/aov.rs:192-213, targets :36-58
       I.type = PT_INTEGRATOR_AOV;
       std::string t = integrator_params.one_string("target", "uv");

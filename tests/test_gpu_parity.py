@@ -191,6 +191,14 @@ def test_aov_integrator(P, pair, target):
         assert st["shadow_rays"] == 0 and st["regular_rays"] == st["camera_rays"]
 
 
+def test_ao_integrator(P):
+    """Integrator "ambientocclusion" (integrators/ao.rs): per-sample values bit for bit vs the oracle (cosine and uniform
+    hemisphere, halton and sobol sample arrays, instances, a surface without a material), image, ray / visit counters, and
+    the pipelined waves against one wave at a time."""
+    from test_hostcheck import check_ao
+    check_ao(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
+
+
 def test_one_sided_triangles_bit_exact(P, pair):
     """Back-face culling of one-sided meshes (triangle.rs:236-246), with and without ReverseOrientation."""
     from test_hostcheck import one_sided_scene

@@ -172,6 +172,22 @@ def test_front_end_constant_foldable_textures(P):
         P.HostScene.parse_string(txt.replace('"spectrum" "scale"', '"spectrum" "imagemap"'))
 
 
+def test_front_end_ao_integrator(P):
+    base = 'Camera "perspective"\n%sIntegrator "ambientocclusion" %s\nWorldBegin\nWorldEnd\n'
+    d = P.HostScene.parse_string(base % ("", "")).desc.integrator
+    assert (d.type, d.ao_samples, d.ao_cos_sample) == (P.capi.PT_INTEGRATOR_AO, 64, 1)                      # ao.rs:124-125 defaults
+    d = P.HostScene.parse_string(base % ("", '"integer nsamples" [7] "bool cossample" ["false"]')).desc.integrator
+    assert (d.ao_samples, d.ao_cos_sample) == (7, 0)
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % ('Sampler "random"\n', ""))
+    lib = P.capi.load()
+    lib.pt_set_options(P.capi.pt_options(1, 0))
+    try:
+        assert P.HostScene.parse_string(base % ("", '"integer nsamples" [7]')).desc.integrator.ao_samples == 1  # ao.rs:128-130
+    finally:
+        lib.pt_set_options(P.capi.pt_options(0, 0))
+
+
 def test_front_end_aov_integrator(P):
     base = 'Camera "perspective"\nIntegrator "aov" %s\nWorldBegin\nWorldEnd\n'
     d = P.HostScene.parse_string(base % "").desc.integrator

@@ -228,6 +228,57 @@ def test_hostcheck_aov_integrator(HC, target):
             assert st[k] == so[k], k
 
 
+def ao_scene(P, nsamples=8, cos=True, res=24, spp=2, instanced=False, sampler="halton"):
+    """Integrator "ambientocclusion" on the tangent scene (meshes with N / S: the AO frame is the TRUE geometry's, not the
+    shading frame) whose short block has no material (the camera ray passes through, ao.rs:68-71), or on instances."""
+    if instanced:
+        txt = P.scenes.instanced_blobs(n_instances=20, n_sub=1, res=(res, res * 2 // 3), spp=spp, n_lights=2, sampler=sampler)
+    else:
+        txt = tangent_scene(P, res=res, spp=spp).replace('Sampler "halton"', 'Sampler "%s"' % sampler)
+        shapes = [l for l in txt.split("\n") if l.startswith("Shape")]
+        white = 'Material "matte" "rgb Kd" [0.725 0.71 0.68]\n'
+        assert white + shapes[5] in txt
+        txt = txt.replace(white + shapes[5], 'Material "none"\n' + shapes[5])
+    assert 'Integrator "path"' in txt and 'Sampler "%s"' % sampler in txt
+    head, rest = txt.split('Integrator "path"', 1)
+    return head + 'Integrator "ambientocclusion" "integer nsamples" [%d] "bool cossample" ["%s"]' % (nsamples, "true" if cos else "false") + rest[rest.index("\n"):]
+
+
+def check_ao(P, n=1200, res=24, spp=2, wave_paths=300, threads=2):
+    """per-sample values bit for bit vs the oracle (sin / cos are glibc-exact on the device), image, ray and visit counters;
+    the wave pipelining is invisible"""
+    import oracle_api
+    for kw in (dict(), dict(cos=False, nsamples=5), dict(instanced=True, nsamples=3), dict(sampler="sobol", nsamples=4, spp=3)):
+        kw = dict(dict(res=res, spp=spp), **kw)
+        hs = P.HostScene.parse_string(ao_scene(P, **kw))
+        I = hs.desc.integrator
+        assert (I.type, I.ao_samples, I.ao_cos_sample) == (P.capi.PT_INTEGRATOR_AO, kw.get("nsamples", 8), int(kw.get("cos", True)))
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        sb = hs.desc.film.sample_bounds
+        rng = np.random.RandomState(6)
+        pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+        sn = rng.randint(0, kw["spp"], n).astype(np.int32)
+        la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+        assert np.array_equal(la.view(np.uint32), lb.view(np.uint32)), (kw, np.abs(la - lb).max())
+        assert la.max() > 0 and (la == 0).all(1).any()
+        rgb, st = sc.render(collect_counters=1, wave_paths=wave_paths)
+        ref, so = orc.render(threads=threads)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-6, kw
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested"):
+            assert st[k] == so[k], (kw, k)
+        assert st["shadow_rays"] > 0
+        if not kw.get("instanced"):
+            assert st["regular_rays"] > st["camera_rays"]      # rays that went through the block without a material
+        one, _ = sc.render(wave_paths=wave_paths, wave_segments=1)
+        assert np.array_equal(one, rgb), kw
+
+
+def test_hostcheck_ao_integrator(HC):
+    """Integrator "ambientocclusion" (integrators/ao.rs): the sampler's 2D sample array (dimensions 5-6 of sample NUMBER
+    n * s + i), cosine / uniform hemisphere directions, one any-hit query each."""
+    check_ao(HC)
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
