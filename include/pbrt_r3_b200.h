@@ -99,7 +99,8 @@ typedef struct pt_light {
   int32_t tri;                /* area: triangle index; spot: index into pt_scene_desc.spots; else -1 */
   int32_t two_sided;          /* area: DiffuseAreaLight.two_sided (lights/diffuse.rs:178) */
   float v[3];                 /* point, spot: p_light (world) | distant: w_light (world, normalised) */
-  float pad;
+  int32_t n_samples;          /* Light::get_sample_count: area "nsamples" (default 1, n / 4 under --quick, diffuse.rs:177-185), else 1;
+                                 read by directlighting's "all" strategy only */
 } pt_light;
 
 /* SpotLight extras (lights/spot.rs:5-56): falloff(w) looks at the z component of normalize(world_to_light * w). */
@@ -147,8 +148,16 @@ typedef struct pt_sampler {
 enum pt_integrator_type {
   PT_INTEGRATOR_PATH = 0,     /* integrators/path.rs */
   PT_INTEGRATOR_AOV = 1,      /* integrators/aov.rs: one closest-hit query per camera sample, a geometric quantity as colour */
-  PT_INTEGRATOR_AO = 2        /* integrators/ao.rs ("ambientocclusion"): nsamples any-hit queries per camera sample, directions
+  PT_INTEGRATOR_AO = 2,       /* integrators/ao.rs ("ambientocclusion"): nsamples any-hit queries per camera sample, directions
                                  from the sampler's 2D sample ARRAY (request_2d_array / get_2d_array) */
+  PT_INTEGRATOR_DIRECT = 3,   /* integrators/directlighting.rs: Le + direct lighting (all lights, or one picked uniformly) at every
+                                 vertex of the specular reflection / transmission TREE (SamplerIntegrator::specular_reflect /
+                                 specular_transmit, core/integrator/sampler.rs:37-160), depth < max_depth */
+  PT_INTEGRATOR_WHITTED = 4   /* integrators/whitted.rs: one light sample per light (no MIS, no Le) on the same tree */
+};
+enum pt_direct_strategy {     /* directlighting.rs:7-10, "strategy" parameter (default "all") */
+  PT_DIRECT_ALL = 0,          /* uniform_sample_all_lights: n_samples per light from the sampler's 2D sample arrays */
+  PT_DIRECT_ONE = 1           /* uniform_sample_one_light without a light distribution */
 };
 enum pt_aov_target {          /* integrators/aov.rs:10-58; the targets that need ray differentials are not supported */
   PT_AOV_DISTANCE = 0,        /* "distance": t_max / |d|                       */
@@ -167,6 +176,7 @@ typedef struct pt_integrator { /* integrators/path.rs:252-271, integrators/aov.r
   float aov_scale;
   int32_t ao_samples;         /* ambientocclusion "nsamples" (default 64; 1 under --quick), ao.rs:124-131 */
   int32_t ao_cos_sample;      /* ambientocclusion "cossample" (default true) */
+  int32_t direct_strategy;    /* pt_direct_strategy (directlighting only) */
 } pt_integrator;
 
 typedef struct pt_accel {     /* accelerators/bvh/create_bvh_accelerator.rs:9-28 */

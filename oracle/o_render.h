@@ -58,7 +58,11 @@ struct Scene {
     if (desc->n_lights > 0) distrib.init(desc, world_bound, world_radius);
     scfg = make_sampler_config(desc->sampler.type, desc->sampler.samples_per_pixel, desc->film.sample_bounds, desc->sampler.sample_at_pixel_center != 0);
     if (desc->integrator.type == PT_INTEGRATOR_AO) scfg.n_arrays_2d = 1;  // AOIntegrator::new: request_2d_array(n_samples) (ao.rs:29)
+    if (desc->integrator.type == PT_INTEGRATOR_DIRECT && desc->integrator.direct_strategy == PT_DIRECT_ALL)  // directlighting.rs:57-63
+      scfg.n_arrays_2d = 2u * n_sampled_lights() * (uint32_t)std::max(desc->integrator.max_depth, 0);
   }
+  // scene.lights: the lights that can be sampled (area lights inside object instances only emit when hit; front end)
+  uint32_t n_sampled_lights() const { return d->n_lights; }
   bool intersect(const Ray& r, Hit* h, Counters* c) const {
     if (c) c->regular_rays++;
     return geom.objects[0]->intersect(geom, r, h, c);
@@ -239,6 +243,104 @@ inline Spec<NC> ao_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* c
   return l;
 }
 
+// uniform_sample_all_lights (sample_lights.rs:24-78): n_samples per light from two 2D sample arrays (which hold the SAME
+// values: every 2D array is filled from dimensions (5, 6), halton.rs:195-206), single get_2d pairs once the requested
+// arrays are used up
+template <int NC>
+inline Spec<NC> sample_all_lights(Scene<NC>& sc, const SurfInt& it, const BSDF<NC>& bsdf, Sampler& sampler, Counters* cnt) {
+  Spec<NC> l;
+  for (uint32_t j = 0; j < sc.n_sampled_lights(); j++) {
+    const uint32_t n = (uint32_t)sc.d->lights[j].n_samples;
+    const bool a = sampler.next_2d_array(), b = sampler.next_2d_array();
+    if (a && b) {
+      Spec<NC> ld;
+      for (uint32_t k = 0; k < n; k++) {
+        Vec2 u = sampler.array_2d_elem(n, k);
+        ld = ld + estimate_direct(sc, it, bsdf, u, (int)j, u, cnt);
+      }
+      l = l + ld / (Float)n;
+    } else {
+      Vec2 u_light = sampler.get_2d();
+      Vec2 u_scattering = sampler.get_2d();
+      l = l + estimate_direct(sc, it, bsdf, u_scattering, (int)j, u_light, cnt);
+    }
+  }
+  return l;
+}
+// uniform_sample_one_light without a distribution (sample_lights.rs:80-128)
+template <int NC>
+inline Spec<NC> sample_one_light_uniform(Scene<NC>& sc, const SurfInt& it, const BSDF<NC>& bsdf, Sampler& sampler, Counters* cnt) {
+  const size_t n_lights = sc.n_sampled_lights();
+  if (n_lights == 0) return Spec<NC>();
+  size_t light_num = std::min((size_t)(sampler.get_1d() * (Float)n_lights), n_lights - 1);
+  Float light_pdf = 1.0f / (Float)n_lights;
+  Vec2 u_light = sampler.get_2d();
+  Vec2 u_scattering = sampler.get_2d();
+  return estimate_direct(sc, it, bsdf, u_scattering, (int)light_num, u_light, cnt) / light_pdf;
+}
+
+template <int NC>
+inline Spec<NC> recursive_li(Scene<NC>& sc, const Ray& ray, Sampler& sampler, Counters* cnt, PathTrace* trace, int depth);
+// SamplerIntegrator::specular_reflect / specular_transmit (core/integrator/sampler.rs:37-160) without the differentials
+template <int NC>
+inline Spec<NC> specular_bounce(Scene<NC>& sc, const Ray& ray, const SurfInt& isect, const BSDF<NC>& bsdf, Sampler& sampler, Counters* cnt, int depth, int type) {
+  Vec3 wo = isect.wo;
+  Vec2 u = sampler.get_2d();
+  Spec<NC> f;
+  Vec3 wi;
+  Float pdf;
+  int stype;
+  if (!bsdf.sample_f(wo, u, type | BSDF_SPECULAR, &f, &wi, &pdf, &stype)) return Spec<NC>();
+  Float wi_ns = abs_dot(wi, isect.sn);
+  if (pdf > 0.0f && !f.is_black() && wi_ns != 0.0f) {
+    RefPoint rp; rp.p = isect.p; rp.p_error = isect.p_error; rp.n = isect.n; rp.time = isect.time;
+    return f * recursive_li(sc, spawn_ray(rp, wi), sampler, cnt, nullptr, depth + 1) * (wi_ns / pdf);
+  }
+  return Spec<NC>();
+}
+// DirectLightingIntegrator::li (directlighting.rs:66-125) and WhittedIntegrator::li (whitted.rs:37-98)
+template <int NC>
+inline Spec<NC> recursive_li(Scene<NC>& sc, const Ray& ray, Sampler& sampler, Counters* cnt, PathTrace* trace, int depth) {
+  const pt_scene_desc* d = sc.d;
+  const bool whitted = d->integrator.type == PT_INTEGRATOR_WHITTED;
+  Hit h;
+  if (!sc.intersect(ray, &h, cnt)) return Spec<NC>();  // sum of light.le(ray): zero without infinite lights
+  SurfInt isect = make_si(d, h);
+  if (trace && trace->first_tri == -1) { trace->first_tri = h.tri; trace->first_t = h.t; }
+  BSDF<NC> bsdf;
+  compute_scattering(d, isect, &bsdf, false);
+  if (!bsdf.valid) {
+    if (whitted) return Spec<NC>();  // whitted.rs:84
+    RefPoint rp; rp.p = isect.p; rp.p_error = isect.p_error; rp.n = isect.n; rp.time = isect.time;
+    return recursive_li(sc, spawn_ray(rp, ray.d), sampler, cnt, trace, depth);  // directlighting.rs:108-110
+  }
+  if (cnt) cnt->vertices++;
+  Spec<NC> l;
+  if (whitted) {  // whitted.rs:61-79: one sample of every light, shading normal, no MIS, no emission
+    RefPoint ref; ref.p = isect.p; ref.p_error = isect.p_error; ref.n = isect.n; ref.time = isect.time;
+    for (uint32_t j = 0; j < sc.n_sampled_lights(); j++) {
+      Vec2 u = sampler.get_2d();
+      LightSample<NC> ls;
+      if (!light_sample_li<NC>(d, sc.world_radius, (int)j, ref, u, &ls)) { l = l + Spec<NC>(); continue; }
+      if (ls.pdf <= 0.0f || ls.li.is_black()) { l = l + Spec<NC>(); continue; }
+      Spec<NC> f = bsdf.f(isect.wo, ls.wi, BSDF_ALL);
+      if (!f.is_black() && !sc.intersect_p(ls.shadow, cnt)) l = l + f * ls.li * (abs_dot(ls.wi, isect.sn) / ls.pdf);
+      else l = l + Spec<NC>();
+    }
+  } else {
+    l = surface_le<NC>(d, isect, isect.wo);
+    if (sc.n_sampled_lights() > 0) {
+      if (d->integrator.direct_strategy == PT_DIRECT_ALL) l = l + sample_all_lights(sc, isect, bsdf, sampler, cnt);
+      else l = l + sample_one_light_uniform(sc, isect, bsdf, sampler, cnt);
+    }
+  }
+  if (depth + 1 < d->integrator.max_depth) {
+    l = l + specular_bounce(sc, ray, isect, bsdf, sampler, cnt, depth, BSDF_REFLECTION);
+    l = l + specular_bounce(sc, ray, isect, bsdf, sampler, cnt, depth, BSDF_TRANSMISSION);
+  }
+  return l;
+}
+
 template <int NC>
 inline Spec<NC> path_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace);
 // SamplerIntegrator::li of the scene's integrator
@@ -246,6 +348,7 @@ template <int NC>
 inline Spec<NC> integrator_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* cnt, PathTrace* trace) {
   if (sc.d->integrator.type == PT_INTEGRATOR_AOV) return aov_li(sc, r, cnt, trace);
   if (sc.d->integrator.type == PT_INTEGRATOR_AO) return ao_li(sc, r, sampler, cnt, trace);
+  if (sc.d->integrator.type == PT_INTEGRATOR_DIRECT || sc.d->integrator.type == PT_INTEGRATOR_WHITTED) return recursive_li(sc, r, sampler, cnt, trace, 0);
   return path_li(sc, r, sampler, cnt, trace);
 }
 

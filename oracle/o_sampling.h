@@ -229,6 +229,7 @@ struct Sampler {
   uint32_t dimension;
   RNG rng;              // random sampler: per-tile stream
   int64_t halton_offset;
+  uint32_t array2d_offset = 0;  // get_2d_array calls so far in this sample (base_sampler.rs:59-70)
 
   Sampler(const SamplerConfig* c, uint32_t tile_seed) : cfg(c), px(0), py(0), sample_num(0), interval_index(0), dimension(0), rng((uint64_t)tile_seed), halton_offset(0) {}
 
@@ -238,7 +239,7 @@ struct Sampler {
     return 0;
   }
   void start_pixel(int x, int y) {
-    px = x; py = y; sample_num = 0; dimension = 0;
+    px = x; py = y; sample_num = 0; dimension = 0; array2d_offset = 0;
     if (cfg->type == 0) {   // halton.rs:115-147
       halton_offset = 0;
       int64_t stride = cfg->sample_stride;
@@ -256,7 +257,7 @@ struct Sampler {
     interval_index = index_for_sample(0);
   }
   bool set_sample_number(int64_t n) {
-    sample_num = n; dimension = 0;
+    sample_num = n; dimension = 0; array2d_offset = 0;
     interval_index = index_for_sample(n);
     return n < cfg->spp;
   }
@@ -286,6 +287,12 @@ struct Sampler {
   // element i of get_2d_array(n) for the current sample: start_pixel fills array[j] from the index of sample NUMBER j,
   // j < n * spp, and get_2d_array hands out [n * s, n * (s + 1)) (halton.rs:193-207, base_sampler.rs:59-70).  Every 2D array
   // reads the same two dimensions (`dim` is not advanced per array in the reference).
+  // get_2d_array: None once every requested array has been handed out (base_sampler.rs:63-65)
+  bool next_2d_array() {
+    if (array2d_offset == cfg->n_arrays_2d) return false;
+    array2d_offset++;
+    return true;
+  }
   Vec2 array_2d_elem(uint32_t n, uint32_t i) const {
     int64_t index = index_for_sample((int64_t)n * sample_num + (int64_t)i);
     uint32_t dim = 5u + cfg->n_arrays_1d;

@@ -608,7 +608,7 @@ struct BSDF {
 
 // ---- Materials (materials/*.rs compute_scattering_functions; constant textures) -----------------------------
 template <int NC>
-inline void compute_scattering(const pt_scene_desc* d, const SurfInt& si, BSDF<NC>* bsdf) {
+inline void compute_scattering(const pt_scene_desc* d, const SurfInt& si, BSDF<NC>* bsdf, bool allow_multiple_lobes = true) {
   bsdf->valid = false;
   int mi = d->tri_material[si.tri];
   if (mi < 0) return;
@@ -663,8 +663,15 @@ inline void compute_scattering(const pt_scene_desc* d, const SurfInt& si, BSDF<N
       if (r.is_black() && t.is_black()) return;
       bsdf->init(si, eta);
       bool is_spec = ur == 0.0f && vr == 0.0f;
-      if (is_spec) {  // allow_multiple_lobes = true in PathIntegrator (path.rs:106)
+      if (is_spec && allow_multiple_lobes) {  // allow_multiple_lobes = true in PathIntegrator (path.rs:106)
         BxDF<NC> b; b.kind = BX_FRESNEL_SPEC; b.r = r; b.t = t; b.eta_a = 1.0f; b.eta_b = eta; bsdf->add(b);
+      } else if (is_spec) {  // glass.rs:80-99 (directlighting / whitted): SpecularReflection + SpecularTransmission
+        if (!r.is_black()) {
+          BxDF<NC> b; b.kind = BX_SPEC_REFL; b.r = r;
+          b.fresnel.kind = FR_DIELECTRIC; b.fresnel.eta_i = 1.0f; b.fresnel.eta_t = eta;
+          bsdf->add(b);
+        }
+        if (!t.is_black()) { BxDF<NC> b; b.kind = BX_SPEC_TRANS; b.t = t; b.eta_a = 1.0f; b.eta_b = eta; bsdf->add(b); }
       } else {
         if (M.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
         if (!r.is_black()) {

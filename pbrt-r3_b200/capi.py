@@ -15,7 +15,8 @@ PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MI
 PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT = 0, 1, 2, 3
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
-PT_INTEGRATOR_PATH, PT_INTEGRATOR_AOV, PT_INTEGRATOR_AO = 0, 1, 2
+PT_INTEGRATOR_PATH, PT_INTEGRATOR_AOV, PT_INTEGRATOR_AO, PT_INTEGRATOR_DIRECT, PT_INTEGRATOR_WHITTED = 0, 1, 2, 3, 4
+PT_DIRECT_ALL, PT_DIRECT_ONE = 0, 1
 PT_AOV_DISTANCE, PT_AOV_DEPTH, PT_AOV_N, PT_AOV_NS, PT_AOV_UV, PT_AOV_DPDUS = 0, 1, 2, 3, 4, 5
 PT_SPECTRUM_RGB, PT_SPECTRUM_SAMPLED = 0, 1
 PT_TRI_REVERSE_ORIENTATION, PT_TRI_SWAPS_HANDEDNESS, PT_TRI_TWO_SIDED, PT_TRI_HAS_N, PT_TRI_HAS_UV, PT_TRI_HAS_S = 1, 2, 4, 8, 16, 32
@@ -32,7 +33,7 @@ class pt_material(C.Structure):
 
 class pt_light(C.Structure):
     _fields_ = [("type", C.c_int32), ("spectrum", C.c_int32), ("tri", C.c_int32), ("two_sided", C.c_int32),
-                ("v", C.c_float * 3), ("pad", C.c_float)]
+                ("v", C.c_float * 3), ("n_samples", C.c_int32)]
 
 
 class pt_spot(C.Structure):
@@ -60,7 +61,7 @@ class pt_sampler(C.Structure):
 
 class pt_integrator(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("rr_threshold", C.c_float), ("light_strategy", C.c_int32), ("type", C.c_int32),
-                ("aov_target", C.c_int32), ("aov_scale", C.c_float), ("ao_samples", C.c_int32), ("ao_cos_sample", C.c_int32)]
+                ("aov_target", C.c_int32), ("aov_scale", C.c_float), ("ao_samples", C.c_int32), ("ao_cos_sample", C.c_int32), ("direct_strategy", C.c_int32)]
 
 
 class pt_accel(C.Structure):

@@ -221,7 +221,10 @@ PT_HD f3 tr_sample_wh(TR D, f3 wo, f2 u) {
 }
 
 // ---- lobes --------------------------------------------------------------------------------------------------
-enum { LB_LAMBERT = 0, LB_OREN = 1, LB_MIRROR = 2, LB_FRESNEL_SPEC = 3, LB_MF_REFL = 4, LB_MF_TRANS = 5 };
+enum { LB_LAMBERT = 0, LB_OREN = 1, LB_MIRROR = 2, LB_FRESNEL_SPEC = 3, LB_MF_REFL = 4, LB_MF_TRANS = 5,
+       // smooth glass without allow_multiple_lobes (directlighting / whitted; glass.rs:80-99): SpecularReflection with a
+       // dielectric Fresnel term and SpecularTransmission (specular.rs) as two lobes
+       LB_SPEC_REFL_D = 6, LB_SPEC_TRANS = 7 };
 enum { F_REFL = 1, F_TRANS = 2, F_DIFF = 4, F_GLOSSY = 8, F_SPEC = 16, F_ALL = 31 };
 enum { FR_NOOP = 0, FR_DIEL = 1, FR_COND = 2 };
 
@@ -234,7 +237,7 @@ struct Lobe {
 };
 // Compile-time lobe sets: a shade kernel specialised for one material class only keeps the code of the lobes and
 // Fresnel terms that class can produce (bits 0-5: LB_* kinds, bits 8-10: FR_* kinds).
-#define PT_CM_ANY 0x73f
+#define PT_CM_ANY 0x7ff
 #define PT_CM_MATTE 0x103
 #define PT_CM_PLASTIC 0x311
 #define PT_CM_MIRROR 0x104
@@ -254,6 +257,8 @@ PT_HD int lobe_type(int kind) {
     case LB_MIRROR: return F_REFL | F_SPEC;
     case LB_FRESNEL_SPEC: return F_REFL | F_TRANS | F_SPEC;
     case LB_MF_REFL: return F_REFL | F_GLOSSY;
+    case LB_SPEC_REFL_D: return F_REFL | F_SPEC;
+    case LB_SPEC_TRANS: return F_TRANS | F_SPEC;
     default: return F_TRANS | F_GLOSSY;
   }
 }
@@ -417,6 +422,25 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe L, f3 wo, f2 u, Sp<NC>* f, f
       ft = ft * ((ei * ei) / (et * et));
       *stype = F_SPEC | F_TRANS;
       *pdf = 1.0f - F;
+      *f = ft / acth(wi);
+      *wi_out = wi;
+      return true;
+    }
+    PT_KIND(LB_SPEC_REFL_D) {  // SpecularReflection::sample_f (specular.rs) with FresnelDielectric(ei, et)
+      f3 wi = mk3(-wo.x, -wo.y, wo.z);
+      *pdf = 1.0f;
+      *f = (sp_const<NC>(fr_diel(cth(wi), L.ei, L.et)) * sp_load<NC>(S.spectra + (size_t)L.sp0 * NC)) / acth(wi);
+      *wi_out = wi;
+      return true;
+    }
+    PT_KIND(LB_SPEC_TRANS) {  // SpecularTransmission::sample_f (specular.rs:78-107), TransportMode::Radiance
+      bool entering = cth(wo) > 0.0f;
+      float ei = entering ? L.ei : L.et, et = entering ? L.et : L.ei;
+      f3 wi;
+      if (!refract3(wo, faceforward(mk3(0.0f, 0.0f, 1.0f), wo), ei / et, &wi)) return false;
+      *pdf = 1.0f;
+      Sp<NC> ft = sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * (sp_const<NC>(1.0f) - sp_const<NC>(fr_diel(cth(wi), L.ei, L.et)));
+      ft = ft * ((ei * ei) / (et * et));
       *f = ft / acth(wi);
       *wi_out = wi;
       return true;
@@ -628,7 +652,8 @@ PT_HD void bsdf_add(BsdfD* B, int& n, const Lobe& L) {
   else B->lobe[1] = L;
   n++;
 }
-template <int NC, int MT = -1>
+// MULTI = allow_multiple_lobes (true: PathIntegrator, path.rs:106; false: directlighting / whitted)
+template <int NC, int MT = -1, bool MULTI = true>
 PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   B->n = -1;
   int mi = ldg(S.tri_material + si.tri);
@@ -686,9 +711,22 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
       if (rb && tb) return;  // no BSDF at all
       eta = M.eta;
       if (M.uroughness == 0.0f && M.vroughness == 0.0f) {
-        Lobe L;
-        L.kind = LB_FRESNEL_SPEC; L.sp0 = M.kr; L.sp1 = M.ks; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = 1.0f; L.et = eta;
-        bsdf_add(B, n, L);
+        if (MULTI) {
+          Lobe L;
+          L.kind = LB_FRESNEL_SPEC; L.sp0 = M.kr; L.sp1 = M.ks; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = 1.0f; L.et = eta;
+          bsdf_add(B, n, L);
+        } else {
+          if (!rb) {
+            Lobe L;
+            L.kind = LB_SPEC_REFL_D; L.sp0 = M.kr; L.sp1 = -1; L.fres = FR_DIEL; L.a = L.b = 0.0f; L.ei = 1.0f; L.et = eta;
+            bsdf_add(B, n, L);
+          }
+          if (!tb) {
+            Lobe L;
+            L.kind = LB_SPEC_TRANS; L.sp0 = M.ks; L.sp1 = -1; L.fres = FR_NOOP; L.a = L.b = 0.0f; L.ei = 1.0f; L.et = eta;
+            bsdf_add(B, n, L);
+          }
+        }
       } else {
         float ax = fmaxf(0.001f, ldg(S.alpha + 2 * mi)), ay = fmaxf(0.001f, ldg(S.alpha + 2 * mi + 1));
         if (!rb) {

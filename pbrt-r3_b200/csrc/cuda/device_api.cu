@@ -392,6 +392,14 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(s->bufs.upload(alpha.data(), alpha.size(), &H.alpha));
   CK(s->bufs.upload(D->lights, (size_t)D->n_lights + D->n_emitters_only, &H.lights));
   CK(s->bufs.upload(D->spots, D->n_spots, &H.spots));
+  H.light_sample_prefix = nullptr;
+  if (D->integrator.type == PT_INTEGRATOR_DIRECT || D->integrator.type == PT_INTEGRATOR_WHITTED) {
+    if (D->integrator.max_depth > PT_RI_MAX_DEPTH) { pt_set_error("directlighting / whitted: maxdepth above 32 is not supported on the GPU path"); return 1; }
+    std::vector<uint32_t> prefix(D->n_lights + 1, 0u);  // directlighting "all": lighting round -> (light, sample)
+    for (uint32_t i = 0; i < D->n_lights; i++) prefix[i + 1] = prefix[i] + (uint32_t)std::max(D->lights[i].n_samples, 1);
+    if (prefix[D->n_lights] > 0x7fffu) { pt_set_error("directlighting: more than 32767 light samples per vertex"); return 1; }
+    CK(s->bufs.upload(prefix.data(), prefix.size(), &H.light_sample_prefix));
+  }
   for (uint32_t i = 0; i < D->n_lights; i++)
     if (D->lights[i].type == PT_LIGHT_SPOT && (D->lights[i].tri < 0 || (uint32_t)D->lights[i].tri >= D->n_spots)) { pt_set_error("spot light index out of range"); return 1; }
 
@@ -476,7 +484,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   memset(&LD, 0, sizeof(LD));
   int strat = D->integrator.light_strategy;
   if (strat == PT_LIGHTS_UNIFORM && D->n_lights != 1) strat = PT_LIGHTS_SPATIAL;
-  if (D->integrator.type == PT_INTEGRATOR_AOV || D->integrator.type == PT_INTEGRATOR_AO) strat = PT_LIGHTS_UNIFORM;  // these integrators never sample a light: no table to build
+  if (D->integrator.type != PT_INTEGRATOR_PATH) strat = PT_LIGHTS_UNIFORM;  // only the path integrator reads a light distribution: no table to build
   LD.strategy = strat;
   for (int a = 0; a < 3; a++) { LD.wb_min[a] = wb.mn[a]; LD.wb_max[a] = wb.mx[a]; LD.voxels[a] = 1; }
   uint32_t n_vox = 1;
@@ -599,6 +607,19 @@ int ensure_wave(pt_scene* s, uint32_t seg_cap, uint32_t nseg = 1) {
   CK(B.alloc(cap, &Q.ext)); CK(B.alloc(cap, &Q.ext_next)); CK(B.alloc(cap, &Q.shadow)); CK(B.alloc(cap, &Q.mis)); CK(B.alloc(32, &Q.counts));
   CK(cudaMemset(Q.counts, 0, 32 * sizeof(uint32_t)));
   CK(B.alloc((size_t)cap * CL_COUNT, &Q.bins));
+  const int itype = s->h.integrator.type;
+  const bool tree = itype == PT_INTEGRATOR_DIRECT || itype == PT_INTEGRATOR_WHITTED;
+  W.sample_num = nullptr; W.arr_off = nullptr;
+  W.n_frames = 0; W.fr_ro = W.fr_rd = W.fr_hit = W.fr_beta = nullptr; W.fr_inst = nullptr;
+  Q.wait = Q.wait_next = nullptr;
+  if (itype == PT_INTEGRATOR_AO || tree) { CK(B.alloc(cap, &W.sample_num)); CK(B.alloc(cap, &W.arr_off)); }
+  if (tree) {  // the pending specular_transmit branches: one frame per depth below max_depth - 1 (ri_body)
+    W.n_frames = (uint32_t)std::max(s->h.integrator.max_depth - 1, 1);
+    const size_t nf = (size_t)cap * W.n_frames;
+    CK(B.alloc(nf, &W.fr_ro)); CK(B.alloc(nf, &W.fr_rd)); CK(B.alloc(nf, &W.fr_hit)); CK(B.alloc(nf, &W.fr_beta));
+    if (s->h.has_instances) CK(B.alloc(nf, &W.fr_inst));
+    CK(B.alloc(cap, &Q.wait)); CK(B.alloc(cap, &Q.wait_next));
+  }
   s->wave_cap = cap;
   return 0;
 }
@@ -638,11 +659,12 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
   Queues Q = s->Q;
   WaveState& W = s->W;
   uint32_t counts[4] = {n, 0, 0, 0};
+  uint32_t n_wait = 0;  // directlighting / whitted: paths between two lighting rounds (no ray of their own to extend)
   cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
   if (timed) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
   const bool inst = s->h.has_instances != 0;
   int guard = 0;
-  while (counts[0] + counts[2] + counts[3] > 0) {
+  while (counts[0] + counts[2] + counts[3] + n_wait > 0) {
     if (++guard > 100000) { pt_set_error("bounce loop did not terminate"); return 1; }
     uint32_t total = counts[0] + counts[3] + counts[2];
     int g = grid_for(s, total, PT_TRACE_BLOCK, 8);
@@ -679,6 +701,14 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
         std::swap(Q.shadow, Q.mis);
         T->launches++;
       }
+    } else if (s->h.integrator.type == PT_INTEGRATOR_DIRECT || s->h.integrator.type == PT_INTEGRATOR_WHITTED) {
+      if constexpr (NC == 3) {  // one step of the specular-tree walk of every path in flight
+        PT_LAUNCH(grid_for(s, (size_t)counts[0] + n_wait, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_ri<NC>)(s->h, W, Q, Q.wait, counts[0], n_wait, nullptr,
+                                                                                                                                count ? s->counters + 2 : nullptr);
+        CK(cudaGetLastError());
+        std::swap(Q.wait, Q.wait_next);
+        T->launches++;
+      }
     } else if (n_ext > 0) {
       int gs = grid_for(s, n_ext, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
       unsigned long long* vc = count ? s->counters + 2 : nullptr;
@@ -687,8 +717,11 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
       CK(cudaGetLastError());
     }
     if (timed) cudaEventRecord(e2, s->stream);
-    CK(cudaMemcpyAsync(counts, Q.counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    uint32_t c8[8];
+    CK(cudaMemcpyAsync(c8, Q.counts, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    for (int k = 0; k < 4; k++) counts[k] = c8[k];
+    n_wait = c8[5];
     if (timed) {
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, e0, e1);
@@ -843,6 +876,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   const bool inst = s->h.has_instances != 0;
   const bool is_aov = s->h.integrator.type == PT_INTEGRATOR_AOV;
   const bool is_ao = s->h.integrator.type == PT_INTEGRATOR_AO;  // paths live on as occlusion rays: the shadow queue counts as in flight
+  const bool is_ri = s->h.integrator.type == PT_INTEGRATOR_DIRECT || s->h.integrator.type == PT_INTEGRATOR_WHITTED;  // ... or on the wait list
   WaveTotals T;
   std::vector<WaveSeg> segs(nseg);
   std::vector<int> seg_of_job(jobs.size(), -1);
@@ -896,8 +930,8 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     T.shadow += c[2];
     T.trace_rays += c[1] + c[2] + c[3];
     for (uint32_t k = 0; k < nseg; k++)
-      if (segs[k].state == WaveSeg::ACTIVE && segs[k].start_iter <= pend.iter && (nseg > 1 ? c[16 + k] : c[1] + (is_ao ? c[2] : 0u)) == 0) segs[k].state = WaveSeg::TRACED;
-    e_last = c[1] + (is_ao ? c[2] : 0u) + n_new_after;
+      if (segs[k].state == WaveSeg::ACTIVE && segs[k].start_iter <= pend.iter && (nseg > 1 ? c[16 + k] : c[1] + (is_ao ? c[2] : 0u) + (is_ri ? c[5] : 0u)) == 0) segs[k].state = WaveSeg::TRACED;
+    e_last = c[1] + (is_ao ? c[2] : 0u) + (is_ri ? c[5] : 0u) + n_new_after;
     pend.any = false;
     return gather_ready();
   };
@@ -971,7 +1005,7 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
     T.trace_rays += n_new;
     T.launches++;
     T.trace_launches++;
-    if (is_ao) cudaMemcpyAsync(Q.counts + 24, Q.counts + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->stream);  // k_ao's input list sizes
+    if (is_ao || is_ri) cudaMemcpyAsync(Q.counts + 24, Q.counts + 1, 5 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s->stream);  // k_ao's / k_ri's input list sizes
     cudaMemsetAsync(Q.counts, 0, 8 * sizeof(uint32_t), s->stream);  // queue counters + the trace fetch counter
     if ((rc = (cudaMemsetAsync(Q.counts + 16, 0, PT_MAX_SEGMENTS * sizeof(uint32_t), s->stream) != cudaSuccess))) { pt_set_error("cudaMemsetAsync failed"); break; }
     if (is_aov) {  // aov.rs: no bounces, nothing is pushed: only the camera rays of this iteration are in the queue
@@ -987,6 +1021,14 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
         PT_LAUNCH(grid_for(s, (size_t)ub_ext + ub_side, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_ao<NC>)(s->h, W, Qo, Q.shadow, n_new, 0u, Q.counts + 24);
         if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_ao launch failed"); break; }
         std::swap(Q.shadow, Q.mis);
+        T.launches++;
+      }
+    } else if (is_ri) {  // directlighting / whitted: one step of the specular-tree walk of every path in flight
+      if constexpr (NC == 3) {
+        PT_LAUNCH(grid_for(s, (size_t)ub_ext + ub_side, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_ri<NC>)(s->h, W, Q, Q.wait, n_new, 0u, Q.counts + 24,
+                                                                                                                             count ? s->counters + 2 : nullptr);
+        if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_ri launch failed"); break; }
+        std::swap(Q.wait, Q.wait_next);
         T.launches++;
       }
     } else if (ub_ext > 0) {

@@ -92,6 +92,7 @@ struct DScene {
   const int32_t* tri_light;
   const pt_material* materials;
   const pt_light* lights;
+  const uint32_t* light_sample_prefix;  // [n_lights + 1] prefix sums of pt_light.n_samples (directlighting "all": round -> light, sample)
   const pt_spot* spots;      // SpotLight extras, indexed by pt_light.tri
   const float* spectra;
   const float* alpha;        // per material: roughness_to_alpha applied on the HOST with libm logf: [n_materials][2]

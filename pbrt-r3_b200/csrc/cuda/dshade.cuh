@@ -39,6 +39,14 @@ struct WaveState {            // all arrays have `cap` path slots; spectra are p
   f4* mis_o; f4* mis_d;       // BSDF-sample MIS ray
   float* pendB;               // NC: BSDF-sample term, cleared unless the ray hits the sampled light's emitting side
   int* mis_light;
+  // integrators that read sample arrays or walk the specular tree (ambientocclusion, directlighting, whitted); null otherwise
+  int* sample_num;            // the camera sample's number within its pixel (selects the slice of a sample array)
+  uint32_t* arr_off;          // get_2d_array calls so far in this sample (base_sampler.rs:59-70)
+  // the pending specular_transmit branches of the tree walk, level-major [level * cap + path]: the vertex (ray, hit) to
+  // come back to, its throughput, its depth (fr_ro.w)
+  uint32_t n_frames;
+  f4* fr_ro; f4* fr_rd; f4* fr_hit; f4* fr_beta;
+  int* fr_inst;
 };
 
 struct Queues {
@@ -47,8 +55,11 @@ struct Queues {
   uint32_t* shadow;
   uint32_t* mis;
   uint32_t* bins;      // traced continuation rays binned by shading class: bins[cls * cap + k]
-  uint32_t* counts;    // [0] ext, [1] ext_next, [2] shadow, [3] mis, [4] trace fetch counter, [8 + cls] bin sizes,
-                       // [16 + segment] continuation rays pushed by the last shade stage for each wave in flight
+  uint32_t* counts;    // [0] ext, [1] ext_next, [2] shadow, [3] mis, [4] trace fetch counter, [5] wait_next, [8 + cls] bin sizes,
+                       // [16 + segment] continuation rays pushed by the last shade stage for each wave in flight,
+                       // [24..29) copy of [1..6) taken after the trace stage (k_ao / k_ri read their input list sizes there)
+  uint32_t* wait;      // directlighting / whitted: paths between two lighting rounds of one vertex (no continuation ray)
+  uint32_t* wait_next;
 };
 #define PT_MAX_SEGMENTS 8
 
@@ -361,7 +372,7 @@ PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int
   st_store<NC>(W.L, W.cap, i, sp_const<NC>(0.0f));
   st_store<NC>(W.pendA, W.cap, i, sp_const<NC>(0.0f));
   st_store<NC>(W.pendB, W.cap, i, sp_const<NC>(0.0f));
-  if (S.integrator.type == PT_INTEGRATOR_AO) W.mis_light[i] = n;  // the sample number selects the slice of the sample array (ao_body)
+  if (W.sample_num) { W.sample_num[i] = n; W.arr_off[i] = 0u; }
   Q.ext[qpos == 0xffffffffu ? i : qpos] = i;
 }
 
@@ -611,7 +622,7 @@ PT_HD void ao_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i) {
       f3 t = cross3(si.n, s);
       const int pk = W.pix[i];
       const int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
-      const int64_t idx = sampler_index(S, px, py, (int64_t)ns * (int64_t)W.mis_light[i] + (int64_t)round);
+      const int64_t idx = sampler_index(S, px, py, (int64_t)ns * (int64_t)W.sample_num[i] + (int64_t)round);
       f2 u = mk2(sampler_dim(S, idx, 5u, px, py), sampler_dim(S, idx, 6u, px, py));
       f3 wl;
       float pdf;
@@ -627,6 +638,262 @@ PT_HD void ao_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i) {
     }
   }
   push_rays(W, Q, i, push_sh, false, push_ext, true);
+}
+
+// ---- directlighting / whitted (integrators/directlighting.rs:66-125, whitted.rs:37-98) ------------------------------
+// li() is a recursion over the TREE of specular reflections and transmissions (SamplerIntegrator::specular_reflect /
+// specular_transmit, core/integrator/sampler.rs:37-160); the sampler's dimensions are consumed depth first.  One path slot
+// walks its tree depth first, one ray at a time: a vertex whose reflection branch is taken leaves a frame (ray, hit,
+// throughput, depth) for its transmission branch, which is sampled - at the dimension the sampler has reached by then -
+// when the reflection subtree is finished.  Radiance is gathered as throughput x term into L (the recursion's nested
+// f * li * w products in a different association: a few ulp).  The lighting of a vertex is a sequence of ROUNDS, one
+// light sample each (shadow ray [+ MIS ray] per round, through the same pendA / pendB mechanism as the path integrator):
+// whitted: one per light; directlighting "one": a single round on a uniformly picked light; "all": n_samples per light
+// from the 2D sample arrays (dimensions (5, 6) of sample NUMBER n * s + k for both arrays - the reference fills every 2D
+// array from the same two dimensions), or one get_2d pair per light once the max_depth * n_lights * 2 arrays are used up.
+// flags: bits 0-7 frames on the stack, 8-15 depth, 16-30 lighting round of the vertex, 31 the vertex reads sample arrays.
+#define PT_RI_MAX_DEPTH 32
+template <int NC>
+PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fresh, unsigned long long* vertex_counter) {
+  const uint32_t cap = W.cap;
+  const bool whitted = S.integrator.type == PT_INTEGRATOR_WHITTED;
+  const int NONSPEC = F_ALL & ~F_SPEC;
+  Sp<NC> L = st_load<NC>(W.L, cap, i);
+  L = L + st_load<NC>(W.pendA, cap, i);
+  L = L + st_load<NC>(W.pendB, cap, i);
+  st_store<NC>(W.pendA, cap, i, sp_const<NC>(0.0f));
+  st_store<NC>(W.pendB, cap, i, sp_const<NC>(0.0f));
+  uint32_t fl = W.flags[i];
+  uint32_t sp = fl & 0xffu, round = fresh ? 0u : ((fl >> 16) & 0x7fffu);
+  int depth = (int)((fl >> 8) & 0xffu);
+  bool arrays = !fresh && (fl >> 31) != 0u;
+  f4 ro4 = W.ray_o[i], rd4 = W.ray_d[i], h4 = W.hit[i];
+  int inst = S.has_instances ? W.hit_inst[i] : -1;
+  Sp<NC> beta = st_load<NC>(W.beta, cap, i);
+  SampleStream st;
+  st.index = W.sindex[i];
+  st.dim = W.dim[i];
+  const int pk = W.pix[i];
+  st.px = (pk & 0xffff) + S.sampler.sb[0];
+  st.py = (pk >> 16) + S.sampler.sb[1];
+  uint32_t arr_off = W.arr_off[i];
+  {  // GlobalSampler: get_1d / get_2d skip the dimensions of the sample arrays, [5, 5 + 2 x arrays) (halton.rs:227-231, 241-245)
+    const uint32_t n_arrays = (!whitted && S.integrator.direct_strategy == PT_DIRECT_ALL) ? 2u * S.n_lights * (uint32_t)S.integrator.max_depth : 0u;
+    if (st.dim < 5u + 2u * n_arrays) st.dim = 5u + 2u * n_arrays;
+  }
+  const float rtime = rd4.w;
+  bool push_sh = false, push_mis = false, push_ext = false, push_wait = false;
+  bool need_pop = false, have_vertex = false;
+  SurfD si;
+  BsdfD B;
+  B.n = -1;
+  if ((int)fbits(h4.w) < 0) need_pop = true;  // the ray left the scene: li = sum of Light::le = 0 (no infinite lights)
+  else {
+    si = make_surface(S, (int)fbits(h4.w), inst, xyz(ro4), xyz(rd4), rtime, h4.x, h4.y, h4.z);
+    make_bsdf<NC, -1, false>(S, si, &B);
+    if (B.n < 0) {  // no BSDF: whitted returns zero (whitted.rs:84), directlighting follows the ray at the same depth (:108-110)
+      if (whitted) need_pop = true;
+      else {
+        f3 o = offset_origin(si.p, si.perr, si.n, xyz(rd4));
+        W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+        push_ext = true;
+      }
+    } else have_vertex = true;
+  }
+  if (have_vertex && fresh) {
+    if (vertex_counter) {
+#if defined(__CUDA_ARCH__)
+      atomicAdd(vertex_counter, 1ull);
+#else
+      (*vertex_counter)++;
+#endif
+    }
+    if (!whitted) L = L + beta * surface_le<NC>(S, si, si.wo);
+  }
+  for (;;) {
+    if (have_vertex) {
+      RefPt ref;
+      ref.p = si.p; ref.perr = si.perr; ref.n = si.n;
+      const uint32_t nl = S.n_lights;
+      const bool all = !whitted && S.integrator.direct_strategy == PT_DIRECT_ALL;
+      if (all && round == 0u && nl > 0u) {  // uniform_sample_all_lights asks for two arrays per light (sample_lights.rs:38-39)
+        arrays = arr_off < 2u * nl * (uint32_t)S.integrator.max_depth;
+        if (arrays) arr_off += 2u * nl;
+      }
+      const uint32_t rounds = nl == 0u ? 0u : (whitted ? nl : (all ? (arrays ? ldg(S.light_sample_prefix + nl) : nl) : 1u));
+      bool emitted = false;
+      while (round < rounds && !emitted) {
+        int ln;
+        f2 u_light, u_scat;
+        float divisor = 1.0f;  // the estimate is divided by light_pdf ("one") or by n_samples ("all" with arrays)
+        if (whitted) { ln = (int)round; u_light = get2d(S, st); u_scat = u_light; }
+        else if (!all) {  // uniform_sample_one_light without a distribution (sample_lights.rs:104-110)
+          uint32_t k = (uint32_t)(get1d(S, st) * (float)nl);
+          ln = (int)(k < nl - 1u ? k : nl - 1u);
+          divisor = 1.0f / (float)nl;
+          u_light = get2d(S, st);
+          u_scat = get2d(S, st);
+        } else if (!arrays) { ln = (int)round; u_light = get2d(S, st); u_scat = get2d(S, st); }
+        else {
+          uint32_t lo = 0u, hi = nl;  // the light whose samples hold round: prefix[lo] <= round < prefix[lo + 1]
+          while (hi - lo > 1u) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (ldg(S.light_sample_prefix + mid) <= round) lo = mid; else hi = mid;
+          }
+          ln = (int)lo;
+          const uint32_t n = (uint32_t)S.lights[ln].n_samples, k = round - ldg(S.light_sample_prefix + lo);
+          const int64_t idx = sampler_index(S, st.px, st.py, (int64_t)n * (int64_t)W.sample_num[i] + (int64_t)k);
+          u_light = mk2(sampler_dim(S, idx, 5u, st.px, st.py), sampler_dim(S, idx, 6u, st.px, st.py));
+          u_scat = u_light;
+          divisor = (float)n;
+        }
+        round++;
+        const pt_light& LT = S.lights[ln];
+        LightSampleD<NC> ls;
+        const bool ok = light_sample<NC>(S, ln, ref, u_light, &ls);
+        if (whitted) {  // whitted.rs:61-79: BSDF over all lobes, shading normal, no MIS
+          if (ok && !(ls.pdf <= 0.0f || sp_black(ls.li))) {
+            Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, F_ALL);
+            if (!sp_black(f)) {
+              st_store<NC>(W.pendA, cap, i, beta * (f * ls.li * (absdot3(ls.wi, si.sn) / ls.pdf)));
+              W.sh_o[i] = mk4(ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, 0.0f);
+              W.sh_d[i] = mk4(ls.sh_d.x, ls.sh_d.y, ls.sh_d.z, 1.0f - PT_SHADOW_EPS);
+              push_sh = true;
+              emitted = true;
+            }
+          }
+          continue;
+        }
+        // estimate_direct_surface (sample_lights.rs:330-453), as in shade_body
+        const bool delta = LT.type != PT_LIGHT_AREA;
+        if (ok && ls.pdf > 0.0f && !sp_black(ls.li)) {
+          Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
+          float spdf = bsdf_pdf(B, si.wo, ls.wi, NONSPEC);
+          if (!sp_black(f)) {
+            Sp<NC> ld;
+            if (delta) ld = f * ls.li / ls.pdf;
+            else ld = f * ls.li * (power_heuristic1(ls.pdf, spdf) / ls.pdf);
+            st_store<NC>(W.pendA, cap, i, beta * (ld / divisor));
+            W.sh_o[i] = mk4(ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, 0.0f);
+            W.sh_d[i] = mk4(ls.sh_d.x, ls.sh_d.y, ls.sh_d.z, 1.0f - PT_SHADOW_EPS);
+            push_sh = true;
+            emitted = true;
+          }
+        }
+        if (!delta) {
+          Sp<NC> f2v;
+          f3 wi2;
+          float pdf2;
+          int stype;
+          if (bsdf_sample<NC>(S, B, si.wo, u_scat, NONSPEC, &f2v, &wi2, &pdf2, &stype)) {
+            Sp<NC> f = f2v * absdot3(wi2, si.sn);
+            if (!sp_black(f) && pdf2 > 0.0f) {
+              float weight = 1.0f;
+              bool go = true;
+              if (!(stype & F_SPEC)) {
+                float lp = light_pdf_li(S, ln, ref, wi2);
+                if (lp == 0.0f) go = false;
+                else weight = power_heuristic1(pdf2, lp);
+              }
+              if (go) {
+                Sp<NC> li = sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
+                Sp<NC> ld = f * li * sp_const<NC>(1.0f) * (weight / pdf2);
+                st_store<NC>(W.pendB, cap, i, beta * (ld / divisor));
+                f3 o = offset_origin(si.p, si.perr, si.n, wi2);
+                W.mis_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+                W.mis_d[i] = mk4(wi2.x, wi2.y, wi2.z, rtime);
+                W.mis_light[i] = ln;
+                push_mis = true;
+                emitted = true;
+              }
+            }
+          }
+        }
+      }
+      if (round < rounds) { push_wait = true; break; }  // the next round waits for this one's rays
+      // specular_reflect, then specular_transmit (directlighting.rs:101-104, whitted.rs:80-83)
+      need_pop = true;
+      if (depth + 1 < S.integrator.max_depth) {
+        for (int branch = 0; branch < 2 && need_pop; branch++) {
+          f2 u = get2d(S, st);
+          Sp<NC> f;
+          f3 wi;
+          float pdf;
+          int stype;
+          if (!bsdf_sample<NC>(S, B, si.wo, u, (branch == 0 ? F_REFL : F_TRANS) | F_SPEC, &f, &wi, &pdf, &stype)) continue;
+          const float wi_ns = absdot3(wi, si.sn);
+          if (!(pdf > 0.0f && !sp_black(f) && wi_ns != 0.0f)) continue;
+          if (branch == 0) {  // come back for the transmission branch
+            const size_t fi = (size_t)sp * cap + i;
+            W.fr_ro[fi] = mk4(ro4.x, ro4.y, ro4.z, bitsf((uint32_t)depth));
+            W.fr_rd[fi] = rd4;
+            W.fr_hit[fi] = h4;
+            reinterpret_cast<f4*>(W.fr_beta)[fi] = mk4(beta.c[0], beta.c[1], beta.c[NC > 2 ? 2 : 0], 0.0f);
+            if (W.fr_inst) W.fr_inst[fi] = inst;
+            sp++;
+          }
+          beta = beta * (f * (wi_ns / pdf));
+          f3 o = offset_origin(si.p, si.perr, si.n, wi);
+          W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+          W.ray_d[i] = mk4(wi.x, wi.y, wi.z, rtime);
+          depth += 1;
+          push_ext = true;
+          need_pop = false;
+        }
+      }
+    }
+    if (!need_pop) break;
+    // this subtree is finished: the innermost pending transmission branch, or the end of the path
+    if (sp == 0u) break;
+    sp--;
+    {
+      const size_t fi = (size_t)sp * cap + i;
+      ro4 = W.fr_ro[fi]; rd4 = W.fr_rd[fi]; h4 = W.fr_hit[fi];
+      const f4 b4 = reinterpret_cast<const f4*>(W.fr_beta)[fi];
+      beta.c[0] = b4.x; beta.c[1] = b4.y; beta.c[NC > 2 ? 2 : 0] = b4.z;
+      inst = W.fr_inst ? W.fr_inst[fi] : -1;
+      depth = (int)fbits(ro4.w);
+    }
+    si = make_surface(S, (int)fbits(h4.w), inst, xyz(ro4), xyz(rd4), rtime, h4.x, h4.y, h4.z);
+    make_bsdf<NC, -1, false>(S, si, &B);
+    // specular_transmit of the frame's vertex
+    f2 u = get2d(S, st);
+    Sp<NC> f;
+    f3 wi;
+    float pdf;
+    int stype;
+    have_vertex = false;
+    if (!bsdf_sample<NC>(S, B, si.wo, u, F_TRANS | F_SPEC, &f, &wi, &pdf, &stype)) continue;
+    const float wi_ns = absdot3(wi, si.sn);
+    if (!(pdf > 0.0f && !sp_black(f) && wi_ns != 0.0f)) continue;
+    beta = beta * (f * (wi_ns / pdf));
+    f3 o = offset_origin(si.p, si.perr, si.n, wi);
+    W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+    W.ray_d[i] = mk4(wi.x, wi.y, wi.z, rtime);
+    depth += 1;
+    push_ext = true;
+    need_pop = false;
+    break;
+  }
+  st_store<NC>(W.L, cap, i, L);
+  st_store<NC>(W.beta, cap, i, beta);
+  W.flags[i] = (arrays ? 0x80000000u : 0u) | ((round & 0x7fffu) << 16) | ((uint32_t)depth << 8) | sp;
+  W.dim[i] = st.dim;
+  W.arr_off[i] = arr_off;
+  push_rays(W, Q, i, push_sh, push_mis, push_ext);
+  if (push_wait) {
+    Q.wait_next[queue_push(&Q.counts[5])] = i;
+    if (W.nseg > 1) {
+      const uint32_t seg = i / W.seg_cap;
+#if defined(__CUDA_ARCH__)
+      unsigned m = __activemask();
+      unsigned peers = __match_any_sync(m, seg);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&Q.counts[16 + seg], (uint32_t)__popc(peers));
+#else
+      Q.counts[16 + seg]++;
+#endif
+    }
+  }
 }
 
 // MIS ray resolution: the BSDF-sampled ray contributes only if it hits the sampled light (pointer equality in the

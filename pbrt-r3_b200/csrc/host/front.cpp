@@ -506,7 +506,7 @@ struct Builder {
     if (!Sv.empty()) flags |= PT_TRI_HAS_S;
 
     int mat = material_for_shape(ps_in);
-    int light_spec = -1, light_two_sided = 0;
+    int light_spec = -1, light_two_sided = 0, light_samples = 1;
     if (is_area) {
       if (gs.area_light_name != "diffuse" && gs.area_light_name != "area")
         throw ParseError("AreaLightSource \"" + gs.area_light_name + "\" unknown");
@@ -515,6 +515,9 @@ struct Builder {
       for (size_t k = 0; k < L.size(); k++) L[k] = L[k] * sc[k];
       light_spec = add_spectrum(L);
       light_two_sided = gs.area_light_params.one_bool("twosided", false) ? 1 : 0;
+      light_samples = gs.area_light_params.one_int("nsamples", 1);  // lights/diffuse.rs:177-185
+      if (pt_current_options().quick_render) light_samples = std::max(light_samples / 4, 1);
+      if (light_samples < 1) throw ParseError("AreaLightSource: nsamples must be positive");
     }
     bool want_n = !N.empty(), want_uv = !UV.empty(), want_s = !Sv.empty();
     size_t ntri = vi.size() / 3;
@@ -560,6 +563,7 @@ struct Builder {
         l.spectrum = light_spec;
         l.tri = tri;
         l.two_sided = light_two_sided;
+        l.n_samples = light_samples;
         if (current_object == 0) {
           hs->lights.push_back(l);
           li = (int32_t)hs->lights.size() - 1;
@@ -578,6 +582,7 @@ struct Builder {
     pt_light l;
     memset(&l, 0, sizeof(l));
     l.tri = -1;
+    l.n_samples = 1;  // Light::get_sample_count default (core/light/light.rs:76-78)
     if (name == "point") {
       std::vector<float> I = one_spectrum(ps, "I", 1.0f), sc = one_spectrum(ps, "scale", 1.0f);
       for (size_t k = 0; k < I.size(); k++) I[k] = I[k] * sc[k];
@@ -925,8 +930,8 @@ struct Builder {
     if (pt_current_options().quick_render && S.type != PT_SAMPLER_RANDOM) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
 
     // Integrator (integrators/path.rs:252-271)
-    if (integrator_name != "path" && integrator_name != "aov" && integrator_name != "ambientocclusion")
-      throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path, aov, ambientocclusion)");
+    if (integrator_name != "path" && integrator_name != "aov" && integrator_name != "ambientocclusion" && integrator_name != "directlighting" && integrator_name != "whitted")
+      throw ParseError("Integrator \"" + integrator_name + "\" is not supported on the GPU path (path, directlighting, whitted, ambientocclusion, aov)");
     pt_integrator& I = D.integrator;
     I.type = PT_INTEGRATOR_PATH;
     if (integrator_name == "ambientocclusion") {  // integrators/ao.rs:119-138
@@ -937,6 +942,14 @@ struct Builder {
       if (I.ao_samples < 1) throw ParseError("Integrator \"ambientocclusion\": nsamples must be positive");
       if (S.type == PT_SAMPLER_RANDOM) throw ParseError("Integrator \"ambientocclusion\" with Sampler \"random\" is not supported on the GPU path (halton, sobol)");
       if (spec.n_channels() != 3) throw ParseError("Integrator \"ambientocclusion\" is only supported with RGB spectra");
+    }
+    if (integrator_name == "directlighting" || integrator_name == "whitted") {  // directlighting.rs:135-158, whitted.rs:109-130
+      const bool direct = integrator_name == "directlighting";
+      I.type = direct ? PT_INTEGRATOR_DIRECT : PT_INTEGRATOR_WHITTED;
+      if (direct) I.direct_strategy = integrator_params.one_string("strategy", "all") == "one" ? PT_DIRECT_ONE : PT_DIRECT_ALL;
+      if (!direct && integrator_params.find(PC_INT, "pixelbounds")) throw ParseError("Integrator \"whitted\": pixelbounds is not supported on the GPU path");
+      if (S.type == PT_SAMPLER_RANDOM) throw ParseError("Integrator \"" + integrator_name + "\" with Sampler \"random\" is not supported on the GPU path (halton, sobol)");
+      if (spec.n_channels() != 3) throw ParseError("Integrator \"" + integrator_name + "\" is only supported with RGB spectra");
     }
     if (integrator_name == "aov") {  // integrators/aov.rs:192-213, targets :36-58
       I.type = PT_INTEGRATOR_AOV;

@@ -199,6 +199,14 @@ def test_ao_integrator(P):
     check_ao(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
 
 
+def test_tree_integrators(P):
+    """Integrators "directlighting" (one / all with sample arrays / arrays used up) and "whitted" (core/integrator/
+    sampler.rs:37-160 specular_reflect / specular_transmit as a depth-first tree walk): per-sample radiance within 2e-5 of
+    the oracle's recursion, equal ray / BVH-visit / vertex counters, image, pipelined waves against one wave at a time."""
+    from test_hostcheck import check_tree
+    check_tree(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
+
+
 def test_one_sided_triangles_bit_exact(P, pair):
     """Back-face culling of one-sided meshes (triangle.rs:236-246), with and without ReverseOrientation."""
     from test_hostcheck import one_sided_scene

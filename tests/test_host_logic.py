@@ -188,6 +188,29 @@ def test_front_end_ao_integrator(P):
         lib.pt_set_options(P.capi.pt_options(0, 0))
 
 
+def test_front_end_tree_integrators(P):
+    base = 'Camera "perspective"\n%sIntegrator %s\nWorldBegin\nAttributeBegin\nAreaLightSource "diffuse" %s\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nAttributeEnd\nLightSource "point"\nWorldEnd\n'
+    hs = P.HostScene.parse_string(base % ("", '"directlighting"', '"integer nsamples" [6]'))
+    d = hs.desc.integrator
+    assert (d.type, d.direct_strategy, d.max_depth) == (P.capi.PT_INTEGRATOR_DIRECT, P.capi.PT_DIRECT_ALL, 5)   # directlighting.rs:140-141
+    assert [hs.desc.lights[i].n_samples for i in range(2)] == [6, 1]                                            # diffuse.rs:177, light.rs:76-78
+    d = P.HostScene.parse_string(base % ("", '"directlighting" "string strategy" ["one"] "integer maxdepth" [3]', "")).desc.integrator
+    assert (d.direct_strategy, d.max_depth) == (P.capi.PT_DIRECT_ONE, 3)
+    d = P.HostScene.parse_string(base % ("", '"whitted"', "")).desc.integrator
+    assert (d.type, d.max_depth) == (P.capi.PT_INTEGRATOR_WHITTED, 5)
+    for bad in ('"whitted" "integer pixelbounds" [0 1 0 1]',):
+        with pytest.raises(P.PbrtError):
+            P.HostScene.parse_string(base % ("", bad, ""))
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % ('Sampler "random"\n', '"whitted"', ""))
+    lib = P.capi.load()
+    lib.pt_set_options(P.capi.pt_options(1, 0))
+    try:
+        assert P.HostScene.parse_string(base % ("", '"directlighting"', '"integer nsamples" [6]')).desc.lights[0].n_samples == 1   # diffuse.rs:181-183
+    finally:
+        lib.pt_set_options(P.capi.pt_options(0, 0))
+
+
 def test_front_end_aov_integrator(P):
     base = 'Camera "perspective"\nIntegrator "aov" %s\nWorldBegin\nWorldEnd\n'
     d = P.HostScene.parse_string(base % "").desc.integrator

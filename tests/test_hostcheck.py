@@ -279,6 +279,64 @@ def test_hostcheck_ao_integrator(HC):
     check_ao(HC)
 
 
+def tree_scene(P, integrator, res=24, spp=2, maxdepth=5, nsamples=1, sampler="halton", instanced=False):
+    """Integrators "directlighting" / "whitted" on the Cornell box with a glass and a metal block, a plastic floor and a
+    mirror wall (the specular reflection / transmission tree branches at the glass), area + point + distant lights; or on
+    the instanced scene."""
+    if instanced:
+        txt = P.scenes.instanced_blobs(n_instances=20, n_sub=1, res=(res, res * 2 // 3), spp=spp, n_lights=2, sampler=sampler)
+    else:
+        txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", extra_lights=True, sampler=sampler)
+        txt = txt.replace('AreaLightSource "diffuse" "rgb L" [17 12 4]', 'AreaLightSource "diffuse" "rgb L" [17 12 4] "integer nsamples" [%d]' % nsamples)
+        shapes = [l for l in txt.split("\n") if l.startswith("Shape")]
+        txt = txt.replace(shapes[1], 'Material "none"\n' + shapes[1].replace("548.8", "500"), 1)   # a sheet without a material below the ceiling
+    head, rest = txt.split('Integrator "path"', 1)
+    return head + 'Integrator %s "integer maxdepth" [%d]' % (integrator, maxdepth) + rest[rest.index("\n"):]
+
+
+TREE_CASES = [('"directlighting" "string strategy" ["one"]', dict()),
+              ('"directlighting"', dict(nsamples=3)),                       # "all": sample arrays, 3 samples of each area-light triangle
+              ('"directlighting"', dict(maxdepth=2, sampler="sobol")),      # arrays run out below the first glass vertex: get_2d pairs
+              ('"directlighting" "string strategy" ["one"]', dict(instanced=True)),
+              ('"whitted"', dict()),
+              ('"whitted"', dict(instanced=True, maxdepth=3, sampler="sobol"))]
+
+
+def check_tree(P, n=1500, res=24, spp=2, wave_paths=300, threads=2, cases=None):
+    """per-sample radiance within a few ulp of the oracle's recursion (same rays, same samples: the ray and BVH visit
+    counters are EQUAL; the nested f * li * w products are associated differently), image, pipelined waves invisible"""
+    import oracle_api
+    for integ, kw in (cases or TREE_CASES):
+        kw = dict(dict(res=res, spp=spp), **kw)
+        hs = P.HostScene.parse_string(tree_scene(P, integ, **kw))
+        whitted = "whitted" in integ
+        assert hs.desc.integrator.type == (P.capi.PT_INTEGRATOR_WHITTED if whitted else P.capi.PT_INTEGRATOR_DIRECT)
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        sb = hs.desc.film.sample_bounds
+        rng = np.random.RandomState(8)
+        pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+        sn = rng.randint(0, kw["spp"], n).astype(np.int32)
+        la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+        bad = np.abs(la - lb) > 2e-5 * np.maximum(np.abs(lb), 1e-3)
+        assert not bad.any(), (integ, kw, int(bad.any(1).sum()), la[bad.any(1)][:3], lb[bad.any(1)][:3])
+        assert la.max() > 0
+        rgb, st = sc.render(collect_counters=1, wave_paths=wave_paths)
+        ref, so = orc.render(threads=threads)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5, (integ, kw)
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[k] == so[k], (integ, kw, k, st[k], so[k])
+        if not kw.get("instanced") and kw.get("maxdepth", 5) >= 5:
+            assert st["path_vertices"] > 1.02 * st["camera_rays"]      # the tree has more than one vertex for some samples
+        one, _ = sc.render(wave_paths=wave_paths, wave_segments=1)
+        assert np.array_equal(one, rgb), (integ, kw)
+
+
+def test_hostcheck_tree_integrators(HC):
+    """Integrators "directlighting" (strategies one / all, sample arrays) and "whitted": the specular reflection /
+    transmission recursion as a depth-first tree walk per path slot."""
+    check_tree(HC)
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')

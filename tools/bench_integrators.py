@@ -63,6 +63,11 @@ def run(name, text, spp):
 
 
 CASES = {
+    "direct_one_grid": lambda: (with_integrator(P.scenes.displaced_grid(n=708, res=1024, spp=16, maxdepth=8), 'Integrator "directlighting" "string strategy" ["one"] "integer maxdepth" [5]'), 16),
+    "direct_all_grid": lambda: (with_integrator(P.scenes.displaced_grid(n=708, res=1024, spp=16, maxdepth=8), 'Integrator "directlighting" "integer maxdepth" [5]'), 16),
+    "whitted_grid": lambda: (with_integrator(P.scenes.displaced_grid(n=708, res=1024, spp=16, maxdepth=8), 'Integrator "whitted" "integer maxdepth" [5]'), 16),
+    "direct_one_instanced": lambda: (with_integrator(P.scenes.instanced_blobs(n_instances=1000, n_sub=5, res=(1920, 1080), spp=4, maxdepth=8, n_lights=256),
+                                                     'Integrator "directlighting" "string strategy" ["one"] "integer maxdepth" [5]'), 4),
     "ao_grid": lambda: (with_integrator(P.scenes.displaced_grid(n=708, res=1024, spp=4, maxdepth=8), 'Integrator "ambientocclusion" "integer nsamples" [64]'), 4),
     "ao_instanced": lambda: (with_integrator(P.scenes.instanced_blobs(n_instances=1000, n_sub=5, res=(1920, 1080), spp=1, maxdepth=8, n_lights=256),
                                              'Integrator "ambientocclusion" "integer nsamples" [64]'), 1),
