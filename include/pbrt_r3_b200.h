@@ -43,7 +43,8 @@ enum pt_light_type {          /* reference src/lights/create_light.rs:13-54 */
   PT_LIGHT_AREA = 0,          /* lights/diffuse.rs  (one per emissive triangle) */
   PT_LIGHT_POINT = 1,         /* lights/point.rs    */
   PT_LIGHT_DISTANT = 2,       /* lights/distant.rs  */
-  PT_LIGHT_SPOT = 3           /* lights/spot.rs     */
+  PT_LIGHT_SPOT = 3,          /* lights/spot.rs     */
+  PT_LIGHT_INFINITE = 4       /* lights/infinite.rs: environment light (constant L, or a lat-long map) */
 };
 
 enum pt_sampler_type {        /* reference src/samplers/create_sampler.rs:12-33 */
@@ -96,12 +97,23 @@ typedef struct pt_material {
 typedef struct pt_light {
   int32_t type;               /* pt_light_type */
   int32_t spectrum;           /* area: Lemit = L*scale | point: I*scale | distant: L*scale (spectrum index) */
-  int32_t tri;                /* area: triangle index; spot: index into pt_scene_desc.spots; else -1 */
+  int32_t tri;                /* area: triangle index; spot: index into pt_scene_desc.spots; infinite: index into
+                                 pt_scene_desc.envmaps; else -1 */
   int32_t two_sided;          /* area: DiffuseAreaLight.two_sided (lights/diffuse.rs:178) */
   float v[3];                 /* point, spot: p_light (world) | distant: w_light (world, normalised) */
   int32_t n_samples;          /* Light::get_sample_count: area "nsamples" (default 1, n / 4 under --quick, diffuse.rs:177-185), else 1;
                                  read by directlighting's "all" strategy only */
 } pt_light;
+
+/* InfiniteAreaLight extras (lights/infinite.rs:12-95): level 0 of the MIPMap<RGBSpectrum> the light looks up.  The
+ * callee builds the pyramid and the Distribution2D from it (make_distribution, infinite.rs:67-93). */
+typedef struct pt_envmap {
+  float l2w[9];               /* upper 3x3 of light_to_world, row-major */
+  float w2l[9];               /* upper 3x3 of world_to_light */
+  int32_t width, height;      /* powers of two; 1 x 1 for a light without "mapname" */
+  const float* texels;        /* width * height RGB triples, row 0 = top: read_image(mapname) clamped at 0, times L * scale
+                                 (make_mipmap, infinite.rs:47-65) */
+} pt_envmap;
 
 /* SpotLight extras (lights/spot.rs:5-56): falloff(w) looks at the z component of normalize(world_to_light * w). */
 typedef struct pt_spot {
@@ -225,6 +237,8 @@ typedef struct pt_scene_desc {
   const pt_light* lights;     /* n_lights + n_emitters_only records */
   uint32_t n_spots;
   const pt_spot* spots;
+  uint32_t n_envmaps;
+  const pt_envmap* envmaps;
 
   pt_camera camera;
   pt_film film;

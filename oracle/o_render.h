@@ -41,6 +41,8 @@ struct Scene {
   LightDistrib<NC> distrib;
   SamplerConfig scfg;
   std::mutex distrib_mutex;
+  std::vector<EnvMap> envs;          // InfiniteAreaLight maps, indexed by pt_light.tri
+  std::vector<int> infinite_lights;  // Scene.infinite_lights (scene.rs:24-25)
 
   void init(const pt_scene_desc* desc) {
     d = desc;
@@ -55,7 +57,11 @@ struct Scene {
     world_bound = geom.objects[0]->bounds;
     Vec3 dg = world_bound.mx - world_bound.mn;
     world_radius = length(dg) * 0.5f;  // Bounds3f::bounding_sphere (bounds3.rs:184-188)
-    if (desc->n_lights > 0) distrib.init(desc, world_bound, world_radius);
+    envs.resize(desc->n_envmaps);
+    for (uint32_t k = 0; k < desc->n_envmaps; k++) envs[k].init(desc->envmaps[k]);
+    for (uint32_t i = 0; i < desc->n_lights; i++)
+      if (desc->lights[i].type == PT_LIGHT_INFINITE) infinite_lights.push_back((int)i);
+    if (desc->n_lights > 0) distrib.init(desc, world_bound, world_radius, envs.data());
     scfg = make_sampler_config(desc->sampler.type, desc->sampler.samples_per_pixel, desc->film.sample_bounds, desc->sampler.sample_at_pixel_center != 0);
     if (desc->integrator.type == PT_INTEGRATOR_AO) scfg.n_arrays_2d = 1;  // AOIntegrator::new: request_2d_array(n_samples) (ao.rs:29)
     if (desc->integrator.type == PT_INTEGRATOR_DIRECT && desc->integrator.direct_strategy == PT_DIRECT_ALL)  // directlighting.rs:57-63
@@ -94,7 +100,7 @@ inline Spec<NC> estimate_direct(Scene<NC>& sc, const SurfInt& it, const BSDF<NC>
   ref.p = it.p; ref.p_error = it.p_error; ref.n = it.n; ref.time = it.time;
   const pt_light& L = d->lights[light_num];
   LightSample<NC> ls;
-  if (light_sample_li<NC>(d, sc.world_radius, light_num, ref, u_light, &ls)) {
+  if (light_sample_li<NC>(d, sc.world_radius, light_num, ref, u_light, &ls, sc.envs.data())) {
 #ifdef ORC_DEBUG_PRINT
     fprintf(stderr, "[or] p=(%g %g %g) n=(%g %g %g) perr=(%g %g %g) light %d\n", it.p.x, it.p.y, it.p.z, it.n.x, it.n.y, it.n.z, it.p_error.x, it.p_error.y, it.p_error.z, light_num);
     fprintf(stderr, "[or] ls pdf %g li %g wi=(%g %g %g) sh_o=(%.9g %.9g %.9g) sh_d=(%.9g %.9g %.9g) occluded %d\n", ls.pdf, ls.li.c[0], ls.wi.x, ls.wi.y, ls.wi.z, ls.shadow.o.x, ls.shadow.o.y, ls.shadow.o.z, ls.shadow.d.x, ls.shadow.d.y, ls.shadow.d.z, (int)sc.intersect_p(ls.shadow, nullptr));
@@ -133,7 +139,7 @@ inline Spec<NC> estimate_direct(Scene<NC>& sc, const SurfInt& it, const BSDF<NC>
     if (!f.is_black() && scattering_pdf > 0.0f) {
       Float weight = 1.0f;
       if (!sampled_specular) {
-        Float light_pdf = light_pdf_li(d, light_num, ref, wi);
+        Float light_pdf = light_pdf_li(d, light_num, ref, wi, sc.envs.data());
         if (light_pdf == 0.0f) return ld;
         weight = power_heuristic(1, scattering_pdf, 1, light_pdf);
       }
@@ -145,7 +151,7 @@ inline Spec<NC> estimate_direct(Scene<NC>& sc, const SurfInt& it, const BSDF<NC>
           SurfInt ls2 = make_si(d, h);
           li = surface_le<NC>(d, ls2, -wi);
         }
-      }  // else: light.le(ray) = 0 for non-infinite lights
+      } else if (L.type == PT_LIGHT_INFINITE) li = env_le<NC>(sc.envs[L.tri], ray.d);  // light.le(ray): zero for the other lights
       if (!li.is_black()) ld = ld + f * li * Spec<NC>(1.0f) * (weight / scattering_pdf);
     }
   }
@@ -304,7 +310,11 @@ inline Spec<NC> recursive_li(Scene<NC>& sc, const Ray& ray, Sampler& sampler, Co
   const pt_scene_desc* d = sc.d;
   const bool whitted = d->integrator.type == PT_INTEGRATOR_WHITTED;
   Hit h;
-  if (!sc.intersect(ray, &h, cnt)) return Spec<NC>();  // sum of light.le(ray): zero without infinite lights
+  if (!sc.intersect(ray, &h, cnt)) {  // sum of light.le(ray) over ALL lights (directlighting.rs:112-122): non-zero for infinite lights
+    Spec<NC> l;
+    for (int li : sc.infinite_lights) l = l + env_le<NC>(sc.envs[sc.d->lights[li].tri], ray.d);
+    return l;
+  }
   SurfInt isect = make_si(d, h);
   if (trace && trace->first_tri == -1) { trace->first_tri = h.tri; trace->first_t = h.t; }
   BSDF<NC> bsdf;
@@ -321,7 +331,7 @@ inline Spec<NC> recursive_li(Scene<NC>& sc, const Ray& ray, Sampler& sampler, Co
     for (uint32_t j = 0; j < sc.n_sampled_lights(); j++) {
       Vec2 u = sampler.get_2d();
       LightSample<NC> ls;
-      if (!light_sample_li<NC>(d, sc.world_radius, (int)j, ref, u, &ls)) { l = l + Spec<NC>(); continue; }
+      if (!light_sample_li<NC>(d, sc.world_radius, (int)j, ref, u, &ls, sc.envs.data())) { l = l + Spec<NC>(); continue; }
       if (ls.pdf <= 0.0f || ls.li.is_black()) { l = l + Spec<NC>(); continue; }
       Spec<NC> f = bsdf.f(isect.wo, ls.wi, BSDF_ALL);
       if (!f.is_black() && !sc.intersect_p(ls.shadow, cnt)) l = l + f * ls.li * (abs_dot(ls.wi, isect.sn) / ls.pdf);
@@ -371,6 +381,7 @@ inline Spec<NC> path_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters*
     if (trace && bounces == 0 && trace->first_tri == -1 && found) { trace->first_tri = h.tri; trace->first_t = h.t; }
     if (bounces == 0 || specular_bounce) {
       if (found) l = l + beta * surface_le<NC>(d, isect, -ray.d);
+      else for (int li : sc.infinite_lights) l = l + beta * env_le<NC>(sc.envs[d->lights[li].tri], ray.d);  // path.rs:92-95
     }
     if (!found || bounces >= max_depth) break;
     BSDF<NC> bsdf;

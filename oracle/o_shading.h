@@ -760,6 +760,134 @@ inline bool tri_sample_from(const pt_scene_desc* d, int tri, const RefPoint& ref
   return true;
 }
 
+// ---- InfiniteAreaLight (lights/infinite.rs) ------------------------------------------------------------------------
+// MIPMap<RGBSpectrum> of a power-of-two map (core/texture/mipmap.rs: make_pyramid :406-441 with downsample_half :225-275,
+// triangle :711-767, lookup :620-637; create_spectrum_mipmap :1013-1026 = trilinear off, s repeats, t clamps) and the
+// Distribution2D built by make_distribution (infinite.rs:67-93; core/sampling/distribution.rs:109-145).
+struct MipLevel { int w = 0, h = 0; std::vector<Float> rgb; };
+struct EnvMap {
+  Float l2w[9], w2l[9];
+  std::vector<MipLevel> pyramid;
+  std::vector<Distribution1D> conditional_v;
+  Distribution1D marginal;
+
+  static std::vector<Float> downsample_half(const std::vector<Float>& img, int width, int height) {  // halves the width
+    int nw = width / 2;
+    std::vector<Float> out((size_t)3 * nw * height);
+    for (int y = 0; y < height; y++)
+      for (int x = 0; x < nw; x++)
+        for (int c = 0; c < 3; c++) {
+          size_t i0 = (size_t)y * width + (2 * x + 0), i1 = (size_t)y * width + (2 * x + 1);
+          out[3 * ((size_t)y * nw + x) + c] = img[3 * i0 + c] * 0.5f + img[3 * i1 + c] * 0.5f;
+        }
+    return out;
+  }
+  static std::vector<Float> transpose(const std::vector<Float>& img, int width, int height) {
+    std::vector<Float> out(img.size());
+    for (int y = 0; y < height; y++)
+      for (int x = 0; x < width; x++)
+        for (int c = 0; c < 3; c++) out[3 * ((size_t)x * height + y) + c] = img[3 * ((size_t)y * width + x) + c];
+    return out;
+  }
+  void make_pyramid(int w, int h, std::vector<Float> data) {
+    MipLevel L; L.w = w; L.h = h; L.rgb = data;
+    pyramid.push_back(L);
+    if (w * h == 1) return;
+    std::vector<Float> s = data;
+    int sw = w, sh = h;
+    if (w > 1) { s = downsample_half(s, w, h); sw = w / 2; }
+    if (h > 1) {
+      s = transpose(s, sw, sh);          // now sh wide, sw high
+      s = downsample_half(s, sh, sw);
+      s = transpose(s, sh / 2, sw);
+      sh = h / 2;
+    }
+    make_pyramid(sw, sh, s);
+  }
+  void triangle(size_t level, Vec2 st, Float out[3]) const {
+    level = std::min(level, pyramid.size() - 1);
+    const MipLevel& I = pyramid[level];
+    Float s = st.x * (Float)I.w - 0.5f, t = st.y * (Float)I.h - 0.5f;
+    int s0 = (int)floorf(s), t0 = (int)floorf(t);
+    Float ds = s - (Float)s0, dt = t - (Float)t0;
+    int s1 = s0 + 1, t1 = t0 + 1;
+    s0 = s0 & (I.w - 1); s1 = s1 & (I.w - 1);                                      // ImageWrap::Repeat
+    t0 = std::min(std::max(t0, 0), I.h - 1); t1 = std::min(std::max(t1, 0), I.h - 1);  // ImageWrap::Clamp
+    for (int c = 0; c < 3; c++) {
+      Float a = I.rgb[3 * ((size_t)t0 * I.w + s0) + c] * ((1.0f - ds) * (1.0f - dt));
+      Float b = I.rgb[3 * ((size_t)t1 * I.w + s0) + c] * ((1.0f - ds) * dt);
+      Float cc = I.rgb[3 * ((size_t)t0 * I.w + s1) + c] * (ds * (1.0f - dt));
+      Float d = I.rgb[3 * ((size_t)t1 * I.w + s1) + c] * (ds * dt);
+      out[c] = a + b + cc + d;
+    }
+  }
+  void lookup(Vec2 st, Float width, Float out[3]) const {
+    Float max_level = (Float)(pyramid.size() - 1);
+    Float level = max_level + log2f(rmax(width, 1e-8f));
+    if (level < 0.0f) { triangle(0, st, out); return; }
+    if (level >= max_level) { for (int c = 0; c < 3; c++) out[c] = pyramid.back().rgb[c]; return; }
+    size_t il = (size_t)floorf(level);
+    Float delta = rclamp(level - (Float)il, 0.0f, 1.0f);
+    Float a[3], b[3];
+    triangle(il, st, a);
+    triangle(il + 1, st, b);
+    for (int c = 0; c < 3; c++) out[c] = a[c] * (1.0f - delta) + b[c] * delta;
+  }
+  static Float rgb_y(const Float* c) { return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]; }
+  void init(const pt_envmap& M) {
+    for (int i = 0; i < 9; i++) { l2w[i] = M.l2w[i]; w2l[i] = M.w2l[i]; }
+    make_pyramid(M.width, M.height, std::vector<Float>(M.texels, M.texels + (size_t)M.width * M.height * 3));
+    size_t width = (size_t)M.width * 2, height = (size_t)M.height * 2;   // make_distribution
+    std::vector<Float> img(width * height);
+    Float fwidth = 0.5f / (Float)std::min(width, height);
+    for (size_t v = 0; v < height; v++) {
+      Float vp = ((Float)v + 0.5f) / (Float)height;
+      Float sin_theta = sinf(PI * vp);
+      for (size_t u = 0; u < width; u++) {
+        Float up = ((Float)u + 0.5f) / (Float)width;
+        Float c[3];
+        lookup(Vec2(up, vp), fwidth, c);
+        img[v * width + u] = rmax(rgb_y(c), 0.0f) * sin_theta;
+      }
+    }
+    std::vector<Float> mf;
+    for (size_t v = 0; v < height; v++) {
+      conditional_v.emplace_back(std::vector<Float>(img.begin() + v * width, img.begin() + (v + 1) * width));
+      mf.push_back(conditional_v.back().func_int);
+    }
+    marginal = Distribution1D(mf);
+  }
+  Vec2 sample_continuous(Vec2 u, Float* pdf) const {
+    Float pdf1, pdf0;
+    size_t v, dummy;
+    Float d1 = marginal.sample_continuous(u.y, &pdf1, &v);
+    Float d0 = conditional_v[v].sample_continuous(u.x, &pdf0, &dummy);
+    *pdf = pdf0 * pdf1;
+    return Vec2(d0, d1);
+  }
+  Float pdf(Vec2 p) const {
+    size_t uc = conditional_v[0].func.size(), vc = marginal.func.size();
+    Float fu = p.x * (Float)uc, fv = p.y * (Float)vc;
+    size_t iu = fu > 0.0f ? (size_t)fu : 0, iv = fv > 0.0f ? (size_t)fv : 0;   // `as usize` saturates
+    iu = std::min(iu, uc - 1); iv = std::min(iv, vc - 1);
+    return conditional_v[iv].func[iu] / marginal.func_int;
+  }
+  Vec3 to_light(Vec3 v) const { return Vec3(w2l[0] * v.x + w2l[1] * v.y + w2l[2] * v.z, w2l[3] * v.x + w2l[4] * v.y + w2l[5] * v.z, w2l[6] * v.x + w2l[7] * v.y + w2l[8] * v.z); }
+  Vec3 to_world(Vec3 v) const { return Vec3(l2w[0] * v.x + l2w[1] * v.y + l2w[2] * v.z, l2w[3] * v.x + l2w[4] * v.y + l2w[5] * v.z, l2w[6] * v.x + l2w[7] * v.y + l2w[8] * v.z); }
+};
+inline Float spherical_theta(Vec3 v) { return acosf(rclamp(v.z, -1.0f, 1.0f)); }                         // geometry/misc.rs:96-104
+inline Float spherical_phi(Vec3 v) { Float p = atan2f(v.y, v.x); return p < 0.0f ? p + 2.0f * PI : p; }
+// InfiniteAreaLight::le (infinite.rs:110-121); RGB spectra only
+template <int NC>
+inline Spec<NC> env_le(const EnvMap& E, Vec3 ray_d) {
+  Vec3 w = normalize(E.to_light(ray_d));
+  Float c[3];
+  E.lookup(Vec2(spherical_phi(w) * INV_2_PI, spherical_theta(w) * INV_PI), 0.0f, c);
+  Spec<NC> r;
+  for (int k = 0; k < 3 && k < NC; k++) r.c[k] = c[k];
+  return r;
+}
+
 template <int NC>
 struct LightSample {
   Spec<NC> li;
@@ -775,8 +903,29 @@ inline Spec<NC> area_l(const pt_scene_desc* d, const pt_light& L, Vec3 n, Vec3 w
 }
 
 template <int NC>
-inline bool light_sample_li(const pt_scene_desc* d, Float world_radius, int li, const RefPoint& it, Vec2 u, LightSample<NC>* out) {
+inline bool light_sample_li(const pt_scene_desc* d, Float world_radius, int li, const RefPoint& it, Vec2 u, LightSample<NC>* out, const EnvMap* envs = nullptr) {
   const pt_light& L = d->lights[li];
+  if (L.type == PT_LIGHT_INFINITE) {  // infinite.rs:123-166
+    const EnvMap& E = envs[L.tri];
+    Float map_pdf;
+    Vec2 uv = E.sample_continuous(u, &map_pdf);
+    if (map_pdf <= 0.0f) return false;
+    Float theta = uv.y * PI, phi = uv.x * 2.0f * PI;
+    Float cos_theta = cosf(theta), sin_theta = rclamp(sinf(theta), 0.0f, 1.0f);
+    Float cos_phi = cosf(phi), sin_phi = sinf(phi);
+    Vec3 wi = E.to_world(Vec3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta));
+    out->wi = wi;
+    out->pdf = sin_theta == 0.0f ? 0.0f : map_pdf / (2.0f * PI * PI * sin_theta);
+    RefPoint pl;
+    pl.p = it.p + wi * (2.0f * world_radius);
+    pl.time = it.time;
+    out->shadow = spawn_ray_to(it, pl);
+    Float c[3];
+    E.lookup(uv, 0.0f, c);
+    out->li = Spec<NC>();
+    for (int k = 0; k < 3 && k < NC; k++) out->li.c[k] = c[k];
+    return true;
+  }
   if (L.type == PT_LIGHT_AREA) {  // diffuse.rs:65-82
     RefPoint ps;
     Float pdf;
@@ -824,8 +973,16 @@ inline bool light_sample_li(const pt_scene_desc* d, Float world_radius, int li, 
   return true;
 }
 // Shape::pdf_from (shape.rs:40-54) for the light's triangle
-inline Float light_pdf_li(const pt_scene_desc* d, int li, const RefPoint& it, Vec3 wi) {
+inline Float light_pdf_li(const pt_scene_desc* d, int li, const RefPoint& it, Vec3 wi, const EnvMap* envs = nullptr) {
   const pt_light& L = d->lights[li];
+  if (L.type == PT_LIGHT_INFINITE) {  // infinite.rs:168-185
+    const EnvMap& E = envs[L.tri];
+    Vec3 wl = E.to_light(wi);
+    Float theta = spherical_theta(wl), phi = spherical_phi(wl);
+    Float sin_theta = rclamp(sinf(theta), 0.0f, 1.0f);
+    if (sin_theta == 0.0f) return 0.0f;
+    return E.pdf(Vec2(phi * INV_2_PI, theta * INV_PI)) / (2.0f * PI * PI * sin_theta);
+  }
   if (L.type != PT_LIGHT_AREA) return 0.0f;
   Ray ray = spawn_ray(it, wi);
   TriHit th;
@@ -835,12 +992,19 @@ inline Float light_pdf_li(const pt_scene_desc* d, int li, const RefPoint& it, Ve
   if (std::isinf(pdf)) return 0.0f;
   return pdf;
 }
-inline bool light_is_delta(const pt_light& L) { return L.type != PT_LIGHT_AREA; }
+inline bool light_is_delta(const pt_light& L) { return L.type != PT_LIGHT_AREA && L.type != PT_LIGHT_INFINITE; }
 
 template <int NC>
-inline Spec<NC> light_power(const pt_scene_desc* d, Float world_radius, int li) {
+inline Spec<NC> light_power(const pt_scene_desc* d, Float world_radius, int li, const EnvMap* envs = nullptr) {
   const pt_light& L = d->lights[li];
   Spec<NC> s = Spec<NC>::load(d->spectra + (size_t)L.spectrum * NC);
+  if (L.type == PT_LIGHT_INFINITE) {  // infinite.rs:103-108
+    Float c[3];
+    envs[L.tri].lookup(Vec2(0.5f, 0.5f), 0.5f, c);
+    Spec<NC> r;
+    for (int k = 0; k < 3 && k < NC; k++) r.c[k] = c[k];
+    return r * (PI * world_radius * world_radius);
+  }
   if (L.type == PT_LIGHT_AREA) return s * ((L.two_sided ? 2.0f : 1.0f) * tri_area(d, L.tri) * PI);
   if (L.type == PT_LIGHT_POINT) return s * (4.0f * PI);
   if (L.type == PT_LIGHT_SPOT) {  // spot.rs:82-85 (minus, unlike pbrt-v3's plus)
@@ -861,15 +1025,16 @@ struct LightDistrib {
   Distribution1D fixed;                                      // uniform / power
   mutable std::vector<std::unique_ptr<Distribution1D>> grid;  // spatial: dense, lazily filled (a pure function of the voxel)
 
-  void init(const pt_scene_desc* desc, const Bounds3& world_bound, Float radius) {
-    d = desc; wb = world_bound; world_radius = radius;
+  const EnvMap* envs = nullptr;
+  void init(const pt_scene_desc* desc, const Bounds3& world_bound, Float radius, const EnvMap* env_maps = nullptr) {
+    d = desc; wb = world_bound; world_radius = radius; envs = env_maps;
     int strat = d->integrator.light_strategy;
     if (strat == PT_LIGHTS_UNIFORM && d->n_lights != 1) strat = PT_LIGHTS_SPATIAL;  // create_light_sample_distribution.rs:23-29
     strategy = strat;
     if (strat == PT_LIGHTS_UNIFORM) fixed = Distribution1D(std::vector<Float>(d->n_lights, 1.0f));
     else if (strat == PT_LIGHTS_POWER) {
       std::vector<Float> pw;
-      for (uint32_t i = 0; i < d->n_lights; i++) pw.push_back(spec_y(d, light_power<NC>(d, world_radius, (int)i)));
+      for (uint32_t i = 0; i < d->n_lights; i++) pw.push_back(spec_y(d, light_power<NC>(d, world_radius, (int)i, envs)));
       fixed = Distribution1D(pw);
     } else {
       const uint32_t max_voxels = 64;
@@ -901,7 +1066,7 @@ struct LightDistrib {
       Vec2 u(radical_inverse(3, i), radical_inverse(4, i));
       for (size_t j = 0; j < nl; j++) {
         LightSample<NC> ls;
-        if (light_sample_li<NC>(d, world_radius, (int)j, it, u, &ls))
+        if (light_sample_li<NC>(d, world_radius, (int)j, it, u, &ls, envs))
           if (ls.pdf > 0.0f) contrib[j] += spec_y(d, ls.li) / ls.pdf;
       }
     }

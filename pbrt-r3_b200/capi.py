@@ -12,7 +12,7 @@ DATA_DIR = os.path.join(HERE, "data")
 
 PT_ABI_VERSION = 3
 PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MIRROR = -1, 0, 1, 2, 3, 4
-PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT = 0, 1, 2, 3
+PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT, PT_LIGHT_INFINITE = 0, 1, 2, 3, 4
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
 PT_INTEGRATOR_PATH, PT_INTEGRATOR_AOV, PT_INTEGRATOR_AO, PT_INTEGRATOR_DIRECT, PT_INTEGRATOR_WHITTED = 0, 1, 2, 3, 4
@@ -34,6 +34,10 @@ class pt_material(C.Structure):
 class pt_light(C.Structure):
     _fields_ = [("type", C.c_int32), ("spectrum", C.c_int32), ("tri", C.c_int32), ("two_sided", C.c_int32),
                 ("v", C.c_float * 3), ("n_samples", C.c_int32)]
+
+
+class pt_envmap(C.Structure):
+    _fields_ = [("l2w", C.c_float * 9), ("w2l", C.c_float * 9), ("width", C.c_int32), ("height", C.c_int32), ("texels", C.POINTER(C.c_float))]
 
 
 class pt_spot(C.Structure):
@@ -77,6 +81,7 @@ class pt_scene_desc(C.Structure):
                 ("instances", C.POINTER(pt_instance)),
                 ("n_materials", C.c_uint32), ("materials", C.POINTER(pt_material)),
                 ("n_lights", C.c_uint32), ("n_emitters_only", C.c_uint32), ("lights", C.POINTER(pt_light)), ("n_spots", C.c_uint32), ("spots", C.POINTER(pt_spot)),
+                ("n_envmaps", C.c_uint32), ("envmaps", C.POINTER(pt_envmap)),
                 ("camera", pt_camera), ("film", pt_film), ("sampler", pt_sampler), ("integrator", pt_integrator), ("accel", pt_accel)]
 
 

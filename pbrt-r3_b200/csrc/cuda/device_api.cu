@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../host/bvh_build.h"
+#include "../host/envmap.h"
 #include "../host/scene_accel.h"
 #include "../host/spectrum_host.h"
 #include "kernels.cuh"
@@ -392,6 +393,41 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(s->bufs.upload(alpha.data(), alpha.size(), &H.alpha));
   CK(s->bufs.upload(D->lights, (size_t)D->n_lights + D->n_emitters_only, &H.lights));
   CK(s->bufs.upload(D->spots, D->n_spots, &H.spots));
+  // ---- infinite lights (lights/infinite.rs): level 0 of the map + Distribution2D tables; the pyramid stays on the host
+  H.envs = nullptr; H.inf_lights = nullptr; H.n_inf = 0;
+  std::vector<pth::EnvMapHost> env_host(D->n_envmaps);
+  {
+    std::vector<EnvDev> envs(D->n_envmaps);
+    for (uint32_t k = 0; k < D->n_envmaps; k++) {
+      const pt_envmap& M = D->envmaps[k];
+      if (M.width < 1 || M.height < 1 || (M.width & (M.width - 1)) || (M.height & (M.height - 1)) || !M.texels) { pt_set_error("pt_envmap: width / height must be powers of two"); return 1; }
+      if (NC != 3) { pt_set_error("infinite lights are only supported with RGB spectra"); return 1; }
+      pth::EnvMapHost& E = env_host[k];
+      E.build_pyramid(M.width, M.height, M.texels);
+      E.build_distribution();
+      EnvDev& V = envs[k];
+      memset(&V, 0, sizeof(V));
+      memcpy(V.l2w, M.l2w, sizeof(V.l2w));
+      memcpy(V.w2l, M.w2l, sizeof(V.w2l));
+      V.w = M.width; V.h = M.height; V.nu = E.nu; V.nv = E.nv; V.m_int = E.m_int;
+      std::vector<f4> tex((size_t)M.width * M.height);
+      for (size_t i = 0; i < tex.size(); i++) tex[i] = mk4(M.texels[3 * i], M.texels[3 * i + 1], M.texels[3 * i + 2], 0.0f);
+      CK(s->bufs.upload(tex.data(), tex.size(), &V.texels));
+      CK(s->bufs.upload(E.func.data(), E.func.size(), &V.func));
+      CK(s->bufs.upload(E.cdf.data(), E.cdf.size(), &V.cdf));
+      CK(s->bufs.upload(E.row_int.data(), E.row_int.size(), &V.row_int));
+      CK(s->bufs.upload(E.mcdf.data(), E.mcdf.size(), &V.mcdf));
+    }
+    std::vector<int32_t> inf;
+    for (uint32_t i = 0; i < D->n_lights; i++)
+      if (D->lights[i].type == PT_LIGHT_INFINITE) {
+        if (D->lights[i].tri < 0 || (uint32_t)D->lights[i].tri >= D->n_envmaps) { pt_set_error("infinite light: envmap index out of range"); return 1; }
+        inf.push_back((int32_t)i);
+      }
+    if (!envs.empty()) CK(s->bufs.upload(envs.data(), envs.size(), &H.envs));
+    if (!inf.empty()) CK(s->bufs.upload(inf.data(), inf.size(), &H.inf_lights));
+    H.n_inf = (uint32_t)inf.size();
+  }
   H.light_sample_prefix = nullptr;
   if (D->integrator.type == PT_INTEGRATOR_DIRECT || D->integrator.type == PT_INTEGRATOR_WHITTED) {
     if (D->integrator.max_depth > PT_RI_MAX_DEPTH) { pt_set_error("directlighting / whitted: maxdepth above 32 is not supported on the GPU path"); return 1; }
@@ -520,8 +556,13 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
         for (uint32_t i = 0; i < D->n_lights; i++) {
           const pt_light& L = D->lights[i];
           const float* sp = D->spectra + (size_t)L.spectrum * NC;
+          float env_rgb[3];
           float k;
-          if (L.type == PT_LIGHT_AREA) {
+          if (L.type == PT_LIGHT_INFINITE) {  // infinite.rs:103-108: lookup((0.5, 0.5), 0.5) * pi r^2
+            env_host[(size_t)L.tri].lookup(0.5f, 0.5f, 0.5f, env_rgb);
+            sp = env_rgb;
+            k = PT_PI * H.world_radius * H.world_radius;
+          } else if (L.type == PT_LIGHT_AREA) {
             const float* p = D->tri_p + (size_t)L.tri * 9;
             f3 a = mk3(p[3] - p[0], p[4] - p[1], p[5] - p[2]), b = mk3(p[6] - p[0], p[7] - p[1], p[8] - p[2]);
             float area = 0.5f * len3(cross3(a, b));

@@ -68,6 +68,19 @@ struct LightDistDev {   // dense restatement of SpatialLightDistribution's hash 
   const float* func_int;  // [n_vox]
 };
 
+struct EnvDev {           // one per LightSource "infinite" (lights/infinite.rs): level 0 of the map + the Distribution2D tables
+  float l2w[9], w2l[9];   // upper 3x3 of light_to_world / world_to_light
+  int32_t w, h;           // level 0 (powers of two); every lookup on the path has width 0 = the bilinear filter of level 0
+  int32_t nu, nv;         // Distribution2D resolution (2w x 2h)
+  const f4* texels;       // [h][w] rgb-
+  const float* func;      // [nv][nu]      conditional_v[v].func
+  const float* cdf;       // [nv][nu + 1]  conditional_v[v].cdf
+  const float* row_int;   // [nv]          conditional_v[v].func_int = marginal.func
+  const float* mcdf;      // [nv + 1]      marginal.cdf
+  float m_int;            // marginal.func_int
+  int32_t pad[3];
+};
+
 struct DScene {
   uint32_t n_channels;
   uint32_t n_tris, n_lights, n_materials, n_objects, n_instances;
@@ -94,6 +107,9 @@ struct DScene {
   const pt_light* lights;
   const uint32_t* light_sample_prefix;  // [n_lights + 1] prefix sums of pt_light.n_samples (directlighting "all": round -> light, sample)
   const pt_spot* spots;      // SpotLight extras, indexed by pt_light.tri
+  const EnvDev* envs;        // InfiniteAreaLight extras, indexed by pt_light.tri
+  const int32_t* inf_lights; // Scene.infinite_lights: indices into lights
+  uint32_t n_inf;
   const float* spectra;
   const float* alpha;        // per material: roughness_to_alpha applied on the HOST with libm logf: [n_materials][2]
   float xyz_w[180];

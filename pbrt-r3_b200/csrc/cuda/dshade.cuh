@@ -114,6 +114,68 @@ PT_HD f3 tri_geo_normal_for_sample(const DScene& S, int tri, f3 p0, f3 p1, f3 p2
   return n;
 }
 
+// ---- InfiniteAreaLight (lights/infinite.rs) --------------------------------------------------------------------------
+// MIPMap::lookup(st, 0.0) = triangle(0, st) (mipmap.rs:620-637, 711-767), s repeats, t clamps (mipmap.rs:1013-1026)
+PT_HD f3 env_lookup0(const EnvDev& E, float s_, float t_) {
+  float s = s_ * (float)E.w - 0.5f, t = t_ * (float)E.h - 0.5f;
+  int s0 = (int)floorf(s), t0 = (int)floorf(t);
+  float ds = s - (float)s0, dt = t - (float)t0;
+  int s1 = s0 + 1, t1 = t0 + 1;
+  s0 &= E.w - 1; s1 &= E.w - 1;
+  t0 = t0 < 0 ? 0 : (t0 > E.h - 1 ? E.h - 1 : t0);
+  t1 = t1 < 0 ? 0 : (t1 > E.h - 1 ? E.h - 1 : t1);
+  f3 a = xyz(ldg4(E.texels + (size_t)t0 * E.w + s0)) * ((1.0f - ds) * (1.0f - dt));
+  f3 b = xyz(ldg4(E.texels + (size_t)t1 * E.w + s0)) * ((1.0f - ds) * dt);
+  f3 c = xyz(ldg4(E.texels + (size_t)t0 * E.w + s1)) * (ds * (1.0f - dt));
+  f3 d = xyz(ldg4(E.texels + (size_t)t1 * E.w + s1)) * (ds * dt);
+  return a + b + c + d;
+}
+template <int NC>
+PT_HD Sp<NC> sp_from_rgb3(f3 c) {  // Spectrum::from_rgb for RGBSpectrum (the front end admits infinite lights with RGB spectra only)
+  Sp<NC> r = sp_const<NC>(0.0f);
+  r.c[0] = c.x; r.c[NC > 1 ? 1 : 0] = c.y; r.c[NC > 2 ? 2 : 0] = c.z;
+  return r;
+}
+PT_HD f3 mat3_vec(const float* m, f3 v) { return mk3(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z); }
+PT_HD float spherical_theta(f3 v) { return acosf(clampf(v.z, -1.0f, 1.0f)); }                             // geometry/misc.rs:96-104
+PT_HD float spherical_phi(f3 v) { float p = atan2f(v.y, v.x); return p < 0.0f ? p + 2.0f * PT_PI : p; }
+// InfiniteAreaLight::le (infinite.rs:110-121)
+template <int NC>
+PT_HD1 Sp<NC> env_le(const DScene& S, int li, f3 d) {
+  const EnvDev& E = S.envs[S.lights[li].tri];
+  f3 w = norm3(mat3_vec(E.w2l, d));
+  float s = spherical_phi(w) * (PT_INV_PI * 0.5f), t = spherical_theta(w) * PT_INV_PI;
+  return sp_from_rgb3<NC>(env_lookup0(E, s, t));
+}
+// Distribution1D::sample_continuous (distribution.rs:66-86) on cdf[0..n], func[0..n)
+PT_HD float dist1d_sample(const float* cdf, const float* func, float func_int, int n, float u, float* pdf, int* off) {
+  uint32_t first = 0, len = (uint32_t)n + 1u;
+  while (len > 0) {
+    uint32_t half = len >> 1, mid = first + half;
+    if (ldg(cdf + mid) <= u) { first = mid + 1; len -= half + 1; }
+    else len = half;
+  }
+  int o = first == 0 ? 0 : (int)first - 1;
+  if (o > n - 1) o = n - 1;
+  float c0 = ldg(cdf + o), c1 = ldg(cdf + o + 1);
+  float du = u - c0;
+  if (c1 - c0 > 0.0f) du /= c1 - c0;
+  *pdf = func_int > 0.0f ? ldg(func + o) / func_int : 0.0f;
+  *off = o;
+  return ((float)o + du) * (1.0f / (float)n);
+}
+// Distribution2D::pdf (distribution.rs:139-145) at (phi / 2 pi, theta / pi)
+PT_HD1 float env_pdf(const DScene& S, int li, f3 w_world) {  // InfiniteAreaLight::pdf_li (infinite.rs:168-185)
+  const EnvDev& E = S.envs[S.lights[li].tri];
+  f3 wi = mat3_vec(E.w2l, w_world);
+  float theta = spherical_theta(wi), phi = spherical_phi(wi);
+  float sin_theta = clampf(pt_sinf(theta), 0.0f, 1.0f);
+  if (sin_theta == 0.0f) return 0.0f;
+  float pu = phi * (PT_INV_PI * 0.5f) * (float)E.nu, pv = theta * PT_INV_PI * (float)E.nv;
+  int iu = pu > 0.0f ? (pu >= (float)E.nu ? E.nu - 1 : (int)pu) : 0, iv = pv > 0.0f ? (pv >= (float)E.nv ? E.nv - 1 : (int)pv) : 0;
+  return (ldg(E.func + (size_t)iv * E.nu + iu) / E.m_int) / (2.0f * PT_PI * PT_PI * sin_theta);
+}
+
 template <int NC>
 struct LightSampleD {
   Sp<NC> li;
@@ -122,12 +184,29 @@ struct LightSampleD {
   f3 sh_o, sh_d;  // VisibilityTester: p0.spawn_ray_to(p1)
 };
 
-// Light::sample_li for area (one triangle), point and distant lights
-template <int NC>
+// Light::sample_li for area (one triangle), point, spot, distant and - ENV, compiled in only where the scene has one -
+// infinite lights
+template <int NC, bool ENV = false>
 PT_HD1 bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSampleD<NC>* out) {
   const pt_light& L = S.lights[li];
   f3 lp, lperr = mk3(0.0f, 0.0f, 0.0f), ln = mk3(0.0f, 0.0f, 0.0f);
-  if (L.type == PT_LIGHT_AREA) {
+  if (ENV && L.type == PT_LIGHT_INFINITE) {  // infinite.rs:123-166
+    const EnvDev& E = S.envs[L.tri];
+    float pdf1, pdf0;
+    int v, uo;
+    float d1 = dist1d_sample(E.mcdf, E.row_int, E.m_int, E.nv, u.y, &pdf1, &v);
+    float d0 = dist1d_sample(E.cdf + (size_t)v * (E.nu + 1), E.func + (size_t)v * E.nu, ldg(E.row_int + v), E.nu, u.x, &pdf0, &uo);
+    float map_pdf = pdf0 * pdf1;
+    if (map_pdf <= 0.0f) return false;
+    float theta = d1 * PT_PI, phi = d0 * 2.0f * PT_PI;
+    float cos_theta = pt_cosf(theta), sin_theta = clampf(pt_sinf(theta), 0.0f, 1.0f);
+    float cos_phi = pt_cosf(phi), sin_phi = pt_sinf(phi);
+    f3 wi = mat3_vec(E.l2w, mk3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta));
+    out->wi = wi;
+    out->pdf = sin_theta == 0.0f ? 0.0f : map_pdf / (2.0f * PT_PI * PT_PI * sin_theta);
+    out->li = sp_from_rgb3<NC>(env_lookup0(E, d0, d1));
+    lp = it.p + wi * (2.0f * S.world_radius);
+  } else if (L.type == PT_LIGHT_AREA) {
     f3 p0, p1, p2;
     tri_verts(S, L.tri, &p0, &p1, &p2);
     float su0 = sqrtf(u.x);
@@ -192,8 +271,10 @@ PT_HD1 bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSa
 }
 
 // Light::pdf_li for the area light's triangle = Shape::pdf_from (re-intersect that one triangle)
+template <bool ENV = false>
 PT_HD1 float light_pdf_li(const DScene& S, int li, const RefPt& it, f3 wi) {
   const pt_light& L = S.lights[li];
+  if (ENV && L.type == PT_LIGHT_INFINITE) return env_pdf(S, li, wi);
   if (L.type != PT_LIGHT_AREA) return 0.0f;
   f3 o = offset_origin(it.p, it.perr, it.n, wi);
   f3 p0, p1, p2;
@@ -377,7 +458,9 @@ PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int
 }
 
 // One iteration of PathIntegrator::li's loop body after scene.intersect (path.rs:87-233) for path slot i.
-template <int NC, int CLS>
+// ENV: the scene has infinite lights (their code is compiled into a second set of shade kernels, so that scenes without
+// one run the same kernels as before): escaped rays reach this stage (class CL_NONE) and add Le of the environment.
+template <int NC, int CLS, bool ENV = false>
 PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsigned long long* vertex_counter) {
   constexpr int CM = cls_cm(CLS), MT = cls_mt(CLS);
   const uint32_t cap = W.cap;
@@ -406,6 +489,9 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   }
   if (bounces == 0 || specular_bounce) {
     if (found) L = L + beta * surface_le<NC>(S, si, -rd);
+    else if (ENV) {  // path.rs:92-95: every infinite light's Le along the escaped ray
+      for (uint32_t k = 0; k < S.n_inf; k++) L = L + beta * env_le<NC>(S, ldg(S.inf_lights + k), rd);
+    }
   }
   if (!found || bounces >= S.integrator.max_depth) { st_store<NC>(W.L, cap, i, L); return; }
   BsdfD B;
@@ -454,9 +540,9 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
       f2 u_light = get2d(S, st);
       f2 u_scat = get2d(S, st);
       const pt_light& LT = S.lights[ln];
-      bool delta = LT.type != PT_LIGHT_AREA;
+      bool delta = LT.type != PT_LIGHT_AREA && !(ENV && LT.type == PT_LIGHT_INFINITE);
       LightSampleD<NC> ls;
-      if (light_sample<NC>(S, ln, ref, u_light, &ls)) {
+      if (light_sample<NC, ENV>(S, ln, ref, u_light, &ls)) {
 #ifdef PT_DEBUG_PRINT
         fprintf(stderr, "[hc] ls pdf %g li %g wi=(%g %g %g) sh_o=(%.9g %.9g %.9g) sh_d=(%.9g %.9g %.9g)\n", ls.pdf, ls.li.c[0], ls.wi.x, ls.wi.y, ls.wi.z, ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, ls.sh_d.x, ls.sh_d.y, ls.sh_d.z);
 #endif
@@ -492,12 +578,13 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
             float weight = 1.0f;
             bool go = true;
             if (!(stype & F_SPEC)) {
-              float lp = light_pdf_li(S, ln, ref, wi2);
+              float lp = light_pdf_li<ENV>(S, ln, ref, wi2);
               if (lp == 0.0f) go = false;
               else weight = power_heuristic1(pdf2, lp);
             }
             if (go) {
-              Sp<NC> li = sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
+              // an area light's Le is its constant; an infinite light's is looked up along wi (the ray must then ESCAPE, mis_resolve)
+              Sp<NC> li = (ENV && LT.type == PT_LIGHT_INFINITE) ? env_le<NC>(S, ln, wi2) : sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
               Sp<NC> ld = f * li * sp_const<NC>(1.0f) * (weight / pdf2);
               st_store<NC>(W.pendB, cap, i, beta * (ld / light_pdf));
               f3 o = offset_origin(si.p, si.perr, si.n, wi2);
@@ -687,8 +774,11 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
   SurfD si;
   BsdfD B;
   B.n = -1;
-  if ((int)fbits(h4.w) < 0) need_pop = true;  // the ray left the scene: li = sum of Light::le = 0 (no infinite lights)
-  else {
+  if ((int)fbits(h4.w) < 0) {  // the ray left the scene: li = sum of Light::le (directlighting.rs:112-122, whitted.rs:86-96)
+    need_pop = true;
+    if (fresh)
+      for (uint32_t k = 0; k < S.n_inf; k++) L = L + beta * env_le<NC>(S, ldg(S.inf_lights + k), xyz(rd4));
+  } else {
     si = make_surface(S, (int)fbits(h4.w), inst, xyz(ro4), xyz(rd4), rtime, h4.x, h4.y, h4.z);
     make_bsdf<NC, -1, false>(S, si, &B);
     if (B.n < 0) {  // no BSDF: whitted returns zero (whitted.rs:84), directlighting follows the ray at the same depth (:108-110)
@@ -750,7 +840,7 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
         round++;
         const pt_light& LT = S.lights[ln];
         LightSampleD<NC> ls;
-        const bool ok = light_sample<NC>(S, ln, ref, u_light, &ls);
+        const bool ok = light_sample<NC, true>(S, ln, ref, u_light, &ls);
         if (whitted) {  // whitted.rs:61-79: BSDF over all lobes, shading normal, no MIS
           if (ok && !(ls.pdf <= 0.0f || sp_black(ls.li))) {
             Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, F_ALL);
@@ -765,7 +855,7 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
           continue;
         }
         // estimate_direct_surface (sample_lights.rs:330-453), as in shade_body
-        const bool delta = LT.type != PT_LIGHT_AREA;
+        const bool delta = LT.type != PT_LIGHT_AREA && LT.type != PT_LIGHT_INFINITE;
         if (ok && ls.pdf > 0.0f && !sp_black(ls.li)) {
           Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
           float spdf = bsdf_pdf(B, si.wo, ls.wi, NONSPEC);
@@ -791,12 +881,12 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
               float weight = 1.0f;
               bool go = true;
               if (!(stype & F_SPEC)) {
-                float lp = light_pdf_li(S, ln, ref, wi2);
+                float lp = light_pdf_li<true>(S, ln, ref, wi2);
                 if (lp == 0.0f) go = false;
                 else weight = power_heuristic1(pdf2, lp);
               }
               if (go) {
-                Sp<NC> li = sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
+                Sp<NC> li = LT.type == PT_LIGHT_INFINITE ? env_le<NC>(S, ln, wi2) : sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
                 Sp<NC> ld = f * li * sp_const<NC>(1.0f) * (weight / pdf2);
                 st_store<NC>(W.pendB, cap, i, beta * (ld / divisor));
                 f3 o = offset_origin(si.p, si.perr, si.n, wi2);
@@ -901,7 +991,9 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
 template <int NC>
 PT_HD void mis_resolve(const DScene& S, WaveState& W, uint32_t i, const HitD& h, bool found, f3 rd) {
   bool keep = false;
-  if (found && h.instance < 0) {
+  if (!found) {  // light.le(ray) (sample_lights.rs:443-445): non-zero for an infinite light only
+    if (S.n_inf != 0u) keep = S.lights[W.mis_light[i]].type == PT_LIGHT_INFINITE;
+  } else if (h.instance < 0) {
     int ln = W.mis_light[i];
     if (ldg(S.tri_light + h.tri) == ln) {
       const pt_light& LT = S.lights[ln];

@@ -258,10 +258,10 @@ struct WaveIO {
       W.hit[i] = mk4(T.hit.b0, T.hit.b1, T.hit.b2, bitsf((uint32_t)tri));
       if (INST) W.hit_inst[i] = T.found ? T.hit.instance : -1;
       if (T.found) W.ray_o[i].w = T.ray_tmax;
-      // A ray that leaves the scene ends its path (no infinite lights on this path: path.rs:93-104 adds nothing), and the
+      // A ray that leaves the scene ends its path (without infinite lights path.rs:93-104 adds nothing), and the
       // pending light / MIS terms of its last vertex are folded into L by k_finish in the same order (L + a) + b that
-      // the shade stage would use: nothing to shade.
-      if (tri < 0) return;
+      // the shade stage would use: nothing to shade.  With infinite lights the escaped ray goes to class CL_NONE for Le.
+      if (tri < 0 && S.n_inf == 0u) return;
       // bin the path by shading class for the per-material shade kernels (warp-aggregated per class)
       const int cls = shade_class(S, tri, (int)(W.flags[i] >> 8));
       uint32_t slot;
@@ -559,7 +559,7 @@ __global__ void k_voxel_contrib(const __grid_constant__ DScene S, float* func, u
       it.n = mk3(0.0f, 0.0f, 0.0f);
       f2 u = mk2(radical_inverse_base(7u, i), radical_inverse_base(11u, i));
       LightSampleD<NC> ls;
-      if (light_sample<NC>(S, (int)j, it, u, &ls))
+      if (light_sample<NC, true>(S, (int)j, it, u, &ls))
         if (ls.pdf > 0.0f) contrib += sp_y(S, ls.li) / ls.pdf;
     }
     func[id] = contrib;

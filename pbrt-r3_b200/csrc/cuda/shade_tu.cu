@@ -11,23 +11,25 @@
 namespace ptd {
 
 // One shade kernel per shading class; the bin size is read on the device (no host round trip between trace and shade).
-template <int NC, int CLS>
+// ENV = the scene has infinite lights (LightSource "infinite"): a second set of kernels, so that every other scene runs
+// exactly the code it ran before the environment light existed.
+template <int NC, int CLS, bool ENV>
 __global__ void __launch_bounds__(PT_SHADE_BLOCK, NC == 3 ? PT_SHADE_MINBLOCKS : PT_SHADE_MINBLOCKS_SPECTRAL) k_shade(const __grid_constant__ DScene S, WaveState W, Queues Q, unsigned long long* vertex_counter) {
   const uint32_t n = Q.counts[8 + CLS];
   const uint32_t* bin = Q.bins + (size_t)CLS * W.cap;
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) shade_body<NC, CLS>(S, W, Q, bin[k], vertex_counter);
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) shade_body<NC, CLS, ENV>(S, W, Q, bin[k], vertex_counter);
 }
 
 
-template <int NC>
+template <int NC, bool ENV>
 static void launch_shade_nc(int cls, int grid, cudaStream_t stream, const DScene& S, const WaveState& W, const Queues& Q, unsigned long long* vc) {
   switch (cls) {
-    case CL_NONE: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_NONE>)(S, W, Q, vc); break;
-    case CL_MATTE: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_MATTE>)(S, W, Q, vc); break;
-    case CL_PLASTIC: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_PLASTIC>)(S, W, Q, vc); break;
-    case CL_GLASS: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_GLASS>)(S, W, Q, vc); break;
-    case CL_METAL: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_METAL>)(S, W, Q, vc); break;
-    case CL_MIRROR: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_MIRROR>)(S, W, Q, vc); break;
+    case CL_NONE: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_NONE, ENV>)(S, W, Q, vc); break;
+    case CL_MATTE: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_MATTE, ENV>)(S, W, Q, vc); break;
+    case CL_PLASTIC: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_PLASTIC, ENV>)(S, W, Q, vc); break;
+    case CL_GLASS: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_GLASS, ENV>)(S, W, Q, vc); break;
+    case CL_METAL: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_METAL, ENV>)(S, W, Q, vc); break;
+    case CL_MIRROR: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_MIRROR, ENV>)(S, W, Q, vc); break;
     default: break;
   }
 }
@@ -36,6 +38,8 @@ static void launch_shade_nc(int cls, int grid, cudaStream_t stream, const DScene
 
 void launch_shade(int n_channels, int cls, int grid, cudaStream_t stream, const ptd::DScene& S, const ptd::WaveState& W, const ptd::Queues& Q,
                   unsigned long long* vertex_counter) {
-  if (n_channels == 3) ptd::launch_shade_nc<3>(cls, grid, stream, S, W, Q, vertex_counter);
-  else ptd::launch_shade_nc<PT_NCS>(cls, grid, stream, S, W, Q, vertex_counter);
+  if (n_channels == 3) {
+    if (S.n_inf != 0u) ptd::launch_shade_nc<3, true>(cls, grid, stream, S, W, Q, vertex_counter);
+    else ptd::launch_shade_nc<3, false>(cls, grid, stream, S, W, Q, vertex_counter);
+  } else ptd::launch_shade_nc<PT_NCS, false>(cls, grid, stream, S, W, Q, vertex_counter);  // infinite lights: RGB only (front end)
 }

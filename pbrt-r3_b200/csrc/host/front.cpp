@@ -33,6 +33,8 @@ struct pt_host_scene {
   std::vector<float> spectra;
   std::vector<float> tri_p, tri_n, tri_uv, tri_s;
   std::vector<pt_spot> spots;
+  std::vector<pt_envmap> envmaps;
+  std::vector<std::vector<float>> env_texels;  // storage behind pt_envmap.texels
   std::vector<uint32_t> tri_flags;
   std::vector<int32_t> tri_material, tri_light;
   std::vector<std::vector<int32_t>> obj_prims;  // object 0 = top level
@@ -635,10 +637,74 @@ struct Builder {
       l.tri = (int32_t)hs->spots.size();
       l.v[0] = p.x; l.v[1] = p.y; l.v[2] = p.z;
       hs->spots.push_back(sp);
+    } else if (name == "infinite" || name == "exinfinite") {  // lights/infinite.rs:271-295 (create_light.rs: both names)
+      if (spec.n_channels() != 3) throw ParseError("LightSource \"infinite\" is only supported with RGB spectra on the GPU path");
+      std::vector<float> L = one_spectrum(ps, "L", 1.0f), sc = one_spectrum(ps, "scale", 1.0f);
+      for (size_t k = 0; k < L.size(); k++) L[k] = L[k] * sc[k];
+      std::string fn = ps.one_string("mapname", "");
+      l.n_samples = ps.one_int("samples", ps.one_int("nsamples", 1));
+      if (pt_current_options().quick_render) l.n_samples = std::max(l.n_samples / 4, 1);
+      pt_envmap em;
+      memset(&em, 0, sizeof(em));
+      std::vector<float> tex;
+      if (fn.empty()) { em.width = em.height = 1; tex = {L[0], L[1], L[2]}; }
+      else {  // make_mipmap (infinite.rs:47-58): texels clamped at zero, times L * scale
+        std::string path = (fn[0] == '/') ? fn : (cur_dir.empty() ? fn : cur_dir + "/" + fn);
+        std::string err = load_pfm(path, &tex, &em.width, &em.height);
+        if (!err.empty()) throw ParseError("LightSource \"infinite\" mapname \"" + path + "\": " + err);
+        if ((em.width & (em.width - 1)) || (em.height & (em.height - 1)))
+          throw ParseError("LightSource \"infinite\": only power-of-two environment maps are supported on the GPU path (MIPMap resampling is not built)");
+        for (size_t i = 0; i < tex.size(); i++) tex[i] = std::max(tex[i], 0.0f) * L[i % 3];
+      }
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) { em.l2w[3 * r + c] = ctm.m.m[4 * r + c]; em.w2l[3 * r + c] = ctm.minv.m[4 * r + c]; }
+      l.type = PT_LIGHT_INFINITE;
+      l.spectrum = add_spectrum(L);
+      l.tri = (int32_t)hs->envmaps.size();
+      hs->envmaps.push_back(em);
+      hs->env_texels.push_back(std::move(tex));
     } else {
-      throw ParseError("LightSource \"" + name + "\" is not supported on the GPU path (point, spot, distant, area lights only)");
+      throw ParseError("LightSource \"" + name + "\" is not supported on the GPU path (point, spot, distant, infinite, area lights only)");
     }
     hs->lights.push_back(l);
+  }
+
+  // read_image for ".pfm" (core/imageio/read_image_pfm.rs:25-106): "PF" / "Pf", width, height, scale (negative = little
+  // endian), rows bottom to top in the file -> row 0 = top here, values times |scale|, grey replicated to RGB
+  static std::string load_pfm(const std::string& path, std::vector<float>* rgb, int32_t* w, int32_t* h) {
+    if (path.size() < 4 || path.substr(path.size() - 4) != ".pfm") return "only .pfm maps are supported on the GPU path";
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return "cannot open file";
+    std::string magic;
+    long long width = 0, height = 0;
+    float scale = 0.0f;
+    f >> magic >> width >> height >> scale;
+    if (!f || (magic != "PF" && magic != "Pf") || width <= 0 || height <= 0 || width > 65536 || height > 65536) return "bad PFM header";
+    f.get();  // the single whitespace after the scale
+    const int nc = magic == "PF" ? 3 : 1;
+    const bool le = scale < 0.0f;
+    std::vector<unsigned char> raw((size_t)width * height * nc * 4);
+    f.read(reinterpret_cast<char*>(raw.data()), (std::streamsize)raw.size());
+    if ((size_t)f.gcount() != raw.size()) return "truncated PFM data";
+    rgb->assign((size_t)width * height * 3, 0.0f);
+    const float a = fabsf(scale);
+    size_t k = 0;
+    for (long long y = 0; y < height; y++) {
+      const long long yy = height - y - 1;
+      for (long long x = 0; x < width; x++)
+        for (int c = 0; c < nc; c++, k++) {
+          const unsigned char* q = raw.data() + 4 * k;
+          uint32_t bits = le ? ((uint32_t)q[0] | (uint32_t)q[1] << 8 | (uint32_t)q[2] << 16 | (uint32_t)q[3] << 24)
+                             : ((uint32_t)q[3] | (uint32_t)q[2] << 8 | (uint32_t)q[1] << 16 | (uint32_t)q[0] << 24);
+          float v;
+          memcpy(&v, &bits, 4);
+          if (a != 1.0f) v *= a;
+          float* dst = rgb->data() + 3 * ((size_t)yy * width + x);
+          if (nc == 3) dst[c] = v; else dst[0] = dst[1] = dst[2] = v;
+        }
+    }
+    *w = (int32_t)width; *h = (int32_t)height;
+    return "";
   }
 
   // ---- directives -----------------------------------------------------------------------------
@@ -1019,6 +1085,9 @@ struct Builder {
     D.n_emitters_only = (uint32_t)hs->emitters_only.size();
     D.n_spots = (uint32_t)hs->spots.size();
     D.spots = hs->spots.data();
+    for (size_t k = 0; k < hs->envmaps.size(); k++) hs->envmaps[k].texels = hs->env_texels[k].data();
+    D.n_envmaps = (uint32_t)hs->envmaps.size();
+    D.envmaps = hs->envmaps.data();
     D.lights = all.data();
   }
 };

@@ -207,6 +207,14 @@ def test_tree_integrators(P):
     check_tree(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
 
 
+def test_infinite_light(P, tmp_path):
+    """LightSource "infinite" (lights/infinite.rs:108-185; Distribution2D, MIPMap level 0): constant and mapped environment,
+    path / directlighting / whitted, spatial and power light distributions.  Same rays as the oracle (equal counters); acos /
+    atan2 are CUDA's on the device, so the lookup coordinates and MIS pdfs differ by a few ulp: per-sample rtol 1e-4."""
+    from test_hostcheck import check_env
+    check_env(P, tmp_path, n=20000, res=72, spp=4, wave_paths=3000, threads=0, rtol=1e-4, frac=0.9995)
+
+
 def test_one_sided_triangles_bit_exact(P, pair):
     """Back-face culling of one-sided meshes (triangle.rs:236-246), with and without ReverseOrientation."""
     from test_hostcheck import one_sided_scene

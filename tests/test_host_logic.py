@@ -211,6 +211,31 @@ def test_front_end_tree_integrators(P):
         lib.pt_set_options(P.capi.pt_options(0, 0))
 
 
+def test_front_end_infinite_light(P, tmp_path):
+    from test_hostcheck import write_pfm
+    img = np.arange(4 * 8 * 3, dtype=np.float32).reshape(4, 8, 3) - 5.0
+    write_pfm(str(tmp_path / "e.pfm"), img)
+    base = 'Camera "perspective"\nWorldBegin\nRotate 90 0 0 1\nLightSource "infinite" "rgb L" [2 1 0.5] %s\nWorldEnd\n'
+    hs = P.HostScene.parse_string(base % '"integer samples" [8]')
+    d = hs.desc
+    assert (d.n_lights, d.n_envmaps, d.lights[0].type, d.lights[0].tri, d.lights[0].n_samples) == (1, 1, P.capi.PT_LIGHT_INFINITE, 0, 8)   # infinite.rs:279
+    e = d.envmaps[0]
+    assert (e.width, e.height) == (1, 1) and [e.texels[k] for k in range(3)] == [2.0, 1.0, 0.5]                      # make_mipmap without a map (:59-64)
+    assert np.allclose(np.array(e.l2w[:9]).reshape(3, 3), [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-7)             # the CTM's rotation
+    assert np.allclose(np.array(e.l2w[:9]).reshape(3, 3).T, np.array(e.w2l[:9]).reshape(3, 3), atol=1e-7)
+    hs = P.HostScene.parse_string(base % ('"string mapname" ["%s"]' % (tmp_path / "e.pfm")))
+    e = hs.desc.envmaps[0]
+    assert (e.width, e.height) == (8, 4)
+    tex = np.array([e.texels[k] for k in range(4 * 8 * 3)], np.float32).reshape(4, 8, 3)
+    assert np.array_equal(tex, np.maximum(img, 0) * np.array([2, 1, 0.5], np.float32))                               # clamped at 0, times L (:52-56); row 0 = top
+    write_pfm(str(tmp_path / "npot.pfm"), np.ones((3, 8, 3), np.float32))
+    for bad in ('"string mapname" ["%s"]' % (tmp_path / "npot.pfm"), '"string mapname" ["%s"]' % (tmp_path / "missing.pfm"), '"string mapname" ["x.exr"]'):
+        with pytest.raises(P.PbrtError):
+            P.HostScene.parse_string(base % bad)
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % "", spectrum="sampled")
+
+
 def test_front_end_aov_integrator(P):
     base = 'Camera "perspective"\nIntegrator "aov" %s\nWorldBegin\nWorldEnd\n'
     d = P.HostScene.parse_string(base % "").desc.integrator
@@ -250,7 +275,7 @@ def test_front_end_instances(P):
 
 
 def test_front_end_errors(P):
-    for bad in ['Shape "sphere"', 'WorldBegin\nLightSource "infinite"', 'Sampler "stratified"\nWorldBegin\nWorldEnd', 'Bogus 1 2 3']:
+    for bad in ['Shape "sphere"', 'WorldBegin\nLightSource "goniometric"', 'Sampler "stratified"\nWorldBegin\nWorldEnd', 'Bogus 1 2 3']:
         with pytest.raises(P.PbrtError):
             P.HostScene.parse_string('Camera "perspective"\n' + bad + "\n")
 

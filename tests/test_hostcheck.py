@@ -337,6 +337,71 @@ def test_hostcheck_tree_integrators(HC):
     check_tree(HC)
 
 
+def write_pfm(path, img):
+    """RGB float image, row 0 = top, as a little-endian PFM (rows bottom to top in the file)"""
+    h, w, _ = img.shape
+    with open(path, "wb") as f:
+        f.write(b"PF\n%d %d\n-1.0\n" % (w, h))
+        f.write(np.ascontiguousarray(img[::-1], "<f4").tobytes())
+
+
+def env_scene(P, tmpdir, mapped, integrator='"path"', res=24, spp=4, sampler="halton", strategy=None):
+    """Cornell box with mixed materials (open towards the camera) inside an environment light: constant, or a 16 x 8
+    lat-long map with one bright texel region, rotated; the box's own area light stays."""
+    txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", sampler=sampler, maxdepth=5)
+    light = 'AttributeBegin\nRotate -70 1 0 0\nRotate 25 0 0 1\nLightSource "infinite" "rgb L" [0.5 0.6 0.9] "rgb scale" [1.5 1 1]%s\nAttributeEnd\n'
+    if mapped:
+        rng = np.random.RandomState(3)
+        img = rng.uniform(0.05, 0.6, (8, 16, 3)).astype(np.float32)
+        img[1:3, 4:7] = [9.0, 7.0, 4.0]       # a sun
+        img[6, 2] = -1.0                      # negative texels are clamped (infinite.rs:54-55)
+        write_pfm(os.path.join(str(tmpdir), "env.pfm"), img)
+        light = light % (' "string mapname" ["%s"]' % os.path.join(str(tmpdir), "env.pfm"))
+    else:
+        light = light % ""
+    txt = txt.replace("WorldEnd", light + "WorldEnd")
+    head, rest = txt.split('Integrator "path"', 1)
+    extra = ' "string lightsamplestrategy" ["%s"]' % strategy if strategy else ""
+    return head + "Integrator " + integrator + extra + rest
+
+
+ENV_CASES = [dict(mapped=False), dict(mapped=True), dict(mapped=True, sampler="sobol", strategy="power"),
+             dict(mapped=True, integrator='"directlighting" "string strategy" ["one"]'), dict(mapped=True, integrator='"whitted"'),
+             dict(mapped=False, integrator='"directlighting"')]
+
+
+def check_env(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=1e-5, frac=1.0):
+    """LightSource "infinite" (lights/infinite.rs): Le of escaped rays, Distribution2D importance sampling + MIS against the
+    oracle's own MIPMap / Distribution2D restatement; same rays (equal counters).  On the GPU acos / atan2 are CUDA's (a few
+    ulp in the lookup coordinates and the MIS pdf): rtol / frac are the caller's."""
+    import oracle_api
+    for kw in ENV_CASES:
+        kw = dict(dict(res=res, spp=spp), **kw)
+        hs = P.HostScene.parse_string(env_scene(P, tmpdir, **kw))
+        assert hs.desc.n_envmaps == 1 and hs.desc.lights[hs.desc.n_lights - 1].type == P.capi.PT_LIGHT_INFINITE
+        assert (hs.desc.envmaps[0].width, hs.desc.envmaps[0].height) == ((16, 8) if kw["mapped"] else (1, 1))
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        sb = hs.desc.film.sample_bounds
+        rng = np.random.RandomState(10)
+        pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+        sn = rng.randint(0, kw["spp"], n).astype(np.int32)
+        la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+        ok = (np.abs(la - lb) <= rtol * np.maximum(np.abs(lb), 1e-3)).all(1)
+        assert ok.mean() >= frac, (kw, ok.mean(), la[~ok][:3], lb[~ok][:3])
+        assert (lb > 0).all(1).mean() > 0.5          # the environment lights most samples
+        rgb, st = sc.render(collect_counters=1, wave_paths=wave_paths)
+        ref, so = orc.render(threads=threads)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-4, kw
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[k] == so[k], (kw, k, st[k], so[k])
+        one, _ = sc.render(wave_paths=wave_paths, wave_segments=1)
+        assert np.array_equal(one, rgb), kw
+
+
+def test_hostcheck_infinite_light(HC, tmp_path):
+    check_env(HC, tmp_path)
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
