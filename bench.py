@@ -264,17 +264,22 @@ def _main(out):
             dev_ms += r0.elapsed_time(r1)
         return st, dev_ms / 1e3
 
+    # the host image every e2e step is read back into: allocated once, page-locked (like the pinned staging copy of the
+    # scene that pt_scene_reupload sends); only rank 0 resolves the film
+    H_img, W_img, _ = hs.image_shape
+    rgb_host = torch.empty((H_img, W_img, 3), dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+
     def step_e2e():
         nb = sc.reupload()
         if world == 1:
-            rgb, st = sc.render(spp_begin=s0, spp_end=s1, **wopts)
+            rgb, st = sc.render(out=rgb_host, spp_begin=s0, spp_end=s1, **wopts)
             return st, nb, rgb.nbytes
         ptr, npx, st = render_partial()
         film = D.film_tensor(ptr, npx, dev)
         D.reduce_film(film, dst=0)
         d2h = 0
         if rank == 0:
-            rgb = sc.film_resolve(film.data_ptr())
+            rgb = sc.film_resolve(film.data_ptr(), out=rgb_host)
             d2h = rgb.nbytes
         return st, nb, d2h
 

@@ -188,7 +188,7 @@ typedef struct pt_integrator { /* integrators/path.rs:252-271, integrators/aov.r
   float aov_scale;
   int32_t ao_samples;         /* ambientocclusion "nsamples" (default 64; 1 under --quick), ao.rs:124-131 */
   int32_t ao_cos_sample;      /* ambientocclusion "cossample" (default true) */
-  int32_t direct_strategy;    /* pt_direct_strategy (directlighting only) */
+  int32_t direct_strategy;    /* enum pt_direct_strategy; directlighting only */
 } pt_integrator;
 
 typedef struct pt_accel {     /* accelerators/bvh/create_bvh_accelerator.rs:9-28 */

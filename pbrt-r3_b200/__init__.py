@@ -154,10 +154,19 @@ class Scene:
             setattr(o, k, int(v))
         return o
 
-    def render(self, **opts):
-        """Integrator::render: returns (rgb[H,W,3] float32 host array, stats dict)."""
+    def _out(self, out):
+        """The host RGB buffer pt_render / pt_film_resolve write: a fresh array, or the caller's own [H,W,3] float32 C-contiguous
+        one (the reference's Film keeps one RGB buffer for its life; a page-locked buffer makes the read-back a plain DMA)."""
         H, W, _ = self.host.image_shape
-        rgb = np.zeros((H, W, 3), np.float32)
+        if out is None:
+            return np.zeros((H, W, 3), np.float32)
+        if out.dtype != np.float32 or out.shape != (H, W, 3) or not out.flags["C_CONTIGUOUS"]:
+            raise PbrtError("out must be a C-contiguous float32 array of shape %r" % ((H, W, 3),))
+        return out
+
+    def render(self, out=None, **opts):
+        """Integrator::render: returns (rgb[H,W,3] float32 host array, stats dict)."""
+        rgb = self._out(out)
         st = pt_stats()
         o = self._opts(**opts)
         _check(self._lib, self._lib.pt_render(self._h, C.byref(o), _p(rgb, C.c_float), C.byref(st)), "pt_render")
@@ -172,9 +181,8 @@ class Scene:
         H, W, _ = self.host.image_shape
         return ptr.value, H * W, st.as_dict()
 
-    def film_resolve(self, dev_ptr=None):
-        H, W, _ = self.host.image_shape
-        rgb = np.zeros((H, W, 3), np.float32)
+    def film_resolve(self, dev_ptr=None, out=None):
+        rgb = self._out(out)
         _check(self._lib, self._lib.pt_film_resolve(self._h, C.c_void_p(dev_ptr or 0), _p(rgb, C.c_float)), "pt_film_resolve")
         return rgb
 
