@@ -36,7 +36,10 @@ enum pt_material_type {       /* reference src/materials/create_material.rs:20-7
   PT_MAT_PLASTIC = 1,         /* materials/plastic.rs:32-70 */
   PT_MAT_GLASS = 2,           /* materials/glass.rs:47-110  */
   PT_MAT_METAL = 3,           /* materials/metal.rs:52-84   */
-  PT_MAT_MIRROR = 4           /* materials/mirror.rs:20-41  */
+  PT_MAT_MIRROR = 4,          /* materials/mirror.rs:20-41  */
+  PT_MAT_UBER = 5,            /* materials/uber.rs:73-128: opacity pass-through + diffuse + glossy + specular reflection / transmission */
+  PT_MAT_SUBSTRATE = 6,       /* materials/substrate.rs:33-60: FresnelBlend */
+  PT_MAT_TRANSLUCENT = 7      /* materials/translucent.rs:37-100: diffuse + glossy reflection and transmission, eta 1.5 */
 };
 
 enum pt_light_type {          /* reference src/lights/create_light.rs:13-54 */
@@ -83,14 +86,16 @@ enum pt_spectrum_kind {       /* core/spectrum/mod.rs:16-20 */
  * pt_scene_desc.spectra (n_channels floats each). */
 typedef struct pt_material {
   int32_t type;               /* pt_material_type */
-  int32_t kd;                 /* matte Kd | plastic Kd                     (spectrum index) */
-  int32_t ks;                 /* plastic Ks | glass Kt | metal k           (spectrum index) */
-  int32_t kr;                 /* mirror Kr | glass Kr | metal eta          (spectrum index) */
+  int32_t kd;                 /* matte Kd | plastic Kd | uber / substrate / translucent Kd       (spectrum index) */
+  int32_t ks;                 /* plastic Ks | glass Kt | metal k | uber / substrate / translucent Ks (spectrum index) */
+  int32_t kr;                 /* mirror Kr | glass Kr | metal eta | uber Kr | translucent reflect  (spectrum index) */
   float sigma;                /* matte sigma (degrees)                                      */
-  float uroughness;           /* plastic/metal roughness (also u), glass uroughness         */
-  float vroughness;           /* glass/metal vroughness                                      */
-  float eta;                  /* glass index                                                 */
+  float uroughness;           /* plastic/metal/uber/translucent roughness (also u), glass/substrate uroughness */
+  float vroughness;           /* glass/metal/uber/substrate vroughness                       */
+  float eta;                  /* glass / uber index                                          */
   int32_t remap_roughness;    /* bool                                                        */
+  int32_t kt;                 /* uber Kt | translucent transmit            (spectrum index, else -1) */
+  int32_t opacity;            /* uber opacity                              (spectrum index, else -1) */
 } pt_material;
 
 /* A light.  Area lights reference a top-level triangle (its index in tri_*). */

@@ -230,7 +230,9 @@ struct TRDist {
 };
 
 // ---- BxDFs ------------------------------------------------------------------------------------------
-enum BxKind { BX_LAMBERT, BX_OREN_NAYAR, BX_SPEC_REFL, BX_SPEC_TRANS, BX_FRESNEL_SPEC, BX_MF_REFL, BX_MF_TRANS };
+enum BxKind { BX_LAMBERT, BX_OREN_NAYAR, BX_SPEC_REFL, BX_SPEC_TRANS, BX_FRESNEL_SPEC, BX_MF_REFL, BX_MF_TRANS,
+              BX_LAMBERT_T /* lambertian.rs:59-99 */, BX_FRESNEL_BLEND /* fresnel_blend.rs: r = Rd, t = Rs */ };
+inline Float pow5(Float v) { return powf(v, 5.0f); }  // fresnel_blend.rs:13-15
 template <int NC>
 struct BxDF {
   int kind;
@@ -247,6 +249,8 @@ struct BxDF {
       case BX_SPEC_TRANS: return BSDF_TRANSMISSION | BSDF_SPECULAR;
       case BX_FRESNEL_SPEC: return BSDF_REFLECTION | BSDF_TRANSMISSION | BSDF_SPECULAR;
       case BX_MF_REFL: return BSDF_REFLECTION | BSDF_GLOSSY;
+      case BX_LAMBERT_T: return BSDF_TRANSMISSION | BSDF_DIFFUSE;
+      case BX_FRESNEL_BLEND: return BSDF_REFLECTION | BSDF_GLOSSY;
       default: return BSDF_TRANSMISSION | BSDF_GLOSSY;
     }
   }
@@ -292,6 +296,16 @@ struct BxDF {
                          (cti * cto * sqrt_denom * sqrt_denom));
         return ((Spec<NC>(1.0f) - F) * t) * dd;
       }
+      case BX_LAMBERT_T: return t * INV_PI;
+      case BX_FRESNEL_BLEND: {  // fresnel_blend.rs:37-57
+        Spec<NC> diffuse = r * (Spec<NC>(1.0f) - t) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wi))) * (1.0f - pow5(1.0f - 0.5f * abs_cos_theta(wo))) * (28.0f / (23.0f * PI));
+        Vec3 wh = wi + wo;
+        if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return Spec<NC>();
+        wh = normalize(wh);
+        Spec<NC> schlick = t + (Spec<NC>(1.0f) - t) * pow5(1.0f - dot(wi, wh));
+        Spec<NC> specular = schlick * (dist.d(wh) / (4.0f * abs_dot(wi, wh) * rmax(abs_cos_theta(wi), abs_cos_theta(wo))));
+        return diffuse + specular;
+      }
       default: return Spec<NC>();  // specular lobes
     }
   }
@@ -314,6 +328,13 @@ struct BxDF {
         Float dwh_dwi = fabsf((eta * eta * wi_wh) / (sqrt_denom * sqrt_denom));
         return dist.pdf(wo, wh) * dwh_dwi;
       }
+      case BX_LAMBERT_T: return !same_hemisphere(wo, wi) ? abs_cos_theta(wi) : 0.0f;  // lambertian.rs:80-86: no 1 / pi
+      case BX_FRESNEL_BLEND: {  // fresnel_blend.rs:92-103
+        if (!same_hemisphere(wo, wi)) return 0.0f;
+        Vec3 wh = normalize(wo + wi);
+        if (dot(wo, wh) < 0.0f) return 0.0f;
+        return 0.5f * (abs_cos_theta(wi) * INV_PI + dist.pdf(wo, wh) / (4.0f * dot(wo, wh)));
+      }
       default: return 0.0f;
     }
   }
@@ -325,6 +346,34 @@ struct BxDF {
         Vec3 wi = cosine_sample_hemisphere(u);
         if (wo.z < 0.0f) wi.z *= -1.0f;
         *pdfo = pdf(wo, wi);
+        *fo = f(wo, wi);
+        *wio = wi;
+        return true;
+      }
+      case BX_LAMBERT_T: {  // lambertian.rs:63-79
+        Vec3 wi = cosine_sample_hemisphere(u);
+        if (wo.z > 0.0f) wi.z *= -1.0f;
+        *pdfo = pdf(wo, wi);
+        if (!(*pdfo > 0.0f)) return false;
+        *fo = f(wo, wi);
+        *wio = wi;
+        return true;
+      }
+      case BX_FRESNEL_BLEND: {  // fresnel_blend.rs:59-90
+        Float ux = u.x;
+        Vec3 wi;
+        if (ux < 0.5f) {
+          ux = rmin(2.0f * ux, ONE_MINUS_EPSILON);
+          wi = cosine_sample_hemisphere(Vec2(ux, u.y));
+          if (wo.z < 0.0f) wi.z *= -1.0f;
+        } else {
+          ux = rmin(2.0f * (ux - 0.5f), ONE_MINUS_EPSILON);
+          Vec3 wh = dist.sample_wh(wo, Vec2(ux, u.y));
+          wi = reflect(wo, wh);
+          if (!same_hemisphere(wo, wi)) return false;
+        }
+        *pdfo = pdf(wo, wi);
+        if (!(*pdfo > 0.0f)) return false;
         *fo = f(wo, wi);
         *wio = wi;
         return true;
@@ -527,7 +576,7 @@ struct BSDF {
   Float eta = 1;
   Vec3 ns, ng, ss, ts;
   int n = 0;
-  BxDF<NC> bx[2];
+  BxDF<NC> bx[8];  // MAX_BXDFS = 8 (bsdf.rs)
   bool valid = false;  // si.bsdf.is_some()
 
   void init(const SurfInt& si, Float eta_) {
@@ -697,6 +746,68 @@ inline void compute_scattering(const pt_scene_desc* d, const SurfInt& si, BSDF<N
       b.fresnel.kind = FR_CONDUCTOR; b.fresnel.c_eta_i = Spec<NC>(1.0f); b.fresnel.c_eta_t = S(M.kr); b.fresnel.c_k = S(M.ks);
       b.dist = TRDist(ur, vr, true);
       bsdf->add(b);
+      break;
+    }
+    case PT_MAT_UBER: {  // uber.rs:73-128
+      Float e = M.eta;
+      Spec<NC> op = S(M.opacity);
+      Spec<NC> t = (Spec<NC>(1.0f) - op).clamp_zero();
+      bsdf->init(si, !t.is_black() ? 1.0f : e);
+      if (!t.is_black()) { BxDF<NC> b; b.kind = BX_SPEC_TRANS; b.t = t; b.eta_a = 1.0f; b.eta_b = 1.0f; bsdf->add(b); }
+      Spec<NC> kd = op * S(M.kd).clamp_zero();
+      if (!kd.is_black()) { BxDF<NC> b; b.kind = BX_LAMBERT; b.r = kd; bsdf->add(b); }
+      Spec<NC> ks = op * S(M.ks).clamp_zero();
+      if (!ks.is_black()) {
+        Float ur = M.uroughness, vr = M.vroughness;
+        if (M.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+        BxDF<NC> b; b.kind = BX_MF_REFL; b.r = ks;
+        b.fresnel.kind = FR_DIELECTRIC; b.fresnel.eta_i = 1.0f; b.fresnel.eta_t = e;
+        b.dist = TRDist(ur, vr, true);
+        bsdf->add(b);
+      }
+      Spec<NC> kr = op * S(M.kr).clamp_zero();
+      if (!kr.is_black()) {
+        BxDF<NC> b; b.kind = BX_SPEC_REFL; b.r = kr;
+        b.fresnel.kind = FR_DIELECTRIC; b.fresnel.eta_i = 1.0f; b.fresnel.eta_t = e;
+        bsdf->add(b);
+      }
+      Spec<NC> kt = op * S(M.kt).clamp_zero();
+      if (!kt.is_black()) { BxDF<NC> b; b.kind = BX_SPEC_TRANS; b.t = kt; b.eta_a = 1.0f; b.eta_b = e; bsdf->add(b); }
+      break;
+    }
+    case PT_MAT_SUBSTRATE: {  // substrate.rs:33-60
+      Spec<NC> d = S(M.kd).clamp_zero(), sp = S(M.ks).clamp_zero();
+      bsdf->init(si, 1.0f);
+      if (!d.is_black() && !sp.is_black()) {
+        Float ur = M.uroughness, vr = M.vroughness;
+        if (M.remap_roughness) { ur = roughness_to_alpha(ur); vr = roughness_to_alpha(vr); }
+        BxDF<NC> b; b.kind = BX_FRESNEL_BLEND; b.r = d; b.t = sp; b.dist = TRDist(ur, vr, true);
+        bsdf->add(b);
+      }
+      break;
+    }
+    case PT_MAT_TRANSLUCENT: {  // translucent.rs:37-100
+      const Float eta = 1.5f;
+      Spec<NC> r = S(M.kr).clamp_zero(), t = S(M.kt).clamp_zero();
+      if (r.is_black() && t.is_black()) return;  // returns before si.bsdf is set
+      bsdf->init(si, eta);
+      Spec<NC> kd = S(M.kd).clamp_zero();
+      if (!kd.is_black()) {
+        if (!r.is_black()) { BxDF<NC> b; b.kind = BX_LAMBERT; b.r = r * kd; bsdf->add(b); }
+        if (!t.is_black()) { BxDF<NC> b; b.kind = BX_LAMBERT_T; b.t = t * kd; bsdf->add(b); }
+      }
+      Spec<NC> ks = S(M.ks).clamp_zero();
+      if (!ks.is_black()) {
+        Float rough = M.uroughness;
+        if (M.remap_roughness) rough = roughness_to_alpha(rough);
+        if (!r.is_black()) {
+          BxDF<NC> b; b.kind = BX_MF_REFL; b.r = r * ks;
+          b.fresnel.kind = FR_DIELECTRIC; b.fresnel.eta_i = 1.0f; b.fresnel.eta_t = eta;
+          b.dist = TRDist(rough, rough, true);
+          bsdf->add(b);
+        }
+        if (!t.is_black()) { BxDF<NC> b; b.kind = BX_MF_TRANS; b.t = t * ks; b.eta_a = 1.0f; b.eta_b = eta; b.dist = TRDist(rough, rough, true); bsdf->add(b); }
+      }
       break;
     }
     default: return;

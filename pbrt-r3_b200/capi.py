@@ -12,6 +12,7 @@ DATA_DIR = os.path.join(HERE, "data")
 
 PT_ABI_VERSION = 3
 PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MIRROR = -1, 0, 1, 2, 3, 4
+PT_MAT_UBER, PT_MAT_SUBSTRATE, PT_MAT_TRANSLUCENT = 5, 6, 7
 PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT, PT_LIGHT_INFINITE = 0, 1, 2, 3, 4
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
@@ -28,7 +29,8 @@ u32p = C.POINTER(C.c_uint32)
 
 class pt_material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_int32), ("ks", C.c_int32), ("kr", C.c_int32), ("sigma", C.c_float),
-                ("uroughness", C.c_float), ("vroughness", C.c_float), ("eta", C.c_float), ("remap_roughness", C.c_int32)]
+                ("uroughness", C.c_float), ("vroughness", C.c_float), ("eta", C.c_float), ("remap_roughness", C.c_int32),
+                ("kt", C.c_int32), ("opacity", C.c_int32)]
 
 
 class pt_light(C.Structure):

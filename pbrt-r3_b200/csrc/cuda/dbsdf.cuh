@@ -224,7 +224,9 @@ PT_HD f3 tr_sample_wh(TR D, f3 wo, f2 u) {
 enum { LB_LAMBERT = 0, LB_OREN = 1, LB_MIRROR = 2, LB_FRESNEL_SPEC = 3, LB_MF_REFL = 4, LB_MF_TRANS = 5,
        // smooth glass without allow_multiple_lobes (directlighting / whitted; glass.rs:80-99): SpecularReflection with a
        // dielectric Fresnel term and SpecularTransmission (specular.rs) as two lobes
-       LB_SPEC_REFL_D = 6, LB_SPEC_TRANS = 7 };
+       LB_SPEC_REFL_D = 6, LB_SPEC_TRANS = 7,
+       // translucent: LambertianTransmission (lambertian.rs:59-99); substrate: FresnelBlend (fresnel_blend.rs)
+       LB_LAMBERT_T = 8, LB_FRESNEL_BLEND = 9 };
 enum { F_REFL = 1, F_TRANS = 2, F_DIFF = 4, F_GLOSSY = 8, F_SPEC = 16, F_ALL = 31 };
 enum { FR_NOOP = 0, FR_DIEL = 1, FR_COND = 2 };
 
@@ -236,33 +238,38 @@ struct Lobe {
   float ei, et;   // dielectric Fresnel eta_i, eta_t | transmission eta_a, eta_b
 };
 // Compile-time lobe sets: a shade kernel specialised for one material class only keeps the code of the lobes and
-// Fresnel terms that class can produce (bits 0-5: LB_* kinds, bits 8-10: FR_* kinds).
-#define PT_CM_ANY 0x7ff
-#define PT_CM_MATTE 0x103
-#define PT_CM_PLASTIC 0x311
-#define PT_CM_MIRROR 0x104
-#define PT_CM_GLASS 0x338
-#define PT_CM_METAL 0x410
+// Fresnel terms that class can produce (bits 0-9: LB_* kinds, bits 12-14: FR_* kinds).
+#define PT_CM_ANY 0x73ff
+#define PT_CM_MATTE 0x1003
+#define PT_CM_PLASTIC 0x3011
+#define PT_CM_MIRROR 0x1004
+#define PT_CM_GLASS 0x3038
+#define PT_CM_METAL 0x4010
 #if defined(__CUDACC__) || defined(__GNUC__)
 #define PT_UNREACHABLE() __builtin_unreachable()
 #else
 #define PT_UNREACHABLE()
 #endif
 #define PT_KIND(K) case K: if (!((CM >> (K)) & 1)) { PT_UNREACHABLE(); }
-#define PT_HAS_FRES(F) (((CM >> (8 + (F))) & 1) != 0)
+#define PT_HAS_FRES(F) (((CM >> (12 + (F))) & 1) != 0)
 
+// CM: the class's lobe set, so that a specialised kernel only compares against the kinds it can meet
+template <int CM = PT_CM_ANY>
 PT_HD int lobe_type(int kind) {
   switch (kind) {
-    case LB_LAMBERT: case LB_OREN: return F_REFL | F_DIFF;
-    case LB_MIRROR: return F_REFL | F_SPEC;
-    case LB_FRESNEL_SPEC: return F_REFL | F_TRANS | F_SPEC;
-    case LB_MF_REFL: return F_REFL | F_GLOSSY;
-    case LB_SPEC_REFL_D: return F_REFL | F_SPEC;
-    case LB_SPEC_TRANS: return F_TRANS | F_SPEC;
-    default: return F_TRANS | F_GLOSSY;
+    case LB_LAMBERT: case LB_OREN: if (!(CM & 3)) { PT_UNREACHABLE(); } return F_REFL | F_DIFF;
+    PT_KIND(LB_MIRROR) return F_REFL | F_SPEC;
+    PT_KIND(LB_FRESNEL_SPEC) return F_REFL | F_TRANS | F_SPEC;
+    PT_KIND(LB_MF_REFL) return F_REFL | F_GLOSSY;
+    PT_KIND(LB_SPEC_REFL_D) return F_REFL | F_SPEC;
+    PT_KIND(LB_SPEC_TRANS) return F_TRANS | F_SPEC;
+    PT_KIND(LB_LAMBERT_T) return F_TRANS | F_DIFF;
+    PT_KIND(LB_FRESNEL_BLEND) return F_REFL | F_GLOSSY;
+    default: if (!((CM >> LB_MF_TRANS) & 1)) { PT_UNREACHABLE(); } return F_TRANS | F_GLOSSY;
   }
 }
-PT_HD bool lobe_matches(int kind, int flags) { int t = lobe_type(kind); return (t & flags) == t; }
+template <int CM = PT_CM_ANY>
+PT_HD bool lobe_matches(int kind, int flags) { int t = lobe_type<CM>(kind); return (t & flags) == t; }
 
 template <int NC, int CM = PT_CM_ANY>
 PT_HD Sp<NC> lobe_fresnel(const DScene& S, const Lobe& L, float ci) {
@@ -277,6 +284,10 @@ PT_HD Sp<NC> lobe_fresnel(const DScene& S, const Lobe& L, float ci) {
   for (int i = 0; i < NC; i++) r.c[i] = fr_cond1(c, ldg(e + i), ldg(k + i));
   return r;
 }
+
+// FresnelBlend's pow5 is `v.powf(5.0)` (fresnel_blend.rs:13-15) = libm powf: v^5 formed in double and rounded once gives the
+// correctly rounded value except in near-tie cases, which is what glibc's powf returns (CUDA's powf does not)
+PT_HD float pow5(float v) { double d = (double)v; return (float)((d * d) * (d * d) * d); }
 
 template <int NC, int CM = PT_CM_ANY>
 PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe L, f3 wo, f3 wi) {
@@ -322,6 +333,18 @@ PT_HDN Sp<NC> lobe_f(const DScene& S, const Lobe L, f3 wo, f3 wi) {
       float dd = fabsf(tr_d(D, wh) * tr_g(D, wo, wi) * eta * eta * absdot3(wi, wh) * absdot3(wo, wh) * factor * factor / (cti * cto * sq * sq));
       return ((sp_const<NC>(1.0f) - sp_const<NC>(F)) * sp_load<NC>(S.spectra + (size_t)L.sp0 * NC)) * dd;
     }
+    PT_KIND(LB_LAMBERT_T) return sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * PT_INV_PI;
+    PT_KIND(LB_FRESNEL_BLEND) {  // fresnel_blend.rs:37-57
+      Sp<NC> rd = sp_load<NC>(S.spectra + (size_t)L.sp0 * NC), rs = sp_load<NC>(S.spectra + (size_t)L.sp1 * NC);
+      Sp<NC> diffuse = rd * (sp_const<NC>(1.0f) - rs) * (1.0f - pow5(1.0f - 0.5f * acth(wi))) * (1.0f - pow5(1.0f - 0.5f * acth(wo))) * (28.0f / (23.0f * PT_PI));
+      f3 wh = wi + wo;
+      if (wh.x == 0.0f && wh.y == 0.0f && wh.z == 0.0f) return sp_const<NC>(0.0f);
+      wh = norm3(wh);
+      TR D; D.ax = L.a; D.ay = L.b;
+      Sp<NC> schlick = rs + (sp_const<NC>(1.0f) - rs) * pow5(1.0f - dot3(wi, wh));
+      Sp<NC> specular = schlick * (tr_d(D, wh) / (4.0f * absdot3(wi, wh) * fmaxf(acth(wi), acth(wo))));
+      return diffuse + specular;
+    }
     default: return sp_const<NC>(0.0f);
   }
 }
@@ -346,6 +369,14 @@ PT_HDN float lobe_pdf(const Lobe L, f3 wo, f3 wi) {
       float dwh = fabsf((eta * eta * wi_wh) / (sq * sq));
       TR D; D.ax = L.a; D.ay = L.b;
       return tr_pdf(D, wo, wh) * dwh;
+    }
+    PT_KIND(LB_LAMBERT_T) return !same_hemi(wo, wi) ? acth(wi) : 0.0f;  // lambertian.rs:80-86 (no 1 / pi in the reference)
+    PT_KIND(LB_FRESNEL_BLEND) {  // fresnel_blend.rs:92-103
+      if (!same_hemi(wo, wi)) return 0.0f;
+      f3 wh = norm3(wo + wi);
+      if (dot3(wo, wh) < 0.0f) return 0.0f;
+      TR D; D.ax = L.a; D.ay = L.b;
+      return 0.5f * (acth(wi) * PT_INV_PI + tr_pdf(D, wo, wh) / (4.0f * dot3(wo, wh)));
     }
     default: return 0.0f;
   }
@@ -442,6 +473,31 @@ PT_HDN bool lobe_sample(const DScene& S, const Lobe L, f3 wo, f2 u, Sp<NC>* f, f
       Sp<NC> ft = sp_load<NC>(S.spectra + (size_t)L.sp0 * NC) * (sp_const<NC>(1.0f) - sp_const<NC>(fr_diel(cth(wi), L.ei, L.et)));
       ft = ft * ((ei * ei) / (et * et));
       *f = ft / acth(wi);
+      *wi_out = wi;
+      return true;
+    }
+    PT_KIND(LB_LAMBERT_T) {  // lambertian.rs:63-79
+      f3 wi = cosine_hemisphere(u);
+      if (wo.z > 0.0f) wi.z *= -1.0f;
+      *pdf = lobe_pdf<CM>(L, wo, wi);
+      *wi_out = wi;
+      return true;
+    }
+    PT_KIND(LB_FRESNEL_BLEND) {  // fresnel_blend.rs:59-90
+      float ux = u.x;
+      f3 wi;
+      if (ux < 0.5f) {
+        ux = fminf(2.0f * ux, PT_ONE_MINUS_EPS);
+        wi = cosine_hemisphere(mk2(ux, u.y));
+        if (wo.z < 0.0f) wi.z *= -1.0f;
+      } else {
+        ux = fminf(2.0f * (ux - 0.5f), PT_ONE_MINUS_EPS);
+        TR D; D.ax = L.a; D.ay = L.b;
+        f3 wh = tr_sample_wh(D, wo, mk2(ux, u.y));
+        wi = reflect3(wo, wh);
+        if (!same_hemi(wo, wi)) return false;
+      }
+      *pdf = lobe_pdf<CM>(L, wo, wi);
       *wi_out = wi;
       return true;
     }
@@ -617,22 +673,37 @@ PT_HD SurfD make_surface(const DScene& S, int tri, int instance, f3 ro, f3 rd, f
 // at most two lobes per BSDF (plastic: diffuse + glossy; rough glass: reflection + transmission).  Loops over the lobes have a
 // constant trip count and the lobe functions take the lobe by value, so that a BsdfD lives in registers: indexed through
 // a pointer it sat in the local-memory frame (ncu, matte kernel: 5 % of the stall samples on the first load of B.lobe[i].kind)
+// The five materials of the path's own classes need two; uber has up to five (uber.rs:85-125), translucent four: those run
+// with BsdfT<PT_LOBES_EXTRA> in their own shade class (CL_EXTRA) and in the tree integrators' kernel.
 #define PT_MAX_LOBES 2
-#define PT_LOBE_LOOP(i) _Pragma("unroll") for (int i = 0; i < PT_MAX_LOBES; i++) if (i < B.n)
-struct BsdfD {
+#define PT_LOBES_EXTRA 5
+#define PT_LOBE_LOOP(i) _Pragma("unroll") for (int i = 0; i < BS::ML; i++) if (i < B.n)
+template <int MLOBES>
+struct BsdfT {
+  static constexpr int ML = MLOBES;
   f3 ns, ng, ss, ts;
   float eta;
   int n;       // number of lobes; -1 = no BSDF (ray passes through)
-  Lobe lobe[PT_MAX_LOBES];
+  Lobe lobe[MLOBES];
 };
-PT_HD f3 to_local(const BsdfD& B, f3 v) { return mk3(dot3(v, B.ss), dot3(v, B.ts), dot3(v, B.ns)); }
-PT_HD f3 to_world(const BsdfD& B, f3 v) {
+typedef BsdfT<PT_MAX_LOBES> BsdfD;
+// lobe i of the BSDF by value (select chain: an indexed read would put the BsdfT into the local-memory frame)
+template <class BS>
+PT_HD Lobe bsdf_lobe(const BS& B, int index) {
+  Lobe L = B.lobe[0];
+#pragma unroll
+  for (int k = 1; k < BS::ML; k++)
+    if (index == k) L = B.lobe[k];
+  return L;
+}
+template <class BS> PT_HD f3 to_local(const BS& B, f3 v) { return mk3(dot3(v, B.ss), dot3(v, B.ts), dot3(v, B.ns)); }
+template <class BS> PT_HD f3 to_world(const BS& B, f3 v) {
   return mk3(B.ss.x * v.x + B.ts.x * v.y + B.ns.x * v.z, B.ss.y * v.x + B.ts.y * v.y + B.ns.y * v.z, B.ss.z * v.x + B.ts.z * v.y + B.ns.z * v.z);
 }
 PT_HD bool fin3(f3 v) { return isfinite_(v.x) && isfinite_(v.y) && isfinite_(v.z); }
-PT_HD int bsdf_count(const BsdfD& B, int flags) {
+template <int CM = PT_CM_ANY, class BS = BsdfD> PT_HD int bsdf_count(const BS& B, int flags) {
   int c = 0;
-  PT_LOBE_LOOP(i) if (lobe_matches(B.lobe[i].kind, flags)) c++;
+  PT_LOBE_LOOP(i) if (lobe_matches<CM>(B.lobe[i].kind, flags)) c++;
   return c;
 }
 
@@ -647,14 +718,20 @@ PT_HD bool spectrum_black(const DScene& S, int idx, bool clamp0) {
 // Spectra that the reference clamps (clamp_zero) are clamped on the HOST at upload when a negative value is
 // present, so the device can treat every stored reflectance as already clamped except matte Kd (never clamped).
 // appends a lobe (the slot index is 0 or 1: two selects instead of an indexed store into the frame)
-PT_HD void bsdf_add(BsdfD* B, int& n, const Lobe& L) {
-  if (n == 0) B->lobe[0] = L;
-  else B->lobe[1] = L;
+template <class BS> PT_HD void bsdf_add(BS* B, int& n, const Lobe& L) {
+  if (BS::ML == 2) {
+    if (n == 0) B->lobe[0] = L;
+    else B->lobe[1] = L;
+  } else {
+#pragma unroll
+    for (int k = 0; k < BS::ML; k++)
+      if (n == k) B->lobe[k] = L;
+  }
   n++;
 }
 // MULTI = allow_multiple_lobes (true: PathIntegrator, path.rs:106; false: directlighting / whitted)
-template <int NC, int MT = -1, bool MULTI = true>
-PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
+template <int NC, int MT = -1, bool MULTI = true, class BS = BsdfD>
+PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BS* B) {
   B->n = -1;
   int mi = ldg(S.tri_material + si.tri);
   if (mi < 0) return;
@@ -750,6 +827,22 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
       bsdf_add(B, n, L);
       break;
     }
+    case PT_MAT_UBER: case PT_MAT_SUBSTRATE: case PT_MAT_TRANSLUCENT: {
+      // uber.rs:85-125, substrate.rs:44-59, translucent.rs:48-98: every parameter is a constant, so the host has already
+      // listed the lobes (device_api.cu material_lobes)
+      if (MT != -1) { PT_UNREACHABLE(); }
+      const MatLobes& T = S.mat_lobes[mi];
+      if (T.n < 0) return;  // translucent with reflect = transmit = 0 leaves si.bsdf unset
+      eta = T.eta;
+#pragma unroll
+      for (int k = 0; k < PT_LOBES_EXTRA; k++)
+        if (k < T.n && k < BS::ML) {
+          Lobe L;
+          L.kind = T.kind[k]; L.sp0 = T.sp0[k]; L.sp1 = T.sp1[k]; L.fres = T.fres[k]; L.a = T.a[k]; L.b = T.b[k]; L.ei = T.ei[k]; L.et = T.et[k];
+          bsdf_add(B, n, L);
+        }
+      break;
+    }
     default: return;
   }
   B->n = n;
@@ -760,36 +853,36 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BsdfD* B) {
   B->ts = norm3(cross3(B->ns, B->ss));
 }
 
-template <int NC, int CM = PT_CM_ANY>
-PT_HD Sp<NC> bsdf_sum_f(const DScene& S, const BsdfD& B, f3 wo, f3 wi, f3 wo_w, f3 wi_w, int flags) {
+template <int NC, int CM = PT_CM_ANY, class BS = BsdfD>
+PT_HD Sp<NC> bsdf_sum_f(const DScene& S, const BS& B, f3 wo, f3 wi, f3 wo_w, f3 wi_w, int flags) {
   bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
   Sp<NC> r = sp_const<NC>(0.0f);
   PT_LOBE_LOOP(i) {
-    int tp = lobe_type(B.lobe[i].kind);
-    if (lobe_matches(B.lobe[i].kind, flags) && ((refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS)))) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+    int tp = lobe_type<CM>(B.lobe[i].kind);
+    if (lobe_matches<CM>(B.lobe[i].kind, flags) && ((refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS)))) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
   }
   return r;
 }
-template <int NC, int CM = PT_CM_ANY>
-PT_HDN Sp<NC> bsdf_f(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
+template <int NC, int CM = PT_CM_ANY, class BS = BsdfD>
+PT_HDN Sp<NC> bsdf_f(const DScene& S, const BS& B, f3 wo_w, f3 wi_w, int flags) {
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return sp_const<NC>(0.0f);
   return bsdf_sum_f<NC, CM>(S, B, wo, wi, wo_w, wi_w, flags);
 }
-template <int CM = PT_CM_ANY>
-PT_HDN float bsdf_pdf(const BsdfD& B, f3 wo_w, f3 wi_w, int flags) {
+template <int CM = PT_CM_ANY, class BS = BsdfD>
+PT_HDN float bsdf_pdf(const BS& B, f3 wo_w, f3 wi_w, int flags) {
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return 0.0f;
   int count = 0;
   float p = 0.0f;
   PT_LOBE_LOOP(i)
-    if (lobe_matches(B.lobe[i].kind, flags)) { p = p + lobe_pdf<CM>(B.lobe[i], wo, wi); count++; }
+    if (lobe_matches<CM>(B.lobe[i].kind, flags)) { p = p + lobe_pdf<CM>(B.lobe[i], wo, wi); count++; }
   return count > 0 ? p / (float)count : 0.0f;
 }
 // BSDF::f and BSDF::pdf for the same pair of directions (estimate_direct's light sample needs both, sample_lights.rs:
 // 366-380): one pass over the lobes with lobe_f_pdf.  Same sums in the same lobe order as bsdf_f / bsdf_pdf.
-template <int NC, int CM = PT_CM_ANY>
-PT_HD1 void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int flags, Sp<NC>* f_out, float* pdf_out) {
+template <int NC, int CM = PT_CM_ANY, class BS = BsdfD>
+PT_HD1 void bsdf_f_pdf(const DScene& S, const BS& B, f3 wo_w, f3 wi_w, int flags, Sp<NC>* f_out, float* pdf_out) {
   *f_out = sp_const<NC>(0.0f);
   *pdf_out = 0.0f;
   f3 wi = to_local(B, wi_w), wo = to_local(B, wo_w);
@@ -799,8 +892,8 @@ PT_HD1 void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int fl
   int count = 0;
   float p = 0.0f;
   PT_LOBE_LOOP(i) {
-    if (!lobe_matches(B.lobe[i].kind, flags)) continue;
-    const int tp = lobe_type(B.lobe[i].kind);
+    if (!lobe_matches<CM>(B.lobe[i].kind, flags)) continue;
+    const int tp = lobe_type<CM>(B.lobe[i].kind);
     const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
     if (((CM >> LB_MF_REFL) & 1) && B.lobe[i].kind == LB_MF_REFL) {
       Sp<NC> fl;
@@ -818,18 +911,18 @@ PT_HD1 void bsdf_f_pdf(const DScene& S, const BsdfD& B, f3 wo_w, f3 wi_w, int fl
   *pdf_out = count > 0 ? p / (float)count : 0.0f;
 }
 
-template <int NC, int CM = PT_CM_ANY>
+template <int NC, int CM = PT_CM_ANY, class BS = BsdfD>
 // (inlined at its two call sites, the MIS sample and the continuation sample: +5 % code, but the BsdfD and the four result
 // slots leave the local-memory frame: k_shade -2 % on config 2, -3 % on the instanced scene, profiles/r2f_ab_sync_and_shade.txt)
-PT_HD bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags, Sp<NC>* f, f3* wi_w_out, float* pdf_out, int* stype) {
-  int matching = bsdf_count(B, flags);
+PT_HD bool bsdf_sample(const DScene& S, const BS& B, f3 wo_w, f2 u, int flags, Sp<NC>* f, f3* wi_w_out, float* pdf_out, int* stype) {
+  int matching = bsdf_count<CM>(B, flags);
   if (matching == 0) return false;
   int comp = (int)floorf(u.x * (float)matching);
   if (comp > matching - 1) comp = matching - 1;
   int index = -1, cnt = comp;
   PT_LOBE_LOOP(i)
-    if (lobe_matches(B.lobe[i].kind, flags)) { if (cnt == 0) { index = i; break; } cnt--; }
-  const Lobe L = index == 0 ? B.lobe[0] : B.lobe[1];
+    if (lobe_matches<CM>(B.lobe[i].kind, flags)) { if (cnt == 0) { index = i; break; } cnt--; }
+  const Lobe L = BS::ML == 2 ? (index == 0 ? B.lobe[0] : B.lobe[1]) : bsdf_lobe(B, index);
   f2 ur = mk2(fminf((u.x * (float)matching) - (float)comp, PT_ONE_MINUS_EPS), u.y);
   f3 wo = to_local(B, wo_w);
   if (wo.z == 0.0f || !fin3(wo)) return false;
@@ -839,13 +932,13 @@ PT_HD bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags
   int t;
   if (!lobe_sample<NC, CM>(S, L, wo, ur, &fv, &wi, &pdf, &t)) return false;
   if (pdf <= 0.0f) return false;
-  int ltype = lobe_type(L.kind);
+  int ltype = lobe_type<CM>(L.kind);
   int sampled = t != 0 ? t : ltype;
   f3 wi_w = to_world(B, wi);
   if (NC != 3 && (ltype & F_SPEC) == 0) {  // 60 bins: the plain form (no spectrum-sized temporaries)
     if (matching > 1)
       PT_LOBE_LOOP(i)
-        if (i != index && lobe_matches(B.lobe[i].kind, flags)) pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
+        if (i != index && lobe_matches<CM>(B.lobe[i].kind, flags)) pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
     fv = bsdf_sum_f<NC, CM>(S, B, wo, wi, wo_w, wi_w, flags);
   } else if ((ltype & F_SPEC) == 0) {
     // pdf += the other matching lobes' pdfs (bsdf.rs:167-176); f = sum over the matching lobes on the right side of the
@@ -853,8 +946,8 @@ PT_HD bool bsdf_sample(const DScene& S, const BsdfD& B, f3 wo_w, f2 u, int flags
     const bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
     Sp<NC> r = sp_const<NC>(0.0f);
     PT_LOBE_LOOP(i) {
-      if (!lobe_matches(B.lobe[i].kind, flags)) continue;
-      const int tp = lobe_type(B.lobe[i].kind);
+      if (!lobe_matches<CM>(B.lobe[i].kind, flags)) continue;
+      const int tp = lobe_type<CM>(B.lobe[i].kind);
       const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
       if (i == index) {
         if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);

@@ -385,10 +385,71 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
     alpha[2 * m] = ur;
     alpha[2 * m + 1] = vr;
   }
+  // uber / substrate / translucent (materials/{uber,substrate,translucent}.rs compute_scattering_functions): every parameter
+  // is a constant, so the lobes are listed here once; products of spectra become pool entries (RGB only, front end)
+  std::vector<MatLobes> lobes(D->n_materials);
+  {
+    auto get = [&](int idx, float* c) { for (uint32_t k = 0; k < NC; k++) c[k] = idx >= 0 ? spectra[(size_t)idx * NC + k] : 0.0f; };
+    auto clamp0 = [&](float* c) { for (uint32_t k = 0; k < NC; k++) c[k] = c[k] < 0.0f ? 0.0f : c[k]; };
+    auto black = [&](const float* c) { for (uint32_t k = 0; k < NC; k++) if (c[k] != 0.0f) return false; return true; };
+    auto add = [&](const float* c) { size_t n = spectra.size() / NC; for (uint32_t k = 0; k < NC; k++) spectra.push_back(c[k]); return (int)n; };
+    for (uint32_t m = 0; m < D->n_materials; m++) {
+      const pt_material& M = mats[m];
+      MatLobes& T = lobes[m];
+      memset(&T, 0, sizeof(T));
+      T.eta = 1.0f;
+      if (M.type != PT_MAT_UBER && M.type != PT_MAT_SUBSTRATE && M.type != PT_MAT_TRANSLUCENT) continue;
+      if (NC != 3) { pt_set_error("uber / substrate / translucent materials are only supported with RGB spectra"); return 1; }
+      const float ax = std::max(0.001f, alpha[2 * m]), ay = std::max(0.001f, alpha[2 * m + 1]);  // TrowbridgeReitzDistribution::new
+      auto lobe = [&](int kind, int sp0, int sp1, int fres, float a, float b, float ei, float et) {
+        const int k = T.n++;
+        T.kind[k] = kind; T.sp0[k] = sp0; T.sp1[k] = sp1; T.fres[k] = fres; T.a[k] = a; T.b[k] = b; T.ei[k] = ei; T.et[k] = et;
+      };
+      float kd[60], ks[60], kr[60], kt[60], op[60], t[60], x[60];
+      get(M.kd, kd); get(M.ks, ks); get(M.kr, kr); get(M.kt, kt); get(M.opacity, op);
+      clamp0(kd); clamp0(ks);
+      if (M.type == PT_MAT_UBER) {  // uber.rs:85-125
+        clamp0(kr); clamp0(kt);
+        for (uint32_t k = 0; k < NC; k++) t[k] = 1.0f - op[k];
+        clamp0(t);
+        T.eta = !black(t) ? 1.0f : M.eta;
+        if (!black(t)) lobe(LB_SPEC_TRANS, add(t), -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
+        for (uint32_t k = 0; k < NC; k++) x[k] = op[k] * kd[k];
+        if (!black(x)) lobe(LB_LAMBERT, add(x), -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
+        for (uint32_t k = 0; k < NC; k++) x[k] = op[k] * ks[k];
+        if (!black(x)) lobe(LB_MF_REFL, add(x), -1, FR_DIEL, ax, ay, 1.0f, M.eta);
+        for (uint32_t k = 0; k < NC; k++) x[k] = op[k] * kr[k];
+        if (!black(x)) lobe(LB_SPEC_REFL_D, add(x), -1, FR_DIEL, 0.0f, 0.0f, 1.0f, M.eta);
+        for (uint32_t k = 0; k < NC; k++) x[k] = op[k] * kt[k];
+        if (!black(x)) lobe(LB_SPEC_TRANS, add(x), -1, FR_NOOP, 0.0f, 0.0f, 1.0f, M.eta);
+      } else if (M.type == PT_MAT_SUBSTRATE) {  // substrate.rs:44-59
+        if (!black(kd) && !black(ks)) lobe(LB_FRESNEL_BLEND, add(kd), add(ks), FR_NOOP, ax, ay, 1.0f, 1.0f);
+      } else {  // translucent.rs:48-98 (reflect = kr, transmit = kt)
+        clamp0(kr); clamp0(kt);
+        T.eta = 1.5f;
+        if (black(kr) && black(kt)) { T.n = -1; continue; }
+        if (!black(kd)) {
+          for (uint32_t k = 0; k < NC; k++) x[k] = kr[k] * kd[k];
+          if (!black(kr)) lobe(LB_LAMBERT, add(x), -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
+          for (uint32_t k = 0; k < NC; k++) x[k] = kt[k] * kd[k];
+          if (!black(kt)) lobe(LB_LAMBERT_T, add(x), -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
+        }
+        if (!black(ks)) {
+          for (uint32_t k = 0; k < NC; k++) x[k] = kr[k] * ks[k];
+          if (!black(kr)) lobe(LB_MF_REFL, add(x), -1, FR_DIEL, ax, ay, 1.0f, 1.5f);
+          for (uint32_t k = 0; k < NC; k++) x[k] = kt[k] * ks[k];
+          if (!black(kt)) lobe(LB_MF_TRANS, add(x), -1, FR_NOOP, ax, ay, 1.0f, 1.5f);
+        }
+      }
+    }
+  }
   s->class_mask = 1u;
-  for (uint32_t m = 0; m < D->n_materials; m++)
+  for (uint32_t m = 0; m < D->n_materials; m++) {
     if (mats[m].type >= 0 && mats[m].type <= 4) s->class_mask |= 1u << (mats[m].type + 1);
+    else if (mats[m].type >= PT_MAT_UBER && mats[m].type <= PT_MAT_TRANSLUCENT) s->class_mask |= 1u << CL_EXTRA;
+  }
   CK(s->bufs.upload(spectra.data(), spectra.size(), &H.spectra));
+  CK(s->bufs.upload(lobes.data(), lobes.size(), &H.mat_lobes));
   CK(s->bufs.upload(mats.data(), mats.size(), &H.materials));
   CK(s->bufs.upload(alpha.data(), alpha.size(), &H.alpha));
   CK(s->bufs.upload(D->lights, (size_t)D->n_lights + D->n_emitters_only, &H.lights));

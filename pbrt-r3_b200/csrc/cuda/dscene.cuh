@@ -68,6 +68,15 @@ struct LightDistDev {   // dense restatement of SpatialLightDistribution's hash 
   const float* func_int;  // [n_vox]
 };
 
+// The lobes of a material whose parameters are all constants, listed by the host (uber, substrate, translucent): what
+// Material::compute_scattering_functions would add, in its order (dbsdf.cuh Lobe fields, structure of arrays)
+struct MatLobes {
+  int32_t n;              // -1: no BSDF at all (the ray passes through)
+  float eta;
+  int32_t kind[5], sp0[5], sp1[5], fres[5];
+  float a[5], b[5], ei[5], et[5];
+};
+
 struct EnvDev {           // one per LightSource "infinite" (lights/infinite.rs): level 0 of the map + the Distribution2D tables
   float l2w[9], w2l[9];   // upper 3x3 of light_to_world / world_to_light
   int32_t w, h;           // level 0 (powers of two); every lookup on the path has width 0 = the bilinear filter of level 0
@@ -104,6 +113,7 @@ struct DScene {
   const int32_t* tri_material;
   const int32_t* tri_light;
   const pt_material* materials;
+  const MatLobes* mat_lobes;  // per material (meaningful for uber / substrate / translucent)
   const pt_light* lights;
   const uint32_t* light_sample_prefix;  // [n_lights + 1] prefix sums of pt_light.n_samples (directlighting "all": round -> light, sample)
   const pt_spot* spots;      // SpotLight extras, indexed by pt_light.tri

@@ -65,7 +65,10 @@ struct Queues {
 
 // Shading classes: one specialised shade kernel per material plugin ("sort by material"); class 0
 // takes the paths that need no BSDF: misses, paths at max depth, surfaces without a material.
-enum { CL_NONE = 0, CL_MATTE = 1, CL_PLASTIC = 2, CL_GLASS = 3, CL_METAL = 4, CL_MIRROR = 5, CL_COUNT = 6, CL_ANY = 7 };
+// CL_EXTRA: uber, substrate and translucent share one generic kernel with room for five lobes (they are not on the
+// BASELINE configs; the five classes above keep their two-lobe BSDF in registers).  At most 8 classes (bin counters).
+enum { CL_NONE = 0, CL_MATTE = 1, CL_PLASTIC = 2, CL_GLASS = 3, CL_METAL = 4, CL_MIRROR = 5, CL_EXTRA = 6, CL_COUNT = 7 };
+PT_HD constexpr int cls_lobes(int c) { return c == CL_EXTRA ? PT_LOBES_EXTRA : PT_MAX_LOBES; }
 PT_HD constexpr int cls_cm(int c) {
   return c == CL_MATTE ? PT_CM_MATTE : c == CL_PLASTIC ? PT_CM_PLASTIC : c == CL_GLASS ? PT_CM_GLASS : c == CL_METAL ? PT_CM_METAL : c == CL_MIRROR ? PT_CM_MIRROR : PT_CM_ANY;
 }
@@ -76,7 +79,7 @@ PT_HD int shade_class(const DScene& S, int tri, int bounces) {
   int mi = ldg(S.tri_material + tri);
   if (mi < 0) return CL_NONE;
   int t = S.materials[mi].type;
-  return (t >= 0 && t <= 4) ? t + 1 : CL_NONE;
+  return (t >= 0 && t <= 4) ? t + 1 : ((t >= PT_MAT_UBER && t <= PT_MAT_TRANSLUCENT) ? CL_EXTRA : CL_NONE);
 }
 
 // PerspectiveCamera::generate_ray_differential without the differentials (constant textures: they cannot reach L)
@@ -494,7 +497,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
     }
   }
   if (!found || bounces >= S.integrator.max_depth) { st_store<NC>(W.L, cap, i, L); return; }
-  BsdfD B;
+  BsdfT<cls_lobes(CLS)> B;
   B.n = -1;
   if (CLS != CL_NONE) make_bsdf<NC, MT>(S, si, &B);
   RefPt ref;
@@ -526,7 +529,7 @@ PT_HD void shade_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, unsi
   const int NONSPEC = F_ALL & ~F_SPEC;
 
   // --- uniform_sample_one_light_surface + estimate_direct_surface (sample_lights.rs:129-176, 330-453)
-  if (CLS != CL_MIRROR && bsdf_count(B, NONSPEC) > 0 && S.n_lights > 0) {
+  if (CLS != CL_MIRROR && bsdf_count<CM>(B, NONSPEC) > 0 && S.n_lights > 0) {
     // path.rs:122-129 adds beta * uniform_sample_one_light(..) even when the estimate is zero: a non-finite beta makes
     // l invalid at this vertex whatever the light / MIS rays find (inf * 0 = NaN).  The terms parked in pendA / pendB
     // are dropped when occluded, so the same effect is folded in here; for a finite beta this adds +0.
@@ -772,7 +775,7 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
   bool push_sh = false, push_mis = false, push_ext = false, push_wait = false;
   bool need_pop = false, have_vertex = false;
   SurfD si;
-  BsdfD B;
+  BsdfT<PT_LOBES_EXTRA> B;
   B.n = -1;
   if ((int)fbits(h4.w) < 0) {  // the ray left the scene: li = sum of Light::le (directlighting.rs:112-122, whitted.rs:86-96)
     need_pop = true;

@@ -30,6 +30,9 @@ static void launch_shade_nc(int cls, int grid, cudaStream_t stream, const DScene
     case CL_GLASS: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_GLASS, ENV>)(S, W, Q, vc); break;
     case CL_METAL: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_METAL, ENV>)(S, W, Q, vc); break;
     case CL_MIRROR: PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_MIRROR, ENV>)(S, W, Q, vc); break;
+    case CL_EXTRA:  // uber / substrate / translucent: RGB only (front end)
+      if constexpr (NC == 3) PT_LAUNCH(grid, PT_SHADE_BLOCK, stream, k_shade<NC, CL_EXTRA, ENV>)(S, W, Q, vc);
+      break;
     default: break;
   }
 }

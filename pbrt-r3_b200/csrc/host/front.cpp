@@ -241,11 +241,11 @@ struct Builder {
     TP tp{&geom, &mat};
     pt_material m;
     memset(&m, 0, sizeof(m));
-    m.kd = m.ks = m.kr = -1;
+    m.kd = m.ks = m.kr = m.kt = m.opacity = -1;
     m.remap_roughness = 1;
     std::string nm = name;
     if (nm == "" || nm == "none") return -1;
-    if (nm != "matte" && nm != "plastic" && nm != "glass" && nm != "metal" && nm != "mirror") {
+    if (nm != "matte" && nm != "plastic" && nm != "glass" && nm != "metal" && nm != "mirror" && nm != "uber" && nm != "substrate" && nm != "translucent") {
       // create_material.rs:65-70: unknown names fall back to matte with a warning
       warn("Unable to create material \"" + nm + "\" on the GPU path; using \"matte\".");
       nm = "matte";
@@ -272,6 +272,40 @@ struct Builder {
       float eta;
       if (!tp_float_or_null(tp, "eta", &eta) && !tp_float_or_null(tp, "index", &eta)) eta = 1.5f;
       m.eta = eta;
+      m.remap_roughness = tp_bool(tp, "remaproughness", true);
+    } else if (nm == "uber") {  // uber.rs:142-168
+      if (spec.n_channels() != 3) throw ParseError("Material \"uber\" is only supported with RGB spectra on the GPU path");
+      m.type = PT_MAT_UBER;
+      m.kd = add_spectrum(tp_spectrum(tp, "Kd", spec.constant(0.25f)));
+      m.ks = add_spectrum(tp_spectrum(tp, "Ks", spec.constant(0.25f)));
+      m.kr = add_spectrum(tp_spectrum(tp, "Kr", spec.constant(0.0f)));
+      m.kt = add_spectrum(tp_spectrum(tp, "Kt", spec.constant(0.0f)));
+      m.opacity = add_spectrum(tp_spectrum(tp, "opacity", spec.constant(1.0f)));
+      float rough = tp_float(tp, "roughness", 0.1f);
+      float ur, vr;
+      m.uroughness = tp_float_or_null(tp, "uroughness", &ur) ? ur : rough;
+      m.vroughness = tp_float_or_null(tp, "vroughness", &vr) ? vr : rough;
+      float eta;
+      if (!tp_float_or_null(tp, "eta", &eta) && !tp_float_or_null(tp, "index", &eta)) eta = 1.5f;
+      m.eta = eta;
+      m.remap_roughness = tp_bool(tp, "remaproughness", true);
+    } else if (nm == "substrate") {  // substrate.rs:62-78
+      if (spec.n_channels() != 3) throw ParseError("Material \"substrate\" is only supported with RGB spectra on the GPU path");
+      m.type = PT_MAT_SUBSTRATE;
+      m.kd = add_spectrum(tp_spectrum(tp, "Kd", spec.constant(0.5f)));
+      m.ks = add_spectrum(tp_spectrum(tp, "Ks", spec.constant(0.5f)));
+      m.uroughness = tp_float(tp, "uroughness", 0.1f);
+      m.vroughness = tp_float(tp, "vroughness", 0.1f);
+      m.remap_roughness = tp_bool(tp, "remaproughness", true);
+    } else if (nm == "translucent") {  // translucent.rs:102-122
+      if (spec.n_channels() != 3) throw ParseError("Material \"translucent\" is only supported with RGB spectra on the GPU path");
+      m.type = PT_MAT_TRANSLUCENT;
+      m.kd = add_spectrum(tp_spectrum(tp, "Kd", spec.constant(0.25f)));
+      m.ks = add_spectrum(tp_spectrum(tp, "Ks", spec.constant(0.25f)));
+      m.kr = add_spectrum(tp_spectrum(tp, "reflect", spec.constant(0.5f)));
+      m.kt = add_spectrum(tp_spectrum(tp, "transmit", spec.constant(0.5f)));
+      m.uroughness = m.vroughness = tp_float(tp, "roughness", 0.1f);
+      m.eta = 1.5f;
       m.remap_roughness = tp_bool(tp, "remaproughness", true);
     } else {  // metal
       m.type = PT_MAT_METAL;

@@ -215,6 +215,14 @@ def test_infinite_light(P, tmp_path):
     check_env(P, tmp_path, n=20000, res=72, spp=4, wave_paths=3000, threads=0, rtol=1e-4, frac=0.9995)
 
 
+def test_extra_materials(P):
+    """Materials uber / substrate / translucent (their own shade class with five-lobe BSDFs; FresnelBlend and
+    LambertianTransmission lobes) under path / directlighting / whitted: radiance within 2e-5 on >= 99.9 % of the samples,
+    equal ray / visit / vertex counters."""
+    from test_hostcheck import check_extra_materials
+    check_extra_materials(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
+
+
 def test_one_sided_triangles_bit_exact(P, pair):
     """Back-face culling of one-sided meshes (triangle.rs:236-246), with and without ReverseOrientation."""
     from test_hostcheck import one_sided_scene

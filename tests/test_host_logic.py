@@ -211,6 +211,26 @@ def test_front_end_tree_integrators(P):
         lib.pt_set_options(P.capi.pt_options(0, 0))
 
 
+def test_front_end_extra_materials(P):
+    base = 'Camera "perspective"\nWorldBegin\nMaterial %s\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n'
+    sp = lambda hs, i: [hs.desc.spectra[3 * i + k] for k in range(3)]
+    hs = P.HostScene.parse_string(base % '"uber"')
+    m = hs.desc.materials[0]                                                                            # uber.rs:142-153 defaults
+    assert m.type == P.capi.PT_MAT_UBER and (m.uroughness, m.vroughness, m.eta, m.remap_roughness) == (np.float32(0.1), np.float32(0.1), 1.5, 1)
+    assert [sp(hs, i) for i in (m.kd, m.ks, m.kr, m.kt, m.opacity)] == [[0.25] * 3, [0.25] * 3, [0.0] * 3, [0.0] * 3, [1.0] * 3]
+    m = P.HostScene.parse_string(base % '"uber" "float roughness" [0.3] "float vroughness" [0.2] "float index" [1.33]').desc.materials[0]
+    assert (m.uroughness, m.vroughness, m.eta) == (np.float32(0.3), np.float32(0.2), np.float32(1.33))
+    hs = P.HostScene.parse_string(base % '"substrate"')
+    m = hs.desc.materials[0]                                                                            # substrate.rs:62-68
+    assert m.type == P.capi.PT_MAT_SUBSTRATE and sp(hs, m.kd) == [0.5] * 3 and sp(hs, m.ks) == [0.5] * 3 and (m.uroughness, m.vroughness) == (np.float32(0.1),) * 2
+    hs = P.HostScene.parse_string(base % '"translucent" "rgb transmit" [0.1 0.2 0.3]')
+    m = hs.desc.materials[0]                                                                            # translucent.rs:102-109
+    assert m.type == P.capi.PT_MAT_TRANSLUCENT and sp(hs, m.kd) == [0.25] * 3 and sp(hs, m.kr) == [0.5] * 3
+    assert np.allclose(sp(hs, m.kt), [0.1, 0.2, 0.3]) and m.eta == 1.5
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % '"uber"', spectrum="sampled")
+
+
 def test_front_end_infinite_light(P, tmp_path):
     from test_hostcheck import write_pfm
     img = np.arange(4 * 8 * 3, dtype=np.float32).reshape(4, 8, 3) - 5.0

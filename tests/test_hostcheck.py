@@ -402,6 +402,60 @@ def test_hostcheck_infinite_light(HC, tmp_path):
     check_env(HC, tmp_path)
 
 
+def extra_materials_scene(P, integrator='"path"', res=24, spp=4, sampler="halton", maxdepth=6):
+    """Cornell box with an uber short block (opacity < 1: the pass-through SpecularTransmission lobe, all five lobes), a
+    substrate tall block (FresnelBlend, anisotropic), a translucent back wall, a second uber floor (Kr only) and a
+    translucent ceiling with reflect = transmit = 0 (no BSDF at all: rays pass through)."""
+    txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", extra_lights=True, sampler=sampler, maxdepth=maxdepth)
+    rep = {'Material "glass" "float eta" [1.5]\n':
+           'Material "uber" "rgb Kd" [0.3 0.2 0.1] "rgb Ks" [0.3 0.3 0.3] "rgb Kr" [0.2 0.2 0.3] "rgb Kt" [0.3 0.4 0.3] "rgb opacity" [0.8 0.7 0.9] "float uroughness" [0.05] "float vroughness" [0.2] "float index" [1.4]\n',
+           'Material "metal" "rgb eta" [0.2 0.92 1.1] "rgb k" [3.9 2.45 2.14] "float roughness" [0.05]\n':
+           'Material "substrate" "rgb Kd" [0.5 0.3 0.2] "rgb Ks" [0.1 0.1 0.15] "float uroughness" [0.02] "float vroughness" [0.3]\n',
+           'Material "mirror" "rgb Kr" [0.8 0.8 0.8]\n':
+           'Material "translucent" "rgb Kd" [0.5 0.5 0.4] "rgb Ks" [0.3 0.3 0.3] "rgb reflect" [0.6 0.5 0.5] "rgb transmit" [0.4 0.5 0.5] "float roughness" [0.2]\n',
+           'Material "plastic" "rgb Kd" [0.4 0.4 0.4] "rgb Ks" [0.3 0.3 0.3] "float roughness" [0.1]\n':
+           'Material "uber" "rgb Kd" [0.4 0.4 0.4] "rgb Ks" [0 0 0] "rgb Kr" [0.3 0.3 0.3]\n'}
+    for a, b in rep.items():
+        assert a in txt
+        txt = txt.replace(a, b)
+    shapes = [l for l in txt.split("\n") if l.startswith("Shape")]
+    white = 'Material "matte" "rgb Kd" [0.725 0.71 0.68]\n'
+    assert white + shapes[1] in txt
+    txt = txt.replace(white + shapes[1], 'Material "translucent" "rgb reflect" [0 0 0] "rgb transmit" [0 0 0]\n' + shapes[1].replace("548.8", "500"))
+    head, rest = txt.split('Integrator "path"', 1)
+    return head + "Integrator " + integrator + rest
+
+
+def check_extra_materials(P, n=1500, res=24, spp=4, wave_paths=300, threads=2):
+    """uber / substrate / translucent (materials/{uber,substrate,translucent}.rs): per-sample radiance against the oracle
+    (FresnelBlend's powf(x, 5) is formed in double on the device: a last-place difference in rare cases), equal counters"""
+    import oracle_api
+    for integ, kw in [('"path"', dict()), ('"path"', dict(sampler="sobol", maxdepth=9)), ('"directlighting" "string strategy" ["one"]', dict()), ('"whitted"', dict())]:
+        hs = P.HostScene.parse_string(extra_materials_scene(P, integ, res=res, spp=spp, **kw))
+        types = sorted(set(hs.desc.materials[i].type for i in range(hs.desc.n_materials)))
+        assert types == [P.capi.PT_MAT_MATTE, P.capi.PT_MAT_UBER, P.capi.PT_MAT_SUBSTRATE, P.capi.PT_MAT_TRANSLUCENT], types
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        sb = hs.desc.film.sample_bounds
+        rng = np.random.RandomState(12)
+        pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+        sn = rng.randint(0, spp, n).astype(np.int32)
+        la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+        ok = (np.abs(la - lb) <= 2e-5 * np.maximum(np.abs(lb), 1e-3)).all(1)
+        assert ok.mean() >= 0.999, (integ, kw, ok.mean(), la[~ok][:3], lb[~ok][:3])
+        assert la.max() > 0
+        rgb, st = sc.render(collect_counters=1, wave_paths=wave_paths)
+        ref, so = orc.render(threads=threads)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-4, (integ, kw)
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[k] == so[k], (integ, kw, k, st[k], so[k])
+        one, _ = sc.render(wave_paths=wave_paths, wave_segments=1)
+        assert np.array_equal(one, rgb), (integ, kw)
+
+
+def test_hostcheck_extra_materials(HC):
+    check_extra_materials(HC)
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
