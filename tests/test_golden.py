@@ -43,6 +43,38 @@ def test_oracle_reproduces_golden_widening(P):
             assert [st[k] for k in K] == list(z[name + "_counters"]), name
 
 
+def round2_scenes(P):
+    import tempfile
+    from test_hostcheck import ao_scene, tree_scene, env_scene, extra_materials_scene
+    return {"ao": ao_scene(P, nsamples=4, res=24, spp=2), "direct_all": tree_scene(P, '"directlighting"', res=24, spp=2, nsamples=2),
+            "whitted": tree_scene(P, '"whitted"', res=24, spp=2), "env_path": env_scene(P, tempfile.gettempdir(), mapped=False, res=24, spp=2),
+            "materials_path": extra_materials_scene(P, res=24, spp=2)}
+
+
+R2_KEYS = ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices")
+
+
+def test_oracle_reproduces_golden_round2(P):
+    """ambientocclusion, directlighting (sample arrays), whitted, the infinite light, uber / substrate / translucent."""
+    import oracle_api
+    z = np.load(os.path.join(G, "round2_24.npz"))
+    for name, txt in round2_scenes(P).items():
+        rgb, st = oracle_api.OracleScene(P.HostScene.parse_string(txt)).render(threads=1)
+        assert np.array_equal(rgb, z[name]), name
+        assert [st[k] for k in R2_KEYS] == list(z[name + "_counters"]), name
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_round2(P):
+    z = np.load(os.path.join(G, "round2_24.npz"))
+    for name, txt in round2_scenes(P).items():
+        sc = P.Scene(P.HostScene.parse_string(txt), 0)
+        rgb, st = sc.render(collect_counters=1)
+        assert np.sqrt(((rgb - z[name]) ** 2).mean()) / z[name].mean() <= 1e-3, name
+        assert [st[k] for k in R2_KEYS] == list(z[name + "_counters"]), name
+        sc.close()
+
+
 def test_oracle_furnace(P):
     """Analytic check the reference has no test for: a closed diffuse box lit by a two-sided emitter in the middle.
     With albedo rho and uniform emission, radiance converges to a finite positive value and energy is conserved:

@@ -34,4 +34,14 @@ rgb5, st5 = oracle_api.OracleScene(hs5).render(threads=1)
 np.savez(os.path.join(out, "widening_32.npz"), spot=rgb3, aov_ns=rgb4, lbvh=rgb5,
          spot_counters=np.array([st3[k] for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested")], np.int64),
          lbvh_counters=np.array([st5[k] for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested")], np.int64))
+# round-2 widening: ambientocclusion / directlighting / whitted, the infinite light (constant; a map needs a file), uber /
+# substrate / translucent
+from test_golden import round2_scenes
+K = ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices")
+r2 = {}
+for name, txt in round2_scenes(P).items():
+    rgb, st = oracle_api.OracleScene(P.HostScene.parse_string(txt)).render(threads=1)
+    r2[name] = rgb
+    r2[name + "_counters"] = np.array([st[k] for k in K], np.int64)
+np.savez(os.path.join(out, "round2_24.npz"), **r2)
 print("golden written:", os.listdir(out))
