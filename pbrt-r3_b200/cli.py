@@ -80,6 +80,23 @@ def render_scene(path, opts):
     finally:
         sc.close()
     if rank == 0:
+        # Film displays (pbrt.rs:296-321): --display-server host:port (tev), -k dir (numbered EXR frames); a display that
+        # cannot be reached is a warning, not an error
+        from . import display
+        shows = []
+        if opts.display_server:
+            try:
+                shows.append(display.TevDisplay(opts.display_server))
+            except Exception as e:
+                sys.stderr.write("WARNING: %s\n" % e)
+        if opts.sequential_display:
+            shows.append(display.SequentialDisplay(opts.sequential_display))
+        try:
+            display.show(shows, hs, rgb)
+        except Exception as e:
+            sys.stderr.write("WARNING: %s\n" % e)
+        for d in shows:
+            d.close()
         imageio.write_image(name, rgb)
         if not opts.quiet:
             print("\n")

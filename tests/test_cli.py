@@ -120,6 +120,71 @@ def test_cli_two_ranks_match_one(P, tmp_path, sampler, spp):
     assert float(np.sqrt(((a - b) ** 2).mean()) / a.mean()) < 1e-5      # the film partials are summed in another order
 
 
+def test_tev_and_sequential_displays(P, tmp_path):
+    """--display-server / --sequential-display (displays/tev/display.rs:155-243 packet layout, 128-pixel tiles :245-330;
+    displays/sequential): a mock tev server receives CreateImage + one UpdateImage per tile and reassembles the film."""
+    import socket
+    import struct
+    import threading
+    from pbrt_r3_b200 import display, imageio
+    W, H = 200, 150
+    rgb = np.random.RandomState(1).uniform(0, 2, (H, W, 3)).astype(np.float32)
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    got = bytearray()
+
+    def serve():
+        c, _ = srv.accept()
+        while True:
+            d = c.recv(1 << 16)
+            if not d:
+                break
+            got.extend(d)
+        c.close()
+    th = threading.Thread(target=serve)
+    th.start()
+
+    class HS:                                   # what display.show reads of a HostScene
+        filename = "out.exr"
+        class desc:
+            class film:
+                full_resolution = (W + 10, H + 20)
+                cropped_pixel_bounds = (5, 10, 5 + W, 10 + H)
+    tev = display.TevDisplay("127.0.0.1:%d" % srv.getsockname()[1])
+    seq = display.SequentialDisplay(str(tmp_path / "frames"))
+    display.show([tev, seq], HS, rgb)
+    tev.close()
+    th.join(timeout=10)
+    srv.close()
+    # parse the stream: u32 length (of the whole packet) | u8 type | u8 grab_focus | name\0 | ...
+    out = np.zeros((H + 20, W + 10, 3), np.float32)
+    pos, kinds = 0, []
+    while pos < len(got):
+        n, kind, focus = struct.unpack_from("<IBB", got, pos)
+        body = bytes(got[pos + 6:pos + n])
+        name, body = body.split(b"\0", 1)
+        assert name == b"out.exr"
+        kinds.append(kind)
+        if kind == display.CREATE_IMAGE:
+            w, h, nc = struct.unpack_from("<III", body)
+            assert (w, h, nc, focus) == (W + 10, H + 20, 3, 1) and body[12:] == b"R\0G\0B\0"
+        else:
+            assert kind == display.UPDATE_IMAGE and focus == 0
+            nc, = struct.unpack_from("<I", body)
+            assert body[4:10] == b"R\0G\0B\0"
+            x, y, w, h = struct.unpack_from("<IIII", body, 10)
+            assert struct.unpack_from("<6q", body, 26) == (0, 1, 2, 3, 3, 3) and w <= 128 and h <= 128
+            out[y:y + h, x:x + w] = np.frombuffer(body, "<f4", w * h * 3, 26 + 48).reshape(h, w, 3)
+        pos += n
+    assert kinds[0] == display.CREATE_IMAGE and kinds.count(display.UPDATE_IMAGE) == 2 * 2     # 200 x 150 in 128-pixel tiles
+    assert np.array_equal(out[10:10 + H, 5:5 + W], rgb)
+    frame = imageio.read_exr(str(tmp_path / "frames" / "00000000.exr"))
+    assert np.array_equal(frame[10:10 + H, 5:5 + W], rgb) and frame.shape == (H + 20, W + 10, 3)
+    with pytest.raises(ValueError):
+        display.TevDisplay("nohostport")
+
+
 def test_exr_reader_compressions(tmp_path):
     """read_exr also reads what other encoders write (tools/run_reference.sh: the reference's `image` crate): ZIPS / ZIP /
     RLE scan-line blocks (byte predictor + even / odd interleave, OpenEXR file layout), HALF and FLOAT channels, RGBA."""
