@@ -381,6 +381,10 @@ int pt_parse_file(const char* path, int pixelsamples_override, int spectrum_kind
 int pt_parse_string(const char* text, int pixelsamples_override, int spectrum_kind, pt_host_scene** out);
 const pt_scene_desc* pt_host_scene_desc(const pt_host_scene* hs);
 const char* pt_host_scene_filename(const pt_host_scene* hs);   /* Film "filename" */
+/* The warnings the parse produced (the reference logs them with warn!: unknown materials falling back to matte,
+ * create_material.rs:65-70; invalid meshes; unreadable SPD files, ...): message i < count, else NULL. */
+uint32_t pt_host_scene_warning_count(const pt_host_scene* hs);
+const char* pt_host_scene_warning(const pt_host_scene* hs, uint32_t i);
 void pt_host_scene_destroy(pt_host_scene* hs);
 
 #ifdef __cplusplus

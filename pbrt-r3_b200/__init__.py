@@ -65,6 +65,11 @@ class HostScene:
         return self._lib.pt_host_scene_filename(self._h).decode()
 
     @property
+    def warnings(self):
+        """what the reference would log with warn! while parsing"""
+        return [self._lib.pt_host_scene_warning(self._h, i).decode() for i in range(self._lib.pt_host_scene_warning_count(self._h))]
+
+    @property
     def image_shape(self):
         b = self.desc.film.cropped_pixel_bounds
         return (b[3] - b[1], b[2] - b[0], 3)

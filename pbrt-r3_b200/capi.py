@@ -111,7 +111,7 @@ EXPORTS = [
     "pt_scene_create", "pt_scene_destroy", "pt_scene_reupload", "pt_last_error", "pt_abi_version", "pt_render", "pt_render_partial", "pt_film_resolve",
     "pt_film_clear", "pt_intersect", "pt_intersect_p", "pt_intersect_device", "pt_sampler_values", "pt_camera_rays", "pt_li",
     "pt_bvh_info", "pt_bvh_node", "pt_light_distribution", "pt_parse_file", "pt_parse_string", "pt_host_scene_desc",
-    "pt_host_scene_filename", "pt_host_scene_destroy", "pt_host_bvh_build", "pt_host_bvh_info", "pt_host_bvh_node",
+    "pt_host_scene_filename", "pt_host_scene_warning_count", "pt_host_scene_warning", "pt_host_scene_destroy", "pt_host_bvh_build", "pt_host_bvh_info", "pt_host_bvh_node",
     "pt_host_bvh_destroy", "pt_set_options", "pt_get_options",
 ]
 
@@ -137,6 +137,10 @@ def load(path=None):
     lib.pt_host_scene_desc.restype = C.POINTER(pt_scene_desc)
     lib.pt_host_scene_filename.argtypes = [vp]
     lib.pt_host_scene_filename.restype = C.c_char_p
+    lib.pt_host_scene_warning_count.argtypes = [vp]
+    lib.pt_host_scene_warning_count.restype = C.c_uint32
+    lib.pt_host_scene_warning.argtypes = [vp, C.c_uint32]
+    lib.pt_host_scene_warning.restype = C.c_char_p
     lib.pt_host_scene_destroy.argtypes = [vp]
     lib.pt_host_scene_destroy.restype = None
     lib.pt_host_bvh_build.argtypes = [C.POINTER(pt_scene_desc), C.POINTER(vp)]

@@ -70,6 +70,9 @@ def render_scene(path, opts):
     ps = max(1, opts.pixelsamples) if opts.pixelsamples is not None else -1
     hs = P.HostScene.parse_file(path, ps, opts.spectrum)
     name = opts.outfile if opts.outfile else hs.filename
+    if rank == 0 and not opts.quiet:
+        for w in hs.warnings:
+            sys.stderr.write("WARNING: %s\n" % w)
     sc = P.Scene(hs, local)
     try:
         if world == 1:

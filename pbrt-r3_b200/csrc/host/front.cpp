@@ -181,9 +181,22 @@ struct Builder {
         *out = spec.from_sampled(lam, val);
         return true;
       }
-      if (!q->s.empty()) throw ParseError("spectrum files are not supported (\"" + key + "\")");
+      if (!q->s.empty()) {
+        // The reference loads the file (an unreadable one is reported) and then files the spectrum under the FILE's name
+        // (scene_context.rs:744-758: add_spectrum_no_key(name, ..)), where find_one_spectrum(key) never looks: the parameter
+        // keeps its default.  Reproduced: the file is opened for the same diagnostic, its values are not used.
+        for (const std::string& fn : q->s) {
+          std::string path = (fn.size() && fn[0] == '/') ? fn : (cur_dir.empty() ? fn : cur_dir + "/" + fn);
+          std::ifstream f(path);
+          if (!f) warn("Unable to read SPD file \"" + path + "\".");
+        }
+        warn("spectrum file parameter \"" + key + "\": pbrt-r3 stores it under the file's name, so the parameter keeps its default (reproduced)");
+        return false;
+      }
     }
-    if (ps.find(PC_BLACKBODY, key)) throw ParseError("blackbody spectra are not supported (\"" + key + "\")");
+    if (const Param* q = ps.find(PC_BLACKBODY, key)) {  // scene_context.rs:763-778
+      if (q->f.size() >= 2) { *out = spec.from_blackbody(q->f); return true; }
+    }
     return false;
   }
   std::vector<float> one_spectrum(const ParamSet& ps, const std::string& key, float dflt) {
@@ -1165,6 +1178,8 @@ int pt_parse_file(const char* path, int pixelsamples_override, int spectrum_kind
 
 const pt_scene_desc* pt_host_scene_desc(const pt_host_scene* hs) { return hs ? &hs->desc : nullptr; }
 const char* pt_host_scene_filename(const pt_host_scene* hs) { return hs ? hs->filename.c_str() : ""; }
+uint32_t pt_host_scene_warning_count(const pt_host_scene* hs) { return hs ? (uint32_t)hs->warnings.size() : 0u; }
+const char* pt_host_scene_warning(const pt_host_scene* hs, uint32_t i) { return (hs && i < hs->warnings.size()) ? hs->warnings[i].c_str() : nullptr; }
 void pt_host_scene_destroy(pt_host_scene* hs) { delete hs; }
 
 }  // extern "C"

@@ -107,6 +107,46 @@ class SpectrumFactory {
     return std::vector<float>{rgb[0], rgb[1], rgb[2]};
   }
 
+  // "blackbody" parameters (pairs of temperature, scale) go through SampledSpectrum even in an RGB build: SampledSpectrum::
+  // from_blackbody (sampled.rs:241-251: blackbody_normalized over CIE_LAMBDA, blackbody.rs:3-33, averaged into the 60 bins)
+  // and then Spectrum::from(&SampledSpectrum) = to_rgb for RGBSpectrum (scene_context.rs:763-778, rgb.rs:409-413)
+  std::vector<float> from_blackbody(const std::vector<float>& values) {
+    load_cie();
+    std::vector<float> s((size_t)NS, 0.0f);
+    for (size_t i = 0; i + 1 < values.size(); i += 2) {
+      const double t = (double)values[i];
+      auto planck = [&](double lambda_nm) {
+        if (t <= 0.0) return 0.0;
+        const double C = 299792458.0, H = 6.62606957e-34, KB = 1.3806488e-23;
+        const double l = lambda_nm * 1e-9;
+        const double lambda5 = (l * l) * (l * l) * l;
+        return (2.0 * H * C * C) / (lambda5 * (std::exp((H * C) / (l * KB * t)) - 1.0));
+      };
+      const double max_l = planck(2.8977721e-3 / t * 1e9);
+      std::vector<float> v(471);
+      for (int k = 0; k < 471; k++) v[(size_t)k] = (float)(planck((double)cie_[3][(size_t)k]) / max_l);
+      std::vector<float> b = sample_spectrum(cie_[3], v);
+      for (int k = 0; k < NS; k++) s[(size_t)k] += b[(size_t)k] * values[i + 1];
+    }
+    return from_binned(s);
+  }
+  // Spectrum::from(&SampledSpectrum): the 60 bins themselves, or SampledSpectrum::to_rgb (sampled.rs:53-67, 89-92)
+  std::vector<float> from_binned(const std::vector<float>& s60) {
+    if (kind_ == 1) return s60;
+    load_sampled_tables();
+    float xyz[3] = {0, 0, 0};
+    for (int i = 0; i < NS; i++) {
+      xyz[0] += xyz60_[0][(size_t)i] * s60[(size_t)i];
+      xyz[1] += xyz60_[1][(size_t)i] * s60[(size_t)i];
+      xyz[2] += xyz60_[2][(size_t)i] * s60[(size_t)i];
+    }
+    const float scale = (float)(700 - 400) / (CIE_Y_INTEGRAL * (float)NS);
+    for (float& c : xyz) c *= scale;
+    float rgb[3];
+    xyz_to_rgb(xyz, rgb);
+    return std::vector<float>{rgb[0], rgb[1], rgb[2]};
+  }
+
   // materials/metal.rs:87-129 default copper eta / k
   std::vector<float> copper_n() { return from_sampled(copper_lambda(), copper(true)); }
   std::vector<float> copper_k() { return from_sampled(copper_lambda(), copper(false)); }

@@ -211,6 +211,51 @@ def test_front_end_tree_integrators(P):
         lib.pt_set_options(P.capi.pt_options(0, 0))
 
 
+def test_front_end_blackbody_and_spectrum_files(P, tmp_path):
+    """ "blackbody" parameters (scene_context.rs:763-778 -> SampledSpectrum::from_blackbody, sampled.rs:241-251, blackbody.rs)
+    against a float64 restatement; "spectrum" FILE parameters keep the parameter's default, like the reference (which
+    files the loaded spectrum under the file's name, scene_context.rs:744-758)."""
+    base = 'Camera "perspective"\nWorldBegin\nAttributeBegin\nAreaLightSource "diffuse" %s\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nAttributeEnd\nWorldEnd\n'
+
+    def light_spectrum(hs):
+        d, nc = hs.desc, hs.desc.n_channels
+        return np.array([d.spectra[d.lights[0].spectrum * nc + k] for k in range(nc)], np.float64)
+
+    def planck(lam_nm, t):
+        c, h, kb = 299792458.0, 6.62606957e-34, 1.3806488e-23
+        l = lam_nm * 1e-9
+        return (2 * h * c * c) / (l ** 5 * (np.exp((h * c) / (l * kb * t)) - 1))
+
+    def bins60(pairs):
+        lam = np.arange(360, 831, dtype=np.float64)
+        out = np.zeros(60)
+        for t, sc in pairs:
+            v = planck(lam, t) / planck(2.8977721e-3 / t * 1e9, t)
+            fine = np.linspace(400, 700, 60 * 200 + 1)
+            vf = np.interp(fine, lam, v)
+            out += np.array([np.trapezoid(vf[i * 200:(i + 1) * 200 + 1], fine[i * 200:(i + 1) * 200 + 1]) / 5.0 for i in range(60)]) * sc
+        return out
+    for pairs in ([(6500.0, 1.0)], [(3000.0, 2.5)], [(6500.0, 1.0), (3000.0, 0.5)]):
+        txt = base % ('"blackbody L" [%s]' % " ".join("%g %g" % p for p in pairs))
+        ref = bins60(pairs)
+        got = light_spectrum(P.HostScene.parse_string(txt, spectrum="sampled"))
+        assert np.allclose(got, ref, rtol=2e-4), (pairs, np.abs(got / ref - 1).max())
+        rgb = light_spectrum(P.HostScene.parse_string(txt))
+        # RGB build: SampledSpectrum::to_rgb of the same bins; the 60-bin X/Y/Z tables are the library's own data: compare through Y
+        y = 0.212671 * rgb[0] + 0.715160 * rgb[1] + 0.072169 * rgb[2]
+        assert 0.5 * ref.mean() < y < 1.5 * ref.max() and rgb.min() > 0
+    assert light_spectrum(P.HostScene.parse_string(base % '"blackbody L" [3000 1]'))[0] > 2 * light_spectrum(P.HostScene.parse_string(base % '"blackbody L" [3000 1]'))[2]   # warm light
+    (tmp_path / "x.spd").write_text("400 0.1\n700 0.9\n")
+    hs = P.HostScene.parse_string(base % ('"spectrum L" ["%s"]' % (tmp_path / "x.spd")))
+    assert list(light_spectrum(hs)) == [1.0, 1.0, 1.0]            # the default of "L" (diffuse.rs:175)
+    assert any("spectrum file" in w for w in hs.warnings)
+    hs = P.HostScene.parse_string(base % '"spectrum L" ["missing.spd"]')
+    assert any("Unable to read SPD file" in w for w in hs.warnings)
+    hs = P.HostScene.parse_string(base % '"spectrum L" [400 2 700 2]')        # inline samples do take effect (param_set.rs add_sampled_spectrum)
+    v = light_spectrum(hs)
+    assert abs(0.212671 * v[0] + 0.715160 * v[1] + 0.072169 * v[2] - 2.0) < 0.02      # an equal-energy spectrum of 2: Y = 2
+
+
 def test_front_end_extra_materials(P):
     base = 'Camera "perspective"\nWorldBegin\nMaterial %s\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n'
     sp = lambda hs, i: [hs.desc.spectra[3 * i + k] for k in range(3)]
