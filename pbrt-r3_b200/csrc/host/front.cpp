@@ -15,6 +15,12 @@
 #include "spectrum_host.h"
 #include "xform.h"
 
+#include <dirent.h>
+#include <ftw.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -50,6 +56,8 @@ struct pt_host_scene {
 };
 
 namespace {
+
+bool read_text_file(const std::string& path, std::string* out);  // plain or gzipped text (defined below)
 
 struct MaterialInstance {
   std::string name;  // plugin name ("" = none)
@@ -924,12 +932,10 @@ struct Builder {
       else if (d == "Include") {
         std::string n = read_string(lx);
         std::string path = (n.size() && n[0] == '/') ? n : (dir.empty() ? n : dir + "/" + n);
-        std::ifstream f(path);
-        if (!f) throw ParseError("Include: cannot open \"" + path + "\"");
-        std::stringstream ss;
-        ss << f.rdbuf();
+        std::string text;
+        if (!read_text_file(path, &text)) throw ParseError("Include: cannot open \"" + path + "\"");
         size_t slash = path.find_last_of('/');
-        parse_text(ss.str(), slash == std::string::npos ? "" : path.substr(0, slash));
+        parse_text(text, slash == std::string::npos ? "" : path.substr(0, slash));
       }
       else if (d == "MakeNamedMedium") { read_string(lx); parse_params(lx); }
       else if (d == "MediumInterface") { read_string(lx); if (lx.peek().kind == TK_STRING) read_string(lx); }
@@ -1139,6 +1145,95 @@ struct Builder {
   }
 };
 
+// read_to_string (core/parser/read_file.rs:38-54): files whose extension is "gz" are gunzipped
+bool read_text_file(const std::string& path, std::string* out) {
+  out->clear();
+  if (path.size() > 3 && path.substr(path.size() - 3) == ".gz") {
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) return false;
+    char buf[1 << 16];
+    int n;
+    while ((n = gzread(g, buf, sizeof(buf))) > 0) out->append(buf, (size_t)n);
+    gzclose(g);
+    return n == 0;
+  }
+  std::ifstream f(path, std::ios::binary);
+  if (!f) return false;
+  std::stringstream ss;
+  ss << f.rdbuf();
+  *out = ss.str();
+  return true;
+}
+
+// pbrt_parse_targz (core/parser/parser.rs:32-58): the archive is unpacked into a temporary directory, the first ".pbrt"
+// file found in it is the scene, the directory is removed after the parse.  ustar / GNU archives with regular files,
+// directories and GNU long names; entries that would leave the directory are refused.
+struct TempDir {
+  std::string path;
+  ~TempDir() {
+    if (path.empty()) return;
+    nftw(path.c_str(), [](const char* p, const struct stat*, int, struct FTW*) { return remove(p); }, 16, FTW_DEPTH | FTW_PHYS);
+  }
+};
+void mkdirs(const std::string& path) {
+  for (size_t i = 1; i <= path.size(); i++)
+    if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0700);
+}
+std::string untar_scene(const std::string& archive, TempDir* tmp) {
+  std::string data;
+  if (!read_text_file(archive, &data)) throw ParseError("cannot read \"" + archive + "\"");
+  char templ[] = "/tmp/pbrt_r3_b200_XXXXXX";
+  if (!mkdtemp(templ)) throw ParseError("cannot create a temporary directory");
+  tmp->path = templ;
+  std::string longname;
+  for (size_t pos = 0; pos + 512 <= data.size();) {
+    const char* h = data.data() + pos;
+    if (h[0] == '\0') break;
+    std::string name(h, strnlen(h, 100));
+    if (memcmp(h + 257, "ustar", 5) == 0 && h[345]) name = std::string(h + 345, strnlen(h + 345, 155)) + "/" + name;
+    const size_t size = (size_t)strtoull(std::string(h + 124, 12).c_str(), nullptr, 8);
+    const char type = h[156];
+    pos += 512;
+    if (pos + size > data.size()) throw ParseError("truncated archive \"" + archive + "\"");
+    if (type == 'L') { longname.assign(data.data() + pos, strnlen(data.data() + pos, size)); pos += (size + 511) / 512 * 512; continue; }
+    if (!longname.empty()) { name = longname; longname.clear(); }
+    if (name.empty() || name[0] == '/' || name.find("..") != std::string::npos) throw ParseError("archive entry \"" + name + "\" leaves the archive");
+    const std::string full = tmp->path + "/" + name;
+    if (type == '5') mkdirs(full);
+    else if (type == '0' || type == '\0') {
+      size_t slash = full.find_last_of('/');
+      mkdirs(full.substr(0, slash));
+      std::ofstream o(full, std::ios::binary);
+      o.write(data.data() + pos, (std::streamsize)size);
+    }
+    pos += (size + 511) / 512 * 512;
+  }
+  // the first .pbrt file, directories in name order (the reference takes read_dir's order)
+  std::vector<std::string> found;
+  std::vector<std::string> stack{tmp->path};
+  while (!stack.empty() && found.empty()) {
+    std::string d = stack.back();
+    stack.pop_back();
+    std::vector<std::string> names;
+    if (DIR* dp = opendir(d.c_str())) {
+      while (struct dirent* e = readdir(dp)) if (strcmp(e->d_name, ".") && strcmp(e->d_name, "..")) names.push_back(e->d_name);
+      closedir(dp);
+    }
+    std::sort(names.begin(), names.end());
+    std::vector<std::string> dirs;
+    for (const std::string& n : names) {
+      struct stat st;
+      const std::string p = d + "/" + n;
+      if (stat(p.c_str(), &st)) continue;
+      if (S_ISDIR(st.st_mode)) dirs.push_back(p);
+      else if (n.size() > 5 && n.substr(n.size() - 5) == ".pbrt") { found.push_back(p); break; }
+    }
+    for (auto it = dirs.rbegin(); it != dirs.rend(); ++it) stack.push_back(*it);
+  }
+  if (found.empty()) throw ParseError("no .pbrt file in \"" + archive + "\"");
+  return found[0];
+}
+
 int parse_common(const std::string& text, const std::string& dir, int pixelsamples_override, int spectrum_kind, pt_host_scene** out) {
   *out = nullptr;
   std::unique_ptr<pt_host_scene> hs(new pt_host_scene());
@@ -1167,13 +1262,14 @@ int pt_parse_string(const char* text, int pixelsamples_override, int spectrum_ki
 
 int pt_parse_file(const char* path, int pixelsamples_override, int spectrum_kind, pt_host_scene** out) {
   if (!path || !out) { pt_set_error("pt_parse_file: null argument"); return 1; }
-  std::ifstream f(path);
-  if (!f) { pt_set_error(std::string("pt_parse_file: cannot open ") + path); return 1; }
-  std::stringstream ss;
-  ss << f.rdbuf();
-  std::string p(path);
+  std::string p(path), text;
+  TempDir tmp;  // a ".tar.gz" scene lives in a temporary directory for the duration of the parse (parser.rs:60-63)
+  if (p.size() > 7 && p.substr(p.size() - 7) == ".tar.gz") {
+    try { p = untar_scene(p, &tmp); } catch (const std::exception& e) { pt_set_error(std::string("pt_parse_file: ") + e.what()); return 1; }
+  }
+  if (!read_text_file(p, &text)) { pt_set_error(std::string("pt_parse_file: cannot open ") + p); return 1; }
   size_t slash = p.find_last_of('/');
-  return parse_common(ss.str(), slash == std::string::npos ? "" : p.substr(0, slash), pixelsamples_override, spectrum_kind, out);
+  return parse_common(text, slash == std::string::npos ? "" : p.substr(0, slash), pixelsamples_override, spectrum_kind, out);
 }
 
 const pt_scene_desc* pt_host_scene_desc(const pt_host_scene* hs) { return hs ? &hs->desc : nullptr; }

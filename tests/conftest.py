@@ -49,7 +49,7 @@ def build_hostcheck():
     deps += [os.path.join(ROOT, "tests", "hostcheck", "cuda_shim.h"), os.path.join(ROOT, "include", "pbrt_r3_b200.h")]
     if not os.path.exists(HOSTCHECK_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOSTCHECK_LIB) for d in deps):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-DPT_HOSTCHECK", "-DPT_NCS=3", "-I", os.path.join(ROOT, "tests", "hostcheck"),
-                               "-x", "c++", "-pthread", "-o", HOSTCHECK_LIB] + srcs + ["-ldl"])
+                               "-x", "c++", "-pthread", "-o", HOSTCHECK_LIB] + srcs + ["-ldl", "-lz"])
     return HOSTCHECK_LIB
 
 

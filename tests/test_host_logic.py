@@ -211,6 +211,29 @@ def test_front_end_tree_integrators(P):
         lib.pt_set_options(P.capi.pt_options(0, 0))
 
 
+def test_front_end_targz_and_gz_scenes(P, tmp_path):
+    """pbrt_parse_file on a ".tar.gz" scene (parser.rs:32-63: unpacked into a temporary directory, first .pbrt file) whose
+    main file Includes a gzipped file (read_file.rs:38-54); same scene as the plain text."""
+    import gzip
+    import tarfile
+    txt = P.scenes.cornell_box(res=16, spp=1)
+    head, rest = txt.split("WorldBegin\n", 1)
+    os.makedirs(tmp_path / "scene" / "geo")
+    (tmp_path / "scene" / "main.pbrt").write_text(head + 'WorldBegin\nInclude "geo/world.pbrt.gz"\n')
+    with gzip.open(tmp_path / "scene" / "geo" / "world.pbrt.gz", "wt") as f:
+        f.write(rest)
+    with tarfile.open(tmp_path / "scene.tar.gz", "w:gz") as t:
+        t.add(tmp_path / "scene", arcname="a_rather_long_directory_name_" * 5 + "/scene")     # GNU long names
+    a, b, c = P.HostScene.parse_string(txt), P.HostScene.parse_file(str(tmp_path / "scene.tar.gz")), P.HostScene.parse_file(str(tmp_path / "scene" / "main.pbrt"))
+    for x in (b, c):
+        assert x.desc.n_tris == a.desc.n_tris == 32 and x.desc.n_lights == a.desc.n_lights
+        assert np.array_equal(np.ctypeslib.as_array(x.desc.tri_p, (32 * 9,)), np.ctypeslib.as_array(a.desc.tri_p, (32 * 9,)))
+    assert not [n for n in os.listdir("/tmp") if n.startswith("pbrt_r3_b200_")]          # the temporary directory is gone
+    (tmp_path / "empty.tar.gz").write_bytes(gzip.compress(b"\0" * 1024))
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_file(str(tmp_path / "empty.tar.gz"))
+
+
 def test_front_end_blackbody_and_spectrum_files(P, tmp_path):
     """ "blackbody" parameters (scene_context.rs:763-778 -> SampledSpectrum::from_blackbody, sampled.rs:241-251, blackbody.rs)
     against a float64 restatement; "spectrum" FILE parameters keep the parameter's default, like the reference (which

@@ -16,7 +16,7 @@ if [ -f $SRC/shade_tu.cu ]; then
   /usr/local/cuda/bin/nvcc $COMMON $SHADE_FLAGS -c $SRC/shade_tu.cu -o /tmp/shade_$NAME.o 2> /tmp/shade_$NAME.log || (cat /tmp/shade_$NAME.log; false)
   OBJS="$OBJS /tmp/shade_$NAME.o"
 fi
-/usr/local/cuda/bin/nvcc -shared -o ../variants/lib_$NAME.so host/front.o host/api_common.o host/bvh_build.o host/scene_accel.o $OBJS -lcudart_static -ldl -lpthread -lrt 2>/dev/null
+/usr/local/cuda/bin/nvcc -shared -o ../variants/lib_$NAME.so host/front.o host/api_common.o host/bvh_build.o host/scene_accel.o $OBJS -lcudart_static -ldl -lpthread -lrt -lz 2>/dev/null
 cp -r ../data ../variants/ 2>/dev/null || true
 grep -A2 "Function properties for _ZN3ptd7k_traceILi3ELb0ELb0" /tmp/dev_$NAME.log | grep -E "Used|spill" | tr '\n' ' '; echo
 echo built ../variants/lib_$NAME.so
