@@ -1196,6 +1196,20 @@ std::string untar_scene(const std::string& archive, TempDir* tmp) {
     pos += 512;
     if (pos + size > data.size()) throw ParseError("truncated archive \"" + archive + "\"");
     if (type == 'L') { longname.assign(data.data() + pos, strnlen(data.data() + pos, size)); pos += (size + 511) / 512 * 512; continue; }
+    if (type == 'x') {  // pax extended header: records "<length> key=value\n"; "path" names the next entry
+      const std::string rec(data.data() + pos, size);
+      for (size_t q = 0; q < rec.size();) {
+        const size_t len = (size_t)strtoull(rec.c_str() + q, nullptr, 10);
+        if (len == 0 || q + len > rec.size()) break;
+        const std::string one = rec.substr(q, len);
+        const size_t sp = one.find(' '), eq = one.find('=');
+        if (sp != std::string::npos && eq != std::string::npos && one.substr(sp + 1, eq - sp - 1) == "path") longname = one.substr(eq + 1, one.size() - eq - 2);
+        q += len;
+      }
+      pos += (size + 511) / 512 * 512;
+      continue;
+    }
+    if (type == 'g') { pos += (size + 511) / 512 * 512; continue; }
     if (!longname.empty()) { name = longname; longname.clear(); }
     if (name.empty() || name[0] == '/' || name.find("..") != std::string::npos) throw ParseError("archive entry \"" + name + "\" leaves the archive");
     const std::string full = tmp->path + "/" + name;
