@@ -750,6 +750,19 @@ int shade_classes(pt_scene* s, int NC, int grid, unsigned long long* vc) {
   return n;
 }
 
+// k_ri in the variant the scene needs: two-lobe BSDFs unless it has uber / translucent materials, the infinite-light code
+// only with an infinite light (the generic kernel is 10-20 % slower with either compiled in)
+template <int NC>
+void launch_ri(pt_scene* s, int grid, const WaveState& W, const Queues& Q, uint32_t n_ext, uint32_t n_wait, const uint32_t* prev, unsigned long long* vc) {
+  if constexpr (NC == 3) {
+    const bool wide = (s->class_mask & (1u << CL_EXTRA)) != 0, env = s->h.n_inf != 0;
+#define PT_RI(ML, ENV) PT_LAUNCH(grid, PT_SHADE_BLOCK, s->stream, k_ri<NC, ML, ENV>)(s->h, W, Q, Q.wait, n_ext, n_wait, prev, vc)
+    if (wide) { if (env) PT_RI(PT_LOBES_EXTRA, true); else PT_RI(PT_LOBES_EXTRA, false); }
+    else { if (env) PT_RI(PT_MAX_LOBES, true); else PT_RI(PT_MAX_LOBES, false); }
+#undef PT_RI
+  }
+}
+
 struct WaveTotals {
   uint64_t regular = 0, shadow = 0, launches = 0, trace_launches = 0, trace_rays = 0;
   double trace_ms = 0, shade_ms = 0;
@@ -805,8 +818,9 @@ int run_bounces(pt_scene* s, uint32_t n, bool count, bool timed, WaveTotals* T) 
       }
     } else if (s->h.integrator.type == PT_INTEGRATOR_DIRECT || s->h.integrator.type == PT_INTEGRATOR_WHITTED) {
       if constexpr (NC == 3) {  // one step of the specular-tree walk of every path in flight
-        PT_LAUNCH(grid_for(s, (size_t)counts[0] + n_wait, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_ri<NC>)(s->h, W, Q, Q.wait, counts[0], n_wait, nullptr,
-                                                                                                                                count ? s->counters + 2 : nullptr);
+        const int gr = grid_for(s, (size_t)counts[0] + n_wait, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
+        unsigned long long* vc = count ? s->counters + 2 : nullptr;
+        launch_ri<NC>(s, gr, W, Q, counts[0], n_wait, nullptr, vc);
         CK(cudaGetLastError());
         std::swap(Q.wait, Q.wait_next);
         T->launches++;
@@ -1127,8 +1141,9 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
       }
     } else if (is_ri) {  // directlighting / whitted: one step of the specular-tree walk of every path in flight
       if constexpr (NC == 3) {
-        PT_LAUNCH(grid_for(s, (size_t)ub_ext + ub_side, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM), PT_SHADE_BLOCK, s->stream, k_ri<NC>)(s->h, W, Q, Q.wait, n_new, 0u, Q.counts + 24,
-                                                                                                                             count ? s->counters + 2 : nullptr);
+        const int gr = grid_for(s, (size_t)ub_ext + ub_side, PT_SHADE_BLOCK, PT_SHADE_GRID_PER_SM);
+        unsigned long long* vc = count ? s->counters + 2 : nullptr;
+        launch_ri<NC>(s, gr, W, Q, n_new, 0u, Q.counts + 24, vc);
         if ((rc = (cudaGetLastError() != cudaSuccess))) { pt_set_error("k_ri launch failed"); break; }
         std::swap(Q.wait, Q.wait_next);
         T.launches++;

@@ -743,9 +743,12 @@ PT_HD void ao_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i) {
 // array from the same two dimensions), or one get_2d pair per light once the max_depth * n_lights * 2 arrays are used up.
 // flags: bits 0-7 frames on the stack, 8-15 depth, 16-30 lighting round of the vertex, 31 the vertex reads sample arrays.
 #define PT_RI_MAX_DEPTH 32
-template <int NC>
+// ML: lobes per BSDF (2, or 5 when the scene has uber / translucent materials: the wider BSDF costs 10-19 % of this stage)
+// ENV: the scene has infinite lights (as for the shade kernels, their code is compiled into separate variants)
+template <int NC, int ML, bool ENV>
 PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fresh, unsigned long long* vertex_counter) {
   const uint32_t cap = W.cap;
+  constexpr int CM = ML == PT_MAX_LOBES ? (PT_CM_ANY & ~((1 << LB_LAMBERT_T) | (1 << LB_FRESNEL_BLEND))) : PT_CM_ANY;  // the extra materials' lobes only with them
   const bool whitted = S.integrator.type == PT_INTEGRATOR_WHITTED;
   const int NONSPEC = F_ALL & ~F_SPEC;
   Sp<NC> L = st_load<NC>(W.L, cap, i);
@@ -775,11 +778,11 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
   bool push_sh = false, push_mis = false, push_ext = false, push_wait = false;
   bool need_pop = false, have_vertex = false;
   SurfD si;
-  BsdfT<PT_LOBES_EXTRA> B;
+  BsdfT<ML> B;
   B.n = -1;
   if ((int)fbits(h4.w) < 0) {  // the ray left the scene: li = sum of Light::le (directlighting.rs:112-122, whitted.rs:86-96)
     need_pop = true;
-    if (fresh)
+    if (ENV && fresh)
       for (uint32_t k = 0; k < S.n_inf; k++) L = L + beta * env_le<NC>(S, ldg(S.inf_lights + k), xyz(rd4));
   } else {
     si = make_surface(S, (int)fbits(h4.w), inst, xyz(ro4), xyz(rd4), rtime, h4.x, h4.y, h4.z);
@@ -843,10 +846,10 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
         round++;
         const pt_light& LT = S.lights[ln];
         LightSampleD<NC> ls;
-        const bool ok = light_sample<NC, true>(S, ln, ref, u_light, &ls);
+        const bool ok = light_sample<NC, ENV>(S, ln, ref, u_light, &ls);
         if (whitted) {  // whitted.rs:61-79: BSDF over all lobes, shading normal, no MIS
           if (ok && !(ls.pdf <= 0.0f || sp_black(ls.li))) {
-            Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, F_ALL);
+            Sp<NC> f = bsdf_f<NC, CM>(S, B, si.wo, ls.wi, F_ALL);
             if (!sp_black(f)) {
               st_store<NC>(W.pendA, cap, i, beta * (f * ls.li * (absdot3(ls.wi, si.sn) / ls.pdf)));
               W.sh_o[i] = mk4(ls.sh_o.x, ls.sh_o.y, ls.sh_o.z, 0.0f);
@@ -858,10 +861,10 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
           continue;
         }
         // estimate_direct_surface (sample_lights.rs:330-453), as in shade_body
-        const bool delta = LT.type != PT_LIGHT_AREA && LT.type != PT_LIGHT_INFINITE;
+        const bool delta = LT.type != PT_LIGHT_AREA && !(ENV && LT.type == PT_LIGHT_INFINITE);
         if (ok && ls.pdf > 0.0f && !sp_black(ls.li)) {
-          Sp<NC> f = bsdf_f<NC>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
-          float spdf = bsdf_pdf(B, si.wo, ls.wi, NONSPEC);
+          Sp<NC> f = bsdf_f<NC, CM>(S, B, si.wo, ls.wi, NONSPEC) * absdot3(ls.wi, si.sn);
+          float spdf = bsdf_pdf<CM>(B, si.wo, ls.wi, NONSPEC);
           if (!sp_black(f)) {
             Sp<NC> ld;
             if (delta) ld = f * ls.li / ls.pdf;
@@ -878,18 +881,18 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
           f3 wi2;
           float pdf2;
           int stype;
-          if (bsdf_sample<NC>(S, B, si.wo, u_scat, NONSPEC, &f2v, &wi2, &pdf2, &stype)) {
+          if (bsdf_sample<NC, CM>(S, B, si.wo, u_scat, NONSPEC, &f2v, &wi2, &pdf2, &stype)) {
             Sp<NC> f = f2v * absdot3(wi2, si.sn);
             if (!sp_black(f) && pdf2 > 0.0f) {
               float weight = 1.0f;
               bool go = true;
               if (!(stype & F_SPEC)) {
-                float lp = light_pdf_li<true>(S, ln, ref, wi2);
+                float lp = light_pdf_li<ENV>(S, ln, ref, wi2);
                 if (lp == 0.0f) go = false;
                 else weight = power_heuristic1(pdf2, lp);
               }
               if (go) {
-                Sp<NC> li = LT.type == PT_LIGHT_INFINITE ? env_le<NC>(S, ln, wi2) : sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
+                Sp<NC> li = (ENV && LT.type == PT_LIGHT_INFINITE) ? env_le<NC>(S, ln, wi2) : sp_load<NC>(S.spectra + (size_t)LT.spectrum * NC);
                 Sp<NC> ld = f * li * sp_const<NC>(1.0f) * (weight / pdf2);
                 st_store<NC>(W.pendB, cap, i, beta * (ld / divisor));
                 f3 o = offset_origin(si.p, si.perr, si.n, wi2);
@@ -913,7 +916,7 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
           f3 wi;
           float pdf;
           int stype;
-          if (!bsdf_sample<NC>(S, B, si.wo, u, (branch == 0 ? F_REFL : F_TRANS) | F_SPEC, &f, &wi, &pdf, &stype)) continue;
+          if (!bsdf_sample<NC, CM>(S, B, si.wo, u, (branch == 0 ? F_REFL : F_TRANS) | F_SPEC, &f, &wi, &pdf, &stype)) continue;
           const float wi_ns = absdot3(wi, si.sn);
           if (!(pdf > 0.0f && !sp_black(f) && wi_ns != 0.0f)) continue;
           if (branch == 0) {  // come back for the transmission branch
@@ -956,7 +959,7 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
     float pdf;
     int stype;
     have_vertex = false;
-    if (!bsdf_sample<NC>(S, B, si.wo, u, F_TRANS | F_SPEC, &f, &wi, &pdf, &stype)) continue;
+    if (!bsdf_sample<NC, CM>(S, B, si.wo, u, F_TRANS | F_SPEC, &f, &wi, &pdf, &stype)) continue;
     const float wi_ns = absdot3(wi, si.sn);
     if (!(pdf > 0.0f && !sp_black(f) && wi_ns != 0.0f)) continue;
     beta = beta * (f * (wi_ns / pdf));
