@@ -58,11 +58,18 @@ wr = sum(p["dram__bytes_write.sum"] for p in per.values())
 l2 = sum(p["lts__t_bytes.sum"] for p in per.values())
 b = json.load(open(os.path.join(G, "bench_%s.json" % tag)))
 alg = b["roofline"]["bytes_per_ray"] * b["value"] * 1e6 * b["ms_per_step"] / 1e3 / b["roofline"]["trace_launches_per_step"]
-json.dump({"k_trace_dram_bytes_per_launch": (rd + wr) / n, "k_trace_dram_read_bytes_per_launch": rd / n, "k_trace_dram_write_bytes_per_launch": wr / n,
-           "k_trace_l2_bytes_per_launch": l2 / n, "k_trace_algorithmic_bytes_per_launch": alg, "launches": n,
-           "source": "profiles/%s_trace_traffic.csv: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum over the %d k_trace launches of the "
-                     "timed step of `bench.py --steps 1 --warmup 3 --no-cpu-baseline` (tools/gpu_round2.sh)" % (tag, n)},
-          open(os.path.join(P, "traffic.json"), "w"), indent=1)
+# profiles/traffic.json is keyed by bench config ("config5" = BASELINE configs[4], ...): bench.py reports the entry of the config it runs
+import re
+cfg_key = "config%d" % (int(re.search(r"configs\[(\d)\]", b["config"]["workload"]).group(1)) + 1)
+tpath = os.path.join(P, "traffic.json")
+allt = json.load(open(tpath)) if os.path.exists(tpath) else {}
+if "k_trace_dram_bytes_per_launch" in allt:      # the round-1 flat file was measured on config 2
+    allt = {"config2": allt}
+allt[cfg_key] = {"k_trace_dram_bytes_per_launch": (rd + wr) / n, "k_trace_dram_read_bytes_per_launch": rd / n, "k_trace_dram_write_bytes_per_launch": wr / n,
+                 "k_trace_l2_bytes_per_launch": l2 / n, "k_trace_algorithmic_bytes_per_launch": alg, "launches": n,
+                 "source": "profiles/%s_trace_traffic.csv: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum over the %d k_trace launches of the "
+                           "timed step of `bench.py --steps 1 --warmup 3 --no-cpu-baseline` (tools/gpu_r2final.sh)" % (tag, n)}
+json.dump(allt, open(tpath, "w"), indent=1)
 print("k_trace per launch: DRAM %.0f MB, L2 %.0f MB, algorithmic %.0f MB (%d launches)" % ((rd + wr) / n / 1e6, l2 / n / 1e6, alg / 1e6, n))
 for kind, width in (("trace", 260), ("shade", 420)):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), os.path.join(G, "prof_%s_%s.ncu-rep" % (kind, tag))], capture_output=True, text=True).stdout
