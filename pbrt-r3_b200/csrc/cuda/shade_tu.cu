@@ -13,8 +13,27 @@ namespace ptd {
 // One shade kernel per shading class; the bin size is read on the device (no host round trip between trace and shade).
 // ENV = the scene has infinite lights (LightSource "infinite"): a second set of kernels, so that every other scene runs
 // exactly the code it ran before the environment light existed.
+// CTAs per SM the register allocation aims at.  The specular classes (glass, mirror) do no light sampling: little
+// arithmetic between scattered loads, so they take more resident warps over registers (PT_SHADE_MINBLOCKS_SPEC).
+#ifndef PT_SHADE_MINBLOCKS_SPEC
+#define PT_SHADE_MINBLOCKS_SPEC 8
+#endif
+#ifndef PT_SHADE_MINBLOCKS_MATTE
+#define PT_SHADE_MINBLOCKS_MATTE PT_SHADE_MINBLOCKS
+#endif
+#ifndef PT_SHADE_MINBLOCKS_PLASTIC
+#define PT_SHADE_MINBLOCKS_PLASTIC PT_SHADE_MINBLOCKS
+#endif
+#ifndef PT_SHADE_MINBLOCKS_METAL
+#define PT_SHADE_MINBLOCKS_METAL PT_SHADE_MINBLOCKS
+#endif
+constexpr int shade_minblocks(int nc, int cls) {
+  return nc != 3 ? PT_SHADE_MINBLOCKS_SPECTRAL
+                 : ((cls == CL_GLASS || cls == CL_MIRROR) ? PT_SHADE_MINBLOCKS_SPEC
+                                                          : (cls == CL_MATTE ? PT_SHADE_MINBLOCKS_MATTE : (cls == CL_PLASTIC ? PT_SHADE_MINBLOCKS_PLASTIC : (cls == CL_METAL ? PT_SHADE_MINBLOCKS_METAL : PT_SHADE_MINBLOCKS))));
+}
 template <int NC, int CLS, bool ENV>
-__global__ void __launch_bounds__(PT_SHADE_BLOCK, NC == 3 ? PT_SHADE_MINBLOCKS : PT_SHADE_MINBLOCKS_SPECTRAL) k_shade(const __grid_constant__ DScene S, WaveState W, Queues Q, unsigned long long* vertex_counter) {
+__global__ void __launch_bounds__(PT_SHADE_BLOCK, shade_minblocks(NC, CLS)) k_shade(const __grid_constant__ DScene S, WaveState W, Queues Q, unsigned long long* vertex_counter) {
   const uint32_t n = Q.counts[8 + CLS];
   const uint32_t* bin = Q.bins + (size_t)CLS * W.cap;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) shade_body<NC, CLS, ENV>(S, W, Q, bin[k], vertex_counter);
