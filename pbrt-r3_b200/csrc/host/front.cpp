@@ -12,6 +12,7 @@
 // The result is the POD scene description of include/pbrt_r3_b200.h; nothing here touches CUDA.
 #include "../../../include/pbrt_r3_b200.h"
 #include "params.h"
+#include "shape_loaders.h"
 #include "spectrum_host.h"
 #include "xform.h"
 
@@ -486,8 +487,8 @@ struct Builder {
   }
 
   void shape(const std::string& name, const ParamSet& ps_in) {
-    if (name != "trianglemesh" && name != "plymesh")
-      throw ParseError("Shape \"" + name + "\" is not supported on the GPU path (triangle meshes: trianglemesh, plymesh)");
+    if (name != "trianglemesh" && name != "plymesh" && name != "heightfield" && name != "loopsubdiv")
+      throw ParseError("Shape \"" + name + "\" is not supported on the GPU path (triangle meshes: trianglemesh, plymesh, heightfield, loopsubdiv)");
     ParamSet ps = ps_in;
     bool is_area = !gs.area_light_name.empty();
     if (is_area) {  // scene_context.rs:405-421
@@ -499,6 +500,23 @@ struct Builder {
     if (ps.find(PC_TEXTURE, "alpha") || ps.find(PC_FLOAT, "alpha") || ps.find(PC_TEXTURE, "shadowalpha") || ps.find(PC_FLOAT, "shadowalpha"))
       throw ParseError("alpha-masked shapes are not supported on the GPU path");
     MeshData M;
+    if (name == "heightfield" || name == "loopsubdiv") {  // shapes/heightfield.rs, shapes/loopsubdiv.rs: meshes by construction
+      pth::LoadedMesh L;
+      try {
+        if (name == "heightfield") {
+          const Param* pz = ps.find(PC_FLOAT, "Pz");
+          L = pth::heightfield_mesh(ps.one_int("nu", -1), ps.one_int("nv", -1), pz ? pz->f : std::vector<float>());
+        } else {
+          const Param* pi = ps.find(PC_INT, "indices");
+          const Param* pp = ps.find(PC_POINT, "P");
+          L = pth::loop_subdiv_mesh(ps.one_int("levels", ps.one_int("nlevels", 3)), pi ? pi->i : std::vector<int32_t>(), pp ? pp->f : std::vector<float>());
+        }
+      } catch (const std::exception& e) { throw ParseError(std::string("Shape \"") + name + "\": " + e.what()); }
+      M.vi = L.vi; M.P = L.P; M.N = L.N; M.UV = L.UV;
+      // create_heightfield hands create_triangle_mesh an EMPTY parameter set (heightfield.rs:62): always two-sided
+      emit_mesh(name == "heightfield" ? ParamSet() : ps, ps_in, is_area, M);
+      return;
+    }
     if (name == "plymesh") {  // shapes/plymesh.rs:253-378
       std::string fn = ps.one_string("filename", "");
       std::string path = (fn.size() && fn[0] == '/') ? fn : (cur_dir.empty() ? fn : cur_dir + "/" + fn);

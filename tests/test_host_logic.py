@@ -211,6 +211,124 @@ def test_front_end_tree_integrators(P):
         lib.pt_set_options(P.capi.pt_options(0, 0))
 
 
+def _loop_reference(P0, F0, levels):
+    """Independent Loop subdivision (closed or open manifold triangle meshes; pbrt-v3 rules: beta = 3/16 for valence 3, else
+    3 / (8 valence); regular interior vertices 1/16; boundary 1/8; odd vertices 3/8 3/8 1/8 1/8 or 1/2 1/2), then the limit
+    positions IN PLACE in vertex order like pbrt-r3 (loopsubdiv.rs:609-619).  float64, dictionary adjacency."""
+    V, F = [np.array(p, np.float64) for p in P0], [tuple(f) for f in F0]
+    beta = lambda n: 3.0 / 16.0 if n == 3 else 3.0 / (8.0 * n)
+
+    def adjacency(V, F):
+        nb, edge_faces = [set() for _ in V], {}
+        for fi, f in enumerate(F):
+            for k in range(3):
+                a, b = f[k], f[(k + 1) % 3]
+                nb[a].add(b); nb[b].add(a)
+                edge_faces.setdefault((min(a, b), max(a, b)), []).append(fi)
+        bverts = [set() for _ in V]
+        for (a, b), fs in edge_faces.items():
+            if len(fs) == 1:
+                bverts[a].add(b); bverts[b].add(a)
+        return nb, edge_faces, bverts
+    for _ in range(levels):
+        nb, edge_faces, bverts = adjacency(V, F)
+        newV = []
+        for i, p in enumerate(V):
+            if bverts[i]:
+                q = list(bverts[i])
+                newV.append((1 - 2 / 8.0) * p + (V[q[0]] + V[q[1]]) / 8.0)
+            else:
+                n = len(nb[i])
+                b = 1.0 / 16.0 if n == 6 else beta(n)
+                newV.append((1 - n * b) * p + b * sum(V[j] for j in nb[i]))
+        emap = {}
+        for (a, b), fs in edge_faces.items():
+            if len(fs) == 1:
+                q = 0.5 * V[a] + 0.5 * V[b]
+            else:
+                o = [next(v for v in F[fi] if v != a and v != b) for fi in fs]
+                q = 3 / 8.0 * (V[a] + V[b]) + 1 / 8.0 * (V[o[0]] + V[o[1]])
+            emap[(a, b)] = len(newV)
+            newV.append(q)
+        newF = []
+        for f in F:
+            e = [emap[(min(f[k], f[(k + 1) % 3]), max(f[k], f[(k + 1) % 3]))] for k in range(3)]
+            newF += [(f[0], e[0], e[2]), (e[0], f[1], e[1]), (e[2], e[1], f[2]), (e[0], e[1], e[2])]
+        V, F = newV, newF
+    nb, edge_faces, bverts = adjacency(V, F)
+    return V, F, nb, bverts
+
+
+def test_front_end_heightfield_and_loopsubdiv(P):
+    """Shapes that are triangle meshes by construction (shapes/heightfield.rs, shapes/loopsubdiv.rs)."""
+    base = 'Camera "perspective"\nWorldBegin\n%s\nWorldEnd\n'
+    tri = lambda hs: np.ctypeslib.as_array(hs.desc.tri_p, (hs.desc.n_tris * 9,)).reshape(-1, 3, 3).copy()
+    hs = P.HostScene.parse_string(base % 'Shape "heightfield" "integer nu" [3] "integer nv" [2] "float Pz" [0 1 0 0.5 0.5 0.5]')
+    assert hs.desc.n_tris == 4 and bool(hs.desc.tri_uv)
+    assert np.array_equal(tri(hs)[0], [[0, 0, 0], [0.5, 0, 1], [0.5, 1, 0.5]]) and np.array_equal(tri(hs)[1], [[0, 0, 0], [0.5, 1, 0.5], [0, 1, 0.5]])   # heightfield.rs:51-58
+    uv = np.ctypeslib.as_array(hs.desc.tri_uv, (4 * 6,)).reshape(-1, 3, 2)
+    assert np.array_equal(uv[0], [[0, 0], [0.5, 0], [0.5, 1]])
+    for bad in ('Shape "heightfield" "integer nu" [3] "float Pz" [0 1 0]', 'Shape "heightfield" "integer nu" [3] "integer nv" [2] "float Pz" [0 1 0]'):
+        with pytest.raises(P.PbrtError):
+            P.HostScene.parse_string(base % bad)
+    # Loop subdivision: octahedron (closed, valence 4), a fan with a valence-3 and a valence-6 vertex... and an open square (boundary rules)
+    oct_p = [(0, 0, 1), (1, 0, 0), (0, 1, 0), (-1, 0, 0), (0, -1, 0), (0, 0, -1)]
+    oct_f = [(0, 1, 2), (0, 2, 3), (0, 3, 4), (0, 4, 1), (5, 2, 1), (5, 3, 2), (5, 4, 3), (5, 1, 4)]
+    tet_p = [(1, 1, 1), (1, -1, -1), (-1, 1, -1), (-1, -1, 1)]
+    tet_f = [(0, 1, 2), (0, 3, 1), (0, 2, 3), (1, 3, 2)]
+    sq_p = [(0, 0, 0), (1, 0, 0.2), (1, 1, 0), (0, 1, 0.3), (0.5, 0.5, 0.5)]
+    sq_f = [(0, 1, 4), (1, 2, 4), (2, 3, 4), (3, 0, 4)]
+    for name, pts, faces in (("octahedron", oct_p, oct_f), ("tetrahedron", tet_p, tet_f), ("open pyramid", sq_p, sq_f)):
+        for levels in (0, 1, 3):
+            txt = 'Shape "loopsubdiv" "integer levels" [%d] "integer indices" [%s] "point P" [%s]' % (
+                levels, " ".join(str(i) for f in faces for i in f), " ".join("%g" % c for p in pts for c in p))
+            hs = P.HostScene.parse_string(base % txt)
+            assert hs.desc.n_tris == len(faces) * 4 ** levels and bool(hs.desc.tri_n), (name, levels)
+            T = tri(hs)
+            V, F, nb, bverts = _loop_reference(pts, faces, levels)
+            # the refined connectivity, then pbrt-r3's in-place limit positions in vertex order: compare as point SETS (the
+            # vertex numbering of the two implementations differs)
+            # the two implementations number vertices and faces alike (children of the old vertices, then the edge vertices in
+            # first-seen order; four children per face): pbrt-r3's IN-PLACE limit positions (loopsubdiv.rs:609-619), vertex by vertex
+            L = [v.copy() for v in V]
+            for i in range(len(L)):
+                if bverts[i]:
+                    q = list(bverts[i])
+                    L[i] = (1 - 2 / 5.0) * L[i] + (L[q[0]] + L[q[1]]) / 5.0
+                else:
+                    nv = len(nb[i])
+                    b = 3.0 / 16.0 if nv == 3 else 3.0 / (8.0 * nv)
+                    gam = 1.0 / (nv + 3.0 / (8.0 * b))
+                    L[i] = (1 - nv * gam) * L[i] + gam * sum(L[j] for j in nb[i])
+            want = np.array([[L[i] for i in f] for f in F])
+            assert np.allclose(T, want, atol=2e-6), (name, levels, np.abs(T - want).max())
+            lo, hi = np.array(pts).min(0), np.array(pts).max(0)
+            assert (T.reshape(-1, 3) >= lo - 1e-6).all() and (T.reshape(-1, 3) <= hi + 1e-6).all()     # convex-hull property of the limit surface
+            # watertightness is kept: every edge of a closed mesh is shared by exactly two triangles
+            key = lambda p: tuple(np.round(p, 6))
+            edges = {}
+            for t in T:
+                for k in range(3):
+                    e = tuple(sorted((key(t[k]), key(t[(k + 1) % 3]))))
+                    edges[e] = edges.get(e, 0) + 1
+            counts = sorted(set(edges.values()))
+            assert counts == ([2] if name != "open pyramid" else [1, 2]), (name, levels, counts)
+            n = np.ctypeslib.as_array(hs.desc.tri_n, (hs.desc.n_tris * 9,)).reshape(-1, 3)
+            assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-5)
+    # level 0 of the octahedron = the limit positions of the control vertices, applied in place in vertex order (loopsubdiv.rs:609-619)
+    hs = P.HostScene.parse_string(base % ('Shape "loopsubdiv" "integer levels" [0] "integer indices" [%s] "point P" [%s]' % (
+        " ".join(str(i) for f in oct_f for i in f), " ".join("%g" % c for p in oct_p for c in p))))
+    g = 1.0 / (4 + 3.0 / (8.0 * (3.0 / 32.0)))
+    V = [np.array(p, np.float64) for p in oct_p]
+    nbr = {0: [1, 2, 3, 4], 1: [0, 2, 4, 5], 2: [0, 1, 3, 5], 3: [0, 2, 4, 5], 4: [0, 1, 3, 5], 5: [1, 2, 3, 4]}
+    for i in range(6):
+        V[i] = (1 - 4 * g) * V[i] + g * sum(V[j] for j in nbr[i])
+    want = np.array([[V[i] for i in f] for f in oct_f])
+    assert np.allclose(tri(hs), want, atol=1e-6)
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % 'Shape "loopsubdiv" "point P" [0 0 0 1 0 0 0 1 0]')
+
+
 def test_front_end_targz_and_gz_scenes(P, tmp_path):
     """pbrt_parse_file on a ".tar.gz" scene (parser.rs:32-63: unpacked into a temporary directory, first .pbrt file) whose
     main file Includes a gzipped file (read_file.rs:38-54); same scene as the plain text."""
