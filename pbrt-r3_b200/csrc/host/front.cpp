@@ -487,8 +487,8 @@ struct Builder {
   }
 
   void shape(const std::string& name, const ParamSet& ps_in) {
-    if (name != "trianglemesh" && name != "plymesh" && name != "heightfield" && name != "loopsubdiv")
-      throw ParseError("Shape \"" + name + "\" is not supported on the GPU path (triangle meshes: trianglemesh, plymesh, heightfield, loopsubdiv)");
+    if (name != "trianglemesh" && name != "plymesh" && name != "heightfield" && name != "loopsubdiv" && name != "nurbs")
+      throw ParseError("Shape \"" + name + "\" is not supported on the GPU path (triangle meshes: trianglemesh, plymesh, heightfield, loopsubdiv, nurbs)");
     ParamSet ps = ps_in;
     bool is_area = !gs.area_light_name.empty();
     if (is_area) {  // scene_context.rs:405-421
@@ -500,21 +500,35 @@ struct Builder {
     if (ps.find(PC_TEXTURE, "alpha") || ps.find(PC_FLOAT, "alpha") || ps.find(PC_TEXTURE, "shadowalpha") || ps.find(PC_FLOAT, "shadowalpha"))
       throw ParseError("alpha-masked shapes are not supported on the GPU path");
     MeshData M;
-    if (name == "heightfield" || name == "loopsubdiv") {  // shapes/heightfield.rs, shapes/loopsubdiv.rs: meshes by construction
+    if (name == "heightfield" || name == "loopsubdiv" || name == "nurbs") {  // shapes/{heightfield,loopsubdiv,nurbs}.rs: meshes by construction
       pth::LoadedMesh L;
       try {
         if (name == "heightfield") {
           const Param* pz = ps.find(PC_FLOAT, "Pz");
           L = pth::heightfield_mesh(ps.one_int("nu", -1), ps.one_int("nv", -1), pz ? pz->f : std::vector<float>());
-        } else {
+        } else if (name == "loopsubdiv") {
           const Param* pi = ps.find(PC_INT, "indices");
           const Param* pp = ps.find(PC_POINT, "P");
           L = pth::loop_subdiv_mesh(ps.one_int("levels", ps.one_int("nlevels", 3)), pi ? pi->i : std::vector<int32_t>(), pp ? pp->f : std::vector<float>());
+        } else {  // nurbs.rs:248-404
+          const Param* uk = ps.find(PC_FLOAT, "uknots");
+          const Param* vk = ps.find(PC_FLOAT, "vknots");
+          const Param* pp = ps.find(PC_POINT, "P");
+          const Param* pw = (pp && !pp->f.empty()) ? nullptr : ps.find(PC_POINT, "Pw");
+          const Param* q = pw ? pw : pp;
+          float r[4];
+          const float* rp[4];
+          const char* rn[4] = {"u0", "u1", "v0", "v1"};
+          for (int k = 0; k < 4; k++) { const Param* f = ps.find(PC_FLOAT, rn[k]); rp[k] = (f && f->f.size() == 1) ? &(r[k] = f->f[0]) : nullptr; }
+          L = pth::nurbs_mesh(ps.one_int("nu", -1), ps.one_int("uorder", -1), uk ? uk->f : std::vector<float>(), ps.one_int("nv", -1), ps.one_int("vorder", -1),
+                              vk ? vk->f : std::vector<float>(), q ? q->f : std::vector<float>(), pw != nullptr, rp[0], rp[1], rp[2], rp[3], ps.one_int("diceu", 30),
+                              ps.one_int("dicev", 30));
         }
       } catch (const std::exception& e) { throw ParseError(std::string("Shape \"") + name + "\": " + e.what()); }
       M.vi = L.vi; M.P = L.P; M.N = L.N; M.UV = L.UV;
-      // create_heightfield hands create_triangle_mesh an EMPTY parameter set (heightfield.rs:62): always two-sided
-      emit_mesh(name == "heightfield" ? ParamSet() : ps, ps_in, is_area, M);
+      // create_heightfield / create_tesselated_mesh hand create_triangle_mesh an EMPTY parameter set (heightfield.rs:62,
+      // nurbs.rs:231): always two-sided
+      emit_mesh(name == "loopsubdiv" ? ps : ParamSet(), ps_in, is_area, M);
       return;
     }
     if (name == "plymesh") {  // shapes/plymesh.rs:253-378

@@ -1,6 +1,7 @@
-// shape_loaders.h — shapes of the reference that are triangle meshes by construction: "heightfield" and "loopsubdiv".
-// Replaces reference src/shapes/heightfield.rs:6-82 and src/shapes/loopsubdiv.rs:283-760 (Loop subdivision surfaces: the
-// pbrt-v3 algorithm on SDVertex / SDFace records, limit positions and limit-surface normals).  Index-based records
+// shape_loaders.h — shapes of the reference that are triangle meshes by construction: "heightfield", "loopsubdiv", "nurbs".
+// Replaces reference src/shapes/heightfield.rs:6-82, src/shapes/loopsubdiv.rs:283-760 (Loop subdivision surfaces: the
+// pbrt-v3 algorithm on SDVertex / SDFace records, limit positions and limit-surface normals) and src/shapes/nurbs.rs:9-404
+// (de Boor evaluation of the rational surface and its derivatives, diced into diceu x dicev vertices).  Index-based records
 // instead of the reference's Arc<RefCell<..>> graph; the same faces in the same order, the same f32 operations in the same
 // order (the reference keys its edge maps by pointer, which only decides which end of an edge is called p0: every sum
 // over the two ends is symmetric).  Host code: runs once per shape while the scene is parsed.
@@ -280,6 +281,108 @@ inline LoadedMesh loop_subdiv_mesh(int n_levels, const std::vector<int32_t>& ind
   for (const SDFace& f : M.F)
     for (int j = 0; j < 3; j++) out.vi.push_back(f.v[j]);
   return out;
+}
+
+// ---- NURBS (nurbs.rs) ------------------------------------------------------------------------------------------------
+namespace nurbs {
+struct H3 { float x = 0, y = 0, z = 0, w = 0; };
+inline int knot_offset(const std::vector<float>& knot, int order, float t) {  // :9-19
+  int k = order - 1;
+  while ((size_t)k + 1 < knot.size() && t > knot[(size_t)k + 1]) k++;
+  return k;
+}
+// nurbs_evaluate (:61-117): de Boor on the `order` control points cp[(cp_offset + i - bias) * stride]; value and derivative
+// (bias = the reference's negative OffsetArray offset when the points are an iso curve that starts at control point `bias`)
+inline H3 evaluate(int order, const std::vector<float>& knots, const H3* cp, int np, int stride, float t, float deriv[3], int bias = 0) {
+  const int ko = knot_offset(knots, order, t);
+  const float* knot = knots.data() + ko;
+  const int cp_offset = ko - order + 1;
+  if (cp_offset - bias < 0 || (cp_offset - bias + order - 1) * stride >= np) throw std::runtime_error("NURBS: parameter outside the knot vector");
+  std::vector<H3> w((size_t)order);
+  for (int i = 0; i < order; i++) w[(size_t)i] = cp[(size_t)((cp_offset + i - bias) * stride)];
+  for (int i = 0; i < order - 2; i++)
+    for (int j = 0; j < order - 1 - i; j++) {
+      const float alpha = (knot[1 + j] - t) / (knot[1 + j] - knot[j + 2 - order + i]);
+      H3& a = w[(size_t)j];
+      const H3& b = w[(size_t)j + 1];
+      a.x = alpha * a.x + (1.0f - alpha) * b.x;
+      a.y = alpha * a.y + (1.0f - alpha) * b.y;
+      a.z = alpha * a.z + (1.0f - alpha) * b.z;
+      a.w = alpha * a.w + (1.0f - alpha) * b.w;
+    }
+  const float alpha = (knot[1] - t) / (knot[1] - knot[0]);
+  H3 val;
+  val.x = alpha * w[0].x + (1.0f - alpha) * w[1].x;
+  val.y = alpha * w[0].y + (1.0f - alpha) * w[1].y;
+  val.z = alpha * w[0].z + (1.0f - alpha) * w[1].z;
+  val.w = alpha * w[0].w + (1.0f - alpha) * w[1].w;
+  if (deriv) {
+    const float factor = (float)(order - 1) / (knot[1] - knot[0]);
+    const float dx = factor * (w[1].x - w[0].x), dy = factor * (w[1].y - w[0].y), dz = factor * (w[1].z - w[0].z), dw = factor * (w[1].w - w[0].w);
+    deriv[0] = (dx / val.w) - (val.x * dw / (val.w * val.w));
+    deriv[1] = (dy / val.w) - (val.y * dw / (val.w * val.w));
+    deriv[2] = (dz / val.w) - (val.z * dw / (val.w * val.w));
+  }
+  return val;
+}
+}  // namespace nurbs
+
+// create_nurbs + create_tesselated_mesh (nurbs.rs:119-404); pw = nu * nv homogeneous control points, u fastest
+inline LoadedMesh nurbs_mesh(int nu, int uorder, const std::vector<float>& uknots, int nv, int vorder, const std::vector<float>& vknots,
+                             const std::vector<float>& P, bool homogeneous, const float* u0p, const float* u1p, const float* v0p, const float* v1p, int diceu,
+                             int dicev) {
+  using nurbs::H3;
+  if (nu == -1) throw std::runtime_error("Must provide number of control points \"nu\" with NURBS shape.");
+  if (uorder == -1) throw std::runtime_error("Must provide u order \"uorder\" with NURBS shape.");
+  if (uknots.empty()) throw std::runtime_error("Must provide u knot vector \"uknots\" with NURBS shape.");
+  if (nu < 1 || uorder < 2 || (int)uknots.size() != nu + uorder) throw std::runtime_error("Number of knots in u knot vector doesn't match sum of number of u control points and u order.");
+  if (nv == -1) throw std::runtime_error("Must provide number of control points \"nv\" with NURBS shape.");
+  if (vorder == -1) throw std::runtime_error("Must provide v order \"vorder\" with NURBS shape.");
+  if (vknots.empty()) throw std::runtime_error("Must provide v knot vector \"vknots\" with NURBS shape.");
+  if (nv < 1 || vorder < 2 || (int)vknots.size() != nv + vorder) throw std::runtime_error("Number of knots in v knot vector doesn't match sum of number of v control points and v order.");
+  if (P.empty()) throw std::runtime_error("Must provide control points via \"P\" or \"Pw\" parameter to NURBS shape.");
+  const size_t comps = homogeneous ? 4 : 3;
+  if (P.size() % comps != 0) throw std::runtime_error("Number of control points must be multiple of 3 or 4.");
+  const size_t npts = P.size() / comps;
+  if (npts != (size_t)nu * (size_t)nv) throw std::runtime_error("Number of control points doesn't match nu * nv.");
+  std::vector<H3> pw(npts);
+  for (size_t i = 0; i < npts; i++) {
+    pw[i].x = P[comps * i]; pw[i].y = P[comps * i + 1]; pw[i].z = P[comps * i + 2];
+    pw[i].w = homogeneous ? P[comps * i + 3] : 1.0f;
+  }
+  auto clampf = [](float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); };
+  const float u0x = uknots[(size_t)uorder - 1], u1x = uknots[(size_t)nu], v0x = vknots[(size_t)vorder - 1], v1x = vknots[(size_t)nv];
+  const float u0 = clampf(u0p ? *u0p : u0x, u0x, u1x), u1 = clampf(u1p ? *u1p : u1x, u0x, u1x);
+  const float v0 = clampf(v0p ? *v0p : v0x, v0x, v1x), v1 = clampf(v1p ? *v1p : v1x, v0x, v1x);
+  diceu = diceu < 2 ? 2 : diceu;
+  dicev = dicev < 2 ? 2 : dicev;
+  auto lerp = [](float t, float a, float b) { return (1.0f - t) * a + t * b; };
+  LoadedMesh M;
+  std::vector<H3> iso((size_t)(uorder > vorder ? uorder : vorder));
+  for (int v = 0; v < dicev; v++)
+    for (int u = 0; u < diceu; u++) {
+      const float uu = lerp((float)u / (float)(diceu - 1), u0, u1), vv = lerp((float)v / (float)(dicev - 1), v0, v1);
+      M.UV.push_back(uu); M.UV.push_back(vv);
+      // nurbs_evaluate_surface (:119-159)
+      const int u_first = nurbs::knot_offset(uknots, uorder, uu) - uorder + 1;
+      for (int i = 0; i < uorder; i++) iso[(size_t)i] = nurbs::evaluate(vorder, vknots, pw.data() + (u_first + i), (int)npts - (u_first + i), nu, vv, nullptr);
+      float dpdu[3], dpdv[3];
+      const H3 p = nurbs::evaluate(uorder, uknots, iso.data(), (int)iso.size(), 1, uu, dpdu, u_first);
+      const int v_first = nurbs::knot_offset(vknots, vorder, vv) - vorder + 1;
+      for (int i = 0; i < vorder; i++) iso[(size_t)i] = nurbs::evaluate(uorder, uknots, pw.data() + (size_t)(v_first + i) * nu, (int)npts - (v_first + i) * nu, 1, uu, nullptr);
+      nurbs::evaluate(vorder, vknots, iso.data(), (int)iso.size(), 1, vv, dpdv, v_first);
+      M.P.push_back(p.x / p.w); M.P.push_back(p.y / p.w); M.P.push_back(p.z / p.w);
+      float n[3] = {dpdu[1] * dpdv[2] - dpdu[2] * dpdv[1], dpdu[2] * dpdv[0] - dpdu[0] * dpdv[2], dpdu[0] * dpdv[1] - dpdu[1] * dpdv[0]};
+      const float len = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      M.N.push_back(n[0] / len); M.N.push_back(n[1] / len); M.N.push_back(n[2] / len);
+    }
+  auto vn = [&](int u, int v) { return (int32_t)(v * diceu + u); };
+  for (int v = 0; v < dicev - 1; v++)
+    for (int u = 0; u < diceu - 1; u++) {
+      const int32_t q[6] = {vn(u, v), vn(u + 1, v), vn(u + 1, v + 1), vn(u, v), vn(u + 1, v + 1), vn(u, v + 1)};
+      M.vi.insert(M.vi.end(), q, q + 6);
+    }
+  return M;
 }
 
 }  // namespace pth

@@ -329,6 +329,54 @@ def test_front_end_heightfield_and_loopsubdiv(P):
         P.HostScene.parse_string(base % 'Shape "loopsubdiv" "point P" [0 0 0 1 0 0 0 1 0]')
 
 
+def test_front_end_nurbs(P):
+    """Shape "nurbs" (shapes/nurbs.rs): a rational tensor-product B-spline surface diced into diceu x dicev vertices; points
+    against scipy's B-spline basis, normals against finite differences of the same surface."""
+    from scipy.interpolate import BSpline
+    base = 'Camera "perspective"\nWorldBegin\n%s\nWorldEnd\n'
+    rng = np.random.RandomState(2)
+    nu, nv, uo, vo = 5, 4, 4, 3
+    uk, vk = np.array([0, 0, 0, 0, 1, 2, 2, 2, 2], np.float64), np.array([0, 0, 0, 1, 2, 2, 2], np.float64)
+    cp, w = rng.uniform(-1, 1, (nv, nu, 3)), rng.uniform(0.5, 2, (nv, nu, 1))
+    pw = np.concatenate([cp * w, w], 2).astype(np.float32)
+    du, dv = 7, 6
+    txt = 'Shape "nurbs" "integer nu" [%d] "integer uorder" [%d] "float uknots" [%s] "integer nv" [%d] "integer vorder" [%d] "float vknots" [%s] "point4 Pw" [%s] "integer diceu" [%d] "integer dicev" [%d]' % (
+        nu, uo, " ".join(map(str, uk)), nv, vo, " ".join(map(str, vk)), " ".join("%.9g" % x for x in pw.reshape(-1)), du, dv)
+    hs = P.HostScene.parse_string(base % txt)
+    assert hs.desc.n_tris == 2 * (du - 1) * (dv - 1) and bool(hs.desc.tri_n) and bool(hs.desc.tri_uv)
+    T = np.ctypeslib.as_array(hs.desc.tri_p, (hs.desc.n_tris * 9,)).reshape(-1, 3, 3)
+    N = np.ctypeslib.as_array(hs.desc.tri_n, (hs.desc.n_tris * 9,)).reshape(-1, 3, 3)
+    UV = np.ctypeslib.as_array(hs.desc.tri_uv, (hs.desc.n_tris * 6,)).reshape(-1, 3, 2)
+
+    def basis(k, order, n, t):
+        t = min(max(t, k[order - 1] + 1e-9), k[n] - 1e-9)
+        return np.nan_to_num(np.array([BSpline.basis_element(k[i:i + order + 1], extrapolate=False)(t) if k[i] != k[i + order] else 0.0 for i in range(n)]))
+
+    def surf(u, v):
+        h = np.einsum("j,i,jik->k", basis(vk, vo, nv, v), basis(uk, uo, nu, u), pw.astype(np.float64))
+        return h[:3] / h[3]
+    for t in range(0, hs.desc.n_tris, 3):
+        for k in range(3):
+            u, v = UV[t, k]
+            assert np.allclose(T[t, k], surf(u, v), atol=2e-6), (t, k)
+            if 0.05 < u < 1.95 and 0.05 < v < 1.95:
+                e = 1e-4
+                n = np.cross(surf(u + e, v) - surf(u - e, v), surf(u, v + e) - surf(u, v - e))
+                assert np.dot(n / np.linalg.norm(n), N[t, k]) > 0.9999, (t, k)
+    assert UV.min() == 0.0 and UV.max() == 2.0           # u0 / u1 default to the knot range (nurbs.rs:357-365)
+    # non-rational "P", a sub-range, the default 30 x 30 dicing
+    flat = 'Shape "nurbs" "integer nu" [2] "integer uorder" [2] "float uknots" [0 0 1 1] "integer nv" [2] "integer vorder" [2] "float vknots" [0 0 1 1] "point P" [0 0 0 1 0 0 0 1 0 1 1 1] "float u0" [0.25] "float u1" [2]'
+    hs = P.HostScene.parse_string(base % flat)
+    assert hs.desc.n_tris == 2 * 29 * 29
+    UV = np.ctypeslib.as_array(hs.desc.tri_uv, (hs.desc.n_tris * 6,)).reshape(-1, 2)
+    assert UV[:, 0].min() == 0.25 and UV[:, 0].max() == 1.0
+    Tp = np.ctypeslib.as_array(hs.desc.tri_p, (hs.desc.n_tris * 9,)).reshape(-1, 3)
+    assert np.allclose(Tp[:, 2], Tp[:, 0] * Tp[:, 1], atol=1e-6)            # the bilinear patch z = x y
+    for bad in ('Shape "nurbs" "integer nu" [2]', flat.replace('"float uknots" [0 0 1 1]', '"float uknots" [0 0 1]')):
+        with pytest.raises(P.PbrtError):
+            P.HostScene.parse_string(base % bad)
+
+
 def test_front_end_targz_and_gz_scenes(P, tmp_path):
     """pbrt_parse_file on a ".tar.gz" scene (parser.rs:32-63: unpacked into a temporary directory, first .pbrt file) whose
     main file Includes a gzipped file (read_file.rs:38-54); same scene as the plain text."""
