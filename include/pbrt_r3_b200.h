@@ -62,7 +62,7 @@ enum pt_accel_type {          /* reference src/accelerators/bvh/accel/mod.rs:4-1
 };
 
 enum pt_split_method {        /* accelerators/bvh/create_bvh_accelerator.rs:13-20 */
-  PT_SPLIT_SAH = 0, PT_SPLIT_MIDDLE = 2, PT_SPLIT_EQUAL = 3
+  PT_SPLIT_SAH = 0, PT_SPLIT_HLBVH = 1 /* build/hlbvh.rs: Morton-code treelets + SAH over the treelets */, PT_SPLIT_MIDDLE = 2, PT_SPLIT_EQUAL = 3
 };
 
 enum pt_light_strategy {      /* core/lightdistrib/create_light_sample_distribution.rs:11-45 */

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <stdexcept>
 #include <vector>
 
 namespace orc {
@@ -105,6 +106,128 @@ struct BuildNode {
   int split_axis = 0;
   size_t first = 0, n = 0;
 };
+
+// ---- HLBVH (build/hlbvh.rs): Morton codes of the centroids, LBVH treelets over the top 12 bits, SAH over the treelets ----
+struct MortonPrim { uint32_t index, code; };
+inline uint32_t left_shift3(uint32_t x) {  // hlbvh.rs:23-37
+  if (x >= 1024u) x = 1023u;
+  x = (x | (x << 16)) & 0x30000ffu;
+  x = (x | (x << 8)) & 0x300f00fu;
+  x = (x | (x << 4)) & 0x30c30c3u;
+  x = (x | (x << 2)) & 0x9249249u;
+  return x;
+}
+struct HlbvhBuilder {
+  size_t max_prims;
+  const PrimInfo* info;
+  std::vector<size_t>* ordered;
+  std::unique_ptr<BuildNode> leaf(const MortonPrim* mp, size_t n) {
+    auto nd = std::make_unique<BuildNode>();
+    nd->first = ordered->size();
+    nd->n = n;
+    Bounds3 b = info[mp[0].index].bounds;
+    ordered->push_back(mp[0].index);
+    for (size_t i = 1; i < n; i++) { ordered->push_back(mp[i].index); b = bunion(b, info[mp[i].index].bounds); }
+    nd->bounds = b;
+    return nd;
+  }
+  static std::unique_ptr<BuildNode> interior(int axis, std::unique_ptr<BuildNode> a, std::unique_ptr<BuildNode> b) {
+    auto nd = std::make_unique<BuildNode>();
+    nd->bounds = bunion(a->bounds, b->bounds);
+    nd->split_axis = axis;
+    nd->c[0] = std::move(a);
+    nd->c[1] = std::move(b);
+    return nd;
+  }
+  std::unique_ptr<BuildNode> split_node(MortonPrim* mp, size_t n, int dim) {  // :86-137: equal counts, axes cycling z, y, x
+    if (n <= max_prims) return leaf(mp, n);
+    std::stable_sort(mp, mp + n, [&](const MortonPrim& a, const MortonPrim& b) { return info[a.index].centroid[dim] < info[b.index].centroid[dim]; });
+    int next_dim = (dim + 3 - 1) % 3;
+    size_t split = n / 2;
+    auto n0 = split_node(mp, split, next_dim);
+    auto n1 = split_node(mp + split, n - split, next_dim);
+    return interior(dim, std::move(n0), std::move(n1));
+  }
+  std::unique_ptr<BuildNode> emit_lbvh(const MortonPrim* mp, size_t n, int bit_index) {  // :139-226
+    if (n <= max_prims) return leaf(mp, n);
+    if (bit_index == -1) {
+      std::vector<MortonPrim> copy(mp, mp + n);
+      return split_node(copy.data(), n, 2);
+    }
+    uint32_t mask = 1u << bit_index;
+    if ((mp[0].code & mask) == (mp[n - 1].code & mask)) return emit_lbvh(mp, n, bit_index - 1);
+    size_t s0 = 0, s1 = n - 1;
+    while (s0 + 1 != s1) {
+      size_t mid = (s0 + s1) / 2;
+      if ((mp[s0].code & mask) == (mp[mid].code & mask)) s0 = mid; else s1 = mid;
+    }
+    auto n0 = emit_lbvh(mp, s1, bit_index - 1);
+    auto n1 = emit_lbvh(mp + s1, n - s1, bit_index - 1);
+    return interior(bit_index % 3, std::move(n0), std::move(n1));
+  }
+  static std::unique_ptr<BuildNode> upper_sah(std::vector<std::unique_ptr<BuildNode>> roots) {  // :234-330
+    if (roots.empty()) throw std::runtime_error("hlbvh: build_upper_sah on an empty side (the reference panics here)");
+    if (roots.size() <= 1) return std::move(roots[0]);
+    Bounds3 bounds = roots[0]->bounds;
+    for (size_t i = 1; i < roots.size(); i++) bounds = bunion(bounds, roots[i]->bounds);
+    Vec3 center = (roots[0]->bounds.mn + roots[0]->bounds.mx) * 0.5f;
+    Bounds3 cb(center, center);
+    for (size_t i = 1; i < roots.size(); i++) cb = bunion_p(cb, (roots[i]->bounds.mn + roots[i]->bounds.mx) * 0.5f);
+    int dim = cb.maximum_extent();
+    const int NB = 12;
+    uint32_t count[NB];
+    Bounds3 bb[NB];
+    for (int i = 0; i < NB; i++) count[i] = 0;
+    auto bucket = [&](const BuildNode& nd) {
+      Float c = (nd.bounds.mn[dim] + nd.bounds.mx[dim]) * 0.5f;
+      size_t b = (size_t)f2u((Float)NB * ((c - cb.mn[dim]) / (cb.mx[dim] - cb.mn[dim])));
+      return (int)std::min(b, (size_t)NB - 1);
+    };
+    for (auto& r : roots) {
+      int b = bucket(*r);
+      count[b]++;
+      if (count[b] == 1) bb[b] = r->bounds; else bb[b] = bunion(bb[b], r->bounds);
+    }
+    Float cost[NB - 1];
+    for (int i = 0; i < NB - 1; i++) {  // as written in the reference: both sides start from bucket i, count1 starts at 1
+      Bounds3 b0 = bb[i], b1 = bb[i];
+      uint32_t c0 = 0, c1 = 1;
+      for (int j = 0; j < i; j++) { b0 = bunion(b0, bb[j]); c0 += count[j]; }
+      for (int j = i + 1; j < NB; j++) { b1 = bunion(b1, bb[j]); c1 += count[j]; }
+      cost[i] = 0.125f + (((Float)c0 * b0.surface_area() + (Float)c1 * b1.surface_area()) / bounds.surface_area());
+    }
+    Float min_cost = cost[0];
+    int min_b = 0;
+    for (int i = 1; i < NB - 1; i++)
+      if (cost[i] < min_cost) { min_cost = cost[i]; min_b = i; }
+    std::vector<std::unique_ptr<BuildNode>> c0, c1;
+    for (auto& r : roots) (bucket(*r) <= min_b ? c0 : c1).push_back(std::move(r));
+    auto n0 = upper_sah(std::move(c0));
+    auto n1 = upper_sah(std::move(c1));
+    return interior(dim, std::move(n0), std::move(n1));
+  }
+  std::unique_ptr<BuildNode> build(size_t n) {  // hlbvh_build (:332-428)
+    Bounds3 bounds = info[0].bounds;
+    for (size_t i = 1; i < n; i++) bounds = bunion(bounds, info[i].bounds);
+    std::vector<MortonPrim> mp(n);
+    for (size_t i = 0; i < n; i++) {
+      mp[i].index = (uint32_t)info[i].number;
+      Vec3 o = bounds.offset(info[i].centroid);
+      Float sc[3] = {rclamp(o.x, 0.0f, 1.0f) * 1024.0f, rclamp(o.y, 0.0f, 1.0f) * 1024.0f, rclamp(o.z, 0.0f, 1.0f) * 1024.0f};
+      mp[i].code = (left_shift3(f2u(ceilf(sc[2]))) << 2) | (left_shift3(f2u(ceilf(sc[1]))) << 1) | left_shift3(f2u(ceilf(sc[0])));
+    }
+    std::stable_sort(mp.begin(), mp.end(), [](const MortonPrim& a, const MortonPrim& b) { return a.code < b.code; });  // LSD radix sort = stable
+    std::vector<std::unique_ptr<BuildNode>> treelets;
+    const uint32_t MASK = 0x3ffc0000u;
+    for (size_t start = 0, end = 1; end <= n; end++)
+      if (end == n || (mp[start].code & MASK) != (mp[end].code & MASK)) {
+        treelets.push_back(emit_lbvh(mp.data() + start, end - start, 29 - 12));
+        start = end;
+      }
+    return upper_sah(std::move(treelets));
+  }
+};
+
 struct Builder {
   size_t max_prims;
   int split;  // pt_split_method
@@ -600,7 +723,11 @@ inline std::unique_ptr<Accel> build_accel(const SceneGeom& g, const int32_t* pri
   Builder B;
   B.max_prims = (size_t)std::min(std::max(cfg.max_prims_in_node, 0), 255);
   B.split = cfg.split_method;
-  auto root = B.build(info.data(), n);
+  std::unique_ptr<BuildNode> root;
+  if (cfg.split_method == PT_SPLIT_HLBVH) {
+    HlbvhBuilder H{B.max_prims, info.data(), &B.ordered};
+    root = H.build(n);
+  } else root = B.build(info.data(), n);
   A->prims.resize(n);
   for (size_t i = 0; i < n; i++) A->prims[i] = prims[B.ordered[i]];
   if (cfg.type == PT_ACCEL_LBVH) { A->lbvh = true; flatten_lbvh(A->lnodes, root.get()); }

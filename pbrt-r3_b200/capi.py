@@ -16,6 +16,7 @@ PT_MAT_UBER, PT_MAT_SUBSTRATE, PT_MAT_TRANSLUCENT = 5, 6, 7
 PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT, PT_LIGHT_INFINITE = 0, 1, 2, 3, 4
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
+PT_SPLIT_SAH, PT_SPLIT_HLBVH, PT_SPLIT_MIDDLE, PT_SPLIT_EQUAL = 0, 1, 2, 3
 PT_INTEGRATOR_PATH, PT_INTEGRATOR_AOV, PT_INTEGRATOR_AO, PT_INTEGRATOR_DIRECT, PT_INTEGRATOR_WHITTED = 0, 1, 2, 3, 4
 PT_DIRECT_ALL, PT_DIRECT_ONE = 0, 1
 PT_AOV_DISTANCE, PT_AOV_DEPTH, PT_AOV_N, PT_AOV_NS, PT_AOV_UV, PT_AOV_DPDUS = 0, 1, 2, 3, 4, 5

@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <stdexcept>
 #include <thread>
 
 namespace pth {
@@ -104,6 +105,139 @@ struct Ctx {
     sort_dim(pi, n, dim);
     return children(self, dim, pi, n / 2, n, ord);
   }
+
+  // ---- splitmethod "hlbvh" (build/hlbvh.rs:332-428): Morton codes of the centroids (10 bits per axis), one LBVH treelet
+  // per run of equal top-12 bits, SAH over the treelet roots.  Sequential: leaves are appended to the ordered list in the
+  // order the reference creates them.
+  struct MortonPrim { uint32_t index, code; };
+  const Info* hl_info = nullptr;
+  size_t hl_ord = 0;
+  static uint32_t left_shift3(uint32_t x) {  // :23-37
+    if (x >= 1024u) x = 1023u;
+    x = (x | (x << 16)) & 0x30000ffu;
+    x = (x | (x << 8)) & 0x300f00fu;
+    x = (x | (x << 4)) & 0x30c30c3u;
+    x = (x | (x << 2)) & 0x9249249u;
+    return x;
+  }
+  static uint32_t f2u(float v) { return v != v ? 0u : (v <= 0.0f ? 0u : (v >= 4294967296.0f ? 0xffffffffu : (uint32_t)v)); }  // `as u32`
+  int32_t hl_leaf(const MortonPrim* mp, size_t n) {
+    const int32_t self = reserve();
+    BuildNodeH& nd = out->tree[(size_t)self];
+    BBox b = hl_info[mp[0].index].b;
+    for (size_t i = 1; i < n; i++) b = b_union(b, hl_info[mp[i].index].b);
+    nd.bounds = b;
+    nd.child[0] = nd.child[1] = -1;
+    nd.axis = 0;
+    nd.first = (uint32_t)hl_ord;
+    nd.n = (uint32_t)n;
+    for (size_t i = 0; i < n; i++) out->ordered[hl_ord + i] = mp[i].index;
+    hl_ord += n;
+    return self;
+  }
+  int32_t hl_interior(int axis, int32_t c0, int32_t c1) {
+    const int32_t self = reserve();
+    set_interior(self, axis, c0, c1);
+    return self;
+  }
+  int32_t hl_split_node(MortonPrim* mp, size_t n, int dim) {  // :86-137
+    if (n <= max_prims) return hl_leaf(mp, n);
+    const Info* info = hl_info;
+    std::stable_sort(mp, mp + n, [info, dim](const MortonPrim& a, const MortonPrim& b) { return info[a.index].c[dim] < info[b.index].c[dim]; });
+    const int next_dim = (dim + 3 - 1) % 3;
+    const size_t split = n / 2;
+    const int32_t n0 = hl_split_node(mp, split, next_dim);
+    const int32_t n1 = hl_split_node(mp + split, n - split, next_dim);
+    return hl_interior(dim, n0, n1);
+  }
+  int32_t hl_emit(const MortonPrim* mp, size_t n, int bit_index) {  // emit_lbvh (:139-226)
+    if (n <= max_prims) return hl_leaf(mp, n);
+    if (bit_index == -1) {
+      std::vector<MortonPrim> copy(mp, mp + n);
+      return hl_split_node(copy.data(), n, 2);
+    }
+    const uint32_t mask = 1u << bit_index;
+    if ((mp[0].code & mask) == (mp[n - 1].code & mask)) return hl_emit(mp, n, bit_index - 1);
+    size_t s0 = 0, s1 = n - 1;
+    while (s0 + 1 != s1) {
+      const size_t mid = (s0 + s1) / 2;
+      if ((mp[s0].code & mask) == (mp[mid].code & mask)) s0 = mid; else s1 = mid;
+    }
+    const int32_t n0 = hl_emit(mp, s1, bit_index - 1);
+    const int32_t n1 = hl_emit(mp + s1, n - s1, bit_index - 1);
+    return hl_interior(bit_index % 3, n0, n1);
+  }
+  int32_t hl_upper_sah(const std::vector<int32_t>& roots) {  // build_upper_sah (:234-330), with the reference's cost formula as written
+    if (roots.empty()) throw std::runtime_error("splitmethod \"hlbvh\": an empty side in the SAH over the treelets (the reference panics here)");
+    if (roots.size() <= 1) return roots[0];
+    auto B = [&](int32_t id) -> const BBox& { return out->tree[(size_t)id].bounds; };
+    BBox bounds = B(roots[0]);
+    for (size_t i = 1; i < roots.size(); i++) bounds = b_union(bounds, B(roots[i]));
+    float cmn[3], cmx[3];
+    for (int a = 0; a < 3; a++) cmn[a] = cmx[a] = (B(roots[0]).mn[a] + B(roots[0]).mx[a]) * 0.5f;
+    for (size_t i = 1; i < roots.size(); i++)
+      for (int a = 0; a < 3; a++) { float c = (B(roots[i]).mn[a] + B(roots[i]).mx[a]) * 0.5f; cmn[a] = mn_(cmn[a], c); cmx[a] = mx_(cmx[a], c); }
+    const int dim = b_max_extent(cmn, cmx);
+    const int NB = 12;
+    uint32_t count[NB];
+    BBox bb[NB];
+    for (int i = 0; i < NB; i++) { count[i] = 0; bb[i] = b_empty(); }
+    auto bucket = [&](int32_t id) {
+      const float c = (B(id).mn[dim] + B(id).mx[dim]) * 0.5f;
+      const uint32_t b = f2u((float)NB * ((c - cmn[dim]) / (cmx[dim] - cmn[dim])));
+      return (int)std::min<uint32_t>(b, (uint32_t)NB - 1);
+    };
+    for (int32_t r : roots) {
+      const int b = bucket(r);
+      count[b]++;
+      bb[b] = count[b] == 1 ? B(r) : b_union(bb[b], B(r));
+    }
+    float cost[NB - 1];
+    for (int i = 0; i < NB - 1; i++) {
+      BBox b0 = bb[i], b1 = bb[i];
+      uint32_t c0 = 0, c1 = 1;
+      for (int j = 0; j < i; j++) { b0 = b_union(b0, bb[j]); c0 += count[j]; }
+      for (int j = i + 1; j < NB; j++) { b1 = b_union(b1, bb[j]); c1 += count[j]; }
+      cost[i] = 0.125f + (((float)c0 * b_area(b0) + (float)c1 * b_area(b1)) / b_area(bounds));
+    }
+    float min_cost = cost[0];
+    int min_b = 0;
+    for (int i = 1; i < NB - 1; i++)
+      if (cost[i] < min_cost) { min_cost = cost[i]; min_b = i; }
+    std::vector<int32_t> c0, c1;
+    for (int32_t r : roots) (bucket(r) <= min_b ? c0 : c1).push_back(r);
+    const int32_t n0 = hl_upper_sah(c0);
+    const int32_t n1 = hl_upper_sah(c1);
+    return hl_interior(dim, n0, n1);
+  }
+  int32_t hlbvh(const Info* info, size_t n) {
+    hl_info = info;
+    hl_ord = 0;
+    BBox bounds = info[0].b;
+    for (size_t i = 1; i < n; i++) bounds = b_union(bounds, info[i].b);
+    std::vector<MortonPrim> mp(n);
+    auto clamp01 = [](float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); };
+    for (size_t i = 0; i < n; i++) {
+      mp[i].index = info[i].number;
+      float o[3];
+      for (int a = 0; a < 3; a++) {  // Bounds3f::offset
+        o[a] = info[i].c[a] - bounds.mn[a];
+        if (bounds.mx[a] > bounds.mn[a]) o[a] = o[a] / (bounds.mx[a] - bounds.mn[a]);
+      }
+      mp[i].code = (left_shift3(f2u(ceilf(clamp01(o[2]) * 1024.0f))) << 2) | (left_shift3(f2u(ceilf(clamp01(o[1]) * 1024.0f))) << 1) |
+                   left_shift3(f2u(ceilf(clamp01(o[0]) * 1024.0f)));
+    }
+    std::stable_sort(mp.begin(), mp.end(), [](const MortonPrim& a, const MortonPrim& b) { return a.code < b.code; });  // the LSD radix sort is stable
+    std::vector<int32_t> treelets;
+    const uint32_t MASK = 0x3ffc0000u;
+    for (size_t start = 0, end = 1; end <= n; end++)
+      if (end == n || (mp[start].code & MASK) != (mp[end].code & MASK)) {
+        treelets.push_back(hl_emit(mp.data() + start, end - start, 29 - 12));
+        start = end;
+      }
+    return hl_upper_sah(treelets);
+  }
+
   int32_t build(Info* pi, size_t n, int32_t self, size_t ord) {  // recursive_build (node.rs:27-105)
     BBox bounds = pi[0].b;
     for (size_t i = 1; i < n; i++) bounds = b_union(bounds, pi[i].b);
@@ -306,8 +440,14 @@ void build_bvh(const std::vector<BBox>& prim_bounds, int max_prims_in_node, int 
     unsigned hw = std::thread::hardware_concurrency();
     c.spare_threads.store((int)std::min(std::max(hw, 1u), 64u) - 1);
   }
-  int32_t root = c.build(info.data(), n, c.reserve(), 0);
-  (void)root;
+  if (split_method == 1) {  // PT_SPLIT_HLBVH: bottom-up, the root is made last; it is copied into node 0 (nothing reads node numbers)
+    const int32_t slot0 = c.reserve();
+    const int32_t root = c.hlbvh(info.data(), n);
+    out->tree[(size_t)slot0] = out->tree[(size_t)root];
+  } else {
+    int32_t root = c.build(info.data(), n, c.reserve(), 0);
+    (void)root;
+  }
   out->tree.resize((size_t)c.next_node.load());
   out->bounds = out->tree[0].bounds;
   Flat f;

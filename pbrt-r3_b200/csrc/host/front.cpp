@@ -1129,8 +1129,7 @@ struct Builder {
     std::string layout = accel_params.one_string("layout", "qbvh");  // GPU-path extension: "lbvh" selects accel/lbvh.rs
     A.type = layout == "lbvh" ? PT_ACCEL_LBVH : PT_ACCEL_QBVH;
     std::string split = accel_params.one_string("splitmethod", "sah");
-    if (split == "hlbvh") throw ParseError("splitmethod \"hlbvh\" is not supported on the GPU path");
-    A.split_method = split == "middle" ? PT_SPLIT_MIDDLE : (split == "equal" ? PT_SPLIT_EQUAL : PT_SPLIT_SAH);
+    A.split_method = split == "middle" ? PT_SPLIT_MIDDLE : (split == "equal" ? PT_SPLIT_EQUAL : (split == "hlbvh" ? PT_SPLIT_HLBVH : PT_SPLIT_SAH));
     A.max_prims_in_node = accel_params.one_int("maxnodeprims", 4);
 
     // emitters-only fix-up: they live after the sampled lights

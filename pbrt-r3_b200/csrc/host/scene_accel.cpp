@@ -1,6 +1,8 @@
 // scene_accel.cpp — see scene_accel.h.
 #include "scene_accel.h"
 
+#include <stdexcept>
+
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -75,7 +77,8 @@ std::string build_objects(const pt_scene_desc* D, std::vector<ObjectHost>* out) 
       O.bounds = pb[0];
       O.ordered.assign(pr, pr + 1);
     } else {
-      build_bvh(pb, D->accel.max_prims_in_node, D->accel.split_method, &O.bvh);
+      try { build_bvh(pb, D->accel.max_prims_in_node, D->accel.split_method, &O.bvh); }
+      catch (const std::exception& e) { return std::string("BVH build: ") + e.what(); }
       O.bounds = O.bvh.bounds;
       O.ordered.resize(n);
       for (size_t i = 0; i < n; i++) O.ordered[i] = pr[O.bvh.ordered[i]];

@@ -191,6 +191,21 @@ def test_aov_integrator(P, pair, target):
         assert st["shadow_rays"] == 0 and st["regular_rays"] == st["camera_rays"]
 
 
+def test_hlbvh_split_method(P, pair):
+    """Accelerator "bvh" "string splitmethod" ["hlbvh"] (build/hlbvh.rs): hits bit-exact and visit counters equal to the oracle's
+    on the Morton-treelet tree, with instances."""
+    hl = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string splitmethod" ["hlbvh"]')
+    for name, txt in (("hl_grid", P.scenes.displaced_grid(n=120, res=64, spp=4)), ("hl_inst", P.scenes.instanced_blobs(n_instances=60, n_sub=2, res=(96, 64), spp=4, n_lights=8))):
+        hs, sc, orc = pair(name, hl(txt))
+        rays = _random_rays(orc, 30000, 31)
+        _check_intersections(sc, orc, rays)
+        rgb, st = sc.render(collect_counters=1)
+        ref, so = orc.render()
+        assert rel_rmse(rgb, ref) <= RMSE_TOL
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested"):
+            assert st[k] == so[k], (name, k)
+
+
 def test_ao_integrator(P):
     """Integrator "ambientocclusion" (integrators/ao.rs): per-sample values bit for bit vs the oracle (cosine and uniform
     hemisphere, halton and sobol sample arrays, instances, a surface without a material), image, ray / visit counters, and

@@ -570,6 +570,31 @@ def test_host_bvh_equals_oracle_other_splits(P, split):
     _compare_bvh(P, P.HostScene.parse_string(txt), [0])
 
 
+@pytest.mark.parametrize("maxprims", [4, 1])
+def test_host_bvh_equals_oracle_hlbvh(P, maxprims):
+    """splitmethod "hlbvh" (build/hlbvh.rs): Morton treelets + SAH over the treelets; host build == oracle restatement, and the
+    tree finds what a brute-force search finds."""
+    import oracle_api
+    hl = 'Accelerator "bvh" "string splitmethod" ["hlbvh"] "integer maxnodeprims" [%d]' % maxprims
+    for txt, objects in ((P.scenes.displaced_grid(n=96, res=32, spp=1), [0]), (P.scenes.cornell_box(), [0]),
+                         (P.scenes.instanced_blobs(n_instances=40, n_sub=2, res=(32, 24), spp=1, n_lights=4), [0, 1, 2])):
+        hs = P.HostScene.parse_string(txt.replace('Accelerator "bvh"', hl))
+        assert hs.desc.accel.split_method == P.capi.PT_SPLIT_HLBVH
+        _compare_bvh(P, hs, objects)
+        sah = oracle_api.OracleScene(P.HostScene.parse_string(txt))
+        orc = oracle_api.OracleScene(hs)
+        assert not np.array_equal(orc.bvh_info(0)[1], sah.bvh_info(0)[1])          # a different tree than the SAH build's
+        wb = orc.world_bound()
+        rng = np.random.RandomState(3)
+        o = rng.uniform(wb[:3] - 1, wb[3:] + 1, (3000, 3)).astype(np.float32)
+        t = rng.uniform(wb[:3], wb[3:], (3000, 3)).astype(np.float32)
+        rays = np.concatenate([o, np.full((3000, 1), np.inf, np.float32), (t - o), np.zeros((3000, 1), np.float32)], 1).astype(np.float32)
+        pa, ta = orc.intersect(rays)[:2]
+        pb, tb = orc.intersect_exhaustive(rays)[:2]
+        assert np.array_equal(pa, pb) and np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+        orc.close(); sah.close()
+
+
 def test_host_bvh_equals_oracle_instances(P):
     hs = P.HostScene.parse_string(P.scenes.instanced_blobs(n_instances=40, n_sub=2, res=(32, 24), spp=1, n_lights=4))
     _compare_bvh(P, hs, [0, 1, 2, 3, 4])

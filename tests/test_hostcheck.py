@@ -456,6 +456,17 @@ def test_hostcheck_extra_materials(HC):
     check_extra_materials(HC)
 
 
+def test_hostcheck_hlbvh_split(HC):
+    """splitmethod "hlbvh": the same stage logic on the Morton-treelet tree (visit counters equal the oracle's)."""
+    hl = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string splitmethod" ["hlbvh"]')
+    hs, sc, orc = _cmp_li(HC, hl(HC.scenes.instanced_blobs(n_instances=30, n_sub=1, res=(48, 32), spp=4, n_lights=4)), 2000, 4, 0.999)
+    rgb, st = sc.render(collect_counters=1)
+    ref, so = orc.render(threads=2)
+    assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5
+    for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+        assert st[k] == so[k], k
+
+
 def test_hostcheck_lbvh_layout(HC):
     """Accelerator layout "lbvh" (accel/lbvh.rs): same stage logic on the binary node layout, instances included."""
     lb = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string layout" "lbvh"')
