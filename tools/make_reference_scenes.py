@@ -15,6 +15,20 @@ S = {
     "config4_spectral_cornell_128_8spp": scenes.cornell_box(res=128, spp=8, maxdepth=5),
     "mixed_materials_96_16spp": scenes.cornell_box(res=96, spp=16, materials="mixed", extra_lights=True, maxdepth=8),
 }
+# round-2 widening: the integrators beside "path", the infinite light, uber / substrate / translucent, hlbvh, loopsubdiv
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import pbrt_r3_b200 as P
+import test_hostcheck as T
+S.update({
+    "r2_ambientocclusion_64_4spp": T.ao_scene(P, nsamples=16, res=64, spp=4),
+    "r2_directlighting_all_64_4spp": T.tree_scene(P, '"directlighting"', res=64, spp=4, nsamples=2),
+    "r2_directlighting_one_64_4spp": T.tree_scene(P, '"directlighting" "string strategy" ["one"]', res=64, spp=4),
+    "r2_whitted_64_4spp": T.tree_scene(P, '"whitted"', res=64, spp=4),
+    "r2_infinite_constant_64_8spp": T.env_scene(P, out, mapped=False, res=64, spp=8),
+    "r2_infinite_map_64_8spp": T.env_scene(P, out, mapped=True, res=64, spp=8),
+    "r2_extra_materials_64_8spp": T.extra_materials_scene(P, res=64, spp=8),
+    "r2_hlbvh_grid_64_4spp": scenes.displaced_grid(n=96, res=64, spp=4).replace('Accelerator "bvh"', 'Accelerator "bvh" "string splitmethod" ["hlbvh"]'),
+})
 for name, txt in S.items():
     open(os.path.join(out, name + ".pbrt"), "w").write(txt)
     print("wrote", name)
