@@ -948,6 +948,11 @@ int render_waves(pt_scene* s, const pt_render_opts* o, pt_stats* st) {
   const bool timed = st != nullptr;
   if (build_pixlist(s, shard_i, shard_n, tile)) return 1;
   uint32_t cap = (o && o->wave_paths > 0) ? (uint32_t)o->wave_paths : (NC == 3 ? PT_WAVE_PATHS_RGB : (1u << 19));
+  if (!(o && o->wave_paths > 0) && (s->h.integrator.type == PT_INTEGRATOR_DIRECT || s->h.integrator.type == PT_INTEGRATOR_WHITTED)) {
+    // the tree walk keeps max_depth - 1 frames of 68 bytes per path slot (ensure_wave): bound them to ~8 GB over the waves in flight
+    const uint64_t frames = (uint64_t)std::max(s->h.integrator.max_depth - 1, 1);
+    cap = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1u << 18, (8ull << 30) / (frames * 68ull * 6ull)));
+  }
   uint32_t npix_total = s->pix_n;
   int ns_total = std::max(s_end - s_begin, 0);
   const bool is_path = s->h.integrator.type == PT_INTEGRATOR_PATH;
