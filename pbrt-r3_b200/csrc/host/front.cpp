@@ -1099,7 +1099,10 @@ struct Builder {
       I.type = direct ? PT_INTEGRATOR_DIRECT : PT_INTEGRATOR_WHITTED;
       if (direct) I.direct_strategy = integrator_params.one_string("strategy", "all") == "one" ? PT_DIRECT_ONE : PT_DIRECT_ALL;
       if (!direct && integrator_params.find(PC_INT, "pixelbounds")) throw ParseError("Integrator \"whitted\": pixelbounds is not supported on the GPU path");
-      if (S.type == PT_SAMPLER_RANDOM) throw ParseError("Integrator \"" + integrator_name + "\" with Sampler \"random\" is not supported on the GPU path (halton, sobol)");
+      // Sampler "random": the per-tile PCG32 streams are drawn from in the recursion's own order by the depth-first walk; the
+      // "all" strategy would also need the sample ARRAYS drawn at every start_pixel (random.rs), which is not built
+      if (S.type == PT_SAMPLER_RANDOM && direct && I.direct_strategy == PT_DIRECT_ALL)
+        throw ParseError("Integrator \"directlighting\" \"strategy\" \"all\" with Sampler \"random\" is not supported on the GPU path (halton, sobol; or strategy \"one\")");
       if (spec.n_channels() != 3) throw ParseError("Integrator \"" + integrator_name + "\" is only supported with RGB spectra");
     }
     if (integrator_name == "aov") {  // integrators/aov.rs:192-213, targets :36-58

@@ -218,8 +218,9 @@ def test_tree_integrators(P):
     """Integrators "directlighting" (one / all with sample arrays / arrays used up) and "whitted" (core/integrator/
     sampler.rs:37-160 specular_reflect / specular_transmit as a depth-first tree walk): per-sample radiance within 2e-5 of
     the oracle's recursion, equal ray / BVH-visit / vertex counters, image, pipelined waves against one wave at a time."""
-    from test_hostcheck import check_tree
+    from test_hostcheck import check_tree, check_tree_random
     check_tree(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
+    check_tree_random(P, res=72, spp=2, threads=0)
 
 
 def test_infinite_light(P, tmp_path):

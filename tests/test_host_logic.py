@@ -201,8 +201,10 @@ def test_front_end_tree_integrators(P):
     for bad in ('"whitted" "integer pixelbounds" [0 1 0 1]',):
         with pytest.raises(P.PbrtError):
             P.HostScene.parse_string(base % ("", bad, ""))
-    with pytest.raises(P.PbrtError):
-        P.HostScene.parse_string(base % ('Sampler "random"\n', '"whitted"', ""))
+    with pytest.raises(P.PbrtError):       # the "all" strategy needs the random sampler's per-pixel sample arrays
+        P.HostScene.parse_string(base % ('Sampler "random"\n', '"directlighting"', ""))
+    for ok in ('"whitted"', '"directlighting" "string strategy" ["one"]'):
+        assert P.HostScene.parse_string(base % ('Sampler "random"\n', ok, "")).desc.sampler.type == P.capi.PT_SAMPLER_RANDOM
     lib = P.capi.load()
     lib.pt_set_options(P.capi.pt_options(1, 0))
     try:

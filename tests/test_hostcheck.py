@@ -331,6 +331,24 @@ def check_tree(P, n=1500, res=24, spp=2, wave_paths=300, threads=2, cases=None):
         assert np.array_equal(one, rgb), (integ, kw)
 
 
+def check_tree_random(P, res=33, spp=2, threads=2):
+    """Sampler "random" under whitted / directlighting "one": the depth-first walk draws from the tile's PCG32 stream in the
+    recursion's own order (same image, same counters as the oracle's recursion)"""
+    import oracle_api
+    for integ in ('"whitted"', '"directlighting" "string strategy" ["one"]'):
+        hs = P.HostScene.parse_string(tree_scene(P, integ, res=res, spp=spp, sampler="random"))
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        rgb, st = sc.render(collect_counters=1)
+        ref, so = orc.render(threads=threads)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5, integ
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[k] == so[k], (integ, k, st[k], so[k])
+
+
+def test_hostcheck_tree_integrators_random_sampler(HC):
+    check_tree_random(HC)
+
+
 def test_hostcheck_tree_integrators(HC):
     """Integrators "directlighting" (strategies one / all, sample arrays) and "whitted": the specular reflection /
     transmission recursion as a depth-first tree walk per path slot."""
