@@ -750,15 +750,18 @@ int shade_classes(pt_scene* s, int NC, int grid, unsigned long long* vc) {
   return n;
 }
 
-// k_ri in the variant the scene needs: two-lobe BSDFs unless it has uber / translucent materials, the infinite-light code
-// only with an infinite light (the generic kernel is 10-20 % slower with either compiled in)
+// k_ri in the variant the scene needs: whitted or directlighting, two-lobe BSDFs unless it has uber / translucent materials,
+// the infinite-light code only with an infinite light (the generic kernel is 10-20 % slower with either compiled in)
 template <int NC>
 void launch_ri(pt_scene* s, int grid, const WaveState& W, const Queues& Q, uint32_t n_ext, uint32_t n_wait, const uint32_t* prev, unsigned long long* vc) {
   if constexpr (NC == 3) {
     const bool wide = (s->class_mask & (1u << CL_EXTRA)) != 0, env = s->h.n_inf != 0;
-#define PT_RI(ML, ENV) PT_LAUNCH(grid, PT_SHADE_BLOCK, s->stream, k_ri<NC, ML, ENV>)(s->h, W, Q, Q.wait, n_ext, n_wait, prev, vc)
-    if (wide) { if (env) PT_RI(PT_LOBES_EXTRA, true); else PT_RI(PT_LOBES_EXTRA, false); }
-    else { if (env) PT_RI(PT_MAX_LOBES, true); else PT_RI(PT_MAX_LOBES, false); }
+#define PT_RI(ML, ENV, WH) PT_LAUNCH(grid, PT_SHADE_BLOCK, s->stream, k_ri<NC, ML, ENV, WH>)(s->h, W, Q, Q.wait, n_ext, n_wait, prev, vc)
+#define PT_RI2(ML, ENV) do { if (wh) PT_RI(ML, ENV, true); else PT_RI(ML, ENV, false); } while (0)
+    const bool wh = s->h.integrator.type == PT_INTEGRATOR_WHITTED;
+    if (wide) { if (env) PT_RI2(PT_LOBES_EXTRA, true); else PT_RI2(PT_LOBES_EXTRA, false); }
+    else { if (env) PT_RI2(PT_MAX_LOBES, true); else PT_RI2(PT_MAX_LOBES, false); }
+#undef PT_RI2
 #undef PT_RI
   }
 }

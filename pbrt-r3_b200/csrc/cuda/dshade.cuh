@@ -745,11 +745,15 @@ PT_HD void ao_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i) {
 #define PT_RI_MAX_DEPTH 32
 // ML: lobes per BSDF (2, or 5 when the scene has uber / translucent materials: the wider BSDF costs 10-19 % of this stage)
 // ENV: the scene has infinite lights (as for the shade kernels, their code is compiled into separate variants)
-template <int NC, int ML, bool ENV>
+// WHITTED: the integrator, as a compile-time switch (each kernel then holds one lighting loop, not both)
+// The body has ONE call site each for make_surface / make_bsdf and two for bsdf_sample (light sampling, specular branches):
+// the popped transmission branch re-enters the loop at the branch stage.  (ncu, profiles/r2z: the first, fully divergent
+// launch of a step stalled 19 cycles per issue on instruction fetch with three inlined copies of the sampling code.)
+template <int NC, int ML, bool ENV, bool WHITTED>
 PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fresh, unsigned long long* vertex_counter) {
   const uint32_t cap = W.cap;
   constexpr int CM = ML == PT_MAX_LOBES ? (PT_CM_ANY & ~((1 << LB_LAMBERT_T) | (1 << LB_FRESNEL_BLEND))) : PT_CM_ANY;  // the extra materials' lobes only with them
-  const bool whitted = S.integrator.type == PT_INTEGRATOR_WHITTED;
+  constexpr bool whitted = WHITTED;
   const int NONSPEC = F_ALL & ~F_SPEC;
   Sp<NC> L = st_load<NC>(W.L, cap, i);
   L = L + st_load<NC>(W.pendA, cap, i);
@@ -780,37 +784,43 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
   SurfD si;
   BsdfT<ML> B;
   B.n = -1;
+  bool need_make = false, lit = false;  // lit: the vertex's lighting rounds are over (a popped transmission branch)
+  int branch0 = 0;
   if ((int)fbits(h4.w) < 0) {  // the ray left the scene: li = sum of Light::le (directlighting.rs:112-122, whitted.rs:86-96)
     need_pop = true;
     if (ENV && fresh)
       for (uint32_t k = 0; k < S.n_inf; k++) L = L + beta * env_le<NC>(S, ldg(S.inf_lights + k), xyz(rd4));
-  } else {
-    si = make_surface(S, (int)fbits(h4.w), inst, xyz(ro4), xyz(rd4), rtime, h4.x, h4.y, h4.z);
-    make_bsdf<NC, -1, false>(S, si, &B);
-    if (B.n < 0) {  // no BSDF: whitted returns zero (whitted.rs:84), directlighting follows the ray at the same depth (:108-110)
-      if (whitted) need_pop = true;
-      else {
-        f3 o = offset_origin(si.p, si.perr, si.n, xyz(rd4));
-        W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
-        push_ext = true;
-      }
-    } else have_vertex = true;
-  }
-  if (have_vertex && fresh) {
-    if (vertex_counter) {
-#if defined(__CUDA_ARCH__)
-      atomicAdd(vertex_counter, 1ull);
-#else
-      (*vertex_counter)++;
-#endif
-    }
-    if (!whitted) L = L + beta * surface_le<NC>(S, si, si.wo);
-  }
+  } else need_make = true;
   for (;;) {
+    if (need_make) {  // the interaction and BSDF of the vertex in (ro4, rd4, h4): just traced, between two rounds, or popped
+      need_make = false;
+      si = make_surface(S, (int)fbits(h4.w), inst, xyz(ro4), xyz(rd4), rtime, h4.x, h4.y, h4.z);
+      make_bsdf<NC, -1, false>(S, si, &B);
+      if (B.n < 0) {  // no BSDF: whitted returns zero (whitted.rs:84), directlighting follows the ray at the same depth (:108-110)
+        if (whitted) need_pop = true;
+        else {
+          f3 o = offset_origin(si.p, si.perr, si.n, xyz(rd4));
+          W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
+          push_ext = true;
+        }
+      } else {
+        have_vertex = true;
+        if (fresh && !lit) {
+          if (vertex_counter) {
+#if defined(__CUDA_ARCH__)
+            atomicAdd(vertex_counter, 1ull);
+#else
+            (*vertex_counter)++;
+#endif
+          }
+          if (!whitted) L = L + beta * surface_le<NC>(S, si, si.wo);
+        }
+      }
+    }
     if (have_vertex) {
       RefPt ref;
       ref.p = si.p; ref.perr = si.perr; ref.n = si.n;
-      const uint32_t nl = S.n_lights;
+      const uint32_t nl = lit ? 0u : S.n_lights;
       const bool all = !whitted && S.integrator.direct_strategy == PT_DIRECT_ALL;
       if (all && round == 0u && nl > 0u) {  // uniform_sample_all_lights asks for two arrays per light (sample_lights.rs:38-39)
         arrays = arr_off < 2u * nl * (uint32_t)S.integrator.max_depth;
@@ -910,7 +920,7 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
       // specular_reflect, then specular_transmit (directlighting.rs:101-104, whitted.rs:80-83)
       need_pop = true;
       if (depth + 1 < S.integrator.max_depth) {
-        for (int branch = 0; branch < 2 && need_pop; branch++) {
+        for (int branch = branch0; branch < 2 && need_pop; branch++) {
           f2 u = get2d(S, st);
           Sp<NC> f;
           f3 wi;
@@ -950,26 +960,8 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
       inst = W.fr_inst ? W.fr_inst[fi] : -1;
       depth = (int)fbits(ro4.w);
     }
-    si = make_surface(S, (int)fbits(h4.w), inst, xyz(ro4), xyz(rd4), rtime, h4.x, h4.y, h4.z);
-    make_bsdf<NC, -1, false>(S, si, &B);
-    // specular_transmit of the frame's vertex
-    f2 u = get2d(S, st);
-    Sp<NC> f;
-    f3 wi;
-    float pdf;
-    int stype;
-    have_vertex = false;
-    if (!bsdf_sample<NC, CM>(S, B, si.wo, u, F_TRANS | F_SPEC, &f, &wi, &pdf, &stype)) continue;
-    const float wi_ns = absdot3(wi, si.sn);
-    if (!(pdf > 0.0f && !sp_black(f) && wi_ns != 0.0f)) continue;
-    beta = beta * (f * (wi_ns / pdf));
-    f3 o = offset_origin(si.p, si.perr, si.n, wi);
-    W.ray_o[i] = mk4(o.x, o.y, o.z, pt_inf());
-    W.ray_d[i] = mk4(wi.x, wi.y, wi.z, rtime);
-    depth += 1;
-    push_ext = true;
-    need_pop = false;
-    break;
+    // specular_transmit of the frame's vertex: back to the branch stage with the vertex rebuilt
+    need_make = true; have_vertex = false; lit = true; branch0 = 1; need_pop = false;
   }
   st_store<NC>(W.L, cap, i, L);
   st_store<NC>(W.beta, cap, i, beta);

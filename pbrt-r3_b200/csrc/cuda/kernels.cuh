@@ -376,14 +376,14 @@ __global__ void __launch_bounds__(PT_SHADE_BLOCK) k_ao(const __grid_constant__ D
 #ifndef PT_RI_MINBLOCKS
 #define PT_RI_MINBLOCKS 3
 #endif
-template <int NC, int ML, bool ENV>
+template <int NC, int ML, bool ENV, bool WHITTED>
 __global__ void __launch_bounds__(PT_SHADE_BLOCK, PT_RI_MINBLOCKS) k_ri(const __grid_constant__ DScene S, WaveState W, Queues Q, const uint32_t* __restrict__ wait_in, uint32_t n_ext, uint32_t n_wait,
                                                        const uint32_t* prev, unsigned long long* vertex_counter) {
   if (prev) { n_ext += prev[0]; n_wait = prev[4]; }
   const uint32_t total = n_ext + n_wait;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
     const bool fresh = k < n_ext;
-    ri_body<NC, ML, ENV>(S, W, Q, fresh ? Q.ext[k] : wait_in[k - n_ext], fresh, vertex_counter);
+    ri_body<NC, ML, ENV, WHITTED>(S, W, Q, fresh ? Q.ext[k] : wait_in[k - n_ext], fresh, vertex_counter);
   }
 }
 
