@@ -72,5 +72,8 @@ allt[cfg_key] = {"k_trace_dram_bytes_per_launch": (rd + wr) / n, "k_trace_dram_r
 json.dump(allt, open(tpath, "w"), indent=1)
 print("k_trace per launch: DRAM %.0f MB, L2 %.0f MB, algorithmic %.0f MB (%d launches)" % ((rd + wr) / n / 1e6, l2 / n / 1e6, alg / 1e6, n))
 for kind, width in (("trace", 260), ("shade", 420)):
+    if not os.path.exists(os.path.join(G, "prof_%s_%s.ncu-rep" % (kind, tag))):
+        print("no prof_%s_%s.ncu-rep: summary skipped" % (kind, tag))
+        continue
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), os.path.join(G, "prof_%s_%s.ncu-rep" % (kind, tag))], capture_output=True, text=True).stdout
     open(os.path.join(P, "%s_ncu_%s_summary.txt" % (tag, kind)), "w").write("\n".join(l[:width] for l in out.splitlines()) + "\n")
