@@ -63,9 +63,15 @@ struct Scene {
       if (desc->lights[i].type == PT_LIGHT_INFINITE) infinite_lights.push_back((int)i);
     if (desc->n_lights > 0) distrib.init(desc, world_bound, world_radius, envs.data());
     scfg = make_sampler_config(desc->sampler.type, desc->sampler.samples_per_pixel, desc->film.sample_bounds, desc->sampler.sample_at_pixel_center != 0);
-    if (desc->integrator.type == PT_INTEGRATOR_AO) scfg.n_arrays_2d = 1;  // AOIntegrator::new: request_2d_array(n_samples) (ao.rs:29)
-    if (desc->integrator.type == PT_INTEGRATOR_DIRECT && desc->integrator.direct_strategy == PT_DIRECT_ALL)  // directlighting.rs:57-63
+    if (desc->integrator.type == PT_INTEGRATOR_AO) {  // AOIntegrator::new: request_2d_array(n_samples) (ao.rs:29)
+      scfg.n_arrays_2d = 1;
+      scfg.array_sizes_2d.assign(1, (uint32_t)desc->integrator.ao_samples);
+    }
+    if (desc->integrator.type == PT_INTEGRATOR_DIRECT && desc->integrator.direct_strategy == PT_DIRECT_ALL) {  // directlighting.rs:57-63
       scfg.n_arrays_2d = 2u * n_sampled_lights() * (uint32_t)std::max(desc->integrator.max_depth, 0);
+      for (int dd = 0; dd < desc->integrator.max_depth; dd++)
+        for (uint32_t j = 0; j < n_sampled_lights(); j++) { scfg.array_sizes_2d.push_back((uint32_t)desc->lights[j].n_samples); scfg.array_sizes_2d.push_back((uint32_t)desc->lights[j].n_samples); }
+    }
   }
   // scene.lights: the lights that can be sampled (area lights inside object instances only emit when hit; front end)
   uint32_t n_sampled_lights() const { return d->n_lights; }
@@ -236,7 +242,7 @@ inline Spec<NC> ao_li(Scene<NC>& sc, const Ray& r, Sampler& sampler, Counters* c
     Vec3 s = normalize(isect.dpdu);
     Vec3 t = cross(isect.n, s);
     for (uint32_t i = 0; i < n_samples; i++) {
-      Vec2 u = sampler.array_2d_elem(n_samples, i);
+      Vec2 u = sampler.array_2d_elem_of(0, n_samples, i);
       Vec3 wl;
       Float pdf;
       if (cos_sample) { wl = cosine_sample_hemisphere(u); pdf = fabsf(wl.z) * INV_PI; }
@@ -260,9 +266,10 @@ inline Spec<NC> sample_all_lights(Scene<NC>& sc, const SurfInt& it, const BSDF<N
     const bool a = sampler.next_2d_array(), b = sampler.next_2d_array();
     if (a && b) {
       Spec<NC> ld;
+      const uint32_t ka = sampler.array2d_offset - 2, kb = sampler.array2d_offset - 1;  // u_light_array, u_scattering_array
       for (uint32_t k = 0; k < n; k++) {
-        Vec2 u = sampler.array_2d_elem(n, k);
-        ld = ld + estimate_direct(sc, it, bsdf, u, (int)j, u, cnt);
+        Vec2 u_light = sampler.array_2d_elem_of(ka, n, k), u_scattering = sampler.array_2d_elem_of(kb, n, k);
+        ld = ld + estimate_direct(sc, it, bsdf, u_scattering, (int)j, u_light, cnt);
       }
       l = l + ld / (Float)n;
     } else {

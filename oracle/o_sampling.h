@@ -174,6 +174,7 @@ struct SamplerConfig {
   uint32_t resolution, log2_resolution;
   // sample arrays the integrator requested (base_sampler.rs:32-44): ambientocclusion one 2D array, directlighting two per light
   uint32_t n_arrays_1d, n_arrays_2d;
+  std::vector<uint32_t> array_sizes_2d;  // n of each requested 2D array, in request order (random sampler: its own values per array)
 };
 
 inline uint64_t math_mod(int64_t a, int64_t b) {  // halton.rs:22-29
@@ -230,6 +231,7 @@ struct Sampler {
   RNG rng;              // random sampler: per-tile stream
   int64_t halton_offset;
   uint32_t array2d_offset = 0;  // get_2d_array calls so far in this sample (base_sampler.rs:59-70)
+  std::vector<std::vector<Vec2>> random_arrays;  // RandomSampler: sample_array2d, refilled by every start_pixel (random.rs:46-60)
 
   Sampler(const SamplerConfig* c, uint32_t tile_seed) : cfg(c), px(0), py(0), sample_num(0), interval_index(0), dimension(0), rng((uint64_t)tile_seed), halton_offset(0) {}
 
@@ -240,6 +242,13 @@ struct Sampler {
   }
   void start_pixel(int x, int y) {
     px = x; py = y; sample_num = 0; dimension = 0; array2d_offset = 0;
+    if (cfg->type == 2 && !cfg->array_sizes_2d.empty()) {  // random.rs:46-60: every element of every array, in order, before the first sample
+      random_arrays.resize(cfg->array_sizes_2d.size());
+      for (size_t a = 0; a < random_arrays.size(); a++) {
+        random_arrays[a].resize((size_t)cfg->array_sizes_2d[a] * (size_t)cfg->spp);
+        for (Vec2& v : random_arrays[a]) { Float x0 = rng.uniform_float(); Float y0 = rng.uniform_float(); v = Vec2(x0, y0); }
+      }
+    }
     if (cfg->type == 0) {   // halton.rs:115-147
       halton_offset = 0;
       int64_t stride = cfg->sample_stride;
@@ -292,6 +301,11 @@ struct Sampler {
     if (array2d_offset == cfg->n_arrays_2d) return false;
     array2d_offset++;
     return true;
+  }
+  // element i of the array handed out by the k-th get_2d_array call of this sample (k = 0, 1, ..)
+  Vec2 array_2d_elem_of(uint32_t k, uint32_t n, uint32_t i) const {
+    if (cfg->type == 2) return random_arrays[k][(size_t)n * (size_t)sample_num + i];
+    return array_2d_elem(n, i);
   }
   Vec2 array_2d_elem(uint32_t n, uint32_t i) const {
     int64_t index = index_for_sample((int64_t)n * sample_num + (int64_t)i);

@@ -497,6 +497,19 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
     if (prefix[D->n_lights] > 0x7fffu) { pt_set_error("directlighting: more than 32767 light samples per vertex"); return 1; }
     CK(s->bufs.upload(prefix.data(), prefix.size(), &H.light_sample_prefix));
   }
+  H.tile_arrays = nullptr;
+  H.tile_arr_stride = 0u;
+  if (D->sampler.type == PT_SAMPLER_RANDOM) {  // floats per tile of the random sampler's 2D sample arrays (build_pixlist allocates them)
+    uint64_t elems = 0;
+    if (D->integrator.type == PT_INTEGRATOR_AO) elems = (uint64_t)std::max(D->integrator.ao_samples, 0);
+    if (D->integrator.type == PT_INTEGRATOR_DIRECT && D->integrator.direct_strategy == PT_DIRECT_ALL) {
+      for (uint32_t i = 0; i < D->n_lights; i++) elems += 2ull * (uint64_t)std::max(D->lights[i].n_samples, 1);
+      elems *= (uint64_t)std::max(D->integrator.max_depth, 0);
+    }
+    elems *= 2ull * (uint64_t)std::max(D->sampler.samples_per_pixel, 0);
+    if (elems > (1ull << 24)) { pt_set_error("Sampler \"random\": the integrator's sample arrays exceed 16M values per pixel"); return 1; }
+    H.tile_arr_stride = (uint32_t)elems;
+  }
   for (uint32_t i = 0; i < D->n_lights; i++)
     if (D->lights[i].type == PT_LIGHT_SPOT && (D->lights[i].tri < 0 || (uint32_t)D->lights[i].tri >= D->n_spots)) { pt_set_error("spot light index out of range"); return 1; }
 
@@ -912,6 +925,8 @@ int build_pixlist(pt_scene* s, int shard_index, int shard_count, int tile) {
     CK(s->pix_bufs->upload(s->tiles_host.data(), s->tiles_host.size(), &dt));
     s->tiles = (int*)dt;
     CK(s->pix_bufs->alloc(s->tiles_host.size() / 3, &s->h.tile_rng));
+    s->h.tile_arrays = nullptr;
+    if (s->h.tile_arr_stride) CK(s->pix_bufs->alloc(s->tiles_host.size() / 3 * (size_t)s->h.tile_arr_stride, &s->h.tile_arrays));
   }
   s->pixlist = (int*)dp;
   s->pix_n = (uint32_t)px.size();

@@ -139,6 +139,10 @@ struct DScene {
   // Sampler "random": PCG32 state of every 16x16 render tile of the current shard (samplers/random.rs; one sequential
   // stream per tile, sampler.rs:285); rewritten by every draw
   uint64_t* tile_rng;
+  // its 2D sample arrays (ambientocclusion, directlighting "all"): RandomSampler::start_pixel draws every element of every
+  // requested array before the pixel's first sample (random.rs:46-60); tile_arr_stride floats per tile, refilled per pixel
+  float* tile_arrays;
+  uint32_t tile_arr_stride;
 };
 
 }  // namespace ptd

@@ -712,8 +712,14 @@ PT_HD void ao_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i) {
       f3 t = cross3(si.n, s);
       const int pk = W.pix[i];
       const int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
-      const int64_t idx = sampler_index(S, px, py, (int64_t)ns * (int64_t)W.sample_num[i] + (int64_t)round);
-      f2 u = mk2(sampler_dim(S, idx, 5u, px, py), sampler_dim(S, idx, 6u, px, py));
+      f2 u;
+      if (S.sampler.type == PT_SAMPLER_RANDOM) {  // element round of this sample's slice of the pixel's array
+        const float* a = S.tile_arrays + (size_t)((uint64_t)W.sindex[i] >> 32) * S.tile_arr_stride + 2u * (uint32_t)(ns * W.sample_num[i] + round);
+        u = mk2(a[0], a[1]);
+      } else {
+        const int64_t idx = sampler_index(S, px, py, (int64_t)ns * (int64_t)W.sample_num[i] + (int64_t)round);
+        u = mk2(sampler_dim(S, idx, 5u, px, py), sampler_dim(S, idx, 6u, px, py));
+      }
       f3 wl;
       float pdf;
       if (S.integrator.ao_cos_sample) { wl = cosine_hemisphere(u); pdf = fabsf(wl.z) * PT_INV_PI; }
@@ -848,9 +854,19 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
           }
           ln = (int)lo;
           const uint32_t n = (uint32_t)S.lights[ln].n_samples, k = round - ldg(S.light_sample_prefix + lo);
-          const int64_t idx = sampler_index(S, st.px, st.py, (int64_t)n * (int64_t)W.sample_num[i] + (int64_t)k);
-          u_light = mk2(sampler_dim(S, idx, 5u, st.px, st.py), sampler_dim(S, idx, 6u, st.px, st.py));
-          u_scat = u_light;
+          if (S.sampler.type == PT_SAMPLER_RANDOM) {
+            // arrays are laid out in request order: per depth, per light, (u_light, u_scattering), n x spp elements each;
+            // this vertex holds arrays arr_off - 2 nl .. arr_off
+            const uint32_t spp = (uint32_t)S.sampler.spp, d = (arr_off - 2u * nl) / (2u * nl);
+            const uint32_t e0 = spp * (d * 2u * ldg(S.light_sample_prefix + nl) + 2u * ldg(S.light_sample_prefix + lo)) + n * (uint32_t)W.sample_num[i] + k;
+            const float* a = S.tile_arrays + (size_t)((uint64_t)st.index >> 32) * S.tile_arr_stride;
+            u_light = mk2(a[2u * e0], a[2u * e0 + 1u]);
+            u_scat = mk2(a[2u * (e0 + spp * n)], a[2u * (e0 + spp * n) + 1u]);
+          } else {
+            const int64_t idx = sampler_index(S, st.px, st.py, (int64_t)n * (int64_t)W.sample_num[i] + (int64_t)k);
+            u_light = mk2(sampler_dim(S, idx, 5u, st.px, st.py), sampler_dim(S, idx, 6u, st.px, st.py));
+            u_scat = u_light;
+          }
           divisor = (float)n;
         }
         round++;

@@ -338,6 +338,10 @@ __global__ void k_raygen_random(const __grid_constant__ DScene S, WaveState W, Q
     uint32_t slot = (uint32_t)tr[0] + q - c0;
     int pk = pixlist[c0 + slot];
     int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
+    if (sample == 0 && S.tile_arr_stride) {  // start_pixel: the pixel's sample arrays come first in the tile's stream
+      float* a = S.tile_arrays + (size_t)(tile0 + t) * S.tile_arr_stride;
+      for (uint32_t k = 0; k < S.tile_arr_stride; k++) a[k] = random_draw(S, tile0 + t, (uint32_t)tr[2]);
+    }
     uint32_t qpos = atomicAdd(&Q.counts[5], 1u);
     raygen_body<NC>(S, W, Q, (uint32_t)sample * npix + slot, px, py, sample, (int)(tile0 + t), (uint32_t)tr[2], qpos);
   }

@@ -1091,7 +1091,6 @@ struct Builder {
       I.ao_samples = integrator_params.one_int("nsamples", 64);
       if (pt_current_options().quick_render) I.ao_samples = 1;
       if (I.ao_samples < 1) throw ParseError("Integrator \"ambientocclusion\": nsamples must be positive");
-      if (S.type == PT_SAMPLER_RANDOM) throw ParseError("Integrator \"ambientocclusion\" with Sampler \"random\" is not supported on the GPU path (halton, sobol)");
       if (spec.n_channels() != 3) throw ParseError("Integrator \"ambientocclusion\" is only supported with RGB spectra");
     }
     if (integrator_name == "directlighting" || integrator_name == "whitted") {  // directlighting.rs:135-158, whitted.rs:109-130
@@ -1100,9 +1099,7 @@ struct Builder {
       if (direct) I.direct_strategy = integrator_params.one_string("strategy", "all") == "one" ? PT_DIRECT_ONE : PT_DIRECT_ALL;
       if (!direct && integrator_params.find(PC_INT, "pixelbounds")) throw ParseError("Integrator \"whitted\": pixelbounds is not supported on the GPU path");
       // Sampler "random": the per-tile PCG32 streams are drawn from in the recursion's own order by the depth-first walk; the
-      // "all" strategy would also need the sample ARRAYS drawn at every start_pixel (random.rs), which is not built
-      if (S.type == PT_SAMPLER_RANDOM && direct && I.direct_strategy == PT_DIRECT_ALL)
-        throw ParseError("Integrator \"directlighting\" \"strategy\" \"all\" with Sampler \"random\" is not supported on the GPU path (halton, sobol; or strategy \"one\")");
+      // "all" strategy's sample ARRAYS are drawn at every start_pixel (random.rs:46-60), before the pixel's first camera sample
       if (spec.n_channels() != 3) throw ParseError("Integrator \"" + integrator_name + "\" is only supported with RGB spectra");
     }
     if (integrator_name == "aov") {  // integrators/aov.rs:192-213, targets :36-58

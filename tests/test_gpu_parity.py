@@ -210,8 +210,9 @@ def test_ao_integrator(P):
     """Integrator "ambientocclusion" (integrators/ao.rs): per-sample values bit for bit vs the oracle (cosine and uniform
     hemisphere, halton and sobol sample arrays, instances, a surface without a material), image, ray / visit counters, and
     the pipelined waves against one wave at a time."""
-    from test_hostcheck import check_ao
+    from test_hostcheck import check_ao, check_ao_random
     check_ao(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
+    check_ao_random(P, res=72, spp=3, threads=0)
 
 
 def test_tree_integrators(P):

@@ -178,8 +178,7 @@ def test_front_end_ao_integrator(P):
     assert (d.type, d.ao_samples, d.ao_cos_sample) == (P.capi.PT_INTEGRATOR_AO, 64, 1)                      # ao.rs:124-125 defaults
     d = P.HostScene.parse_string(base % ("", '"integer nsamples" [7] "bool cossample" ["false"]')).desc.integrator
     assert (d.ao_samples, d.ao_cos_sample) == (7, 0)
-    with pytest.raises(P.PbrtError):
-        P.HostScene.parse_string(base % ('Sampler "random"\n', ""))
+    assert P.HostScene.parse_string(base % ('Sampler "random"\n', "")).desc.sampler.type == P.capi.PT_SAMPLER_RANDOM
     lib = P.capi.load()
     lib.pt_set_options(P.capi.pt_options(1, 0))
     try:
@@ -201,9 +200,7 @@ def test_front_end_tree_integrators(P):
     for bad in ('"whitted" "integer pixelbounds" [0 1 0 1]',):
         with pytest.raises(P.PbrtError):
             P.HostScene.parse_string(base % ("", bad, ""))
-    with pytest.raises(P.PbrtError):       # the "all" strategy needs the random sampler's per-pixel sample arrays
-        P.HostScene.parse_string(base % ('Sampler "random"\n', '"directlighting"', ""))
-    for ok in ('"whitted"', '"directlighting" "string strategy" ["one"]'):
+    for ok in ('"whitted"', '"directlighting" "string strategy" ["one"]', '"directlighting"', '"ambientocclusion"'):
         assert P.HostScene.parse_string(base % ('Sampler "random"\n', ok, "")).desc.sampler.type == P.capi.PT_SAMPLER_RANDOM
     lib = P.capi.load()
     lib.pt_set_options(P.capi.pt_options(1, 0))

@@ -331,12 +331,32 @@ def check_tree(P, n=1500, res=24, spp=2, wave_paths=300, threads=2, cases=None):
         assert np.array_equal(one, rgb), (integ, kw)
 
 
-def check_tree_random(P, res=33, spp=2, threads=2):
-    """Sampler "random" under whitted / directlighting "one": the depth-first walk draws from the tile's PCG32 stream in the
-    recursion's own order (same image, same counters as the oracle's recursion)"""
+def check_ao_random(P, res=33, spp=3, threads=2):
+    """ambientocclusion under Sampler "random": the pixel's nsamples x spp array is drawn by start_pixel, before its first
+    camera sample (image and counters equal to the oracle's)"""
     import oracle_api
-    for integ in ('"whitted"', '"directlighting" "string strategy" ["one"]'):
-        hs = P.HostScene.parse_string(tree_scene(P, integ, res=res, spp=spp, sampler="random"))
+    for kw in (dict(nsamples=4), dict(nsamples=3, cos=False, instanced=True)):
+        hs = P.HostScene.parse_string(ao_scene(P, res=res, spp=spp, sampler="random", **kw))
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        rgb, st = sc.render(collect_counters=1)
+        ref, so = orc.render(threads=threads)
+        assert ref.mean() > 0 and np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-6, kw
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested"):
+            assert st[k] == so[k], (kw, k, st[k], so[k])
+
+
+def test_hostcheck_ao_random_sampler(HC):
+    check_ao_random(HC)
+
+
+def check_tree_random(P, res=33, spp=2, threads=2):
+    """Sampler "random" under whitted / directlighting: the depth-first walk draws from the tile's PCG32 stream in the
+    recursion's own order (same image, same counters as the oracle's recursion); strategy "all" reads the sample arrays
+    RandomSampler::start_pixel draws ahead of every pixel (separate u_light / u_scattering arrays, random.rs:46-60), then
+    get_2d pairs once they run out (maxdepth 2: the glass vertex and its reflection use them up)"""
+    import oracle_api
+    for integ, kw in (('"whitted"', {}), ('"directlighting" "string strategy" ["one"]', {}), ('"directlighting"', dict(nsamples=3)), ('"directlighting"', dict(nsamples=2, maxdepth=2))):
+        hs = P.HostScene.parse_string(tree_scene(P, integ, res=res, spp=spp, sampler="random", **kw))
         sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
         rgb, st = sc.render(collect_counters=1)
         ref, so = orc.render(threads=threads)
