@@ -136,13 +136,21 @@ typedef struct pt_instance {
   float minv[16];
 } pt_instance;
 
-typedef struct pt_camera {    /* cameras/perspective.rs, core/camera/projective.rs */
+enum pt_camera_type {
+  PT_CAMERA_PERSPECTIVE = 0,  /* cameras/perspective.rs */
+  PT_CAMERA_ORTHOGRAPHIC = 1, /* cameras/orthographic.rs:60-90 */
+  PT_CAMERA_ENVIRONMENT = 2   /* cameras/environment.rs:36-58: lat-long directions from film.full_resolution; no lens, raster_to_camera unused */
+};
+
+typedef struct pt_camera {    /* cameras/{perspective,orthographic,environment}.rs, core/camera/projective.rs */
   float raster_to_camera[16]; /* ProjectiveCamera.raster_to_camera.m   (row-major) */
   float camera_to_world[16];  /* BaseCamera.camera_to_world (static)   (row-major) */
   float lens_radius;
   float focal_distance;
   float shutter_open;
   float shutter_close;
+  int32_t type;               /* pt_camera_type */
+  int32_t pad;
 } pt_camera;
 
 typedef struct pt_film {      /* core/film/film.rs:64-164 */

@@ -15,12 +15,21 @@ namespace orc {
 
 struct CameraSample { Vec2 p_film, p_lens; Float time; };
 
-// PerspectiveCamera::generate_ray_differential (differentials dropped: constant textures only)
-inline Ray camera_ray(const pt_camera& C, const CameraSample& s) {
+// PerspectiveCamera::generate_ray_differential (perspective.rs:121-183), OrthographicCamera (orthographic.rs:60-90),
+// EnvironmentCamera::generate_ray (environment.rs:36-58); differentials dropped: constant textures only
+inline Ray camera_ray(const pt_camera& C, const pt_film& F, const CameraSample& s) {
   Mat4 r2c = mat_of(C.raster_to_camera), c2w = mat_of(C.camera_to_world);
+  if (C.type == PT_CAMERA_ENVIRONMENT) {
+    Float theta = PI * s.p_film.y / (Float)F.full_resolution[1];
+    Float phi = 2.0f * PI * s.p_film.x / (Float)F.full_resolution[0];
+    Vec3 dir(std::sin(theta) * std::cos(phi), std::cos(theta), std::sin(theta) * std::sin(phi));
+    Ray ray(Vec3(0, 0, 0), dir, INF, lerp(s.time, C.shutter_open, C.shutter_close));
+    return transform_ray(c2w, ray);
+  }
   Vec3 p_camera = r2c.point(Vec3(s.p_film.x, s.p_film.y, 0.0f));
-  Vec3 dir = normalize(p_camera);
-  Ray ray(Vec3(0, 0, 0), dir, INF, s.time);
+  Ray ray(Vec3(0, 0, 0), Vec3(0, 0, 0), INF, s.time);
+  if (C.type == PT_CAMERA_ORTHOGRAPHIC) { ray.o = p_camera; ray.d = Vec3(0.0f, 0.0f, 1.0f); }
+  else ray.d = normalize(p_camera);
   if (C.lens_radius > 0.0f) {
     Vec2 pl = concentric_sample_disk(s.p_lens) * C.lens_radius;
     Float ft = C.focal_distance / ray.d.z;
@@ -582,7 +591,7 @@ inline void render(Scene<NC>& sc, int n_threads, int s0, int s1, float* out_rgb,
             cs.p_film = Vec2((Float)x, (Float)y) + u;
             cs.p_lens = sampler.get_2d();
             cs.time = sampler.get_1d();
-            Ray ray = camera_ray(d->camera, cs);
+            Ray ray = camera_ray(d->camera, d->film, cs);
             cnt.camera_rays++;
             Spec<NC> l = integrator_li(sc, ray, sampler, &cnt, nullptr);
             l = validate_radiance(d, l);

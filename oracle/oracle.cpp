@@ -51,7 +51,7 @@ static void do_li(Scene<NC>& S, const int32_t* pixel_xy, const int32_t* sample_n
     cs.p_film = Vec2((Float)pixel_xy[2 * i], (Float)pixel_xy[2 * i + 1]) + u;
     cs.p_lens = sampler.get_2d();
     cs.time = sampler.get_1d();
-    Ray ray = camera_ray(S.d->camera, cs);
+    Ray ray = camera_ray(S.d->camera, S.d->film, cs);
     PathTrace tr;
     Spec<NC> l = integrator_li(S, ray, sampler, &cnt, &tr);
     for (int k = 0; k < NC; k++) out_l[(size_t)i * NC + k] = l.c[k];
@@ -204,7 +204,7 @@ int orc_camera_rays(orc_scene* s, const int32_t* pixel_xy, const int32_t* sample
     cs.p_film = Vec2((Float)pixel_xy[2 * i], (Float)pixel_xy[2 * i + 1]) + u;
     cs.p_lens = sm.get_2d();
     cs.time = sm.get_1d();
-    Ray r = camera_ray(s->d->camera, cs);
+    Ray r = camera_ray(s->d->camera, s->d->film, cs);
     float* q = rays + (size_t)i * 8;
     q[0] = r.o.x; q[1] = r.o.y; q[2] = r.o.z; q[3] = r.t_max; q[4] = r.d.x; q[5] = r.d.y; q[6] = r.d.z; q[7] = r.time;
     if (p_film) { p_film[2 * i] = cs.p_film.x; p_film[2 * i + 1] = cs.p_film.y; }

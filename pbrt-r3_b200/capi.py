@@ -17,6 +17,7 @@ PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT, PT_LIGHT_INFINIT
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
 PT_SPLIT_SAH, PT_SPLIT_HLBVH, PT_SPLIT_MIDDLE, PT_SPLIT_EQUAL = 0, 1, 2, 3
+PT_CAMERA_PERSPECTIVE, PT_CAMERA_ORTHOGRAPHIC, PT_CAMERA_ENVIRONMENT = 0, 1, 2
 PT_INTEGRATOR_PATH, PT_INTEGRATOR_AOV, PT_INTEGRATOR_AO, PT_INTEGRATOR_DIRECT, PT_INTEGRATOR_WHITTED = 0, 1, 2, 3, 4
 PT_DIRECT_ALL, PT_DIRECT_ONE = 0, 1
 PT_AOV_DISTANCE, PT_AOV_DEPTH, PT_AOV_N, PT_AOV_NS, PT_AOV_UV, PT_AOV_DPDUS = 0, 1, 2, 3, 4, 5
@@ -53,7 +54,7 @@ class pt_instance(C.Structure):
 
 class pt_camera(C.Structure):
     _fields_ = [("raster_to_camera", C.c_float * 16), ("camera_to_world", C.c_float * 16), ("lens_radius", C.c_float),
-                ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float)]
+                ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float), ("type", C.c_int32), ("pad", C.c_int32)]
 
 
 class pt_film(C.Structure):

@@ -82,13 +82,26 @@ PT_HD int shade_class(const DScene& S, int tri, int bounces) {
   return (t >= 0 && t <= 4) ? t + 1 : ((t >= PT_MAT_UBER && t <= PT_MAT_TRANSLUCENT) ? CL_EXTRA : CL_NONE);
 }
 
-// PerspectiveCamera::generate_ray_differential without the differentials (constant textures: they cannot reach L)
-PT_HD DRay camera_ray(const pt_camera& C, f2 p_film, f2 p_lens, float time) {
-  f3 pc = mat_point(C.raster_to_camera, mk3(p_film.x, p_film.y, 0.0f));
+// {Perspective,Orthographic,Environment}Camera::generate_ray_differential without the differentials (constant textures:
+// they cannot reach L)
+PT_HD DRay camera_ray(const pt_camera& C, const int32_t* full_res, f2 p_film, f2 p_lens, float time) {
   DRay r;
-  r.o = mk3(0.0f, 0.0f, 0.0f);
-  r.d = norm3(pc);
   r.tmax = pt_inf();
+  r.time = lerpf(time, C.shutter_open, C.shutter_close);
+  if (C.type == PT_CAMERA_ENVIRONMENT) {  // environment.rs:36-58
+    const float theta = PT_PI * p_film.y / (float)full_res[1], phi = 2.0f * PT_PI * p_film.x / (float)full_res[0];
+    r.o = mk3(0.0f, 0.0f, 0.0f);
+    r.d = mk3(pt_sinf(theta) * pt_cosf(phi), pt_cosf(theta), pt_sinf(theta) * pt_sinf(phi));
+    return xform_ray(C.camera_to_world, r);
+  }
+  f3 pc = mat_point(C.raster_to_camera, mk3(p_film.x, p_film.y, 0.0f));
+  if (C.type == PT_CAMERA_ORTHOGRAPHIC) {  // orthographic.rs:60-90: parallel rays from the film plane
+    r.o = pc;
+    r.d = mk3(0.0f, 0.0f, 1.0f);
+  } else {
+    r.o = mk3(0.0f, 0.0f, 0.0f);
+    r.d = norm3(pc);
+  }
   if (C.lens_radius > 0.0f) {
     f2 dl = concentric_disk(p_lens);
     f2 pl = mk2(dl.x * C.lens_radius, dl.y * C.lens_radius);
@@ -97,7 +110,6 @@ PT_HD DRay camera_ray(const pt_camera& C, f2 p_film, f2 p_lens, float time) {
     r.o = mk3(pl.x, pl.y, 0.0f);
     r.d = norm3(pf - r.o);
   }
-  r.time = lerpf(time, C.shutter_open, C.shutter_close);
   return xform_ray(C.camera_to_world, r);
 }
 
@@ -443,7 +455,7 @@ PT_HD void raygen_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, int
   f2 pf = mk2((float)px + u.x, (float)py + u.y);
   f2 pl = get2d(S, st);
   float tm = get1d(S, st);
-  DRay r = camera_ray(S.camera, pf, pl, tm);
+  DRay r = camera_ray(S.camera, S.film.full_resolution, pf, pl, tm);
   W.ray_o[i] = mk4(r.o.x, r.o.y, r.o.z, r.tmax);
   W.ray_d[i] = mk4(r.d.x, r.d.y, r.d.z, r.time);
   W.p_film[i] = pf;

@@ -1045,8 +1045,11 @@ struct Builder {
     hs->filename = film_params.one_string("filename", "pbrt.exr");
 
     // Camera (perspective.rs:345-394, projective.rs:23-53)
-    if (camera_name != "perspective") throw ParseError("Camera \"" + camera_name + "\" is not supported on the GPU path (perspective only)");
+    // orthographic.rs:193-253, environment.rs:90-151 read the same parameters (the environment camera ignores lens and window)
+    if (camera_name != "perspective" && camera_name != "orthographic" && camera_name != "environment")
+      throw ParseError("Camera \"" + camera_name + "\" is not supported on the GPU path (perspective, orthographic, environment)");
     pt_camera& Cm = D.camera;
+    Cm.type = camera_name == "perspective" ? PT_CAMERA_PERSPECTIVE : (camera_name == "orthographic" ? PT_CAMERA_ORTHOGRAPHIC : PT_CAMERA_ENVIRONMENT);
     float so = camera_params.one_float("shutteropen", 0.0f), sc = camera_params.one_float("shutterclose", 1.0f);
     if (sc < so) std::swap(so, sc);
     float aspect = (float)xres / (float)yres;
@@ -1063,7 +1066,9 @@ struct Builder {
     float fov = camera_params.one_float("fov", 90.0f);
     float halffov = camera_params.one_float("halffov", -1.0f);
     if (halffov > 0.0f) fov = 2.0f * halffov;
-    Xf camera_to_screen = x_perspective(fov, 1e-2f, 1000.0f);
+    Xf camera_to_screen = Cm.type == PT_CAMERA_PERSPECTIVE ? x_perspective(fov, 1e-2f, 1000.0f)
+                                                           : x_scale(1.0f, 1.0f, 1.0f / (1.0f - 0.0f)) * x_translate(0.0f, 0.0f, -0.0f);  // Transform::orthographic(0, 1), transform.rs:85-87
+    if (Cm.type == PT_CAMERA_ENVIRONMENT) Cm.lens_radius = 0.0f;
     Xf screen_to_raster = x_scale((float)xres, (float)yres, 1.0f) * x_scale(1.0f / (sw[1] - sw[0]), 1.0f / (sw[2] - sw[3]), 1.0f) *
                           x_translate(-sw[0], -sw[3], 0.0f);
     Xf raster_to_camera = xinverse(camera_to_screen) * xinverse(screen_to_raster);

@@ -240,6 +240,13 @@ def test_extra_materials(P):
     check_extra_materials(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
 
 
+def test_cameras(P):
+    """Camera "orthographic" (with and without a lens) and "environment": camera rays bit for bit vs the oracle, per-sample
+    radiance, image and counters (halton / sobol / random samplers)."""
+    from test_hostcheck import check_cameras
+    check_cameras(P, n=20000, res=72, spp=4, threads=0)
+
+
 def test_one_sided_triangles_bit_exact(P, pair):
     """Back-face culling of one-sided meshes (triangle.rs:236-246), with and without ReverseOrientation."""
     from test_hostcheck import one_sided_scene

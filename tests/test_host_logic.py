@@ -172,6 +172,25 @@ def test_front_end_constant_foldable_textures(P):
         P.HostScene.parse_string(txt.replace('"spectrum" "scale"', '"spectrum" "imagemap"'))
 
 
+def test_front_end_cameras(P):
+    """orthographic.rs:193-253 / environment.rs:90-151: same parameters as the perspective camera; Transform::orthographic(0, 1)
+    is the identity, so raster_to_camera maps the raster onto the screen window at z = 0"""
+    base = '%s\nFilm "image" "integer xresolution" [40] "integer yresolution" [20]\nWorldBegin\nWorldEnd\n'
+    d = P.HostScene.parse_string(base % 'Camera "orthographic"').desc.camera
+    assert d.type == P.capi.PT_CAMERA_ORTHOGRAPHIC and d.lens_radius == 0.0 and d.focal_distance == np.float32(1e6)
+    m = np.array(list(d.raster_to_camera), np.float32).reshape(4, 4)
+    corner = lambda x, y: (m @ np.array([x, y, 0, 1], np.float32))[:3]
+    assert np.allclose(corner(0, 0), [-2, 1, 0], atol=1e-6) and np.allclose(corner(40, 20), [2, -1, 0], atol=1e-6)   # frame = 2: window (-2, 2) x (-1, 1), y flipped
+    d = P.HostScene.parse_string(base % 'Camera "orthographic" "float screenwindow" [-3 5 -1 7] "float lensradius" [0.5]').desc.camera
+    m = np.array(list(d.raster_to_camera), np.float32).reshape(4, 4)
+    assert np.allclose(corner(0, 0), [-3, 7, 0], atol=1e-6) and np.allclose(corner(40, 20), [5, -1, 0], atol=1e-6) and d.lens_radius == 0.5
+    d = P.HostScene.parse_string(base % 'Camera "environment" "float lensradius" [0.5] "float shutterclose" [0.25]').desc.camera
+    assert d.type == P.capi.PT_CAMERA_ENVIRONMENT and d.lens_radius == 0.0 and d.shutter_close == 0.25
+    assert P.HostScene.parse_string(base % 'Camera "perspective"').desc.camera.type == P.capi.PT_CAMERA_PERSPECTIVE
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % 'Camera "realistic"')
+
+
 def test_front_end_ao_integrator(P):
     base = 'Camera "perspective"\n%sIntegrator "ambientocclusion" %s\nWorldBegin\nWorldEnd\n'
     d = P.HostScene.parse_string(base % ("", "")).desc.integrator

@@ -494,6 +494,55 @@ def test_hostcheck_extra_materials(HC):
     check_extra_materials(HC)
 
 
+CAMERA_CASES = [('Camera "orthographic" "float screenwindow" [-285 285 -280 280]', None),
+                ('Camera "orthographic" "float screenwindow" [-285 285 -280 280] "float lensradius" [6] "float focaldistance" [1000] "float shutteropen" [0.2]', None),
+                ('Camera "environment"', "LookAt 278 273 250  278 273 500  0 1 0")]
+
+
+def camera_scene(P, cam, lookat=None, res=24, spp=4, sampler="halton"):
+    txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", extra_lights=True, sampler=sampler)
+    assert 'Camera "perspective" "float fov" [39.3077]' in txt
+    txt = txt.replace('Camera "perspective" "float fov" [39.3077]', cam)
+    if lookat:
+        txt = txt.replace("LookAt 278 273 -800  278 273 0  0 1 0", lookat)
+        txt = txt.replace('"integer yresolution" [%d]' % res, '"integer yresolution" [%d]' % (res // 2))   # lat-long: 2 x 1
+    return txt
+
+
+def check_cameras(P, n=1500, res=24, spp=4, threads=2):
+    """Camera "orthographic" (cameras/orthographic.rs:60-90, with and without a lens) and "environment" (environment.rs:36-58,
+    from inside the box): camera rays bit for bit (sin / cos are glibc-exact on the device), per-sample radiance, image, counters"""
+    import oracle_api
+    for (cam, lookat), sampler in zip(CAMERA_CASES, ("halton", "sobol", "random")):
+        hs = P.HostScene.parse_string(camera_scene(P, cam, lookat, res=res, spp=spp, sampler=sampler))
+        want = P.capi.PT_CAMERA_ENVIRONMENT if "environment" in cam else P.capi.PT_CAMERA_ORTHOGRAPHIC
+        assert hs.desc.camera.type == want
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        if sampler != "random":
+            sb = hs.desc.film.sample_bounds
+            rng = np.random.RandomState(14)
+            pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+            sn = rng.randint(0, spp, n).astype(np.int32)
+            (ra, pa), (rb, pb) = sc.camera_rays(pix, sn), orc.camera_rays(pix, sn)
+            assert np.array_equal(ra.view(np.uint32), rb.view(np.uint32)) and np.array_equal(pa, pb), cam
+            if want == P.capi.PT_CAMERA_ORTHOGRAPHIC and "lensradius" not in cam:
+                assert np.ptp(ra[:, 4:7], axis=0).max() == 0 and np.ptp(ra[:, 0]) > 400      # rays = (o, tmax, d, time): parallel, from a plane
+            la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+            ok = (np.abs(la - lb) <= 1e-5 * np.maximum(np.abs(lb), 1e-3)).all(1)
+            assert ok.mean() >= 0.999 and la.max() > 0, (cam, ok.mean())
+        rgb, st = sc.render(collect_counters=1)
+        ref, so = orc.render(threads=threads)
+        assert ref.mean() > 0 and np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-4, cam
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[k] == so[k], (cam, k, st[k], so[k])
+        if want == P.capi.PT_CAMERA_ENVIRONMENT:
+            assert (rgb.reshape(-1, 3).sum(1) > 0).mean() > 0.7       # from inside the box (open towards -z) most directions see a wall
+
+
+def test_hostcheck_cameras(HC):
+    check_cameras(HC)
+
+
 def test_hostcheck_hlbvh_split(HC):
     """splitmethod "hlbvh": the same stage logic on the Morton-treelet tree (visit counters equal the oracle's)."""
     hl = lambda t: t.replace('Accelerator "bvh"', 'Accelerator "bvh" "string splitmethod" ["hlbvh"]')
