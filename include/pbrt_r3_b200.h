@@ -115,7 +115,7 @@ typedef struct pt_light {
 typedef struct pt_envmap {
   float l2w[9];               /* upper 3x3 of light_to_world, row-major */
   float w2l[9];               /* upper 3x3 of world_to_light */
-  int32_t width, height;      /* powers of two; 1 x 1 for a light without "mapname" */
+  int32_t width, height;      /* as read from the file (the MIPMap resamples to powers of two itself); 1 x 1 for a light without "mapname" */
   const float* texels;        /* width * height RGB triples, row 0 = top: read_image(mapname) clamped at 0, times L * scale
                                  (make_mipmap, infinite.rs:47-65) */
 } pt_envmap;

@@ -872,7 +872,7 @@ inline bool tri_sample_from(const pt_scene_desc* d, int tri, const RefPoint& ref
 }
 
 // ---- InfiniteAreaLight (lights/infinite.rs) ------------------------------------------------------------------------
-// MIPMap<RGBSpectrum> of a power-of-two map (core/texture/mipmap.rs: make_pyramid :406-441 with downsample_half :225-275,
+// MIPMap<RGBSpectrum> (core/texture/mipmap.rs: resample_image :316-404 for sides that are not powers of two, make_pyramid :406-441 with downsample_half :225-275,
 // triangle :711-767, lookup :620-637; create_spectrum_mipmap :1013-1026 = trilinear off, s repeats, t clamps) and the
 // Distribution2D built by make_distribution (infinite.rs:67-93; core/sampling/distribution.rs:109-145).
 struct MipLevel { int w = 0, h = 0; std::vector<Float> rgb; };
@@ -915,6 +915,73 @@ struct EnvMap {
     }
     make_pyramid(sw, sh, s);
   }
+  // ---- resampling of maps whose sides are not powers of two (mipmap.rs:291-404) ----
+  static Float lanczos(Float x, Float tau) {  // core/texture/noise.rs:150-162
+    x = std::fabs(x);
+    if (x < 1e-5f) return 1.0f;
+    if (x > 1.0f) return 0.0f;
+    x *= PI;
+    Float s = std::sin(x * tau) / (x * tau);
+    Float l = std::sin(x) / x;
+    return s * l;
+  }
+  struct ResampleWeight { int first_texel; Float weight[4]; };
+  static std::vector<ResampleWeight> resample_weights(size_t old_res, size_t new_res) {  // mipmap.rs:291-314
+    std::vector<ResampleWeight> wt(new_res);
+    const Float filter_width = 2.0f;
+    for (size_t i = 0; i < new_res; i++) {
+      Float center = ((Float)i + 0.5f) * ((Float)old_res / (Float)new_res);
+      Float first_texel = floorf((center - filter_width) + 0.5f);
+      for (int j = 0; j < 4; j++) {
+        Float pos = first_texel + (Float)j + 0.5f;
+        wt[i].weight[j] = lanczos((pos - center) / filter_width, filter_width);
+      }
+      Float inv_sum_wts = 1.0f / (wt[i].weight[0] + wt[i].weight[1] + wt[i].weight[2] + wt[i].weight[3]);
+      for (int j = 0; j < 4; j++) wt[i].weight[j] *= inv_sum_wts;
+      wt[i].first_texel = (int)first_texel;
+    }
+    return wt;
+  }
+  static int math_mod(int a, int b) { int r = a - (a / b) * b; return r < 0 ? r + b : r; }
+  // resample_image (mipmap.rs:316-404) with swrap = Repeat, twrap = Clamp
+  static std::vector<Float> resample_image(const std::vector<Float>& img, int rw, int rh, int* ow, int* oh) {
+    int pw = 1, ph = 1;
+    while (pw < rw) pw *= 2;
+    while (ph < rh) ph *= 2;
+    *ow = pw; *oh = ph;
+    if (pw == rw && ph == rh) return img;
+    std::vector<Float> out((size_t)3 * pw * ph, 0.0f);
+    std::vector<ResampleWeight> sw = resample_weights((size_t)rw, (size_t)pw);
+    for (int t = 0; t < rh; t++)
+      for (int s = 0; s < pw; s++)
+        for (int j = 0; j < 4; j++) {
+          int orig_s = math_mod(sw[(size_t)s].first_texel + j, rw);
+          if (orig_s >= 0 && orig_s < rw) {
+            Float w = sw[(size_t)s].weight[j];
+            size_t src = (size_t)t * rw + orig_s, dst = (size_t)t * pw + s;
+            for (int c = 0; c < 3; c++) out[3 * dst + c] += img[3 * src + c] * w;
+          }
+        }
+    std::vector<ResampleWeight> tw = resample_weights((size_t)rh, (size_t)ph);
+    for (int s = 0; s < pw; s++) {
+      std::vector<Float> buffer((size_t)3 * rh);
+      for (int t = 0; t < rh; t++)
+        for (int c = 0; c < 3; c++) buffer[3 * (size_t)t + c] = out[3 * ((size_t)t * pw + s) + c];
+      for (int t = 0; t < ph; t++) {
+        Float l[3] = {0.0f, 0.0f, 0.0f};
+        for (int j = 0; j < 4; j++) {
+          int orig_t = std::min(std::max(tw[(size_t)t].first_texel + j, 0), rh - 1);
+          if (orig_t >= 0 && orig_t < rh) {
+            Float w = tw[(size_t)t].weight[j];
+            for (int c = 0; c < 3; c++) l[c] += buffer[3 * (size_t)orig_t + c] * w;
+          }
+        }
+        for (int c = 0; c < 3; c++) out[3 * ((size_t)t * pw + s) + c] = l[c];
+      }
+    }
+    for (Float& v : out) v = std::max(v, 0.0f);
+    return out;
+  }
   void triangle(size_t level, Vec2 st, Float out[3]) const {
     level = std::min(level, pyramid.size() - 1);
     const MipLevel& I = pyramid[level];
@@ -947,8 +1014,10 @@ struct EnvMap {
   static Float rgb_y(const Float* c) { return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]; }
   void init(const pt_envmap& M) {
     for (int i = 0; i < 9; i++) { l2w[i] = M.l2w[i]; w2l[i] = M.w2l[i]; }
-    make_pyramid(M.width, M.height, std::vector<Float>(M.texels, M.texels + (size_t)M.width * M.height * 3));
-    size_t width = (size_t)M.width * 2, height = (size_t)M.height * 2;   // make_distribution
+    int rw = 0, rh = 0;
+    std::vector<Float> data = resample_image(std::vector<Float>(M.texels, M.texels + (size_t)M.width * M.height * 3), M.width, M.height, &rw, &rh);
+    make_pyramid(rw, rh, data);
+    size_t width = (size_t)rw * 2, height = (size_t)rh * 2;   // make_distribution: lmap.width() / height() (infinite.rs:70-72)
     std::vector<Float> img(width * height);
     Float fwidth = 0.5f / (Float)std::min(width, height);
     for (size_t v = 0; v < height; v++) {

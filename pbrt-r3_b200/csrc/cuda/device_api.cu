@@ -461,7 +461,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
     std::vector<EnvDev> envs(D->n_envmaps);
     for (uint32_t k = 0; k < D->n_envmaps; k++) {
       const pt_envmap& M = D->envmaps[k];
-      if (M.width < 1 || M.height < 1 || (M.width & (M.width - 1)) || (M.height & (M.height - 1)) || !M.texels) { pt_set_error("pt_envmap: width / height must be powers of two"); return 1; }
+      if (M.width < 1 || M.height < 1 || M.width > (1 << 14) || M.height > (1 << 14) || !M.texels) { pt_set_error("pt_envmap: width / height must be in 1 .. 16384"); return 1; }
       if (NC != 3) { pt_set_error("infinite lights are only supported with RGB spectra"); return 1; }
       pth::EnvMapHost& E = env_host[k];
       E.build_pyramid(M.width, M.height, M.texels);
@@ -470,9 +470,10 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
       memset(&V, 0, sizeof(V));
       memcpy(V.l2w, M.l2w, sizeof(V.l2w));
       memcpy(V.w2l, M.w2l, sizeof(V.w2l));
-      V.w = M.width; V.h = M.height; V.nu = E.nu; V.nv = E.nv; V.m_int = E.m_int;
-      std::vector<f4> tex((size_t)M.width * M.height);
-      for (size_t i = 0; i < tex.size(); i++) tex[i] = mk4(M.texels[3 * i], M.texels[3 * i + 1], M.texels[3 * i + 2], 0.0f);
+      const pth::EnvMapHost::Level& L0 = E.pyramid[0];  // the map as the MIPMap holds it (resampled to powers of two)
+      V.w = L0.w; V.h = L0.h; V.nu = E.nu; V.nv = E.nv; V.m_int = E.m_int;
+      std::vector<f4> tex((size_t)L0.w * L0.h);
+      for (size_t i = 0; i < tex.size(); i++) tex[i] = mk4(L0.rgb[3 * i], L0.rgb[3 * i + 1], L0.rgb[3 * i + 2], 0.0f);
       CK(s->bufs.upload(tex.data(), tex.size(), &V.texels));
       CK(s->bufs.upload(E.func.data(), E.func.size(), &V.func));
       CK(s->bufs.upload(E.cdf.data(), E.cdf.size(), &V.cdf));

@@ -2,7 +2,8 @@
 // Distribution2D the light samples from.  Replaces reference src/lights/infinite.rs:67-93 (make_distribution), 103-108
 // (power), src/core/texture/mipmap.rs:225-275,406-441 (box-filter pyramid), 620-637 (lookup), 711-767 (triangle) with
 // the wrap modes of create_spectrum_mipmap (:1013-1026: s repeats, t clamps), src/core/sampling/distribution.rs:34-58,
-// 110-127.  Power-of-two maps only (the Lanczos resampling of other sizes, mipmap.rs:291-404, is not built).
+// 110-127.  Maps whose sides are not powers of two are first resampled up to the next powers of two with a four-tap Lanczos
+// filter, first along s (repeat) then along t (clamp) (mipmap.rs:291-404, noise.rs:150-162).
 // The device reads level 0 (every lookup on the path has width 0, which selects the bilinear "triangle" filter of level 0)
 // and the distribution tables; the pyramid only exists here, for make_distribution and power().
 #pragma once
@@ -26,9 +27,64 @@ struct EnvMapHost {
 
   static float lum(const float* c) { return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]; }  // RGBSpectrum::y (rgb.rs)
 
+  // one output sample of the resampling filter: four taps starting at texel `first`
+  struct Taps { int first; float w[4]; };
+  static float lanczos2(float x) {  // lanczos(x, tau = 2) (noise.rs:150-162)
+    const float PI = 3.14159265358979323846f, tau = 2.0f;
+    x = fabsf(x);
+    if (x < 1e-5f) return 1.0f;
+    if (x > 1.0f) return 0.0f;
+    x *= PI;
+    const float s = sinf(x * tau) / (x * tau);
+    return s * (sinf(x) / x);
+  }
+  static std::vector<Taps> taps_for(int old_res, int new_res) {  // resample_weights (mipmap.rs:291-314)
+    std::vector<Taps> out((size_t)new_res);
+    for (int i = 0; i < new_res; i++) {
+      const float center = ((float)i + 0.5f) * ((float)old_res / (float)new_res);
+      const float first = floorf((center - 2.0f) + 0.5f);
+      Taps& T = out[(size_t)i];
+      T.first = (int)first;
+      for (int j = 0; j < 4; j++) T.w[j] = lanczos2(((first + (float)j + 0.5f) - center) / 2.0f);
+      const float inv = 1.0f / (T.w[0] + T.w[1] + T.w[2] + T.w[3]);
+      for (int j = 0; j < 4; j++) T.w[j] *= inv;
+    }
+    return out;
+  }
+  static int round_up_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+  // resample_image (mipmap.rs:316-404): rows are stretched first (s wraps around), then columns (t clamps); negative lobes of
+  // the filter are cut off at zero at the end
+  static Level resample_to_pow2(int w, int h, const float* texels) {
+    Level R{round_up_pow2(w), round_up_pow2(h), {}};
+    if (R.w == w && R.h == h) { R.rgb.assign(texels, texels + (size_t)w * h * 3); return R; }
+    R.rgb.assign((size_t)R.w * R.h * 3, 0.0f);
+    const std::vector<Taps> ts = taps_for(w, R.w), tt = taps_for(h, R.h);
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < R.w; x++)
+        for (int j = 0; j < 4; j++) {
+          const int sx = ((ts[(size_t)x].first + j) % w + w) % w;
+          for (int c = 0; c < 3; c++) R.rgb[3 * ((size_t)y * R.w + x) + c] += texels[3 * ((size_t)y * w + sx) + c] * ts[(size_t)x].w[j];
+        }
+    std::vector<float> column((size_t)h * 3);
+    for (int x = 0; x < R.w; x++) {
+      for (int y = 0; y < h; y++)
+        for (int c = 0; c < 3; c++) column[3 * (size_t)y + c] = R.rgb[3 * ((size_t)y * R.w + x) + c];
+      for (int y = 0; y < R.h; y++) {
+        float acc[3] = {0.0f, 0.0f, 0.0f};
+        for (int j = 0; j < 4; j++) {
+          const int sy = std::min(std::max(tt[(size_t)y].first + j, 0), h - 1);
+          for (int c = 0; c < 3; c++) acc[c] += column[3 * (size_t)sy + c] * tt[(size_t)y].w[j];
+        }
+        for (int c = 0; c < 3; c++) R.rgb[3 * ((size_t)y * R.w + x) + c] = acc[c];
+      }
+    }
+    for (float& v : R.rgb) v = std::max(v, 0.0f);
+    return R;
+  }
+
   void build_pyramid(int w, int h, const float* texels) {  // make_pyramid: halve x, then y, until 1 x 1
     pyramid.clear();
-    Level L{w, h, std::vector<float>(texels, texels + (size_t)w * h * 3)};
+    Level L = resample_to_pow2(w, h, texels);
     for (;;) {
       pyramid.push_back(L);
       if (L.w * L.h == 1) break;

@@ -739,8 +739,7 @@ struct Builder {
         std::string path = (fn[0] == '/') ? fn : (cur_dir.empty() ? fn : cur_dir + "/" + fn);
         std::string err = load_pfm(path, &tex, &em.width, &em.height);
         if (!err.empty()) throw ParseError("LightSource \"infinite\" mapname \"" + path + "\": " + err);
-        if ((em.width & (em.width - 1)) || (em.height & (em.height - 1)))
-          throw ParseError("LightSource \"infinite\": only power-of-two environment maps are supported on the GPU path (MIPMap resampling is not built)");
+        if (em.width > (1 << 14) || em.height > (1 << 14)) throw ParseError("LightSource \"infinite\": environment maps above 16384 pixels a side are not supported");
         for (size_t i = 0; i < tex.size(); i++) tex[i] = std::max(tex[i], 0.0f) * L[i % 3];
       }
       for (int r = 0; r < 3; r++)

@@ -501,7 +501,9 @@ def test_front_end_infinite_light(P, tmp_path):
     tex = np.array([e.texels[k] for k in range(4 * 8 * 3)], np.float32).reshape(4, 8, 3)
     assert np.array_equal(tex, np.maximum(img, 0) * np.array([2, 1, 0.5], np.float32))                               # clamped at 0, times L (:52-56); row 0 = top
     write_pfm(str(tmp_path / "npot.pfm"), np.ones((3, 8, 3), np.float32))
-    for bad in ('"string mapname" ["%s"]' % (tmp_path / "npot.pfm"), '"string mapname" ["%s"]' % (tmp_path / "missing.pfm"), '"string mapname" ["x.exr"]'):
+    e = P.HostScene.parse_string(base % ('"string mapname" ["%s"]' % (tmp_path / "npot.pfm"))).desc.envmaps[0]
+    assert (e.width, e.height) == (8, 3)       # handed over as read: the MIPMap resamples to 8 x 4 (mipmap.rs:316-404)
+    for bad in ('"string mapname" ["%s"]' % (tmp_path / "missing.pfm"), '"string mapname" ["x.exr"]'):
         with pytest.raises(P.PbrtError):
             P.HostScene.parse_string(base % bad)
     with pytest.raises(P.PbrtError):

@@ -383,18 +383,21 @@ def write_pfm(path, img):
         f.write(np.ascontiguousarray(img[::-1], "<f4").tobytes())
 
 
-def env_scene(P, tmpdir, mapped, integrator='"path"', res=24, spp=4, sampler="halton", strategy=None):
+def env_scene(P, tmpdir, mapped, integrator='"path"', res=24, spp=4, sampler="halton", strategy=None, map_shape=(8, 16), constant=None):
     """Cornell box with mixed materials (open towards the camera) inside an environment light: constant, or a 16 x 8
     lat-long map with one bright texel region, rotated; the box's own area light stays."""
     txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", sampler=sampler, maxdepth=5)
     light = 'AttributeBegin\nRotate -70 1 0 0\nRotate 25 0 0 1\nLightSource "infinite" "rgb L" [0.5 0.6 0.9] "rgb scale" [1.5 1 1]%s\nAttributeEnd\n'
     if mapped:
         rng = np.random.RandomState(3)
-        img = rng.uniform(0.05, 0.6, (8, 16, 3)).astype(np.float32)
+        img = rng.uniform(0.05, 0.6, tuple(map_shape) + (3,)).astype(np.float32)
         img[1:3, 4:7] = [9.0, 7.0, 4.0]       # a sun
-        img[6, 2] = -1.0                      # negative texels are clamped (infinite.rs:54-55)
-        write_pfm(os.path.join(str(tmpdir), "env.pfm"), img)
-        light = light % (' "string mapname" ["%s"]' % os.path.join(str(tmpdir), "env.pfm"))
+        img[map_shape[0] - 2, 2] = -1.0       # negative texels are clamped (infinite.rs:54-55)
+        if constant is not None:
+            img[:] = constant
+        name = "env_%dx%d%s.pfm" % (map_shape[1], map_shape[0], "" if constant is None else "_c")
+        write_pfm(os.path.join(str(tmpdir), name), img)
+        light = light % (' "string mapname" ["%s"]' % os.path.join(str(tmpdir), name))
     else:
         light = light % ""
     txt = txt.replace("WorldEnd", light + "WorldEnd")
@@ -405,7 +408,8 @@ def env_scene(P, tmpdir, mapped, integrator='"path"', res=24, spp=4, sampler="ha
 
 ENV_CASES = [dict(mapped=False), dict(mapped=True), dict(mapped=True, sampler="sobol", strategy="power"),
              dict(mapped=True, integrator='"directlighting" "string strategy" ["one"]'), dict(mapped=True, integrator='"whitted"'),
-             dict(mapped=False, integrator='"directlighting"')]
+             dict(mapped=False, integrator='"directlighting"'),
+             dict(mapped=True, map_shape=(7, 12)), dict(mapped=True, map_shape=(9, 16), sampler="sobol")]   # resampled to 16 x 8 / 16 x 16 (mipmap.rs:316-404)
 
 
 def check_env(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=1e-5, frac=1.0):
@@ -417,7 +421,7 @@ def check_env(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=
         kw = dict(dict(res=res, spp=spp), **kw)
         hs = P.HostScene.parse_string(env_scene(P, tmpdir, **kw))
         assert hs.desc.n_envmaps == 1 and hs.desc.lights[hs.desc.n_lights - 1].type == P.capi.PT_LIGHT_INFINITE
-        assert (hs.desc.envmaps[0].width, hs.desc.envmaps[0].height) == ((16, 8) if kw["mapped"] else (1, 1))
+        assert (hs.desc.envmaps[0].width, hs.desc.envmaps[0].height) == (tuple(kw.get("map_shape", (8, 16)))[::-1] if kw["mapped"] else (1, 1))
         sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
         sb = hs.desc.film.sample_bounds
         rng = np.random.RandomState(10)
@@ -438,6 +442,14 @@ def check_env(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=
 
 def test_hostcheck_infinite_light(HC, tmp_path):
     check_env(HC, tmp_path)
+
+
+def test_hostcheck_resampled_constant_map(HC, tmp_path):
+    """A constant 5 x 3 map resampled to 8 x 4 stays constant up to rounding (the Lanczos weights are normalised): the render
+    equals that of a constant 8 x 4 map."""
+    a = HC.Scene(HC.HostScene.parse_string(env_scene(HC, tmp_path, True, map_shape=(3, 5), constant=1.0))).render()[0]
+    b = HC.Scene(HC.HostScene.parse_string(env_scene(HC, tmp_path, True, map_shape=(4, 8), constant=1.0))).render()[0]
+    assert b.mean() > 0 and np.sqrt(((a - b) ** 2).mean()) / b.mean() < 1e-3
 
 
 def extra_materials_scene(P, integrator='"path"', res=24, spp=4, sampler="halton", maxdepth=6):
