@@ -47,7 +47,9 @@ enum pt_light_type {          /* reference src/lights/create_light.rs:13-54 */
   PT_LIGHT_POINT = 1,         /* lights/point.rs    */
   PT_LIGHT_DISTANT = 2,       /* lights/distant.rs  */
   PT_LIGHT_SPOT = 3,          /* lights/spot.rs     */
-  PT_LIGHT_INFINITE = 4       /* lights/infinite.rs: environment light (constant L, or a lat-long map) */
+  PT_LIGHT_INFINITE = 4,      /* lights/infinite.rs: environment light (constant L, or a lat-long map) */
+  PT_LIGHT_PROJECTION = 5,    /* lights/projection.rs: a point light seen through a slide (perspective projection of an image) */
+  PT_LIGHT_GONIOMETRIC = 6    /* lights/goniometric.rs: a point light scaled by a lat-long image of directions */
 };
 
 enum pt_sampler_type {        /* reference src/samplers/create_sampler.rs:12-33 */
@@ -102,10 +104,10 @@ typedef struct pt_material {
 typedef struct pt_light {
   int32_t type;               /* pt_light_type */
   int32_t spectrum;           /* area: Lemit = L*scale | point: I*scale | distant: L*scale (spectrum index) */
-  int32_t tri;                /* area: triangle index; spot: index into pt_scene_desc.spots; infinite: index into
-                                 pt_scene_desc.envmaps; else -1 */
+  int32_t tri;                /* area: triangle index; spot: index into pt_scene_desc.spots; infinite, projection, goniometric:
+                                 index into pt_scene_desc.envmaps; else -1 */
   int32_t two_sided;          /* area: DiffuseAreaLight.two_sided (lights/diffuse.rs:178) */
-  float v[3];                 /* point, spot: p_light (world) | distant: w_light (world, normalised) */
+  float v[3];                 /* point, spot, projection, goniometric: p_light (world) | distant: w_light (world, normalised) */
   int32_t n_samples;          /* Light::get_sample_count: area "nsamples" (default 1, n / 4 under --quick, diffuse.rs:177-185), else 1;
                                  read by directlighting's "all" strategy only */
 } pt_light;
@@ -117,7 +119,14 @@ typedef struct pt_envmap {
   float w2l[9];               /* upper 3x3 of world_to_light */
   int32_t width, height;      /* as read from the file (the MIPMap resamples to powers of two itself); 1 x 1 for a light without "mapname" */
   const float* texels;        /* width * height RGB triples, row 0 = top: read_image(mapname) clamped at 0, times L * scale
-                                 (make_mipmap, infinite.rs:47-65) */
+                                 (make_mipmap, infinite.rs:47-65); projection / goniometric: clamped at 0 only, the
+                                 intensity I * scale (L * scale) is pt_light.spectrum */
+  float xf[16];               /* projection: light_projection = Transform::perspective(fov, 1e-3, 1e30) (projection.rs:44-46) |
+                                 goniometric: the full world_to_light (its scale() transforms the direction as a POINT,
+                                 goniometric.rs:33-34), row-major */
+  float screen_bounds[4];     /* projection: min.x, min.y, max.x, max.y (projection.rs:33-41) */
+  float hitcher;              /* projection: 1e-3 */
+  float cos_total_width;      /* projection: z of the normalised corner direction (projection.rs:47-50), for power() */
 } pt_envmap;
 
 /* SpotLight extras (lights/spot.rs:5-56): falloff(w) looks at the z component of normalize(world_to_light * w). */

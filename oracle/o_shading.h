@@ -878,6 +878,7 @@ inline bool tri_sample_from(const pt_scene_desc* d, int tri, const RefPoint& ref
 struct MipLevel { int w = 0, h = 0; std::vector<Float> rgb; };
 struct EnvMap {
   Float l2w[9], w2l[9];
+  Float xf[16], screen[4], hitcher = 0, cos_total_width = 0;  // ProjectionLight / GonioPhotometricLight extras (pt_envmap)
   std::vector<MipLevel> pyramid;
   std::vector<Distribution1D> conditional_v;
   Distribution1D marginal;
@@ -1014,6 +1015,9 @@ struct EnvMap {
   static Float rgb_y(const Float* c) { return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]; }
   void init(const pt_envmap& M) {
     for (int i = 0; i < 9; i++) { l2w[i] = M.l2w[i]; w2l[i] = M.w2l[i]; }
+    for (int i = 0; i < 16; i++) xf[i] = M.xf[i];
+    for (int i = 0; i < 4; i++) screen[i] = M.screen_bounds[i];
+    hitcher = M.hitcher; cos_total_width = M.cos_total_width;
     int rw = 0, rh = 0;
     std::vector<Float> data = resample_image(std::vector<Float>(M.texels, M.texels + (size_t)M.width * M.height * 3), M.width, M.height, &rw, &rh);
     make_pyramid(rw, rh, data);
@@ -1125,6 +1129,39 @@ inline bool light_sample_li(const pt_scene_desc* d, Float world_radius, int li, 
     out->wi = normalize(v - it.p);
     out->pdf = 1.0f;
     pl.p = v;
+  } else if (L.type == PT_LIGHT_PROJECTION) {  // projection.rs:81-99, projection() :64-79
+    const EnvMap& E = envs[L.tri];
+    Vec3 wi = normalize(v - it.p);
+    Vec3 w = -wi;
+    Float rgb[3] = {0.0f, 0.0f, 0.0f};
+    Vec3 wl(E.w2l[0] * w.x + E.w2l[1] * w.y + E.w2l[2] * w.z, E.w2l[3] * w.x + E.w2l[4] * w.y + E.w2l[5] * w.z, E.w2l[6] * w.x + E.w2l[7] * w.y + E.w2l[8] * w.z);
+    if (!(wl.z < E.hitcher)) {
+      Vec3 p = mat_of(E.xf).point(wl);
+      if (p.x >= E.screen[0] && p.x <= E.screen[2] && p.y >= E.screen[1] && p.y <= E.screen[3]) {
+        Vec2 st(p.x - E.screen[0], p.y - E.screen[1]);  // Bounds2::offset (bounds2.rs:44-53)
+        if (E.screen[2] > E.screen[0]) st.x = st.x / (E.screen[2] - E.screen[0]);
+        if (E.screen[3] > E.screen[1]) st.y = st.y / (E.screen[3] - E.screen[1]);
+        E.lookup(st, 0.0f, rgb);
+      }
+    }
+    Spec<NC> m;
+    for (int k = 0; k < 3 && k < NC; k++) m.c[k] = rgb[k];
+    out->li = (Spec<NC>::load(d->spectra + (size_t)L.spectrum * NC) * m) / distance_squared(v, it.p);
+    out->wi = wi;
+    out->pdf = 1.0f;
+    pl.p = v;
+  } else if (L.type == PT_LIGHT_GONIOMETRIC) {  // goniometric.rs:47-62, scale() :33-41
+    const EnvMap& E = envs[L.tri];
+    Vec3 wi = normalize(v - it.p);
+    Vec3 wp = mat_of(E.xf).point(-wi);  // world_to_light.transform_point(w): a point transform, as the reference does
+    Float rgb[3];
+    E.lookup(Vec2(spherical_phi(wp) * INV_2_PI, spherical_theta(wp) * INV_PI), 0.0f, rgb);
+    Spec<NC> m;
+    for (int k = 0; k < 3 && k < NC; k++) m.c[k] = rgb[k];
+    out->li = (Spec<NC>::load(d->spectra + (size_t)L.spectrum * NC) * m) / distance_squared(v, it.p);
+    out->wi = wi;
+    out->pdf = 1.0f;
+    pl.p = v;
   } else if (L.type == PT_LIGHT_SPOT) {  // spot.rs:62-80, falloff :44-57
     const pt_spot& S = d->spots[L.tri];
     Vec3 wi = normalize(v - it.p);
@@ -1184,6 +1221,14 @@ inline Spec<NC> light_power(const pt_scene_desc* d, Float world_radius, int li, 
     Spec<NC> r;
     for (int k = 0; k < 3 && k < NC; k++) r.c[k] = c[k];
     return r * (PI * world_radius * world_radius);
+  }
+  if (L.type == PT_LIGHT_PROJECTION || L.type == PT_LIGHT_GONIOMETRIC) {
+    Float c[3];
+    envs[L.tri].lookup(Vec2(0.5f, 0.5f), 0.5f, c);
+    Spec<NC> r;
+    for (int k = 0; k < 3 && k < NC; k++) r.c[k] = c[k];
+    if (L.type == PT_LIGHT_PROJECTION) return r * s * (2.0f * PI * (1.0f - envs[L.tri].cos_total_width));  // projection.rs:113-117
+    return (s * (4.0f * PI)) * r;                                                                          // goniometric.rs:64-68
   }
   if (L.type == PT_LIGHT_AREA) return s * ((L.two_sided ? 2.0f : 1.0f) * tri_area(d, L.tri) * PI);
   if (L.type == PT_LIGHT_POINT) return s * (4.0f * PI);

@@ -13,7 +13,7 @@ DATA_DIR = os.path.join(HERE, "data")
 PT_ABI_VERSION = 3
 PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MIRROR = -1, 0, 1, 2, 3, 4
 PT_MAT_UBER, PT_MAT_SUBSTRATE, PT_MAT_TRANSLUCENT = 5, 6, 7
-PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT, PT_LIGHT_INFINITE = 0, 1, 2, 3, 4
+PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT, PT_LIGHT_INFINITE, PT_LIGHT_PROJECTION, PT_LIGHT_GONIOMETRIC = 0, 1, 2, 3, 4, 5, 6
 PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM = 0, 1, 2
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
 PT_SPLIT_SAH, PT_SPLIT_HLBVH, PT_SPLIT_MIDDLE, PT_SPLIT_EQUAL = 0, 1, 2, 3
@@ -41,7 +41,8 @@ class pt_light(C.Structure):
 
 
 class pt_envmap(C.Structure):
-    _fields_ = [("l2w", C.c_float * 9), ("w2l", C.c_float * 9), ("width", C.c_int32), ("height", C.c_int32), ("texels", C.POINTER(C.c_float))]
+    _fields_ = [("l2w", C.c_float * 9), ("w2l", C.c_float * 9), ("width", C.c_int32), ("height", C.c_int32), ("texels", C.POINTER(C.c_float)),
+                ("xf", C.c_float * 16), ("screen_bounds", C.c_float * 4), ("hitcher", C.c_float), ("cos_total_width", C.c_float)]
 
 
 class pt_spot(C.Structure):

@@ -455,7 +455,7 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   CK(s->bufs.upload(D->lights, (size_t)D->n_lights + D->n_emitters_only, &H.lights));
   CK(s->bufs.upload(D->spots, D->n_spots, &H.spots));
   // ---- infinite lights (lights/infinite.rs): level 0 of the map + Distribution2D tables; the pyramid stays on the host
-  H.envs = nullptr; H.inf_lights = nullptr; H.n_inf = 0;
+  H.envs = nullptr; H.inf_lights = nullptr; H.n_inf = 0; H.has_map_lights = 0;
   std::vector<pth::EnvMapHost> env_host(D->n_envmaps);
   {
     std::vector<EnvDev> envs(D->n_envmaps);
@@ -472,6 +472,9 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
       memcpy(V.w2l, M.w2l, sizeof(V.w2l));
       const pth::EnvMapHost::Level& L0 = E.pyramid[0];  // the map as the MIPMap holds it (resampled to powers of two)
       V.w = L0.w; V.h = L0.h; V.nu = E.nu; V.nv = E.nv; V.m_int = E.m_int;
+      V.hitcher = M.hitcher;
+      memcpy(V.xf, M.xf, sizeof(V.xf));
+      memcpy(V.screen, M.screen_bounds, sizeof(V.screen));
       std::vector<f4> tex((size_t)L0.w * L0.h);
       for (size_t i = 0; i < tex.size(); i++) tex[i] = mk4(L0.rgb[3 * i], L0.rgb[3 * i + 1], L0.rgb[3 * i + 2], 0.0f);
       CK(s->bufs.upload(tex.data(), tex.size(), &V.texels));
@@ -481,11 +484,13 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
       CK(s->bufs.upload(E.mcdf.data(), E.mcdf.size(), &V.mcdf));
     }
     std::vector<int32_t> inf;
-    for (uint32_t i = 0; i < D->n_lights; i++)
-      if (D->lights[i].type == PT_LIGHT_INFINITE) {
-        if (D->lights[i].tri < 0 || (uint32_t)D->lights[i].tri >= D->n_envmaps) { pt_set_error("infinite light: envmap index out of range"); return 1; }
-        inf.push_back((int32_t)i);
-      }
+    for (uint32_t i = 0; i < D->n_lights; i++) {
+      const int lt = D->lights[i].type;
+      if (lt != PT_LIGHT_INFINITE && lt != PT_LIGHT_PROJECTION && lt != PT_LIGHT_GONIOMETRIC) continue;
+      if (D->lights[i].tri < 0 || (uint32_t)D->lights[i].tri >= D->n_envmaps) { pt_set_error("infinite / projection / goniometric light: envmap index out of range"); return 1; }
+      if (lt == PT_LIGHT_INFINITE) inf.push_back((int32_t)i);
+      else H.has_map_lights = 1;
+    }
     if (!envs.empty()) CK(s->bufs.upload(envs.data(), envs.size(), &H.envs));
     if (!inf.empty()) CK(s->bufs.upload(inf.data(), inf.size(), &H.inf_lights));
     H.n_inf = (uint32_t)inf.size();
@@ -642,6 +647,17 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
             f3 a = mk3(p[3] - p[0], p[4] - p[1], p[5] - p[2]), b = mk3(p[6] - p[0], p[7] - p[1], p[8] - p[2]);
             float area = 0.5f * len3(cross3(a, b));
             k = (L.two_sided ? 2.0f : 1.0f) * area * PT_PI;
+          } else if (L.type == PT_LIGHT_PROJECTION) {  // projection.rs:113-117: map((0.5, 0.5), 0.5) * I * 2 pi (1 - cos_total_width)
+            env_host[(size_t)L.tri].lookup(0.5f, 0.5f, 0.5f, env_rgb);
+            for (int c = 0; c < 3; c++) env_rgb[c] = env_rgb[c] * sp[c];
+            sp = env_rgb;
+            k = 2.0f * PT_PI * (1.0f - D->envmaps[L.tri].cos_total_width);
+          } else if (L.type == PT_LIGHT_GONIOMETRIC) {  // goniometric.rs:64-68: 4 pi * L * map((0.5, 0.5), 0.5)
+            float c3[3];
+            env_host[(size_t)L.tri].lookup(0.5f, 0.5f, 0.5f, c3);
+            for (int c = 0; c < 3; c++) env_rgb[c] = ((4.0f * PT_PI) * sp[c]) * c3[c];
+            sp = env_rgb;
+            k = 1.0f;
           } else if (L.type == PT_LIGHT_POINT) k = 4.0f * PT_PI;
           else if (L.type == PT_LIGHT_SPOT) k = 2.0f * PT_PI * (1.0f - 0.5f * (D->spots[L.tri].cos_falloff_start - D->spots[L.tri].cos_total_width));  // spot.rs:82-85
           else k = PT_PI * H.world_radius * H.world_radius;
@@ -769,7 +785,7 @@ int shade_classes(pt_scene* s, int NC, int grid, unsigned long long* vc) {
 template <int NC>
 void launch_ri(pt_scene* s, int grid, const WaveState& W, const Queues& Q, uint32_t n_ext, uint32_t n_wait, const uint32_t* prev, unsigned long long* vc) {
   if constexpr (NC == 3) {
-    const bool wide = (s->class_mask & (1u << CL_EXTRA)) != 0, env = s->h.n_inf != 0;
+    const bool wide = (s->class_mask & (1u << CL_EXTRA)) != 0, env = s->h.n_inf != 0 || s->h.has_map_lights;
 #define PT_RI(ML, ENV, WH) PT_LAUNCH(grid, PT_SHADE_BLOCK, s->stream, k_ri<NC, ML, ENV, WH>)(s->h, W, Q, Q.wait, n_ext, n_wait, prev, vc)
 #define PT_RI2(ML, ENV) do { if (wh) PT_RI(ML, ENV, true); else PT_RI(ML, ENV, false); } while (0)
     const bool wh = s->h.integrator.type == PT_INTEGRATOR_WHITTED;

@@ -87,7 +87,10 @@ struct EnvDev {           // one per LightSource "infinite" (lights/infinite.rs)
   const float* row_int;   // [nv]          conditional_v[v].func_int = marginal.func
   const float* mcdf;      // [nv + 1]      marginal.cdf
   float m_int;            // marginal.func_int
-  int32_t pad[3];
+  float hitcher;          // projection light: near plane
+  int32_t pad[2];
+  float xf[16];           // projection light: light_projection | goniometric light: world_to_light (4x4, row-major)
+  float screen[4];        // projection light: screen bounds min.x, min.y, max.x, max.y
 };
 
 struct DScene {
@@ -118,6 +121,7 @@ struct DScene {
   const uint32_t* light_sample_prefix;  // [n_lights + 1] prefix sums of pt_light.n_samples (directlighting "all": round -> light, sample)
   const pt_spot* spots;      // SpotLight extras, indexed by pt_light.tri
   const EnvDev* envs;        // InfiniteAreaLight extras, indexed by pt_light.tri
+  int32_t has_map_lights;    // projection / goniometric lights: their code lives in the ENV variants of the kernels
   const int32_t* inf_lights; // Scene.infinite_lights: indices into lights
   uint32_t n_inf;
   const float* spectra;

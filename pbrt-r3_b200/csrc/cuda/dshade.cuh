@@ -252,6 +252,32 @@ PT_HD1 bool light_sample(const DScene& S, int li, const RefPt& it, f2 u, LightSa
     out->wi = norm3(v - it.p);
     out->pdf = 1.0f;
     lp = v;
+  } else if (ENV && (L.type == PT_LIGHT_PROJECTION || L.type == PT_LIGHT_GONIOMETRIC)) {
+    // projection.rs:64-110, goniometric.rs:33-62: a point light times an image looked up in the direction -wi
+    f3 v = mk3(L.v[0], L.v[1], L.v[2]);
+    const EnvDev& E = S.envs[L.tri];
+    f3 wi = norm3(v - it.p);
+    f3 w = -wi;
+    f3 rgb = mk3(0.0f, 0.0f, 0.0f);
+    if (L.type == PT_LIGHT_PROJECTION) {
+      f3 wl = mat3_vec(E.w2l, w);
+      if (!(wl.z < E.hitcher)) {
+        f3 p = mat_point(E.xf, wl);
+        if (p.x >= E.screen[0] && p.x <= E.screen[2] && p.y >= E.screen[1] && p.y <= E.screen[3]) {
+          float sx = p.x - E.screen[0], sy = p.y - E.screen[1];  // Bounds2f::offset (bounds2.rs:44-53)
+          if (E.screen[2] > E.screen[0]) sx = sx / (E.screen[2] - E.screen[0]);
+          if (E.screen[3] > E.screen[1]) sy = sy / (E.screen[3] - E.screen[1]);
+          rgb = env_lookup0(E, sx, sy);
+        }
+      }
+    } else {
+      f3 wp = mat_point(E.xf, w);  // the direction as a POINT: the light's translation is applied (goniometric.rs:34)
+      rgb = env_lookup0(E, spherical_phi(wp) * (PT_INV_PI * 0.5f), spherical_theta(wp) * PT_INV_PI);
+    }
+    out->li = (sp_load<NC>(S.spectra + (size_t)L.spectrum * NC) * sp_from_rgb3<NC>(rgb)) / dist2(v, it.p);
+    out->wi = wi;
+    out->pdf = 1.0f;
+    lp = v;
   } else if (L.type == PT_LIGHT_SPOT) {  // lights/spot.rs:44-57 (falloff), 62-80 (sample_li)
     f3 v = mk3(L.v[0], L.v[1], L.v[2]);
     const pt_spot& P = S.spots[L.tri];

@@ -61,7 +61,7 @@ static void launch_shade_nc(int cls, int grid, cudaStream_t stream, const DScene
 void launch_shade(int n_channels, int cls, int grid, cudaStream_t stream, const ptd::DScene& S, const ptd::WaveState& W, const ptd::Queues& Q,
                   unsigned long long* vertex_counter) {
   if (n_channels == 3) {
-    if (S.n_inf != 0u) ptd::launch_shade_nc<3, true>(cls, grid, stream, S, W, Q, vertex_counter);
+    if (S.n_inf != 0u || S.has_map_lights) ptd::launch_shade_nc<3, true>(cls, grid, stream, S, W, Q, vertex_counter);
     else ptd::launch_shade_nc<3, false>(cls, grid, stream, S, W, Q, vertex_counter);
   } else ptd::launch_shade_nc<PT_NCS, false>(cls, grid, stream, S, W, Q, vertex_counter);  // infinite lights: RGB only (front end)
 }

@@ -749,8 +749,47 @@ struct Builder {
       l.tri = (int32_t)hs->envmaps.size();
       hs->envmaps.push_back(em);
       hs->env_texels.push_back(std::move(tex));
+    } else if (name == "projection" || name == "goniometric") {  // lights/projection.rs:176-195, goniometric.rs:143-159
+      if (spec.n_channels() != 3) throw ParseError("LightSource \"" + name + "\" is only supported with RGB spectra on the GPU path");
+      const bool proj = name == "projection";
+      std::vector<float> I = one_spectrum(ps, proj ? "I" : "L", 1.0f), sc = one_spectrum(ps, "scale", 1.0f);
+      for (size_t k = 0; k < I.size(); k++) I[k] = I[k] * sc[k];
+      std::string fn = ps.one_string("mapname", "");
+      pt_envmap em;
+      memset(&em, 0, sizeof(em));
+      std::vector<float> tex;
+      if (fn.empty()) { em.width = em.height = 1; tex = {1.0f, 1.0f, 1.0f}; }
+      else {  // make_mipmap: texels clamped at zero
+        std::string path = (fn[0] == '/') ? fn : (cur_dir.empty() ? fn : cur_dir + "/" + fn);
+        std::string err = load_pfm(path, &tex, &em.width, &em.height);
+        if (!err.empty()) throw ParseError("LightSource \"" + name + "\" mapname \"" + path + "\": " + err);
+        if (em.width > (1 << 14) || em.height > (1 << 14)) throw ParseError("LightSource \"" + name + "\": maps above 16384 pixels a side are not supported");
+        for (size_t i = 0; i < tex.size(); i++) tex[i] = std::max(tex[i], 0.0f);
+      }
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) { em.l2w[3 * r + c] = ctm.m.m[4 * r + c]; em.w2l[3 * r + c] = ctm.minv.m[4 * r + c]; }
+      if (proj) {  // ProjectionLight::new (projection.rs:21-62)
+        const float fov = ps.one_float("fov", 45.0f);
+        const float aspect = (float)em.width / (float)em.height;
+        if (aspect > 1.0f) { em.screen_bounds[0] = -aspect; em.screen_bounds[1] = -1.0f; em.screen_bounds[2] = aspect; em.screen_bounds[3] = 1.0f; }
+        else { em.screen_bounds[0] = -1.0f; em.screen_bounds[1] = -1.0f / aspect; em.screen_bounds[2] = 1.0f; em.screen_bounds[3] = 1.0f / aspect; }
+        em.hitcher = 1e-3f;
+        Xf light_projection = x_perspective(fov, 1e-3f, 1e30f);
+        memcpy(em.xf, light_projection.m.m, sizeof(em.xf));
+        V3 w_corner = vnorm(m_point(light_projection.minv, v3(em.screen_bounds[2], em.screen_bounds[3], 0.0f)));
+        em.cos_total_width = w_corner.z;
+      } else {
+        memcpy(em.xf, ctm.minv.m, sizeof(em.xf));
+      }
+      V3 p = m_point(ctm.m, v3(0, 0, 0));
+      l.type = proj ? PT_LIGHT_PROJECTION : PT_LIGHT_GONIOMETRIC;
+      l.spectrum = add_spectrum(I);
+      l.v[0] = p.x; l.v[1] = p.y; l.v[2] = p.z;
+      l.tri = (int32_t)hs->envmaps.size();
+      hs->envmaps.push_back(em);
+      hs->env_texels.push_back(std::move(tex));
     } else {
-      throw ParseError("LightSource \"" + name + "\" is not supported on the GPU path (point, spot, distant, infinite, area lights only)");
+      throw ParseError("LightSource \"" + name + "\" is not supported on the GPU path (point, spot, distant, infinite, projection, goniometric, area lights only)");
     }
     hs->lights.push_back(l);
   }

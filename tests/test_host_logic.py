@@ -172,6 +172,35 @@ def test_front_end_constant_foldable_textures(P):
         P.HostScene.parse_string(txt.replace('"spectrum" "scale"', '"spectrum" "imagemap"'))
 
 
+def test_front_end_map_lights(P, tmp_path):
+    """projection.rs:21-62, 176-195 / goniometric.rs:143-159: p_light, I * scale, the slide's screen bounds from its aspect,
+    Transform::perspective(fov, 1e-3, 1e30), cos_total_width from the corner direction"""
+    from test_hostcheck import write_pfm
+    write_pfm(str(tmp_path / "slide.pfm"), np.full((4, 10, 3), 0.5, np.float32))
+    base = 'Camera "perspective"\nWorldBegin\nTranslate 1 2 3\n%s\nWorldEnd\n'
+    hs = P.HostScene.parse_string(base % ('LightSource "projection" "rgb I" [2 3 4] "rgb scale" [2 1 1] "float fov" [60] "string mapname" ["%s"]' % (tmp_path / "slide.pfm")))
+    L, E = hs.desc.lights[0], hs.desc.envmaps[0]
+    assert L.type == P.capi.PT_LIGHT_PROJECTION and list(L.v) == [1, 2, 3] and L.tri == 0
+    assert list(hs.desc.spectra[3 * L.spectrum:3 * L.spectrum + 3]) == [4, 3, 4]
+    assert (E.width, E.height) == (10, 4) and list(E.screen_bounds) == [-2.5, -1, 2.5, 1] and E.hitcher == np.float32(1e-3)
+    t = np.tan(np.radians(30.0))
+    corner = np.array([2.5 * t, t, 1.0])
+    assert abs(E.cos_total_width - 1.0 / np.linalg.norm(corner)) < 1e-6
+    m = np.array(list(E.xf), np.float64).reshape(4, 4)
+    q = m @ np.array([corner[0], corner[1], 1.0, 1.0])
+    assert np.allclose(q[:2] / q[3], [2.5, 1.0], atol=1e-5)            # the corner direction projects onto the screen corner
+    hs = P.HostScene.parse_string(base % 'LightSource "projection"')    # no map: one white texel, aspect 1, fov 45
+    E = hs.desc.envmaps[0]
+    assert (E.width, E.height) == (1, 1) and list(E.screen_bounds) == [-1, -1, 1, 1] and list(E.texels[0:3]) == [1, 1, 1]
+    hs = P.HostScene.parse_string(base % 'LightSource "goniometric" "rgb L" [5 6 7]')
+    L, E = hs.desc.lights[0], hs.desc.envmaps[0]
+    assert L.type == P.capi.PT_LIGHT_GONIOMETRIC and list(L.v) == [1, 2, 3]
+    m = np.array(list(E.xf), np.float32).reshape(4, 4)
+    assert np.array_equal(m, np.array([[1, 0, 0, -1], [0, 1, 0, -2], [0, 0, 1, -3], [0, 0, 0, 1]], np.float32))   # world_to_light, translation included
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % 'LightSource "projection" "string mapname" ["missing.pfm"]')
+
+
 def test_front_end_cameras(P):
     """orthographic.rs:193-253 / environment.rs:90-151: same parameters as the perspective camera; Transform::orthographic(0, 1)
     is the identity, so raster_to_camera maps the raster onto the screen window at z = 0"""
@@ -549,7 +578,7 @@ def test_front_end_instances(P):
 
 
 def test_front_end_errors(P):
-    for bad in ['Shape "sphere"', 'WorldBegin\nLightSource "goniometric"', 'Sampler "stratified"\nWorldBegin\nWorldEnd', 'Bogus 1 2 3']:
+    for bad in ['Shape "sphere"', 'WorldBegin\nLightSource "laser"', 'Sampler "stratified"\nWorldBegin\nWorldEnd', 'Bogus 1 2 3']:
         with pytest.raises(P.PbrtError):
             P.HostScene.parse_string('Camera "perspective"\n' + bad + "\n")
 

@@ -444,6 +444,67 @@ def test_hostcheck_infinite_light(HC, tmp_path):
     check_env(HC, tmp_path)
 
 
+def map_light_scene(P, tmpdir, kind, integrator='"path"', res=24, spp=4, sampler="halton", strategy=None, mapped=True):
+    """Cornell box (mixed materials) lit by a LightSource "projection" (a slide projected from the camera side onto the
+    blocks and the back wall) or "goniometric" (near the ceiling, translated: the reference transforms the direction as a
+    point) in place of the box's area light's company: the area light stays, dimmed by nothing."""
+    txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", sampler=sampler, maxdepth=5)
+    mapname = ""
+    if mapped:
+        rng = np.random.RandomState(5)
+        shape = (6, 10) if kind == "projection" else (8, 16)      # the slide is resampled to 16 x 8 (aspect 10 / 6 > 1)
+        img = rng.uniform(0.0, 1.0, shape + (3,)).astype(np.float32)
+        img[2:4, 3:6] = [6.0, 1.0, 0.5]
+        img[0, 0] = -2.0                                          # clamped at zero by make_mipmap
+        name = os.path.join(str(tmpdir), "%s.pfm" % kind)
+        write_pfm(name, img)
+        mapname = ' "string mapname" ["%s"]' % name
+    if kind == "projection":
+        light = ('AttributeBegin\nTranslate 278 273 -300\nRotate 8 0 1 0\nLightSource "projection" "rgb I" [90000 80000 70000] "rgb scale" [2 2 1] "float fov" [50]%s\nAttributeEnd\n' % mapname)
+    else:
+        light = ('AttributeBegin\nTranslate 278 400 280\nRotate 90 1 0 0\nScale 2 2 2\nLightSource "goniometric" "rgb L" [50000 50000 60000]%s\nAttributeEnd\n' % mapname)
+    txt = txt.replace("WorldEnd", light + "WorldEnd")
+    head, rest = txt.split('Integrator "path"', 1)
+    extra = ' "string lightsamplestrategy" ["%s"]' % strategy if strategy else ""
+    return head + "Integrator " + integrator + extra + rest
+
+
+MAP_LIGHT_CASES = [dict(kind="projection"), dict(kind="goniometric"), dict(kind="projection", mapped=False, sampler="sobol", strategy="power"),
+                   dict(kind="goniometric", strategy="power"), dict(kind="projection", integrator='"directlighting"'),
+                   dict(kind="goniometric", integrator='"whitted"')]
+
+
+def check_map_lights(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=1e-5, frac=1.0):
+    """LightSource "projection" / "goniometric" (lights/projection.rs, goniometric.rs) against the oracle: same rays (equal
+    counters); the goniometric light's acos / atan2 are CUDA's on the GPU (rtol / frac are the caller's)"""
+    import oracle_api
+    for kw in MAP_LIGHT_CASES:
+        kw = dict(dict(res=res, spp=spp), **kw)
+        hs = P.HostScene.parse_string(map_light_scene(P, tmpdir, **kw))
+        L = hs.desc.lights[hs.desc.n_lights - 1]
+        assert L.type == (P.capi.PT_LIGHT_PROJECTION if kw["kind"] == "projection" else P.capi.PT_LIGHT_GONIOMETRIC) and hs.desc.n_envmaps == 1
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        sb = hs.desc.film.sample_bounds
+        rng = np.random.RandomState(16)
+        pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+        sn = rng.randint(0, kw["spp"], n).astype(np.int32)
+        la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+        ok = (np.abs(la - lb) <= rtol * np.maximum(np.abs(lb), 1e-3)).all(1)
+        assert ok.mean() >= frac, (kw, ok.mean(), la[~ok][:3], lb[~ok][:3])
+        # the light matters: without it the same samples are darker
+        base = oracle_api.OracleScene(P.HostScene.parse_string(map_light_scene(P, tmpdir, **kw).replace(' "rgb scale" [2 2 1]', "").replace('LightSource "%s"' % kw["kind"], 'LightSource "%s" "rgb scale" [0 0 0]' % kw["kind"]))).li(pix, sn)[0]
+        assert lb.sum() > 1.05 * base.sum(), (kw, lb.sum(), base.sum())
+        rgb, st = sc.render(collect_counters=1, wave_paths=wave_paths)
+        ref, so = orc.render(threads=threads)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-4, kw
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[k] == so[k], (kw, k, st[k], so[k])
+
+
+def test_hostcheck_map_lights(HC, tmp_path):
+    check_map_lights(HC, tmp_path)
+
+
 def test_hostcheck_resampled_constant_map(HC, tmp_path):
     """A constant 5 x 3 map resampled to 8 x 4 stays constant up to rounding (the Lanczos weights are normalised): the render
     equals that of a constant 8 x 4 map."""
