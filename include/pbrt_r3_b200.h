@@ -39,7 +39,9 @@ enum pt_material_type {       /* reference src/materials/create_material.rs:20-7
   PT_MAT_MIRROR = 4,          /* materials/mirror.rs:20-41  */
   PT_MAT_UBER = 5,            /* materials/uber.rs:73-128: opacity pass-through + diffuse + glossy + specular reflection / transmission */
   PT_MAT_SUBSTRATE = 6,       /* materials/substrate.rs:33-60: FresnelBlend */
-  PT_MAT_TRANSLUCENT = 7      /* materials/translucent.rs:37-100: diffuse + glossy reflection and transmission, eta 1.5 */
+  PT_MAT_TRANSLUCENT = 7,     /* materials/translucent.rs:37-100: diffuse + glossy reflection and transmission, eta 1.5 */
+  PT_MAT_MIX = 8              /* materials/mix.rs:60-93: the lobes of two other materials as ScaledBxDFs (kd, ks = their indices in
+                                 materials, neither a mix itself; kr = spectrum index of "amount") */
 };
 
 enum pt_light_type {          /* reference src/lights/create_light.rs:13-54 */

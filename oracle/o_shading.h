@@ -256,7 +256,17 @@ struct BxDF {
   }
   bool matches(int flags) const { int tp = type(); return (tp & flags) == tp; }
 
-  Spec<NC> f(Vec3 wo, Vec3 wi) const {
+  // ScaledBxDF (reflection/scaled.rs:7-62, used by MixMaterial): f and sample_f times `scale`; pdf and type unchanged
+  bool scaled = false;
+  Spec<NC> scale;
+  Spec<NC> f(Vec3 wo, Vec3 wi) const { Spec<NC> v = f_raw(wo, wi); return scaled ? scale * v : v; }
+  bool sample_f(Vec3 wo, Vec2 u, Spec<NC>* fo, Vec3* wio, Float* pdfo, int* stype) const {
+    if (!sample_raw(wo, u, fo, wio, pdfo, stype)) return false;
+    if (scaled) *fo = scale * *fo;
+    return true;
+  }
+
+  Spec<NC> f_raw(Vec3 wo, Vec3 wi) const {
     switch (kind) {
       case BX_LAMBERT: return r * INV_PI;
       case BX_OREN_NAYAR: {
@@ -339,14 +349,14 @@ struct BxDF {
     }
   }
   // returns false for None; sampled_type 0 = "use get_type()"
-  bool sample_f(Vec3 wo, Vec2 u, Spec<NC>* fo, Vec3* wio, Float* pdfo, int* stype) const {
+  bool sample_raw(Vec3 wo, Vec2 u, Spec<NC>* fo, Vec3* wio, Float* pdfo, int* stype) const {
     *stype = 0;
     switch (kind) {
       case BX_LAMBERT: case BX_OREN_NAYAR: {  // bxdf.rs:74-85 sample_f_default
         Vec3 wi = cosine_sample_hemisphere(u);
         if (wo.z < 0.0f) wi.z *= -1.0f;
         *pdfo = pdf(wo, wi);
-        *fo = f(wo, wi);
+        *fo = f_raw(wo, wi);
         *wio = wi;
         return true;
       }
@@ -355,7 +365,7 @@ struct BxDF {
         if (wo.z > 0.0f) wi.z *= -1.0f;
         *pdfo = pdf(wo, wi);
         if (!(*pdfo > 0.0f)) return false;
-        *fo = f(wo, wi);
+        *fo = f_raw(wo, wi);
         *wio = wi;
         return true;
       }
@@ -374,7 +384,7 @@ struct BxDF {
         }
         *pdfo = pdf(wo, wi);
         if (!(*pdfo > 0.0f)) return false;
-        *fo = f(wo, wi);
+        *fo = f_raw(wo, wi);
         *wio = wi;
         return true;
       }
@@ -430,7 +440,7 @@ struct BxDF {
         Float p = dist.pdf(wo, wh) / (4.0f * dot(wo, wh));
         if (p == 0.0f) return false;
         *pdfo = p;
-        *fo = f(wo, wi);
+        *fo = f_raw(wo, wi);
         *wio = wi;
         return true;
       }
@@ -444,7 +454,7 @@ struct BxDF {
         Float p = pdf(wo, wi);
         if (!(p > 0.0f)) return false;
         *pdfo = p;
-        *fo = f(wo, wi);
+        *fo = f_raw(wo, wi);
         *wio = wi;
         return true;
       }
@@ -657,13 +667,32 @@ struct BSDF {
 
 // ---- Materials (materials/*.rs compute_scattering_functions; constant textures) -----------------------------
 template <int NC>
+inline void material_scattering(const pt_scene_desc* d, int mi, const SurfInt& si, BSDF<NC>* bsdf, bool allow_multiple_lobes);
+template <int NC>
 inline void compute_scattering(const pt_scene_desc* d, const SurfInt& si, BSDF<NC>* bsdf, bool allow_multiple_lobes = true) {
   bsdf->valid = false;
   int mi = d->tri_material[si.tri];
   if (mi < 0) return;
+  material_scattering<NC>(d, mi, si, bsdf, allow_multiple_lobes);
+}
+template <int NC>
+inline void material_scattering(const pt_scene_desc* d, int mi, const SurfInt& si, BSDF<NC>* bsdf, bool allow_multiple_lobes) {
+  bsdf->valid = false;
   const pt_material& M = d->materials[mi];
   auto S = [&](int idx) { return Spec<NC>::load(d->spectra + (size_t)idx * NC); };
   switch (M.type) {
+    case PT_MAT_MIX: {  // mix.rs:60-93 (kd, ks = the two materials, kr = amount)
+      Spec<NC> s1 = S(M.kr).clamp_zero();
+      Spec<NC> s2 = (Spec<NC>(1.0f) - s1).clamp_zero();
+      BSDF<NC> b1, b2;
+      material_scattering<NC>(d, M.kd, si, &b1, allow_multiple_lobes);
+      material_scattering<NC>(d, M.ks, si, &b2, allow_multiple_lobes);
+      if (!b1.valid || !b2.valid) return;  // the reference asserts both exist
+      bsdf->init(si, b1.eta);
+      for (int i = 0; i < b1.n; i++) { BxDF<NC> b = b1.bx[i]; b.scaled = true; b.scale = s1; bsdf->add(b); }
+      for (int i = 0; i < b2.n; i++) { BxDF<NC> b = b2.bx[i]; b.scaled = true; b.scale = s2; bsdf->add(b); }
+      break;
+    }
     case PT_MAT_MATTE: {
       bsdf->init(si, 1.0f);
       Spec<NC> r = S(M.kd);  // NOT clamped (matte.rs:39-41)

@@ -236,6 +236,7 @@ struct Lobe {
   int fres;       // FR_*
   float a, b;     // Oren-Nayar A,B | alpha_x, alpha_y
   float ei, et;   // dielectric Fresnel eta_i, eta_t | transmission eta_a, eta_b
+  int scale = -1; // ScaledBxDF (MixMaterial): spectrum index of the factor on f, -1 = none; only read by the five-lobe BSDFs
 };
 // Compile-time lobe sets: a shade kernel specialised for one material class only keeps the code of the lobes and
 // Fresnel terms that class can produce (bits 0-9: LB_* kinds, bits 12-14: FR_* kinds).
@@ -827,7 +828,7 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BS* B) {
       bsdf_add(B, n, L);
       break;
     }
-    case PT_MAT_UBER: case PT_MAT_SUBSTRATE: case PT_MAT_TRANSLUCENT: {
+    case PT_MAT_UBER: case PT_MAT_SUBSTRATE: case PT_MAT_TRANSLUCENT: case PT_MAT_MIX: {
       // uber.rs:85-125, substrate.rs:44-59, translucent.rs:48-98: every parameter is a constant, so the host has already
       // listed the lobes (device_api.cu material_lobes)
       if (MT != -1) { PT_UNREACHABLE(); }
@@ -838,7 +839,7 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BS* B) {
       for (int k = 0; k < PT_LOBES_EXTRA; k++)
         if (k < T.n && k < BS::ML) {
           Lobe L;
-          L.kind = T.kind[k]; L.sp0 = T.sp0[k]; L.sp1 = T.sp1[k]; L.fres = T.fres[k]; L.a = T.a[k]; L.b = T.b[k]; L.ei = T.ei[k]; L.et = T.et[k];
+          L.kind = T.kind[k]; L.sp0 = T.sp0[k]; L.sp1 = T.sp1[k]; L.fres = T.fres[k]; L.a = T.a[k]; L.b = T.b[k]; L.ei = T.ei[k]; L.et = T.et[k]; L.scale = T.scale[k];
           bsdf_add(B, n, L);
         }
       break;
@@ -853,13 +854,21 @@ PT_HD1 void make_bsdf(const DScene& S, const SurfD& si, BS* B) {
   B->ts = norm3(cross3(B->ns, B->ss));
 }
 
+// ScaledBxDF::f / sample_f (reflection/scaled.rs:32-47): scale * f; pdf and type are the wrapped lobe's
+template <int NC, class BS>
+PT_HD Sp<NC> lobe_scaled(const DScene& S, const Lobe& L, Sp<NC> f) {
+  if constexpr (BS::ML == PT_LOBES_EXTRA) {
+    if (L.scale >= 0) return sp_load<NC>(S.spectra + (size_t)L.scale * NC) * f;
+  }
+  return f;
+}
 template <int NC, int CM = PT_CM_ANY, class BS = BsdfD>
 PT_HD Sp<NC> bsdf_sum_f(const DScene& S, const BS& B, f3 wo, f3 wi, f3 wo_w, f3 wi_w, int flags) {
   bool refl = (dot3(wi_w, B.ng) * dot3(wo_w, B.ng)) > 0.0f;
   Sp<NC> r = sp_const<NC>(0.0f);
   PT_LOBE_LOOP(i) {
     int tp = lobe_type<CM>(B.lobe[i].kind);
-    if (lobe_matches<CM>(B.lobe[i].kind, flags) && ((refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS)))) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+    if (lobe_matches<CM>(B.lobe[i].kind, flags) && ((refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS)))) r = r + lobe_scaled<NC, BS>(S, B.lobe[i], lobe_f<NC, CM>(S, B.lobe[i], wo, wi));
   }
   return r;
 }
@@ -899,10 +908,10 @@ PT_HD1 void bsdf_f_pdf(const DScene& S, const BS& B, f3 wo_w, f3 wi_w, int flags
       Sp<NC> fl;
       float pl;
       lobe_f_pdf<NC, CM>(S, B.lobe[i], wo, wi, want_f, &fl, &pl);
-      if (want_f) r = r + fl;
+      if (want_f) r = r + lobe_scaled<NC, BS>(S, B.lobe[i], fl);
       p = p + pl;
     } else {  // nothing to share: no spectrum-sized temporary (matters for 60 bins)
-      if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+      if (want_f) r = r + lobe_scaled<NC, BS>(S, B.lobe[i], lobe_f<NC, CM>(S, B.lobe[i], wo, wi));
       p = p + lobe_pdf<CM>(B.lobe[i], wo, wi);
     }
     count++;
@@ -931,6 +940,7 @@ PT_HD bool bsdf_sample(const DScene& S, const BS& B, f3 wo_w, f2 u, int flags, S
   float pdf;
   int t;
   if (!lobe_sample<NC, CM>(S, L, wo, ur, &fv, &wi, &pdf, &t)) return false;
+  fv = lobe_scaled<NC, BS>(S, L, fv);
   if (pdf <= 0.0f) return false;
   int ltype = lobe_type<CM>(L.kind);
   int sampled = t != 0 ? t : ltype;
@@ -950,15 +960,15 @@ PT_HD bool bsdf_sample(const DScene& S, const BS& B, f3 wo_w, f2 u, int flags, S
       const int tp = lobe_type<CM>(B.lobe[i].kind);
       const bool want_f = (refl && (tp & F_REFL)) || (!refl && (tp & F_TRANS));
       if (i == index) {
-        if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+        if (want_f) r = r + lobe_scaled<NC, BS>(S, B.lobe[i], lobe_f<NC, CM>(S, B.lobe[i], wo, wi));
       } else if (((CM >> LB_MF_REFL) & 1) && B.lobe[i].kind == LB_MF_REFL) {
         Sp<NC> fl;
         float pl;
         lobe_f_pdf<NC, CM>(S, B.lobe[i], wo, wi, want_f, &fl, &pl);
-        if (want_f) r = r + fl;
+        if (want_f) r = r + lobe_scaled<NC, BS>(S, B.lobe[i], fl);
         pdf += pl;
       } else {
-        if (want_f) r = r + lobe_f<NC, CM>(S, B.lobe[i], wo, wi);
+        if (want_f) r = r + lobe_scaled<NC, BS>(S, B.lobe[i], lobe_f<NC, CM>(S, B.lobe[i], wo, wi));
         pdf += lobe_pdf<CM>(B.lobe[i], wo, wi);
       }
     }

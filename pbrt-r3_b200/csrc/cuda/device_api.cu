@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../host/bvh_build.h"
@@ -393,20 +394,59 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
     auto clamp0 = [&](float* c) { for (uint32_t k = 0; k < NC; k++) c[k] = c[k] < 0.0f ? 0.0f : c[k]; };
     auto black = [&](const float* c) { for (uint32_t k = 0; k < NC; k++) if (c[k] != 0.0f) return false; return true; };
     auto add = [&](const float* c) { size_t n = spectra.size() / NC; for (uint32_t k = 0; k < NC; k++) spectra.push_back(c[k]); return (int)n; };
-    for (uint32_t m = 0; m < D->n_materials; m++) {
+    // the lobes of material m appended to T (every lobe scaled by spectrum `scale`, -1 = none); false = no BSDF at all
+    const bool multi = D->integrator.type == PT_INTEGRATOR_PATH;  // allow_multiple_lobes: path.rs passes true, the tree integrators false
+    std::function<bool(uint32_t, MatLobes&, int)> list_lobes = [&](uint32_t m, MatLobes& T, int scale) -> bool {
       const pt_material& M = mats[m];
-      MatLobes& T = lobes[m];
-      memset(&T, 0, sizeof(T));
-      T.eta = 1.0f;
-      if (M.type != PT_MAT_UBER && M.type != PT_MAT_SUBSTRATE && M.type != PT_MAT_TRANSLUCENT) continue;
-      if (NC != 3) { pt_set_error("uber / substrate / translucent materials are only supported with RGB spectra"); return 1; }
       const float ax = std::max(0.001f, alpha[2 * m]), ay = std::max(0.001f, alpha[2 * m + 1]);  // TrowbridgeReitzDistribution::new
+      bool overflow = false;
       auto lobe = [&](int kind, int sp0, int sp1, int fres, float a, float b, float ei, float et) {
+        if (T.n >= 5) { overflow = true; return; }
         const int k = T.n++;
-        T.kind[k] = kind; T.sp0[k] = sp0; T.sp1[k] = sp1; T.fres[k] = fres; T.a[k] = a; T.b[k] = b; T.ei[k] = ei; T.et[k] = et;
+        T.kind[k] = kind; T.sp0[k] = sp0; T.sp1[k] = sp1; T.fres[k] = fres; T.a[k] = a; T.b[k] = b; T.ei[k] = ei; T.et[k] = et; T.scale[k] = scale;
       };
       float kd[60], ks[60], kr[60], kt[60], op[60], t[60], x[60];
       get(M.kd, kd); get(M.ks, ks); get(M.kr, kr); get(M.kt, kt); get(M.opacity, op);
+      if (M.type == PT_MAT_MATTE) {  // matte.rs:37-56 (Kd is not clamped)
+        if (!black(kd)) {
+          const float sig = std::min(std::max(M.sigma, 0.0f), 90.0f);
+          if (sig == 0.0f) lobe(LB_LAMBERT, M.kd, -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
+          else {
+            const float sg = sig * (PT_PI / 180.0f), s2 = sg * sg;
+            lobe(LB_OREN, M.kd, -1, FR_NOOP, 1.0f - (s2 / (2.0f * (s2 + 0.33f))), 0.45f * s2 / (s2 + 0.09f), 1.0f, 1.0f);
+          }
+        }
+        return !overflow;
+      }
+      if (M.type == PT_MAT_PLASTIC) {  // plastic.rs:43-70 (Kd, Ks clamped above)
+        if (!black(kd)) lobe(LB_LAMBERT, M.kd, -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
+        if (!black(ks)) lobe(LB_MF_REFL, M.ks, -1, FR_DIEL, ax, ax, 1.5f, 1.0f);
+        return !overflow;
+      }
+      if (M.type == PT_MAT_MIRROR) {
+        if (!black(kr)) lobe(LB_MIRROR, M.kr, -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
+        return !overflow;
+      }
+      if (M.type == PT_MAT_METAL) {
+        lobe(LB_MF_REFL, M.kr, M.ks, FR_COND, ax, ay, 1.0f, 1.0f);
+        return !overflow;
+      }
+      if (M.type == PT_MAT_GLASS) {  // glass.rs:47-110 (Kr = kr, Kt = ks)
+        const bool rb = black(kr), tb = black(ks);
+        if (rb && tb) return false;
+        T.eta = M.eta;
+        if (M.uroughness == 0.0f && M.vroughness == 0.0f) {
+          if (multi) lobe(LB_FRESNEL_SPEC, M.kr, M.ks, FR_NOOP, 0.0f, 0.0f, 1.0f, M.eta);
+          else {
+            if (!rb) lobe(LB_SPEC_REFL_D, M.kr, -1, FR_DIEL, 0.0f, 0.0f, 1.0f, M.eta);
+            if (!tb) lobe(LB_SPEC_TRANS, M.ks, -1, FR_NOOP, 0.0f, 0.0f, 1.0f, M.eta);
+          }
+        } else {
+          if (!rb) lobe(LB_MF_REFL, M.kr, -1, FR_DIEL, ax, ay, 1.0f, M.eta);
+          if (!tb) lobe(LB_MF_TRANS, M.ks, -1, FR_NOOP, ax, ay, 1.0f, M.eta);
+        }
+        return !overflow;
+      }
       clamp0(kd); clamp0(ks);
       if (M.type == PT_MAT_UBER) {  // uber.rs:85-125
         clamp0(kr); clamp0(kt);
@@ -424,10 +464,10 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
         if (!black(x)) lobe(LB_SPEC_TRANS, add(x), -1, FR_NOOP, 0.0f, 0.0f, 1.0f, M.eta);
       } else if (M.type == PT_MAT_SUBSTRATE) {  // substrate.rs:44-59
         if (!black(kd) && !black(ks)) lobe(LB_FRESNEL_BLEND, add(kd), add(ks), FR_NOOP, ax, ay, 1.0f, 1.0f);
-      } else {  // translucent.rs:48-98 (reflect = kr, transmit = kt)
+      } else if (M.type == PT_MAT_TRANSLUCENT) {  // translucent.rs:48-98 (reflect = kr, transmit = kt)
         clamp0(kr); clamp0(kt);
         T.eta = 1.5f;
-        if (black(kr) && black(kt)) { T.n = -1; continue; }
+        if (black(kr) && black(kt)) return false;
         if (!black(kd)) {
           for (uint32_t k = 0; k < NC; k++) x[k] = kr[k] * kd[k];
           if (!black(kr)) lobe(LB_LAMBERT, add(x), -1, FR_NOOP, 0.0f, 0.0f, 1.0f, 1.0f);
@@ -441,12 +481,45 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
           if (!black(kt)) lobe(LB_MF_TRANS, add(x), -1, FR_NOOP, ax, ay, 1.0f, 1.5f);
         }
       }
+      return !overflow;
+    };
+    for (uint32_t m = 0; m < D->n_materials; m++) {
+      const pt_material& M = mats[m];
+      MatLobes& T = lobes[m];
+      memset(&T, 0, sizeof(T));
+      T.eta = 1.0f;
+      for (int k = 0; k < 5; k++) T.scale[k] = -1;
+      if (M.type < PT_MAT_UBER || M.type > PT_MAT_MIX) continue;
+      if (NC != 3) { pt_set_error("uber / substrate / translucent / mix materials are only supported with RGB spectra"); return 1; }
+      if (M.type != PT_MAT_MIX) {
+        if (!list_lobes(m, T, -1)) T.n = -1;
+        continue;
+      }
+      // MixMaterial (mix.rs:60-93): the lobes of both materials as ScaledBxDFs, s1 = clamp(amount), s2 = clamp(1 - s1); eta of the first
+      if (M.kd < 0 || M.ks < 0 || (uint32_t)M.kd >= D->n_materials || (uint32_t)M.ks >= D->n_materials || mats[M.kd].type == PT_MAT_MIX || mats[M.ks].type == PT_MAT_MIX) {
+        pt_set_error("mix material: sub-material index out of range, or a nested mix (not supported)"); return 1;
+      }
+      float s1[60], s2[60];
+      get(M.kr, s1); clamp0(s1);
+      for (uint32_t k = 0; k < NC; k++) s2[k] = 1.0f - s1[k];
+      clamp0(s2);
+      MatLobes A, B2;
+      memset(&A, 0, sizeof(A)); memset(&B2, 0, sizeof(B2));
+      A.eta = B2.eta = 1.0f;
+      const bool ok1 = list_lobes((uint32_t)M.kd, A, add(s1)), ok2 = list_lobes((uint32_t)M.ks, B2, add(s2));
+      if (!ok1 || !ok2 || A.n + B2.n > 5) { pt_set_error("mix material: a sub-material without a BSDF, or more than five lobes in total (not supported on the GPU path)"); return 1; }
+      T = A;
+      for (int k = 0; k < B2.n; k++) {
+        const int q = T.n++;
+        T.kind[q] = B2.kind[k]; T.sp0[q] = B2.sp0[k]; T.sp1[q] = B2.sp1[k]; T.fres[q] = B2.fres[k]; T.a[q] = B2.a[k]; T.b[q] = B2.b[k]; T.ei[q] = B2.ei[k]; T.et[q] = B2.et[k];
+        T.scale[q] = B2.scale[k];
+      }
     }
   }
   s->class_mask = 1u;
   for (uint32_t m = 0; m < D->n_materials; m++) {
     if (mats[m].type >= 0 && mats[m].type <= 4) s->class_mask |= 1u << (mats[m].type + 1);
-    else if (mats[m].type >= PT_MAT_UBER && mats[m].type <= PT_MAT_TRANSLUCENT) s->class_mask |= 1u << CL_EXTRA;
+    else if (mats[m].type >= PT_MAT_UBER && mats[m].type <= PT_MAT_MIX) s->class_mask |= 1u << CL_EXTRA;
   }
   CK(s->bufs.upload(spectra.data(), spectra.size(), &H.spectra));
   CK(s->bufs.upload(lobes.data(), lobes.size(), &H.mat_lobes));

@@ -73,7 +73,7 @@ struct LightDistDev {   // dense restatement of SpatialLightDistribution's hash 
 struct MatLobes {
   int32_t n;              // -1: no BSDF at all (the ray passes through)
   float eta;
-  int32_t kind[5], sp0[5], sp1[5], fres[5];
+  int32_t kind[5], sp0[5], sp1[5], fres[5], scale[5];  // scale: MixMaterial's factor on the lobe (spectrum index, -1 = none)
   float a[5], b[5], ei[5], et[5];
 };
 

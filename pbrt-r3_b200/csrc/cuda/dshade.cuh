@@ -79,7 +79,7 @@ PT_HD int shade_class(const DScene& S, int tri, int bounces) {
   int mi = ldg(S.tri_material + tri);
   if (mi < 0) return CL_NONE;
   int t = S.materials[mi].type;
-  return (t >= 0 && t <= 4) ? t + 1 : ((t >= PT_MAT_UBER && t <= PT_MAT_TRANSLUCENT) ? CL_EXTRA : CL_NONE);
+  return (t >= 0 && t <= 4) ? t + 1 : ((t >= PT_MAT_UBER && t <= PT_MAT_MIX) ? CL_EXTRA : CL_NONE);
 }
 
 // {Perspective,Orthographic,Environment}Camera::generate_ray_differential without the differentials (constant textures:

@@ -267,6 +267,31 @@ struct Builder {
     m.remap_roughness = 1;
     std::string nm = name;
     if (nm == "" || nm == "none") return -1;
+    if (nm == "mix") {  // scene_context.rs:446-451 + mix.rs:96-103: two named materials (matte from these parameters when unknown)
+      if (spec.n_channels() != 3) throw ParseError("Material \"mix\" is only supported with RGB spectra on the GPU path");
+      static const ParamSet empty;
+      int sub[2];
+      const char* keys[2] = {"namedmaterial1", "namedmaterial2"};
+      for (int k = 0; k < 2; k++) {
+        std::string key;
+        for (const ParamSet* ps : {tp.geom, tp.mat})
+          if (key.empty()) if (const Param* q = ps->find(PC_STRING, keys[k])) if (q->s.size() == 1) key = q->s[0];
+        auto it = gs.named_materials.find(key);
+        if (it == gs.named_materials.end()) sub[k] = make_material("matte", geom, mat);
+        else {
+          if (it->second.name == "mix") throw ParseError("Material \"mix\" of a \"mix\" material is not supported on the GPU path");
+          sub[k] = make_material(it->second.name, it->second.params, empty);
+        }
+        if (sub[k] < 0) throw ParseError("Material \"mix\": \"" + key + "\" has no BSDF (material \"none\"), which the reference does not accept either");
+      }
+      m.type = PT_MAT_MIX;
+      m.kd = sub[0]; m.ks = sub[1];
+      m.kr = add_spectrum(tp_spectrum(tp, "amount", spec.constant(0.5f)));
+      for (size_t k = 0; k < hs->materials.size(); k++)
+        if (memcmp(&hs->materials[k], &m, sizeof(m)) == 0) return (int)k;
+      hs->materials.push_back(m);
+      return (int)hs->materials.size() - 1;
+    }
     if (nm != "matte" && nm != "plastic" && nm != "glass" && nm != "metal" && nm != "mirror" && nm != "uber" && nm != "substrate" && nm != "translucent") {
       // create_material.rs:65-70: unknown names fall back to matte with a warning
       warn("Unable to create material \"" + nm + "\" on the GPU path; using \"matte\".");

@@ -240,6 +240,13 @@ def test_extra_materials(P):
     check_extra_materials(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
 
 
+def test_mix_material(P):
+    """Material "mix" (ScaledBxDF lobes of two named materials in the generic five-lobe class) under path / directlighting /
+    whitted: radiance within 2e-5 on >= 99.9 % of the samples, equal ray / visit / vertex counters."""
+    from test_hostcheck import check_mix
+    check_mix(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
+
+
 def test_map_lights(P, tmp_path):
     """LightSource "projection" / "goniometric": per-sample radiance against the oracle (acos / atan2 are CUDA's: 99.5 % of the
     samples within 1e-4), equal counters, image."""

@@ -201,6 +201,26 @@ def test_front_end_map_lights(P, tmp_path):
         P.HostScene.parse_string(base % 'LightSource "projection" "string mapname" ["missing.pfm"]')
 
 
+def test_front_end_mix_material(P):
+    """scene_context.rs:446-451, mix.rs:96-103: two named materials (matte from the mix's own parameters for an unknown
+    name), "amount" default 0.5; identical sub-materials are shared"""
+    base = ('Camera "perspective"\nWorldBegin\nMakeNamedMaterial "a" "string type" ["plastic"] "rgb Kd" [0.5 0.3 0.2]\n'
+            'MakeNamedMaterial "b" "string type" ["mirror"]\n%s\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\nWorldEnd\n')
+    hs = P.HostScene.parse_string(base % 'Material "mix" "string namedmaterial1" ["a"] "string namedmaterial2" ["b"] "rgb amount" [0.2 0.4 0.6]')
+    d = hs.desc
+    M = d.materials[d.tri_material[0]]
+    assert M.type == P.capi.PT_MAT_MIX and d.materials[M.kd].type == P.capi.PT_MAT_PLASTIC and d.materials[M.ks].type == P.capi.PT_MAT_MIRROR
+    assert np.allclose(list(d.spectra[3 * M.kr:3 * M.kr + 3]), [0.2, 0.4, 0.6])
+    hs = P.HostScene.parse_string(base % 'Material "mix" "string namedmaterial1" ["zzz"] "string namedmaterial2" ["b"] "rgb Kd" [0.1 0.2 0.3]')
+    d = hs.desc
+    M = d.materials[d.tri_material[0]]
+    sub = d.materials[M.kd]
+    assert sub.type == P.capi.PT_MAT_MATTE and np.allclose(list(d.spectra[3 * sub.kd:3 * sub.kd + 3]), [0.1, 0.2, 0.3])
+    assert np.allclose(list(d.spectra[3 * M.kr:3 * M.kr + 3]), [0.5, 0.5, 0.5])
+    with pytest.raises(P.PbrtError):
+        P.HostScene.parse_string(base % 'MakeNamedMaterial "n" "string type" ["none"]\nMaterial "mix" "string namedmaterial1" ["n"] "string namedmaterial2" ["b"]')
+
+
 def test_front_end_cameras(P):
     """orthographic.rs:193-253 / environment.rs:90-151: same parameters as the perspective camera; Transform::orthographic(0, 1)
     is the identity, so raster_to_camera maps the raster onto the screen window at z = 0"""

@@ -567,6 +567,77 @@ def test_hostcheck_extra_materials(HC):
     check_extra_materials(HC)
 
 
+def mix_scene(P, integrator='"path"', res=24, spp=4, sampler="halton", maxdepth=6):
+    """Cornell box whose short block is a mix of plastic and smooth glass (amount per channel), the tall block a mix of
+    substrate and rough metal, the floor a mix of OrenNayar matte and mirror with a negative / above-one amount (clamped),
+    the back wall a mix of a known named material with an unknown one (matte from the mix's own parameters)."""
+    txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", extra_lights=True, sampler=sampler, maxdepth=maxdepth)
+    named = ('MakeNamedMaterial "pl" "string type" ["plastic"] "rgb Kd" [0.5 0.3 0.2] "rgb Ks" [0.4 0.4 0.4] "float roughness" [0.08]\n'
+             'MakeNamedMaterial "gl" "string type" ["glass"] "float eta" [1.45]\n'
+             'MakeNamedMaterial "sub" "string type" ["substrate"] "rgb Kd" [0.2 0.5 0.3] "rgb Ks" [0.3 0.3 0.3] "float uroughness" [0.05] "float vroughness" [0.2]\n'
+             'MakeNamedMaterial "met" "string type" ["metal"] "float roughness" [0.1]\n'
+             'MakeNamedMaterial "on" "string type" ["matte"] "rgb Kd" [0.6 0.6 0.5] "float sigma" [25]\n'
+             'MakeNamedMaterial "mir" "string type" ["mirror"] "rgb Kr" [0.85 0.85 0.9]\n')
+    rep = {'Material "glass" "float eta" [1.5]\n': 'Material "mix" "string namedmaterial1" ["pl"] "string namedmaterial2" ["gl"] "rgb amount" [0.7 0.4 0.55]\n',
+           'Material "metal" "rgb eta" [0.2 0.92 1.1] "rgb k" [3.9 2.45 2.14] "float roughness" [0.05]\n': 'Material "mix" "string namedmaterial1" ["sub"] "string namedmaterial2" ["met"] "float amount" [0.35]\n',
+           'Material "plastic" "rgb Kd" [0.4 0.4 0.4] "rgb Ks" [0.3 0.3 0.3] "float roughness" [0.1]\n': 'Material "mix" "string namedmaterial1" ["on"] "string namedmaterial2" ["mir"] "rgb amount" [-0.5 0.6 1.5]\n',
+           'Material "mirror" "rgb Kr" [0.8 0.8 0.8]\n': 'Material "mix" "string namedmaterial1" ["pl"] "string namedmaterial2" ["nope"] "rgb Kd" [0.1 0.2 0.6]\n'}
+    for a, b in rep.items():
+        assert a in txt, a
+        txt = txt.replace(a, b)
+    txt = txt.replace("WorldBegin\n", "WorldBegin\n" + named, 1)
+    head, rest = txt.split('Integrator "path"', 1)
+    return head + 'Integrator %s "integer maxdepth" [%d]' % (integrator, maxdepth) + rest[rest.index("\n"):]
+
+
+def check_mix(P, n=1500, res=24, spp=4, wave_paths=300, threads=2):
+    """Material "mix" (materials/mix.rs, reflection/scaled.rs): per-sample radiance against the oracle's ScaledBxDF
+    restatement under path (FresnelSpecular glass) and the tree integrators (split specular lobes), equal counters"""
+    import oracle_api
+    for integ, kw in [('"path"', dict()), ('"path"', dict(sampler="sobol", maxdepth=9)), ('"directlighting" "string strategy" ["one"]', dict()), ('"whitted"', dict())]:
+        hs = P.HostScene.parse_string(mix_scene(P, integ, res=res, spp=spp, **kw))
+        mats = [hs.desc.materials[i] for i in range(hs.desc.n_materials)]
+        mixes = [m for m in mats if m.type == P.capi.PT_MAT_MIX]
+        assert len(mixes) == 4 and all(mats[m.kd].type != P.capi.PT_MAT_MIX and mats[m.ks].type != P.capi.PT_MAT_MIX for m in mixes)
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        sb = hs.desc.film.sample_bounds
+        rng = np.random.RandomState(18)
+        pix = np.stack([rng.randint(sb[0], sb[2], n), rng.randint(sb[1], sb[3], n)], 1).astype(np.int32)
+        sn = rng.randint(0, spp, n).astype(np.int32)
+        la, lb = sc.li(pix, sn), orc.li(pix, sn)[0]
+        ok = (np.abs(la - lb) <= 2e-5 * np.maximum(np.abs(lb), 1e-3)).all(1)
+        assert ok.mean() >= 0.999, (integ, kw, ok.mean(), la[~ok][:3], lb[~ok][:3])
+        assert la.max() > 0
+        rgb, st = sc.render(collect_counters=1, wave_paths=wave_paths)
+        ref, so = orc.render(threads=threads)
+        assert np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-4, (integ, kw)
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested", "path_vertices"):
+            assert st[k] == so[k], (integ, kw, k, st[k], so[k])
+
+
+def test_hostcheck_mix_material(HC):
+    check_mix(HC)
+
+
+def test_hostcheck_mix_limits(HC):
+    """amount 1 = the first material alone (s2 = 0 scales the second one's lobes to black): same image as that material;
+    more than five lobes in total, and a mix of mixes, are refused"""
+    base = HC.scenes.cornell_box(res=16, spp=2, materials="mixed")
+    named = ('MakeNamedMaterial "a" "string type" ["plastic"] "rgb Kd" [0.5 0.3 0.2]\nMakeNamedMaterial "b" "string type" ["matte"]\n'
+             'MakeNamedMaterial "u" "string type" ["uber"] "rgb Kr" [0.2 0.2 0.2] "rgb Kt" [0.2 0.2 0.2] "rgb opacity" [0.5 0.5 0.5]\n'
+             'MakeNamedMaterial "mm" "string type" ["mix"] "string namedmaterial1" ["a"] "string namedmaterial2" ["b"]\n')
+    gl = 'Material "glass" "float eta" [1.5]\n'
+    one = base.replace("WorldBegin\n", "WorldBegin\n" + named, 1).replace(gl, 'Material "mix" "string namedmaterial1" ["a"] "string namedmaterial2" ["b"] "float amount" [1]\n')
+    alone = base.replace(gl, 'Material "plastic" "rgb Kd" [0.5 0.3 0.2]\n')
+    a = HC.Scene(HC.HostScene.parse_string(one)).render()[0]
+    b = HC.Scene(HC.HostScene.parse_string(alone)).render()[0]
+    assert b.mean() > 0 and np.sqrt(((a - b) ** 2).mean()) / b.mean() < 0.05      # same estimator up to the lobe choice among 3 instead of 2
+    with pytest.raises(HC.PbrtError):
+        HC.Scene(HC.HostScene.parse_string(base.replace("WorldBegin\n", "WorldBegin\n" + named, 1).replace(gl, 'Material "mix" "string namedmaterial1" ["u"] "string namedmaterial2" ["a"]\n')))
+    with pytest.raises(HC.PbrtError):
+        HC.HostScene.parse_string(base.replace("WorldBegin\n", "WorldBegin\n" + named, 1).replace(gl, 'Material "mix" "string namedmaterial1" ["mm"] "string namedmaterial2" ["a"]\n'))
+
+
 CAMERA_CASES = [('Camera "orthographic" "float screenwindow" [-285 285 -280 280]', None),
                 ('Camera "orthographic" "float screenwindow" [-285 285 -280 280] "float lensradius" [6] "float focaldistance" [1000] "float shutteropen" [0.2]', None),
                 ('Camera "environment"', "LookAt 278 273 250  278 273 500  0 1 0")]
