@@ -12,6 +12,7 @@
 #include <memory>
 #include <string>
 #include <functional>
+#include <thread>
 #include <vector>
 
 #include "../host/bvh_build.h"
@@ -222,8 +223,21 @@ int grid_for(const pt_scene* s, size_t n, int block, int per_sm) {
 template <int NC>
 int precompute_light_distribution(pt_scene* s, uint32_t n_vox, float* func, float* cdf, float* func_int) {
   size_t total = (size_t)n_vox * s->h.n_lights;
-  PT_LAUNCH(grid_for(s, total, 128, 16), 128, s->stream, k_voxel_contrib<NC>)(s->h, func, n_vox);
+#ifdef PT_HOSTCHECK
+  {  // tests/hostcheck: the serial stand-in for a launch would spend ~10 s per Cornell scene here; slices on host threads
+    hostcheck::begin_launch();
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 16));
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) {
+      const size_t a = total * t / nt, b = total * (t + 1) / nt;
+      th.emplace_back([=]() { k_voxel_contrib<NC>(s->h, func, n_vox, a, b - a); });
+    }
+    for (std::thread& t : th) t.join();
+  }
+#else
+  PT_LAUNCH(grid_for(s, total, 128, 16), 128, s->stream, k_voxel_contrib<NC>)(s->h, func, n_vox, (size_t)0, total);
   CK(cudaGetLastError());
+#endif
   PT_LAUNCH(grid_for(s, n_vox, 128, 16), 128, s->stream, k_voxel_cdf)(s->h.n_lights, n_vox, func, cdf, func_int);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s->stream));

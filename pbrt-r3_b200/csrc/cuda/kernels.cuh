@@ -543,10 +543,12 @@ __global__ void k_sampler_values(const __grid_constant__ DScene S, const int* pi
 
 // ---- SpatialLightDistribution::compute_distribution for every voxel (spatial.rs:113-197) ---------------------------
 template <int NC>
-__global__ void k_voxel_contrib(const __grid_constant__ DScene S, float* func, uint32_t n_vox) {
+__global__ void k_voxel_contrib(const __grid_constant__ DScene S, float* func, uint32_t n_vox, size_t first, size_t count) {
+  // (voxel, light) pairs first .. first + count of the n_vox x n_lights table (the whole table on the device; the CPU test
+  // build gives each host thread a slice)
   const uint32_t nl = S.n_lights;
   const LightDistDev& D = S.ld;
-  for (size_t id = blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < (size_t)n_vox * nl; id += (size_t)gridDim.x * blockDim.x) {
+  for (size_t id = first + blockIdx.x * (size_t)blockDim.x + threadIdx.x; id < first + count; id += (size_t)gridDim.x * blockDim.x) {
     uint32_t vox = (uint32_t)(id / nl), j = (uint32_t)(id % nl);
     uint32_t pz = vox % D.voxels[2], py = (vox / D.voxels[2]) % D.voxels[1], px = vox / (D.voxels[2] * D.voxels[1]);
     const uint32_t pi[3] = {px, py, pz};

@@ -412,12 +412,12 @@ ENV_CASES = [dict(mapped=False), dict(mapped=True), dict(mapped=True, sampler="s
              dict(mapped=True, map_shape=(7, 12)), dict(mapped=True, map_shape=(9, 16), sampler="sobol")]   # resampled to 16 x 8 / 16 x 16 (mipmap.rs:316-404)
 
 
-def check_env(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=1e-5, frac=1.0):
+def check_env(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=1e-5, frac=1.0, cases=None):
     """LightSource "infinite" (lights/infinite.rs): Le of escaped rays, Distribution2D importance sampling + MIS against the
     oracle's own MIPMap / Distribution2D restatement; same rays (equal counters).  On the GPU acos / atan2 are CUDA's (a few
     ulp in the lookup coordinates and the MIS pdf): rtol / frac are the caller's."""
     import oracle_api
-    for kw in ENV_CASES:
+    for kw in (cases or ENV_CASES):
         kw = dict(dict(res=res, spp=spp), **kw)
         hs = P.HostScene.parse_string(env_scene(P, tmpdir, **kw))
         assert hs.desc.n_envmaps == 1 and hs.desc.lights[hs.desc.n_lights - 1].type == P.capi.PT_LIGHT_INFINITE
@@ -441,7 +441,7 @@ def check_env(P, tmpdir, n=1500, res=24, spp=4, wave_paths=300, threads=2, rtol=
 
 
 def test_hostcheck_infinite_light(HC, tmp_path):
-    check_env(HC, tmp_path)
+    check_env(HC, tmp_path, cases=[ENV_CASES[k] for k in (0, 2, 3, 4, 6, 7)])      # all eight on the GPU (test_gpu_parity.py)
 
 
 def map_light_scene(P, tmpdir, kind, integrator='"path"', res=24, spp=4, sampler="halton", strategy=None, mapped=True):
@@ -508,8 +508,8 @@ def test_hostcheck_map_lights(HC, tmp_path):
 def test_hostcheck_resampled_constant_map(HC, tmp_path):
     """A constant 5 x 3 map resampled to 8 x 4 stays constant up to rounding (the Lanczos weights are normalised): the render
     equals that of a constant 8 x 4 map."""
-    a = HC.Scene(HC.HostScene.parse_string(env_scene(HC, tmp_path, True, map_shape=(3, 5), constant=1.0))).render()[0]
-    b = HC.Scene(HC.HostScene.parse_string(env_scene(HC, tmp_path, True, map_shape=(4, 8), constant=1.0))).render()[0]
+    a = HC.Scene(HC.HostScene.parse_string(env_scene(HC, tmp_path, True, map_shape=(3, 5), constant=1.0, res=16, spp=2, strategy="power"))).render(wave_paths=300)[0]
+    b = HC.Scene(HC.HostScene.parse_string(env_scene(HC, tmp_path, True, map_shape=(4, 8), constant=1.0, res=16, spp=2, strategy="power"))).render(wave_paths=300)[0]
     assert b.mean() > 0 and np.sqrt(((a - b) ** 2).mean()) / b.mean() < 1e-3
 
 
@@ -594,7 +594,8 @@ def check_mix(P, n=1500, res=24, spp=4, wave_paths=300, threads=2):
     """Material "mix" (materials/mix.rs, reflection/scaled.rs): per-sample radiance against the oracle's ScaledBxDF
     restatement under path (FresnelSpecular glass) and the tree integrators (split specular lobes), equal counters"""
     import oracle_api
-    for integ, kw in [('"path"', dict()), ('"path"', dict(sampler="sobol", maxdepth=9)), ('"directlighting" "string strategy" ["one"]', dict()), ('"whitted"', dict())]:
+    power = '"path" "string lightsamplestrategy" ["power"]'      # no voxel table: 10 s per scene in the CPU build
+    for integ, kw in [(power, dict()), (power, dict(sampler="sobol", maxdepth=9)), ('"directlighting" "string strategy" ["one"]', dict()), ('"whitted"', dict())]:
         hs = P.HostScene.parse_string(mix_scene(P, integ, res=res, spp=spp, **kw))
         mats = [hs.desc.materials[i] for i in range(hs.desc.n_materials)]
         mixes = [m for m in mats if m.type == P.capi.PT_MAT_MIX]
@@ -647,6 +648,7 @@ def camera_scene(P, cam, lookat=None, res=24, spp=4, sampler="halton"):
     txt = P.scenes.cornell_box(res=res, spp=spp, materials="mixed", extra_lights=True, sampler=sampler)
     assert 'Camera "perspective" "float fov" [39.3077]' in txt
     txt = txt.replace('Camera "perspective" "float fov" [39.3077]', cam)
+    txt = txt.replace('Integrator "path"', 'Integrator "path" "string lightsamplestrategy" ["power"]')     # no voxel table: 10 s per scene in the CPU build
     if lookat:
         txt = txt.replace("LookAt 278 273 -800  278 273 0  0 1 0", lookat)
         txt = txt.replace('"integer yresolution" [%d]' % res, '"integer yresolution" [%d]' % (res // 2))   # lat-long: 2 x 1
