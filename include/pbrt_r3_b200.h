@@ -57,7 +57,8 @@ enum pt_light_type {          /* reference src/lights/create_light.rs:13-54 */
 enum pt_sampler_type {        /* reference src/samplers/create_sampler.rs:12-33 */
   PT_SAMPLER_HALTON = 0,      /* samplers/halton.rs */
   PT_SAMPLER_SOBOL = 1,       /* samplers/sobol.rs  */
-  PT_SAMPLER_RANDOM = 2       /* samplers/random.rs */
+  PT_SAMPLER_RANDOM = 2,      /* samplers/random.rs */
+  PT_SAMPLER_STRATIFIED = 3   /* samplers/stratified.rs (xsamples = ysamples): per-pixel tables + the tile's RNG, like random */
 };
 
 enum pt_accel_type {          /* reference src/accelerators/bvh/accel/mod.rs:4-10 */
@@ -176,9 +177,11 @@ typedef struct pt_film {      /* core/film/film.rs:64-164 */
 
 typedef struct pt_sampler {
   int32_t type;               /* pt_sampler_type */
-  int32_t samples_per_pixel;  /* as requested (sobol rounds up to a power of two itself) */
+  int32_t samples_per_pixel;  /* as requested (sobol rounds up to a power of two itself); stratified: strata * strata */
   int32_t sample_at_pixel_center; /* halton only */
-  int32_t pad;
+  int32_t strata;             /* stratified: xsamples = ysamples (samplers/stratified.rs:130-150) */
+  int32_t jitter;             /* stratified: "jitter" */
+  int32_t n_sampled_dimensions; /* stratified: "dimensions" = 1D and 2D tables per pixel; later requests draw from the RNG */
 } pt_sampler;
 
 enum pt_integrator_type {

@@ -72,6 +72,11 @@ struct Scene {
       if (desc->lights[i].type == PT_LIGHT_INFINITE) infinite_lights.push_back((int)i);
     if (desc->n_lights > 0) distrib.init(desc, world_bound, world_radius, envs.data());
     scfg = make_sampler_config(desc->sampler.type, desc->sampler.samples_per_pixel, desc->film.sample_bounds, desc->sampler.sample_at_pixel_center != 0);
+    if (desc->sampler.type == PT_SAMPLER_STRATIFIED) {  // create_stratified_sampler (stratified.rs:130-150)
+      scfg.strat_n = desc->sampler.strata;
+      scfg.strat_dims = desc->sampler.n_sampled_dimensions;
+      scfg.jitter = desc->sampler.jitter != 0;
+    }
     if (desc->integrator.type == PT_INTEGRATOR_AO) {  // AOIntegrator::new: request_2d_array(n_samples) (ao.rs:29)
       scfg.n_arrays_2d = 1;
       scfg.array_sizes_2d.assign(1, (uint32_t)desc->integrator.ao_samples);
@@ -583,7 +588,7 @@ inline void render(Scene<NC>& sc, int n_threads, int s0, int s1, float* out_rgb,
       for (int y = tile[1]; y < tile[3]; y++)
         for (int x = tile[0]; x < tile[2]; x++) {
           sampler.start_pixel(x, y);
-          const bool indexed = d->sampler.type != PT_SAMPLER_RANDOM;  // halton / sobol: sample s is a pure function of (pixel, s)
+          const bool indexed = d->sampler.type < PT_SAMPLER_RANDOM;  // halton / sobol: sample s is a pure function of (pixel, s)
           for (int s = indexed ? std::max(s0, 0) : 0; s < (indexed ? std::min(s1, spp) : spp); s++) {
             if (s > 0) sampler.set_sample_number(s);
             CameraSample cs;

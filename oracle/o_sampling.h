@@ -175,6 +175,9 @@ struct SamplerConfig {
   // sample arrays the integrator requested (base_sampler.rs:32-44): ambientocclusion one 2D array, directlighting two per light
   uint32_t n_arrays_1d, n_arrays_2d;
   std::vector<uint32_t> array_sizes_2d;  // n of each requested 2D array, in request order (random sampler: its own values per array)
+  // stratified (samplers/stratified.rs:15-30): xsamples = ysamples strata per axis, jitter, n_sampled_dimensions tables
+  int strat_n = 0, strat_dims = 0;
+  bool jitter = true;
 };
 
 inline uint64_t math_mod(int64_t a, int64_t b) {  // halton.rs:22-29
@@ -232,6 +235,48 @@ struct Sampler {
   int64_t halton_offset;
   uint32_t array2d_offset = 0;  // get_2d_array calls so far in this sample (base_sampler.rs:59-70)
   std::vector<std::vector<Vec2>> random_arrays;  // RandomSampler: sample_array2d, refilled by every start_pixel (random.rs:46-60)
+  // PixelSampler tables (core/sampler/pixel_sampler.rs:10-16): [dimension][sample of the pixel]
+  std::vector<std::vector<Float>> samples1d;
+  std::vector<std::vector<Vec2>> samples2d;
+  uint32_t current1d = 0, current2d = 0;
+  template <class T> void shuffle(T* v, size_t count) {  // shuffle_array with one dimension (sampling.rs:4-15)
+    for (size_t i = 0; i < count; i++) { size_t other = i + rng.uniform_uint32((uint32_t)(count - i)); std::swap(v[i], v[other]); }
+  }
+  void stratified_start_pixel() {  // stratified.rs:33-88
+    const size_t spp = (size_t)cfg->spp;
+    samples1d.assign((size_t)cfg->strat_dims, std::vector<Float>(spp));
+    samples2d.assign((size_t)cfg->strat_dims, std::vector<Vec2>(spp));
+    for (auto& t : samples1d) {  // stratified_sample_1d (sampling.rs:17-23) + shuffle
+      Float inv = 1.0f / (Float)spp;
+      for (size_t i = 0; i < spp; i++) { Float delta = cfg->jitter ? rng.uniform_float() : 0.5f; t[i] = std::min(((Float)i + delta) * inv, ONE_MINUS_EPSILON); }
+      shuffle(t.data(), spp);
+    }
+    for (auto& t : samples2d) {  // stratified_sample_2d (sampling.rs:25-44; xsamples == ysamples) + shuffle
+      const int n = cfg->strat_n;
+      Float dx = 1.0f / (Float)n, dy = 1.0f / (Float)n;
+      for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++) {
+          Float jx = cfg->jitter ? rng.uniform_float() : 0.5f;
+          Float jy = cfg->jitter ? rng.uniform_float() : 0.5f;
+          t[(size_t)(y * n + x)] = Vec2(std::min(((Float)x + jx) * dx, ONE_MINUS_EPSILON), std::min(((Float)y + jy) * dy, ONE_MINUS_EPSILON));
+        }
+      shuffle(t.data(), spp);
+    }
+    random_arrays.resize(cfg->array_sizes_2d.size());  // the 2D arrays: one Latin hypercube per sample (stratified.rs:72-82, sampling.rs:46-81)
+    for (size_t a = 0; a < random_arrays.size(); a++) {
+      const size_t n = cfg->array_sizes_2d[a];
+      random_arrays[a].assign(n * spp, Vec2(0, 0));
+      for (size_t j = 0; j < spp; j++) {
+        std::vector<Float> v(2 * n);
+        Float inv = 1.0f / (Float)n;
+        for (size_t i = 0; i < n; i++)
+          for (size_t k = 0; k < 2; k++) { Float sj = ((Float)i + rng.uniform_float()) * inv; v[2 * i + k] = std::min(sj, ONE_MINUS_EPSILON); }
+        for (size_t k = 0; k < 2; k++)
+          for (size_t i = 0; i < n; i++) { size_t other = i + rng.uniform_uint32((uint32_t)(n - i)); std::swap(v[2 * i + k], v[2 * other + k]); }
+        for (size_t i = 0; i < n; i++) random_arrays[a][j * n + i] = Vec2(v[2 * i], v[2 * i + 1]);
+      }
+    }
+  }
 
   Sampler(const SamplerConfig* c, uint32_t tile_seed) : cfg(c), px(0), py(0), sample_num(0), interval_index(0), dimension(0), rng((uint64_t)tile_seed), halton_offset(0) {}
 
@@ -242,6 +287,8 @@ struct Sampler {
   }
   void start_pixel(int x, int y) {
     px = x; py = y; sample_num = 0; dimension = 0; array2d_offset = 0;
+    current1d = current2d = 0;
+    if (cfg->type == 3) { stratified_start_pixel(); return; }
     if (cfg->type == 2 && !cfg->array_sizes_2d.empty()) {  // random.rs:46-60: every element of every array, in order, before the first sample
       random_arrays.resize(cfg->array_sizes_2d.size());
       for (size_t a = 0; a < random_arrays.size(); a++) {
@@ -267,6 +314,7 @@ struct Sampler {
   }
   bool set_sample_number(int64_t n) {
     sample_num = n; dimension = 0; array2d_offset = 0;
+    current1d = current2d = 0;
     interval_index = index_for_sample(n);
     return n < cfg->spp;
   }
@@ -304,7 +352,7 @@ struct Sampler {
   }
   // element i of the array handed out by the k-th get_2d_array call of this sample (k = 0, 1, ..)
   Vec2 array_2d_elem_of(uint32_t k, uint32_t n, uint32_t i) const {
-    if (cfg->type == 2) return random_arrays[k][(size_t)n * (size_t)sample_num + i];
+    if (cfg->type >= 2) return random_arrays[k][(size_t)n * (size_t)sample_num + i];
     return array_2d_elem(n, i);
   }
   Vec2 array_2d_elem(uint32_t n, uint32_t i) const {
@@ -313,6 +361,10 @@ struct Sampler {
     return Vec2(sample_dimension(index, dim), sample_dimension(index, dim + 1));
   }
   Float get_1d() {
+    if (cfg->type == 3) {  // BasePixelSampler::get_1d (pixel_sampler.rs:53-64)
+      if (current1d < samples1d.size()) return samples1d[current1d++][(size_t)sample_num];
+      return rng.uniform_float();
+    }
     if (cfg->type == 2) return rng.uniform_float();
     if (dimension >= 5u && dimension < array_end_dim()) dimension = array_end_dim();
     Float x = sample_dimension(interval_index, dimension);
@@ -320,7 +372,8 @@ struct Sampler {
     return x;
   }
   Vec2 get_2d() {
-    if (cfg->type == 2) { Float a = rng.uniform_float(); Float b = rng.uniform_float(); return Vec2(a, b); }
+    if (cfg->type == 3 && current2d < samples2d.size()) return samples2d[current2d++][(size_t)sample_num];  // pixel_sampler.rs:66-77
+    if (cfg->type >= 2) { Float a = rng.uniform_float(); Float b = rng.uniform_float(); return Vec2(a, b); }
     if (dimension + 1u >= 5u && dimension < array_end_dim()) dimension = array_end_dim();
     Float x = sample_dimension(interval_index, dimension);
     Float y = sample_dimension(interval_index, dimension + 1);

@@ -183,7 +183,7 @@ int orc_intersect_p(orc_scene* s, const float* rays, uint32_t n, uint8_t* occlud
 
 int orc_sampler_values(orc_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, uint32_t dim0, uint32_t ndims, float* out) {
   const SamplerConfig& cfg = s->nc == 3 ? s->s3->scfg : s->s60->scfg;
-  if (cfg.type == PT_SAMPLER_RANDOM) { g_err = "random sampler has no index-based stream"; return 1; }
+  if (cfg.type >= PT_SAMPLER_RANDOM) { g_err = "random / stratified samplers have no index-based stream"; return 1; }
   for (uint32_t i = 0; i < n; i++) {
     Sampler sm(&cfg, 0);
     sm.start_pixel(pixel_xy[2 * i], pixel_xy[2 * i + 1]);

@@ -592,7 +592,9 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   }
   H.tile_arrays = nullptr;
   H.tile_arr_stride = 0u;
-  if (D->sampler.type == PT_SAMPLER_RANDOM) {  // floats per tile of the random sampler's 2D sample arrays (build_pixlist allocates them)
+  H.tile_tab = 0u;
+  H.tile_sample = nullptr;
+  if (D->sampler.type >= PT_SAMPLER_RANDOM) {  // floats per tile of the random / stratified samplers' tables and 2D sample arrays (build_pixlist allocates them)
     uint64_t elems = 0;
     if (D->integrator.type == PT_INTEGRATOR_AO) elems = (uint64_t)std::max(D->integrator.ao_samples, 0);
     if (D->integrator.type == PT_INTEGRATOR_DIRECT && D->integrator.direct_strategy == PT_DIRECT_ALL) {
@@ -600,6 +602,10 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
       elems *= (uint64_t)std::max(D->integrator.max_depth, 0);
     }
     elems *= 2ull * (uint64_t)std::max(D->sampler.samples_per_pixel, 0);
+    if (D->sampler.type == PT_SAMPLER_STRATIFIED) {
+      H.tile_tab = 3u * (uint32_t)std::max(D->sampler.n_sampled_dimensions, 0) * (uint32_t)std::max(D->sampler.samples_per_pixel, 0);
+      elems += H.tile_tab;
+    }
     if (elems > (1ull << 24)) { pt_set_error("Sampler \"random\": the integrator's sample arrays exceed 16M values per pixel"); return 1; }
     H.tile_arr_stride = (uint32_t)elems;
   }
@@ -612,6 +618,12 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   SD.type = D->sampler.type;
   SD.spp = D->sampler.samples_per_pixel;
   SD.at_center = D->sampler.sample_at_pixel_center;
+  SD.nd = D->sampler.n_sampled_dimensions; SD.strata = D->sampler.strata; SD.jitter = D->sampler.jitter;
+  SD.inc2d = 2u; SD.x2d = 0u; SD.y2d = 1u;
+  if (SD.type == PT_SAMPLER_STRATIFIED) {
+    if (SD.strata < 1 || SD.strata * SD.strata != SD.spp || SD.nd < 0 || SD.nd > 64) { pt_set_error("pt_sampler: stratified needs strata^2 = samples_per_pixel, 0 <= n_sampled_dimensions <= 64"); return 1; }
+    SD.inc2d = 0x10000u; SD.x2d = 0x4000u; SD.y2d = 0x8000u;
+  }
   for (int i = 0; i < 4; i++) SD.sb[i] = D->film.sample_bounds[i];
   if (SD.sb[2] - SD.sb[0] >= 65536 || SD.sb[3] - SD.sb[1] >= 32768) { pt_set_error("film too large for packed pixel ids"); return 1; }
   {
@@ -1024,13 +1036,15 @@ int build_pixlist(pt_scene* s, int shard_index, int shard_count, int tile) {
   CK(s->pix_bufs->upload(px.data(), px.size(), &dp));
   s->tiles = nullptr;
   s->h.tile_rng = nullptr;
-  if (s->h.sampler.type == PT_SAMPLER_RANDOM && !s->tiles_host.empty()) {
+  s->h.tile_sample = nullptr;
+  if (s->h.sampler.type >= PT_SAMPLER_RANDOM && !s->tiles_host.empty()) {
     const int* dt = nullptr;
     CK(s->pix_bufs->upload(s->tiles_host.data(), s->tiles_host.size(), &dt));
     s->tiles = (int*)dt;
     CK(s->pix_bufs->alloc(s->tiles_host.size() / 3, &s->h.tile_rng));
     s->h.tile_arrays = nullptr;
     if (s->h.tile_arr_stride) CK(s->pix_bufs->alloc(s->tiles_host.size() / 3 * (size_t)s->h.tile_arr_stride, &s->h.tile_arrays));
+    if (s->h.sampler.type == PT_SAMPLER_STRATIFIED) CK(s->pix_bufs->alloc(s->tiles_host.size() / 3, &s->h.tile_sample));
   }
   s->pixlist = (int*)dp;
   s->pix_n = (uint32_t)px.size();
@@ -1493,7 +1507,7 @@ int pt_render_partial(pt_scene* s, const pt_render_opts* opts, float** dev_film_
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, s->stream));
   int rc;
-  if (s->h.sampler.type == PT_SAMPLER_RANDOM) rc = s->h.n_channels == 3 ? render_waves_random<3>(s, opts, stats) : render_waves_random<PT_NCS>(s, opts, stats);
+  if (s->h.sampler.type >= PT_SAMPLER_RANDOM) rc = s->h.n_channels == 3 ? render_waves_random<3>(s, opts, stats) : render_waves_random<PT_NCS>(s, opts, stats);
   else rc = s->h.n_channels == 3 ? render_waves<3>(s, opts, stats) : render_waves<PT_NCS>(s, opts, stats);
   if (rc) {
     cudaEventDestroy(e0);
@@ -1609,7 +1623,7 @@ int pt_intersect_device(pt_scene* s, const void* dev_o_tmax, const void* dev_d_t
 int pt_sampler_values(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, uint32_t dim0, uint32_t ndims, float* out) {
   if (!s || !pixel_xy || !sample_num || !out) { pt_set_error("null argument"); return 1; }
   CK(cudaSetDevice(s->device));
-  if (s->h.sampler.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\" has no index-based stream: only pt_render reproduces it (per-tile sequential PCG32)"); return 1; }
+  if (s->h.sampler.type >= PT_SAMPLER_RANDOM) { pt_set_error("Samplers \"random\" / \"stratified\" have no index-based stream: only pt_render reproduces them (per-tile sequential PCG32)"); return 1; }
   if (n == 0 || ndims == 0) return 0;
   DevBufs B;
   const int *pxy, *sn;
@@ -1648,7 +1662,7 @@ static int run_list(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_
 int pt_camera_rays(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, float* rays, float* p_film) {
   if (!s || !pixel_xy || !sample_num || !rays) { pt_set_error("null argument"); return 1; }
   CK(cudaSetDevice(s->device));
-  if (s->h.sampler.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\" has no index-based stream: only pt_render reproduces it (per-tile sequential PCG32)"); return 1; }
+  if (s->h.sampler.type >= PT_SAMPLER_RANDOM) { pt_set_error("Samplers \"random\" / \"stratified\" have no index-based stream: only pt_render reproduces them (per-tile sequential PCG32)"); return 1; }
   if (n == 0) return 0;
   if (run_list(s, pixel_xy, sample_num, n, false)) return 1;
   std::vector<f4> o(n), d(n);
@@ -1667,7 +1681,7 @@ int pt_camera_rays(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_n
 int pt_li(pt_scene* s, const int32_t* pixel_xy, const int32_t* sample_num, uint32_t n, float* out_l) {
   if (!s || !pixel_xy || !sample_num || !out_l) { pt_set_error("null argument"); return 1; }
   CK(cudaSetDevice(s->device));
-  if (s->h.sampler.type == PT_SAMPLER_RANDOM) { pt_set_error("Sampler \"random\" has no index-based stream: only pt_render reproduces it (per-tile sequential PCG32)"); return 1; }
+  if (s->h.sampler.type >= PT_SAMPLER_RANDOM) { pt_set_error("Samplers \"random\" / \"stratified\" have no index-based stream: only pt_render reproduces them (per-tile sequential PCG32)"); return 1; }
   if (n == 0) return 0;
   if (run_list(s, pixel_xy, sample_num, n, true)) return 1;
   const uint32_t NC = s->h.n_channels, cap = s->W.cap;

@@ -184,9 +184,83 @@ PT_HD float random_draw(const DScene& S, uint32_t tile_slot, uint64_t tile_seq) 
   uint32_t r = (xs >> rot) | (xs << ((~rot + 1u) & 31u));
   return fminf(PT_ONE_MINUS_EPS, (float)r * 2.3283064365386963e-10f);
 }
+PT_HD uint32_t random_u32(const DScene& S, uint32_t tile_slot, uint64_t tile_seq) {
+  uint64_t old = S.tile_rng[tile_slot];
+  S.tile_rng[tile_slot] = old * 0x5851f42d4c957f2dULL + ((tile_seq << 1) | 1ull);
+  uint32_t xs = (uint32_t)(((old >> 18) ^ old) >> 27);
+  uint32_t rot = (uint32_t)(old >> 59);
+  return (xs >> rot) | (xs << ((~rot + 1u) & 31u));
+}
+PT_HD uint32_t random_bounded(const DScene& S, uint32_t tile_slot, uint64_t tile_seq, uint32_t b) {  // RNG::uniform_uint32_threshold (rng.rs:46-54)
+  const uint32_t threshold = (~b + 1u) % b;
+  for (;;) {
+    uint32_t r = random_u32(S, tile_slot, tile_seq);
+    if (r >= threshold) return r % b;
+  }
+}
+// StratifiedSampler::start_pixel (stratified.rs:33-88) for the tile's next pixel: the 1D tables (stratified + shuffled), the
+// 2D tables, then one Latin hypercube per sample for every requested 2D array (n_arr arrays of arr_n[a] elements per sample;
+// arr_n = null: one array of arr_n0).  Layout: [nd][spp] | [nd][spp][2] | arrays in request order, [spp][n][2] each.
+PT_HD void stratified_start_pixel(const DScene& S, uint32_t tile_slot, uint64_t seq, uint32_t n_arr, const uint32_t* arr_prefix, uint32_t arr_n0) {
+  const SamplerDev& c = S.sampler;
+  const uint32_t spp = (uint32_t)c.spp, nd = (uint32_t)c.nd;
+  float* t = S.tile_arrays + (size_t)tile_slot * S.tile_arr_stride;
+  const float inv = 1.0f / (float)spp;
+  for (uint32_t d = 0; d < nd; d++, t += spp) {
+    for (uint32_t i = 0; i < spp; i++) { float delta = c.jitter ? random_draw(S, tile_slot, seq) : 0.5f; t[i] = fminf(((float)i + delta) * inv, PT_ONE_MINUS_EPS); }
+    for (uint32_t i = 0; i < spp; i++) { uint32_t o = i + random_bounded(S, tile_slot, seq, spp - i); float a = t[i]; t[i] = t[o]; t[o] = a; }
+  }
+  const uint32_t n = (uint32_t)c.strata;
+  const float dx = 1.0f / (float)n;
+  for (uint32_t d = 0; d < nd; d++, t += 2u * spp) {
+    for (uint32_t y = 0; y < n; y++)
+      for (uint32_t x = 0; x < n; x++) {
+        float jx = c.jitter ? random_draw(S, tile_slot, seq) : 0.5f;
+        float jy = c.jitter ? random_draw(S, tile_slot, seq) : 0.5f;
+        t[2u * (y * n + x)] = fminf(((float)x + jx) * dx, PT_ONE_MINUS_EPS);
+        t[2u * (y * n + x) + 1u] = fminf(((float)y + jy) * dx, PT_ONE_MINUS_EPS);
+      }
+    for (uint32_t i = 0; i < spp; i++) {
+      uint32_t o = i + random_bounded(S, tile_slot, seq, spp - i);
+      float a = t[2u * i], b = t[2u * i + 1u];
+      t[2u * i] = t[2u * o]; t[2u * i + 1u] = t[2u * o + 1u];
+      t[2u * o] = a; t[2u * o + 1u] = b;
+    }
+  }
+  for (uint32_t a = 0; a < n_arr; a++) {  // latin_hypercube_2d per sample (sampling.rs:46-81)
+    // arr_prefix (directlighting): prefix sums of the lights' n_samples; arrays come in pairs (u_light, u_scattering) per light
+    const uint32_t nl = arr_prefix ? (n_arr / 2u) / (uint32_t)S.integrator.max_depth : 0u;
+    const uint32_t j = arr_prefix ? (a / 2u) % nl : 0u;
+    const uint32_t na = arr_prefix ? arr_prefix[j + 1u] - arr_prefix[j] : arr_n0;
+    const float inva = 1.0f / (float)na;
+    for (uint32_t s = 0; s < spp; s++, t += 2u * na) {
+      for (uint32_t i = 0; i < na; i++)
+        for (uint32_t k = 0; k < 2u; k++) t[2u * i + k] = fminf(((float)i + random_draw(S, tile_slot, seq)) * inva, PT_ONE_MINUS_EPS);
+      for (uint32_t k = 0; k < 2u; k++)
+        for (uint32_t i = 0; i < na; i++) {
+          uint32_t o = i + random_bounded(S, tile_slot, seq, na - i);
+          float v = t[2u * i + k]; t[2u * i + k] = t[2u * o + k]; t[2u * o + k] = v;
+        }
+    }
+  }
+}
+// BasePixelSampler::get_1d / get_2d (pixel_sampler.rs:53-77): dim = requests so far (1D low half, 2D high half) + which value
+PT_HD float stratified_dim(const DScene& S, int64_t index, uint32_t dim) {
+  const uint32_t tile = (uint32_t)((uint64_t)index >> 32), nd = (uint32_t)S.sampler.nd, spp = (uint32_t)S.sampler.spp;
+  const float* t = S.tile_arrays + (size_t)tile * S.tile_arr_stride;
+  if (dim & 0xc000u) {
+    const uint32_t d2 = dim >> 16;
+    if (d2 < nd) return t[nd * spp + 2u * (d2 * spp + S.tile_sample[tile]) + ((dim & 0x8000u) ? 1u : 0u)];
+  } else {
+    const uint32_t d1 = dim & 0x3fffu;
+    if (d1 < nd) return t[d1 * spp + S.tile_sample[tile]];
+  }
+  return random_draw(S, tile, (uint64_t)(uint32_t)index);
+}
 PT_HDN float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, int py) {
   const SamplerDev& c = S.sampler;
   if (c.type == PT_SAMPLER_RANDOM) return random_draw(S, (uint32_t)((uint64_t)index >> 32), (uint64_t)(uint32_t)index);
+  if (c.type == PT_SAMPLER_STRATIFIED) return stratified_dim(S, index, dim);
   if (c.type == PT_SAMPLER_HALTON) {  // halton.rs:149-162
     if (c.at_center && dim < 2) return 0.5f;
     if (dim == 0) return radical_inverse2((uint64_t)(index >> c.base_exponents[0]));
@@ -218,9 +292,9 @@ PT_HD float get1d(const DScene& S, SampleStream& st) {
   return v;
 }
 PT_HD f2 get2d(const DScene& S, SampleStream& st) {
-  float a = sampler_dim(S, st.index, st.dim, st.px, st.py);
-  float b = sampler_dim(S, st.index, st.dim + 1, st.px, st.py);
-  st.dim += 2;
+  float a = sampler_dim(S, st.index, st.dim + S.sampler.x2d, st.px, st.py);
+  float b = sampler_dim(S, st.index, st.dim + S.sampler.y2d, st.px, st.py);
+  st.dim += S.sampler.inc2d;
   return mk2(a, b);
 }
 

@@ -57,6 +57,11 @@ struct SamplerDev {     // samplers/{halton,sobol}.rs state that is constant ove
   int32_t at_center;
   int32_t base_scales[2], base_exponents[2], sample_stride, mult_inverse[2];
   uint32_t resolution, log2_resolution;
+  // Sampler "stratified" (a PixelSampler, core/sampler/pixel_sampler.rs): SampleStream::dim holds the 1D requests so far in its
+  // low half and the 2D requests in its high half; the first `nd` of each read the pixel's tables, later ones the tile's RNG.
+  // inc2d / x2d / y2d: what get2d adds to dim (2, 0, 1 for the index-based samplers: kernel-parameter constants either way)
+  int32_t nd, strata, jitter;
+  uint32_t inc2d, x2d, y2d;
 };
 
 struct LightDistDev {   // dense restatement of SpatialLightDistribution's hash table (a pure function of the voxel)
@@ -147,6 +152,10 @@ struct DScene {
   // requested array before the pixel's first sample (random.rs:46-60); tile_arr_stride floats per tile, refilled per pixel
   float* tile_arrays;
   uint32_t tile_arr_stride;
+  // Sampler "stratified": the tile buffer starts with the pixel's tables ([nd][spp] 1D values, [nd][spp] 2D pairs; tile_tab
+  // floats), the sample arrays follow; tile_sample = sample number of the tile's path in flight
+  uint32_t tile_tab;
+  uint32_t* tile_sample;
 };
 
 }  // namespace ptd

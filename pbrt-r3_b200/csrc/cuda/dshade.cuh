@@ -751,8 +751,8 @@ PT_HD void ao_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i) {
       const int pk = W.pix[i];
       const int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
       f2 u;
-      if (S.sampler.type == PT_SAMPLER_RANDOM) {  // element round of this sample's slice of the pixel's array
-        const float* a = S.tile_arrays + (size_t)((uint64_t)W.sindex[i] >> 32) * S.tile_arr_stride + 2u * (uint32_t)(ns * W.sample_num[i] + round);
+      if (S.sampler.type >= PT_SAMPLER_RANDOM) {  // element round of this sample's slice of the pixel's array
+        const float* a = S.tile_arrays + (size_t)((uint64_t)W.sindex[i] >> 32) * S.tile_arr_stride + S.tile_tab + 2u * (uint32_t)(ns * W.sample_num[i] + round);
         u = mk2(a[0], a[1]);
       } else {
         const int64_t idx = sampler_index(S, px, py, (int64_t)ns * (int64_t)W.sample_num[i] + (int64_t)round);
@@ -820,7 +820,7 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
   uint32_t arr_off = W.arr_off[i];
   {  // GlobalSampler: get_1d / get_2d skip the dimensions of the sample arrays, [5, 5 + 2 x arrays) (halton.rs:227-231, 241-245)
     const uint32_t n_arrays = (!whitted && S.integrator.direct_strategy == PT_DIRECT_ALL) ? 2u * S.n_lights * (uint32_t)S.integrator.max_depth : 0u;
-    if (st.dim < 5u + 2u * n_arrays) st.dim = 5u + 2u * n_arrays;
+    if (S.sampler.type < PT_SAMPLER_RANDOM && st.dim < 5u + 2u * n_arrays) st.dim = 5u + 2u * n_arrays;
   }
   const float rtime = rd4.w;
   bool push_sh = false, push_mis = false, push_ext = false, push_wait = false;
@@ -892,12 +892,12 @@ PT_HD void ri_body(const DScene& S, WaveState& W, Queues& Q, uint32_t i, bool fr
           }
           ln = (int)lo;
           const uint32_t n = (uint32_t)S.lights[ln].n_samples, k = round - ldg(S.light_sample_prefix + lo);
-          if (S.sampler.type == PT_SAMPLER_RANDOM) {
+          if (S.sampler.type >= PT_SAMPLER_RANDOM) {
             // arrays are laid out in request order: per depth, per light, (u_light, u_scattering), n x spp elements each;
             // this vertex holds arrays arr_off - 2 nl .. arr_off
             const uint32_t spp = (uint32_t)S.sampler.spp, d = (arr_off - 2u * nl) / (2u * nl);
             const uint32_t e0 = spp * (d * 2u * ldg(S.light_sample_prefix + nl) + 2u * ldg(S.light_sample_prefix + lo)) + n * (uint32_t)W.sample_num[i] + k;
-            const float* a = S.tile_arrays + (size_t)((uint64_t)st.index >> 32) * S.tile_arr_stride;
+            const float* a = S.tile_arrays + (size_t)((uint64_t)st.index >> 32) * S.tile_arr_stride + S.tile_tab;
             u_light = mk2(a[2u * e0], a[2u * e0 + 1u]);
             u_scat = mk2(a[2u * (e0 + spp * n)], a[2u * (e0 + spp * n) + 1u]);
           } else {

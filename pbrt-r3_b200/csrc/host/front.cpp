@@ -1143,10 +1143,23 @@ struct Builder {
     if (sampler_name == "halton") { S.type = PT_SAMPLER_HALTON; S.samples_per_pixel = sampler_params.one_int("pixelsamples", 16); }
     else if (sampler_name == "sobol") { S.type = PT_SAMPLER_SOBOL; S.samples_per_pixel = sampler_params.one_int("pixelsamples", 16); }
     else if (sampler_name == "random") { S.type = PT_SAMPLER_RANDOM; S.samples_per_pixel = sampler_params.one_int("pixelsamples", 4); }
-    else throw ParseError("Sampler \"" + sampler_name + "\" is not supported on the GPU path (halton, sobol, random)");
+    else if (sampler_name == "stratified") {  // create_stratified_sampler (stratified.rs:130-150)
+      S.type = PT_SAMPLER_STRATIFIED;
+      S.jitter = sampler_params.one_bool("jitter", true) ? 1 : 0;
+      int xs = sampler_params.one_int("xsamples", 4), ys = sampler_params.one_int("ysamples", 4);
+      S.n_sampled_dimensions = sampler_params.one_int("dimensions", 4);
+      if (pt_current_options().quick_render) xs = ys = 1;
+      // stratified_sample_2d loops x over 0..ny (sampling.rs:34-36): with xsamples != ysamples the reference leaves table entries
+      // of the previous pixel in place (or indexes out of bounds); only the square case is reproduced
+      if (xs != ys) throw ParseError("Sampler \"stratified\": xsamples != ysamples is not supported on the GPU path");
+      if (xs < 1 || xs > 64 || S.n_sampled_dimensions < 0 || S.n_sampled_dimensions > 64) throw ParseError("Sampler \"stratified\": xsamples / dimensions out of range (1..64, 0..64)");
+      S.strata = xs;
+      S.samples_per_pixel = xs * ys;
+    }
+    else throw ParseError("Sampler \"" + sampler_name + "\" is not supported on the GPU path (halton, sobol, random, stratified)");
     S.sample_at_pixel_center = sampler_params.one_bool("samplepixelcenter", false) ? 1 : 0;
-    if (pixelsamples_override > 0) S.samples_per_pixel = pixelsamples_override;  // pbrt.rs:234-238 (replace_params_int before the factory runs)
-    if (pt_current_options().quick_render && S.type != PT_SAMPLER_RANDOM) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
+    if (pixelsamples_override > 0 && S.type != PT_SAMPLER_STRATIFIED) S.samples_per_pixel = pixelsamples_override;  // pbrt.rs:234-238 (replace_params_int before the factory runs)
+    if (pt_current_options().quick_render && S.type < PT_SAMPLER_RANDOM) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
 
     // Integrator (integrators/path.rs:252-271)
     if (integrator_name != "path" && integrator_name != "aov" && integrator_name != "ambientocclusion" && integrator_name != "directlighting" && integrator_name != "whitted")

@@ -26,7 +26,7 @@ def shard_opts(sampler_type, spp_total, rank, world):
     shard the sample numbers (of the EFFECTIVE count, see effective_spp).  Sampler "random" draws from one sequential
     PCG32 stream per 16x16 render tile (samplers/random.rs), so only whole tiles can be split: interleave the tiles
     across ranks."""
-    if int(sampler_type) == 2:   # PT_SAMPLER_RANDOM
+    if int(sampler_type) >= 2:   # PT_SAMPLER_RANDOM, PT_SAMPLER_STRATIFIED
         return {"shard_index": int(rank), "shard_count": int(world)}
     b, e = spp_shard(effective_spp(sampler_type, spp_total), rank, world)
     return {"spp_begin": b, "spp_end": e}

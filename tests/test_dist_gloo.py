@@ -15,7 +15,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _scene_text(P, sampler, spp):
-    txt = P.scenes.cornell_box(res=32, spp=spp, sampler=sampler)
+    txt = P.scenes.cornell_box(res=32, spp=spp, sampler="halton" if sampler == "stratified" else sampler)
+    if sampler == "stratified":      # spp = strata^2; tiles are interleaved over the ranks like the random sampler's
+        from test_hostcheck import stratified_variant
+        txt = stratified_variant(txt, strata=int(round(spp ** 0.5)))
     # the serial host build of the 64^3-voxel light table is irrelevant here
     return txt.replace('Integrator "path"', 'Integrator "path" "string lightsamplestrategy" ["power"]')
 
@@ -58,6 +61,7 @@ def test_shard_opts_by_sampler():
     assert D.shard_opts(0, 64, 1, 4) == {"spp_begin": 16, "spp_end": 32}
     assert D.shard_opts(1, 64, 3, 4) == {"spp_begin": 48, "spp_end": 64}
     assert D.shard_opts(2, 64, 1, 4) == {"shard_index": 1, "shard_count": 4}
+    assert D.shard_opts(3, 16, 2, 4) == {"shard_index": 2, "shard_count": 4}      # stratified: per-tile streams too
     # Sobol takes the next power of two (sobol.rs:24): 6 requested = 8 rendered, and all 8 are sharded
     assert D.effective_spp(1, 6) == 8 and D.effective_spp(0, 6) == 6
     assert [D.shard_opts(1, 6, r, 2) for r in range(2)] == [{"spp_begin": 0, "spp_end": 4}, {"spp_begin": 4, "spp_end": 8}]
@@ -66,7 +70,7 @@ def test_shard_opts_by_sampler():
 import pytest
 
 
-@pytest.mark.parametrize("sampler,spp", [("halton", 8), ("sobol", 6), ("random", 2)])
+@pytest.mark.parametrize("sampler,spp", [("halton", 8), ("sobol", 6), ("random", 2), ("stratified", 4)])
 def test_two_rank_film_reduce_matches_single_process(HC, tmp_path, sampler, spp):
     import oracle_api
     P = HC

@@ -247,6 +247,13 @@ def test_mix_material(P):
     check_mix(P, n=20000, res=72, spp=4, wave_paths=3000, threads=0)
 
 
+def test_stratified_sampler(P):
+    """Sampler "stratified": per-pixel shuffled tables, the tile's PCG32 stream after them, Latin-hypercube sample arrays
+    (path / ambientocclusion / directlighting all / whitted): image and counters equal to the oracle's."""
+    from test_hostcheck import check_stratified
+    check_stratified(P, res=72, threads=0)
+
+
 def test_map_lights(P, tmp_path):
     """LightSource "projection" / "goniometric": per-sample radiance against the oracle (acos / atan2 are CUDA's: 99.5 % of the
     samples within 1e-4), equal counters, image."""

@@ -221,6 +221,23 @@ def test_front_end_mix_material(P):
         P.HostScene.parse_string(base % 'MakeNamedMaterial "n" "string type" ["none"]\nMaterial "mix" "string namedmaterial1" ["n"] "string namedmaterial2" ["b"]')
 
 
+def test_front_end_stratified_sampler(P):
+    """create_stratified_sampler (stratified.rs:130-150): defaults 4 x 4, jitter, 4 dimensions; --quick = 1 x 1"""
+    base = 'Camera "perspective"\n%s\nWorldBegin\nWorldEnd\n'
+    S = P.HostScene.parse_string(base % 'Sampler "stratified"').desc.sampler
+    assert (S.type, S.samples_per_pixel, S.strata, S.jitter, S.n_sampled_dimensions) == (P.capi.PT_SAMPLER_STRATIFIED, 16, 4, 1, 4)
+    S = P.HostScene.parse_string(base % 'Sampler "stratified" "integer xsamples" [3] "integer ysamples" [3] "bool jitter" ["false"] "integer dimensions" [7]').desc.sampler
+    assert (S.samples_per_pixel, S.strata, S.jitter, S.n_sampled_dimensions) == (9, 3, 0, 7)
+    with pytest.raises(P.PbrtError):       # the reference's 2D stratification loops x over ysamples: only the square case is reproduced
+        P.HostScene.parse_string(base % 'Sampler "stratified" "integer xsamples" [2] "integer ysamples" [3]')
+    lib = P.capi.load()
+    lib.pt_set_options(P.capi.pt_options(1, 0))
+    try:
+        assert P.HostScene.parse_string(base % 'Sampler "stratified"').desc.sampler.samples_per_pixel == 1
+    finally:
+        lib.pt_set_options(P.capi.pt_options(0, 0))
+
+
 def test_front_end_cameras(P):
     """orthographic.rs:193-253 / environment.rs:90-151: same parameters as the perspective camera; Transform::orthographic(0, 1)
     is the identity, so raster_to_camera maps the raster onto the screen window at z = 0"""
@@ -598,7 +615,7 @@ def test_front_end_instances(P):
 
 
 def test_front_end_errors(P):
-    for bad in ['Shape "sphere"', 'WorldBegin\nLightSource "laser"', 'Sampler "stratified"\nWorldBegin\nWorldEnd', 'Bogus 1 2 3']:
+    for bad in ['Shape "sphere"', 'WorldBegin\nLightSource "laser"', 'Sampler "maxmindist"\nWorldBegin\nWorldEnd', 'Bogus 1 2 3']:
         with pytest.raises(P.PbrtError):
             P.HostScene.parse_string('Camera "perspective"\n' + bad + "\n")
 

@@ -349,6 +349,44 @@ def test_hostcheck_ao_random_sampler(HC):
     check_ao_random(HC)
 
 
+def stratified_variant(txt, strata=2, dims=4, jitter=True):
+    """the scene text with Sampler "stratified" (strata x strata samples per pixel) in place of its sampler"""
+    lines = txt.split("\n")
+    k = [i for i, l in enumerate(lines) if l.startswith("Sampler ")][0]
+    lines[k] = 'Sampler "stratified" "integer xsamples" [%d] "integer ysamples" [%d] "integer dimensions" [%d] "bool jitter" ["%s"]' % (strata, strata, dims, "true" if jitter else "false")
+    return "\n".join(lines)
+
+
+def check_stratified(P, res=33, threads=2):
+    """Sampler "stratified" (samplers/stratified.rs, core/sampler/pixel_sampler.rs): the pixel's shuffled 1D / 2D tables for the
+    first `dimensions` requests of each kind, the tile's PCG32 stream afterwards, Latin-hypercube sample arrays for
+    ambientocclusion and directlighting "all" - drawn on the device in the reference's order: image and counters equal to
+    the oracle's (a 33-pixel image has partial tiles)"""
+    import oracle_api
+    power = 'Integrator "path" "string lightsamplestrategy" ["power"]'
+    cases = [(P.scenes.cornell_box(res=res, spp=4, materials="mixed", extra_lights=True).replace('Integrator "path"', power), dict(strata=2)),
+             (P.scenes.cornell_box(res=res, spp=4, materials="mixed", extra_lights=True).replace('Integrator "path"', power), dict(strata=3, dims=1, jitter=False)),
+             (P.scenes.cornell_box(res=res, spp=4, materials="mixed").replace('Integrator "path"', power), dict(strata=1, dims=0)),
+             (ao_scene(P, res=res, spp=4, nsamples=5), dict(strata=2)),
+             (tree_scene(P, '"directlighting"', res=res, spp=4, nsamples=3), dict(strata=2, dims=2)),
+             (tree_scene(P, '"whitted"', res=res, spp=4), dict(strata=2))]
+    for txt, kw in cases:
+        hs = P.HostScene.parse_string(stratified_variant(txt, **kw))
+        S = hs.desc.sampler
+        assert (S.type, S.samples_per_pixel, S.strata) == (P.capi.PT_SAMPLER_STRATIFIED, kw["strata"] ** 2, kw["strata"])
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        rgb, st = sc.render(collect_counters=1)
+        ref, so = orc.render(threads=threads)
+        assert ref.mean() > 0 and np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5, kw
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested"):
+            assert st[k] == so[k], (kw, k, st[k], so[k])
+        assert st["camera_rays"] >= res * res * kw["strata"] ** 2
+
+
+def test_hostcheck_stratified_sampler(HC):
+    check_stratified(HC)
+
+
 def check_tree_random(P, res=33, spp=2, threads=2):
     """Sampler "random" under whitted / directlighting: the depth-first walk draws from the tile's PCG32 stream in the
     recursion's own order (same image, same counters as the oracle's recursion); strategy "all" reads the sample arrays
