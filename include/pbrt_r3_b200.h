@@ -58,7 +58,9 @@ enum pt_sampler_type {        /* reference src/samplers/create_sampler.rs:12-33 
   PT_SAMPLER_HALTON = 0,      /* samplers/halton.rs */
   PT_SAMPLER_SOBOL = 1,       /* samplers/sobol.rs  */
   PT_SAMPLER_RANDOM = 2,      /* samplers/random.rs */
-  PT_SAMPLER_STRATIFIED = 3   /* samplers/stratified.rs (xsamples = ysamples): per-pixel tables + the tile's RNG, like random */
+  PT_SAMPLER_STRATIFIED = 3,  /* samplers/stratified.rs (xsamples = ysamples): per-pixel tables + the tile's RNG, like random */
+  PT_SAMPLER_ZEROTWO = 4      /* samplers/zerotwosequence.rs ("02sequence" / "lowdiscrepancy"): scrambled (0,2)-sequence tables per pixel;
+                                 samples_per_pixel as requested (rounded up to a power of two by the callee), n_sampled_dimensions */
 };
 
 enum pt_accel_type {          /* reference src/accelerators/bvh/accel/mod.rs:4-10 */

@@ -72,6 +72,12 @@ struct Scene {
       if (desc->lights[i].type == PT_LIGHT_INFINITE) infinite_lights.push_back((int)i);
     if (desc->n_lights > 0) distrib.init(desc, world_bound, world_radius, envs.data());
     scfg = make_sampler_config(desc->sampler.type, desc->sampler.samples_per_pixel, desc->film.sample_bounds, desc->sampler.sample_at_pixel_center != 0);
+    if (desc->sampler.type == PT_SAMPLER_ZEROTWO) {  // ZeroTwoSequenceSampler::new (zerotwosequence.rs:13-26)
+      uint32_t p2 = 1;
+      while (p2 < (uint32_t)std::max(desc->sampler.samples_per_pixel, 1)) p2 *= 2;
+      scfg.spp = (int)p2;
+      scfg.strat_dims = desc->sampler.n_sampled_dimensions;
+    }
     if (desc->sampler.type == PT_SAMPLER_STRATIFIED) {  // create_stratified_sampler (stratified.rs:130-150)
       scfg.strat_n = desc->sampler.strata;
       scfg.strat_dims = desc->sampler.n_sampled_dimensions;

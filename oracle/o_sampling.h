@@ -242,6 +242,56 @@ struct Sampler {
   template <class T> void shuffle(T* v, size_t count) {  // shuffle_array with one dimension (sampling.rs:4-15)
     for (size_t i = 0; i < count; i++) { size_t other = i + rng.uniform_uint32((uint32_t)(count - i)); std::swap(v[i], v[other]); }
   }
+  // ---- ZeroTwoSequenceSampler (samplers/zerotwosequence.rs:30-63; core/lowdiscrepancy/van_der_corput.rs:59-145) ----
+  static const uint32_t* sobol_matrix(int which) {  // CVAN_DER_CORPUT = CSOBOL[0] = bit reversal; CSOBOL[1][i] = CSOBOL[1][i-1] ^ (CSOBOL[1][i-1] >> 1)
+    static uint32_t m[2][32];
+    static bool ready = false;
+    if (!ready) {
+      for (int i = 0; i < 32; i++) m[0][i] = 1u << (31 - i);
+      m[1][0] = 1u << 31;
+      for (int i = 1; i < 32; i++) m[1][i] = m[1][i - 1] ^ (m[1][i - 1] >> 1);
+      ready = true;
+    }
+    return m[which];
+  }
+  static Float u32_to_unit(uint32_t v) { return std::min((Float)v * 2.3283064365386963e-10f, ONE_MINUS_EPSILON); }
+  template <class T> void shuffle_blocks(T* v, size_t count, size_t dim) {  // shuffle_array (sampling.rs:4-15)
+    for (size_t i = 0; i < count; i++) {
+      size_t other = i + rng.uniform_uint32((uint32_t)(count - i));
+      for (size_t j = 0; j < dim; j++) std::swap(v[dim * i + j], v[dim * other + j]);
+    }
+  }
+  void van_der_corput(size_t n_per, size_t n_pixel, Float* out) {  // van_der_corput.rs:94-115
+    uint32_t v = rng.uniform_uint32();
+    const uint32_t* c = sobol_matrix(0);
+    for (size_t i = 0; i < n_per * n_pixel; i++) { out[i] = u32_to_unit(v); v ^= c[__builtin_ctz((uint32_t)(i + 1))]; }
+    for (size_t i = 0; i < n_pixel; i++) shuffle_blocks(out + i * n_per, n_per, 1);
+    shuffle_blocks(out, n_pixel, n_per);
+  }
+  void sobol_2d(size_t n_per, size_t n_pixel, Vec2* out) {  // van_der_corput.rs:118-145
+    uint32_t v0 = rng.uniform_uint32();
+    uint32_t v1 = rng.uniform_uint32();
+    const uint32_t *c0 = sobol_matrix(0), *c1 = sobol_matrix(1);
+    for (size_t i = 0; i < n_per * n_pixel; i++) {
+      out[i] = Vec2(u32_to_unit(v0), u32_to_unit(v1));
+      int z = __builtin_ctz((uint32_t)(i + 1));
+      v0 ^= c0[z]; v1 ^= c1[z];
+    }
+    for (size_t i = 0; i < n_pixel; i++) shuffle_blocks(out + i * n_per, n_per, 1);
+    shuffle_blocks(out, n_pixel, n_per);
+  }
+  void zerotwo_start_pixel() {
+    const size_t spp = (size_t)cfg->spp;
+    samples1d.assign((size_t)cfg->strat_dims, std::vector<Float>(spp));
+    samples2d.assign((size_t)cfg->strat_dims, std::vector<Vec2>(spp));
+    for (auto& t : samples1d) van_der_corput(1, spp, t.data());
+    for (auto& t : samples2d) sobol_2d(1, spp, t.data());
+    random_arrays.resize(cfg->array_sizes_2d.size());
+    for (size_t a = 0; a < random_arrays.size(); a++) {
+      random_arrays[a].assign((size_t)cfg->array_sizes_2d[a] * spp, Vec2(0, 0));
+      sobol_2d(cfg->array_sizes_2d[a], spp, random_arrays[a].data());
+    }
+  }
   void stratified_start_pixel() {  // stratified.rs:33-88
     const size_t spp = (size_t)cfg->spp;
     samples1d.assign((size_t)cfg->strat_dims, std::vector<Float>(spp));
@@ -289,6 +339,7 @@ struct Sampler {
     px = x; py = y; sample_num = 0; dimension = 0; array2d_offset = 0;
     current1d = current2d = 0;
     if (cfg->type == 3) { stratified_start_pixel(); return; }
+    if (cfg->type == 4) { zerotwo_start_pixel(); return; }
     if (cfg->type == 2 && !cfg->array_sizes_2d.empty()) {  // random.rs:46-60: every element of every array, in order, before the first sample
       random_arrays.resize(cfg->array_sizes_2d.size());
       for (size_t a = 0; a < random_arrays.size(); a++) {
@@ -361,7 +412,7 @@ struct Sampler {
     return Vec2(sample_dimension(index, dim), sample_dimension(index, dim + 1));
   }
   Float get_1d() {
-    if (cfg->type == 3) {  // BasePixelSampler::get_1d (pixel_sampler.rs:53-64)
+    if (cfg->type >= 3) {  // BasePixelSampler::get_1d (pixel_sampler.rs:53-64)
       if (current1d < samples1d.size()) return samples1d[current1d++][(size_t)sample_num];
       return rng.uniform_float();
     }
@@ -372,7 +423,7 @@ struct Sampler {
     return x;
   }
   Vec2 get_2d() {
-    if (cfg->type == 3 && current2d < samples2d.size()) return samples2d[current2d++][(size_t)sample_num];  // pixel_sampler.rs:66-77
+    if (cfg->type >= 3 && current2d < samples2d.size()) return samples2d[current2d++][(size_t)sample_num];  // pixel_sampler.rs:66-77
     if (cfg->type >= 2) { Float a = rng.uniform_float(); Float b = rng.uniform_float(); return Vec2(a, b); }
     if (dimension + 1u >= 5u && dimension < array_end_dim()) dimension = array_end_dim();
     Float x = sample_dimension(interval_index, dimension);

@@ -14,7 +14,7 @@ PT_ABI_VERSION = 3
 PT_MAT_NONE, PT_MAT_MATTE, PT_MAT_PLASTIC, PT_MAT_GLASS, PT_MAT_METAL, PT_MAT_MIRROR = -1, 0, 1, 2, 3, 4
 PT_MAT_UBER, PT_MAT_SUBSTRATE, PT_MAT_TRANSLUCENT, PT_MAT_MIX = 5, 6, 7, 8
 PT_LIGHT_AREA, PT_LIGHT_POINT, PT_LIGHT_DISTANT, PT_LIGHT_SPOT, PT_LIGHT_INFINITE, PT_LIGHT_PROJECTION, PT_LIGHT_GONIOMETRIC = 0, 1, 2, 3, 4, 5, 6
-PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM, PT_SAMPLER_STRATIFIED = 0, 1, 2, 3
+PT_SAMPLER_HALTON, PT_SAMPLER_SOBOL, PT_SAMPLER_RANDOM, PT_SAMPLER_STRATIFIED, PT_SAMPLER_ZEROTWO = 0, 1, 2, 3, 4
 PT_ACCEL_QBVH, PT_ACCEL_LBVH = 0, 1
 PT_SPLIT_SAH, PT_SPLIT_HLBVH, PT_SPLIT_MIDDLE, PT_SPLIT_EQUAL = 0, 1, 2, 3
 PT_CAMERA_PERSPECTIVE, PT_CAMERA_ORTHOGRAPHIC, PT_CAMERA_ENVIRONMENT = 0, 1, 2

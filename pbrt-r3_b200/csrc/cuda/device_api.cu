@@ -601,9 +601,10 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
       for (uint32_t i = 0; i < D->n_lights; i++) elems += 2ull * (uint64_t)std::max(D->lights[i].n_samples, 1);
       elems *= (uint64_t)std::max(D->integrator.max_depth, 0);
     }
-    elems *= 2ull * (uint64_t)std::max(D->sampler.samples_per_pixel, 0);
-    if (D->sampler.type == PT_SAMPLER_STRATIFIED) {
-      H.tile_tab = 3u * (uint32_t)std::max(D->sampler.n_sampled_dimensions, 0) * (uint32_t)std::max(D->sampler.samples_per_pixel, 0);
+    const uint64_t spp_eff = D->sampler.type == PT_SAMPLER_ZEROTWO ? round_up_pow2((uint32_t)std::max(D->sampler.samples_per_pixel, 1)) : (uint64_t)std::max(D->sampler.samples_per_pixel, 0);
+    elems *= 2ull * spp_eff;
+    if (D->sampler.type >= PT_SAMPLER_STRATIFIED) {
+      H.tile_tab = 3u * (uint32_t)std::max(D->sampler.n_sampled_dimensions, 0) * (uint32_t)spp_eff;
       elems += H.tile_tab;
     }
     if (elems > (1ull << 24)) { pt_set_error("Sampler \"random\": the integrator's sample arrays exceed 16M values per pixel"); return 1; }
@@ -620,6 +621,11 @@ int build_scene(pt_scene* s, const pt_scene_desc* D) {
   SD.at_center = D->sampler.sample_at_pixel_center;
   SD.nd = D->sampler.n_sampled_dimensions; SD.strata = D->sampler.strata; SD.jitter = D->sampler.jitter;
   SD.inc2d = 2u; SD.x2d = 0u; SD.y2d = 1u;
+  if (SD.type == PT_SAMPLER_ZEROTWO) {  // ZeroTwoSequenceSampler::new rounds up to a power of two (zerotwosequence.rs:13-21)
+    SD.spp = (int)round_up_pow2((uint32_t)std::max(SD.spp, 1));
+    if (SD.nd < 0 || SD.nd > 64) { pt_set_error("pt_sampler: 0 <= n_sampled_dimensions <= 64"); return 1; }
+    SD.inc2d = 0x10000u; SD.x2d = 0x4000u; SD.y2d = 0x8000u;
+  }
   if (SD.type == PT_SAMPLER_STRATIFIED) {
     if (SD.strata < 1 || SD.strata * SD.strata != SD.spp || SD.nd < 0 || SD.nd > 64) { pt_set_error("pt_sampler: stratified needs strata^2 = samples_per_pixel, 0 <= n_sampled_dimensions <= 64"); return 1; }
     SD.inc2d = 0x10000u; SD.x2d = 0x4000u; SD.y2d = 0x8000u;
@@ -1044,7 +1050,7 @@ int build_pixlist(pt_scene* s, int shard_index, int shard_count, int tile) {
     CK(s->pix_bufs->alloc(s->tiles_host.size() / 3, &s->h.tile_rng));
     s->h.tile_arrays = nullptr;
     if (s->h.tile_arr_stride) CK(s->pix_bufs->alloc(s->tiles_host.size() / 3 * (size_t)s->h.tile_arr_stride, &s->h.tile_arrays));
-    if (s->h.sampler.type == PT_SAMPLER_STRATIFIED) CK(s->pix_bufs->alloc(s->tiles_host.size() / 3, &s->h.tile_sample));
+    if (s->h.sampler.type >= PT_SAMPLER_STRATIFIED) CK(s->pix_bufs->alloc(s->tiles_host.size() / 3, &s->h.tile_sample));
   }
   s->pixlist = (int*)dp;
   s->pix_n = (uint32_t)px.size();

@@ -244,6 +244,59 @@ PT_HD void stratified_start_pixel(const DScene& S, uint32_t tile_slot, uint64_t 
     }
   }
 }
+// ZeroTwoSequenceSampler::start_pixel (zerotwosequence.rs:30-63; van_der_corput / sobol_2d, lowdiscrepancy/van_der_corput.rs:
+// 59-145): every table is a Gray-code walk of a randomly scrambled generator matrix, then shuffled within each pixel sample's
+// block and across the blocks.  Same layout and array bookkeeping as stratified_start_pixel.
+PT_HD void zerotwo_blocks_shuffle(const DScene& S, uint32_t tile_slot, uint64_t seq, float* t, uint32_t n, uint32_t spp, uint32_t width) {
+  // shuffle_array(&samples[i * n..], n, 1) for every pixel sample i, then shuffle_array(samples, spp, n) (sampling.rs:4-15);
+  // width = floats per element
+  for (uint32_t i = 0; i < spp; i++)
+    for (uint32_t j = 0; j < n; j++) {
+      uint32_t o = j + random_bounded(S, tile_slot, seq, n - j);
+      for (uint32_t w = 0; w < width; w++) { float* a = t + width * (i * n + j) + w; float* b = t + width * (i * n + o) + w; float v = *a; *a = *b; *b = v; }
+    }
+  for (uint32_t i = 0; i < spp; i++) {
+    uint32_t o = i + random_bounded(S, tile_slot, seq, spp - i);
+    for (uint32_t w = 0; w < width * n; w++) { float* a = t + width * n * i + w; float* b = t + width * n * o + w; float v = *a; *a = *b; *b = v; }
+  }
+}
+PT_HD void zerotwo_start_pixel(const DScene& S, uint32_t tile_slot, uint64_t seq, uint32_t n_arr, const uint32_t* arr_prefix, uint32_t arr_n0) {
+  const SamplerDev& c = S.sampler;
+  const uint32_t spp = (uint32_t)c.spp, nd = (uint32_t)c.nd;
+  float* t = S.tile_arrays + (size_t)tile_slot * S.tile_arr_stride;
+  uint32_t c1[32];  // second Sobol' generator matrix: c1[0] = 2^31, c1[i] = c1[i-1] ^ (c1[i-1] >> 1); the first is 2^31 >> i
+  c1[0] = 0x80000000u;
+  for (int i = 1; i < 32; i++) c1[i] = c1[i - 1] ^ (c1[i - 1] >> 1);
+  for (uint32_t d = 0; d < nd; d++, t += spp) {
+    uint32_t v = random_u32(S, tile_slot, seq);
+    for (uint32_t i = 0; i < spp; i++) { t[i] = fminf((float)v * 2.3283064365386963e-10f, PT_ONE_MINUS_EPS); v ^= 0x80000000u >> (ffs_(i + 1u) - 1); }
+    zerotwo_blocks_shuffle(S, tile_slot, seq, t, 1u, spp, 1u);
+  }
+  for (uint32_t d = 0; d < nd; d++, t += 2u * spp) {
+    uint32_t v0 = random_u32(S, tile_slot, seq), v1 = random_u32(S, tile_slot, seq);
+    for (uint32_t i = 0; i < spp; i++) {
+      t[2u * i] = fminf((float)v0 * 2.3283064365386963e-10f, PT_ONE_MINUS_EPS);
+      t[2u * i + 1u] = fminf((float)v1 * 2.3283064365386963e-10f, PT_ONE_MINUS_EPS);
+      const int z = ffs_(i + 1u) - 1;
+      v0 ^= 0x80000000u >> z; v1 ^= c1[z];
+    }
+    zerotwo_blocks_shuffle(S, tile_slot, seq, t, 1u, spp, 2u);
+  }
+  for (uint32_t a = 0; a < n_arr; a++) {
+    const uint32_t nl = arr_prefix ? (n_arr / 2u) / (uint32_t)S.integrator.max_depth : 0u;
+    const uint32_t j = arr_prefix ? (a / 2u) % nl : 0u;
+    const uint32_t na = arr_prefix ? arr_prefix[j + 1u] - arr_prefix[j] : arr_n0;
+    uint32_t v0 = random_u32(S, tile_slot, seq), v1 = random_u32(S, tile_slot, seq);
+    for (uint32_t i = 0; i < na * spp; i++) {
+      t[2u * i] = fminf((float)v0 * 2.3283064365386963e-10f, PT_ONE_MINUS_EPS);
+      t[2u * i + 1u] = fminf((float)v1 * 2.3283064365386963e-10f, PT_ONE_MINUS_EPS);
+      const int z = ffs_(i + 1u) - 1;
+      v0 ^= 0x80000000u >> z; v1 ^= c1[z];
+    }
+    zerotwo_blocks_shuffle(S, tile_slot, seq, t, na, spp, 2u);
+    t += 2u * na * spp;
+  }
+}
 // BasePixelSampler::get_1d / get_2d (pixel_sampler.rs:53-77): dim = requests so far (1D low half, 2D high half) + which value
 PT_HD float stratified_dim(const DScene& S, int64_t index, uint32_t dim) {
   const uint32_t tile = (uint32_t)((uint64_t)index >> 32), nd = (uint32_t)S.sampler.nd, spp = (uint32_t)S.sampler.spp;
@@ -260,7 +313,7 @@ PT_HD float stratified_dim(const DScene& S, int64_t index, uint32_t dim) {
 PT_HDN float sampler_dim(const DScene& S, int64_t index, uint32_t dim, int px, int py) {
   const SamplerDev& c = S.sampler;
   if (c.type == PT_SAMPLER_RANDOM) return random_draw(S, (uint32_t)((uint64_t)index >> 32), (uint64_t)(uint32_t)index);
-  if (c.type == PT_SAMPLER_STRATIFIED) return stratified_dim(S, index, dim);
+  if (c.type >= PT_SAMPLER_STRATIFIED) return stratified_dim(S, index, dim);
   if (c.type == PT_SAMPLER_HALTON) {  // halton.rs:149-162
     if (c.at_center && dim < 2) return 0.5f;
     if (dim == 0) return radical_inverse2((uint64_t)(index >> c.base_exponents[0]));

@@ -338,11 +338,12 @@ __global__ void k_raygen_random(const __grid_constant__ DScene S, WaveState W, Q
     uint32_t slot = (uint32_t)tr[0] + q - c0;
     int pk = pixlist[c0 + slot];
     int px = (pk & 0xffff) + S.sampler.sb[0], py = (pk >> 16) + S.sampler.sb[1];
-    if (S.sampler.type == PT_SAMPLER_STRATIFIED) {  // start_pixel: tables and Latin-hypercube arrays of the pixel; current_pixel_sample_index
+    if (S.sampler.type >= PT_SAMPLER_STRATIFIED) {  // start_pixel: tables and Latin-hypercube arrays of the pixel; current_pixel_sample_index
       if (sample == 0) {
         const bool all = S.integrator.type == PT_INTEGRATOR_DIRECT && S.integrator.direct_strategy == PT_DIRECT_ALL;
         const uint32_t n_arr = S.integrator.type == PT_INTEGRATOR_AO ? 1u : (all ? 2u * S.n_lights * (uint32_t)S.integrator.max_depth : 0u);
-        stratified_start_pixel(S, tile0 + t, (uint32_t)tr[2], n_arr, all ? S.light_sample_prefix : nullptr, (uint32_t)S.integrator.ao_samples);
+        if (S.sampler.type == PT_SAMPLER_STRATIFIED) stratified_start_pixel(S, tile0 + t, (uint32_t)tr[2], n_arr, all ? S.light_sample_prefix : nullptr, (uint32_t)S.integrator.ao_samples);
+        else zerotwo_start_pixel(S, tile0 + t, (uint32_t)tr[2], n_arr, all ? S.light_sample_prefix : nullptr, (uint32_t)S.integrator.ao_samples);
       }
       S.tile_sample[tile0 + t] = (uint32_t)sample;
     } else if (sample == 0 && S.tile_arr_stride) {  // start_pixel: the pixel's sample arrays come first in the tile's stream

@@ -1156,10 +1156,16 @@ struct Builder {
       S.strata = xs;
       S.samples_per_pixel = xs * ys;
     }
-    else throw ParseError("Sampler \"" + sampler_name + "\" is not supported on the GPU path (halton, sobol, random, stratified)");
+    else if (sampler_name == "02sequence" || sampler_name == "lowdiscrepancy") {  // create_zerotwosequence_sampler (zerotwosequence.rs:107-125)
+      S.type = PT_SAMPLER_ZEROTWO;
+      S.samples_per_pixel = sampler_params.one_int("pixelsamples", 16);
+      S.n_sampled_dimensions = sampler_params.one_int("dimensions", 4);
+      if (S.n_sampled_dimensions < 0 || S.n_sampled_dimensions > 64) throw ParseError("Sampler \"02sequence\": dimensions out of range (0..64)");
+    }
+    else throw ParseError("Sampler \"" + sampler_name + "\" is not supported on the GPU path (halton, sobol, random, stratified, 02sequence)");
     S.sample_at_pixel_center = sampler_params.one_bool("samplepixelcenter", false) ? 1 : 0;
     if (pixelsamples_override > 0 && S.type != PT_SAMPLER_STRATIFIED) S.samples_per_pixel = pixelsamples_override;  // pbrt.rs:234-238 (replace_params_int before the factory runs)
-    if (pt_current_options().quick_render && S.type < PT_SAMPLER_RANDOM) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
+    if (pt_current_options().quick_render && (S.type < PT_SAMPLER_RANDOM || S.type == PT_SAMPLER_ZEROTWO)) S.samples_per_pixel = 1;  // halton.rs:288-290, sobol.rs:199-201
 
     // Integrator (integrators/path.rs:252-271)
     if (integrator_name != "path" && integrator_name != "aov" && integrator_name != "ambientocclusion" && integrator_name != "directlighting" && integrator_name != "whitted")

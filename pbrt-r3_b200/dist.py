@@ -16,7 +16,7 @@ def effective_spp(sampler_type, spp):
     """Samples per pixel the sampler really takes: SobolSampler rounds the request up to a power of two
     (samplers/sobol.rs:24), as pt_scene_create does on the device."""
     spp = max(int(spp), 1)
-    if int(sampler_type) == 1:   # PT_SAMPLER_SOBOL
+    if int(sampler_type) in (1, 4):   # PT_SAMPLER_SOBOL, PT_SAMPLER_ZEROTWO
         return 1 << (spp - 1).bit_length()
     return spp
 

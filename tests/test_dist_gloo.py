@@ -62,6 +62,7 @@ def test_shard_opts_by_sampler():
     assert D.shard_opts(1, 64, 3, 4) == {"spp_begin": 48, "spp_end": 64}
     assert D.shard_opts(2, 64, 1, 4) == {"shard_index": 1, "shard_count": 4}
     assert D.shard_opts(3, 16, 2, 4) == {"shard_index": 2, "shard_count": 4}      # stratified: per-tile streams too
+    assert D.shard_opts(4, 6, 0, 2) == {"shard_index": 0, "shard_count": 2} and D.effective_spp(4, 6) == 8   # 02sequence: tiles; spp rounds up
     # Sobol takes the next power of two (sobol.rs:24): 6 requested = 8 rendered, and all 8 are sharded
     assert D.effective_spp(1, 6) == 8 and D.effective_spp(0, 6) == 6
     assert [D.shard_opts(1, 6, r, 2) for r in range(2)] == [{"spp_begin": 0, "spp_end": 4}, {"spp_begin": 4, "spp_end": 8}]

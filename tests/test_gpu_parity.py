@@ -254,6 +254,13 @@ def test_stratified_sampler(P):
     check_stratified(P, res=72, threads=0)
 
 
+def test_zerotwo_sampler(P):
+    """Sampler "02sequence" / "lowdiscrepancy": scrambled (0,2)-sequence tables and sample arrays drawn on the device in the
+    reference's order: image and counters equal to the oracle's."""
+    from test_hostcheck import check_zerotwo
+    check_zerotwo(P, res=72, threads=0)
+
+
 def test_map_lights(P, tmp_path):
     """LightSource "projection" / "goniometric": per-sample radiance against the oracle (acos / atan2 are CUDA's: 99.5 % of the
     samples within 1e-4), equal counters, image."""

@@ -228,6 +228,10 @@ def test_front_end_stratified_sampler(P):
     assert (S.type, S.samples_per_pixel, S.strata, S.jitter, S.n_sampled_dimensions) == (P.capi.PT_SAMPLER_STRATIFIED, 16, 4, 1, 4)
     S = P.HostScene.parse_string(base % 'Sampler "stratified" "integer xsamples" [3] "integer ysamples" [3] "bool jitter" ["false"] "integer dimensions" [7]').desc.sampler
     assert (S.samples_per_pixel, S.strata, S.jitter, S.n_sampled_dimensions) == (9, 3, 0, 7)
+    Z = P.HostScene.parse_string(base % 'Sampler "02sequence"').desc.sampler                      # zerotwosequence.rs:107-125
+    assert (Z.type, Z.samples_per_pixel, Z.n_sampled_dimensions) == (P.capi.PT_SAMPLER_ZEROTWO, 16, 4)
+    Z = P.HostScene.parse_string(base % 'Sampler "lowdiscrepancy" "integer pixelsamples" [6] "integer dimensions" [2]').desc.sampler
+    assert (Z.type, Z.samples_per_pixel, Z.n_sampled_dimensions) == (P.capi.PT_SAMPLER_ZEROTWO, 6, 2)   # rounded up to 8 by the sampler itself
     with pytest.raises(P.PbrtError):       # the reference's 2D stratification loops x over ysamples: only the square case is reproduced
         P.HostScene.parse_string(base % 'Sampler "stratified" "integer xsamples" [2] "integer ysamples" [3]')
     lib = P.capi.load()

